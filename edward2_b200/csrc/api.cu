@@ -1,0 +1,422 @@
+// extern "C" entry points of libed2b200.so (declared in include/ed2b200.h).  Each layer-level call composes
+// the tcgen05 GEMM with the bandwidth-bound kernels on the caller's stream; nothing here synchronises.
+#include "../../include/ed2b200.h"
+
+#include <cuda_runtime.h>
+
+#include "gemm.h"
+#include "kernels.h"
+#include "status.h"
+
+using namespace ed2;
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline Noise N(const ed2_noise& n) { return Noise{n.injected, n.seed, n.stream}; }
+
+#define ED2_TRY(expr)            \
+  do {                           \
+    int _st = (expr);            \
+    if (_st != ED2_OK) return _st; \
+  } while (0)
+
+EpiParams epi_default() {
+  EpiParams e{};
+  e.alpha = 1.f;
+  e.beta = 1.f;
+  e.act_scale = 1.f;
+  return e;
+}
+
+int check_dt(int dt) {
+  if (dt != kF32 && dt != kBF16) return set_error(ED2_ERR_BAD_DTYPE, "dtype must be ED2_F32 or ED2_BF16, got %d", dt);
+  return ED2_OK;
+}
+
+// y[B][O] = epilogue( x[B][I] · w[I][O] )        (A K-major, B MN-major)
+int gemm_xw(int dt, const void* x, int x_ld, const void* w, int w_ld, int B, int I, int O, const EpiParams& ep,
+            cudaStream_t s) {
+  GemmDesc g{};
+  g.A = x; g.lda = x_ld; g.major_a = kMajorK;
+  g.B = w; g.ldb = w_ld; g.major_b = kMajorMN;
+  g.M = B; g.N = O; g.K = I;
+  g.ep = ep;
+  return gemm(dt, g, s);
+}
+// dx[B][I] = epilogue( g[B][O] · wᵀ )            (A K-major; B K-major: w[I][O] is [N=I][K=O])
+int gemm_gwt(int dt, const void* gz, int g_ld, const void* w, int w_ld, int B, int I, int O, const EpiParams& ep,
+             cudaStream_t s) {
+  GemmDesc g{};
+  g.A = gz; g.lda = g_ld; g.major_a = kMajorK;
+  g.B = w; g.ldb = w_ld; g.major_b = kMajorK;
+  g.M = B; g.N = I; g.K = O;
+  g.ep = ep;
+  return gemm(dt, g, s);
+}
+// dw[I][O] = epilogue( xᵀ[I][B] · g[B][O] )      (A MN-major, B MN-major)
+int gemm_xtg(int dt, const void* x, int x_ld, const void* gz, int g_ld, int B, int I, int O, const EpiParams& ep,
+             cudaStream_t s) {
+  GemmDesc g{};
+  g.A = x; g.lda = x_ld; g.major_a = kMajorMN;
+  g.B = gz; g.ldb = g_ld; g.major_b = kMajorMN;
+  g.M = I; g.N = O; g.K = B;
+  g.ep = ep;
+  return gemm(dt, g, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ed2_version(void) { return "ed2b200 0.1.0 (sm_100a)"; }
+const char* ed2_last_error(void) { return last_error(); }
+long long ed2_launch_count(void) { return launch_count(); }
+
+int ed2_check_device(int dev) {
+  cudaDeviceProp p;
+  cudaError_t e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (p.major != 10) return set_error(ED2_ERR_UNSUPPORTED_ARCH, "device %d is sm_%d%d; this library is sm_100a only", dev, p.major, p.minor);
+  return ED2_OK;
+}
+
+int ed2_gemm(const ed2_gemm_desc* d, void* stream) {
+  if (d == nullptr) return set_error(ED2_ERR_BAD_ARG, "null desc");
+  ED2_TRY(check_dt(d->dtype));
+  GemmDesc g{};
+  g.A = d->a; g.lda = d->lda; g.major_a = d->major_a;
+  g.B = d->b; g.ldb = d->ldb; g.major_b = d->major_b;
+  g.M = d->m; g.N = d->n; g.K = d->k;
+  EpiParams& e = g.ep;
+  e = epi_default();
+  e.alpha = d->alpha; e.beta = d->beta; e.act_scale = d->act_scale; e.act = d->act; e.group_rows = d->group_rows;
+  e.elem_scale = d->elem_scale; e.elem_scale_ld = d->elem_scale_ld; e.elem_scale_dt = d->elem_scale_dtype;
+  e.col_scale = d->col_scale; e.col_scale_ld = d->col_scale_ld;
+  e.addend = d->addend; e.addend_ld = d->addend_ld; e.addend_dt = d->addend_dtype;
+  e.col_bias = d->col_bias; e.col_bias_ld = d->col_bias_ld;
+  e.out = d->out; e.out_ld = d->out_ld; e.out_dt = d->out_dtype;
+  e.raw = d->raw; e.raw_ld = d->raw_ld; e.raw_dt = d->raw_dtype;
+  e.row_sum = d->row_sum;
+  g.block_n = d->block_n; g.cta_group = d->cta_group; g.max_ctas = d->max_ctas; g.no_tma_store = d->no_tma_store;
+  return gemm(d->dtype, g, S(stream));
+}
+
+int ed2_philox_normal(float* out, long long n, uint64_t seed, uint64_t stream, void* s) { return k_philox_fill(0, out, n, seed, stream, S(s)); }
+int ed2_philox_uniform(float* out, long long n, uint64_t seed, uint64_t stream, void* s) { return k_philox_fill(1, out, n, seed, stream, S(s)); }
+int ed2_philox_sign(float* out, long long n, uint64_t seed, uint64_t stream, void* s) { return k_philox_fill(2, out, n, seed, stream, S(s)); }
+int ed2_philox_raw(uint32_t* out, long long nb, uint64_t seed, uint64_t stream, void* s) { return k_philox_raw(out, nb, seed, stream, S(s)); }
+
+int ed2_cast(const void* src, int sdt, int sld, void* dst, int ddt, int dld, long long rows, long long cols, void* s) {
+  ED2_TRY(check_dt(sdt));
+  ED2_TRY(check_dt(ddt));
+  return k_cast2d(src, sdt, sld, dst, ddt, dld, rows, cols, S(s));
+}
+
+int ed2_sample_normal_weights(const float* mu, const float* rho, ed2_noise eps, long long rows, long long cols, int mode,
+                              void* w, int w_dtype, int w_ld, void* mean_out, int mean_ld, double* kl_out,
+                              float kl_scale, float prior_mean, float prior_std, void* s) {
+  ED2_TRY(check_dt(w_dtype));
+  return k_sample_weights(mu, rho, N(eps), rows, cols, mode, w, w_dtype, w_ld, mean_out, mean_ld, kl_out, kl_scale,
+                          Prior{prior_mean, prior_std}, S(s));
+}
+
+int ed2_normal_kl_fwd(const float* mu, const float* rho, long long n, float pm, float ps, float scale, double* out, void* s) {
+  return k_normal_kl_fwd(mu, rho, n, Prior{pm, ps}, scale, out, S(s));
+}
+int ed2_normal_kl_bwd(const float* mu, const float* rho, long long n, float pm, float ps, float scale,
+                      const float* upstream, float* dmu, float* drho, void* s) {
+  return k_normal_kl_bwd(mu, rho, n, Prior{pm, ps}, scale, upstream, dmu, drho, S(s));
+}
+
+// ------------------------------------------------------------------------------------------ BatchEnsemble
+int ed2_be_dense_fwd(const ed2_be_fwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  if (a->ensemble_size <= 0 || a->batch % a->ensemble_size != 0)
+    return set_error(ED2_ERR_BAD_SHAPE, "batch %d is not divisible by ensemble_size %d", a->batch, a->ensemble_size);
+  cudaStream_t s = S(stream);
+  const int rpm = a->batch / a->ensemble_size;
+  ED2_TRY(k_scale_rows(a->x, a->dtype, a->x_ld, a->batch, a->in_dim, rpm, 0, a->alpha, nullptr, Noise{}, a->xa,
+                       a->xa_ld, nullptr, 0, s));
+  EpiParams e = epi_default();
+  e.group_rows = rpm;
+  e.col_scale = a->gamma; e.col_scale_ld = a->out_dim;
+  e.col_bias = a->bias; e.col_bias_ld = a->out_dim;
+  e.act = a->act;
+  e.out = a->y; e.out_ld = a->y_ld; e.out_dt = a->dtype;
+  e.raw = a->z; e.raw_ld = a->z_ld; e.raw_dt = a->dtype;
+  return gemm_xw(a->dtype, a->xa, a->xa_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e, s);
+}
+
+int ed2_be_dense_bwd(const ed2_be_bwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  cudaStream_t s = S(stream);
+  const int rpm = a->batch / a->ensemble_size;
+  BwdOutArgs o{};
+  o.dt = a->dtype; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = rpm; o.act = a->act; o.fast = 1;
+  o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld; o.z = a->z; o.z_ld = a->z_ld;
+  o.gamma = a->gamma;
+  o.dz = a->dz; o.dz_ld = a->dz_ld;
+  o.d_fast_mu = a->dgamma; o.dbias = a->dbias;
+  ED2_TRY(k_bwd_out(o, s));
+  EpiParams e = epi_default();
+  e.out = a->dw; e.out_ld = a->out_dim; e.out_dt = kF32;
+  ED2_TRY(gemm_xtg(a->dtype, a->xa, a->xa_ld, a->dz, a->dz_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  EpiParams e2 = epi_default();
+  e2.out = a->dxa; e2.out_ld = a->dxa_ld; e2.out_dt = a->dtype;
+  ED2_TRY(gemm_gwt(a->dtype, a->dz, a->dz_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s));
+  BwdInArgs i{};
+  i.dt = a->dtype; i.rows = a->batch; i.cols = a->in_dim; i.rows_per_member = rpm; i.fast = 1;
+  i.dxf = a->dxa; i.dxf_ld = a->dxa_ld; i.x = a->x; i.x_ld = a->x_ld;
+  i.fw_mu = a->alpha;
+  i.dx = a->dx; i.dx_ld = a->dx_ld;
+  i.d_fast_mu = a->dalpha;
+  return k_bwd_in(i, s);
+}
+
+// ------------------------------------------------------------------------------------------ Rank-1
+int ed2_rank1_dense_fwd(const ed2_rank1_fwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  if (a->ensemble_size <= 0 || a->batch % a->ensemble_size != 0)
+    return set_error(ED2_ERR_BAD_SHAPE, "batch %d is not divisible by ensemble_size %d", a->batch, a->ensemble_size);
+  cudaStream_t s = S(stream);
+  const int rpm = a->batch / a->ensemble_size;
+  ED2_TRY(k_scale_rows(a->x, a->dtype, a->x_ld, a->batch, a->in_dim, rpm, 1, a->mu_r, a->rho_r, N(a->eps_r), a->xr,
+                       a->xr_ld, nullptr, 0, s));
+  ED2_TRY(k_scale_rows(nullptr, a->dtype, 0, a->batch, a->out_dim, rpm, 1, a->mu_s, a->rho_s, N(a->eps_s), nullptr, 0,
+                       a->s_buf, a->s_ld, s));
+  EpiParams e = epi_default();
+  e.group_rows = rpm;
+  e.elem_scale = a->s_buf; e.elem_scale_ld = a->s_ld; e.elem_scale_dt = a->dtype;
+  e.col_bias = a->bias; e.col_bias_ld = a->out_dim;
+  e.act = a->act;
+  e.out = a->y; e.out_ld = a->y_ld; e.out_dt = a->dtype;
+  e.raw = a->z; e.raw_ld = a->z_ld; e.raw_dt = a->dtype;
+  return gemm_xw(a->dtype, a->xr, a->xr_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e, s);
+}
+
+int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  cudaStream_t s = S(stream);
+  const int rpm = a->batch / a->ensemble_size;
+  BwdOutArgs o{};
+  o.dt = a->dtype; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = rpm; o.act = a->act; o.fast = 2;
+  o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld; o.z = a->z; o.z_ld = a->z_ld;
+  o.s_buf = a->s_buf; o.s_ld = a->s_ld;
+  o.mu_s = a->mu_s; o.rho_s = a->rho_s; o.eps_s = N(a->eps_s);
+  o.dz = a->dz; o.dz_ld = a->dz_ld;
+  o.d_fast_mu = a->dmu_s; o.d_fast_rho = a->rho_s ? a->drho_s : nullptr; o.dbias = a->dbias;
+  ED2_TRY(k_bwd_out(o, s));
+  EpiParams e = epi_default();
+  e.out = a->dw; e.out_ld = a->out_dim; e.out_dt = kF32;
+  ED2_TRY(gemm_xtg(a->dtype, a->xr, a->xr_ld, a->dz, a->dz_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  EpiParams e2 = epi_default();
+  e2.out = a->dxr; e2.out_ld = a->dxr_ld; e2.out_dt = a->dtype;
+  ED2_TRY(gemm_gwt(a->dtype, a->dz, a->dz_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s));
+  BwdInArgs i{};
+  i.dt = a->dtype; i.rows = a->batch; i.cols = a->in_dim; i.rows_per_member = rpm; i.fast = 2;
+  i.dxf = a->dxr; i.dxf_ld = a->dxr_ld; i.x = a->x; i.x_ld = a->x_ld;
+  i.fw_mu = a->mu_r; i.fw_rho = a->rho_r; i.eps = N(a->eps_r);
+  i.dx = a->dx; i.dx_ld = a->dx_ld;
+  i.d_fast_mu = a->dmu_r; i.d_fast_rho = a->rho_r ? a->drho_r : nullptr;
+  return k_bwd_in(i, s);
+}
+
+// ------------------------------------------------------------------------------------------ Reparameterization
+int ed2_reparam_dense_fwd(const ed2_reparam_fwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  cudaStream_t s = S(stream);
+  ED2_TRY(k_sample_weights(a->mu, a->rho, N(a->eps), a->in_dim, a->out_dim, 0, a->w_lp, a->dtype, a->w_ld, nullptr, 0,
+                           a->kl_out, a->kl_scale, Prior{a->prior_mean, a->prior_std}, s));
+  EpiParams e = epi_default();
+  e.col_bias = a->bias; e.col_bias_ld = a->out_dim;
+  e.act = a->act;
+  e.out = a->y; e.out_ld = a->y_ld; e.out_dt = a->dtype;
+  return gemm_xw(a->dtype, a->x, a->x_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e, s);
+}
+
+int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  cudaStream_t s = S(stream);
+  BwdOutArgs o{};
+  o.dt = a->dtype; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = a->batch; o.act = a->act; o.fast = 0;
+  o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld;
+  o.dz = a->gp; o.dz_ld = a->gp_ld;
+  o.dbias = a->dbias;
+  ED2_TRY(k_bwd_out(o, s));
+  // dW = xᵀ gp lands in dmu; the finishing pass turns it into (dmu, drho) in place.
+  EpiParams e = epi_default();
+  e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
+  ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, a->gp, a->gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  ED2_TRY(k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
+                               a->kl_grad_scale, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho, s));
+  if (a->dx != nullptr) {
+    EpiParams e2 = epi_default();
+    e2.out = a->dx; e2.out_ld = a->dx_ld; e2.out_dt = a->dtype;
+    ED2_TRY(gemm_gwt(a->dtype, a->gp, a->gp_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s));
+  }
+  return ED2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ Flipout
+int ed2_flipout_dense_fwd(const ed2_flipout_fwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  cudaStream_t s = S(stream);
+  ED2_TRY(k_sample_weights(a->mu, a->rho, N(a->eps), a->in_dim, a->out_dim, 1, a->delta_lp, a->dtype, a->delta_ld,
+                           a->mu_lp, a->mu_ld, a->kl_out, a->kl_scale, Prior{a->prior_mean, a->prior_std}, s));
+  ED2_TRY(k_scale_rows(a->x, a->dtype, a->x_ld, a->batch, a->in_dim, a->batch, 2, nullptr, nullptr, N(a->sign_in),
+                       a->xs, a->xs_ld, nullptr, 0, s));
+  // pert = ((x∘S) Δ) ∘ T : T either injected fp32 (used directly) or materialised from Philox into `y` (dtype,
+  // ±1 is exact in bf16) — y is overwritten by the second GEMM afterwards.
+  EpiParams e = epi_default();
+  if (a->sign_out.injected != nullptr) {
+    e.elem_scale = a->sign_out.injected; e.elem_scale_ld = a->out_dim; e.elem_scale_dt = kF32;
+  } else {
+    ED2_TRY(k_fill_noise(1, N(a->sign_out), a->y, a->dtype, a->y_ld, a->batch, a->out_dim, s));
+    e.elem_scale = a->y; e.elem_scale_ld = a->y_ld; e.elem_scale_dt = a->dtype;
+  }
+  e.out = a->pert; e.out_ld = a->pert_ld; e.out_dt = kF32;
+  ED2_TRY(gemm_xw(a->dtype, a->xs, a->xs_ld, a->delta_lp, a->delta_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  EpiParams e2 = epi_default();
+  e2.addend = a->pert; e2.addend_ld = a->pert_ld; e2.addend_dt = kF32;
+  e2.col_bias = a->bias; e2.col_bias_ld = a->out_dim;
+  e2.act = a->act;
+  e2.out = a->y; e2.out_ld = a->y_ld; e2.out_dt = a->dtype;
+  return gemm_xw(a->dtype, a->x, a->x_ld, a->mu_lp, a->mu_ld, a->batch, a->in_dim, a->out_dim, e2, s);
+}
+
+int ed2_flipout_dense_bwd(const ed2_flipout_bwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  cudaStream_t s = S(stream);
+  BwdOutArgs o{};
+  o.dt = a->dtype; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = a->batch; o.act = a->act; o.fast = 3;
+  o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld;
+  o.sign_out = N(a->sign_out);
+  o.dz = a->gp; o.dz_ld = a->gp_ld; o.dz2 = a->gt; o.dz2_ld = a->gt_ld;
+  o.dbias = a->dbias;
+  ED2_TRY(k_bwd_out(o, s));
+  // dmu_w = xᵀ gp -> dmu ; dΔ = (x∘S)ᵀ (gp∘T) -> drho ; finishing pass combines with eps, sigmoid(rho), KL.
+  EpiParams e = epi_default();
+  e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
+  ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, a->gp, a->gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  EpiParams e1 = epi_default();
+  e1.out = a->drho; e1.out_ld = a->out_dim; e1.out_dt = kF32;
+  ED2_TRY(gemm_xtg(a->dtype, a->xs, a->xs_ld, a->gt, a->gt_ld, a->batch, a->in_dim, a->out_dim, e1, s));
+  ED2_TRY(k_normal_grad_finish(a->dmu, a->drho, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
+                               a->kl_grad_scale, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho, s));
+  if (a->dx != nullptr) {
+    // tmp = ((gp∘T) Δᵀ) ∘ S ;  dx = gp μᵀ + tmp
+    EpiParams e2 = epi_default();
+    const void* sign_in_buf = a->sign_in.injected;
+    int sign_dt = kF32, sign_ld = a->in_dim;
+    if (sign_in_buf == nullptr) {
+      // materialise S into dx (dtype), consumed as elem_scale before dx is overwritten by the last GEMM
+      ED2_TRY(k_fill_noise(1, N(a->sign_in), a->dx, a->dtype, a->dx_ld, a->batch, a->in_dim, s));
+      sign_in_buf = a->dx; sign_dt = a->dtype; sign_ld = a->dx_ld;
+    }
+    e2.elem_scale = sign_in_buf; e2.elem_scale_ld = sign_ld; e2.elem_scale_dt = sign_dt;
+    e2.out = a->tmp; e2.out_ld = a->tmp_ld; e2.out_dt = kF32;
+    ED2_TRY(gemm_gwt(a->dtype, a->gt, a->gt_ld, a->delta_lp, a->delta_ld, a->batch, a->in_dim, a->out_dim, e2, s));
+    EpiParams e3 = epi_default();
+    e3.addend = a->tmp; e3.addend_ld = a->tmp_ld; e3.addend_dt = kF32;
+    e3.out = a->dx; e3.out_ld = a->dx_ld; e3.out_dt = a->dtype;
+    ED2_TRY(gemm_gwt(a->dtype, a->gp, a->gp_ld, a->mu_lp, a->mu_ld, a->batch, a->in_dim, a->out_dim, e3, s));
+  }
+  return ED2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ SNGP head
+int ed2_spectral_norm_update(const float* w, int in_dim, int out_dim, float* u, float* v, int iterations,
+                             float norm_multiplier, int mode, int update_uv, float* w_out, void* w_out_lp, int w_lp_ld,
+                             float* sigma_out, float* workspace, void* stream) {
+  if (in_dim <= 0 || out_dim <= 0) return set_error(ED2_ERR_BAD_SHAPE, "spectral_norm: empty kernel");
+  return k_spectral_norm(w, in_dim, out_dim, u, v, iterations, norm_multiplier, mode, update_uv, w_out, w_out_lp,
+                         w_lp_ld, sigma_out, workspace, S(stream));
+}
+
+int ed2_input_normalize(const void* x, int x_dtype, int x_ld, void* y, int y_dtype, int y_ld, long long rows, int cols,
+                        const float* gamma, const float* beta, float eps, int scale_only, float scale, void* stream) {
+  ED2_TRY(check_dt(x_dtype));
+  ED2_TRY(check_dt(y_dtype));
+  return k_input_normalize(x, x_dtype, x_ld, y, y_dtype, y_ld, rows, cols, gamma, beta, eps, scale_only, scale, S(stream));
+}
+
+int ed2_rff_fwd(int dtype, const void* x, int x_ld, const void* wt, int wt_ld, const float* bias, float scale, int batch,
+                int in_dim, int num_features, void* phi, int phi_ld, int phi_dtype, float* pre, int pre_ld, void* stream) {
+  ED2_TRY(check_dt(dtype));
+  GemmDesc g{};
+  g.A = x; g.lda = x_ld; g.major_a = kMajorK;
+  g.B = wt; g.ldb = wt_ld; g.major_b = kMajorK;
+  g.M = batch; g.N = num_features; g.K = in_dim;
+  g.ep = epi_default();
+  g.ep.col_bias = bias; g.ep.col_bias_ld = num_features;
+  g.ep.act = kActCos; g.ep.act_scale = scale;
+  g.ep.out = phi; g.ep.out_ld = phi_ld; g.ep.out_dt = phi_dtype;
+  g.ep.raw = pre; g.ep.raw_ld = pre_ld; g.ep.raw_dt = kF32;
+  return gemm(dtype, g, S(stream));
+}
+
+int ed2_laplace_precision_update(int dtype, const void* phi, int phi_ld, int batch, int num_features, float momentum,
+                                 long long batch_total, float* precision, float* partial_out, void* stream) {
+  ED2_TRY(check_dt(dtype));
+  GemmDesc g{};
+  g.A = phi; g.lda = phi_ld; g.major_a = kMajorMN;
+  g.B = phi; g.ldb = phi_ld; g.major_b = kMajorMN;
+  g.M = num_features; g.N = num_features; g.K = batch;
+  g.ep = epi_default();
+  if (partial_out != nullptr) {
+    g.ep.out = partial_out; g.ep.out_ld = num_features; g.ep.out_dt = kF32;
+  } else {
+    // in-place blend: every element of P is read (addend) and written (out) by the same thread
+    g.ep.addend = precision; g.ep.addend_ld = num_features; g.ep.addend_dt = kF32;
+    if (momentum > 0.f) {
+      g.ep.alpha = (1.f - momentum) / static_cast<float>(batch_total);
+      g.ep.beta = momentum;
+    }
+    g.ep.out = precision; g.ep.out_ld = num_features; g.ep.out_dt = kF32;
+  }
+  return gemm(dtype, g, S(stream));
+}
+
+int ed2_precision_blend(float* precision, const float* summed, int num_features, float momentum, long long batch_total,
+                        void* stream) {
+  return k_precision_blend(precision, summed, (long long)num_features * num_features, momentum, batch_total, S(stream));
+}
+
+int ed2_predictive_variance(int dtype, const void* phi, int phi_ld, const void* sigma_lp, int sigma_ld, int batch,
+                            int num_features, float ridge, float* var, const float* logits, int num_classes,
+                            float mean_field_factor, int likelihood, float* logits_out, void* stream) {
+  ED2_TRY(check_dt(dtype));
+  cudaStream_t s = S(stream);
+  cudaMemsetAsync(var, 0, sizeof(float) * (size_t)batch, s);
+  GemmDesc g{};
+  g.A = phi; g.lda = phi_ld; g.major_a = kMajorK;
+  g.B = sigma_lp; g.ldb = sigma_ld; g.major_b = kMajorK;  // Sigma is symmetric
+  g.M = batch; g.N = num_features; g.K = num_features;
+  g.ep = epi_default();
+  g.ep.alpha = ridge;
+  g.ep.elem_scale = phi; g.ep.elem_scale_ld = phi_ld; g.ep.elem_scale_dt = dtype;
+  g.ep.row_sum = var;
+  ED2_TRY(gemm(dtype, g, s));
+  if (logits != nullptr && logits_out != nullptr)
+    ED2_TRY(k_mean_field(logits, var, batch, num_classes, mean_field_factor, likelihood, 1.f, logits_out, s));
+  return ED2_OK;
+}
+
+int ed2_mean_field_logits(const float* logits, const float* var, int batch, int num_classes, float mean_field_factor,
+                          int likelihood, float* out, void* stream) {
+  return k_mean_field(logits, var, batch, num_classes, mean_field_factor, likelihood, 1.f, out, S(stream));
+}
+
+int ed2_rff_bwd(int dtype, const void* dphi, int dphi_ld, int dphi_dtype, const float* pre, int pre_ld,
+                const float* bias, const void* w, int w_ld, float scale, int batch, int in_dim, int num_features,
+                void* gpre, int gpre_ld, void* dx, int dx_ld, int dx_dtype, void* stream) {
+  ED2_TRY(check_dt(dtype));
+  cudaStream_t s = S(stream);
+  ED2_TRY(k_rff_bwd_prep(dphi, dphi_dtype, dphi_ld, pre, pre_ld, bias, scale, batch, num_features, gpre, dtype, gpre_ld, s));
+  EpiParams e = epi_default();
+  e.out = dx; e.out_ld = dx_ld; e.out_dt = dx_dtype;
+  return gemm_gwt(dtype, gpre, gpre_ld, w, w_ld, batch, in_dim, num_features, e, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,607 @@
+// Bandwidth-bound kernels of the stochastic-weight layers: Philox fills, casts, TrainableNormal sampling with
+// the analytic KL fused in, KL forward/backward, fast-weight scaling and the column reductions of the backward
+// passes.  All are coalesced, 16-byte vectorised where alignment allows, and use warp-shuffle + shared-memory
+// reductions with one atomic per block (fp64 for the KL scalar).
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+
+#include "gemm_epilogue.h"
+#include "status.h"
+
+namespace ed2 {
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kMaxGrid = 148 * 8;
+constexpr float kSoftplusEps = 1e-7f;  // keras.backend.epsilon(), edward2/tensorflow/constraints.py:56-63
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float ld1(const void* p, int dt, long long i) {
+  return dt == kBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+                     : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st1(void* p, int dt, long long i, float v) {
+  if (dt == kBF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+
+// 4 consecutive elements starting at element offset i; vectorised when the address is 4-element aligned.
+__device__ __forceinline__ void ld4(const void* p, int dt, long long i, int valid, float (&f)[4]) {
+  if (dt == kBF16) {
+    const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(p) + i;
+    if (valid == 4 && (reinterpret_cast<uintptr_t>(q) & 7) == 0) {
+      uint2 r = *reinterpret_cast<const uint2*>(q);
+      float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.x));
+      float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.y));
+      f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = j < valid ? __bfloat162float(q[j]) : 0.f;
+    }
+  } else {
+    const float* q = reinterpret_cast<const float*>(p) + i;
+    if (valid == 4 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+      float4 r = *reinterpret_cast<const float4*>(q);
+      f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = j < valid ? q[j] : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void st4(void* p, int dt, long long i, int valid, const float (&f)[4]) {
+  if (dt == kBF16) {
+    __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p) + i;
+    if (valid == 4 && (reinterpret_cast<uintptr_t>(q) & 7) == 0) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+      uint2 r;
+      r.x = *reinterpret_cast<uint32_t*>(&a);
+      r.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(q) = r;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < valid) q[j] = __float2bfloat16_rn(f[j]);
+    }
+  } else {
+    float* q = reinterpret_cast<float*>(p) + i;
+    if (valid == 4 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+      *reinterpret_cast<float4*>(q) = make_float4(f[0], f[1], f[2], f[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < valid) q[j] = f[j];
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum -> one fp64 atomic
+__device__ __forceinline__ void block_atomic_add(double* out, float v, float scale) {
+  __shared__ float red[kBlock / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < kBlock / 32 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(out, static_cast<double>(t) * static_cast<double>(scale));
+  }
+}
+
+int grid_for(long long work_items) {
+  long long g = (work_items + kBlock - 1) / kBlock;
+  if (g < 1) g = 1;
+  if (g > kMaxGrid) g = kMaxGrid;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------------------------------- Philox fills
+template <int kKind>
+__global__ void philox_fill_kernel(float* out, long long n, uint64_t seed, uint64_t stream) {
+  const long long nblk = (n + 3) >> 2;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+    float e[4];
+    if (kKind == 0) philox_normal4(seed, stream, b, e);
+    else if (kKind == 1) philox_uniform4(seed, stream, b, e);
+    else philox_sign4(seed, stream, b, e);
+    const long long i = b << 2;
+    const int valid = static_cast<int>(min(4LL, n - i));
+    st4(out, kF32, i, valid, e);
+  }
+}
+
+__global__ void philox_raw_kernel(uint32_t* out, long long nblk, uint64_t seed, uint64_t stream) {
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+    uint32_t x[4];
+    philox_block(seed, stream, b, x);
+    reinterpret_cast<uint4*>(out)[b] = make_uint4(x[0], x[1], x[2], x[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- cast
+__global__ void cast2d_kernel(const void* src, int sdt, long long sld, void* dst, int ddt, long long dld,
+                              long long rows, long long cols) {
+  const long long gpr = (cols + 3) >> 2;  // groups per row
+  const long long total = rows * gpr;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long r = g / gpr, c = (g - r * gpr) << 2;
+    const int valid = static_cast<int>(min(4LL, cols - c));
+    float f[4];
+    ld4(src, sdt, r * sld + c, valid, f);
+    st4(dst, ddt, r * dld + c, valid, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- sampling + KL
+__device__ __forceinline__ float kl_elem(float mu, float sigma, float pm, float ps) {
+  const float d = mu - pm;
+  return logf(ps / sigma) + (sigma * sigma + d * d) / (2.f * ps * ps) - 0.5f;
+}
+
+// One thread = one Philox block = 4 consecutive flat elements of the [rows][cols] parameter.
+__global__ void sample_weights_kernel(const float* __restrict__ mu, const float* __restrict__ rho, Noise eps,
+                                      long long rows, long long cols, int mode, void* w, int wdt, long long wld,
+                                      void* mean_out, long long mean_ld, double* kl_out, float kl_scale, Prior p) {
+  const long long n = rows * cols;
+  const long long nblk = (n + 3) >> 2;
+  const bool row_aligned = (cols & 3) == 0;
+  float kl = 0.f;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+    const long long i = b << 2;
+    const int valid = static_cast<int>(min(4LL, n - i));
+    float m[4], r[4], e[4], o[4];
+    ld4(mu, kF32, i, valid, m);
+    ld4(rho, kF32, i, valid, r);
+    noise4<0>(eps, i, n, e);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sigma = softplus_f(r[j]) + kSoftplusEps;
+      o[j] = mode == 0 ? fmaf(sigma, e[j], m[j]) : sigma * e[j];
+      if (kl_out != nullptr && j < valid) kl += kl_elem(m[j], sigma, p.mean, p.stddev);
+    }
+    if (row_aligned) {
+      const long long rr = i / cols, cc = i - rr * cols;
+      st4(w, wdt, rr * wld + cc, valid, o);
+      if (mean_out != nullptr) st4(mean_out, wdt, rr * mean_ld + cc, valid, m);
+    } else {
+      for (int j = 0; j < valid; ++j) {
+        const long long rr = (i + j) / cols, cc = (i + j) - rr * cols;
+        st1(w, wdt, rr * wld + cc, o[j]);
+        if (mean_out != nullptr) st1(mean_out, wdt, rr * mean_ld + cc, m[j]);
+      }
+    }
+  }
+  if (kl_out != nullptr) block_atomic_add(kl_out, kl, kl_scale);
+}
+
+__global__ void normal_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ rho, long long n, Prior p,
+                                     float scale, double* out) {
+  const long long nblk = (n + 3) >> 2;
+  float kl = 0.f;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+    const long long i = b << 2;
+    const int valid = static_cast<int>(min(4LL, n - i));
+    float m[4], r[4];
+    ld4(mu, kF32, i, valid, m);
+    ld4(rho, kF32, i, valid, r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < valid) kl += kl_elem(m[j], softplus_f(r[j]) + kSoftplusEps, p.mean, p.stddev);
+  }
+  block_atomic_add(out, kl, scale);
+}
+
+__global__ void normal_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ rho, long long n, Prior p,
+                                     float scale, const float* upstream, float* dmu, float* drho) {
+  const float g = (upstream != nullptr ? *upstream : 1.f) * scale;
+  const float inv_s2 = 1.f / (p.stddev * p.stddev);
+  const long long nblk = (n + 3) >> 2;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+    const long long i = b << 2;
+    const int valid = static_cast<int>(min(4LL, n - i));
+    float m[4], r[4], a[4], c[4];
+    ld4(mu, kF32, i, valid, m);
+    ld4(rho, kF32, i, valid, r);
+    ld4(dmu, kF32, i, valid, a);
+    ld4(drho, kF32, i, valid, c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sigma = softplus_f(r[j]) + kSoftplusEps;
+      a[j] += g * (m[j] - p.mean) * inv_s2;
+      c[j] += g * (sigma * inv_s2 - 1.f / sigma) * sigmoid_f(r[j]);
+    }
+    st4(dmu, kF32, i, valid, a);
+    st4(drho, kF32, i, valid, c);
+  }
+}
+
+__global__ void normal_grad_finish_kernel(const float* d_mean, const float* d_pert, const float* __restrict__ mu,
+                                          const float* __restrict__ rho, Noise eps, long long n, float klg, Prior p,
+                                          float* dmu, float* drho) {
+  const float inv_s2 = 1.f / (p.stddev * p.stddev);
+  const long long nblk = (n + 3) >> 2;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+    const long long i = b << 2;
+    const int valid = static_cast<int>(min(4LL, n - i));
+    float m[4], r[4], gm[4], gp[4], e[4], om[4], orr[4];
+    ld4(mu, kF32, i, valid, m);
+    ld4(rho, kF32, i, valid, r);
+    ld4(d_mean, kF32, i, valid, gm);
+    ld4(d_pert, kF32, i, valid, gp);
+    noise4<0>(eps, i, n, e);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sigma = softplus_f(r[j]) + kSoftplusEps;
+      om[j] = gm[j] + klg * (m[j] - p.mean) * inv_s2;
+      orr[j] = (gp[j] * e[j] + klg * (sigma * inv_s2 - 1.f / sigma)) * sigmoid_f(r[j]);
+    }
+    st4(dmu, kF32, i, valid, om);
+    st4(drho, kF32, i, valid, orr);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- fast weights
+constexpr float kClip = 10.f;  // edward2/tensorflow/layers/dense.py:1109-1111
+
+// factor for 4 consecutive columns c..c+3 of row `row` (member e)
+template <int kMode>
+__device__ __forceinline__ void fast_factor4(const float* fw_mu, const float* fw_rho, const Noise& nz, long long row,
+                                             int e, int c, int cols, int valid, float (&f)[4], float (&raw)[4],
+                                             float (&en)[4]) {
+  if (kMode == 2) {
+    const long long idx = row * cols + c;
+    if ((idx & 3) == 0) noise4<1>(nz, idx, (long long)1 << 62, f);
+    else
+      for (int j = 0; j < 4; ++j) f[j] = j < valid ? noise1<1>(nz, idx + j) : 0.f;
+    return;
+  }
+  float m[4];
+  ld4(fw_mu, kF32, (long long)e * cols + c, valid, m);
+  if (kMode == 0 || fw_rho == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[j] = m[j]; raw[j] = m[j]; en[j] = 0.f; }
+    return;
+  }
+  float r[4];
+  ld4(fw_rho, kF32, (long long)e * cols + c, valid, r);
+  const long long idx = row * cols + c;
+  if ((idx & 3) == 0) noise4<0>(nz, idx, (long long)1 << 62, en);
+  else
+    for (int j = 0; j < 4; ++j) en[j] = j < valid ? noise1<0>(nz, idx + j) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    raw[j] = fmaf(softplus_f(r[j]) + kSoftplusEps, en[j], m[j]);
+    f[j] = fminf(fmaxf(raw[j], -kClip), kClip);
+  }
+}
+
+template <int kMode>
+__global__ void scale_rows_kernel(const void* x, int dt, long long x_ld, long long rows, int cols, int rpm,
+                                  const float* fw_mu, const float* fw_rho, Noise nz, void* xo, long long xo_ld,
+                                  void* f_out, long long f_ld) {
+  const long long gpr = (cols + 3) >> 2;
+  const long long total = rows * gpr;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long r = g / gpr;
+    const int c = static_cast<int>(g - r * gpr) << 2;
+    const int valid = min(4, cols - c);
+    const int e = static_cast<int>(r / rpm);
+    float f[4], raw[4], en[4];
+    fast_factor4<kMode>(fw_mu, fw_rho, nz, r, e, c, cols, valid, f, raw, en);
+    if (x != nullptr) {
+      float xv[4];
+      ld4(x, dt, r * x_ld + c, valid, xv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xv[j] *= f[j];
+      st4(xo, dt, r * xo_ld + c, valid, xv);
+    }
+    if (f_out != nullptr) st4(f_out, dt, r * f_ld + c, valid, f);
+  }
+}
+
+// Column-reduction tiles: a block owns 128 columns x up to kRowsPerBlock rows that all belong to one member.
+constexpr int kRowsPerBlock = 64;
+
+__device__ __forceinline__ void reduce_cols_and_add(float (&a0)[4], float (&a1)[4], float (&a2)[4], bool use0, bool use1,
+                                                    bool use2, float* o0, float* o1, float* o2, long long base, int c,
+                                                    int cols) {
+  __shared__ float red[3][kBlock / 32][128 + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][warp][lane * 4 + j] = a0[j];
+    red[1][warp][lane * 4 + j] = a1[j];
+    red[2][warp][lane * 4 + j] = a2[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cc = c - lane * 4 + threadIdx.x;  // block's first column + threadIdx.x
+    if (cc < cols) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; ++w) {
+        s0 += red[0][w][threadIdx.x];
+        s1 += red[1][w][threadIdx.x];
+        s2 += red[2][w][threadIdx.x];
+      }
+      if (use0) atomicAdd(o0 + base + cc, s0);
+      if (use1) atomicAdd(o1 + base + cc, s1);
+      if (use2) atomicAdd(o2 + base + cc, s2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks_per_member = (a.rows_per_member + kRowsPerBlock - 1) / kRowsPerBlock;
+  const int e = blockIdx.y / chunks_per_member;
+  const int chunk = blockIdx.y - e * chunks_per_member;
+  const long long row0 = (long long)e * a.rows_per_member + (long long)chunk * kRowsPerBlock;
+  const long long row_end = min((long long)(e + 1) * a.rows_per_member, row0 + kRowsPerBlock);
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int valid = max(0, min(4, a.cols - c));
+  float acc_mu[4] = {0, 0, 0, 0}, acc_rho[4] = {0, 0, 0, 0}, acc_b[4] = {0, 0, 0, 0};
+  float gam[4] = {1, 1, 1, 1}, mus[4], rhos[4], sig_s[4], sgm_s[4];
+  if (valid > 0) {
+    if (a.fast == 1) ld4(a.gamma, kF32, (long long)e * a.cols + c, valid, gam);
+    if (a.fast == 2) {
+      ld4(a.mu_s, kF32, (long long)e * a.cols + c, valid, mus);
+      if (a.rho_s != nullptr) {
+        ld4(a.rho_s, kF32, (long long)e * a.cols + c, valid, rhos);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sig_s[j] = softplus_f(rhos[j]) + kSoftplusEps; sgm_s[j] = sigmoid_f(rhos[j]); }
+      }
+    }
+  }
+  if (valid > 0) {
+    for (long long r = row0 + warp; r < row_end; r += kBlock / 32) {
+      float g[4], y[4];
+      ld4(a.gy, a.dt, r * a.gy_ld + c, valid, g);
+      if (a.act == kActRelu) {
+        ld4(a.y, a.dt, r * a.y_ld + c, valid, y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] = y[j] > 0.f ? g[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc_b[j] += g[j];
+      float dz[4];
+      if (a.fast == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dz[j] = g[j];
+      } else if (a.fast == 1) {
+        float z[4];
+        ld4(a.z, a.dt, r * a.z_ld + c, valid, z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dz[j] = g[j] * gam[j]; acc_mu[j] += g[j] * z[j]; }
+      } else if (a.fast == 2) {
+        float z[4], sv[4];
+        ld4(a.z, a.dt, r * a.z_ld + c, valid, z);
+        ld4(a.s_buf, a.dt, r * a.s_ld + c, valid, sv);
+        if (a.rho_s != nullptr) {
+          float en[4];
+          const long long idx = r * a.cols + c;
+          if ((idx & 3) == 0) noise4<0>(a.eps_s, idx, (long long)1 << 62, en);
+          else
+            for (int j = 0; j < 4; ++j) en[j] = j < valid ? noise1<0>(a.eps_s, idx + j) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float raw = fmaf(sig_s[j], en[j], mus[j]);
+            const float pass = (raw < -kClip || raw > kClip) ? 0.f : 1.f;
+            const float ds = g[j] * z[j] * pass;
+            acc_mu[j] += ds;
+            acc_rho[j] += ds * en[j] * sgm_s[j];
+            dz[j] = g[j] * sv[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { acc_mu[j] += g[j] * z[j]; dz[j] = g[j] * sv[j]; }
+        }
+      } else {  // flipout: dz = gp, dz2 = gp ∘ T
+        float tt[4];
+        const long long idx = r * a.cols + c;
+        if ((idx & 3) == 0) noise4<1>(a.sign_out, idx, (long long)1 << 62, tt);
+        else
+          for (int j = 0; j < 4; ++j) tt[j] = j < valid ? noise1<1>(a.sign_out, idx + j) : 0.f;
+        float d2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dz[j] = g[j]; d2[j] = g[j] * tt[j]; }
+        st4(a.dz2, a.dt, r * a.dz2_ld + c, valid, d2);
+      }
+      st4(a.dz, a.dt, r * a.dz_ld + c, valid, dz);
+    }
+  }
+  reduce_cols_and_add(acc_mu, acc_rho, acc_b, a.d_fast_mu != nullptr, a.d_fast_rho != nullptr, a.dbias != nullptr,
+                      a.d_fast_mu, a.d_fast_rho, a.dbias, (long long)e * a.cols, c, a.cols);
+}
+
+__global__ void __launch_bounds__(kBlock) bwd_in_kernel(BwdInArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks_per_member = (a.rows_per_member + kRowsPerBlock - 1) / kRowsPerBlock;
+  const int e = blockIdx.y / chunks_per_member;
+  const int chunk = blockIdx.y - e * chunks_per_member;
+  const long long row0 = (long long)e * a.rows_per_member + (long long)chunk * kRowsPerBlock;
+  const long long row_end = min((long long)(e + 1) * a.rows_per_member, row0 + kRowsPerBlock);
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int valid = max(0, min(4, a.cols - c));
+  float acc_mu[4] = {0, 0, 0, 0}, acc_rho[4] = {0, 0, 0, 0}, unused[4] = {0, 0, 0, 0};
+  float sgm[4] = {0, 0, 0, 0};
+  if (valid > 0 && a.fast == 2 && a.fw_rho != nullptr) {
+    float rr[4];
+    ld4(a.fw_rho, kF32, (long long)e * a.cols + c, valid, rr);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sgm[j] = sigmoid_f(rr[j]);
+  }
+  if (valid > 0) {
+    for (long long r = row0 + warp; r < row_end; r += kBlock / 32) {
+      float d[4], xv[4], f[4], raw[4], en[4];
+      ld4(a.dxf, a.dt, r * a.dxf_ld + c, valid, d);
+      ld4(a.x, a.dt, r * a.x_ld + c, valid, xv);
+      if (a.fast == 1) fast_factor4<0>(a.fw_mu, nullptr, a.eps, r, e, c, a.cols, valid, f, raw, en);
+      else fast_factor4<1>(a.fw_mu, a.fw_rho, a.eps, r, e, c, a.cols, valid, f, raw, en);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pass = (a.fast == 2 && a.fw_rho != nullptr && (raw[j] < -kClip || raw[j] > kClip)) ? 0.f : 1.f;
+        const float df = d[j] * xv[j] * pass;
+        acc_mu[j] += df;
+        acc_rho[j] += df * en[j] * sgm[j];
+        d[j] *= f[j];
+      }
+      if (a.dx != nullptr) st4(a.dx, a.dt, r * a.dx_ld + c, valid, d);
+    }
+  }
+  reduce_cols_and_add(acc_mu, acc_rho, unused, a.d_fast_mu != nullptr, a.d_fast_rho != nullptr, false, a.d_fast_mu,
+                      a.d_fast_rho, nullptr, (long long)e * a.cols, c, a.cols);
+}
+
+template <int kKind>
+__global__ void fill_noise_kernel(Noise nz, void* out, int dt, long long ld, long long rows, long long cols) {
+  const long long gpr = (cols + 3) >> 2;
+  const long long total = rows * gpr;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long r = g / gpr, c = (g - r * gpr) << 2;
+    const int valid = static_cast<int>(min(4LL, cols - c));
+    const long long idx = r * cols + c;
+    float e[4];
+    if ((idx & 3) == 0) noise4<kKind>(nz, idx, rows * cols, e);
+    else
+      for (int j = 0; j < 4; ++j) e[j] = j < valid ? noise1<kKind>(nz, idx + j) : 0.f;
+    st4(out, dt, r * ld + c, valid, e);
+  }
+}
+
+__global__ void scale_inplace_kernel(float* x, long long n, float a) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] *= a;
+}
+
+}  // namespace
+
+// =============================================================================================== launchers
+int k_philox_fill(int kind, float* out, long long n, uint64_t seed, uint64_t stream, cudaStream_t s) {
+  if (n <= 0) return ED2_OK;
+  const int g = grid_for((n + 3) / 4);
+  if (kind == 0) philox_fill_kernel<0><<<g, kBlock, 0, s>>>(out, n, seed, stream);
+  else if (kind == 1) philox_fill_kernel<1><<<g, kBlock, 0, s>>>(out, n, seed, stream);
+  else philox_fill_kernel<2><<<g, kBlock, 0, s>>>(out, n, seed, stream);
+  count_launch();
+  return check_launch("philox_fill");
+}
+
+int k_philox_raw(uint32_t* out, long long nblk, uint64_t seed, uint64_t stream, cudaStream_t s) {
+  if (nblk <= 0) return ED2_OK;
+  philox_raw_kernel<<<grid_for(nblk), kBlock, 0, s>>>(out, nblk, seed, stream);
+  count_launch();
+  return check_launch("philox_raw");
+}
+
+int k_cast2d(const void* src, int sdt, long long sld, void* dst, int ddt, long long dld, long long rows,
+             long long cols, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  cast2d_kernel<<<grid_for(rows * ((cols + 3) / 4)), kBlock, 0, s>>>(src, sdt, sld, dst, ddt, dld, rows, cols);
+  count_launch();
+  return check_launch("cast2d");
+}
+
+int k_sample_weights(const float* mu, const float* rho, Noise eps, long long rows, long long cols, int mode, void* w,
+                     int wdt, long long wld, void* mean_out, long long mean_ld, double* kl_out, float kl_scale,
+                     Prior p, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  sample_weights_kernel<<<grid_for((rows * cols + 3) / 4), kBlock, 0, s>>>(mu, rho, eps, rows, cols, mode, w, wdt, wld,
+                                                                          mean_out, mean_ld, kl_out, kl_scale, p);
+  count_launch();
+  return check_launch("sample_weights");
+}
+
+int k_normal_kl_fwd(const float* mu, const float* rho, long long n, Prior p, float scale, double* out, cudaStream_t s) {
+  if (n <= 0) return ED2_OK;
+  normal_kl_fwd_kernel<<<grid_for((n + 3) / 4), kBlock, 0, s>>>(mu, rho, n, p, scale, out);
+  count_launch();
+  return check_launch("normal_kl_fwd");
+}
+
+int k_normal_kl_bwd(const float* mu, const float* rho, long long n, Prior p, float scale, const float* upstream,
+                    float* dmu, float* drho, cudaStream_t s) {
+  if (n <= 0) return ED2_OK;
+  normal_kl_bwd_kernel<<<grid_for((n + 3) / 4), kBlock, 0, s>>>(mu, rho, n, p, scale, upstream, dmu, drho);
+  count_launch();
+  return check_launch("normal_kl_bwd");
+}
+
+int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* mu, const float* rho, Noise eps,
+                         long long n, float klg, Prior p, float* dmu, float* drho, cudaStream_t s) {
+  if (n <= 0) return ED2_OK;
+  normal_grad_finish_kernel<<<grid_for((n + 3) / 4), kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, p, dmu, drho);
+  count_launch();
+  return check_launch("normal_grad_finish");
+}
+
+int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols, int rpm, int mode,
+                 const float* fw_mu, const float* fw_rho, Noise nz, void* xo, long long xo_ld, void* f_out,
+                 long long f_ld, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  if (rpm <= 0) rpm = static_cast<int>(rows);
+  const int g = grid_for(rows * ((cols + 3) / 4));
+  if (mode == 0) scale_rows_kernel<0><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld);
+  else if (mode == 1) scale_rows_kernel<1><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld);
+  else scale_rows_kernel<2><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld);
+  count_launch();
+  return check_launch("scale_rows");
+}
+
+int k_bwd_out(const BwdOutArgs& a_in, cudaStream_t s) {
+  BwdOutArgs a = a_in;
+  if (a.rows <= 0 || a.cols <= 0) return ED2_OK;
+  if (a.rows_per_member <= 0) a.rows_per_member = static_cast<int>(a.rows);
+  const int members = static_cast<int>(a.rows / a.rows_per_member);
+  const size_t bytes = sizeof(float) * (size_t)members * a.cols;
+  if (a.d_fast_mu) cudaMemsetAsync(a.d_fast_mu, 0, bytes, s);
+  if (a.d_fast_rho) cudaMemsetAsync(a.d_fast_rho, 0, bytes, s);
+  if (a.dbias) cudaMemsetAsync(a.dbias, 0, bytes, s);
+  const int chunks = (a.rows_per_member + kRowsPerBlock - 1) / kRowsPerBlock;
+  dim3 grid((a.cols + 127) / 128, members * chunks);
+  bwd_out_kernel<<<grid, kBlock, 0, s>>>(a);
+  count_launch();
+  return check_launch("bwd_out");
+}
+
+int k_bwd_in(const BwdInArgs& a_in, cudaStream_t s) {
+  BwdInArgs a = a_in;
+  if (a.rows <= 0 || a.cols <= 0) return ED2_OK;
+  if (a.rows_per_member <= 0) a.rows_per_member = static_cast<int>(a.rows);
+  const int members = static_cast<int>(a.rows / a.rows_per_member);
+  const size_t bytes = sizeof(float) * (size_t)members * a.cols;
+  if (a.d_fast_mu) cudaMemsetAsync(a.d_fast_mu, 0, bytes, s);
+  if (a.d_fast_rho) cudaMemsetAsync(a.d_fast_rho, 0, bytes, s);
+  const int chunks = (a.rows_per_member + kRowsPerBlock - 1) / kRowsPerBlock;
+  dim3 grid((a.cols + 127) / 128, members * chunks);
+  bwd_in_kernel<<<grid, kBlock, 0, s>>>(a);
+  count_launch();
+  return check_launch("bwd_in");
+}
+
+int k_fill_noise(int kind, Noise nz, void* out, int dt, long long ld, long long rows, long long cols, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  const int g = grid_for(rows * ((cols + 3) / 4));
+  if (kind == 0) fill_noise_kernel<0><<<g, kBlock, 0, s>>>(nz, out, dt, ld, rows, cols);
+  else fill_noise_kernel<1><<<g, kBlock, 0, s>>>(nz, out, dt, ld, rows, cols);
+  count_launch();
+  return check_launch("fill_noise");
+}
+
+int k_scale_inplace(float* x, long long n, float a, cudaStream_t s) {
+  if (n <= 0) return ED2_OK;
+  scale_inplace_kernel<<<grid_for(n), kBlock, 0, s>>>(x, n, a);
+  count_launch();
+  return check_launch("scale_inplace");
+}
+
+}  // namespace ed2

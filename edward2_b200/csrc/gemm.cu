@@ -1,0 +1,152 @@
+// Host side of the tcgen05 GEMM: tensor-map construction, configuration choice, launch.
+#include "gemm.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "gemm_sm100.cuh"
+#include "status.h"
+
+namespace ed2 {
+
+namespace {
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+// 2-D row-major tensor [rows][cols] with pitch `ld` elements; box = [box_rows][box_cols]; 128-byte swizzle.
+bool make_map(CUtensorMap* tm, const void* ptr, int dt, long long rows, long long cols, long long ld, int box_rows,
+              int box_cols) {
+  EncodeFn enc = get_encode_fn();
+  if (!enc) return false;
+  const int es = dt == kBF16 ? 2 : 4;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, dt == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool tma_ok(const void* p, long long ld, int es) {
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ((ld * es) & 15) == 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int MA, int MB, int BN, int CG>
+int launch_one(const GemmDesc& g, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+               cudaStream_t stream) {
+  using Cfg = tc::Config<BN, CG>;
+  auto kern = tc::gemm_bf16_kernel<MA, MB, BN, CG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
+                                           cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tile_m = tc::kBlockM * CG;
+  const int num_tiles = ((g.M + tile_m - 1) / tile_m) * ((g.N + BN - 1) / BN);
+  int clusters = num_sms() / CG;
+  if (g.max_ctas > 0) clusters = std::min(clusters, std::max(1, g.max_ctas / CG));
+  clusters = std::min(clusters, num_tiles);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, g.M, g.N, g.K, g.ep);
+  if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return ED2_OK;
+}
+
+template <int MA, int MB>
+int dispatch_cfg(const GemmDesc& g, int bn, int cg, const CUtensorMap& ta, const CUtensorMap& tb,
+                 const CUtensorMap& to, cudaStream_t s) {
+  if (bn == 128 && cg == 1) return launch_one<MA, MB, 128, 1>(g, ta, tb, to, s);
+  if (bn == 256 && cg == 1) return launch_one<MA, MB, 256, 1>(g, ta, tb, to, s);
+  if (bn == 128 && cg == 2) return launch_one<MA, MB, 128, 2>(g, ta, tb, to, s);
+  if (bn == 256 && cg == 2) return launch_one<MA, MB, 256, 2>(g, ta, tb, to, s);
+  return set_error(ED2_ERR_BAD_ARG, "unsupported gemm config block_n=%d cta_group=%d", bn, cg);
+}
+
+int default_cta_group() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ED2_GEMM_CTA_GROUP");
+    v = e ? std::atoi(e) : 2;
+    if (v != 1 && v != 2) v = 2;
+  }
+  return v;
+}
+
+}  // namespace
+
+int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
+  GemmDesc g = g_in;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(ED2_ERR_BAD_SHAPE, "gemm: empty shape %d %d %d", g.M, g.N, g.K);
+  if (!tma_ok(g.A, g.lda, 2) || !tma_ok(g.B, g.ldb, 2))
+    return set_error(ED2_ERR_BAD_ARG, "gemm: A/B must be 16-byte aligned with a pitch that is a multiple of 8 bf16 "
+                                      "(lda=%d ldb=%d)", g.lda, g.ldb);
+  int bn = g.block_n ? g.block_n : (g.N > 128 ? 256 : 128);
+  int cg = g.cta_group ? g.cta_group : default_cta_group();
+  if (cg == 2 && g.M <= 128) cg = 1;
+  const int load_n = bn / cg;
+
+  CUtensorMap ta, tb, to;
+  std::memset(&to, 0, sizeof(to));
+  bool ok = true;
+  if (g.major_a == kMajorK) ok &= make_map(&ta, g.A, kBF16, g.M, g.K, g.lda, tc::kBlockM, tc::kBlockK);
+  else ok &= make_map(&ta, g.A, kBF16, g.K, g.M, g.lda, tc::kBlockK, 64);
+  if (g.major_b == kMajorK) ok &= make_map(&tb, g.B, kBF16, g.N, g.K, g.ldb, load_n, tc::kBlockK);
+  else ok &= make_map(&tb, g.B, kBF16, g.K, g.N, g.ldb, tc::kBlockK, 64);
+  if (!ok) return set_error(ED2_ERR_CUDA, "cuTensorMapEncodeTiled failed for a GEMM operand");
+
+  const int oes = g.ep.out_dt == kBF16 ? 2 : 4;
+  g.ep.out_tma = 0;
+  if (g.ep.out == nullptr && g.ep.row_sum == nullptr) return set_error(ED2_ERR_BAD_ARG, "gemm: out is null");
+  if (g.ep.out != nullptr && !g.no_tma_store && tma_ok(g.ep.out, g.ep.out_ld, oes)) {
+    if (make_map(&to, g.ep.out, g.ep.out_dt, g.M, g.N, g.ep.out_ld, tc::kBlockM, 128 / oes)) g.ep.out_tma = 1;
+  }
+
+  if (g.major_a == kMajorK && g.major_b == kMajorK) return dispatch_cfg<kMajorK, kMajorK>(g, bn, cg, ta, tb, to, stream);
+  if (g.major_a == kMajorK && g.major_b == kMajorMN) return dispatch_cfg<kMajorK, kMajorMN>(g, bn, cg, ta, tb, to, stream);
+  if (g.major_a == kMajorMN && g.major_b == kMajorK) return dispatch_cfg<kMajorMN, kMajorK>(g, bn, cg, ta, tb, to, stream);
+  return dispatch_cfg<kMajorMN, kMajorMN>(g, bn, cg, ta, tb, to, stream);
+}
+
+}  // namespace ed2

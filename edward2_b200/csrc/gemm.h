@@ -1,0 +1,27 @@
+// Internal interface of the tcgen05 GEMM (see gemm_sm100.cuh for the kernel and the epilogue contract).
+#pragma once
+#include <cuda_runtime.h>
+#include "gemm_epilogue.h"
+
+namespace ed2 {
+
+struct GemmDesc {
+  const void* A;  // bf16. K-major: [M][lda] (k contiguous); MN-major: [K][lda] (m contiguous)
+  int lda;
+  int major_a;
+  const void* B;  // bf16. K-major: [N][ldb] (k contiguous); MN-major: [K][ldb] (n contiguous)
+  int ldb;
+  int major_b;
+  int M, N, K;
+  EpiParams ep;
+  int block_n;       // 0 = auto, else 128 | 256
+  int cta_group;     // 0 = auto, else 1 | 2
+  int max_ctas;      // 0 = all SMs
+  int no_tma_store;  // force the direct-store epilogue (testing)
+};
+
+int gemm_bf16(const GemmDesc& g, cudaStream_t stream);  // tcgen05 tensor cores
+int gemm_f32(const GemmDesc& g, cudaStream_t stream);   // fp32 FFMA path
+int gemm(int dtype, const GemmDesc& g, cudaStream_t stream);
+
+}  // namespace ed2

@@ -1,0 +1,116 @@
+// fp32 GEMM with the same layouts and fused epilogue as the tcgen05 kernel: exact fp32 products, fp32 FFMA
+// accumulation.  It serves the fp32 parity path (1e-5 vs the float64 oracle) and the small, launch-bound
+// fp32 shapes (BASELINE config 1: BatchEnsemble MLP 784-512-512-10 at batch 128), where the problem is far
+// below one tensor-core wave and the step is latency- rather than math-bound.
+#include "gemm.h"
+#include "status.h"
+
+#include <cuda_bf16.h>
+
+namespace ed2 {
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__device__ __forceinline__ float ld_elem(const void* p, int dt, long long idx) {
+  return dt == kBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx])
+                     : reinterpret_cast<const float*>(p)[idx];
+}
+__device__ __forceinline__ void st_elem(void* p, int dt, long long idx, float v) {
+  if (dt == kBF16) reinterpret_cast<__nv_bfloat16*>(p)[idx] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[idx] = v;
+}
+
+template <int MA, int MB>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda,
+                                                       const float* __restrict__ B, int ldb, int M, int N, int K,
+                                                       EpiParams ep) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int t = threadIdx.x;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int ty = t / 16, tx = t % 16;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = t + i * 256;
+      int m, k;
+      if (MA == kMajorK) { k = idx % TK; m = idx / TK; } else { m = idx % TM; k = idx / TM; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < K) v = MA == kMajorK ? A[(long long)gm * lda + gk] : A[(long long)gk * lda + gm];
+      As[k][m] = v;
+      int n, kk;
+      if (MB == kMajorK) { kk = idx % TK; n = idx / TK; } else { n = idx % TN; kk = idx / TN; }
+      const int gn = n0 + n, gk2 = k0 + kk;
+      float w = 0.f;
+      if (gn < N && gk2 < K) w = MB == kMajorK ? B[(long long)gn * ldb + gk2] : B[(long long)gk2 * ldb + gn];
+      Bs[kk][n] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int grp = ep.group_rows > 0 ? m / ep.group_rows : 0;
+    float rs = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] * ep.alpha;
+      if (ep.raw) st_elem(ep.raw, ep.raw_dt, (long long)m * ep.raw_ld + n, v);
+      if (ep.elem_scale) v *= ld_elem(ep.elem_scale, ep.elem_scale_dt, (long long)m * ep.elem_scale_ld + n);
+      if (ep.col_scale) v *= ep.col_scale[(long long)grp * ep.col_scale_ld + n];
+      if (ep.addend) v = fmaf(ep.beta, ld_elem(ep.addend, ep.addend_dt, (long long)m * ep.addend_ld + n), v);
+      if (ep.col_bias) v += ep.col_bias[(long long)grp * ep.col_bias_ld + n];
+      if (ep.act == kActRelu) v = fmaxf(v, 0.f);
+      else if (ep.act == kActCos) v = cosf(v) * ep.act_scale;
+      if (ep.out) st_elem(ep.out, ep.out_dt, (long long)m * ep.out_ld + n, v);
+      rs += v;
+    }
+    if (ep.row_sum) atomicAdd(ep.row_sum + m, rs);
+  }
+}
+
+}  // namespace
+
+int gemm_f32(const GemmDesc& g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(ED2_ERR_BAD_SHAPE, "gemm_f32: empty shape");
+  dim3 grid((g.N + TN - 1) / TN, (g.M + TM - 1) / TM);
+  const float* A = reinterpret_cast<const float*>(g.A);
+  const float* B = reinterpret_cast<const float*>(g.B);
+  if (g.major_a == kMajorK && g.major_b == kMajorK)
+    gemm_f32_kernel<kMajorK, kMajorK><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
+  else if (g.major_a == kMajorK && g.major_b == kMajorMN)
+    gemm_f32_kernel<kMajorK, kMajorMN><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
+  else if (g.major_a == kMajorMN && g.major_b == kMajorK)
+    gemm_f32_kernel<kMajorMN, kMajorK><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
+  else
+    gemm_f32_kernel<kMajorMN, kMajorMN><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
+  count_launch();
+  return check_launch("gemm_f32");
+}
+
+int gemm(int dtype, const GemmDesc& g, cudaStream_t stream) {
+  if (dtype == kBF16) return gemm_bf16(g, stream);
+  if (dtype == kF32) return gemm_f32(g, stream);
+  return set_error(ED2_ERR_BAD_DTYPE, "gemm: unknown dtype %d", dtype);
+}
+
+}  // namespace ed2

@@ -1,0 +1,101 @@
+// Host launchers of the element-wise / reduction kernels (elementwise.cu, sngp.cu).  All enqueue on `s`.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "philox.cuh"
+
+namespace ed2 {
+
+struct Prior {
+  float mean, stddev;
+};
+
+int k_philox_fill(int kind /*0 normal 1 uniform 2 sign*/, float* out, long long n, uint64_t seed, uint64_t stream,
+                  cudaStream_t s);
+int k_philox_raw(uint32_t* out, long long n_blocks, uint64_t seed, uint64_t stream, cudaStream_t s);
+int k_cast2d(const void* src, int sdt, long long sld, void* dst, int ddt, long long dld, long long rows,
+             long long cols, cudaStream_t s);
+int k_sample_weights(const float* mu, const float* rho, Noise eps, long long rows, long long cols, int mode, void* w,
+                     int wdt, long long wld, void* mean_out, long long mean_ld, double* kl_out, float kl_scale,
+                     Prior p, cudaStream_t s);
+int k_normal_kl_fwd(const float* mu, const float* rho, long long n, Prior p, float scale, double* out, cudaStream_t s);
+int k_normal_kl_bwd(const float* mu, const float* rho, long long n, Prior p, float scale, const float* upstream,
+                    float* dmu, float* drho, cudaStream_t s);
+// dmu = d_mean + kl*(mu-m)/s^2 ; drho = (d_pert*eps + kl*(sigma/s^2 - 1/sigma)) * sigmoid(rho)
+int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* mu, const float* rho, Noise eps,
+                         long long n, float kl_grad_scale, Prior p, float* dmu, float* drho, cudaStream_t s);
+
+// ---- forward input preparation:  xo = x ∘ f  (f = alpha[e] | clip(mu+sigma*eps) | sign), dt in/out
+// mode 0: per-member vector fw_mu[e][cols] (BatchEnsemble alpha)
+// mode 1: per-example sampled fast weight clip(fw_mu[e] + softplus(fw_rho[e])*eps[b], -10, 10) (rank-1)
+// mode 2: per-example sign noise (Flipout sign_input)
+// s_out (optional, modes 0/1): the factor itself written as a [rows][cols] tensor in dt (rank-1 `s`).
+int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols, int rows_per_member, int mode,
+                 const float* fw_mu, const float* fw_rho, Noise nz, void* xo, long long xo_ld, void* f_out,
+                 long long f_ld, cudaStream_t s);
+
+// ---- backward preparation on the output side of a layer:
+//   gp = gy ∘ act'(y)
+//   plain (fast == 0): dz = gp                   dbias[n]    = Σ_m gp
+//   BE    (fast == 1): dz = gp ∘ gamma[e]        dgamma[e,n] = Σ gp ∘ z     dbias[e,n] = Σ gp
+//   rank1 (fast == 2): dz = gp ∘ s[b,n]          dmu_s[e,n]  = Σ gp∘z∘1[|s_raw|<=10]   drho_s likewise ∘ eps ∘ sigmoid(rho)
+//   flipout (fast == 3): dz = gp,  dz2 = gp ∘ T[b,n]   dbias[n] = Σ gp
+struct BwdOutArgs {
+  int dt;
+  long long rows;
+  int cols;
+  int rows_per_member;  // rows for plain/flipout
+  int act;
+  int fast;
+  const void* gy; long long gy_ld;
+  const void* y; long long y_ld;
+  const void* z; long long z_ld;
+  const void* s_buf; long long s_ld;
+  const float* gamma;           // BE
+  const float* mu_s; const float* rho_s; Noise eps_s;  // rank-1
+  Noise sign_out;               // flipout (injected fp32 or philox sign)
+  void* dz; long long dz_ld;
+  void* dz2; long long dz2_ld;
+  float* d_fast_mu;   // dgamma | dmu_s        [E][cols], pre-zeroed by the launcher
+  float* d_fast_rho;  // drho_s or nullptr
+  float* dbias;       // [E][cols] or nullptr
+};
+int k_bwd_out(const BwdOutArgs& a, cudaStream_t s);
+
+// ---- backward on the input side: given dxf = d(x∘f) [rows][cols] (dt)
+//   BE   : dx = dxf ∘ alpha[e]; dalpha[e,i] = Σ dxf ∘ x
+//   rank1: dx = dxf ∘ r[b,i];   dmu_r = Σ dxf∘x∘1[] ; drho_r = Σ dxf∘x∘eps∘sigmoid(rho)∘1[]
+struct BwdInArgs {
+  int dt;
+  long long rows;
+  int cols;
+  int rows_per_member;
+  int fast;  // 1 BE, 2 rank-1
+  const void* dxf; long long dxf_ld;
+  const void* x; long long x_ld;
+  const float* fw_mu; const float* fw_rho; Noise eps;
+  void* dx; long long dx_ld;  // may be nullptr
+  float* d_fast_mu; float* d_fast_rho;
+};
+int k_bwd_in(const BwdInArgs& a, cudaStream_t s);
+
+// flipout: out[b,i] (dt) = a[b,i] (fp32) ∘ S + c ... handled by GEMM epilogue; this materialises a sign tensor
+int k_fill_noise(int kind, Noise nz, void* out, int dt, long long ld, long long rows, long long cols, cudaStream_t s);
+
+// ---- SNGP
+int k_spectral_norm(const float* w, int in_dim, int out_dim, float* u, float* v, int iterations, float c, int mode,
+                    int update_uv, float* w_out, void* w_out_lp, long long w_lp_ld, float* sigma_out, float* ws,
+                    cudaStream_t s);
+int k_input_normalize(const void* x, int xdt, long long x_ld, void* y, int ydt, long long y_ld, long long rows,
+                      int cols, const float* gamma, const float* beta, float eps, int scale_only, float scale,
+                      cudaStream_t s);
+int k_precision_blend(float* precision, const float* summed, long long n, float momentum, long long batch_total,
+                      cudaStream_t s);
+int k_mean_field(const float* logits, const float* var, long long batch, int classes, float factor, int likelihood,
+                 float var_scale, float* out, cudaStream_t s);
+int k_rff_bwd_prep(const void* dphi, int ddt, long long dphi_ld, const float* pre, long long pre_ld, const float* bias, float scale,
+                   long long rows, int cols, void* gpre, int gdt, long long gpre_ld, cudaStream_t s);
+int k_scale_inplace(float* x, long long n, float a, cudaStream_t s);
+
+}  // namespace ed2

@@ -1,0 +1,122 @@
+// Philox4x32-10 counter-based generator (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3",
+// SC'11; Random123 reference constants) and the element-indexed noise streams used by every sampling
+// kernel in this library.
+//
+// Stream contract (identical on host and device, see oracle/philox.py):
+//   key      = (seed_lo, seed_hi)
+//   counter  = (block_lo, block_hi, stream_lo, stream_hi)     block = element_index / 4
+//   outputs  = 4 x uint32 -> the 4 consecutive elements 4*block .. 4*block+3 of the stream
+// so the value of element i depends only on (seed, stream, i): forward, backward and any tiling regenerate
+// the same epsilon without storing it (SURVEY.md §7 hard part 3).
+//   uniform  u = ((x >> 8) + 0.5) * 2^-24            in (0, 1), exactly representable
+//   normal   Box-Muller on (x0,x1) -> (z0,z1), (x2,x3) -> (z2,z3)
+//   sign     +1 if bit 31 of x is set else -1        (P(+1) = 1/2)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ed2 {
+
+struct PhiloxKey {
+  uint32_t k0, k1;
+};
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#ifdef __CUDA_ARCH__
+  const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+#else
+  const uint64_t p0 = static_cast<uint64_t>(M0) * c[0], p1 = static_cast<uint64_t>(M1) * c[2];
+  const uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+  const uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
+#endif
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += W0;
+    k1 += W1;
+  }
+}
+
+__host__ __device__ __forceinline__ void philox_block(uint64_t seed, uint64_t stream, uint64_t block,
+                                                      uint32_t (&out)[4]) {
+  out[0] = static_cast<uint32_t>(block);
+  out[1] = static_cast<uint32_t>(block >> 32);
+  out[2] = static_cast<uint32_t>(stream);
+  out[3] = static_cast<uint32_t>(stream >> 32);
+  philox4x32_10(out, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+}
+
+__host__ __device__ __forceinline__ float u32_to_uniform(uint32_t x) {
+  return (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
+}
+
+__device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& z0, float& z1) {
+  const float u0 = u32_to_uniform(x0), u1 = u32_to_uniform(x1);
+  const float r = sqrtf(-2.0f * logf(u0));
+  float s, c;
+  sincospif(2.0f * u1, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t block, float (&z)[4]) {
+  uint32_t x[4];
+  philox_block(seed, stream, block, x);
+  box_muller(x[0], x[1], z[0], z[1]);
+  box_muller(x[2], x[3], z[2], z[3]);
+}
+
+__device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t stream, uint64_t block, float (&u)[4]) {
+  uint32_t x[4];
+  philox_block(seed, stream, block, x);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) u[i] = u32_to_uniform(x[i]);
+}
+
+__device__ __forceinline__ void philox_sign4(uint64_t seed, uint64_t stream, uint64_t block, float (&s)[4]) {
+  uint32_t x[4];
+  philox_block(seed, stream, block, x);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[i] = (x[i] >> 31) ? 1.0f : -1.0f;
+}
+
+// Noise source for one tensor: either an injected array (parity tests inject the reference's draws) or a
+// Philox stream.  `kind`: 0 normal, 1 sign.
+struct Noise {
+  const float* injected;  // nullptr -> Philox
+  uint64_t seed;
+  uint64_t stream;
+};
+
+// 4 consecutive noise values starting at flat element index idx (idx % 4 == 0).
+template <int kKind>
+__device__ __forceinline__ void noise4(const Noise& nz, long long idx, long long n, float (&e)[4]) {
+  if (nz.injected != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e[i] = (idx + i < n) ? __ldg(nz.injected + idx + i) : 0.f;
+  } else if constexpr (kKind == 0) {
+    philox_normal4(nz.seed, nz.stream, static_cast<uint64_t>(idx >> 2), e);
+  } else {
+    philox_sign4(nz.seed, nz.stream, static_cast<uint64_t>(idx >> 2), e);
+  }
+}
+
+// single element at arbitrary flat index
+template <int kKind>
+__device__ __forceinline__ float noise1(const Noise& nz, long long idx) {
+  if (nz.injected != nullptr) return __ldg(nz.injected + idx);
+  float e[4];
+  if constexpr (kKind == 0) philox_normal4(nz.seed, nz.stream, static_cast<uint64_t>(idx >> 2), e);
+  else philox_sign4(nz.seed, nz.stream, static_cast<uint64_t>(idx >> 2), e);
+  return e[idx & 3];
+}
+
+}  // namespace ed2

@@ -1,0 +1,291 @@
+// SNGP-head kernels that are not contractions: the spectral-norm power iteration (coalesced, bandwidth-bound
+// matvecs over the weight matrix), input LayerNorm, the precision-matrix momentum blend and mean-field logits.
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+
+#include "gemm_epilogue.h"
+#include "status.h"
+
+namespace ed2 {
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float red[kBlock / 32];
+  __shared__ float total;
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < kBlock / 32 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) total = t;
+  }
+  __syncthreads();
+  const float r = total;
+  __syncthreads();
+  return r;
+}
+
+// t[i] = sum_o W[i][o] * u[o]   — one warp per row, float4 loads along the contiguous axis.
+__global__ void __launch_bounds__(kBlock) matvec_rows_kernel(const float* __restrict__ w, int rows, int cols,
+                                                             const float* __restrict__ u, float* __restrict__ t) {
+  const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * kBlock) >> 5;
+  const bool vec = (cols & 3) == 0;
+  for (int r = warp; r < rows; r += nwarps) {
+    const float* wr = w + (long long)r * cols;
+    float acc = 0.f;
+    if (vec) {
+      for (int c = lane * 4; c < cols; c += 128) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(wr + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(u + c));
+        acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) acc += wr[c] * u[c];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) t[r] = acc;
+  }
+}
+
+// t[o] += sum_{i in slab} v[i] * W[i][o]   — block = 128 columns x a slab of rows; coalesced along o.
+constexpr int kSlabRows = 128;
+__global__ void __launch_bounds__(kBlock) matvec_cols_kernel(const float* __restrict__ w, int rows, int cols,
+                                                             const float* __restrict__ v, float* __restrict__ t) {
+  __shared__ float red[kBlock / 32][128 + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int r0 = blockIdx.y * kSlabRows;
+  const int r1 = min(rows, r0 + kSlabRows);
+  float acc[4] = {0, 0, 0, 0};
+  if (c < cols) {
+    const bool vec = (cols & 3) == 0;
+    for (int r = r0 + warp; r < r1; r += kBlock / 32) {
+      const float vv = __ldg(v + r);
+      const float* wr = w + (long long)r * cols + c;
+      if (vec) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(wr));
+        acc[0] += vv * a.x; acc[1] += vv * a.y; acc[2] += vv * a.z; acc[3] += vv * a.w;
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (c + j < cols) acc[j] += vv * wr[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[warp][lane * 4 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < cols) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < kBlock / 32; ++k) s += red[k][threadIdx.x];
+      atomicAdd(t + cc, s);
+    }
+  }
+}
+
+// dst = src * rsqrt(max(sum(src^2), 1e-12))   (tf.nn.l2_normalize / edward2/jax/nn/normalization.py:50-51)
+__global__ void __launch_bounds__(kBlock) l2_normalize_kernel(const float* __restrict__ src, int n, float* dst) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += kBlock) acc += src[i] * src[i];
+  const float tot = block_sum(acc);
+  const float inv = rsqrtf(fmaxf(tot, 1e-12f));
+  for (int i = threadIdx.x; i < n; i += kBlock) dst[i] = src[i] * inv;
+}
+
+// scal[0] = sigma = <u, u_raw>;  scal[1] = multiplicative factor applied to W
+__global__ void __launch_bounds__(kBlock) sigma_kernel(const float* __restrict__ u, const float* __restrict__ u_raw,
+                                                       int n, float c, int mode, float* scal, float* sigma_out) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += kBlock) acc += u[i] * u_raw[i];
+  const float sigma = block_sum(acc);
+  if (threadIdx.x == 0) {
+    float factor;
+    if (mode == 0) factor = (c / sigma) < 1.f ? (c / sigma) : 1.f;  // normalization.py:387-390
+    else factor = 1.f / fmaxf(sigma / c, 1.f);                      // jax/nn/normalization.py:175-178
+    scal[0] = sigma;
+    scal[1] = factor;
+    if (sigma_out != nullptr) *sigma_out = sigma;
+  }
+}
+
+__global__ void scale_w_kernel(const float* __restrict__ w, long long rows, long long cols, const float* scal,
+                               int mode, float c, float* w_out, __nv_bfloat16* w_lp, long long lp_ld) {
+  const float sigma = scal[0], factor = scal[1];
+  const float div = fmaxf(sigma / c, 1.f);
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    const float y = mode == 0 ? (factor < 1.f ? factor * x : x) : x / div;
+    if (w_out != nullptr) w_out[i] = y;
+    if (w_lp != nullptr) {
+      const long long r = i / cols, cc = i - r * cols;
+      w_lp[r * lp_ld + cc] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+__device__ __forceinline__ float ld1(const void* p, int dt, long long i) {
+  return dt == kBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+                     : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st1(void* p, int dt, long long i, float v) {
+  if (dt == kBF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+
+// one warp per row; two-pass mean/variance in registers-from-L1 (row is re-read from L1/L2, not HBM)
+__global__ void __launch_bounds__(kBlock) input_normalize_kernel(const void* x, int xdt, long long x_ld, void* y,
+                                                                 int ydt, long long y_ld, long long rows, int cols,
+                                                                 const float* gamma, const float* beta, float eps,
+                                                                 int scale_only, float scale) {
+  const long long warp = (blockIdx.x * (long long)kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * kBlock) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    if (scale_only) {
+      for (int c = lane; c < cols; c += 32) st1(y, ydt, r * y_ld + c, ld1(x, xdt, r * x_ld + c) * scale);
+      continue;
+    }
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += ld1(x, xdt, r * x_ld + c);
+    const float mean = warp_sum(s) / cols;
+    float q = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float d = ld1(x, xdt, r * x_ld + c) - mean;
+      q += d * d;
+    }
+    const float inv = rsqrtf(warp_sum(q) / cols + eps);
+    for (int c = lane; c < cols; c += 32) {
+      float v = (ld1(x, xdt, r * x_ld + c) - mean) * inv;
+      if (gamma != nullptr) v *= gamma[c];
+      if (beta != nullptr) v += beta[c];
+      st1(y, ydt, r * y_ld + c, v);
+    }
+  }
+}
+
+__global__ void precision_blend_kernel(float* p, const float* __restrict__ summed, long long n, float momentum,
+                                       float inv_batch) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (momentum > 0.f) p[i] = momentum * p[i] + (1.f - momentum) * summed[i] * inv_batch;
+    else p[i] = p[i] + summed[i];
+  }
+}
+
+__global__ void mean_field_kernel(const float* __restrict__ logits, const float* __restrict__ var, long long batch,
+                                  int classes, float factor, int likelihood, float var_scale, float* out) {
+  const long long n = batch * classes;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / classes;
+    float l = logits[i];
+    if (factor >= 0.f) {  // utils.py:400-402: a negative factor returns the logits unchanged
+      const float v = var[b] * var_scale;
+      const float scale = likelihood == 1 ? expf(-v * factor * 0.5f) : sqrtf(1.f + v * factor);
+      l = l / scale;
+    }
+    out[i] = l;
+  }
+}
+
+__global__ void rff_bwd_prep_kernel(const void* dphi, int ddt, long long dphi_ld, const float* __restrict__ pre,
+                                    long long pre_ld, const float* __restrict__ bias, float scale, long long rows, int cols, void* gpre, int gdt,
+                                    long long gpre_ld) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    const float g = ld1(dphi, ddt, r * dphi_ld + c);
+    st1(gpre, gdt, r * gpre_ld + c, -scale * sinf(pre[r * pre_ld + c] + (bias != nullptr ? bias[c] : 0.f)) * g);
+  }
+}
+
+int grid_for(long long n) {
+  long long g = (n + kBlock - 1) / kBlock;
+  if (g < 1) g = 1;
+  if (g > 148 * 8) g = 148 * 8;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+int k_spectral_norm(const float* w, int in_dim, int out_dim, float* u, float* v, int iterations, float c, int mode,
+                    int update_uv, float* w_out, void* w_out_lp, long long w_lp_ld, float* sigma_out, float* ws,
+                    cudaStream_t s) {
+  // workspace: v_raw [in_dim] | u_raw [out_dim] | scal [8]
+  float* v_raw = ws;
+  float* u_raw = ws + in_dim;
+  float* scal = u_raw + out_dim;
+  const int row_grid = std::min(148 * 4, (in_dim + 7) / 8);
+  dim3 col_grid((out_dim + 127) / 128, (in_dim + kSlabRows - 1) / kSlabRows);
+  int launches = 0;
+  const int iters = update_uv ? iterations : 0;
+  for (int it = 0; it < iters; ++it) {
+    matvec_rows_kernel<<<row_grid, kBlock, 0, s>>>(w, in_dim, out_dim, u, v_raw);       // u Wᵀ
+    l2_normalize_kernel<<<1, kBlock, 0, s>>>(v_raw, in_dim, v);
+    cudaMemsetAsync(u_raw, 0, sizeof(float) * out_dim, s);
+    matvec_cols_kernel<<<col_grid, kBlock, 0, s>>>(w, in_dim, out_dim, v, u_raw);       // v W
+    l2_normalize_kernel<<<1, kBlock, 0, s>>>(u_raw, out_dim, u);
+    launches += 4;
+  }
+  if (iters == 0) {
+    cudaMemsetAsync(u_raw, 0, sizeof(float) * out_dim, s);
+    matvec_cols_kernel<<<col_grid, kBlock, 0, s>>>(w, in_dim, out_dim, v, u_raw);
+    ++launches;
+  }
+  sigma_kernel<<<1, kBlock, 0, s>>>(u, u_raw, out_dim, c, mode, scal, sigma_out);
+  ++launches;
+  if (w_out != nullptr || w_out_lp != nullptr) {
+    scale_w_kernel<<<grid_for((long long)in_dim * out_dim), kBlock, 0, s>>>(
+        w, in_dim, out_dim, scal, mode, c, w_out, reinterpret_cast<__nv_bfloat16*>(w_out_lp), w_lp_ld);
+    ++launches;
+  }
+  count_launch(launches);
+  return check_launch("spectral_norm");
+}
+
+int k_input_normalize(const void* x, int xdt, long long x_ld, void* y, int ydt, long long y_ld, long long rows,
+                      int cols, const float* gamma, const float* beta, float eps, int scale_only, float scale,
+                      cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  const int g = static_cast<int>(std::min<long long>(148 * 8, (rows + 7) / 8));
+  input_normalize_kernel<<<g, kBlock, 0, s>>>(x, xdt, x_ld, y, ydt, y_ld, rows, cols, gamma, beta, eps, scale_only, scale);
+  count_launch();
+  return check_launch("input_normalize");
+}
+
+int k_precision_blend(float* precision, const float* summed, long long n, float momentum, long long batch_total,
+                      cudaStream_t s) {
+  precision_blend_kernel<<<grid_for(n), kBlock, 0, s>>>(precision, summed, n, momentum, 1.f / (float)batch_total);
+  count_launch();
+  return check_launch("precision_blend");
+}
+
+int k_mean_field(const float* logits, const float* var, long long batch, int classes, float factor, int likelihood,
+                 float var_scale, float* out, cudaStream_t s) {
+  if (batch <= 0) return ED2_OK;
+  mean_field_kernel<<<grid_for(batch * classes), kBlock, 0, s>>>(logits, var, batch, classes, factor, likelihood, var_scale, out);
+  count_launch();
+  return check_launch("mean_field");
+}
+
+int k_rff_bwd_prep(const void* dphi, int ddt, long long dphi_ld, const float* pre, long long pre_ld, const float* bias, float scale,
+                   long long rows, int cols, void* gpre, int gdt, long long gpre_ld, cudaStream_t s) {
+  if (rows <= 0) return ED2_OK;
+  rff_bwd_prep_kernel<<<grid_for(rows * cols), kBlock, 0, s>>>(dphi, ddt, dphi_ld, pre, pre_ld, bias, scale, rows, cols, gpre, gdt, gpre_ld);
+  count_launch();
+  return check_launch("rff_bwd_prep");
+}
+
+}  // namespace ed2

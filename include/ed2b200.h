@@ -1,0 +1,341 @@
+/* ed2b200.h — C ABI of libed2b200.so: sm_100a (B200) kernels for the Edward2 stochastic-weight dense layers
+ * and the SNGP random-feature Gaussian-process head.
+ *
+ * The reference (google/edward2 0.0.3) is pure Python over TF/JAX and has NO native boundary for this path
+ * (SURVEY.md §0.2); this header DEFINES the boundary a TF custom op / jax.ffi custom call / ctypes stub
+ * binds to.  Each entry point cites the reference lines whose arithmetic it replaces (paths relative to
+ * the reference checkout).
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer owned by the caller; the library never frees caller memory;
+ *  - scratch memory comes from a caller-provided workspace sized by the matching *_workspace_bytes();
+ *  - every entry point only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and returns;
+ *  - return value: 0 = OK, negative = ed2_status; text via ed2_last_error() (thread-local);
+ *  - tensors are row-major with an explicit leading dimension in ELEMENTS;
+ *  - dtype: ED2_F32 or ED2_BF16 for activations; parameters and gradients of parameters are fp32;
+ *  - randomness: every noise tensor is EITHER injected (non-NULL device pointer to fp32 values, used by the
+ *    parity tests to inject the reference's draws) OR drawn in-kernel from Philox4x32-10 keyed by
+ *    (seed, stream) and indexed by flat element index (ed2_noise.injected == NULL);
+ *  - there is no CPU fallback: on a machine without an sm_100 GPU every compute entry point fails.
+ */
+#ifndef ED2B200_H_
+#define ED2B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ED2_OK = 0,
+  ED2_ERR_BAD_SHAPE = -1,
+  ED2_ERR_BAD_DTYPE = -2,
+  ED2_ERR_BAD_ARG = -3,
+  ED2_ERR_UNSUPPORTED_ARCH = -4,
+  ED2_ERR_CUDA = -5,
+  ED2_ERR_WORKSPACE = -6
+} ed2_status;
+
+typedef enum { ED2_F32 = 0, ED2_BF16 = 1 } ed2_dtype;
+typedef enum { ED2_ACT_NONE = 0, ED2_ACT_RELU = 1, ED2_ACT_COS = 2 } ed2_activation;
+typedef enum { ED2_MAJOR_K = 0, ED2_MAJOR_MN = 1 } ed2_major;
+
+/* A noise tensor: injected values or a Philox stream (see Conventions). */
+typedef struct {
+  const float* injected; /* NULL -> Philox(seed, stream) */
+  uint64_t seed;
+  uint64_t stream;
+} ed2_noise;
+
+const char* ed2_version(void);
+const char* ed2_last_error(void);
+/* number of kernels this library has launched in this process (bench.py reports the delta) */
+long long ed2_launch_count(void);
+/* 0 if device `dev` is an sm_100 part this library can run on */
+int ed2_check_device(int dev);
+
+/* ------------------------------------------------------------------------------------------------
+ * Generic fused GEMM (building block of every layer below; exported for tests and for composition).
+ *   out = act( ((alpha * A·B) ∘ elem_scale ∘ col_scale[g(m)]) + beta * addend + col_bias[g(m)] )
+ *   raw = alpha * A·B                      (optional)
+ *   row_sum[m] += sum_n out[m,n]           (optional, fp32 atomics; `out` may then be NULL)
+ * g(m) = m / group_rows (0 when group_rows == 0).  dtype selects the engine: ED2_BF16 = tcgen05 tensor
+ * cores (bf16 in, fp32 accumulate in TMEM); ED2_F32 = fp32 path (exact fp32 products, fp32 accumulate).
+ * Layouts: A K-major = [M][lda], MN-major = [K][lda]; B K-major = [N][ldb], MN-major = [K][ldb]. */
+typedef struct {
+  int dtype; /* operand dtype: ED2_BF16 or ED2_F32 */
+  const void* a; int lda; int major_a;
+  const void* b; int ldb; int major_b;
+  int m, n, k;
+  float alpha, beta, act_scale;
+  int act;
+  int group_rows;
+  const void* elem_scale; int elem_scale_ld; int elem_scale_dtype;
+  const float* col_scale; int col_scale_ld;
+  const void* addend; int addend_ld; int addend_dtype;
+  const float* col_bias; int col_bias_ld;
+  void* out; int out_ld; int out_dtype;
+  void* raw; int raw_ld; int raw_dtype;
+  float* row_sum;
+  /* tuning / test knobs, 0 = automatic */
+  int block_n, cta_group, max_ctas, no_tma_store;
+} ed2_gemm_desc;
+
+int ed2_gemm(const ed2_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Philox sampler, exposed for the statistical tests.  out[i], i in [0,n), fp32.
+ * Replaces tf.random.* / tfp Normal.sample at edward2/tensorflow/random_variable.py:161-174 and
+ * edward2/tensorflow/layers/dense.py:261-270. */
+int ed2_philox_normal(float* out, long long n, uint64_t seed, uint64_t stream, void* s);
+int ed2_philox_uniform(float* out, long long n, uint64_t seed, uint64_t stream, void* s);
+int ed2_philox_sign(float* out, long long n, uint64_t seed, uint64_t stream, void* s);
+int ed2_philox_raw(uint32_t* out, long long n_blocks, uint64_t seed, uint64_t stream, void* s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise building blocks. */
+/* dst[r, c] = (dtype_out) src[r, c]; rows x cols with pitches (elements); used to make bf16 working copies */
+int ed2_cast(const void* src, int src_dtype, int src_ld, void* dst, int dst_dtype, int dst_ld, long long rows,
+             long long cols, void* s);
+
+/* TrainableNormal sample (edward2/tensorflow/initializers.py:500-511, constraints.py:62-63):
+ *   sigma = softplus(rho) + 1e-7;  w = mu + sigma * eps   (mode 0)   or   delta = sigma * eps   (mode 1)
+ * over `rows x cols` fp32 parameters with pitch cols; output `w` in w_dtype with pitch w_ld.  If kl_out is
+ * non-NULL also accumulates kl_scale * sum KL(N(mu,sigma) || N(prior_mean, prior_std))
+ * (edward2/tensorflow/regularizers.py:175-186) into *kl_out (fp64 device scalar, zeroed by the caller) while mu/rho
+ * are in registers.  mean_out (optional) receives (w_dtype) mu — the Flipout mean operand. */
+int ed2_sample_normal_weights(const float* mu, const float* rho, ed2_noise eps, long long rows, long long cols,
+                              int mode, void* w, int w_dtype, int w_ld, void* mean_out, int mean_ld,
+                              double* kl_out, float kl_scale, float prior_mean, float prior_std, void* s);
+
+/* NormalKLDivergence (edward2/tensorflow/regularizers.py:166-186): *out += scale * sum_i KL(q_i || p).
+ * sigma = softplus(rho) + 1e-7.  Warp-shuffle + block reduction, fp64 final accumulation. */
+int ed2_normal_kl_fwd(const float* mu, const float* rho, long long n, float prior_mean, float prior_std,
+                      float scale, double* out, void* s);
+/* d_mu += g * scale * (mu - m)/s^2 ;  d_rho += g * scale * (sigma/s^2 - 1/sigma) * sigmoid(rho);
+ * g = *upstream (device scalar) or 1 if NULL. */
+int ed2_normal_kl_bwd(const float* mu, const float* rho, long long n, float prior_mean, float prior_std,
+                      float scale, const float* upstream, float* d_mu, float* d_rho, void* s);
+
+/* ------------------------------------------------------------------------------------------------
+ * DenseBatchEnsemble (edward2/tensorflow/layers/dense.py:551-584; edward2/jax/nn/dense.py:258-272)
+ *   y[e,n,:] = act( ((x[e,n,:] ∘ alpha[e]) W) ∘ gamma[e] + bias[e] ),   batch rows member-major.
+ * Saves for backward: xa = x∘alpha (dtype, [B][xa_ld]) and z = (x∘alpha)W (dtype, [B][z_ld]).
+ * w_lp: [I][w_ld] working copy of W in `dtype` (== w when dtype is fp32). */
+typedef struct {
+  int dtype;
+  int batch, in_dim, out_dim, ensemble_size;
+  int act;
+  const void* x; int x_ld;
+  const void* w_lp; int w_ld;
+  const float* alpha;     /* [E][in_dim]  */
+  const float* gamma;     /* [E][out_dim] */
+  const float* bias;      /* [E][out_dim] or NULL */
+  void* y; int y_ld;
+  void* xa; int xa_ld;    /* saved */
+  void* z; int z_ld;      /* saved; may be NULL for inference */
+} ed2_be_fwd_args;
+int ed2_be_dense_fwd(const ed2_be_fwd_args* a, void* stream);
+
+typedef struct {
+  int dtype;
+  int batch, in_dim, out_dim, ensemble_size;
+  int act;
+  const void* gy; int gy_ld;   /* dL/dy */
+  const void* y; int y_ld;
+  const void* z; int z_ld;
+  const void* x; int x_ld;
+  const void* xa; int xa_ld;
+  const void* w_lp; int w_ld;
+  const float* alpha; const float* gamma;
+  void* dz; int dz_ld;         /* workspace [B][out_dim] in dtype */
+  void* dxa; int dxa_ld;       /* workspace [B][in_dim] in dtype */
+  void* dx; int dx_ld;         /* NULL to skip (first layer) */
+  float* dw;                   /* [I][O] fp32, overwritten */
+  float* dalpha; float* dgamma; float* dbias; /* [E][.] fp32, overwritten; dbias may be NULL */
+} ed2_be_bwd_args;
+int ed2_be_dense_bwd(const ed2_be_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DenseRank1 (edward2/tensorflow/layers/dense.py:1096-1144), multiplicative perturbations:
+ *   r[b,:] = clip(mu_r[e] + sigma_r[e]*eps_r[b,:], -10, 10)   (per example, when sampled)
+ *   y = act( ((x ∘ r) W) ∘ s + bias[e] )
+ * If rho_r (rho_s) is NULL the fast weight is deterministic: r[b,:] = mu_r[e]. */
+typedef struct {
+  int dtype;
+  int batch, in_dim, out_dim, ensemble_size;
+  int act;
+  const void* x; int x_ld;
+  const void* w_lp; int w_ld;
+  const float* mu_r; const float* rho_r; ed2_noise eps_r;  /* [E][in_dim],  noise [B][in_dim]  */
+  const float* mu_s; const float* rho_s; ed2_noise eps_s;  /* [E][out_dim], noise [B][out_dim] */
+  const float* bias;                                        /* [E][out_dim] or NULL */
+  void* y; int y_ld;
+  void* xr; int xr_ld;      /* saved x∘r */
+  void* s_buf; int s_ld;    /* saved s [B][out_dim] in dtype */
+  void* z; int z_ld;        /* saved (x∘r)W; may be NULL for inference */
+} ed2_rank1_fwd_args;
+int ed2_rank1_dense_fwd(const ed2_rank1_fwd_args* a, void* stream);
+
+typedef struct {
+  int dtype;
+  int batch, in_dim, out_dim, ensemble_size;
+  int act;
+  const void* gy; int gy_ld;
+  const void* y; int y_ld;
+  const void* z; int z_ld;
+  const void* x; int x_ld;
+  const void* xr; int xr_ld;
+  const void* s_buf; int s_ld;
+  const void* w_lp; int w_ld;
+  const float* mu_r; const float* rho_r; ed2_noise eps_r;
+  const float* mu_s; const float* rho_s; ed2_noise eps_s;
+  void* dz; int dz_ld;
+  void* dxr; int dxr_ld;
+  void* dx; int dx_ld;
+  float* dw;
+  float* dmu_r; float* drho_r; float* dmu_s; float* drho_s; float* dbias; /* drho_* / dbias may be NULL */
+} ed2_rank1_bwd_args;
+int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DenseReparameterization (edward2/tensorflow/layers/dense.py:73-83):  y = act(x (mu + sigma∘eps) + b)
+ * w_lp receives the sampled kernel in `dtype` ([I][w_ld]); it stays L2-resident between the sampling pass
+ * and the GEMM and is re-used by the backward pass.  kl_out as in ed2_sample_normal_weights. */
+typedef struct {
+  int dtype;
+  int batch, in_dim, out_dim;
+  int act;
+  const void* x; int x_ld;
+  const float* mu; const float* rho; ed2_noise eps;   /* [I][O] fp32 */
+  const float* bias;                                   /* [O] fp32 or NULL */
+  void* w_lp; int w_ld;
+  void* y; int y_ld;
+  double* kl_out; float kl_scale; float prior_mean; float prior_std;
+} ed2_reparam_fwd_args;
+int ed2_reparam_dense_fwd(const ed2_reparam_fwd_args* a, void* stream);
+
+typedef struct {
+  int dtype;
+  int batch, in_dim, out_dim;
+  int act;
+  const void* gy; int gy_ld;
+  const void* y; int y_ld;
+  const void* x; int x_ld;
+  const void* w_lp; int w_ld;
+  const float* mu; const float* rho; ed2_noise eps;
+  void* gp; int gp_ld;        /* workspace [B][O] dtype: gy ∘ act'(y) */
+  void* dx; int dx_ld;        /* NULL to skip */
+  float* dmu; float* drho;    /* [I][O] fp32, overwritten: likelihood term + kl_grad_scale * dKL */
+  float* dbias;               /* [O] or NULL */
+  float kl_grad_scale; float prior_mean; float prior_std;   /* kl_grad_scale = 0 -> no KL term */
+} ed2_reparam_bwd_args;
+int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DenseFlipout (edward2/tensorflow/layers/dense.py:255-285):
+ *   y = act( x·mu + ((x ∘ S)·Delta) ∘ T + b ),  Delta = sigma ∘ eps,  S [B][I], T [B][O].
+ * S and T are noise tensors of kind "sign" (Philox draws ±1; injected values may be arbitrary floats — the
+ * reference's sign_output is Uniform[-1,3) for float inputs). */
+typedef struct {
+  int dtype;
+  int batch, in_dim, out_dim;
+  int act;
+  const void* x; int x_ld;
+  const float* mu; const float* rho; ed2_noise eps;
+  ed2_noise sign_in; ed2_noise sign_out;
+  const float* bias;
+  void* mu_lp; int mu_ld;        /* [I][O] dtype working copies (outputs, saved) */
+  void* delta_lp; int delta_ld;
+  void* xs; int xs_ld;           /* saved x∘S [B][I] dtype */
+  float* pert; int pert_ld;      /* workspace [B][O] fp32: ((x∘S)Delta)∘T */
+  void* y; int y_ld;
+  double* kl_out; float kl_scale; float prior_mean; float prior_std;
+} ed2_flipout_fwd_args;
+int ed2_flipout_dense_fwd(const ed2_flipout_fwd_args* a, void* stream);
+
+typedef struct {
+  int dtype;
+  int batch, in_dim, out_dim;
+  int act;
+  const void* gy; int gy_ld;
+  const void* y; int y_ld;
+  const void* x; int x_ld;
+  const void* xs; int xs_ld;
+  const void* mu_lp; int mu_ld;
+  const void* delta_lp; int delta_ld;
+  const float* mu; const float* rho; ed2_noise eps;
+  ed2_noise sign_in; ed2_noise sign_out;
+  void* gp; int gp_ld;          /* workspace [B][O] dtype */
+  void* gt; int gt_ld;          /* workspace [B][O] dtype: gp ∘ T */
+  float* tmp; int tmp_ld;       /* workspace [B][I] fp32 */
+  void* dx; int dx_ld;
+  float* dmu; float* drho; float* dbias;
+  float kl_grad_scale; float prior_mean; float prior_std;
+} ed2_flipout_bwd_args;
+int ed2_flipout_dense_bwd(const ed2_flipout_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SNGP head.
+ * SpectralNormalization (edward2/tensorflow/layers/normalization.py:369-391;
+ * edward2/jax/nn/normalization.py:159-178).  w [I][O] fp32, u [O], v [I] (updated in place).
+ *   mode 0 (TF):  v <- l2n(u Wᵀ); u <- l2n(v W); sigma = v W uᵀ; w_out = w * min(1, c/sigma)
+ *   mode 1 (JAX): v <- l2n(Wᵀ-apply); u_ <- W v; u <- l2n(u_); sigma = <u,u_>; w_out = w / max(sigma/c, 1)
+ * (for a Dense kernel both compute the same power iteration; they differ in the l2-normalise epsilon.)
+ * w_out may alias w (TF in-place semantics).  sigma_out: device scalar.  w_out_lp (optional): normalised
+ * kernel in bf16 with pitch w_lp_ld, written in the same pass.  workspace: >= (I + O + 8) floats. */
+int ed2_spectral_norm_update(const float* w, int in_dim, int out_dim, float* u, float* v, int iterations,
+                             float norm_multiplier, int mode, int update_uv, float* w_out, void* w_out_lp,
+                             int w_lp_ld, float* sigma_out, float* workspace, void* stream);
+
+/* LayerNormalization over the last axis (Keras defaults eps=1e-3, with gamma/beta; Flax eps=1e-6 without):
+ * y = (x - mean) / sqrt(var + eps) * gamma + beta   (edward2/tensorflow/layers/random_feature.py:167-171,252;
+ * edward2/jax/nn/random_feature.py:98-102).  gamma/beta may be NULL.  Or, with scale_only != 0,
+ * y = x * scale (random_feature.py:254-256). */
+int ed2_input_normalize(const void* x, int x_dtype, int x_ld, void* y, int y_dtype, int y_ld, long long rows,
+                        int cols, const float* gamma, const float* beta, float eps, int scale_only, float scale,
+                        void* stream);
+
+/* Random Fourier features (edward2/tensorflow/layers/random_feature.py:258-266;
+ * edward2/jax/nn/random_feature.py:209-214):  phi = cos(x W + b) * scale.
+ * wt: the frozen projection stored TRANSPOSED, [D][in_dim] in `dtype` (K-major B operand).
+ * pre (optional): fp32 [B][D] receives x W (without the bias) for the backward pass. */
+int ed2_rff_fwd(int dtype, const void* x, int x_ld, const void* wt, int wt_ld, const float* bias, float scale,
+                int batch, int in_dim, int num_features, void* phi, int phi_ld, int phi_dtype, float* pre,
+                int pre_ld, void* stream);
+/* dx = (-scale * sin(pre + b) ∘ dphi) Wᵀ  (W and b are frozen: only the input gradient exists).
+ * w: [in_dim][D] in `dtype`; gpre: workspace [B][D] in `dtype`. */
+int ed2_rff_bwd(int dtype, const void* dphi, int dphi_ld, int dphi_dtype, const float* pre, int pre_ld,
+                const float* bias, const void* w, int w_ld, float scale, int batch, int in_dim, int num_features,
+                void* gpre, int gpre_ld, void* dx, int dx_ld, int dx_dtype, void* stream);
+
+/* LaplaceRandomFeatureCovariance precision update (edward2/tensorflow/layers/random_feature.py:394-423;
+ * edward2/jax/nn/random_feature.py:350-362).  phi [B][D] in `dtype`.
+ *   momentum > 0:  P <- momentum * P + (1 - momentum) * phiᵀphi / batch_total
+ *   else        :  P <- P + phiᵀphi
+ * partial_out (optional): if non-NULL the un-blended local product phiᵀphi is written there instead and P is
+ * untouched — the data-parallel caller all-reduces it over NCCL and finishes with ed2_precision_blend. */
+int ed2_laplace_precision_update(int dtype, const void* phi, int phi_ld, int batch, int num_features,
+                                 float momentum, long long batch_total, float* precision, float* partial_out,
+                                 void* stream);
+int ed2_precision_blend(float* precision, const float* summed, int num_features, float momentum,
+                        long long batch_total, void* stream);
+
+/* Predictive variance diag(ridge * phi Sigma phiᵀ) (edward2/jax/nn/random_feature.py:393-404 diagonal form;
+ * edward2/tensorflow/layers/random_feature.py:482-485 takes its diagonal) fused with mean-field logits
+ * (edward2/tensorflow/layers/utils.py:379-424): if logits != NULL,
+ *   logits_out = logits / sqrt(1 + var * mean_field_factor)      (likelihood 0: logistic / gaussian)
+ *   logits_out = logits / exp(-var * mean_field_factor / 2)      (likelihood 1: poisson)
+ * sigma_lp: covariance matrix [D][D] in `dtype`.  var [B] fp32 (zeroed internally). */
+int ed2_predictive_variance(int dtype, const void* phi, int phi_ld, const void* sigma_lp, int sigma_ld, int batch,
+                            int num_features, float ridge, float* var, const float* logits, int num_classes,
+                            float mean_field_factor, int likelihood, float* logits_out, void* stream);
+int ed2_mean_field_logits(const float* logits, const float* var, int batch, int num_classes,
+                          float mean_field_factor, int likelihood, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ED2B200_H_ */
