@@ -106,7 +106,7 @@ class ReparamBwd(C.Structure):
         ("mu", _vp), ("rho", _vp), ("eps", Noise),
         ("gp", _vp), ("gp_ld", _i), ("dx", _vp), ("dx_ld", _i),
         ("dmu", _vp), ("drho", _vp), ("dbias", _vp),
-        ("kl_grad_scale", _f), ("prior_mean", _f), ("prior_std", _f),
+        ("kl_grad_scale", _f), ("prior_mean", _f), ("prior_std", _f), ("kl_upstream", _vp),
     ]
 
 
@@ -130,7 +130,7 @@ class FlipoutBwd(C.Structure):
         ("mu", _vp), ("rho", _vp), ("eps", Noise), ("sign_in", Noise), ("sign_out", Noise),
         ("gp", _vp), ("gp_ld", _i), ("gt", _vp), ("gt_ld", _i), ("tmp", _vp), ("tmp_ld", _i),
         ("dx", _vp), ("dx_ld", _i), ("dmu", _vp), ("drho", _vp), ("dbias", _vp),
-        ("kl_grad_scale", _f), ("prior_mean", _f), ("prior_std", _f),
+        ("kl_grad_scale", _f), ("prior_mean", _f), ("prior_std", _f), ("kl_upstream", _vp),
     ]
 
 
@@ -149,6 +149,7 @@ SIGNATURES = {
     "ed2_sample_normal_weights": (_i, [_vp, _vp, Noise, _ll, _ll, _i, _vp, _i, _i, _vp, _i, _vp, _f, _f, _f, _vp]),
     "ed2_normal_kl_fwd": (_i, [_vp, _vp, _ll, _f, _f, _f, _vp, _vp]),
     "ed2_normal_kl_bwd": (_i, [_vp, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "ed2_act_bwd": (_i, [_i, _vp, _i, _vp, _i, _ll, _i, _i, _vp, _i, _vp, _vp]),
     "ed2_be_dense_fwd": (_i, [C.POINTER(BeFwd), _vp]),
     "ed2_be_dense_bwd": (_i, [C.POINTER(BeBwd), _vp]),
     "ed2_rank1_dense_fwd": (_i, [C.POINTER(Rank1Fwd), _vp]),

@@ -129,6 +129,17 @@ int ed2_normal_kl_bwd(const float* mu, const float* rho, long long n, float pm, 
   return k_normal_kl_bwd(mu, rho, n, Prior{pm, ps}, scale, upstream, dmu, drho, S(s));
 }
 
+int ed2_act_bwd(int dtype, const void* gy, int gy_ld, const void* y, int y_ld, long long rows, int cols, int act,
+                void* gp, int gp_ld, float* dbias, void* s) {
+  ED2_TRY(check_dt(dtype));
+  BwdOutArgs o{};
+  o.dt = dtype; o.rows = rows; o.cols = cols; o.rows_per_member = static_cast<int>(rows); o.act = act; o.fast = 0;
+  o.gy = gy; o.gy_ld = gy_ld; o.y = y; o.y_ld = y_ld;
+  o.dz = gp; o.dz_ld = gp_ld;
+  o.dbias = dbias;
+  return k_bwd_out(o, S(s));
+}
+
 // ------------------------------------------------------------------------------------------ BatchEnsemble
 int ed2_be_dense_fwd(const ed2_be_fwd_args* a, void* stream) {
   ED2_TRY(check_dt(a->dtype));
@@ -249,7 +260,7 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
   e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
   ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, a->gp, a->gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
   ED2_TRY(k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
-                               a->kl_grad_scale, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho, s));
+                               a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho, s));
   if (a->dx != nullptr) {
     EpiParams e2 = epi_default();
     e2.out = a->dx; e2.out_ld = a->dx_ld; e2.out_dt = a->dtype;
@@ -303,7 +314,7 @@ int ed2_flipout_dense_bwd(const ed2_flipout_bwd_args* a, void* stream) {
   e1.out = a->drho; e1.out_ld = a->out_dim; e1.out_dt = kF32;
   ED2_TRY(gemm_xtg(a->dtype, a->xs, a->xs_ld, a->gt, a->gt_ld, a->batch, a->in_dim, a->out_dim, e1, s));
   ED2_TRY(k_normal_grad_finish(a->dmu, a->drho, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
-                               a->kl_grad_scale, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho, s));
+                               a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho, s));
   if (a->dx != nullptr) {
     // tmp = ((gp∘T) Δᵀ) ∘ S ;  dx = gp μᵀ + tmp
     EpiParams e2 = epi_default();

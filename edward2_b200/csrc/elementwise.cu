@@ -225,8 +225,9 @@ __global__ void normal_kl_bwd_kernel(const float* __restrict__ mu, const float* 
 }
 
 __global__ void normal_grad_finish_kernel(const float* d_mean, const float* d_pert, const float* __restrict__ mu,
-                                          const float* __restrict__ rho, Noise eps, long long n, float klg, Prior p,
-                                          float* dmu, float* drho) {
+                                          const float* __restrict__ rho, Noise eps, long long n, float klg_in,
+                                          const float* kl_upstream, Prior p, float* dmu, float* drho) {
+  const float klg = klg_in * (kl_upstream != nullptr ? *kl_upstream : 1.f);
   const float inv_s2 = 1.f / (p.stddev * p.stddev);
   const long long nblk = (n + 3) >> 2;
   for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
@@ -537,9 +538,10 @@ int k_normal_kl_bwd(const float* mu, const float* rho, long long n, Prior p, flo
 }
 
 int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* mu, const float* rho, Noise eps,
-                         long long n, float klg, Prior p, float* dmu, float* drho, cudaStream_t s) {
+                         long long n, float klg, const float* kl_upstream, Prior p, float* dmu, float* drho,
+                         cudaStream_t s) {
   if (n <= 0) return ED2_OK;
-  normal_grad_finish_kernel<<<grid_for((n + 3) / 4), kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, p, dmu, drho);
+  normal_grad_finish_kernel<<<grid_for((n + 3) / 4), kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
   count_launch();
   return check_launch("normal_grad_finish");
 }

@@ -1,0 +1,369 @@
+"""torch.autograd bindings of the layer-level C entry points (one C call per layer forward / backward).
+
+The forward and backward arithmetic is entirely in libed2b200.so; torch provides tensors, streams and the tape.
+All functions take 2-D row-major activations [B, features]; N-D inputs are flattened by the layer classes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from ._lib import BF16, F32
+
+
+def _compute_dt(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"compute dtype must be float32 or bfloat16, got {dtype}")
+
+
+def _aligned(t: torch.Tensor) -> bool:
+    if t.dim() != 2 or t.stride(1) != 1:
+        return False
+    if t.dtype == torch.float32:
+        return True
+    return t.data_ptr() % 16 == 0 and (t.stride(0) * t.element_size()) % 16 == 0
+
+
+def as_compute(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """`t` as a 2-D tensor of `dtype` whose rows satisfy the TMA alignment rule (copy only if needed)."""
+    if t.dtype == dtype and _aligned(t):
+        return t
+    if t.dtype not in (torch.float32, torch.bfloat16) or t.stride(-1) != 1:
+        t = t.contiguous().to(torch.float32)
+    return ops.cast(t, dtype)
+
+
+def _new(rows: int, cols: int, dtype: torch.dtype, device) -> torch.Tensor:
+    return _lib.empty_padded(rows, cols, dtype, device)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _ldn(t):
+    return 0 if t is None else _lib.ld(t)
+
+
+class Randomness:
+    """A noise tensor: injected values (parity tests) or a Philox (seed, stream) pair."""
+
+    def __init__(self, injected: torch.Tensor | None = None, seed: int = 0, stream: int = 0):
+        self.injected = None if injected is None else injected.to(torch.float32).contiguous()
+        self.seed, self.stream = int(seed), int(stream)
+
+    def c(self) -> _lib.Noise:
+        return _lib.noise(self.injected, self.seed, self.stream)
+
+
+# ------------------------------------------------------------------------------------------------- BatchEnsemble
+class BatchEnsembleDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, alpha, gamma, bias, act, ensemble_size, dtype):
+        lib = _lib.load()
+        B, I = x.shape
+        O = kernel.shape[1]
+        dev = x.device
+        xc = as_compute(x, dtype)
+        w_lp = kernel if dtype == torch.float32 else ops.cast(kernel, dtype)
+        need_grad = any(ctx.needs_input_grad)
+        y, xa = _new(B, O, dtype, dev), _new(B, I, dtype, dev)
+        z = _new(B, O, dtype, dev) if need_grad else None
+        a = _lib.BeFwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), B, I, O, ensemble_size, act
+        a.x, a.x_ld, a.w_lp, a.w_ld = xc.data_ptr(), _lib.ld(xc), w_lp.data_ptr(), _lib.ld(w_lp)
+        a.alpha, a.gamma, a.bias = alpha.data_ptr(), gamma.data_ptr(), _p(bias)
+        a.y, a.y_ld, a.xa, a.xa_ld, a.z, a.z_ld = y.data_ptr(), _lib.ld(y), xa.data_ptr(), _lib.ld(xa), _p(z), _ldn(z)
+        _lib.check(lib.ed2_be_dense_fwd(C.byref(a), _lib.stream_ptr()), "ed2_be_dense_fwd")
+        if need_grad:
+            ctx.save_for_backward(xc, xa, z, y, w_lp, alpha, gamma)
+            ctx.meta = (act, ensemble_size, dtype, bias is not None, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        xc, xa, z, y, w_lp, alpha, gamma = ctx.saved_tensors
+        act, E, dtype, has_bias, x_dtype = ctx.meta
+        B, I = xc.shape
+        O = y.shape[1]
+        dev = xc.device
+        gyc = as_compute(gy, dtype)
+        dz, dxa = _new(B, O, dtype, dev), _new(B, I, dtype, dev)
+        dx = _new(B, I, dtype, dev) if ctx.needs_input_grad[0] else None
+        dw = torch.empty(I, O, dtype=torch.float32, device=dev)
+        dalpha = torch.empty(E, I, dtype=torch.float32, device=dev)
+        dgamma = torch.empty(E, O, dtype=torch.float32, device=dev)
+        dbias = torch.empty(E, O, dtype=torch.float32, device=dev) if has_bias else None
+        a = _lib.BeBwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), B, I, O, E, act
+        a.gy, a.gy_ld, a.y, a.y_ld, a.z, a.z_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y), z.data_ptr(), _lib.ld(z)
+        a.x, a.x_ld, a.xa, a.xa_ld, a.w_lp, a.w_ld = xc.data_ptr(), _lib.ld(xc), xa.data_ptr(), _lib.ld(xa), w_lp.data_ptr(), _lib.ld(w_lp)
+        a.alpha, a.gamma = alpha.data_ptr(), gamma.data_ptr()
+        a.dz, a.dz_ld, a.dxa, a.dxa_ld, a.dx, a.dx_ld = dz.data_ptr(), _lib.ld(dz), dxa.data_ptr(), _lib.ld(dxa), _p(dx), _ldn(dx)
+        a.dw, a.dalpha, a.dgamma, a.dbias = dw.data_ptr(), dalpha.data_ptr(), dgamma.data_ptr(), _p(dbias)
+        _lib.check(lib.ed2_be_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_be_dense_bwd")
+        if dx is not None and dx.dtype != x_dtype:
+            dx = dx.to(x_dtype)
+        return dx, dw, dalpha, dgamma, dbias, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------- Rank-1
+class Rank1Dense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, mu_r, rho_r, mu_s, rho_s, bias, act, ensemble_size, dtype, eps_r, eps_s):
+        lib = _lib.load()
+        B, I = x.shape
+        O = kernel.shape[1]
+        dev = x.device
+        xc = as_compute(x, dtype)
+        w_lp = kernel if dtype == torch.float32 else ops.cast(kernel, dtype)
+        need_grad = any(ctx.needs_input_grad)
+        y, xr, s_buf = _new(B, O, dtype, dev), _new(B, I, dtype, dev), _new(B, O, dtype, dev)
+        z = _new(B, O, dtype, dev) if need_grad else None
+        a = _lib.Rank1Fwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), B, I, O, ensemble_size, act
+        a.x, a.x_ld, a.w_lp, a.w_ld = xc.data_ptr(), _lib.ld(xc), w_lp.data_ptr(), _lib.ld(w_lp)
+        a.mu_r, a.rho_r, a.eps_r = mu_r.data_ptr(), _p(rho_r), eps_r.c()
+        a.mu_s, a.rho_s, a.eps_s = mu_s.data_ptr(), _p(rho_s), eps_s.c()
+        a.bias = _p(bias)
+        a.y, a.y_ld, a.xr, a.xr_ld = y.data_ptr(), _lib.ld(y), xr.data_ptr(), _lib.ld(xr)
+        a.s_buf, a.s_ld, a.z, a.z_ld = s_buf.data_ptr(), _lib.ld(s_buf), _p(z), _ldn(z)
+        _lib.check(lib.ed2_rank1_dense_fwd(C.byref(a), _lib.stream_ptr()), "ed2_rank1_dense_fwd")
+        if need_grad:
+            saved = [xc, xr, s_buf, z, y, w_lp, mu_r, mu_s]
+            ctx.has_rho = (rho_r is not None, rho_s is not None)
+            if rho_r is not None:
+                saved.append(rho_r)
+            if rho_s is not None:
+                saved.append(rho_s)
+            ctx.save_for_backward(*saved)
+            ctx.meta = (act, ensemble_size, dtype, bias is not None, x.dtype, eps_r, eps_s)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        saved = list(ctx.saved_tensors)
+        xc, xr, s_buf, z, y, w_lp, mu_r, mu_s = saved[:8]
+        rest = saved[8:]
+        rho_r = rest.pop(0) if ctx.has_rho[0] else None
+        rho_s = rest.pop(0) if ctx.has_rho[1] else None
+        act, E, dtype, has_bias, x_dtype, eps_r, eps_s = ctx.meta
+        B, I = xc.shape
+        O = y.shape[1]
+        dev = xc.device
+        gyc = as_compute(gy, dtype)
+        dz, dxr = _new(B, O, dtype, dev), _new(B, I, dtype, dev)
+        dx = _new(B, I, dtype, dev) if ctx.needs_input_grad[0] else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        dw = torch.empty(I, O, **f32)
+        dmu_r, dmu_s = torch.empty(E, I, **f32), torch.empty(E, O, **f32)
+        drho_r = torch.empty(E, I, **f32) if rho_r is not None else None
+        drho_s = torch.empty(E, O, **f32) if rho_s is not None else None
+        dbias = torch.empty(E, O, **f32) if has_bias else None
+        a = _lib.Rank1Bwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), B, I, O, E, act
+        a.gy, a.gy_ld, a.y, a.y_ld, a.z, a.z_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y), z.data_ptr(), _lib.ld(z)
+        a.x, a.x_ld, a.xr, a.xr_ld = xc.data_ptr(), _lib.ld(xc), xr.data_ptr(), _lib.ld(xr)
+        a.s_buf, a.s_ld, a.w_lp, a.w_ld = s_buf.data_ptr(), _lib.ld(s_buf), w_lp.data_ptr(), _lib.ld(w_lp)
+        a.mu_r, a.rho_r, a.eps_r = mu_r.data_ptr(), _p(rho_r), eps_r.c()
+        a.mu_s, a.rho_s, a.eps_s = mu_s.data_ptr(), _p(rho_s), eps_s.c()
+        a.dz, a.dz_ld, a.dxr, a.dxr_ld, a.dx, a.dx_ld = dz.data_ptr(), _lib.ld(dz), dxr.data_ptr(), _lib.ld(dxr), _p(dx), _ldn(dx)
+        a.dw, a.dmu_r, a.drho_r, a.dmu_s, a.drho_s, a.dbias = dw.data_ptr(), dmu_r.data_ptr(), _p(drho_r), dmu_s.data_ptr(), _p(drho_s), _p(dbias)
+        _lib.check(lib.ed2_rank1_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_rank1_dense_bwd")
+        if dx is not None and dx.dtype != x_dtype:
+            dx = dx.to(x_dtype)
+        return dx, dw, dmu_r, drho_r, dmu_s, drho_s, dbias, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------- Reparameterization
+class ReparamDense(torch.autograd.Function):
+    """Returns (y, kl): kl = kl_scale * KL(q||p) accumulated in the sampling pass (0-dim fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, mu, rho, bias, act, dtype, eps, kl_scale, prior_mean, prior_std):
+        lib = _lib.load()
+        B, I = x.shape
+        O = mu.shape[1]
+        dev = x.device
+        xc = as_compute(x, dtype)
+        w_lp, y = _new(I, O, dtype, dev), _new(B, O, dtype, dev)
+        kl64 = torch.zeros((), dtype=torch.float64, device=dev) if kl_scale != 0 else None
+        a = _lib.ReparamFwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.act = _compute_dt(dtype), B, I, O, act
+        a.x, a.x_ld = xc.data_ptr(), _lib.ld(xc)
+        a.mu, a.rho, a.eps, a.bias = mu.data_ptr(), rho.data_ptr(), eps.c(), _p(bias)
+        a.w_lp, a.w_ld, a.y, a.y_ld = w_lp.data_ptr(), _lib.ld(w_lp), y.data_ptr(), _lib.ld(y)
+        a.kl_out, a.kl_scale, a.prior_mean, a.prior_std = _p(kl64), kl_scale, prior_mean, prior_std
+        _lib.check(lib.ed2_reparam_dense_fwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_fwd")
+        ctx.save_for_backward(xc, y, w_lp, mu, rho)
+        ctx.meta = (act, dtype, bias is not None, x.dtype, eps, kl_scale, prior_mean, prior_std)
+        ctx.set_materialize_grads(False)
+        kl = kl64.to(torch.float32) if kl64 is not None else torch.zeros((), device=dev)
+        return y, kl
+
+    @staticmethod
+    def backward(ctx, gy, gkl):
+        lib = _lib.load()
+        xc, y, w_lp, mu, rho = ctx.saved_tensors
+        act, dtype, has_bias, x_dtype, eps, kl_scale, pm, ps = ctx.meta
+        B, I = xc.shape
+        O = y.shape[1]
+        dev = xc.device
+        if gy is None:
+            gy = torch.zeros(B, O, dtype=dtype, device=dev)
+        gyc = as_compute(gy, dtype)
+        gp = _new(B, O, dtype, dev)
+        dx = _new(B, I, dtype, dev) if ctx.needs_input_grad[0] else None
+        dmu = torch.empty(I, O, dtype=torch.float32, device=dev)
+        drho = torch.empty(I, O, dtype=torch.float32, device=dev)
+        dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
+        up = gkl.to(torch.float32).reshape(1).contiguous() if gkl is not None else None
+        a = _lib.ReparamBwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.act = _compute_dt(dtype), B, I, O, act
+        a.gy, a.gy_ld, a.y, a.y_ld, a.x, a.x_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y), xc.data_ptr(), _lib.ld(xc)
+        a.w_lp, a.w_ld = w_lp.data_ptr(), _lib.ld(w_lp)
+        a.mu, a.rho, a.eps = mu.data_ptr(), rho.data_ptr(), eps.c()
+        a.gp, a.gp_ld, a.dx, a.dx_ld = gp.data_ptr(), _lib.ld(gp), _p(dx), _ldn(dx)
+        a.dmu, a.drho, a.dbias = dmu.data_ptr(), drho.data_ptr(), _p(dbias)
+        a.kl_grad_scale = kl_scale if gkl is not None else 0.0
+        a.prior_mean, a.prior_std, a.kl_upstream = pm, ps, _p(up)
+        _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd")
+        if dx is not None and dx.dtype != x_dtype:
+            dx = dx.to(x_dtype)
+        return dx, dmu, drho, dbias, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------- Flipout
+class FlipoutDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mu, rho, bias, act, dtype, eps, sign_in, sign_out, kl_scale, prior_mean, prior_std):
+        lib = _lib.load()
+        B, I = x.shape
+        O = mu.shape[1]
+        dev = x.device
+        xc = as_compute(x, dtype)
+        mu_lp, delta_lp = _new(I, O, dtype, dev), _new(I, O, dtype, dev)
+        xs, y = _new(B, I, dtype, dev), _new(B, O, dtype, dev)
+        pert = torch.empty(B, _lib.pad8(O), dtype=torch.float32, device=dev)
+        kl64 = torch.zeros((), dtype=torch.float64, device=dev) if kl_scale != 0 else None
+        a = _lib.FlipoutFwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.act = _compute_dt(dtype), B, I, O, act
+        a.x, a.x_ld = xc.data_ptr(), _lib.ld(xc)
+        a.mu, a.rho, a.eps = mu.data_ptr(), rho.data_ptr(), eps.c()
+        a.sign_in, a.sign_out, a.bias = sign_in.c(), sign_out.c(), _p(bias)
+        a.mu_lp, a.mu_ld, a.delta_lp, a.delta_ld = mu_lp.data_ptr(), _lib.ld(mu_lp), delta_lp.data_ptr(), _lib.ld(delta_lp)
+        a.xs, a.xs_ld, a.pert, a.pert_ld = xs.data_ptr(), _lib.ld(xs), pert.data_ptr(), pert.stride(0)
+        a.y, a.y_ld = y.data_ptr(), _lib.ld(y)
+        a.kl_out, a.kl_scale, a.prior_mean, a.prior_std = _p(kl64), kl_scale, prior_mean, prior_std
+        _lib.check(lib.ed2_flipout_dense_fwd(C.byref(a), _lib.stream_ptr()), "ed2_flipout_dense_fwd")
+        ctx.save_for_backward(xc, xs, y, mu_lp, delta_lp, mu, rho)
+        ctx.meta = (act, dtype, bias is not None, x.dtype, eps, sign_in, sign_out, kl_scale, prior_mean, prior_std)
+        ctx.set_materialize_grads(False)
+        kl = kl64.to(torch.float32) if kl64 is not None else torch.zeros((), device=dev)
+        return y, kl
+
+    @staticmethod
+    def backward(ctx, gy, gkl):
+        lib = _lib.load()
+        xc, xs, y, mu_lp, delta_lp, mu, rho = ctx.saved_tensors
+        act, dtype, has_bias, x_dtype, eps, sign_in, sign_out, kl_scale, pm, ps = ctx.meta
+        B, I = xc.shape
+        O = y.shape[1]
+        dev = xc.device
+        if gy is None:
+            gy = torch.zeros(B, O, dtype=dtype, device=dev)
+        gyc = as_compute(gy, dtype)
+        gp, gt = _new(B, O, dtype, dev), _new(B, O, dtype, dev)
+        need_dx = ctx.needs_input_grad[0]
+        dx = _new(B, I, dtype, dev) if need_dx else None
+        tmp = torch.empty(B, _lib.pad8(I), dtype=torch.float32, device=dev) if need_dx else None
+        dmu = torch.empty(I, O, dtype=torch.float32, device=dev)
+        drho = torch.empty(I, O, dtype=torch.float32, device=dev)
+        dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
+        up = gkl.to(torch.float32).reshape(1).contiguous() if gkl is not None else None
+        a = _lib.FlipoutBwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.act = _compute_dt(dtype), B, I, O, act
+        a.gy, a.gy_ld, a.y, a.y_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y)
+        a.x, a.x_ld, a.xs, a.xs_ld = xc.data_ptr(), _lib.ld(xc), xs.data_ptr(), _lib.ld(xs)
+        a.mu_lp, a.mu_ld, a.delta_lp, a.delta_ld = mu_lp.data_ptr(), _lib.ld(mu_lp), delta_lp.data_ptr(), _lib.ld(delta_lp)
+        a.mu, a.rho, a.eps, a.sign_in, a.sign_out = mu.data_ptr(), rho.data_ptr(), eps.c(), sign_in.c(), sign_out.c()
+        a.gp, a.gp_ld, a.gt, a.gt_ld = gp.data_ptr(), _lib.ld(gp), gt.data_ptr(), _lib.ld(gt)
+        a.tmp, a.tmp_ld = _p(tmp), 0 if tmp is None else tmp.stride(0)
+        a.dx, a.dx_ld = _p(dx), _ldn(dx)
+        a.dmu, a.drho, a.dbias = dmu.data_ptr(), drho.data_ptr(), _p(dbias)
+        a.kl_grad_scale = kl_scale if gkl is not None else 0.0
+        a.prior_mean, a.prior_std, a.kl_upstream = pm, ps, _p(up)
+        _lib.check(lib.ed2_flipout_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_flipout_dense_bwd")
+        if dx is not None and dx.dtype != x_dtype:
+            dx = dx.to(x_dtype)
+        return dx, dmu, drho, dbias, None, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------- KL regulariser
+class NormalKL(torch.autograd.Function):
+    """scale * sum KL(N(mu, softplus(rho)+1e-7) || N(m, s)) as a 0-dim fp32 tensor (regularizers.py:175-186)."""
+
+    @staticmethod
+    def forward(ctx, mu, rho, prior_mean, prior_std, scale):
+        kl = ops.normal_kl(mu, rho, prior_mean, prior_std, scale)
+        ctx.save_for_backward(mu, rho)
+        ctx.meta = (prior_mean, prior_std, scale)
+        return kl.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        mu, rho = ctx.saved_tensors
+        pm, ps, scale = ctx.meta
+        dmu, drho = torch.zeros_like(mu), torch.zeros_like(rho)
+        ops.normal_kl_bwd(mu, rho, dmu, drho, pm, ps, scale, upstream=g.to(torch.float32).reshape(1).contiguous())
+        return dmu, drho, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------- plain dense on the GEMM
+class Dense(torch.autograd.Function):
+    """y = act(x W + b) on the tcgen05 GEMM (the deterministic layer wrapped by SpectralNormalization and the
+    GP output layer).  `w_scale` (0-dim tensor or None) multiplies dW in backward: SpectralNormalization's
+    W_hat = W * factor with the factor under stop_gradient (edward2/jax/nn/normalization.py:177-178)."""
+
+    @staticmethod
+    def forward(ctx, x, w_eff, bias, act, dtype, w_scale):
+        B, I = x.shape
+        O = w_eff.shape[1]
+        xc = as_compute(x, dtype)
+        w_lp = w_eff if (dtype == torch.float32 and w_eff.dtype == torch.float32) else as_compute(w_eff, dtype)
+        y = _new(B, O, dtype, x.device)
+        b2 = bias.reshape(1, -1) if bias is not None else None
+        ops.gemm(xc, w_lp, B, O, I, major_a=ops.MAJOR_K, major_b=ops.MAJOR_MN, out=y, act=act, col_bias=b2)
+        ctx.save_for_backward(xc, y, w_lp, w_scale if w_scale is not None else torch.empty(0, device=x.device))
+        ctx.meta = (act, dtype, bias is not None, x.dtype, w_scale is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, y, w_lp, w_scale = ctx.saved_tensors
+        act, dtype, has_bias, x_dtype, has_scale = ctx.meta
+        B, I = xc.shape
+        O = y.shape[1]
+        dev = xc.device
+        gyc = as_compute(gy, dtype)
+        gp = _new(B, O, dtype, dev)
+        dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
+        ops.act_bwd(gyc, y, gp, dbias, act)
+        dw = torch.empty(I, O, dtype=torch.float32, device=dev)
+        ops.gemm(xc, gp, I, O, B, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=dw)
+        if has_scale:
+            dw = dw * w_scale
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _new(B, I, dtype, dev)
+            ops.gemm(gp, w_lp, B, I, O, major_a=ops.MAJOR_K, major_b=ops.MAJOR_K, out=dx)
+            if dx.dtype != x_dtype:
+                dx = dx.to(x_dtype)
+        return dx, dw, dbias, None, None, None

@@ -95,3 +95,11 @@ def normal_kl_bwd(mu, rho, dmu, drho, prior_mean=0.0, prior_std=1.0, scale=1.0, 
     _lib.check(lib.ed2_normal_kl_bwd(mu.data_ptr(), rho.data_ptr(), mu.numel(), prior_mean, prior_std, scale,
                                      _lib.ptr(upstream), dmu.data_ptr(), drho.data_ptr(), _lib.stream_ptr()),
                "normal_kl_bwd")
+
+
+def act_bwd(gy: torch.Tensor, y: torch.Tensor, gp: torch.Tensor, dbias: torch.Tensor | None, act: int) -> None:
+    """gp = gy ∘ act'(y); dbias = column sums of gp."""
+    lib = _lib.load()
+    rows, cols = y.shape
+    _lib.check(lib.ed2_act_bwd(_lib.dt_of(y), gy.data_ptr(), _lib.ld(gy), y.data_ptr(), _lib.ld(y), rows, cols, act,
+                               gp.data_ptr(), _lib.ld(gp), _lib.ptr(dbias), _lib.stream_ptr()), "ed2_act_bwd")

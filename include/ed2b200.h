@@ -119,6 +119,11 @@ int ed2_normal_kl_fwd(const float* mu, const float* rho, long long n, float prio
 int ed2_normal_kl_bwd(const float* mu, const float* rho, long long n, float prior_mean, float prior_std,
                       float scale, const float* upstream, float* d_mu, float* d_rho, void* s);
 
+/* gp = gy ∘ act'(y) (relu' evaluated on the output);  dbias[n] = sum_m gp[m,n] (optional, overwritten).
+ * The output-side backward step of a plain dense layer (the layer SpectralNormalization wraps). */
+int ed2_act_bwd(int dtype, const void* gy, int gy_ld, const void* y, int y_ld, long long rows, int cols, int act,
+                void* gp, int gp_ld, float* dbias, void* s);
+
 /* ------------------------------------------------------------------------------------------------
  * DenseBatchEnsemble (edward2/tensorflow/layers/dense.py:551-584; edward2/jax/nn/dense.py:258-272)
  *   y[e,n,:] = act( ((x[e,n,:] ∘ alpha[e]) W) ∘ gamma[e] + bias[e] ),   batch rows member-major.
@@ -231,6 +236,7 @@ typedef struct {
   float* dmu; float* drho;    /* [I][O] fp32, overwritten: likelihood term + kl_grad_scale * dKL */
   float* dbias;               /* [O] or NULL */
   float kl_grad_scale; float prior_mean; float prior_std;   /* kl_grad_scale = 0 -> no KL term */
+  const float* kl_upstream;   /* optional device scalar multiplying kl_grad_scale (dLoss/dKL) */
 } ed2_reparam_bwd_args;
 int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream);
 
@@ -274,6 +280,7 @@ typedef struct {
   void* dx; int dx_ld;
   float* dmu; float* drho; float* dbias;
   float kl_grad_scale; float prior_mean; float prior_std;
+  const float* kl_upstream;
 } ed2_flipout_bwd_args;
 int ed2_flipout_dense_bwd(const ed2_flipout_bwd_args* a, void* stream);
 
