@@ -4,3 +4,5 @@
 All arithmetic runs in libed2b200.so (hand-written CUDA behind the C ABI of include/ed2b200.h).
 """
 __version__ = "0.1.0"
+
+from . import constraints, initializers, layers, nn, regularizers  # noqa: E402,F401

@@ -160,6 +160,7 @@ SIGNATURES = {
     "ed2_flipout_dense_bwd": (_i, [C.POINTER(FlipoutBwd), _vp]),
     "ed2_spectral_norm_update": (_i, [_vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "ed2_input_normalize": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _vp, _f, _i, _f, _vp]),
+    "ed2_layernorm_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _f, _vp, _i, _i, _vp, _vp, _vp]),
     "ed2_rff_fwd": (_i, [_i, _vp, _i, _vp, _i, _vp, _f, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
     "ed2_rff_bwd": (_i, [_i, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _f, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "ed2_laplace_precision_update": (_i, [_i, _vp, _i, _i, _i, _f, _ll, _vp, _vp, _vp]),

@@ -352,6 +352,15 @@ int ed2_input_normalize(const void* x, int x_dtype, int x_ld, void* y, int y_dty
   return k_input_normalize(x, x_dtype, x_ld, y, y_dtype, y_ld, rows, cols, gamma, beta, eps, scale_only, scale, S(stream));
 }
 
+int ed2_layernorm_bwd(const void* x, int x_dtype, int x_ld, const void* dy, int dy_dtype, int dy_ld, long long rows,
+                      int cols, const float* gamma, float eps, void* dx, int dx_dtype, int dx_ld, float* dgamma,
+                      float* dbeta, void* stream) {
+  ED2_TRY(check_dt(x_dtype));
+  ED2_TRY(check_dt(dy_dtype));
+  return k_layernorm_bwd(x, x_dtype, x_ld, dy, dy_dtype, dy_ld, rows, cols, gamma, eps, dx, dx_dtype, dx_ld, dgamma,
+                         dbeta, S(stream));
+}
+
 int ed2_rff_fwd(int dtype, const void* x, int x_ld, const void* wt, int wt_ld, const float* bias, float scale, int batch,
                 int in_dim, int num_features, void* phi, int phi_ld, int phi_dtype, float* pre, int pre_ld, void* stream) {
   ED2_TRY(check_dt(dtype));

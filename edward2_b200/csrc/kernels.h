@@ -91,6 +91,9 @@ int k_spectral_norm(const float* w, int in_dim, int out_dim, float* u, float* v,
 int k_input_normalize(const void* x, int xdt, long long x_ld, void* y, int ydt, long long y_ld, long long rows,
                       int cols, const float* gamma, const float* beta, float eps, int scale_only, float scale,
                       cudaStream_t s);
+int k_layernorm_bwd(const void* x, int xdt, long long x_ld, const void* dy, int dydt, long long dy_ld, long long rows,
+                    int cols, const float* gamma, float eps, void* dx, int dxdt, long long dx_ld, float* dgamma,
+                    float* dbeta, cudaStream_t s);
 int k_precision_blend(float* precision, const float* summed, long long n, float momentum, long long batch_total,
                       cudaStream_t s);
 int k_mean_field(const float* logits, const float* var, long long batch, int classes, float factor, int likelihood,

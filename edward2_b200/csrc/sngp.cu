@@ -177,6 +177,65 @@ __global__ void __launch_bounds__(kBlock) input_normalize_kernel(const void* x, 
   }
 }
 
+
+// LayerNorm backward, one warp per row; column sums for dgamma / dbeta are accumulated in shared memory per block
+// and flushed with one global atomic per column per block.
+//   xhat = (x - mean) * inv;  g = dy * gamma;  dx = inv * (g - mean(g) - xhat * mean(g * xhat))
+__global__ void __launch_bounds__(kBlock) layernorm_bwd_kernel(const void* x, int xdt, long long x_ld, const void* dy,
+                                                               int dydt, long long dy_ld, long long rows, int cols,
+                                                               const float* gamma, float eps, void* dx, int dxdt,
+                                                               long long dx_ld, float* dgamma, float* dbeta) {
+  extern __shared__ float sh[];
+  float* sg = sh;
+  float* sb = sh + cols;
+  const bool want_param = dgamma != nullptr || dbeta != nullptr;
+  if (want_param) {
+    for (int c = threadIdx.x; c < cols; c += kBlock) { sg[c] = 0.f; sb[c] = 0.f; }
+    __syncthreads();
+  }
+  const long long warp = (blockIdx.x * (long long)kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * kBlock) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += ld1(x, xdt, r * x_ld + c);
+    const float mean = warp_sum(s) / cols;
+    float q = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float d = ld1(x, xdt, r * x_ld + c) - mean;
+      q += d * d;
+    }
+    const float inv = rsqrtf(warp_sum(q) / cols + eps);
+    float sum_g = 0.f, sum_gx = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float xh = (ld1(x, xdt, r * x_ld + c) - mean) * inv;
+      const float d = ld1(dy, dydt, r * dy_ld + c);
+      const float g = d * (gamma != nullptr ? gamma[c] : 1.f);
+      sum_g += g;
+      sum_gx += g * xh;
+      if (want_param) {
+        atomicAdd(&sg[c], d * xh);
+        atomicAdd(&sb[c], d);
+      }
+    }
+    const float mg = warp_sum(sum_g) / cols, mgx = warp_sum(sum_gx) / cols;
+    if (dx != nullptr) {
+      for (int c = lane; c < cols; c += 32) {
+        const float xh = (ld1(x, xdt, r * x_ld + c) - mean) * inv;
+        const float g = ld1(dy, dydt, r * dy_ld + c) * (gamma != nullptr ? gamma[c] : 1.f);
+        st1(dx, dxdt, r * dx_ld + c, inv * (g - mg - xh * mgx));
+      }
+    }
+  }
+  if (want_param) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += kBlock) {
+      if (dgamma != nullptr) atomicAdd(dgamma + c, sg[c]);
+      if (dbeta != nullptr) atomicAdd(dbeta + c, sb[c]);
+    }
+  }
+}
+
 __global__ void precision_blend_kernel(float* p, const float* __restrict__ summed, long long n, float momentum,
                                        float inv_batch) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -263,6 +322,26 @@ int k_input_normalize(const void* x, int xdt, long long x_ld, void* y, int ydt, 
   input_normalize_kernel<<<g, kBlock, 0, s>>>(x, xdt, x_ld, y, ydt, y_ld, rows, cols, gamma, beta, eps, scale_only, scale);
   count_launch();
   return check_launch("input_normalize");
+}
+
+
+int k_layernorm_bwd(const void* x, int xdt, long long x_ld, const void* dy, int dydt, long long dy_ld, long long rows,
+                    int cols, const float* gamma, float eps, void* dx, int dxdt, long long dx_ld, float* dgamma,
+                    float* dbeta, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  if (cols > 8192) return set_error(ED2_ERR_BAD_SHAPE, "layernorm_bwd: feature dimension %d > 8192", cols);
+  if (dgamma) cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, s);
+  if (dbeta) cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, s);
+  const int g = static_cast<int>(std::min<long long>(148 * 2, (rows + 7) / 8));
+  const size_t smem = 2 * sizeof(float) * (size_t)cols;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 8192);
+    attr = true;
+  }
+  layernorm_bwd_kernel<<<g, kBlock, smem, s>>>(x, xdt, x_ld, dy, dydt, dy_ld, rows, cols, gamma, eps, dx, dxdt, dx_ld, dgamma, dbeta);
+  count_launch();
+  return check_launch("layernorm_bwd");
 }
 
 int k_precision_blend(float* precision, const float* summed, long long n, float momentum, long long batch_total,

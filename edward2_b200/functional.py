@@ -367,3 +367,52 @@ class Dense(torch.autograd.Function):
             if dx.dtype != x_dtype:
                 dx = dx.to(x_dtype)
         return dx, dw, dbias, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------- SNGP head
+class LayerNorm(torch.autograd.Function):
+    """LayerNormalization over the last axis (Keras: eps=1e-3 with gamma/beta; Flax: eps=1e-6 without)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, out_dtype):
+        xc = x if (x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.float32, torch.bfloat16)) else x.contiguous().float()
+        y = ops.input_normalize(xc, out_dtype, gamma, beta, eps)
+        ctx.save_for_backward(xc, gamma if gamma is not None else torch.empty(0, device=x.device))
+        ctx.meta = (eps, gamma is not None, beta is not None, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, gamma = ctx.saved_tensors
+        eps, has_gamma, has_beta, x_dtype = ctx.meta
+        dyc = dy if (dy.stride(1) == 1 and dy.dtype in (torch.float32, torch.bfloat16)) else dy.contiguous().float()
+        dx, dgamma, dbeta = ops.layernorm_bwd(xc, dyc, gamma if has_gamma else None, eps,
+                                              want_dx=ctx.needs_input_grad[0], want_params=has_gamma or has_beta)
+        if dx is not None and dx.dtype != x_dtype:
+            dx = dx.to(x_dtype)
+        return dx, (dgamma if has_gamma else None), (dbeta if has_beta else None), None, None
+
+
+class RandomFourierFeatures(torch.autograd.Function):
+    """phi = scale * cos(x W + b) with W, b frozen (random_feature.py:258-266; jax random_feature.py:209-214).
+    w_t: Wᵀ [D, d] and w: [d, D], both in the compute dtype (frozen copies made once by the layer)."""
+
+    @staticmethod
+    def forward(ctx, x, w_t, w, bias, scale, dtype, phi_dtype):
+        xc = as_compute(x, dtype)
+        need = ctx.needs_input_grad[0]
+        phi, pre = ops.rff_fwd(xc, w_t, bias, scale, phi_dtype, want_pre=need)
+        if need:
+            ctx.save_for_backward(pre, bias, w)
+            ctx.meta = (scale, x.dtype, dtype)
+        return phi
+
+    @staticmethod
+    def backward(ctx, dphi):
+        pre, bias, w = ctx.saved_tensors
+        scale, x_dtype, dtype = ctx.meta
+        dphic = dphi if (dphi.stride(1) == 1 and dphi.dtype in (torch.float32, torch.bfloat16)) else dphi.contiguous().float()
+        dx = ops.rff_bwd(dphic, pre, bias, w, scale, dtype)
+        if dx.dtype != x_dtype:
+            dx = dx.to(x_dtype)
+        return dx, None, None, None, None, None, None

@@ -1,0 +1,339 @@
+"""`ed.layers` dense layers on libed2b200: DenseReparameterization, DenseFlipout, DenseBatchEnsemble, DenseRank1 and
+the deterministic Dense that SpectralNormalization wraps.
+
+Constructor arguments, call signatures, error behaviour and `.losses` follow
+/root/reference/edward2/tensorflow/layers/dense.py (:33-83, :227-285, :470-607, :991-1175).  Parameters are fp32
+masters; `dtype` selects the compute dtype ('float32' or 'bfloat16').
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import constraints, functional as F, initializers, ops, regularizers
+from .base import Layer, flatten_batch
+
+# Philox stream ids of the noise tensors of one layer call
+S_KERNEL, S_BIAS, S_SIGN_IN, S_SIGN_OUT, S_R, S_S = 0, 1, 2, 3, 4, 5
+
+
+def _is_trainable(init) -> bool:
+    return isinstance(init, initializers.TrainableInitializer)
+
+
+def _make_weight(layer: nn.Module, name: str, shape, initializer, device):
+    """`add_weight` semantics of edward2/tensorflow/layers/utils.py:38-75: a trainable initializer becomes the
+    weight's variational posterior (it owns mean / stddev); a plain initializer yields a Parameter."""
+    if _is_trainable(initializer):
+        if not initializer.built:
+            initializer.build(tuple(shape), device=device)
+        return None  # the initializer module (already an attribute of the layer) owns <name>/mean, <name>/stddev
+    p = nn.Parameter(initializer(tuple(shape)).to(device=device, dtype=torch.float32))
+    layer.register_parameter(name, p)
+    return p
+
+
+class _FusedKL:
+    """KL tensor produced by the sampling pass of the last forward, valid while (mean, rho) are unchanged."""
+
+    def __init__(self):
+        self.value = None
+        self.versions = None
+
+    def set(self, kl, mean, rho):
+        self.value, self.versions = kl, (mean._version, rho._version)
+
+    def get(self, mean, rho):
+        if self.value is not None and self.versions == (mean._version, rho._version):
+            return self.value
+        return None
+
+
+class Dense(Layer):
+    """Deterministic densely-connected layer (the tf.keras.layers.Dense the reference wraps / subclasses)."""
+
+    def __init__(self, units, activation=None, use_bias=True, kernel_initializer="glorot_uniform",
+                 bias_initializer="zeros", kernel_regularizer=None, bias_regularizer=None, activity_regularizer=None,
+                 kernel_constraint=None, bias_constraint=None, **kwargs):
+        super().__init__(**kwargs)
+        self.units = int(units)
+        self.activation = activation
+        self._act = ops.act_id(activation)
+        self.use_bias = use_bias
+        self.kernel_initializer = initializers.get(kernel_initializer)
+        self.bias_initializer = initializers.get(bias_initializer)
+        self.kernel_regularizer = regularizers.get(kernel_regularizer)
+        self.bias_regularizer = regularizers.get(bias_regularizer)
+        self._w_scale = None  # set by the JAX-style SpectralNormalization (stop-gradient factor)
+
+    def build(self, input_shape):
+        dev = self._device
+        self.kernel = nn.Parameter(self.kernel_initializer((input_shape[-1], self.units)).to(dev))
+        self.bias = nn.Parameter(self.bias_initializer((self.units,)).to(dev)) if self.use_bias else None
+        self.built = True
+
+    def call(self, inputs, training=None):
+        x, lead = flatten_batch(inputs)
+        y = F.Dense.apply(x, self.kernel, self.bias, self._act, self.compute_dtype, None)
+        return y.reshape(*lead, self.units)
+
+    @property
+    def losses(self):
+        out = []
+        if self.kernel_regularizer is not None:
+            out.append(self.kernel_regularizer(self.kernel))
+        if self.bias_regularizer is not None and self.bias is not None:
+            out.append(self.bias_regularizer(self.bias))
+        return out
+
+    def get_config(self):
+        cfg = super().get_config()
+        cfg.update(units=self.units, activation=self.activation, use_bias=self.use_bias,
+                   kernel_initializer=initializers.serialize(self.kernel_initializer),
+                   bias_initializer=initializers.serialize(self.bias_initializer))
+        return cfg
+
+
+class DenseReparameterization(Layer):
+    """Bayesian dense layer estimated via reparameterization (dense.py:33-83): y = act(x (mu + sigma∘eps) + b) with
+    one kernel sample per call, drawn in-kernel; `.losses` holds the KL regularizer (fused into the sampling pass)."""
+
+    def __init__(self, units, activation=None, use_bias=True, kernel_initializer="trainable_normal",
+                 bias_initializer="zero", kernel_regularizer="normal_kl_divergence", bias_regularizer=None,
+                 activity_regularizer=None, **kwargs):
+        super().__init__(**kwargs)
+        self.units = int(units)
+        self.activation = activation
+        self._act = ops.act_id(activation)
+        self.use_bias = use_bias
+        self.kernel_initializer = initializers.get(kernel_initializer)
+        self.bias_initializer = initializers.get(bias_initializer)
+        self.kernel_regularizer = regularizers.get(kernel_regularizer)
+        self.bias_regularizer = regularizers.get(bias_regularizer)
+        if activity_regularizer is not None:
+            raise NotImplementedError("activity_regularizer is outside the hot path")
+        self._kl = _FusedKL()
+
+    def build(self, input_shape):
+        dev = self._device
+        in_dim = input_shape[-1]
+        self.kernel = _make_weight(self, "kernel", (in_dim, self.units), self.kernel_initializer, dev)
+        self.bias = _make_weight(self, "bias", (self.units,), self.bias_initializer, dev) if self.use_bias else None
+        self.built = True
+
+    # -- weights ---------------------------------------------------------------------------------------------
+    def _kernel_params(self):
+        if _is_trainable(self.kernel_initializer):
+            return self.kernel_initializer.params()
+        return self.kernel, None
+
+    def _bias_value(self):
+        """dense.py:73-78: a trainable bias initializer is re-sampled on every call (small vector: host-side
+        composition of the Philox draw with autograd through mean / rho)."""
+        if not self.use_bias:
+            return None
+        if _is_trainable(self.bias_initializer):
+            mean, rho = self.bias_initializer.params()
+            if rho is None:
+                return mean
+            nz = self._noise("bias_eps", S_BIAS)
+            eps = nz.injected if nz.injected is not None else ops.philox("normal", mean.numel(), nz.seed, nz.stream, mean.device)
+            return mean + (torch.nn.functional.softplus(rho) + constraints.EPSILON) * eps.reshape(mean.shape)
+        return self.bias
+
+    def _fused_kl_args(self):
+        r = self.kernel_regularizer
+        if isinstance(r, regularizers.NormalKLDivergence):
+            return r.scale_factor, r.mean, r.stddev
+        return 0.0, 0.0, 1.0
+
+    def call(self, inputs, training=None):
+        x, lead = flatten_batch(inputs)
+        mean, rho = self._kernel_params()
+        bias = self._bias_value()
+        if rho is None:  # deterministic kernel: ordinary dense layer
+            y = F.Dense.apply(x, mean, bias, self._act, self.compute_dtype, None)
+            return y.reshape(*lead, self.units)
+        kl_scale, pm, ps = self._fused_kl_args()
+        y, kl = F.ReparamDense.apply(x, mean, rho, bias, self._act, self.compute_dtype,
+                                     self._noise("eps", S_KERNEL), kl_scale, pm, ps)
+        if kl_scale != 0.0:
+            self._kl.set(kl, mean, rho)
+        return y.reshape(*lead, self.units)
+
+    @property
+    def losses(self):
+        out = []
+        if self.kernel_regularizer is not None and _is_trainable(self.kernel_initializer):
+            mean, rho = self._kernel_params()
+            fused = self._kl.get(mean, rho) if rho is not None else None
+            out.append(fused if fused is not None else self.kernel_regularizer(self.kernel_initializer))
+        if self.bias_regularizer is not None and self.use_bias and _is_trainable(self.bias_initializer):
+            out.append(self.bias_regularizer(self.bias_initializer))
+        return out
+
+    def get_config(self):
+        cfg = super().get_config()
+        cfg.update(units=self.units, activation=self.activation, use_bias=self.use_bias,
+                   kernel_initializer=initializers.serialize(self.kernel_initializer),
+                   bias_initializer=initializers.serialize(self.bias_initializer),
+                   kernel_regularizer=regularizers.serialize(self.kernel_regularizer),
+                   bias_regularizer=regularizers.serialize(self.bias_regularizer))
+        return cfg
+
+
+class DenseFlipout(DenseReparameterization):
+    """Bayesian dense layer estimated via Flipout (dense.py:227-285):
+    y = act(x·mean + ((x∘S)·Delta)∘T + b), Delta = sigma∘eps, per-example sign tensors S [.., I] and T [.., O]."""
+
+    def call(self, inputs, training=None):
+        mean, rho = self._kernel_params()
+        if rho is None:  # dense.py:256-257: not a random variable -> parent behaviour
+            return super().call(inputs)
+        x, lead = flatten_batch(inputs)
+        bias = self._bias_value()
+        kl_scale, pm, ps = self._fused_kl_args()
+        y, kl = F.FlipoutDense.apply(x, mean, rho, bias, self._act, self.compute_dtype, self._noise("eps", S_KERNEL),
+                                     self._noise("sign_input", S_SIGN_IN), self._noise("sign_output", S_SIGN_OUT),
+                                     kl_scale, pm, ps)
+        if kl_scale != 0.0:
+            self._kl.set(kl, mean, rho)
+        return y.reshape(*lead, self.units)
+
+
+class DenseBatchEnsemble(Layer):
+    """A batch ensemble dense layer (dense.py:470-607): y[e] = act(((x[e]∘alpha[e]) W)∘gamma[e] + bias[e]),
+    batch rows member-major [ensemble_size * examples_per_model, features]."""
+
+    def __init__(self, units, rank=1, ensemble_size=4, activation=None, use_bias=True, alpha_initializer="ones",
+                 gamma_initializer="ones", kernel_initializer="glorot_uniform", bias_initializer="zeros",
+                 kernel_regularizer=None, bias_regularizer=None, activity_regularizer=None, kernel_constraint=None,
+                 bias_constraint=None, **kwargs):
+        super().__init__(**kwargs)
+        if rank != 1:
+            raise NotImplementedError("rank > 1 fast weights (dense.py:560-570) are not built; rank=1 is the hot path")
+        self.units, self.rank, self.ensemble_size = int(units), rank, int(ensemble_size)
+        self.ensemble_activation = activation
+        self._act = ops.act_id(activation)
+        self.use_ensemble_bias = use_bias
+        self.alpha_initializer = initializers.get(alpha_initializer)
+        self.gamma_initializer = initializers.get(gamma_initializer)
+        self.kernel_initializer = initializers.get(kernel_initializer)
+        self.ensemble_bias_initializer = initializers.get(bias_initializer)
+        self.kernel_regularizer = regularizers.get(kernel_regularizer)
+        self.ensemble_bias_regularizer = regularizers.get(bias_regularizer)
+
+    def build(self, input_shape):
+        dev = self._device
+        in_dim, E = input_shape[-1], self.ensemble_size
+        self.kernel = nn.Parameter(self.kernel_initializer((in_dim, self.units)).to(dev))
+        self.alpha = nn.Parameter(self.alpha_initializer((E, in_dim)).to(dev))
+        self.gamma = nn.Parameter(self.gamma_initializer((E, self.units)).to(dev))
+        self.ensemble_bias = (nn.Parameter(self.ensemble_bias_initializer((E, self.units)).to(dev))
+                              if self.use_ensemble_bias else None)
+        self.built = True
+
+    def call(self, inputs, training=None):
+        if inputs.dim() != 2:
+            raise ValueError("DenseBatchEnsemble (TF signature) takes [ensemble_size * examples_per_model, features]")
+        if inputs.shape[0] % self.ensemble_size != 0:
+            raise ValueError(f"batch size {inputs.shape[0]} is not divisible by ensemble_size {self.ensemble_size}")
+        return F.BatchEnsembleDense.apply(inputs, self.kernel, self.alpha, self.gamma, self.ensemble_bias, self._act,
+                                          self.ensemble_size, self.compute_dtype)
+
+    @property
+    def losses(self):
+        out = []
+        if self.kernel_regularizer is not None:
+            out.append(self.kernel_regularizer(self.kernel))
+        if self.ensemble_bias_regularizer is not None and self.ensemble_bias is not None:
+            out.append(self.ensemble_bias_regularizer(self.ensemble_bias))
+        return out
+
+    def get_config(self):
+        cfg = super().get_config()
+        cfg.update(units=self.units, ensemble_size=self.ensemble_size, ensemble_activation=self.ensemble_activation,
+                   use_ensemble_bias=self.use_ensemble_bias,
+                   alpha_initializer=initializers.serialize(self.alpha_initializer),
+                   gamma_initializer=initializers.serialize(self.gamma_initializer),
+                   ensemble_bias_initializer=initializers.serialize(self.ensemble_bias_initializer),
+                   ensemble_bias_regularizer=regularizers.serialize(self.ensemble_bias_regularizer))
+        return cfg
+
+
+class DenseRank1(Layer):
+    """A rank-1 Bayesian neural net dense layer (dense.py:991-1175): per-example fast weights
+    r = clip(mu_r[e] + sigma_r[e]∘eps_r, min, max), s likewise; y = act(((x∘r) W)∘s + bias[e])."""
+
+    def __init__(self, units, activation=None, use_bias=True, alpha_initializer="trainable_normal",
+                 gamma_initializer="trainable_normal", kernel_initializer="glorot_uniform", bias_initializer="zeros",
+                 alpha_regularizer="normal_kl_divergence", gamma_regularizer="normal_kl_divergence",
+                 kernel_regularizer=None, bias_regularizer=None, activity_regularizer=None, alpha_constraint=None,
+                 gamma_constraint=None, kernel_constraint=None, bias_constraint=None, use_additive_perturbation=False,
+                 min_perturbation_value=-10, max_perturbation_value=10, ensemble_size=1, **kwargs):
+        super().__init__(**kwargs)
+        if use_additive_perturbation:
+            raise NotImplementedError("additive perturbations (dense.py:1126-1127) are not built yet")
+        if (min_perturbation_value, max_perturbation_value) != (-10, 10):
+            raise NotImplementedError("the fused kernels clip at the reference defaults [-10, 10]")
+        self.units, self.ensemble_size = int(units), int(ensemble_size)
+        self.ensemble_activation = activation
+        self._act = ops.act_id(activation)
+        self.use_ensemble_bias = use_bias
+        self.alpha_initializer = initializers.get(alpha_initializer)
+        self.gamma_initializer = initializers.get(gamma_initializer)
+        self.kernel_initializer = initializers.get(kernel_initializer)
+        self.ensemble_bias_initializer = initializers.get(bias_initializer)
+        if _is_trainable(self.ensemble_bias_initializer):
+            raise NotImplementedError("per-example sampled ensemble bias (dense.py:1131-1139) is not built yet")
+        self.alpha_regularizer = regularizers.get(alpha_regularizer)
+        self.gamma_regularizer = regularizers.get(gamma_regularizer)
+        self.kernel_regularizer = regularizers.get(kernel_regularizer)
+        self.ensemble_bias_regularizer = regularizers.get(bias_regularizer)
+
+    def build(self, input_shape):
+        dev = self._device
+        in_dim, E = input_shape[-1], self.ensemble_size
+        self.kernel = nn.Parameter(self.kernel_initializer((in_dim, self.units)).to(dev))
+        self.alpha = _make_weight(self, "alpha", (E, in_dim), self.alpha_initializer, dev)
+        self.gamma = _make_weight(self, "gamma", (E, self.units), self.gamma_initializer, dev)
+        self.ensemble_bias = (nn.Parameter(self.ensemble_bias_initializer((E, self.units)).to(dev))
+                              if self.use_ensemble_bias else None)
+        self.built = True
+
+    def _fast(self, init, param):
+        return init.params() if _is_trainable(init) else (param, None)
+
+    def call(self, inputs, training=None):
+        if inputs.dim() != 2:  # dense.py:1100: restricted to 2-D inputs
+            raise ValueError("DenseRank1 takes [ensemble_size * examples_per_model, features]")
+        if inputs.shape[0] % self.ensemble_size != 0:
+            raise ValueError(f"batch size {inputs.shape[0]} is not divisible by ensemble_size {self.ensemble_size}")
+        mu_r, rho_r = self._fast(self.alpha_initializer, self.alpha)
+        mu_s, rho_s = self._fast(self.gamma_initializer, self.gamma)
+        return F.Rank1Dense.apply(inputs, self.kernel, mu_r, rho_r, mu_s, rho_s, self.ensemble_bias, self._act,
+                                  self.ensemble_size, self.compute_dtype, self._noise("eps_alpha", S_R),
+                                  self._noise("eps_gamma", S_S))
+
+    @property
+    def losses(self):
+        out = []
+        if self.alpha_regularizer is not None and _is_trainable(self.alpha_initializer):
+            out.append(self.alpha_regularizer(self.alpha_initializer))
+        if self.gamma_regularizer is not None and _is_trainable(self.gamma_initializer):
+            out.append(self.gamma_regularizer(self.gamma_initializer))
+        if self.kernel_regularizer is not None:
+            out.append(self.kernel_regularizer(self.kernel))
+        if self.ensemble_bias_regularizer is not None and self.ensemble_bias is not None:
+            out.append(self.ensemble_bias_regularizer(self.ensemble_bias))
+        return out
+
+    def get_config(self):
+        cfg = super().get_config()
+        cfg.update(units=self.units, ensemble_size=self.ensemble_size, ensemble_activation=self.ensemble_activation,
+                   use_ensemble_bias=self.use_ensemble_bias,
+                   alpha_initializer=initializers.serialize(self.alpha_initializer),
+                   gamma_initializer=initializers.serialize(self.gamma_initializer),
+                   alpha_regularizer=regularizers.serialize(self.alpha_regularizer),
+                   gamma_regularizer=regularizers.serialize(self.gamma_regularizer))
+        return cfg

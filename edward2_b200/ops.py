@@ -103,3 +103,121 @@ def act_bwd(gy: torch.Tensor, y: torch.Tensor, gp: torch.Tensor, dbias: torch.Te
     rows, cols = y.shape
     _lib.check(lib.ed2_act_bwd(_lib.dt_of(y), gy.data_ptr(), _lib.ld(gy), y.data_ptr(), _lib.ld(y), rows, cols, act,
                                gp.data_ptr(), _lib.ld(gp), _lib.ptr(dbias), _lib.stream_ptr()), "ed2_act_bwd")
+
+
+# ------------------------------------------------------------------------------------------------- SNGP ops
+def spectral_norm_update(w: torch.Tensor, u: torch.Tensor, v: torch.Tensor, iterations: int, norm_multiplier: float,
+                         mode: int, update_uv: bool, w_out: torch.Tensor | None, w_out_lp: torch.Tensor | None = None):
+    """Power iteration + normalisation (ed2_spectral_norm_update).  Returns (sigma, factor) device scalars
+    (factor = multiplicative scale applied to w)."""
+    lib = _lib.load()
+    in_dim, out_dim = w.shape
+    assert w.is_contiguous() and w.dtype == torch.float32
+    ws = torch.empty(in_dim + out_dim + 8, dtype=torch.float32, device=w.device)
+    _lib.check(lib.ed2_spectral_norm_update(w.data_ptr(), in_dim, out_dim, u.data_ptr(), v.data_ptr(), iterations,
+                                            norm_multiplier, mode, int(update_uv), _lib.ptr(w_out), _lib.ptr(w_out_lp),
+                                            0 if w_out_lp is None else _lib.ld(w_out_lp), None, ws.data_ptr(),
+                                            _lib.stream_ptr()), "ed2_spectral_norm_update")
+    scal = ws[in_dim + out_dim:]
+    return scal[0], scal[1]
+
+
+def input_normalize(x: torch.Tensor, out_dtype: torch.dtype, gamma=None, beta=None, eps=1e-3, scale_only=False,
+                    scale=1.0) -> torch.Tensor:
+    lib = _lib.load()
+    rows, cols = x.shape
+    y = _lib.empty_padded(rows, cols, out_dtype, x.device)
+    _lib.check(lib.ed2_input_normalize(x.data_ptr(), _lib.dt_of(x), _lib.ld(x), y.data_ptr(), _lib.dt_of(y), _lib.ld(y),
+                                       rows, cols, _lib.ptr(gamma), _lib.ptr(beta), eps, int(scale_only), scale,
+                                       _lib.stream_ptr()), "ed2_input_normalize")
+    return y
+
+
+def layernorm_bwd(x, dy, gamma, eps, want_dx=True, want_params=True):
+    lib = _lib.load()
+    rows, cols = x.shape
+    dx = _lib.empty_padded(rows, cols, x.dtype, x.device) if want_dx else None
+    dgamma = torch.empty(cols, dtype=torch.float32, device=x.device) if want_params else None
+    dbeta = torch.empty(cols, dtype=torch.float32, device=x.device) if want_params else None
+    _lib.check(lib.ed2_layernorm_bwd(x.data_ptr(), _lib.dt_of(x), _lib.ld(x), dy.data_ptr(), _lib.dt_of(dy), _lib.ld(dy),
+                                     rows, cols, _lib.ptr(gamma), eps, _lib.ptr(dx), _lib.dt_of(x),
+                                     0 if dx is None else _lib.ld(dx), _lib.ptr(dgamma), _lib.ptr(dbeta),
+                                     _lib.stream_ptr()), "ed2_layernorm_bwd")
+    return dx, dgamma, dbeta
+
+
+def rff_fwd(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, scale: float, phi_dtype: torch.dtype,
+            want_pre: bool):
+    """phi = scale * cos(x W + b); wt = Wᵀ [D, d] in x.dtype.  Returns (phi, pre or None)."""
+    lib = _lib.load()
+    B, d = x.shape
+    D = wt.shape[0]
+    phi = _lib.empty_padded(B, D, phi_dtype, x.device)
+    pre = torch.empty(B, D, dtype=torch.float32, device=x.device) if want_pre else None
+    _lib.check(lib.ed2_rff_fwd(_lib.dt_of(x), x.data_ptr(), _lib.ld(x), wt.data_ptr(), _lib.ld(wt), bias.data_ptr(),
+                               scale, B, d, D, phi.data_ptr(), _lib.ld(phi), _lib.dt_of(phi), _lib.ptr(pre),
+                               0 if pre is None else D, _lib.stream_ptr()), "ed2_rff_fwd")
+    return phi, pre
+
+
+def rff_bwd(dphi: torch.Tensor, pre: torch.Tensor, bias: torch.Tensor, w: torch.Tensor, scale: float,
+            dx_dtype: torch.dtype) -> torch.Tensor:
+    """dx = (-scale * sin(pre + b) ∘ dphi) Wᵀ;  w [d, D] in the compute dtype."""
+    lib = _lib.load()
+    B, D = pre.shape
+    d = w.shape[0]
+    gpre = _lib.empty_padded(B, D, w.dtype, w.device)
+    dx = _lib.empty_padded(B, d, dx_dtype, w.device)
+    _lib.check(lib.ed2_rff_bwd(_lib.dt_of(w), dphi.data_ptr(), _lib.ld(dphi), _lib.dt_of(dphi), pre.data_ptr(), D,
+                               bias.data_ptr(), w.data_ptr(), _lib.ld(w), scale, B, d, D, gpre.data_ptr(),
+                               _lib.ld(gpre), dx.data_ptr(), _lib.ld(dx), _lib.dt_of(dx), _lib.stream_ptr()),
+               "ed2_rff_bwd")
+    return dx
+
+
+def laplace_precision_update(phi: torch.Tensor, precision: torch.Tensor, momentum: float, batch_total: int | None = None,
+                             partial_out: torch.Tensor | None = None) -> None:
+    """P <- m P + (1-m) phiᵀphi / batch_total  (m > 0)  |  P + phiᵀphi; or the raw local product into partial_out."""
+    lib = _lib.load()
+    B, D = phi.shape
+    assert precision.is_contiguous() and precision.dtype == torch.float32
+    _lib.check(lib.ed2_laplace_precision_update(_lib.dt_of(phi), phi.data_ptr(), _lib.ld(phi), B, D, momentum,
+                                                batch_total if batch_total is not None else B, precision.data_ptr(),
+                                                _lib.ptr(partial_out), _lib.stream_ptr()), "ed2_laplace_precision_update")
+
+
+def precision_blend(precision: torch.Tensor, summed: torch.Tensor, momentum: float, batch_total: int) -> None:
+    lib = _lib.load()
+    D = precision.shape[0]
+    _lib.check(lib.ed2_precision_blend(precision.data_ptr(), summed.data_ptr(), D, momentum, batch_total,
+                                       _lib.stream_ptr()), "ed2_precision_blend")
+
+
+def predictive_variance(phi: torch.Tensor, sigma_lp: torch.Tensor, ridge: float, logits: torch.Tensor | None = None,
+                        mean_field_factor: float = -1.0, likelihood: int = 0):
+    """var[b] = ridge * phi[b] Sigma phi[b]ᵀ (+ optional fused mean-field logits). Returns (var, logits_out)."""
+    lib = _lib.load()
+    B, D = phi.shape
+    var = torch.empty(B, dtype=torch.float32, device=phi.device)
+    out = None
+    K = 0
+    if logits is not None:
+        logits = logits.to(torch.float32).contiguous()
+        K = logits.shape[1]
+        out = torch.empty_like(logits)
+    _lib.check(lib.ed2_predictive_variance(_lib.dt_of(phi), phi.data_ptr(), _lib.ld(phi), sigma_lp.data_ptr(),
+                                           _lib.ld(sigma_lp), B, D, ridge, var.data_ptr(), _lib.ptr(logits), K,
+                                           mean_field_factor, likelihood, _lib.ptr(out), _lib.stream_ptr()),
+               "ed2_predictive_variance")
+    return var, out
+
+
+def mean_field_logits(logits: torch.Tensor, var: torch.Tensor, mean_field_factor: float, likelihood: int) -> torch.Tensor:
+    lib = _lib.load()
+    lg = logits.to(torch.float32).contiguous()
+    B, K = lg.shape
+    out = torch.empty_like(lg)
+    _lib.check(lib.ed2_mean_field_logits(lg.data_ptr(), var.to(torch.float32).contiguous().data_ptr(), B, K,
+                                         mean_field_factor, likelihood, out.data_ptr(), _lib.stream_ptr()),
+               "ed2_mean_field_logits")
+    return out

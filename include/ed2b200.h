@@ -305,6 +305,12 @@ int ed2_input_normalize(const void* x, int x_dtype, int x_ld, void* y, int y_dty
                         int cols, const float* gamma, const float* beta, float eps, int scale_only, float scale,
                         void* stream);
 
+/* Backward of the LayerNormalization above (the reference relies on autodiff): dx, and dgamma / dbeta column
+ * sums (optional, overwritten). */
+int ed2_layernorm_bwd(const void* x, int x_dtype, int x_ld, const void* dy, int dy_dtype, int dy_ld, long long rows,
+                      int cols, const float* gamma, float eps, void* dx, int dx_dtype, int dx_ld, float* dgamma,
+                      float* dbeta, void* stream);
+
 /* Random Fourier features (edward2/tensorflow/layers/random_feature.py:258-266;
  * edward2/jax/nn/random_feature.py:209-214):  phi = cos(x W + b) * scale.
  * wt: the frozen projection stored TRANSPOSED, [D][in_dim] in `dtype` (K-major B operand).

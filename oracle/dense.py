@@ -80,14 +80,15 @@ def batch_ensemble_fwd(x, w, alpha, gamma, bias=None, act=None):
     return y.reshape(E * n, -1), z.reshape(E * n, -1)
 
 
-def batch_ensemble_bwd(x, w, alpha, gamma, bias, act, gy):
-    """Closed-form gradients of batch_ensemble_fwd."""
+def batch_ensemble_bwd(x, w, alpha, gamma, bias, act, gy, y_mask=None):
+    """Closed-form gradients of batch_ensemble_fwd.  y_mask: optional forward output whose sign
+    pattern defines relu' (bf16 parity is conditioned on the kernel's own activation pattern)."""
     x = np.asarray(x, dtype=np.float64)
     w = np.asarray(w, dtype=np.float64)
     E = alpha.shape[0]
     n = x.shape[0] // E
     y, z = batch_ensemble_fwd(x, w, alpha, gamma, bias, act)
-    gp = activation_grad(y, np.asarray(gy, dtype=np.float64), act).reshape(E, n, -1)
+    gp = activation_grad(y if y_mask is None else y_mask, np.asarray(gy, dtype=np.float64), act).reshape(E, n, -1)
     ze = z.reshape(E, n, -1)
     xe = x.reshape(E, n, -1)
     dz = gp * gamma[:, None, :]
@@ -133,7 +134,7 @@ def rank1_fwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias=None, act=None)
     return activation(pre, act), z, r, s
 
 
-def rank1_bwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act, gy):
+def rank1_bwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act, gy, y_mask=None):
     x = np.asarray(x, dtype=np.float64)
     w = np.asarray(w, dtype=np.float64)
     E = mu_r.shape[0]
@@ -141,7 +142,7 @@ def rank1_bwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act, gy):
     y, z, r, s = rank1_fwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act)
     _, mask_r, er = rank1_factors(mu_r, rho_r, eps_r, E)
     _, mask_s, es = rank1_factors(mu_s, rho_s, eps_s, E)
-    gp = activation_grad(y, np.asarray(gy, dtype=np.float64), act)
+    gp = activation_grad(y if y_mask is None else y_mask, np.asarray(gy, dtype=np.float64), act)
     dz = gp * s
     ds = gp * z * mask_s
     dmu_s = ds.reshape(E, n, -1).sum(1)
@@ -167,10 +168,10 @@ def reparam_fwd(x, mu, rho, eps, bias=None, act=None):
     return activation(pre, act), w
 
 
-def reparam_bwd(x, mu, rho, eps, bias, act, gy):
+def reparam_bwd(x, mu, rho, eps, bias, act, gy, y_mask=None):
     x = np.asarray(x, dtype=np.float64)
     y, w = reparam_fwd(x, mu, rho, eps, bias, act)
-    gp = activation_grad(y, np.asarray(gy, dtype=np.float64), act)
+    gp = activation_grad(y if y_mask is None else y_mask, np.asarray(gy, dtype=np.float64), act)
     dw = x.T @ gp
     return dict(dx=gp @ w.T, dmu=dw, drho=dw * np.asarray(eps, dtype=np.float64) * sigmoid(rho), dbias=gp.sum(0))
 
@@ -188,11 +189,11 @@ def flipout_fwd(x, mu, rho, eps, sign_in, sign_out, bias=None, act=None):
     return activation(pre, act), delta
 
 
-def flipout_bwd(x, mu, rho, eps, sign_in, sign_out, bias, act, gy):
+def flipout_bwd(x, mu, rho, eps, sign_in, sign_out, bias, act, gy, y_mask=None):
     x = np.asarray(x, dtype=np.float64)
     mu = np.asarray(mu, dtype=np.float64)
     y, delta = flipout_fwd(x, mu, rho, eps, sign_in, sign_out, bias, act)
-    gp = activation_grad(y, np.asarray(gy, dtype=np.float64), act)
+    gp = activation_grad(y if y_mask is None else y_mask, np.asarray(gy, dtype=np.float64), act)
     gt = gp * sign_out
     dmu = x.T @ gp
     ddelta = (x * sign_in).T @ gt

@@ -13,6 +13,11 @@ DTYPES = [torch.float32, torch.bfloat16]
 ACTS = {None: 0, "relu": 1}
 
 
+def _mask(y, dtype):
+    """fp32: the oracle's own relu pattern; bf16: the kernel's (see oracle/dense.py *_bwd y_mask)."""
+    return None if dtype == torch.float32 else to_np(y)
+
+
 def _check(name, got, want, tol):
     e = rel_err(to_np(got), want)
     assert e <= tol, f"{name}: rel err {e:.3e} > {tol:.1e}"
@@ -43,10 +48,8 @@ def test_batch_ensemble(cuda, dtype, act, shape):
 
     y_ref, _ = od.batch_ensemble_fwd(x, w, alpha, gamma, bias, act)
     _check("y", y, y_ref, tol)
-    if dtype == torch.bfloat16:
-        # backward parity is defined on the kernel's own (bf16-rounded) forward outputs feeding relu'
-        pass
-    g = od.batch_ensemble_bwd(x, w, alpha, gamma, bias, act, gy)
+    # bf16: relu' is conditioned on the kernel's own activation pattern (elements within rounding noise of 0 flip)
+    g = od.batch_ensemble_bwd(x, w, alpha, gamma, bias, act, gy, y_mask=_mask(y, dtype))
     _check("dx", xt.grad, g["dx"], tol)
     _check("dw", wt.grad, g["dw"], tol)
     _check("dalpha", at.grad, g["dalpha"], tol)
@@ -92,7 +95,7 @@ def test_rank1(cuda, dtype, sampled, shape):
     y_ref, _, _, s_ref = od.rank1_fwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, "relu")
     # in bf16 the kernel stores s rounded to bf16; tolerance covers it
     _check("y", y, y_ref, tol)
-    g = od.rank1_bwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, "relu", gy)
+    g = od.rank1_bwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, "relu", gy, y_mask=_mask(y, dtype))
     _check("dx", xt.grad, g["dx"], tol)
     _check("dw", wt.grad, g["dw"], tol)
     _check("dmu_r", mr.grad, g["dmu_r"], tol)
@@ -136,7 +139,7 @@ def test_reparam(cuda, dtype, shape):
     _check("y", y, y_ref, tol)
     kl_ref = od.normal_kl(mu, rho, 0.0, 1.0, kl_scale)
     assert abs(kl.item() - kl_ref) <= 1e-5 * abs(kl_ref)
-    g = od.reparam_bwd(x, mu, rho, eps, bias, "relu", gy)
+    g = od.reparam_bwd(x, mu, rho, eps, bias, "relu", gy, y_mask=_mask(y, dtype))
     kmu, krho = od.normal_kl_grad(mu, rho, 0.0, 1.0, kl_scale * 3.0)
     _check("dx", xt.grad, g["dx"], tol)
     _check("dmu", mt.grad, g["dmu"] + kmu, tol)
@@ -176,7 +179,7 @@ def test_flipout(cuda, dtype, uniform_sign_out, shape):
     _check("y", y, y_ref, tol)
     kl_ref = od.normal_kl(mu, rho)
     assert abs(kl.item() - kl_ref) <= 1e-5 * abs(kl_ref)
-    g = od.flipout_bwd(x, mu, rho, eps, s_in, s_out, bias, "relu", gy)
+    g = od.flipout_bwd(x, mu, rho, eps, s_in, s_out, bias, "relu", gy, y_mask=_mask(y, dtype))
     _check("dx", xt.grad, g["dx"], tol)
     _check("dmu", mt.grad, g["dmu"], tol)
     _check("drho", rt.grad, g["drho"], tol)
