@@ -129,6 +129,12 @@ int ed2_normal_kl_bwd(const float* mu, const float* rho, long long n, float pm, 
   return k_normal_kl_bwd(mu, rho, n, Prior{pm, ps}, scale, upstream, dmu, drho, S(s));
 }
 
+int ed2_softmax_xent(const void* logits, int dtype, int ld, const long long* labels, long long rows, int cols,
+                     float loss_scale, float grad_scale, double* loss, void* dlogits, int d_dtype, int d_ld, void* s) {
+  ED2_TRY(check_dt(dtype));
+  return k_softmax_xent(logits, dtype, ld, labels, rows, cols, loss_scale, grad_scale, loss, dlogits, d_dtype, d_ld, S(s));
+}
+
 int ed2_act_bwd(int dtype, const void* gy, int gy_ld, const void* y, int y_ld, long long rows, int cols, int act,
                 void* gp, int gp_ld, float* dbias, void* s) {
   ED2_TRY(check_dt(dtype));

@@ -6,6 +6,8 @@
 
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "gemm_epilogue.h"
 #include "status.h"
 
@@ -484,6 +486,41 @@ __global__ void scale_inplace_kernel(float* x, long long n, float a) {
     x[i] *= a;
 }
 
+
+// Mean softmax cross-entropy, forward and gradient in one pass (one warp per row): the synthetic loss of the
+// benchmark harness.  loss += sum_rows (logsumexp - z[label]) * loss_scale;
+// dlogits = (softmax - onehot) * grad_scale.
+__global__ void __launch_bounds__(kBlock) softmax_xent_kernel(const void* logits, int dt, long long ld,
+                                                              const long long* labels, long long rows, int cols,
+                                                              float loss_scale, float grad_scale, double* loss,
+                                                              void* dlogits, int ddt, long long dld) {
+  const long long warp = (blockIdx.x * (long long)kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * kBlock) >> 5;
+  float local = 0.f;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, ld1(logits, dt, r * ld + c));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int c = lane; c < cols; c += 32) se += expf(ld1(logits, dt, r * ld + c) - mx);
+    se = warp_sum(se);
+    const int lab = static_cast<int>(labels[r]);
+    const float lse = logf(se) + mx;
+    if (lane == 0) local += lse - ld1(logits, dt, r * ld + lab);
+    if (dlogits != nullptr) {
+      const float inv = 1.f / se;
+      for (int c = lane; c < cols; c += 32) {
+        float p = expf(ld1(logits, dt, r * ld + c) - mx) * inv;
+        if (c == lab) p -= 1.f;
+        st1(dlogits, ddt, r * dld + c, p * grad_scale);
+      }
+    }
+  }
+  block_atomic_add(loss, local, loss_scale);
+}
+
 }  // namespace
 
 // =============================================================================================== launchers
@@ -597,6 +634,16 @@ int k_fill_noise(int kind, Noise nz, void* out, int dt, long long ld, long long 
   else fill_noise_kernel<1><<<g, kBlock, 0, s>>>(nz, out, dt, ld, rows, cols);
   count_launch();
   return check_launch("fill_noise");
+}
+
+int k_softmax_xent(const void* logits, int dt, long long ld, const long long* labels, long long rows, int cols,
+                   float loss_scale, float grad_scale, double* loss, void* dlogits, int ddt, long long dld,
+                   cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  const int g = static_cast<int>(std::min<long long>(kMaxGrid, (rows + 7) / 8));
+  softmax_xent_kernel<<<g, kBlock, 0, s>>>(logits, dt, ld, labels, rows, cols, loss_scale, grad_scale, loss, dlogits, ddt, dld);
+  count_launch();
+  return check_launch("softmax_xent");
 }
 
 int k_scale_inplace(float* x, long long n, float a, cudaStream_t s) {

@@ -100,6 +100,9 @@ int k_mean_field(const float* logits, const float* var, long long batch, int cla
                  float var_scale, float* out, cudaStream_t s);
 int k_rff_bwd_prep(const void* dphi, int ddt, long long dphi_ld, const float* pre, long long pre_ld, const float* bias, float scale,
                    long long rows, int cols, void* gpre, int gdt, long long gpre_ld, cudaStream_t s);
+int k_softmax_xent(const void* logits, int dt, long long ld, const long long* labels, long long rows, int cols,
+                   float loss_scale, float grad_scale, double* loss, void* dlogits, int ddt, long long dld,
+                   cudaStream_t s);
 int k_scale_inplace(float* x, long long n, float a, cudaStream_t s);
 
 }  // namespace ed2

@@ -416,3 +416,30 @@ class RandomFourierFeatures(torch.autograd.Function):
         if dx.dtype != x_dtype:
             dx = dx.to(x_dtype)
         return dx, None, None, None, None, None, None
+
+
+class SoftmaxCrossEntropy(torch.autograd.Function):
+    """Mean softmax cross-entropy with integer labels; the gradient is produced in the forward pass.
+    `denominator` is the (global) batch size the mean is taken over."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, denominator):
+        lib = _lib.load()
+        B, K = logits.shape
+        lg = logits if (logits.stride(1) == 1 and logits.dtype in (torch.float32, torch.bfloat16)) else logits.contiguous().float()
+        loss = torch.zeros((), dtype=torch.float64, device=logits.device)
+        need = ctx.needs_input_grad[0]
+        d = _new(B, K, lg.dtype, lg.device) if need else None
+        inv = 1.0 / float(denominator)
+        _lib.check(lib.ed2_softmax_xent(lg.data_ptr(), _lib.dt_of(lg), _lib.ld(lg), labels.data_ptr(), B, K, inv, inv,
+                                        loss.data_ptr(), _p(d), _lib.dt_of(lg), _ldn(d), _lib.stream_ptr()),
+                   "ed2_softmax_xent")
+        if need:
+            ctx.save_for_backward(d)
+        return loss.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        # upstream of a scalar loss is 1 in every use here; a different factor scales the stored gradient
+        return d * g.to(d.dtype), None, None

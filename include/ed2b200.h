@@ -119,6 +119,13 @@ int ed2_normal_kl_fwd(const float* mu, const float* rho, long long n, float prio
 int ed2_normal_kl_bwd(const float* mu, const float* rho, long long n, float prior_mean, float prior_std,
                       float scale, const float* upstream, float* d_mu, float* d_rho, void* s);
 
+/* Softmax cross-entropy with integer labels (int64), loss and gradient in one pass — the synthetic training loss of
+ * the benchmark harness (the reference's scripts use tf.keras.losses.sparse_categorical_crossentropy,
+ * experimental/marginalization_mixup/sngp.py:400-409).  *loss (fp64, caller-zeroed) += loss_scale * sum_rows CE;
+ * dlogits = grad_scale * (softmax - onehot) (optional). */
+int ed2_softmax_xent(const void* logits, int dtype, int ld, const long long* labels, long long rows, int cols,
+                     float loss_scale, float grad_scale, double* loss, void* dlogits, int d_dtype, int d_ld, void* s);
+
 /* gp = gy ∘ act'(y) (relu' evaluated on the output);  dbias[n] = sum_m gp[m,n] (optional, overwritten).
  * The output-side backward step of a plain dense layer (the layer SpectralNormalization wraps). */
 int ed2_act_bwd(int dtype, const void* gy, int gy_ld, const void* y, int y_ld, long long rows, int cols, int act,
