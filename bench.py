@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — samples/s for one forward + backward step of the Edward2 stochastic-weight hot path on B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` (under torchrun for N > 1)
+prints ONE JSON line from rank 0.  Workload at N=1 = BASELINE.json configs[1]: Bayesian MLP 1024-4096-4096-1000,
+batch 4096, bf16 compute, DenseReparameterization layers with the analytic KL regularizer (the DenseFlipout variant
+of the same config is measured in the same run and reported under "variants").  `--impl reference` times the
+torch-CPU restatement of the reference's CPU path (oracle/torch_cpu.py; the reference itself cannot run here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = [1024, 4096, 4096, 1000]
+BATCH = 4096
+KL_SCALE = 1.0 / 50000
+METRIC = "samples/sec fwd+bwd"
+WORKLOAD = "cfg2: DenseReparameterization Bayesian MLP 1024-4096-4096-1000 + KL, batch 4096/GPU, bf16"
+
+
+def flops_per_step(batch: int, flipout: bool) -> float:
+    """fwd + dW for every layer, dX for layers 2..L; Flipout doubles every product."""
+    f = 0.0
+    for li, (i, o) in enumerate(zip(DIMS[:-1], DIMS[1:])):
+        f += 2.0 * batch * i * o * 2          # forward + dW
+        if li > 0:
+            f += 2.0 * batch * i * o          # dX
+    return f * (2.0 if flipout else 1.0)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16=d.get("bf16_tflops_sustained", 1400.0), bf16_burst=d.get("bf16_tflops", 1590.0),
+                    hbm=d.get("hbm_gbs", 6650.0), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path, restated (kind "port"), on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import torch_cpu
+
+    sample_batch = 512
+    sps, dt, threads = torch_cpu.time_bayesian_mlp(DIMS, sample_batch, False, max(1, args.steps), max(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "torch-CPU fp32 restatement of the reference's CPU path "
+                   "(TF/TFP/JAX not installable here); each step = a 512-row sample of the 4096-row batch"},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample_batch}-row batches of the cfg2 MLP, {args.steps} fwd+bwd steps"},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def build_model(ed, flipout: bool, device, step_counter):
+    import torch
+
+    cls = ed.layers.DenseFlipout if flipout else ed.layers.DenseReparameterization
+    layers = []
+    for li, units in enumerate(DIMS[1:]):
+        reg = ed.regularizers.NormalKLDivergence(scale_factor=KL_SCALE)
+        layers.append(cls(units, activation="relu" if li < len(DIMS) - 2 else None, kernel_regularizer=reg,
+                          dtype="bfloat16", seed=2026 + li))
+    x0 = torch.zeros(8, DIMS[0], dtype=torch.bfloat16, device=device)
+    h = x0
+    with torch.no_grad():
+        for l in layers:
+            h = l(h)
+    for l in layers:
+        l.step_counter = step_counter
+    return layers
+
+
+def make_step(layers, global_batch):
+    from edward2_b200 import functional as F
+
+    def step(x, labels):
+        h = x
+        for l in layers:
+            h = l(h)
+        loss = F.SoftmaxCrossEntropy.apply(h, labels, global_batch)
+        for l in layers:
+            loss = loss + l.losses[0]
+        loss.backward()
+        return loss.detach()
+
+    return step
+
+
+def params_of(layers):
+    return [p for l in layers for p in l.parameters()]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import edward2_b200 as ed
+    from edward2_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    lib = _lib.load()
+    _lib.check(lib.ed2_check_device(local), "ed2_check_device")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    global_batch = BATCH * world
+    pk = peaks()
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(BATCH, DIMS[0], generator=gen).to(torch.bfloat16).pin_memory()
+    y_host = torch.randint(0, DIMS[-1], (BATCH,), generator=gen).pin_memory()
+    x_dev, y_dev = x_host.to(device), y_host.to(device)
+    step_counter = torch.zeros((), dtype=torch.int64, device=device)
+
+    def measure(flipout: bool, steps: int, warmup: int, want_e2e: bool):
+        layers = build_model(ed, flipout, device, step_counter)
+        params = params_of(layers)
+        handles = []
+        if world > 1:
+            # gradient all-reduce launched as soon as each parameter's gradient is final, overlapping the rest of
+            # the backward pass (NCCL runs on its own stream)
+            def hook(p):
+                handles.append(dist.all_reduce(p.grad, async_op=True))
+            for p in params:
+                p.register_post_accumulate_grad_hook(hook)
+        raw_step = make_step(layers, global_batch)
+
+        def zero():
+            for p in params:
+                p.grad = None
+
+        use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+        graph, static_loss = None, None
+
+        def eager_step(x, y):
+            zero()
+            step_counter.add_(1)
+            loss = raw_step(x, y)
+            for h in handles:
+                h.wait()
+            handles.clear()
+            return loss
+
+        x_static, y_static = x_dev.clone(), y_dev.clone()
+        eager_step(x_static, y_static)  # builds workspaces, sets kernel attributes
+        torch.cuda.synchronize()
+        a0 = _lib.launch_count()
+        eager_step(x_static, y_static)
+        launches_per_step = _lib.launch_count() - a0
+        if use_graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    eager_step(x_static, y_static)
+            torch.cuda.current_stream().wait_stream(s)
+            zero()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_counter.add_(1)
+                static_loss = raw_step(x_static, y_static)
+
+        def run_step():
+            if graph is not None:
+                graph.replay()
+                return static_loss
+            return eager_step(x_static, y_static)
+
+        def sync_all():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        for _ in range(max(warmup, 3)):
+            run_step()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run_step()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1) / steps
+        # kernels of libed2b200 launched in the timed region (a graph replay re-launches the captured ones)
+        launches = launches_per_step * steps
+        t = torch.tensor([ms], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+        e2e_ms = None
+        if want_e2e:
+            # end to end through the public layer API with HOST buffers: H2D of the batch, step, D2H of the loss
+            loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+            for _ in range(2):
+                x_static.copy_(x_host, non_blocking=True)
+                y_static.copy_(y_host, non_blocking=True)
+                loss_host.copy_(run_step(), non_blocking=True)
+            sync_all()
+            e0.record()
+            for _ in range(steps):
+                x_static.copy_(x_host, non_blocking=True)
+                y_static.copy_(y_host, non_blocking=True)
+                loss_host.copy_(run_step(), non_blocking=True)
+            e1.record()
+            sync_all()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        loss_val = float(run_step().item())
+        return dict(ms=ms, e2e_ms=e2e_ms, launches=launches, loss=loss_val, graph=graph is not None, layers=layers)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    main = measure(False, args.steps, args.warmup, True)
+    clocks = sampler.stop() if sampler else None
+    del main["layers"]
+    torch.cuda.empty_cache()
+    flip = None
+    if not args.skip_variants:
+        try:
+            flip = measure(True, max(3, args.steps // 2), 3, False)
+            del flip["layers"]
+        except Exception as e:  # noqa: BLE001
+            flip = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): the 8 GEMM launches of one step, timed alone
+    roof = None
+    try:
+        shapes = []
+        for li, (i, o) in enumerate(zip(DIMS[:-1], DIMS[1:])):
+            shapes.append(("fwd", BATCH, o, i, ops.MAJOR_K, ops.MAJOR_MN))
+            shapes.append(("dW", i, o, BATCH, ops.MAJOR_MN, ops.MAJOR_MN))
+            if li > 0:
+                shapes.append(("dX", BATCH, i, o, ops.MAJOR_K, ops.MAJOR_K))
+        bufs = []
+        for (_, m, n, k, ma, mb) in shapes:
+            a = torch.randn((m, k) if ma == ops.MAJOR_K else (k, m), device=device).to(torch.bfloat16)
+            b = torch.randn((n, k) if mb == ops.MAJOR_K else (k, n), device=device).to(torch.bfloat16)
+            out = _lib.empty_padded(m, n, torch.float32 if _ == "dW" else torch.bfloat16, device)
+            bufs.append((a, b, out))
+        def gemms():
+            for (_, m, n, k, ma, mb), (a, b, out) in zip(shapes, bufs):
+                ops.gemm(a, b, m, n, k, major_a=ma, major_b=mb, out=out)
+        for _ in range(3):
+            gemms()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            gemms()
+        e1.record()
+        torch.cuda.synchronize()
+        gemm_ms = e0.elapsed_time(e1) / reps
+        fl = flops_per_step(BATCH, False)
+        achieved = fl / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "ed2::tc::gemm_bf16_kernel (8 launches per step)", "achieved": achieved,
+                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": None,
+                "peak_source": pk["src"], "gemm_ms_per_step": gemm_ms, "algorithmic_flops_per_step": fl,
+                "gemm_share_of_step": gemm_ms / main["ms"]}
+        del bufs
+    except Exception as e:  # noqa: BLE001
+        roof = {"error": str(e)[:200]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        try:
+            from oracle import torch_cpu
+
+            sps, dt, threads = torch_cpu.time_bayesian_mlp(DIMS, 1024, False, steps=4, warmup=1)
+            cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+                   "sample": "4 fwd+bwd steps on 1024-row batches of the cfg2 MLP (torch-CPU fp32 restatement)",
+                   "s_per_step": dt}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"error": str(e)[:200]}
+
+    value = global_batch / (main["ms"] * 1e-3)
+    fl = flops_per_step(BATCH, False)
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": main["ms"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}",
+                   "l2": "inputs > L2: one step touches ~0.6 GB (fp32 mu/rho + grads 400 MB, bf16 W 50 MB, activations)",
+                   "cuda_graph": main["graph"], "kl_scale": KL_SCALE},
+        "e2e": {"value": global_batch / (main["e2e_ms"] * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": (x_host.numel() * 2 + y_host.numel() * 8) * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": main["e2e_ms"]},
+        "gpu_launches": main["launches"],
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "step_tflops": fl * world / (main["ms"] * 1e-3) / 1e12,
+        "step_frac_of_tensor_peak": fl / (main["ms"] * 1e-3) / 1e12 / pk["bf16"],
+        "loss": main["loss"],
+        "variants": {"flipout": None if flip is None else (
+            flip if "error" in flip else {"value": global_batch / (flip["ms"] * 1e-3), "ms_per_step": flip["ms"],
+                                          "step_tflops": flops_per_step(BATCH, True) * world / (flip["ms"] * 1e-3) / 1e12,
+                                          "loss": flip["loss"]})},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-variants", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,7 +22,7 @@ _vp, _i, _f, _ll, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_uint6
 
 
 class Noise(C.Structure):
-    _fields_ = [("injected", _vp), ("seed", _u64), ("stream", _u64)]
+    _fields_ = [("injected", _vp), ("seed", _u64), ("stream", _u64), ("step", _vp)]
 
 
 class GemmDesc(C.Structure):
@@ -233,7 +233,7 @@ def ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
-def noise(injected: torch.Tensor | None = None, seed: int = 0, stream: int = 0) -> Noise:
+def noise(injected: torch.Tensor | None = None, seed: int = 0, stream: int = 0, step: torch.Tensor | None = None) -> Noise:
     n = Noise()
     if injected is not None:
         assert injected.dtype == torch.float32 and injected.is_contiguous() and injected.is_cuda
@@ -242,6 +242,7 @@ def noise(injected: torch.Tensor | None = None, seed: int = 0, stream: int = 0) 
         n.injected = None
     n.seed = seed & 0xFFFFFFFFFFFFFFFF
     n.stream = stream & 0xFFFFFFFFFFFFFFFF
+    n.step = None if step is None else step.data_ptr()
     return n
 
 

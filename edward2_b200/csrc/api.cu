@@ -13,7 +13,7 @@ using namespace ed2;
 namespace {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-inline Noise N(const ed2_noise& n) { return Noise{n.injected, n.seed, n.stream}; }
+inline Noise N(const ed2_noise& n) { return Noise{n.injected, n.seed, n.stream, n.step}; }
 
 #define ED2_TRY(expr)            \
   do {                           \

@@ -94,7 +94,13 @@ struct Noise {
   const float* injected;  // nullptr -> Philox
   uint64_t seed;
   uint64_t stream;
+  const uint64_t* step;   // optional device counter: key = seed + step[0] * 0x9E3779B97F4A7C15 (CUDA-graph replays)
 };
+
+__device__ __forceinline__ uint64_t noise_key(const Noise& nz) {
+  return nz.step != nullptr ? nz.seed + __ldg(reinterpret_cast<const unsigned long long*>(nz.step)) * 0x9E3779B97F4A7C15ull
+                            : nz.seed;
+}
 
 // 4 consecutive noise values starting at flat element index idx (idx % 4 == 0).
 template <int kKind>
@@ -103,9 +109,9 @@ __device__ __forceinline__ void noise4(const Noise& nz, long long idx, long long
 #pragma unroll
     for (int i = 0; i < 4; ++i) e[i] = (idx + i < n) ? __ldg(nz.injected + idx + i) : 0.f;
   } else if constexpr (kKind == 0) {
-    philox_normal4(nz.seed, nz.stream, static_cast<uint64_t>(idx >> 2), e);
+    philox_normal4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
   } else {
-    philox_sign4(nz.seed, nz.stream, static_cast<uint64_t>(idx >> 2), e);
+    philox_sign4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
   }
 }
 
@@ -114,8 +120,8 @@ template <int kKind>
 __device__ __forceinline__ float noise1(const Noise& nz, long long idx) {
   if (nz.injected != nullptr) return __ldg(nz.injected + idx);
   float e[4];
-  if constexpr (kKind == 0) philox_normal4(nz.seed, nz.stream, static_cast<uint64_t>(idx >> 2), e);
-  else philox_sign4(nz.seed, nz.stream, static_cast<uint64_t>(idx >> 2), e);
+  if constexpr (kKind == 0) philox_normal4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
+  else philox_sign4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
   return e[idx & 3];
 }
 

@@ -53,12 +53,14 @@ def _ldn(t):
 class Randomness:
     """A noise tensor: injected values (parity tests) or a Philox (seed, stream) pair."""
 
-    def __init__(self, injected: torch.Tensor | None = None, seed: int = 0, stream: int = 0):
+    def __init__(self, injected: torch.Tensor | None = None, seed: int = 0, stream: int = 0,
+                 step: torch.Tensor | None = None):
         self.injected = None if injected is None else injected.to(torch.float32).contiguous()
         self.seed, self.stream = int(seed), int(stream)
+        self.step = step  # int64 device scalar folded into the Philox key (see ed2_noise.step)
 
     def c(self) -> _lib.Noise:
-        return _lib.noise(self.injected, self.seed, self.stream)
+        return _lib.noise(self.injected, self.seed, self.stream, self.step)
 
 
 # ------------------------------------------------------------------------------------------------- BatchEnsemble

@@ -40,6 +40,7 @@ class Layer(nn.Module):
         self._calls = 0
         self._injected = {}
         self._extra_losses = []
+        self.step_counter = None  # optional int64 device scalar advanced by the caller once per step
 
     # -- Keras surface -------------------------------------------------------------------------------------
     def build(self, input_shape):
@@ -75,6 +76,8 @@ class Layer(nn.Module):
 
         if name in self._injected and self._injected[name] is not None:
             return F.Randomness(self._injected[name])
+        if self.step_counter is not None:  # device-side step: fresh noise on every CUDA-graph replay
+            return F.Randomness(seed=self.seed, stream=stream, step=self.step_counter)
         key = (self.seed + self._calls * GOLDEN) & MASK64
         return F.Randomness(seed=key, stream=stream)
 

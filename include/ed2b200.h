@@ -47,6 +47,8 @@ typedef struct {
   const float* injected; /* NULL -> Philox(seed, stream) */
   uint64_t seed;
   uint64_t stream;
+  const uint64_t* step;  /* optional DEVICE counter folded into the key: seed + step[0] * 0x9E3779B97F4A7C15, so a
+                            captured CUDA graph draws fresh noise on every replay */
 } ed2_noise;
 
 const char* ed2_version(void);
