@@ -206,21 +206,23 @@ def run_ours(args):
             return loss
 
         x_static, y_static = x_dev.clone(), y_dev.clone()
-        eager_step(x_static, y_static)  # builds workspaces, sets kernel attributes
+        # every pre-capture step runs on the capture-side stream so that autograd's AccumulateGrad nodes are bound
+        # to it (a node created on the legacy stream would invalidate the capture)
+        side = torch.cuda.Stream() if use_graph else torch.cuda.current_stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            eager_step(x_static, y_static)  # builds workspaces, sets kernel attributes
+            torch.cuda.synchronize()
+            a0 = _lib.launch_count()
+            eager_step(x_static, y_static)
+            launches_per_step = _lib.launch_count() - a0
+            eager_step(x_static, y_static)
+        torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        a0 = _lib.launch_count()
-        eager_step(x_static, y_static)
-        launches_per_step = _lib.launch_count() - a0
         if use_graph:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(3):
-                    eager_step(x_static, y_static)
-            torch.cuda.current_stream().wait_stream(s)
             zero()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=side):
                 step_counter.add_(1)
                 static_loss = raw_step(x_static, y_static)
 

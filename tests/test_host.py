@@ -1,0 +1,78 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/ed2b200.h declares (no
+compute calls without a GPU), the string-alias lookups, initializer statistics, and that the product code never
+imports the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from edward2_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "ed2b200.h")).read()
+    declared = set(re.findall(r"\b(ed2_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in ed2b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.ed2_version().decode().startswith("ed2b200")
+
+
+def test_no_cpu_fallback():
+    """Compute entry points must fail loudly without a GPU (no CPU path behind the API)."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import edward2_b200 as ed
+
+    layer = ed.layers.DenseReparameterization(4)
+    with pytest.raises((RuntimeError, AssertionError)):
+        layer(torch.zeros(2, 3))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "edward2_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_string_aliases():
+    import edward2_b200 as ed
+
+    for name in ("trainable_normal", "trainable_deterministic", "zeros", "zero", "ones", "glorot_uniform", "he_normal",
+                 "random_sign", "orthogonal_random_features"):
+        assert ed.initializers.get(name) is not None
+    assert isinstance(ed.regularizers.get("normal_kl_divergence"), ed.regularizers.NormalKLDivergence)
+    assert isinstance(ed.constraints.get("softplus"), ed.constraints.Softplus)
+    assert ed.initializers.get(None) is None and ed.regularizers.get(None) is None
+    with pytest.raises(ValueError):
+        ed.initializers.get("no_such_initializer")
+    with pytest.raises(ValueError):
+        ed.layers.LaplaceRandomFeatureCovariance(likelihood="bogus")
+    with pytest.raises(ValueError):
+        ed.layers.DenseReparameterization(4, activation="tanh")
+
+
+def test_initializer_statistics():
+    import edward2_b200 as ed
+
+    tn = ed.initializers.TrainableNormal(seed=0)
+    tn.build((200, 100))
+    mean, rho = tn.params()
+    np.testing.assert_allclose(mean.detach().numpy(), 0, atol=1e-4)
+    np.testing.assert_allclose(torch.nn.functional.softplus(rho).detach().numpy(), 0.048587, atol=5e-2)
+    s = ed.initializers.RandomSign(probs=0.5, seed=1)((1000, 10))
+    assert set(np.unique(s.numpy())) == {-1.0, 1.0} and abs(float(s.mean())) < 0.1
+    w = ed.initializers.OrthogonalRandomFeatures(stddev=1.0, random_norm=False, seed=0)((8, 20)).double().numpy()
+    np.testing.assert_allclose((w ** 2).sum(0), 8 * np.ones(20), atol=1e-5)
+    g = w[:, :8].T @ w[:, :8]
+    np.testing.assert_allclose(g - np.diag(np.diag(g)), 0, atol=1e-3)
+    c = ed.constraints.Softplus()(torch.tensor([-100.0, 0.0]))
+    assert (c > 0).all()

@@ -1,0 +1,230 @@
+"""CPU tests of the oracle: known-answer vectors, the reference's algebraic identities, closed-form gradients vs
+float64 autograd, and the committed golden vectors (tests/golden/oracle_vectors.npz)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense as od, philox as op, sngp as og
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_philox_known_answers():
+    kat = json.load(open(os.path.join(GOLD, "philox_kat.json")))
+    for v in kat["vectors"]:
+        c = np.array([int(x, 16) for x in v["counter"]], dtype=np.uint32)
+        k = np.array([int(x, 16) for x in v["key"]], dtype=np.uint32)
+        out = op.philox4x32_10(c, k)
+        assert [f"{int(x):08x}" for x in out] == v["output"]
+
+
+def test_philox_stream_moments_and_ks():
+    """moment and KS tests of the stream recipe (host restatement; the device sampler is compared with
+    it value by value in the GPU tests)."""
+    from scipy import stats
+
+    n = 1_000_000
+    z = op.normal(7, 1, n)
+    assert abs(z.mean()) < 4e-3 and abs(z.var() - 1) < 6e-3
+    assert abs(stats.skew(z)) < 1e-2 and abs(stats.kurtosis(z)) < 2e-2
+    assert stats.kstest(z[:200_000], "norm").pvalue > 1e-3
+    u = op.uniform(7, 2, n)
+    assert 0 < u.min() and u.max() < 1
+    assert stats.kstest(u[:200_000], "uniform").pvalue > 1e-3
+    s = op.sign(7, 3, n)
+    assert set(np.unique(s)) == {-1.0, 1.0}
+    assert stats.binomtest(int((s > 0).sum()), n, 0.5).pvalue > 1e-3
+    # element i depends only on (seed, stream, i): any tiling regenerates the same values
+    assert np.array_equal(op.normal(7, 1, 1000)[400:800], op.normal(7, 1, 800)[400:])
+    assert not np.array_equal(op.normal(7, 1, 100), op.normal(8, 1, 100))
+    assert not np.array_equal(op.normal(7, 1, 100), op.normal(7, 2, 100))
+
+
+def test_mean_field_logits_known_answers():
+    """edward2/tensorflow/layers/utils_test.py:201-241; edward2/jax/nn/utils_test.py:28-68."""
+    rng = np.random.RandomState(0)
+    logits = rng.randn(10, 12)
+    covmat = np.diag([1.5] * 10)
+    np.testing.assert_allclose(og.mean_field_logits(logits, covmat, 2.0), logits / 2.0, atol=1e-4)
+    np.testing.assert_allclose(og.mean_field_logits(logits, covmat, 2.0, "poisson"), logits * np.exp(1.5), atol=1e-4)
+    np.testing.assert_allclose(og.mean_field_logits(logits, None, -1), logits, atol=1e-4)
+    np.testing.assert_allclose(og.mean_field_logits(logits, None, 3.0), logits / 2.0, atol=1e-4)
+    np.testing.assert_allclose(og.mean_field_logits(logits, np.full(10, 1.5), 2.0), logits / 2.0, atol=1e-4)
+    with pytest.raises(ValueError):
+        og.mean_field_logits(logits, covmat, likelihood="gaussian")
+
+
+def test_batch_ensemble_equals_member_loop():
+    """dense_test.py:289-316 / jax dense_test.py:34-71."""
+    rng = np.random.default_rng(0)
+    E, n, I, O = 3, 4, 5, 5
+    x, w = rng.standard_normal((E * n, I)), rng.standard_normal((I, O))
+    a, g, b = rng.standard_normal((E, I)), rng.standard_normal((E, O)), rng.standard_normal((E, O))
+    y, _ = od.batch_ensemble_fwd(x, w, a, g, b)
+    loop = np.concatenate([((x[e * n:(e + 1) * n] * a[e]) @ w) * g[e] + b[e] for e in range(E)])
+    np.testing.assert_allclose(y, loop, rtol=1e-12, atol=1e-12)
+
+
+def test_kl_properties():
+    """regularizers_test.py:65-80: KL >= 0, linear in scale_factor, 0 for q == p; TFP's expm1 form agrees."""
+    rng = np.random.default_rng(1)
+    mu, rho = rng.standard_normal((20, 10)), rng.standard_normal((20, 10))
+    k = od.normal_kl(mu, rho)
+    assert k >= 0
+    assert abs(od.normal_kl(mu, rho, scale_factor=0.3) - 0.3 * k) < 1e-12 * k
+    rho0 = np.log(np.expm1(1.0 - 1e-7))
+    assert abs(od.normal_kl(np.zeros(5), np.full(5, rho0))) < 1e-12
+    sigma = od.stddev(rho)
+    ratio = sigma / 1.0
+    tfp = (0.5 * (mu / 1.0) ** 2 + 0.5 * np.expm1(2 * np.log(ratio)) - np.log(ratio)).sum()
+    assert abs(tfp - k) < 1e-10 * k
+    np.testing.assert_allclose(od.stddev(-3.0), 0.048587, atol=1e-5)  # initializers_test.py:73-86
+
+
+def _t(a, grad=True):
+    return torch.tensor(np.asarray(a, dtype=np.float64), requires_grad=grad)
+
+
+def test_closed_form_gradients_match_autograd():
+    rng = np.random.default_rng(2)
+    E, n, I, O = 2, 5, 7, 6
+    B = E * n
+    x, w = rng.standard_normal((B, I)), rng.standard_normal((I, O))
+    gy = rng.standard_normal((B, O))
+    sp = lambda r: torch.nn.functional.softplus(r) + 1e-7  # noqa: E731
+
+    # BatchEnsemble
+    a, g, b = rng.standard_normal((E, I)), rng.standard_normal((E, O)), rng.standard_normal((E, O))
+    xt, wt, at, gt, bt = _t(x), _t(w), _t(a), _t(g), _t(b)
+    y = torch.relu(((xt.reshape(E, n, I) * at[:, None]) @ wt) * gt[:, None] + bt[:, None]).reshape(B, O)
+    y.backward(_t(gy, False))
+    got = od.batch_ensemble_bwd(x, w, a, g, b, "relu", gy)
+    for k_, t_ in (("dx", xt), ("dw", wt), ("dalpha", at), ("dgamma", gt), ("dbias", bt)):
+        np.testing.assert_allclose(got[k_], t_.grad.numpy(), rtol=1e-10, atol=1e-10)
+
+    # Reparameterisation and Flipout
+    mu, rho, eps, b1 = rng.standard_normal((I, O)), rng.standard_normal((I, O)), rng.standard_normal((I, O)), rng.standard_normal(O)
+    s_in, s_out = rng.choice([-1.0, 1.0], (B, I)), rng.uniform(-1, 3, (B, O))
+    xt, mt, rt, bt = _t(x), _t(mu), _t(rho), _t(b1)
+    torch.relu(xt @ (mt + sp(rt) * _t(eps, False)) + bt).backward(_t(gy, False))
+    got = od.reparam_bwd(x, mu, rho, eps, b1, "relu", gy)
+    for k_, t_ in (("dx", xt), ("dmu", mt), ("drho", rt), ("dbias", bt)):
+        np.testing.assert_allclose(got[k_], t_.grad.numpy(), rtol=1e-10, atol=1e-10)
+    xt, mt, rt, bt = _t(x), _t(mu), _t(rho), _t(b1)
+    torch.relu(xt @ mt + ((xt * _t(s_in, False)) @ (sp(rt) * _t(eps, False))) * _t(s_out, False) + bt).backward(_t(gy, False))
+    got = od.flipout_bwd(x, mu, rho, eps, s_in, s_out, b1, "relu", gy)
+    for k_, t_ in (("dx", xt), ("dmu", mt), ("drho", rt), ("dbias", bt)):
+        np.testing.assert_allclose(got[k_], t_.grad.numpy(), rtol=1e-10, atol=1e-10)
+
+    # Rank-1 with clipping active on some draws
+    mu_r, mu_s = rng.standard_normal((E, I)), rng.standard_normal((E, O))
+    rho_r, rho_s = rng.standard_normal((E, I)), rng.standard_normal((E, O))
+    eps_r, eps_s = rng.standard_normal((B, I)), rng.standard_normal((B, O))
+    eps_r[0, :2] = 60.0
+    eps_s[3, :2] = -60.0
+    xt, wt, mrt, rrt, mst, rst, bt = _t(x), _t(w), _t(mu_r), _t(rho_r), _t(mu_s), _t(rho_s), _t(b)
+    rep = lambda t_: t_.repeat_interleave(n, dim=0)  # noqa: E731
+    r = torch.clamp(rep(mrt) + rep(sp(rrt)) * _t(eps_r, False), -10, 10)
+    s = torch.clamp(rep(mst) + rep(sp(rst)) * _t(eps_s, False), -10, 10)
+    torch.relu(((xt * r) @ wt) * s + rep(bt)).backward(_t(gy, False))
+    got = od.rank1_bwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, b, "relu", gy)
+    for k_, t_ in (("dx", xt), ("dw", wt), ("dmu_r", mrt), ("drho_r", rrt), ("dmu_s", mst), ("drho_s", rst), ("dbias", bt)):
+        np.testing.assert_allclose(got[k_], t_.grad.numpy(), rtol=1e-9, atol=1e-9)
+
+    # KL gradient
+    mt, rt = _t(mu), _t(rho)
+    sg = sp(rt)
+    (0.7 * (torch.log(1.3 / sg) + (sg ** 2 + (mt - 0.2) ** 2) / (2 * 1.3 ** 2) - 0.5).sum()).backward()
+    dmu, drho = od.normal_kl_grad(mu, rho, 0.2, 1.3, 0.7)
+    np.testing.assert_allclose(dmu, mt.grad.numpy(), rtol=1e-10)
+    np.testing.assert_allclose(drho, rt.grad.numpy(), rtol=1e-10)
+
+    # RFF input gradient
+    W, bb = rng.standard_normal((I, 9)), rng.uniform(0, 6.28, 9)
+    xt = _t(x)
+    (0.5 * torch.cos(xt @ _t(W, False) + _t(bb, False))).backward(_t(rng.standard_normal((B, 9)), False) * 0 + 1)
+    np.testing.assert_allclose(og.rff_bwd(x, W, bb, 0.5, np.ones((B, 9))), xt.grad.numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_laplace_precision_identities():
+    """jax random_feature_test.py:381-528: exact update P = ridge I + ΦᵀΦ; momentum update; orthogonal data ->
+    (1 + ridge) I; diag == diag(full); TF (momentum <= 0) and JAX (momentum None) predictive covariances agree."""
+    rng = np.random.default_rng(3)
+    B, D, ridge = 40, 12, 0.7
+    phi = rng.standard_normal((B, D))
+    p_jax = og.precision_update_jax(ridge * np.eye(D), phi)
+    np.testing.assert_allclose(p_jax, ridge * np.eye(D) + phi.T @ phi, rtol=1e-12)
+    m = 0.9
+    np.testing.assert_allclose(og.precision_update_jax(ridge * np.eye(D), phi, m),
+                               m * ridge * np.eye(D) + (1 - m) * phi.T @ phi / B, rtol=1e-12)
+    q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    np.testing.assert_allclose(og.precision_update_jax(ridge * np.eye(D), q), (1 + ridge) * np.eye(D), atol=1e-10)
+    full = og.predictive_covariance_jax(phi, p_jax, ridge, diagonal_only=False)
+    np.testing.assert_allclose(og.predictive_covariance_jax(phi, p_jax, ridge), np.diag(full), rtol=1e-10)
+    p_tf = og.precision_update_tf(np.zeros((D, D)), phi, momentum=-1)
+    cov_tf = og.predictive_covariance_tf(phi, og.covariance_tf(p_tf, ridge), ridge)
+    np.testing.assert_allclose(cov_tf, full, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(og.predictive_variance(phi, og.covariance_tf(p_tf, ridge), ridge), np.diag(cov_tf), rtol=1e-10)
+    with pytest.raises(ValueError):
+        og.precision_update_tf(p_tf, phi, logits=np.zeros((B, 3)), likelihood="poisson")
+
+
+def test_primal_equals_dual_posterior():
+    """jax random_feature_test.py:155-180: the random-feature (primal) posterior variance equals the kernel (dual) form
+    K** - K*ᵀ (K + ridge I)^-1 K* with K = ΦΦᵀ (max diff < 1e-6)."""
+    rng = np.random.default_rng(4)
+    D, ridge = 32, 1.0
+    phi_tr, phi_ts = rng.standard_normal((50, D)) / np.sqrt(D), rng.standard_normal((20, D)) / np.sqrt(D)
+    prec = ridge * np.eye(D) + phi_tr.T @ phi_tr
+    primal = og.predictive_covariance_jax(phi_ts, prec, ridge, diagonal_only=False)
+    k_tr, k_x, k_ts = phi_tr @ phi_tr.T, phi_tr @ phi_ts.T, phi_ts @ phi_ts.T
+    dual = k_ts - k_x.T @ np.linalg.solve(k_tr + ridge * np.eye(50), k_x)
+    assert np.abs(primal - dual).max() < 1e-6
+
+
+def test_rff_approximates_rbf_kernel():
+    """jax random_feature_test.py:284-302: Φ Φᵀ approximates exp(-|x-y|^2 / 2) (atol 5e-2, D = 10240)."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((10, 6)) * 0.7
+    D = 10240
+    phi, _ = og.rff(x, rng.standard_normal((6, D)), rng.uniform(0, 2 * np.pi, D), np.sqrt(2.0 / D))
+    d2 = ((x[:, None] - x[None]) ** 2).sum(-1)
+    np.testing.assert_allclose(phi @ phi.T, np.exp(-d2 / 2), atol=5e-2)
+
+
+def test_spectral_norm_variants_agree_and_converge():
+    """normalization_test.py:68-102; jax normalization_test.py:52-104: sigma -> largest singular value, normalised
+    kernel has spectral norm min(sigma, c); the TF and JAX formulations compute the same iteration."""
+    rng = np.random.default_rng(6)
+    w, u, v = rng.standard_normal((30, 20)), rng.standard_normal(20), rng.standard_normal(30)
+    wt, ut, vt, st = og.spectral_norm_tf(w, u, v, 200, 0.95)
+    wj, uj, vj, sj = og.spectral_norm_jax(w, u, v, 200, 0.95)
+    s_true = np.linalg.svd(w, compute_uv=False)[0]
+    assert abs(st - s_true) < 1e-6 * s_true and abs(sj - s_true) < 1e-6 * s_true
+    np.testing.assert_allclose(wt, wj, rtol=1e-9)
+    assert abs(np.linalg.svd(wt, compute_uv=False)[0] - 0.95) < 1e-6
+    small = w * (0.5 / s_true)
+    ws, _, _, _ = og.spectral_norm_tf(small, u, v, 200, 0.95)
+    np.testing.assert_allclose(ws, small)
+    w1, _, _, s1 = og.spectral_norm_tf(w, u, v, 1, 0.95, training=False)
+    assert abs(s1 - float(v.reshape(1, -1) @ w @ u.reshape(-1, 1))) < 1e-12
+
+
+def test_golden_vectors_pin_the_oracle():
+    g = np.load(os.path.join(GOLD, "oracle_vectors.npz"))
+    y, _ = od.batch_ensemble_fwd(g["be_x"], g["be_w"], g["be_alpha"], g["be_gamma"], g["be_bias"], "relu")
+    np.testing.assert_allclose(y, g["be_y"], rtol=1e-12)
+    y, _ = od.reparam_fwd(g["be_x"], g["bn_mu"], g["bn_rho"], g["bn_eps"], g["bn_bias"], "relu")
+    np.testing.assert_allclose(y, g["rp_y"], rtol=1e-12)
+    y, _ = od.flipout_fwd(g["be_x"], g["bn_mu"], g["bn_rho"], g["bn_eps"], g["bn_sign_in"], g["bn_sign_out"], g["bn_bias"], "relu")
+    np.testing.assert_allclose(y, g["fl_y"], rtol=1e-12)
+    y, _, _, _ = od.rank1_fwd(g["be_x"], g["be_w"], g["r1_mu_r"], g["r1_rho_r"], g["r1_eps_r"], g["r1_mu_s"], g["r1_rho_s"],
+                              g["r1_eps_s"], g["be_bias"], "relu")
+    np.testing.assert_allclose(y, g["r1_y"], rtol=1e-12)
+    assert abs(od.normal_kl(g["bn_mu"], g["bn_rho"], 0.5, 0.7, 0.25) - float(g["kl"])) < 1e-12
+    np.testing.assert_allclose(op.normal(2026, 3, 64), g["philox_normal"], rtol=1e-14)
+    wn, _, _, sg = og.spectral_norm_tf(g["sn_w_in"], g["sn_u_in"], g["sn_v_in"], 2, 0.95, True)
+    np.testing.assert_allclose(wn, g["sn_tf_w"], rtol=1e-12)
