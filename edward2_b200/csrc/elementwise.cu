@@ -149,40 +149,52 @@ __device__ __forceinline__ float kl_elem(float mu, float sigma, float pm, float 
   return logf(ps / sigma) + (sigma * sigma + d * d) / (2.f * ps * ps) - 0.5f;
 }
 
-// One thread = one Philox block = 4 consecutive flat elements of the [rows][cols] parameter.
-__global__ void sample_weights_kernel(const float* __restrict__ mu, const float* __restrict__ rho, Noise eps,
-                                      long long rows, long long cols, int mode, void* w, int wdt, long long wld,
-                                      void* mean_out, long long mean_ld, double* kl_out, float kl_scale, Prior p) {
-  const long long n = rows * cols;
-  const long long nblk = (n + 3) >> 2;
-  const bool row_aligned = (cols & 3) == 0;
+// Lean per-element math of the sampling / gradient passes (they are issue-bound, not HBM-bound: Philox + Box-Muller
+// + softplus + KL is ~100 instructions per weight):  e = exp(rho), sigma = log1p(e) + eps, and from the same e
+// sigmoid(rho) = e / (1 + e).  KL uses log(ps) - log(sigma) with the hardware lg2 (abs err 2^-21 near 1, 2 ulp away).
+__device__ __forceinline__ float sigma_from_rho(float rho, float& e) {
+  e = __expf(fminf(rho, 80.f));
+  return (rho > 20.f ? rho : log1pf(e)) + kSoftplusEps;
+}
+__device__ __forceinline__ float kl_fast(float mu, float sigma, float pm, float log_ps, float inv_2s2) {
+  const float d = mu - pm;
+  return log_ps - __logf(sigma) + (sigma * sigma + d * d) * inv_2s2 - 0.5f;
+}
+
+// Thread = 4 consecutive columns of one row (= one Philox block when cols % 4 == 0); blockIdx.y strides over rows,
+// so no index division is needed for the pitched output.
+template <bool kWantKl>
+__global__ void __launch_bounds__(kBlock) sample_weights_kernel(const float* __restrict__ mu,
+                                                                const float* __restrict__ rho, Noise eps, int rows,
+                                                                int cols, int mode, void* w, int wdt, long long wld,
+                                                                void* mean_out, long long mean_ld, double* kl_out,
+                                                                float kl_scale, Prior p) {
+  const int c = (blockIdx.x * kBlock + threadIdx.x) * 4;
+  const int valid = min(4, cols - c);
+  const float log_ps = __logf(p.stddev), inv_2s2 = 0.5f / (p.stddev * p.stddev);
+  const long long n = (long long)rows * cols;
   float kl = 0.f;
-  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
-    const long long i = b << 2;
-    const int valid = static_cast<int>(min(4LL, n - i));
-    float m[4], r[4], e[4], o[4];
-    ld4(mu, kF32, i, valid, m);
-    ld4(rho, kF32, i, valid, r);
-    noise4<0>(eps, i, n, e);
+  if (valid > 0) {
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+      const long long i = (long long)r * cols + c;
+      float m[4], rh[4], e[4], o[4];
+      ld4(mu, kF32, i, valid, m);
+      ld4(rho, kF32, i, valid, rh);
+      if ((i & 3) == 0) noise4<0>(eps, i, n, e);
+      else
+        for (int j = 0; j < 4; ++j) e[j] = j < valid ? noise1<0>(eps, i + j) : 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float sigma = softplus_f(r[j]) + kSoftplusEps;
-      o[j] = mode == 0 ? fmaf(sigma, e[j], m[j]) : sigma * e[j];
-      if (kl_out != nullptr && j < valid) kl += kl_elem(m[j], sigma, p.mean, p.stddev);
-    }
-    if (row_aligned) {
-      const long long rr = i / cols, cc = i - rr * cols;
-      st4(w, wdt, rr * wld + cc, valid, o);
-      if (mean_out != nullptr) st4(mean_out, wdt, rr * mean_ld + cc, valid, m);
-    } else {
-      for (int j = 0; j < valid; ++j) {
-        const long long rr = (i + j) / cols, cc = (i + j) - rr * cols;
-        st1(w, wdt, rr * wld + cc, o[j]);
-        if (mean_out != nullptr) st1(mean_out, wdt, rr * mean_ld + cc, m[j]);
+      for (int j = 0; j < 4; ++j) {
+        float ex;
+        const float sigma = sigma_from_rho(rh[j], ex);
+        o[j] = mode == 0 ? fmaf(sigma, e[j], m[j]) : sigma * e[j];
+        if (kWantKl && j < valid) kl += kl_fast(m[j], sigma, p.mean, log_ps, inv_2s2);
       }
+      st4(w, wdt, (long long)r * wld + c, valid, o);
+      if (mean_out != nullptr) st4(mean_out, wdt, (long long)r * mean_ld + c, valid, m);
     }
   }
-  if (kl_out != nullptr) block_atomic_add(kl_out, kl, kl_scale);
+  if (kWantKl) block_atomic_add(kl_out, kl, kl_scale);
 }
 
 __global__ void normal_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ rho, long long n, Prior p,
@@ -226,9 +238,11 @@ __global__ void normal_kl_bwd_kernel(const float* __restrict__ mu, const float* 
   }
 }
 
-__global__ void normal_grad_finish_kernel(const float* d_mean, const float* d_pert, const float* __restrict__ mu,
-                                          const float* __restrict__ rho, Noise eps, long long n, float klg_in,
-                                          const float* kl_upstream, Prior p, float* dmu, float* drho) {
+__global__ void __launch_bounds__(kBlock) normal_grad_finish_kernel(const float* d_mean, const float* d_pert,
+                                                                    const float* __restrict__ mu,
+                                                                    const float* __restrict__ rho, Noise eps,
+                                                                    long long n, float klg_in, const float* kl_upstream,
+                                                                    Prior p, float* dmu, float* drho) {
   const float klg = klg_in * (kl_upstream != nullptr ? *kl_upstream : 1.f);
   const float inv_s2 = 1.f / (p.stddev * p.stddev);
   const long long nblk = (n + 3) >> 2;
@@ -243,9 +257,11 @@ __global__ void normal_grad_finish_kernel(const float* d_mean, const float* d_pe
     noise4<0>(eps, i, n, e);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float sigma = softplus_f(r[j]) + kSoftplusEps;
+      float ex;
+      const float sigma = sigma_from_rho(r[j], ex);
+      const float sgm = __fdividef(ex, 1.f + ex);  // sigmoid(rho)
       om[j] = gm[j] + klg * (m[j] - p.mean) * inv_s2;
-      orr[j] = (gp[j] * e[j] + klg * (sigma * inv_s2 - 1.f / sigma)) * sigmoid_f(r[j]);
+      orr[j] = (gp[j] * e[j] + klg * (sigma * inv_s2 - __fdividef(1.f, sigma))) * sgm;
     }
     st4(dmu, kF32, i, valid, om);
     st4(drho, kF32, i, valid, orr);
@@ -343,6 +359,7 @@ __device__ __forceinline__ void reduce_cols_and_add(float (&a0)[4], float (&a1)[
   }
 }
 
+template <int kFast>
 __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks_per_member = (a.rows_per_member + kRowsPerBlock - 1) / kRowsPerBlock;
@@ -355,8 +372,8 @@ __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
   float acc_mu[4] = {0, 0, 0, 0}, acc_rho[4] = {0, 0, 0, 0}, acc_b[4] = {0, 0, 0, 0};
   float gam[4] = {1, 1, 1, 1}, mus[4], rhos[4], sig_s[4], sgm_s[4];
   if (valid > 0) {
-    if (a.fast == 1) ld4(a.gamma, kF32, (long long)e * a.cols + c, valid, gam);
-    if (a.fast == 2) {
+    if (kFast == 1) ld4(a.gamma, kF32, (long long)e * a.cols + c, valid, gam);
+    if (kFast == 2) {
       ld4(a.mu_s, kF32, (long long)e * a.cols + c, valid, mus);
       if (a.rho_s != nullptr) {
         ld4(a.rho_s, kF32, (long long)e * a.cols + c, valid, rhos);
@@ -365,7 +382,33 @@ __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
       }
     }
   }
-  if (valid > 0) {
+  if (kFast == 0 && valid > 0) {
+    // plain layer: 4 rows per iteration so that 8 independent 8/16-byte loads are in flight per thread
+    constexpr int kStep = kBlock / 32;
+    for (long long r = row0 + warp; r < row_end; r += 4 * kStep) {
+      float g[4][4], y[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + u * kStep;
+        if (rr < row_end) {
+          ld4(a.gy, a.dt, rr * a.gy_ld + c, valid, g[u]);
+          if (a.act == kActRelu) ld4(a.y, a.dt, rr * a.y_ld + c, valid, y[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + u * kStep;
+        if (rr < row_end) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (a.act == kActRelu) g[u][j] = y[u][j] > 0.f ? g[u][j] : 0.f;
+            acc_b[j] += g[u][j];
+          }
+          st4(a.dz, a.dt, rr * a.dz_ld + c, valid, g[u]);
+        }
+      }
+    }
+  } else if (valid > 0) {
     for (long long r = row0 + warp; r < row_end; r += kBlock / 32) {
       float g[4], y[4];
       ld4(a.gy, a.dt, r * a.gy_ld + c, valid, g);
@@ -377,15 +420,15 @@ __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc_b[j] += g[j];
       float dz[4];
-      if (a.fast == 0) {
+      if (kFast == 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) dz[j] = g[j];
-      } else if (a.fast == 1) {
+      } else if (kFast == 1) {
         float z[4];
         ld4(a.z, a.dt, r * a.z_ld + c, valid, z);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { dz[j] = g[j] * gam[j]; acc_mu[j] += g[j] * z[j]; }
-      } else if (a.fast == 2) {
+      } else if (kFast == 2) {
         float z[4], sv[4];
         ld4(a.z, a.dt, r * a.z_ld + c, valid, z);
         ld4(a.s_buf, a.dt, r * a.s_ld + c, valid, sv);
@@ -553,8 +596,15 @@ int k_sample_weights(const float* mu, const float* rho, Noise eps, long long row
                      int wdt, long long wld, void* mean_out, long long mean_ld, double* kl_out, float kl_scale,
                      Prior p, cudaStream_t s) {
   if (rows <= 0 || cols <= 0) return ED2_OK;
-  sample_weights_kernel<<<grid_for((rows * cols + 3) / 4), kBlock, 0, s>>>(mu, rho, eps, rows, cols, mode, w, wdt, wld,
-                                                                          mean_out, mean_ld, kl_out, kl_scale, p);
+  const int gx = static_cast<int>((cols + 4 * kBlock - 1) / (4 * kBlock));
+  const int gy = static_cast<int>(std::min<long long>(rows, std::max(1, kMaxGrid / gx)));
+  dim3 grid(gx, gy);
+  if (kl_out != nullptr)
+    sample_weights_kernel<true><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld, mean_out,
+                                                        mean_ld, kl_out, kl_scale, p);
+  else
+    sample_weights_kernel<false><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld, mean_out,
+                                                         mean_ld, kl_out, kl_scale, p);
   count_launch();
   return check_launch("sample_weights");
 }
@@ -607,7 +657,12 @@ int k_bwd_out(const BwdOutArgs& a_in, cudaStream_t s) {
   if (a.dbias) cudaMemsetAsync(a.dbias, 0, bytes, s);
   const int chunks = (a.rows_per_member + kRowsPerBlock - 1) / kRowsPerBlock;
   dim3 grid((a.cols + 127) / 128, members * chunks);
-  bwd_out_kernel<<<grid, kBlock, 0, s>>>(a);
+  switch (a.fast) {
+    case 0: bwd_out_kernel<0><<<grid, kBlock, 0, s>>>(a); break;
+    case 1: bwd_out_kernel<1><<<grid, kBlock, 0, s>>>(a); break;
+    case 2: bwd_out_kernel<2><<<grid, kBlock, 0, s>>>(a); break;
+    default: bwd_out_kernel<3><<<grid, kBlock, 0, s>>>(a); break;
+  }
   count_launch();
   return check_launch("bwd_out");
 }

@@ -60,7 +60,8 @@ __host__ __device__ __forceinline__ float u32_to_uniform(uint32_t x) {
 
 __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& z0, float& z1) {
   const float u0 = u32_to_uniform(x0), u1 = u32_to_uniform(x1);
-  const float r = sqrtf(-2.0f * logf(u0));
+  float r;  // sqrt.approx (1 ulp): the IEEE sqrtf costs a fix-up sequence and a slow-path call per draw
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * logf(u0)));
   float s, c;
   sincospif(2.0f * u1, &s, &c);
   z0 = r * c;

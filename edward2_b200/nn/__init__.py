@@ -1,1 +1,15 @@
-"""JAX / Flax call signatures of the reference (`edward2.jax.nn.*`) on libed2b200 (filled in by nn/*.py)."""
+"""JAX / Flax call signatures of the reference (`edward2.jax.nn.*`) on libed2b200.
+
+The JAX backend of the reference exports DenseBatchEnsemble, RandomFeatureGaussianProcess, RandomFourierFeatures,
+LaplaceRandomFeatureCovariance, SpectralNormalization and utils (edward2/jax/nn/__init__.py:18-53); it has no
+DenseRank1 / DenseFlipout / DenseReparameterization.
+"""
+from . import utils
+from .dense import DenseBatchEnsemble
+from .module import Module
+from .normalization import Dense, SpectralNormalization
+from .random_feature import LaplaceRandomFeatureCovariance, RandomFeatureGaussianProcess, RandomFourierFeatures
+from .utils import make_sign_initializer, mean_field_logits
+
+__all__ = ["Module", "Dense", "DenseBatchEnsemble", "SpectralNormalization", "LaplaceRandomFeatureCovariance",
+           "RandomFeatureGaussianProcess", "RandomFourierFeatures", "make_sign_initializer", "mean_field_logits", "utils"]
