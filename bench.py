@@ -135,6 +135,11 @@ def make_step(layers, global_batch):
     from edward2_b200 import functional as F
 
     def step(x, labels):
+        # scheduling hint: draw the kernel samples of the later layers on side streams now, so the issue-bound sampling
+        # passes overlap the first layers' GEMMs (same Philox streams as without the hint)
+        for l in layers[1:]:
+            if hasattr(l, "presample"):
+                l.presample()
         h = x
         for l in layers:
             h = l(h)
@@ -193,7 +198,7 @@ def run_ours(args):
             for p in params:
                 p.grad = None
 
-        use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+        use_graph = args.graph in ("on", "auto")
         graph, static_loss = None, None
 
         def eager_step(x, y):
@@ -221,10 +226,19 @@ def run_ours(args):
         torch.cuda.synchronize()
         if use_graph:
             zero()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                step_counter.add_(1)
-                static_loss = raw_step(x_static, y_static)
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    step_counter.add_(1)
+                    static_loss = raw_step(x_static, y_static)
+                    for h in handles:      # join the NCCL all-reduces into the captured step
+                        h.wait()
+                    handles.clear()
+            except Exception as e:  # noqa: BLE001  (e.g. a collective that cannot be captured) -> eager steps
+                sys.stderr.write(f"[bench] CUDA-graph capture failed, running eagerly: {str(e)[:300]}\n")
+                graph, static_loss = None, None
+                handles.clear()
+                torch.cuda.synchronize()
 
         def run_step():
             if graph is not None:
@@ -257,18 +271,41 @@ def run_ours(args):
 
         e2e_ms = None
         if want_e2e:
-            # end to end through the public layer API with HOST buffers: H2D of the batch, step, D2H of the loss
-            loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-            for _ in range(2):
-                x_static.copy_(x_host, non_blocking=True)
-                y_static.copy_(y_host, non_blocking=True)
-                loss_host.copy_(run_step(), non_blocking=True)
+            # end to end through the public layer API with HOST buffers: every step copies ITS batch from pinned host
+            # memory (H2D on a copy stream into one of two staging slots, overlapping the previous step's compute),
+            # runs the step and reads the loss back (D2H)
+            loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+            copy_stream = torch.cuda.Stream()
+            xs, ys = [x_dev.clone(), x_dev.clone()], [y_dev.clone(), y_dev.clone()]
+            ev_h2d = [torch.cuda.Event(), torch.cuda.Event()]
+            ev_used = [torch.cuda.Event(), torch.cuda.Event()]
+            main = torch.cuda.current_stream()
+            for ev in ev_used:
+                ev.record(main)
+
+            def prefetch(i):
+                slot = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev_used[slot])
+                    xs[slot].copy_(x_host, non_blocking=True)
+                    ys[slot].copy_(y_host, non_blocking=True)
+                    ev_h2d[slot].record(copy_stream)
+
+            def e2e_loop(n):
+                prefetch(0)
+                for i in range(n):
+                    prefetch(i + 1)
+                    slot = i % 2
+                    main.wait_event(ev_h2d[slot])
+                    x_static.copy_(xs[slot], non_blocking=True)
+                    y_static.copy_(ys[slot], non_blocking=True)
+                    ev_used[slot].record(main)
+                    loss_host.copy_(run_step().to(torch.float64), non_blocking=True)
+
+            e2e_loop(2)
             sync_all()
             e0.record()
-            for _ in range(steps):
-                x_static.copy_(x_host, non_blocking=True)
-                y_static.copy_(y_host, non_blocking=True)
-                loss_host.copy_(run_step(), non_blocking=True)
+            e2e_loop(steps)
             e1.record()
             sync_all()
             t = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
@@ -361,7 +398,7 @@ def run_ours(args):
                    "cuda_graph": main["graph"], "kl_scale": KL_SCALE},
         "e2e": {"value": global_batch / (main["e2e_ms"] * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": (x_host.numel() * 2 + y_host.numel() * 8) * world,
-                "d2h_bytes_per_step": 4 * world, "ms_per_step": main["e2e_ms"]},
+                "d2h_bytes_per_step": 8 * world, "ms_per_step": main["e2e_ms"]},
         "gpu_launches": main["launches"],
         "clocks": clocks,
         "roofline": roof,

@@ -40,6 +40,8 @@ class GemmDesc(C.Structure):
         ("out", _vp), ("out_ld", _i), ("out_dtype", _i),
         ("raw", _vp), ("raw_ld", _i), ("raw_dtype", _i),
         ("row_sum", _vp),
+        ("mask_src", _vp), ("mask_ld", _i), ("mask_dtype", _i),
+        ("col_sum", _vp), ("col_sum_ld", _i),
         ("block_n", _i), ("cta_group", _i), ("max_ctas", _i), ("no_tma_store", _i),
     ]
 
@@ -107,6 +109,7 @@ class ReparamBwd(C.Structure):
         ("gp", _vp), ("gp_ld", _i), ("dx", _vp), ("dx_ld", _i),
         ("dmu", _vp), ("drho", _vp), ("dbias", _vp),
         ("kl_grad_scale", _f), ("prior_mean", _f), ("prior_std", _f), ("kl_upstream", _vp),
+        ("gy_premasked", _i), ("x_is_relu", _i), ("prev_dbias", _vp),
     ]
 
 

@@ -65,6 +65,46 @@ int gemm_xtg(int dt, const void* x, int x_ld, const void* gz, int g_ld, int B, i
   return gemm(dt, g, s);
 }
 
+// Fork-join onto a per-thread side stream (capturable: the side stream joins the caller's capture through events).
+class ForkJoin {
+ public:
+  ForkJoin(cudaStream_t main, bool enable) : main_(main), on_(enable) {
+    if (!on_) return;
+    Ctx& c = ctx();
+    if (c.side == nullptr) {
+      if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c.joined, cudaEventDisableTiming) != cudaSuccess) {
+        c.side = nullptr;
+        on_ = false;
+        return;
+      }
+    }
+    if (cudaEventRecord(c.fork, main_) != cudaSuccess || cudaStreamWaitEvent(c.side, c.fork, 0) != cudaSuccess) on_ = false;
+  }
+  cudaStream_t side() { return on_ ? ctx().side : main_; }
+  void join() {
+    if (!on_) return;
+    Ctx& c = ctx();
+    cudaEventRecord(c.joined, c.side);
+    cudaStreamWaitEvent(main_, c.joined, 0);
+    on_ = false;
+  }
+  ~ForkJoin() { join(); }
+
+ private:
+  struct Ctx {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, joined = nullptr;
+  };
+  static Ctx& ctx() {
+    thread_local Ctx c;
+    return c;
+  }
+  cudaStream_t main_;
+  bool on_;
+};
+
 }  // namespace
 
 extern "C" {
@@ -98,6 +138,8 @@ int ed2_gemm(const ed2_gemm_desc* d, void* stream) {
   e.out = d->out; e.out_ld = d->out_ld; e.out_dt = d->out_dtype;
   e.raw = d->raw; e.raw_ld = d->raw_ld; e.raw_dt = d->raw_dtype;
   e.row_sum = d->row_sum;
+  e.mask_src = d->mask_src; e.mask_ld = d->mask_ld; e.mask_dt = d->mask_dtype;
+  e.col_sum = d->col_sum; e.col_sum_ld = d->col_sum_ld;
   g.block_n = d->block_n; g.cta_group = d->cta_group; g.max_ctas = d->max_ctas; g.no_tma_store = d->no_tma_store;
   return gemm(d->dtype, g, S(stream));
 }
@@ -255,24 +297,41 @@ int ed2_reparam_dense_fwd(const ed2_reparam_fwd_args* a, void* stream) {
 int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
   ED2_TRY(check_dt(a->dtype));
   cudaStream_t s = S(stream);
-  BwdOutArgs o{};
-  o.dt = a->dtype; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = a->batch; o.act = a->act; o.fast = 0;
-  o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld;
-  o.dz = a->gp; o.dz_ld = a->gp_ld;
-  o.dbias = a->dbias;
-  ED2_TRY(k_bwd_out(o, s));
+  const void* gp = a->gp;
+  int gp_ld = a->gp_ld;
+  if (a->gy_premasked) {
+    gp = a->gy;  // the producer's dX epilogue already applied act'(y) and accumulated dbias
+    gp_ld = a->gy_ld;
+  } else {
+    BwdOutArgs o{};
+    o.dt = a->dtype; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = a->batch; o.act = a->act; o.fast = 0;
+    o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld;
+    o.dz = a->gp; o.dz_ld = a->gp_ld;
+    o.dbias = a->dbias;
+    ED2_TRY(k_bwd_out(o, s));
+  }
   // dW = xᵀ gp lands in dmu; the finishing pass turns it into (dmu, drho) in place.
   EpiParams e = epi_default();
   e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
-  ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, a->gp, a->gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, gp, gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  // fork: the finishing pass (CUDA cores, issue-bound) runs beside the dX GEMM (tensor cores) on a side stream
+  ForkJoin fj(s, a->dx != nullptr);
   ED2_TRY(k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
-                               a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho, s));
+                               a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
+                               fj.side()));
+  int st = ED2_OK;
   if (a->dx != nullptr) {
     EpiParams e2 = epi_default();
     e2.out = a->dx; e2.out_ld = a->dx_ld; e2.out_dt = a->dtype;
-    ED2_TRY(gemm_gwt(a->dtype, a->gp, a->gp_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s));
+    if (a->x_is_relu && a->prev_dbias != nullptr) {
+      cudaMemsetAsync(a->prev_dbias, 0, sizeof(float) * (size_t)a->in_dim, s);
+      e2.mask_src = a->x; e2.mask_ld = a->x_ld; e2.mask_dt = a->dtype;
+      e2.col_sum = a->prev_dbias; e2.col_sum_ld = a->in_dim;
+    }
+    st = gemm_gwt(a->dtype, gp, gp_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s);
   }
-  return ED2_OK;
+  fj.join();
+  return st;
 }
 
 // ------------------------------------------------------------------------------------------ Flipout

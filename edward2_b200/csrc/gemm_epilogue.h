@@ -15,6 +15,8 @@ enum : int { kF32 = 0, kBF16 = 1 };
 //   v += beta * addend[m,n]                        (Flipout mean term, momentum blend of the precision)
 //   v += col_bias[(m / group_rows), n]
 //   v = act(v)                                     (none | relu | cos(v) * act_scale)
+//   v = mask_src[m,n] > 0 ? v : 0                  (optional: ReLU backward of the layer that produced A's consumer input)
+//   col_sum[g(m), n] += sum_m v                    (optional; fp32 atomics: bias gradient of that layer)
 //   out[m,n] = v                                   (skipped when out == nullptr)
 //   row_sum[m] += sum_n v                          (optional; fp32 atomicAdd, one per row per tile)
 struct EpiParams {
@@ -41,6 +43,11 @@ struct EpiParams {
   int raw_ld;
   int raw_dt;
   float* row_sum;
+  const void* mask_src;
+  int mask_ld;
+  int mask_dt;
+  float* col_sum;
+  int col_sum_ld;
 };
 
 }  // namespace ed2

@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       if (ep.col_bias) v += ep.col_bias[(long long)grp * ep.col_bias_ld + n];
       if (ep.act == kActRelu) v = fmaxf(v, 0.f);
       else if (ep.act == kActCos) v = cosf(v) * ep.act_scale;
+      if (ep.mask_src && !(ld_elem(ep.mask_src, ep.mask_dt, (long long)m * ep.mask_ld + n) > 0.f)) v = 0.f;
       if (ep.out) st_elem(ep.out, ep.out_dt, (long long)m * ep.out_ld + n, v);
+      if (ep.col_sum) atomicAdd(ep.col_sum + (long long)grp * ep.col_sum_ld + n, v);
       rs += v;
     }
     if (ep.row_sum) atomicAdd(ep.row_sum + m, rs);

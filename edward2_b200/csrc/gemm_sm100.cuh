@@ -194,6 +194,33 @@ __device__ __forceinline__ void store_row32(void* base, int dt, long long row_of
   }
 }
 
+
+// Column sums of a 32-row x 32-column register tile (one row per lane): butterfly transpose-reduce, 31 shuffles;
+// lane j ends with the sum of column j over the warp's 32 rows and issues one atomic.  All 32 rows of a warp must
+// belong to the same group (the host only enables col_sum when group_rows is 0 or a multiple of 32).
+__device__ __forceinline__ void col_sum_chunk(const EpiParams& ep, float (&v)[32], bool active, int warp_row0, int nc,
+                                              int N, uint32_t lane) {
+  if (!active) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  const int n = nc + static_cast<int>(lane);
+  if (n < N) {
+    const int grp = ep.group_rows > 0 ? warp_row0 / ep.group_rows : 0;
+    atomicAdd(ep.col_sum + static_cast<long long>(grp) * ep.col_sum_ld + n, v[0]);
+  }
+}
+
 template <int kMajorA, int kMajorB, int BLOCK_N, int kCtaGroup>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -392,6 +419,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
 
+        if (ep.mask_src != nullptr && active) {
+          float s[32];
+          load_row32(ep.mask_src, ep.mask_dt, static_cast<long long>(m) * ep.mask_ld, nc, n_valid, s);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = s[j] > 0.f ? v[j] : 0.f;
+        }
         if (ep.row_sum != nullptr && active) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) row_acc += (j < n_valid ? v[j] : 0.f);
@@ -399,6 +432,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (!ep.out_tma) {
           if (active && ep.out != nullptr)
             store_row32(ep.out, ep.out_dt, static_cast<long long>(m) * ep.out_ld, nc, n_valid, v);
+          if (ep.col_sum != nullptr) col_sum_chunk(ep, v, active, m0 + ew * 32, nc, N, lane);
           continue;
         }
         // ---- staged store: swizzled smem (conflict-free 16-byte chunks) + one TMA store per buffer.
@@ -427,6 +461,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                               __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
           }
         }
+        if (ep.col_sum != nullptr) col_sum_chunk(ep, v, active, m0 + ew * 32, nc, N, lane);
         if (!is_bf16 || sub == 1) {
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(1, kEpiThreads);

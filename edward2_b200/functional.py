@@ -184,19 +184,57 @@ class Rank1Dense(torch.autograd.Function):
         return dx, dw, dmu_r, drho_r, dmu_s, drho_s, dbias, None, None, None, None, None
 
 
+class ReluLink:
+    """Cross-layer fusion token.  A layer whose fused activation is ReLU attaches one to its output tensor; the layer
+    that consumes that tensor applies relu'(x) = (x > 0) and the bias-gradient column sums in its own dX GEMM epilogue
+    and records the result here, so the producing layer's backward can skip its output-side pass.  Matching is by the
+    gradient tensor's data pointer: anything else (fan-out, intermediate ops, dtype casts) falls back to the unfused
+    path, which is always correct because the ReLU mask is idempotent."""
+
+    __slots__ = ("dx_ptr", "dbias")
+
+    def __init__(self):
+        self.dx_ptr, self.dbias = None, None
+
+
+def take_link(t: torch.Tensor):
+    return getattr(t, "_ed2_relu_link", None)
+
+
+def attach_link(t: torch.Tensor, link) -> torch.Tensor:
+    if link is not None:
+        t._ed2_relu_link = link
+    return t
+
+
 # ------------------------------------------------------------------------------------------------- Reparameterization
 class ReparamDense(torch.autograd.Function):
     """Returns (y, kl): kl = kl_scale * KL(q||p) accumulated in the sampling pass (0-dim fp32)."""
 
     @staticmethod
-    def forward(ctx, x, mu, rho, bias, act, dtype, eps, kl_scale, prior_mean, prior_std):
+    def forward(ctx, x, mu, rho, bias, act, dtype, eps, kl_scale, prior_mean, prior_std, in_link=None, out_link=None,
+                presampled=None):
         lib = _lib.load()
         B, I = x.shape
         O = mu.shape[1]
         dev = x.device
         xc = as_compute(x, dtype)
-        w_lp, y = _new(I, O, dtype, dev), _new(B, O, dtype, dev)
-        kl64 = torch.zeros((), dtype=torch.float64, device=dev) if kl_scale != 0 else None
+        if xc.data_ptr() != x.data_ptr():
+            in_link = None  # the mask must be read from the very tensor the producer wrote
+        y = _new(B, O, dtype, dev)
+        if presampled is not None:
+            w_lp, kl64 = presampled  # drawn ahead of time on a side stream by layer.presample()
+        else:
+            w_lp = _new(I, O, dtype, dev)
+            kl64 = torch.zeros((), dtype=torch.float64, device=dev) if kl_scale != 0 else None
+        ctx.links = (in_link, out_link)
+        if presampled is not None:
+            ops.gemm(xc, w_lp, B, O, I, major_a=ops.MAJOR_K, major_b=ops.MAJOR_MN, out=y, act=act,
+                     col_bias=bias.reshape(1, -1) if bias is not None else None)
+            ctx.save_for_backward(xc, y, w_lp, mu, rho)
+            ctx.meta = (act, dtype, bias is not None, x.dtype, eps, kl_scale, prior_mean, prior_std)
+            ctx.set_materialize_grads(False)
+            return y, (kl64 if kl64 is not None else torch.zeros((), dtype=torch.float64, device=dev))
         a = _lib.ReparamFwd()
         a.dtype, a.batch, a.in_dim, a.out_dim, a.act = _compute_dt(dtype), B, I, O, act
         a.x, a.x_ld = xc.data_ptr(), _lib.ld(xc)
@@ -207,39 +245,51 @@ class ReparamDense(torch.autograd.Function):
         ctx.save_for_backward(xc, y, w_lp, mu, rho)
         ctx.meta = (act, dtype, bias is not None, x.dtype, eps, kl_scale, prior_mean, prior_std)
         ctx.set_materialize_grads(False)
-        kl = kl64.to(torch.float32) if kl64 is not None else torch.zeros((), device=dev)
-        return y, kl
+        # the KL stays fp64 (the accumulator's type): no conversion kernels on the step's critical path
+        return y, (kl64 if kl64 is not None else torch.zeros((), dtype=torch.float64, device=dev))
 
     @staticmethod
     def backward(ctx, gy, gkl):
         lib = _lib.load()
         xc, y, w_lp, mu, rho = ctx.saved_tensors
         act, dtype, has_bias, x_dtype, eps, kl_scale, pm, ps = ctx.meta
+        in_link, out_link = ctx.links
         B, I = xc.shape
         O = y.shape[1]
         dev = xc.device
         if gy is None:
             gy = torch.zeros(B, O, dtype=dtype, device=dev)
         gyc = as_compute(gy, dtype)
-        gp = _new(B, O, dtype, dev)
-        dx = _new(B, I, dtype, dev) if ctx.needs_input_grad[0] else None
+        premasked = (out_link is not None and out_link.dx_ptr is not None and out_link.dx_ptr == gyc.data_ptr()
+                     and gyc.shape == y.shape)
+        gp = None if premasked else _new(B, O, dtype, dev)
+        need_dx = ctx.needs_input_grad[0]
+        dx = _new(B, I, dtype, dev) if need_dx else None
         dmu = torch.empty(I, O, dtype=torch.float32, device=dev)
         drho = torch.empty(I, O, dtype=torch.float32, device=dev)
-        dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
-        up = gkl.to(torch.float32).reshape(1).contiguous() if gkl is not None else None
+        if premasked:
+            dbias = out_link.dbias if has_bias else None
+        else:
+            dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
+        fuse_prev = need_dx and in_link is not None and dx.dtype == x_dtype
+        prev_dbias = torch.empty(I, dtype=torch.float32, device=dev) if fuse_prev else None
+        up = gkl.to(torch.float32).reshape(1) if gkl is not None else None
         a = _lib.ReparamBwd()
         a.dtype, a.batch, a.in_dim, a.out_dim, a.act = _compute_dt(dtype), B, I, O, act
         a.gy, a.gy_ld, a.y, a.y_ld, a.x, a.x_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y), xc.data_ptr(), _lib.ld(xc)
         a.w_lp, a.w_ld = w_lp.data_ptr(), _lib.ld(w_lp)
         a.mu, a.rho, a.eps = mu.data_ptr(), rho.data_ptr(), eps.c()
-        a.gp, a.gp_ld, a.dx, a.dx_ld = gp.data_ptr(), _lib.ld(gp), _p(dx), _ldn(dx)
-        a.dmu, a.drho, a.dbias = dmu.data_ptr(), drho.data_ptr(), _p(dbias)
+        a.gp, a.gp_ld, a.dx, a.dx_ld = _p(gp), _ldn(gp), _p(dx), _ldn(dx)
+        a.dmu, a.drho, a.dbias = dmu.data_ptr(), drho.data_ptr(), (None if premasked else _p(dbias))
         a.kl_grad_scale = kl_scale if gkl is not None else 0.0
         a.prior_mean, a.prior_std, a.kl_upstream = pm, ps, _p(up)
+        a.gy_premasked, a.x_is_relu, a.prev_dbias = int(premasked), int(fuse_prev), _p(prev_dbias)
         _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd")
+        if fuse_prev:
+            in_link.dx_ptr, in_link.dbias = dx.data_ptr(), prev_dbias
         if dx is not None and dx.dtype != x_dtype:
             dx = dx.to(x_dtype)
-        return dx, dmu, drho, dbias, None, None, None, None, None, None
+        return dx, dmu, drho, dbias, None, None, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------- Flipout

@@ -147,7 +147,37 @@ class DenseReparameterization(Layer):
             return r.scale_factor, r.mean, r.stddev
         return 0.0, 0.0, 1.0
 
+    def presample(self):
+        """Optional: draw this call's kernel sample (and its KL) NOW on a side stream, so that the issue-bound sampling
+        pass overlaps whatever the main stream is doing (typically the previous layer's GEMM).  The next `call` uses
+        it.  Purely a scheduling hint: the draw is the same Philox stream the un-hinted call would use."""
+        if not self.built or not _is_trainable(self.kernel_initializer):
+            return
+        mean, rho = self._kernel_params()
+        if rho is None:
+            return
+        from .. import _lib
+        import ctypes as C
+
+        kl_scale, pm, ps = self._fused_kl_args()
+        dev = mean.device
+        I, O = mean.shape
+        if not hasattr(self, "_side_stream"):
+            self._side_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        w_lp = _lib.empty_padded(I, O, self.compute_dtype, dev)
+        kl64 = torch.zeros((), dtype=torch.float64, device=dev) if kl_scale != 0 else None
+        self._side_stream.wait_stream(main)
+        with torch.cuda.stream(self._side_stream):
+            nz = self._noise("eps", S_KERNEL)
+            _lib.check(_lib.load().ed2_sample_normal_weights(
+                mean.data_ptr(), rho.data_ptr(), nz.c(), I, O, 0, w_lp.data_ptr(), _lib.dt_of(w_lp), _lib.ld(w_lp),
+                None, 0, None if kl64 is None else kl64.data_ptr(), kl_scale, pm, ps, _lib.stream_ptr()),
+                "ed2_sample_normal_weights")
+        self._presampled = (w_lp, kl64, nz)
+
     def call(self, inputs, training=None):
+        in_link = F.take_link(inputs)
         x, lead = flatten_batch(inputs)
         mean, rho = self._kernel_params()
         bias = self._bias_value()
@@ -155,10 +185,23 @@ class DenseReparameterization(Layer):
             y = F.Dense.apply(x, mean, bias, self._act, self.compute_dtype, None)
             return y.reshape(*lead, self.units)
         kl_scale, pm, ps = self._fused_kl_args()
-        y, kl = F.ReparamDense.apply(x, mean, rho, bias, self._act, self.compute_dtype,
-                                     self._noise("eps", S_KERNEL), kl_scale, pm, ps)
+        fusable = len(lead) == 1 and not _is_trainable(self.bias_initializer)
+        out_link = F.ReluLink() if (fusable and self._act == ops.ACT_RELU) else None
+        pre = getattr(self, "_presampled", None)
+        self._presampled = None
+        if pre is not None:
+            w_lp, kl64, nz = pre
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            y, kl = F.ReparamDense.apply(x, mean, rho, bias, self._act, self.compute_dtype, nz, kl_scale, pm, ps,
+                                         in_link if fusable else None, out_link, (w_lp, kl64))
+        else:
+            y, kl = F.ReparamDense.apply(x, mean, rho, bias, self._act, self.compute_dtype,
+                                         self._noise("eps", S_KERNEL), kl_scale, pm, ps,
+                                         in_link if fusable else None, out_link, None)
         if kl_scale != 0.0:
             self._kl.set(kl, mean, rho)
+        if len(lead) == 1:
+            return F.attach_link(y, out_link)
         return y.reshape(*lead, self.units)
 
     @property

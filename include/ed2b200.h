@@ -63,6 +63,7 @@ int ed2_check_device(int dev);
  *   out = act( ((alpha * A·B) ∘ elem_scale ∘ col_scale[g(m)]) + beta * addend + col_bias[g(m)] )
  *   raw = alpha * A·B                      (optional)
  *   row_sum[m] += sum_n out[m,n]           (optional, fp32 atomics; `out` may then be NULL)
+ *   mask_src / col_sum: ReLU-backward mask and bias-gradient column sums fused into a dX product
  * g(m) = m / group_rows (0 when group_rows == 0).  dtype selects the engine: ED2_BF16 = tcgen05 tensor
  * cores (bf16 in, fp32 accumulate in TMEM); ED2_F32 = fp32 path (exact fp32 products, fp32 accumulate).
  * Layouts: A K-major = [M][lda], MN-major = [K][lda]; B K-major = [N][ldb], MN-major = [K][ldb]. */
@@ -81,6 +82,8 @@ typedef struct {
   void* out; int out_ld; int out_dtype;
   void* raw; int raw_ld; int raw_dtype;
   float* row_sum;
+  const void* mask_src; int mask_ld; int mask_dtype;  /* out = mask_src[m,n] > 0 ? out : 0 (applied last) */
+  float* col_sum; int col_sum_ld;                     /* col_sum[g(m), n] += sum_m out[m,n] (fp32 atomics) */
   /* tuning / test knobs, 0 = automatic */
   int block_n, cta_group, max_ctas, no_tma_store;
 } ed2_gemm_desc;
@@ -246,6 +249,11 @@ typedef struct {
   float* dbias;               /* [O] or NULL */
   float kl_grad_scale; float prior_mean; float prior_std;   /* kl_grad_scale = 0 -> no KL term */
   const float* kl_upstream;   /* optional device scalar multiplying kl_grad_scale (dLoss/dKL) */
+  /* Cross-layer fusion (optional).  gy_premasked != 0: gy already equals gy ∘ act'(y) and dbias was accumulated by the
+   * layer that produced gy (its dX epilogue) -> the output-side pass is skipped and gp is not written.
+   * x_is_relu != 0: x is the output of a ReLU layer -> dx := dx ∘ (x > 0) in the dX epilogue and prev_dbias[in_dim]
+   * (zeroed here) receives its column sums, i.e. the producing layer's bias gradient. */
+  int gy_premasked; int x_is_relu; float* prev_dbias;
 } ed2_reparam_bwd_args;
 int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream);
 
