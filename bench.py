@@ -184,14 +184,13 @@ def run_ours(args):
     def measure(flipout: bool, steps: int, warmup: int, want_e2e: bool):
         layers = build_model(ed, flipout, device, step_counter)
         params = params_of(layers)
-        handles = []
+        reducer = None
         if world > 1:
             # gradient all-reduce launched as soon as each parameter's gradient is final, overlapping the rest of
-            # the backward pass (NCCL runs on its own stream)
-            def hook(p):
-                handles.append(dist.all_reduce(p.grad, async_op=True))
-            for p in params:
-                p.register_post_accumulate_grad_hook(hook)
+            # the backward pass (NCCL runs on its own stream); bf16 buckets halve the NVLink bytes
+            from edward2_b200.dist import GradientAllReduce
+
+            reducer = GradientAllReduce(params, compress=None if args.fp32_allreduce else torch.bfloat16)
         raw_step = make_step(layers, global_batch)
 
         def zero():
@@ -205,9 +204,8 @@ def run_ours(args):
             zero()
             step_counter.add_(1)
             loss = raw_step(x, y)
-            for h in handles:
-                h.wait()
-            handles.clear()
+            if reducer is not None:
+                reducer.wait()
             return loss
 
         x_static, y_static = x_dev.clone(), y_dev.clone()
@@ -231,13 +229,13 @@ def run_ours(args):
                 with torch.cuda.graph(graph, stream=side):
                     step_counter.add_(1)
                     static_loss = raw_step(x_static, y_static)
-                    for h in handles:      # join the NCCL all-reduces into the captured step
-                        h.wait()
-                    handles.clear()
+                    if reducer is not None:  # join the NCCL all-reduces into the captured step
+                        reducer.wait()
             except Exception as e:  # noqa: BLE001  (e.g. a collective that cannot be captured) -> eager steps
                 sys.stderr.write(f"[bench] CUDA-graph capture failed, running eagerly: {str(e)[:300]}\n")
                 graph, static_loss = None, None
-                handles.clear()
+                if reducer is not None:
+                    reducer.handles.clear()
                 torch.cuda.synchronize()
 
         def run_step():
@@ -395,7 +393,9 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}",
                    "l2": "inputs > L2: one step touches ~0.6 GB (fp32 mu/rho + grads 400 MB, bf16 W 50 MB, activations)",
-                   "cuda_graph": main["graph"], "kl_scale": KL_SCALE},
+                   "cuda_graph": main["graph"], "kl_scale": KL_SCALE,
+                   "grad_allreduce": None if world == 1 else ("fp32" if args.fp32_allreduce else "bf16 buckets") +
+                   ", per-parameter, overlapped with backward"},
         "e2e": {"value": global_batch / (main["e2e_ms"] * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": (x_host.numel() * 2 + y_host.numel() * 8) * world,
                 "d2h_bytes_per_step": 8 * world, "ms_per_step": main["e2e_ms"]},
@@ -423,6 +423,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--fp32-allreduce", action="store_true", help="all-reduce fp32 gradients instead of bf16 buckets")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-variants", action="store_true")
     args = ap.parse_args()

@@ -35,7 +35,9 @@ constexpr int kThreads = 256;
 constexpr int kEpiThreads = 128;
 constexpr int kStoreBufBytes = kBlockM * 128;  // one staging buffer: 128 rows x 128 B (SWIZZLE_128B)
 constexpr int kNumStoreBufs = 2;
-constexpr int kSmemBudget = 227 * 1024;
+// Leave ~32 KB of the SM's 227 KB to other kernels: the issue-bound sampling / gradient-finishing kernels are launched
+// on side streams and must be able to co-reside with a GEMM CTA (tensor cores + TMA leave the CUDA cores idle).
+constexpr int kSmemBudget = 195 * 1024;
 
 template <int BLOCK_N, int kCtaGroup>
 struct Config {

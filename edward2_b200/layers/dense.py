@@ -229,6 +229,9 @@ class DenseFlipout(DenseReparameterization):
     """Bayesian dense layer estimated via Flipout (dense.py:227-285):
     y = act(x·mean + ((x∘S)·Delta)∘T + b), Delta = sigma∘eps, per-example sign tensors S [.., I] and T [.., O]."""
 
+    def presample(self):
+        """No-op: the Flipout forward samples inside its own call."""
+
     def call(self, inputs, training=None):
         mean, rho = self._kernel_params()
         if rho is None:  # dense.py:256-257: not a random variable -> parent behaviour

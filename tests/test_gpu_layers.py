@@ -253,3 +253,65 @@ def test_spectral_normalization_layer(cuda):
     np.testing.assert_allclose(to_np(small.kernel), k0)
     with pytest.raises(ValueError):
         ed.layers.SpectralNormalization(torch.nn.Linear(3, 3))
+
+
+@pytest.mark.parametrize("dtype,tol", [("float32", 1e-5), ("bfloat16", 2e-2)])
+def test_two_layer_mlp_cross_layer_fusion(cuda, dtype, tol):
+    """Two stacked DenseReparameterization layers: the second layer's dX epilogue applies the first layer's ReLU mask
+    and accumulates its bias gradient (functional.ReluLink).  Gradients must equal the oracle's layer-by-layer chain,
+    with and without the presample() scheduling hint."""
+    ed = _ed()
+    from edward2_b200 import functional as F
+
+    rng = np.random.default_rng(11)
+    B, I, H, O = 136, 72, 264, 40
+    tdt = torch.float32 if dtype == "float32" else torch.bfloat16
+    x = torch.tensor(rng.standard_normal((B, I)), dtype=torch.float32, device=cuda).to(tdt)
+    eps1 = torch.tensor(rng.standard_normal((I, H)), dtype=torch.float32, device=cuda)
+    eps2 = torch.tensor(rng.standard_normal((H, O)), dtype=torch.float32, device=cuda)
+    gy = torch.tensor(rng.standard_normal((B, O)), dtype=torch.float32, device=cuda).to(tdt)
+    results = []
+    for hint in (False, True):
+        l1 = ed.layers.DenseReparameterization(H, activation="relu", dtype=dtype, seed=5,
+                                               kernel_initializer=ed.initializers.TrainableNormal(
+                                                   mean_initializer=ed.initializers.RandomNormal(stddev=0.1, seed=1), seed=1))
+        l2 = ed.layers.DenseReparameterization(O, activation=None, dtype=dtype, seed=6,
+                                               kernel_initializer=ed.initializers.TrainableNormal(
+                                                   mean_initializer=ed.initializers.RandomNormal(stddev=0.1, seed=2), seed=2))
+        l1.inject(eps=eps1)
+        l2.inject(eps=eps2)
+        with torch.no_grad():
+            l2(l1(x))  # build
+            l1.bias.copy_(torch.tensor(rng.standard_normal(H) * 0.1, device=cuda))
+        rng = np.random.default_rng(12)  # same bias in both passes
+        if hint:
+            l2.presample()
+        h = l1(x)
+        link = F.take_link(h)
+        assert link is not None
+        out = l2(h)
+        out.backward(gy)
+        torch.cuda.synchronize()
+        assert link.dx_ptr is not None, "the fused dX epilogue path was not taken"
+        results.append((l1, l2, out))
+    (l1, l2, out) = results[0]
+    m1, r1 = l1.kernel_initializer.params()
+    m2, r2 = l2.kernel_initializer.params()
+    xin = to_np(x)
+    h_ref, _ = od.reparam_fwd(xin, to_np(m1), to_np(r1), to_np(eps1), to_np(l1.bias), "relu")
+    if dtype == "bfloat16":  # the kernel feeds layer 2 with its own bf16-rounded activations
+        h_ref_in = to_np(l1(x).detach())
+    else:
+        h_ref_in = h_ref
+    y_ref, _ = od.reparam_fwd(h_ref_in, to_np(m2), to_np(r2), to_np(eps2), to_np(l2.bias), None)
+    assert rel_err(to_np(out), y_ref) < tol
+    g2 = od.reparam_bwd(h_ref_in, to_np(m2), to_np(r2), to_np(eps2), to_np(l2.bias), None, to_np(gy))
+    g1 = od.reparam_bwd(xin, to_np(m1), to_np(r1), to_np(eps1), to_np(l1.bias), "relu", g2["dx"], y_mask=h_ref_in)
+    assert rel_err(to_np(m2.grad), g2["dmu"]) < tol
+    assert rel_err(to_np(m1.grad), g1["dmu"]) < tol
+    assert rel_err(to_np(r1.grad), g1["drho"]) < tol
+    assert rel_err(to_np(l1.bias.grad), g1["dbias"]) < tol
+    # the presample() hint changes scheduling only
+    (p1, p2, pout) = results[1]
+    assert rel_err(to_np(pout), to_np(out)) < 1e-6
+    assert rel_err(to_np(p1.kernel_initializer.mean.grad), to_np(m1.grad)) < 1e-5
