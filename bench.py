@@ -143,10 +143,9 @@ def make_step(layers, global_batch):
         h = x
         for l in layers:
             h = l(h)
-        loss = F.SoftmaxCrossEntropy.apply(h, labels, global_batch)
-        for l in layers:
-            loss = loss + l.losses[0]
-        loss.backward()
+        # cross-entropy + the layers' KL regularisers, summed by one kernel
+        loss = F.SoftmaxCrossEntropy.apply(h, labels, global_batch, *[l.losses[0] for l in layers])
+        F.backward(loss)
         return loss.detach()
 
     return step

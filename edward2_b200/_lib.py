@@ -152,7 +152,7 @@ SIGNATURES = {
     "ed2_sample_normal_weights": (_i, [_vp, _vp, Noise, _ll, _ll, _i, _vp, _i, _i, _vp, _i, _vp, _f, _f, _f, _vp]),
     "ed2_normal_kl_fwd": (_i, [_vp, _vp, _ll, _f, _f, _f, _vp, _vp]),
     "ed2_normal_kl_bwd": (_i, [_vp, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp]),
-    "ed2_softmax_xent": (_i, [_vp, _i, _i, _vp, _ll, _i, _f, _f, _vp, _vp, _i, _i, _vp]),
+    "ed2_softmax_xent": (_i, [_vp, _i, _i, _vp, _ll, _i, _f, _f, _vp, _vp, _i, _i, _vp, _i, _vp]),
     "ed2_act_bwd": (_i, [_i, _vp, _i, _vp, _i, _ll, _i, _i, _vp, _i, _vp, _vp]),
     "ed2_be_dense_fwd": (_i, [C.POINTER(BeFwd), _vp]),
     "ed2_be_dense_bwd": (_i, [C.POINTER(BeBwd), _vp]),

@@ -172,9 +172,14 @@ int ed2_normal_kl_bwd(const float* mu, const float* rho, long long n, float pm, 
 }
 
 int ed2_softmax_xent(const void* logits, int dtype, int ld, const long long* labels, long long rows, int cols,
-                     float loss_scale, float grad_scale, double* loss, void* dlogits, int d_dtype, int d_ld, void* s) {
+                     float loss_scale, float grad_scale, double* loss, void* dlogits, int d_dtype, int d_ld,
+                     const double* const* extra_terms, int n_extra, void* s) {
   ED2_TRY(check_dt(dtype));
-  return k_softmax_xent(logits, dtype, ld, labels, rows, cols, loss_scale, grad_scale, loss, dlogits, d_dtype, d_ld, S(s));
+  if (n_extra < 0 || n_extra > 8) return set_error(ED2_ERR_BAD_ARG, "softmax_xent: at most 8 extra loss terms");
+  XentExtras ex{};
+  ex.n = n_extra;
+  for (int i = 0; i < n_extra; ++i) ex.terms[i] = extra_terms[i];
+  return k_softmax_xent(logits, dtype, ld, labels, rows, cols, loss_scale, grad_scale, loss, dlogits, d_dtype, d_ld, ex, S(s));
 }
 
 int ed2_act_bwd(int dtype, const void* gy, int gy_ld, const void* y, int y_ld, long long rows, int cols, int act,

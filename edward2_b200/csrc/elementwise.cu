@@ -241,9 +241,9 @@ __global__ void normal_kl_bwd_kernel(const float* __restrict__ mu, const float* 
 __global__ void __launch_bounds__(kBlock) normal_grad_finish_kernel(const float* d_mean, const float* d_pert,
                                                                     const float* __restrict__ mu,
                                                                     const float* __restrict__ rho, Noise eps,
-                                                                    long long n, float klg_in, const float* kl_upstream,
+                                                                    long long n, float klg_in, const double* kl_upstream,
                                                                     Prior p, float* dmu, float* drho) {
-  const float klg = klg_in * (kl_upstream != nullptr ? *kl_upstream : 1.f);
+  const float klg = klg_in * (kl_upstream != nullptr ? static_cast<float>(*kl_upstream) : 1.f);
   const float inv_s2 = 1.f / (p.stddev * p.stddev);
   const long long nblk = (n + 3) >> 2;
   for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
@@ -536,7 +536,7 @@ __global__ void scale_inplace_kernel(float* x, long long n, float a) {
 __global__ void __launch_bounds__(kBlock) softmax_xent_kernel(const void* logits, int dt, long long ld,
                                                               const long long* labels, long long rows, int cols,
                                                               float loss_scale, float grad_scale, double* loss,
-                                                              void* dlogits, int ddt, long long dld) {
+                                                              void* dlogits, int ddt, long long dld, XentExtras ex) {
   const long long warp = (blockIdx.x * (long long)kBlock + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long nwarps = ((long long)gridDim.x * kBlock) >> 5;
@@ -562,6 +562,11 @@ __global__ void __launch_bounds__(kBlock) softmax_xent_kernel(const void* logits
     }
   }
   block_atomic_add(loss, local, loss_scale);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // regulariser terms (e.g. the layers' KL scalars) join the same scalar
+    double extra = 0.0;
+    for (int i = 0; i < ex.n; ++i) extra += *ex.terms[i];
+    if (ex.n > 0) atomicAdd(loss, extra);
+  }
 }
 
 }  // namespace
@@ -625,7 +630,7 @@ int k_normal_kl_bwd(const float* mu, const float* rho, long long n, Prior p, flo
 }
 
 int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* mu, const float* rho, Noise eps,
-                         long long n, float klg, const float* kl_upstream, Prior p, float* dmu, float* drho,
+                         long long n, float klg, const double* kl_upstream, Prior p, float* dmu, float* drho,
                          cudaStream_t s) {
   if (n <= 0) return ED2_OK;
   normal_grad_finish_kernel<<<grid_for((n + 3) / 4), kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
@@ -693,10 +698,10 @@ int k_fill_noise(int kind, Noise nz, void* out, int dt, long long ld, long long 
 
 int k_softmax_xent(const void* logits, int dt, long long ld, const long long* labels, long long rows, int cols,
                    float loss_scale, float grad_scale, double* loss, void* dlogits, int ddt, long long dld,
-                   cudaStream_t s) {
+                   const XentExtras& ex, cudaStream_t s) {
   if (rows <= 0 || cols <= 0) return ED2_OK;
   const int g = static_cast<int>(std::min<long long>(kMaxGrid, (rows + 7) / 8));
-  softmax_xent_kernel<<<g, kBlock, 0, s>>>(logits, dt, ld, labels, rows, cols, loss_scale, grad_scale, loss, dlogits, ddt, dld);
+  softmax_xent_kernel<<<g, kBlock, 0, s>>>(logits, dt, ld, labels, rows, cols, loss_scale, grad_scale, loss, dlogits, ddt, dld, ex);
   count_launch();
   return check_launch("softmax_xent");
 }

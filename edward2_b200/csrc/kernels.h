@@ -24,7 +24,7 @@ int k_normal_kl_bwd(const float* mu, const float* rho, long long n, Prior p, flo
                     float* dmu, float* drho, cudaStream_t s);
 // dmu = d_mean + kl*(mu-m)/s^2 ; drho = (d_pert*eps + kl*(sigma/s^2 - 1/sigma)) * sigmoid(rho)
 int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* mu, const float* rho, Noise eps,
-                         long long n, float kl_grad_scale, const float* kl_upstream, Prior p, float* dmu, float* drho,
+                         long long n, float kl_grad_scale, const double* kl_upstream, Prior p, float* dmu, float* drho,
                          cudaStream_t s);
 
 // ---- forward input preparation:  xo = x ∘ f  (f = alpha[e] | clip(mu+sigma*eps) | sign), dt in/out
@@ -100,9 +100,13 @@ int k_mean_field(const float* logits, const float* var, long long batch, int cla
                  float var_scale, float* out, cudaStream_t s);
 int k_rff_bwd_prep(const void* dphi, int ddt, long long dphi_ld, const float* pre, long long pre_ld, const float* bias, float scale,
                    long long rows, int cols, void* gpre, int gdt, long long gpre_ld, cudaStream_t s);
+struct XentExtras {
+  int n;
+  const double* terms[8];
+};
 int k_softmax_xent(const void* logits, int dt, long long ld, const long long* labels, long long rows, int cols,
                    float loss_scale, float grad_scale, double* loss, void* dlogits, int ddt, long long dld,
-                   cudaStream_t s);
+                   const XentExtras& ex, cudaStream_t s);
 int k_scale_inplace(float* x, long long n, float a, cudaStream_t s);
 
 }  // namespace ed2

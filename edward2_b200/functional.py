@@ -273,7 +273,7 @@ class ReparamDense(torch.autograd.Function):
             dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
         fuse_prev = need_dx and in_link is not None and dx.dtype == x_dtype
         prev_dbias = torch.empty(I, dtype=torch.float32, device=dev) if fuse_prev else None
-        up = gkl.to(torch.float32).reshape(1) if gkl is not None else None
+        up = (gkl if gkl.dtype == torch.float64 else gkl.to(torch.float64)).reshape(1) if gkl is not None else None
         a = _lib.ReparamBwd()
         a.dtype, a.batch, a.in_dim, a.out_dim, a.act = _compute_dt(dtype), B, I, O, act
         a.gy, a.gy_ld, a.y, a.y_ld, a.x, a.x_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y), xc.data_ptr(), _lib.ld(xc)
@@ -339,7 +339,7 @@ class FlipoutDense(torch.autograd.Function):
         dmu = torch.empty(I, O, dtype=torch.float32, device=dev)
         drho = torch.empty(I, O, dtype=torch.float32, device=dev)
         dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
-        up = gkl.to(torch.float32).reshape(1).contiguous() if gkl is not None else None
+        up = (gkl if gkl.dtype == torch.float64 else gkl.to(torch.float64)).reshape(1) if gkl is not None else None
         a = _lib.FlipoutBwd()
         a.dtype, a.batch, a.in_dim, a.out_dim, a.act = _compute_dt(dtype), B, I, O, act
         a.gy, a.gy_ld, a.y, a.y_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y)
@@ -470,12 +470,32 @@ class RandomFourierFeatures(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
+class _UnitGrad:
+    """Cached constant 1.0 used as the root gradient by `backward(loss)`: our loss node recognises it by identity and
+    skips the (B x classes) multiply by the upstream scalar."""
+
+    cache = {}
+
+    @classmethod
+    def get(cls, device, dtype):
+        key = (str(device), dtype)
+        if key not in cls.cache:
+            cls.cache[key] = torch.ones((), dtype=dtype, device=device)
+        return cls.cache[key]
+
+
+def backward(loss: torch.Tensor) -> None:
+    """loss.backward() with a cached unit root gradient (saves a fill and a full-size multiply per step)."""
+    torch.autograd.backward(loss, grad_tensors=_UnitGrad.get(loss.device, loss.dtype))
+
+
 class SoftmaxCrossEntropy(torch.autograd.Function):
-    """Mean softmax cross-entropy with integer labels; the gradient is produced in the forward pass.
-    `denominator` is the (global) batch size the mean is taken over."""
+    """loss = mean softmax cross-entropy (integer labels) + sum(extra scalar terms), as ONE kernel; the logits
+    gradient is produced in the forward pass.  `denominator` is the (global) batch size the mean is taken over;
+    `extras` are 0-dim fp64 tensors (e.g. the layers' KL losses) whose gradient is the upstream scalar itself."""
 
     @staticmethod
-    def forward(ctx, logits, labels, denominator):
+    def forward(ctx, logits, labels, denominator, *extras):
         lib = _lib.load()
         B, K = logits.shape
         lg = logits if (logits.stride(1) == 1 and logits.dtype in (torch.float32, torch.bfloat16)) else logits.contiguous().float()
@@ -483,15 +503,19 @@ class SoftmaxCrossEntropy(torch.autograd.Function):
         need = ctx.needs_input_grad[0]
         d = _new(B, K, lg.dtype, lg.device) if need else None
         inv = 1.0 / float(denominator)
+        ex = [e if e.dtype == torch.float64 else e.to(torch.float64) for e in extras]
+        arr = (C.c_void_p * max(1, len(ex)))(*[e.data_ptr() for e in ex])
         _lib.check(lib.ed2_softmax_xent(lg.data_ptr(), _lib.dt_of(lg), _lib.ld(lg), labels.data_ptr(), B, K, inv, inv,
-                                        loss.data_ptr(), _p(d), _lib.dt_of(lg), _ldn(d), _lib.stream_ptr()),
-                   "ed2_softmax_xent")
+                                        loss.data_ptr(), _p(d), _lib.dt_of(lg), _ldn(d), arr, len(ex),
+                                        _lib.stream_ptr()), "ed2_softmax_xent")
         if need:
             ctx.save_for_backward(d)
-        return loss.to(torch.float32)
+        ctx.n_extra = len(extras)
+        return loss
 
     @staticmethod
     def backward(ctx, g):
-        (d,) = ctx.saved_tensors
-        # upstream of a scalar loss is 1 in every use here; a different factor scales the stored gradient
-        return d * g.to(d.dtype), None, None
+        (d,) = ctx.saved_tensors if ctx.needs_input_grad[0] else (None,)
+        if d is not None and g is not _UnitGrad.cache.get((str(g.device), g.dtype)):
+            d = d * g.to(d.dtype)
+        return (d, None, None) + tuple(g for _ in range(ctx.n_extra))

@@ -127,9 +127,11 @@ int ed2_normal_kl_bwd(const float* mu, const float* rho, long long n, float prio
 /* Softmax cross-entropy with integer labels (int64), loss and gradient in one pass — the synthetic training loss of
  * the benchmark harness (the reference's scripts use tf.keras.losses.sparse_categorical_crossentropy,
  * experimental/marginalization_mixup/sngp.py:400-409).  *loss (fp64, caller-zeroed) += loss_scale * sum_rows CE;
- * dlogits = grad_scale * (softmax - onehot) (optional). */
+ * dlogits = grad_scale * (softmax - onehot) (optional).  extra_terms: HOST array of n_extra (<= 8) device pointers to
+ * fp64 scalars (the layers' KL regularisers) that are added into *loss by the same kernel. */
 int ed2_softmax_xent(const void* logits, int dtype, int ld, const long long* labels, long long rows, int cols,
-                     float loss_scale, float grad_scale, double* loss, void* dlogits, int d_dtype, int d_ld, void* s);
+                     float loss_scale, float grad_scale, double* loss, void* dlogits, int d_dtype, int d_ld,
+                     const double* const* extra_terms, int n_extra, void* s);
 
 /* gp = gy ∘ act'(y) (relu' evaluated on the output);  dbias[n] = sum_m gp[m,n] (optional, overwritten).
  * The output-side backward step of a plain dense layer (the layer SpectralNormalization wraps). */
@@ -248,7 +250,7 @@ typedef struct {
   float* dmu; float* drho;    /* [I][O] fp32, overwritten: likelihood term + kl_grad_scale * dKL */
   float* dbias;               /* [O] or NULL */
   float kl_grad_scale; float prior_mean; float prior_std;   /* kl_grad_scale = 0 -> no KL term */
-  const float* kl_upstream;   /* optional device scalar multiplying kl_grad_scale (dLoss/dKL) */
+  const double* kl_upstream;   /* optional fp64 device scalar multiplying kl_grad_scale (dLoss/dKL) */
   /* Cross-layer fusion (optional).  gy_premasked != 0: gy already equals gy ∘ act'(y) and dbias was accumulated by the
    * layer that produced gy (its dX epilogue) -> the output-side pass is skipped and gp is not written.
    * x_is_relu != 0: x is the output of a ReLU layer -> dx := dx ∘ (x > 0) in the dX epilogue and prev_dbias[in_dim]
@@ -297,7 +299,7 @@ typedef struct {
   void* dx; int dx_ld;
   float* dmu; float* drho; float* dbias;
   float kl_grad_scale; float prior_mean; float prior_std;
-  const float* kl_upstream;
+  const double* kl_upstream;
 } ed2_flipout_bwd_args;
 int ed2_flipout_dense_bwd(const ed2_flipout_bwd_args* a, void* stream);
 
