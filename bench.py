@@ -210,7 +210,8 @@ def run_ours(args):
         x_static, y_static = x_dev.clone(), y_dev.clone()
         # every pre-capture step runs on the capture-side stream so that autograd's AccumulateGrad nodes are bound
         # to it (a node created on the legacy stream would invalidate the capture)
-        side = torch.cuda.Stream() if use_graph else torch.cuda.current_stream()
+        # high priority: when an SM has room, a GEMM CTA of the main stream is placed before side-stream blocks
+        side = torch.cuda.Stream(priority=-1) if use_graph else torch.cuda.current_stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             eager_step(x_static, y_static)  # builds workspaces, sets kernel attributes

@@ -72,7 +72,9 @@ class ForkJoin {
     if (!on_) return;
     Ctx& c = ctx();
     if (c.side == nullptr) {
-      if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);  // side work is low priority: GEMM CTAs are placed first
+      if (cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, lo) != cudaSuccess ||
           cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&c.joined, cudaEventDisableTiming) != cudaSuccess) {
         c.side = nullptr;

@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "gemm_epilogue.h"
 #include "status.h"
@@ -16,6 +17,19 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kMaxGrid = 148 * 8;
+
+// Grid cap of the issue-bound sampling / finishing kernels.  They are meant to run on side streams BESIDE a GEMM
+// (tensor cores), so they must not fill an SM's register file: 2 resident blocks per SM leave room for a GEMM CTA.
+int side_grid_cap() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ED2_SIDE_BLOCKS_PER_SM");
+    int b = e ? std::atoi(e) : 2;
+    if (b < 1 || b > 8) b = 2;
+    v = 148 * b;
+  }
+  return v;
+}
 constexpr float kSoftplusEps = 1e-7f;  // keras.backend.epsilon(), edward2/tensorflow/constraints.py:56-63
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
@@ -602,7 +616,7 @@ int k_sample_weights(const float* mu, const float* rho, Noise eps, long long row
                      Prior p, cudaStream_t s) {
   if (rows <= 0 || cols <= 0) return ED2_OK;
   const int gx = static_cast<int>((cols + 4 * kBlock - 1) / (4 * kBlock));
-  const int gy = static_cast<int>(std::min<long long>(rows, std::max(1, kMaxGrid / gx)));
+  const int gy = static_cast<int>(std::min<long long>(rows, std::max(1, side_grid_cap() / gx)));
   dim3 grid(gx, gy);
   if (kl_out != nullptr)
     sample_weights_kernel<true><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld, mean_out,
@@ -633,7 +647,7 @@ int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* 
                          long long n, float klg, const double* kl_upstream, Prior p, float* dmu, float* drho,
                          cudaStream_t s) {
   if (n <= 0) return ED2_OK;
-  normal_grad_finish_kernel<<<grid_for((n + 3) / 4), kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
+  normal_grad_finish_kernel<<<std::min(grid_for((n + 3) / 4), side_grid_cap()), kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
   count_launch();
   return check_launch("normal_grad_finish");
 }

@@ -270,6 +270,7 @@ def test_two_layer_mlp_cross_layer_fusion(cuda, dtype, tol):
     eps1 = torch.tensor(rng.standard_normal((I, H)), dtype=torch.float32, device=cuda)
     eps2 = torch.tensor(rng.standard_normal((H, O)), dtype=torch.float32, device=cuda)
     gy = torch.tensor(rng.standard_normal((B, O)), dtype=torch.float32, device=cuda).to(tdt)
+    bias1 = torch.tensor(rng.standard_normal(H) * 0.1, dtype=torch.float32, device=cuda)
     results = []
     for hint in (False, True):
         l1 = ed.layers.DenseReparameterization(H, activation="relu", dtype=dtype, seed=5,
@@ -282,8 +283,7 @@ def test_two_layer_mlp_cross_layer_fusion(cuda, dtype, tol):
         l2.inject(eps=eps2)
         with torch.no_grad():
             l2(l1(x))  # build
-            l1.bias.copy_(torch.tensor(rng.standard_normal(H) * 0.1, device=cuda))
-        rng = np.random.default_rng(12)  # same bias in both passes
+            l1.bias.copy_(bias1)
         if hint:
             l2.presample()
         h = l1(x)
