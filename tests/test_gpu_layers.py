@@ -275,10 +275,12 @@ def test_two_layer_mlp_cross_layer_fusion(cuda, dtype, tol):
     for hint in (False, True):
         l1 = ed.layers.DenseReparameterization(H, activation="relu", dtype=dtype, seed=5,
                                                kernel_initializer=ed.initializers.TrainableNormal(
-                                                   mean_initializer=ed.initializers.RandomNormal(stddev=0.1, seed=1), seed=1))
+                                                   mean_initializer=ed.initializers.RandomNormal(stddev=0.1, seed=1),
+                                                   stddev_initializer=ed.initializers.TruncatedNormal(-3.0, 0.1, seed=3)))
         l2 = ed.layers.DenseReparameterization(O, activation=None, dtype=dtype, seed=6,
                                                kernel_initializer=ed.initializers.TrainableNormal(
-                                                   mean_initializer=ed.initializers.RandomNormal(stddev=0.1, seed=2), seed=2))
+                                                   mean_initializer=ed.initializers.RandomNormal(stddev=0.1, seed=2),
+                                                   stddev_initializer=ed.initializers.TruncatedNormal(-3.0, 0.1, seed=4)))
         l1.inject(eps=eps1)
         l2.inject(eps=eps2)
         with torch.no_grad():
