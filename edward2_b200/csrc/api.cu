@@ -292,13 +292,23 @@ int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream) {
 int ed2_reparam_dense_fwd(const ed2_reparam_fwd_args* a, void* stream) {
   ED2_TRY(check_dt(a->dtype));
   cudaStream_t s = S(stream);
+  const Prior prior{a->prior_mean, a->prior_std};
+  // bf16: the sampling pass is on the critical path (the GEMM needs W), the KL is not (only the loss needs it):
+  // sample with hardware-approximate math and no KL, enqueue the GEMM, then run the accurate KL reduction on the
+  // side stream beside the GEMM.  fp32 keeps the single precise pass with the KL fused in.
+  const bool split_kl = a->dtype == kBF16 && a->kl_out != nullptr;
   ED2_TRY(k_sample_weights(a->mu, a->rho, N(a->eps), a->in_dim, a->out_dim, 0, a->w_lp, a->dtype, a->w_ld, nullptr, 0,
-                           a->kl_out, a->kl_scale, Prior{a->prior_mean, a->prior_std}, s));
+                           split_kl ? nullptr : a->kl_out, a->kl_scale, prior, s));
+  ForkJoin fj(s, split_kl);  // fork BEFORE the GEMM so the KL pass depends only on what precedes it
   EpiParams e = epi_default();
   e.col_bias = a->bias; e.col_bias_ld = a->out_dim;
   e.act = a->act;
   e.out = a->y; e.out_ld = a->y_ld; e.out_dt = a->dtype;
-  return gemm_xw(a->dtype, a->x, a->x_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e, s);
+  int st = gemm_xw(a->dtype, a->x, a->x_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e, s);
+  if (split_kl && st == ED2_OK)
+    st = k_normal_kl_fwd(a->mu, a->rho, (long long)a->in_dim * a->out_dim, prior, a->kl_scale, a->kl_out, fj.side());
+  fj.join();
+  return st;
 }
 
 int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
@@ -321,11 +331,9 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
   EpiParams e = epi_default();
   e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
   ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, gp, gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
-  // fork: the finishing pass (CUDA cores, issue-bound) runs beside the dX GEMM (tensor cores) on a side stream
+  // fork after dW: the finishing pass (CUDA cores) runs beside the dX GEMM (tensor cores).  The GEMM is enqueued
+  // FIRST so that its CTAs are resident before the side kernel's blocks fill the remaining registers of each SM.
   ForkJoin fj(s, a->dx != nullptr);
-  ED2_TRY(k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
-                               a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
-                               fj.side()));
   int st = ED2_OK;
   if (a->dx != nullptr) {
     EpiParams e2 = epi_default();
@@ -337,6 +345,10 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
     }
     st = gemm_gwt(a->dtype, gp, gp_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s);
   }
+  if (st == ED2_OK)
+    st = k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
+                              a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
+                              a->dtype == kBF16, fj.side());
   fj.join();
   return st;
 }
@@ -386,7 +398,8 @@ int ed2_flipout_dense_bwd(const ed2_flipout_bwd_args* a, void* stream) {
   e1.out = a->drho; e1.out_ld = a->out_dim; e1.out_dt = kF32;
   ED2_TRY(gemm_xtg(a->dtype, a->xs, a->xs_ld, a->gt, a->gt_ld, a->batch, a->in_dim, a->out_dim, e1, s));
   ED2_TRY(k_normal_grad_finish(a->dmu, a->drho, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
-                               a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho, s));
+                               a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
+                               a->dtype == kBF16, s));
   if (a->dx != nullptr) {
     // tmp = ((gp∘T) Δᵀ) ∘ S ;  dx = gp μᵀ + tmp
     EpiParams e2 = epi_default();

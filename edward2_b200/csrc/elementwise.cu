@@ -170,6 +170,12 @@ __device__ __forceinline__ float sigma_from_rho(float rho, float& e) {
   e = __expf(fminf(rho, 80.f));
   return (rho > 20.f ? rho : log1pf(e)) + kSoftplusEps;
 }
+// bf16-output variant: sigma only needs ~3 significant digits, so softplus is lg2(1 + ex2(rho)) on the SFU.
+__device__ __forceinline__ float sigma_from_rho_fast(float rho, float& e) {
+  e = __expf(fminf(rho, 80.f));
+  const float sp = e < 2.44140625e-4f ? e : __logf(1.f + e);
+  return (rho > 20.f ? rho : sp) + kSoftplusEps;
+}
 __device__ __forceinline__ float kl_fast(float mu, float sigma, float pm, float log_ps, float inv_2s2) {
   const float d = mu - pm;
   return log_ps - __logf(sigma) + (sigma * sigma + d * d) * inv_2s2 - 0.5f;
@@ -177,7 +183,7 @@ __device__ __forceinline__ float kl_fast(float mu, float sigma, float pm, float 
 
 // Thread = 4 consecutive columns of one row (= one Philox block when cols % 4 == 0); blockIdx.y strides over rows,
 // so no index division is needed for the pitched output.
-template <bool kWantKl>
+template <bool kWantKl, bool kFast>
 __global__ void __launch_bounds__(kBlock) sample_weights_kernel(const float* __restrict__ mu,
                                                                 const float* __restrict__ rho, Noise eps, int rows,
                                                                 int cols, int mode, void* w, int wdt, long long wld,
@@ -194,13 +200,13 @@ __global__ void __launch_bounds__(kBlock) sample_weights_kernel(const float* __r
       float m[4], rh[4], e[4], o[4];
       ld4(mu, kF32, i, valid, m);
       ld4(rho, kF32, i, valid, rh);
-      if ((i & 3) == 0) noise4<0>(eps, i, n, e);
+      if ((i & 3) == 0) noise4<0, kFast>(eps, i, n, e);
       else
         for (int j = 0; j < 4; ++j) e[j] = j < valid ? noise1<0>(eps, i + j) : 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float ex;
-        const float sigma = sigma_from_rho(rh[j], ex);
+        const float sigma = kFast ? sigma_from_rho_fast(rh[j], ex) : sigma_from_rho(rh[j], ex);
         o[j] = mode == 0 ? fmaf(sigma, e[j], m[j]) : sigma * e[j];
         if (kWantKl && j < valid) kl += kl_fast(m[j], sigma, p.mean, log_ps, inv_2s2);
       }
@@ -252,6 +258,7 @@ __global__ void normal_kl_bwd_kernel(const float* __restrict__ mu, const float* 
   }
 }
 
+template <bool kFast>
 __global__ void __launch_bounds__(kBlock) normal_grad_finish_kernel(const float* d_mean, const float* d_pert,
                                                                     const float* __restrict__ mu,
                                                                     const float* __restrict__ rho, Noise eps,
@@ -268,11 +275,11 @@ __global__ void __launch_bounds__(kBlock) normal_grad_finish_kernel(const float*
     ld4(rho, kF32, i, valid, r);
     ld4(d_mean, kF32, i, valid, gm);
     ld4(d_pert, kF32, i, valid, gp);
-    noise4<0>(eps, i, n, e);
+    noise4<0, kFast>(eps, i, n, e);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float ex;
-      const float sigma = sigma_from_rho(r[j], ex);
+      const float sigma = kFast ? sigma_from_rho_fast(r[j], ex) : sigma_from_rho(r[j], ex);
       const float sgm = __fdividef(ex, 1.f + ex);  // sigmoid(rho)
       om[j] = gm[j] + klg * (m[j] - p.mean) * inv_s2;
       orr[j] = (gp[j] * e[j] + klg * (sigma * inv_s2 - __fdividef(1.f, sigma))) * sgm;
@@ -618,12 +625,17 @@ int k_sample_weights(const float* mu, const float* rho, Noise eps, long long row
   const int gx = static_cast<int>((cols + 4 * kBlock - 1) / (4 * kBlock));
   const int gy = static_cast<int>(std::min<long long>(rows, std::max(1, side_grid_cap() / gx)));
   dim3 grid(gx, gy);
+  // bf16 output without the fused KL: hardware-approximate transcendentals (the result is rounded to 8 mantissa bits)
+  const bool fast = wdt == kBF16 && kl_out == nullptr;
   if (kl_out != nullptr)
-    sample_weights_kernel<true><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld, mean_out,
-                                                        mean_ld, kl_out, kl_scale, p);
+    sample_weights_kernel<true, false><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld,
+                                                               mean_out, mean_ld, kl_out, kl_scale, p);
+  else if (fast)
+    sample_weights_kernel<false, true><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld,
+                                                               mean_out, mean_ld, kl_out, kl_scale, p);
   else
-    sample_weights_kernel<false><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld, mean_out,
-                                                         mean_ld, kl_out, kl_scale, p);
+    sample_weights_kernel<false, false><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld,
+                                                                mean_out, mean_ld, kl_out, kl_scale, p);
   count_launch();
   return check_launch("sample_weights");
 }
@@ -644,10 +656,12 @@ int k_normal_kl_bwd(const float* mu, const float* rho, long long n, Prior p, flo
 }
 
 int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* mu, const float* rho, Noise eps,
-                         long long n, float klg, const double* kl_upstream, Prior p, float* dmu, float* drho,
+                         long long n, float klg, const double* kl_upstream, Prior p, float* dmu, float* drho, bool fast,
                          cudaStream_t s) {
   if (n <= 0) return ED2_OK;
-  normal_grad_finish_kernel<<<std::min(grid_for((n + 3) / 4), side_grid_cap()), kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
+  const int g = std::min(grid_for((n + 3) / 4), side_grid_cap());
+  if (fast) normal_grad_finish_kernel<true><<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
+  else normal_grad_finish_kernel<false><<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
   count_launch();
   return check_launch("normal_grad_finish");
 }

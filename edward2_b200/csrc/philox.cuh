@@ -68,11 +68,30 @@ __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& z0, 
   z1 = r * s;
 }
 
+// Same Box-Muller pair from hardware approximations (lg2 / sin / cos): abs error ~1e-6 (up to ~1e-4 for the 1e-6 of
+// draws with u0 within 1e-6 of 1) -- used when the sampled tensor is rounded to bf16 anyway.  The angle is shifted to
+// (-pi, pi), where __sincosf is accurate: cos(2 pi u) = -cos(2 pi u - pi).
+__device__ __forceinline__ void box_muller_fast(uint32_t x0, uint32_t x1, float& z0, float& z1) {
+  const float u0 = u32_to_uniform(x0), u1 = u32_to_uniform(x1);
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u0)));
+  float s, c;
+  __sincosf(6.283185307179586f * u1 - 3.141592653589793f, &s, &c);
+  z0 = -r * c;
+  z1 = -r * s;
+}
+
+template <bool kFast = false>
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t block, float (&z)[4]) {
   uint32_t x[4];
   philox_block(seed, stream, block, x);
-  box_muller(x[0], x[1], z[0], z[1]);
-  box_muller(x[2], x[3], z[2], z[3]);
+  if constexpr (kFast) {
+    box_muller_fast(x[0], x[1], z[0], z[1]);
+    box_muller_fast(x[2], x[3], z[2], z[3]);
+  } else {
+    box_muller(x[0], x[1], z[0], z[1]);
+    box_muller(x[2], x[3], z[2], z[3]);
+  }
 }
 
 __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t stream, uint64_t block, float (&u)[4]) {
@@ -104,13 +123,13 @@ __device__ __forceinline__ uint64_t noise_key(const Noise& nz) {
 }
 
 // 4 consecutive noise values starting at flat element index idx (idx % 4 == 0).
-template <int kKind>
+template <int kKind, bool kFast = false>
 __device__ __forceinline__ void noise4(const Noise& nz, long long idx, long long n, float (&e)[4]) {
   if (nz.injected != nullptr) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) e[i] = (idx + i < n) ? __ldg(nz.injected + idx + i) : 0.f;
   } else if constexpr (kKind == 0) {
-    philox_normal4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
+    philox_normal4<kFast>(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
   } else {
     philox_sign4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
   }

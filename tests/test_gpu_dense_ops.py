@@ -219,3 +219,33 @@ def test_philox_stream_invariance(cuda):
     torch.cuda.synchronize()
     assert rel_err(to_np(y1), to_np(y2)) < 1e-5
     assert rel_err(to_np(g1), to_np(rho.grad)) < 1e-5
+
+
+def test_reparam_bf16_native_sampler(cuda):
+    """bf16 path with the in-kernel Philox sampler (hardware-approximate Box-Muller / softplus, KL on the side stream)
+    vs the oracle fed with the host restatement of the same stream."""
+    from edward2_b200 import functional as F
+    from oracle import philox as op
+
+    B, I, O = 136, 264, 520
+    rng = np.random.default_rng(5)
+    f32 = lambda a: np.float32(a).astype(np.float64)  # noqa: E731
+    x = round_to(rng.standard_normal((B, I)), torch.bfloat16)
+    mu = f32(rng.standard_normal((I, O)) / np.sqrt(I))
+    rho = f32(rng.standard_normal((I, O)) * 0.5 - 3.0)
+    gy = round_to(rng.standard_normal((B, O)), torch.bfloat16)
+    eps = op.normal(77, 0, I * O).reshape(I, O)
+    xt = dev(x, torch.bfloat16, cuda, True)
+    mt, rt = dev(mu, torch.float32, cuda, True), dev(rho, torch.float32, cuda, True)
+    y, kl = F.ReparamDense.apply(xt, mt, rt, None, ACTS["relu"], torch.bfloat16, F.Randomness(seed=77, stream=0), 0.5, 0.0, 1.0)
+    (y.float() * dev(gy, torch.float32, cuda)).sum().backward()
+    torch.cuda.synchronize()
+    w_rounded = round_to(mu + od.stddev(rho) * eps, torch.bfloat16)
+    y_ref = od.activation(x @ w_rounded, "relu")
+    _check("y", y, y_ref, 2e-2)
+    kl_ref = od.normal_kl(mu, rho, 0.0, 1.0, 0.5)
+    assert abs(kl.item() - kl_ref) <= 1e-5 * abs(kl_ref)
+    g = od.reparam_bwd(x, mu, rho, eps, None, "relu", gy, y_mask=to_np(y))
+    _check("dmu", mt.grad, g["dmu"], 2e-2)
+    _check("drho", rt.grad, g["drho"], 2e-2)
+    _check("dx", xt.grad, g["dx"], 2e-2)
