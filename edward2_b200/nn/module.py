@@ -67,6 +67,11 @@ class Module:
                 setattr(self, n, kwargs.pop(n))
             elif not hasattr(type(self), n):
                 raise TypeError(f"missing required field {n!r}")
+            else:
+                # copy the class-level default onto the instance: a function default must stay a plain function
+                # (looked up through the instance it would be bound as a method)
+                setattr(self, n, type(self).__dict__.get(n, getattr(type(self), n)) if not callable(getattr(type(self), n))
+                        else _unbound(type(self), n))
         if kwargs:
             raise TypeError(f"unexpected fields {sorted(kwargs)}")
         self._scope = None
@@ -144,6 +149,13 @@ class Module:
     def sow(self, col, name, value):
         if self._scope.initializing or self.is_mutable_collection(col):
             self._scope.collection(col, create=True)[name] = value
+
+
+def _unbound(klass, name):
+    for k in klass.__mro__:
+        if name in k.__dict__:
+            return k.__dict__[name]
+    return getattr(klass, name)
 
 
 class _Variable:
