@@ -357,8 +357,11 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
 int ed2_flipout_dense_fwd(const ed2_flipout_fwd_args* a, void* stream) {
   ED2_TRY(check_dt(a->dtype));
   cudaStream_t s = S(stream);
+  const bool split_kl = a->dtype == kBF16 && a->kl_out != nullptr;
   ED2_TRY(k_sample_weights(a->mu, a->rho, N(a->eps), a->in_dim, a->out_dim, 1, a->delta_lp, a->dtype, a->delta_ld,
-                           a->mu_lp, a->mu_ld, a->kl_out, a->kl_scale, Prior{a->prior_mean, a->prior_std}, s));
+                           a->mu_lp, a->mu_ld, split_kl ? nullptr : a->kl_out, a->kl_scale,
+                           Prior{a->prior_mean, a->prior_std}, s));
+  ForkJoin fj(s, split_kl);  // the accurate KL reduction runs beside the GEMMs on the side stream
   ED2_TRY(k_scale_rows(a->x, a->dtype, a->x_ld, a->batch, a->in_dim, a->batch, 2, nullptr, nullptr, N(a->sign_in),
                        a->xs, a->xs_ld, nullptr, 0, s));
   // pert = ((x∘S) Δ) ∘ T : T either injected fp32 (used directly) or materialised from Philox into `y` (dtype,
@@ -372,12 +375,17 @@ int ed2_flipout_dense_fwd(const ed2_flipout_fwd_args* a, void* stream) {
   }
   e.out = a->pert; e.out_ld = a->pert_ld; e.out_dt = kF32;
   ED2_TRY(gemm_xw(a->dtype, a->xs, a->xs_ld, a->delta_lp, a->delta_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  if (split_kl)
+    ED2_TRY(k_normal_kl_fwd(a->mu, a->rho, (long long)a->in_dim * a->out_dim, Prior{a->prior_mean, a->prior_std},
+                            a->kl_scale, a->kl_out, fj.side()));
   EpiParams e2 = epi_default();
   e2.addend = a->pert; e2.addend_ld = a->pert_ld; e2.addend_dt = kF32;
   e2.col_bias = a->bias; e2.col_bias_ld = a->out_dim;
   e2.act = a->act;
   e2.out = a->y; e2.out_ld = a->y_ld; e2.out_dt = a->dtype;
-  return gemm_xw(a->dtype, a->x, a->x_ld, a->mu_lp, a->mu_ld, a->batch, a->in_dim, a->out_dim, e2, s);
+  const int st = gemm_xw(a->dtype, a->x, a->x_ld, a->mu_lp, a->mu_ld, a->batch, a->in_dim, a->out_dim, e2, s);
+  fj.join();
+  return st;
 }
 
 int ed2_flipout_dense_bwd(const ed2_flipout_bwd_args* a, void* stream) {

@@ -217,6 +217,88 @@ __global__ void __launch_bounds__(kBlock) sample_weights_kernel(const float* __r
   if (kWantKl) block_atomic_add(kl_out, kl, kl_scale);
 }
 
+
+// ---- lean hot-path kernels (bf16 compute mode, Philox noise, 8-element-aligned rows): straight-line code, 8 weights
+// per thread (two Philox blocks), no alignment / tail / injected-noise branches.  ~40 instructions and 4 MUFU ops per
+// weight instead of ~125: the sampling pass sits on the forward critical path (the GEMM needs W).
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int kMode, bool kMean>
+__global__ void __launch_bounds__(kBlock) sample_bf16_lean_kernel(const float* __restrict__ mu,
+                                                                  const float* __restrict__ rho, uint64_t seed,
+                                                                  uint64_t stream, const uint64_t* step, int rows,
+                                                                  int cols, __nv_bfloat16* __restrict__ w, int wld,
+                                                                  __nv_bfloat16* __restrict__ mean_out, int mean_ld) {
+  const int c = (blockIdx.x * kBlock + threadIdx.x) * 8;
+  if (c >= cols) return;
+  const uint64_t key = step != nullptr ? seed + __ldg(reinterpret_cast<const unsigned long long*>(step)) * 0x9E3779B97F4A7C15ull : seed;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const long long i = (long long)r * cols + c;
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + i)), m1 = __ldg(reinterpret_cast<const float4*>(mu + i) + 1);
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rho + i)), r1 = __ldg(reinterpret_cast<const float4*>(rho + i) + 1);
+    float e[8];
+    {
+      float t[4];
+      philox_normal4<true>(key, stream, static_cast<uint64_t>(i >> 2), t);
+      e[0] = t[0]; e[1] = t[1]; e[2] = t[2]; e[3] = t[3];
+      philox_normal4<true>(key, stream, static_cast<uint64_t>(i >> 2) + 1, t);
+      e[4] = t[0]; e[5] = t[1]; e[6] = t[2]; e[7] = t[3];
+    }
+    const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const float rh[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float ex;
+      const float sigma = sigma_from_rho_fast(rh[j], ex);
+      o[j] = kMode == 0 ? fmaf(sigma, e[j], m[j]) : sigma * e[j];
+    }
+    uint4 q;
+    q.x = pack2_bf16(o[0], o[1]); q.y = pack2_bf16(o[2], o[3]); q.z = pack2_bf16(o[4], o[5]); q.w = pack2_bf16(o[6], o[7]);
+    *reinterpret_cast<uint4*>(w + (long long)r * wld + c) = q;
+    if (kMean) {
+      uint4 p;
+      p.x = pack2_bf16(m[0], m[1]); p.y = pack2_bf16(m[2], m[3]); p.z = pack2_bf16(m[4], m[5]); p.w = pack2_bf16(m[6], m[7]);
+      *reinterpret_cast<uint4*>(mean_out + (long long)r * mean_ld + c) = p;
+    }
+  }
+}
+
+// dmu = d_mean + klg (mu - m) / s^2 ;  drho = (d_pert * eps + klg (sigma / s^2 - 1 / sigma)) * sigmoid(rho)
+__global__ void __launch_bounds__(kBlock) grad_finish_lean_kernel(const float* d_mean, const float* d_pert,
+                                                                  const float* __restrict__ mu,
+                                                                  const float* __restrict__ rho, uint64_t seed,
+                                                                  uint64_t stream, const uint64_t* step, long long n,
+                                                                  float klg_in, const double* kl_upstream, Prior p,
+                                                                  float* dmu, float* drho) {
+  const float klg = klg_in * (kl_upstream != nullptr ? static_cast<float>(*kl_upstream) : 1.f);
+  const float inv_s2 = 1.f / (p.stddev * p.stddev);
+  const uint64_t key = step != nullptr ? seed + __ldg(reinterpret_cast<const unsigned long long*>(step)) * 0x9E3779B97F4A7C15ull : seed;
+  const long long nblk = n >> 2;  // n % 4 == 0 (checked by the launcher)
+  for (long long b = blockIdx.x * (long long)kBlock + threadIdx.x; b < nblk; b += (long long)gridDim.x * kBlock) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + b), r = __ldg(reinterpret_cast<const float4*>(rho) + b);
+    const float4 gm = reinterpret_cast<const float4*>(d_mean)[b], gp = reinterpret_cast<const float4*>(d_pert)[b];
+    float e[4];
+    philox_normal4<true>(key, stream, static_cast<uint64_t>(b), e);
+    const float mm[4] = {m.x, m.y, m.z, m.w}, rr[4] = {r.x, r.y, r.z, r.w};
+    const float g1[4] = {gm.x, gm.y, gm.z, gm.w}, g2[4] = {gp.x, gp.y, gp.z, gp.w};
+    float om[4], orr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ex;
+      const float sigma = sigma_from_rho_fast(rr[j], ex);
+      const float sgm = __fdividef(ex, 1.f + ex);
+      om[j] = g1[j] + klg * (mm[j] - p.mean) * inv_s2;
+      orr[j] = (g2[j] * e[j] + klg * (sigma * inv_s2 - __fdividef(1.f, sigma))) * sgm;
+    }
+    reinterpret_cast<float4*>(dmu)[b] = make_float4(om[0], om[1], om[2], om[3]);
+    reinterpret_cast<float4*>(drho)[b] = make_float4(orr[0], orr[1], orr[2], orr[3]);
+  }
+}
+
 __global__ void normal_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ rho, long long n, Prior p,
                                      float scale, double* out) {
   const long long nblk = (n + 3) >> 2;
@@ -627,6 +709,26 @@ int k_sample_weights(const float* mu, const float* rho, Noise eps, long long row
   dim3 grid(gx, gy);
   // bf16 output without the fused KL: hardware-approximate transcendentals (the result is rounded to 8 mantissa bits)
   const bool fast = wdt == kBF16 && kl_out == nullptr;
+  const bool lean = fast && eps.injected == nullptr && cols % 8 == 0 && wld % 8 == 0 && (mean_out == nullptr || mean_ld % 8 == 0) &&
+                    (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(mu) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(rho) & 15) == 0 && (reinterpret_cast<uintptr_t>(mean_out) & 15) == 0;
+  if (lean) {
+    const int lgx = static_cast<int>((cols + 8 * kBlock - 1) / (8 * kBlock));
+    const int lgy = static_cast<int>(std::min<long long>(rows, std::max(1, side_grid_cap() / lgx)));
+    dim3 lgrid(lgx, lgy);
+    auto* wp = reinterpret_cast<__nv_bfloat16*>(w);
+    auto* mp = reinterpret_cast<__nv_bfloat16*>(mean_out);
+    if (mode == 0 && mp == nullptr)
+      sample_bf16_lean_kernel<0, false><<<lgrid, kBlock, 0, s>>>(mu, rho, eps.seed, eps.stream, eps.step, (int)rows, (int)cols, wp, (int)wld, mp, (int)mean_ld);
+    else if (mode == 0)
+      sample_bf16_lean_kernel<0, true><<<lgrid, kBlock, 0, s>>>(mu, rho, eps.seed, eps.stream, eps.step, (int)rows, (int)cols, wp, (int)wld, mp, (int)mean_ld);
+    else if (mp == nullptr)
+      sample_bf16_lean_kernel<1, false><<<lgrid, kBlock, 0, s>>>(mu, rho, eps.seed, eps.stream, eps.step, (int)rows, (int)cols, wp, (int)wld, mp, (int)mean_ld);
+    else
+      sample_bf16_lean_kernel<1, true><<<lgrid, kBlock, 0, s>>>(mu, rho, eps.seed, eps.stream, eps.step, (int)rows, (int)cols, wp, (int)wld, mp, (int)mean_ld);
+    count_launch();
+    return check_launch("sample_weights(lean)");
+  }
   if (kl_out != nullptr)
     sample_weights_kernel<true, false><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld,
                                                                mean_out, mean_ld, kl_out, kl_scale, p);
@@ -660,6 +762,12 @@ int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* 
                          cudaStream_t s) {
   if (n <= 0) return ED2_OK;
   const int g = std::min(grid_for((n + 3) / 4), side_grid_cap());
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (fast && eps.injected == nullptr && n % 4 == 0 && al16(d_mean) && al16(d_pert) && al16(mu) && al16(rho) && al16(dmu) && al16(drho)) {
+    grad_finish_lean_kernel<<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps.seed, eps.stream, eps.step, n, klg, kl_upstream, p, dmu, drho);
+    count_launch();
+    return check_launch("normal_grad_finish(lean)");
+  }
   if (fast) normal_grad_finish_kernel<true><<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
   else normal_grad_finish_kernel<false><<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
   count_launch();

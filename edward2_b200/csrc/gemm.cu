@@ -69,6 +69,10 @@ int launch_one(const GemmDesc& g, const CUtensorMap& ta, const CUtensorMap& tb, 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
                                            cudaGetErrorString(e));
+    // Ask for the largest shared-memory carveout: the CTA itself needs ~194 KB, and the remaining ~32 KB are what lets
+    // blocks of the side-stream kernels (sampling, KL, gradient finishing) co-reside with it on the same SM.
+    static const bool max_carveout = [] { const char* e = std::getenv("ED2_GEMM_CARVEOUT"); return e == nullptr || std::atoi(e) != 0; }();
+    if (max_carveout) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   const int tile_m = tc::kBlockM * CG;
