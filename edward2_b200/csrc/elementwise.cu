@@ -378,7 +378,7 @@ constexpr float kClip = 10.f;  // edward2/tensorflow/layers/dense.py:1109-1111
 template <int kMode>
 __device__ __forceinline__ void fast_factor4(const float* fw_mu, const float* fw_rho, const Noise& nz, long long row,
                                              int e, int c, int cols, int valid, float (&f)[4], float (&raw)[4],
-                                             float (&en)[4]) {
+                                             float (&en)[4], bool fast = false) {
   if (kMode == 2) {
     const long long idx = row * cols + c;
     if ((idx & 3) == 0) noise4<1>(nz, idx, (long long)1 << 62, f);
@@ -396,7 +396,11 @@ __device__ __forceinline__ void fast_factor4(const float* fw_mu, const float* fw
   float r[4];
   ld4(fw_rho, kF32, (long long)e * cols + c, valid, r);
   const long long idx = row * cols + c;
-  if ((idx & 3) == 0) noise4<0>(nz, idx, (long long)1 << 62, en);
+  if ((idx & 3) == 0) {
+    // bf16 compute mode: hardware-approximate Box-Muller (the factor is rounded to bf16 before use)
+    if (fast) noise4<0, true>(nz, idx, (long long)1 << 62, en);
+    else noise4<0>(nz, idx, (long long)1 << 62, en);
+  }
   else
     for (int j = 0; j < 4; ++j) en[j] = j < valid ? noise1<0>(nz, idx + j) : 0.f;
 #pragma unroll
@@ -418,7 +422,7 @@ __global__ void scale_rows_kernel(const void* x, int dt, long long x_ld, long lo
     const int valid = min(4, cols - c);
     const int e = static_cast<int>(r / rpm);
     float f[4], raw[4], en[4];
-    fast_factor4<kMode>(fw_mu, fw_rho, nz, r, e, c, cols, valid, f, raw, en);
+    fast_factor4<kMode>(fw_mu, fw_rho, nz, r, e, c, cols, valid, f, raw, en, dt == kBF16);
     if (x != nullptr) {
       float xv[4];
       ld4(x, dt, r * x_ld + c, valid, xv);
@@ -538,7 +542,10 @@ __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
         if (a.rho_s != nullptr) {
           float en[4];
           const long long idx = r * a.cols + c;
-          if ((idx & 3) == 0) noise4<0>(a.eps_s, idx, (long long)1 << 62, en);
+          if ((idx & 3) == 0) {
+            if (a.dt == kBF16) noise4<0, true>(a.eps_s, idx, (long long)1 << 62, en);
+            else noise4<0>(a.eps_s, idx, (long long)1 << 62, en);
+          }
           else
             for (int j = 0; j < 4; ++j) en[j] = j < valid ? noise1<0>(a.eps_s, idx + j) : 0.f;
 #pragma unroll
@@ -595,7 +602,7 @@ __global__ void __launch_bounds__(kBlock) bwd_in_kernel(BwdInArgs a) {
       ld4(a.dxf, a.dt, r * a.dxf_ld + c, valid, d);
       ld4(a.x, a.dt, r * a.x_ld + c, valid, xv);
       if (a.fast == 1) fast_factor4<0>(a.fw_mu, nullptr, a.eps, r, e, c, a.cols, valid, f, raw, en);
-      else fast_factor4<1>(a.fw_mu, a.fw_rho, a.eps, r, e, c, a.cols, valid, f, raw, en);
+      else fast_factor4<1>(a.fw_mu, a.fw_rho, a.eps, r, e, c, a.cols, valid, f, raw, en, a.dt == kBF16);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float pass = (a.fast == 2 && a.fw_rho != nullptr && (raw[j] < -kClip || raw[j] > kClip)) ? 0.f : 1.f;

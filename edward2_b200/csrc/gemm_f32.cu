@@ -10,7 +10,7 @@
 namespace ed2 {
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TK = 16;
 
 __device__ __forceinline__ float ld_elem(const void* p, int dt, long long idx) {
   return dt == kBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx])
@@ -21,7 +21,9 @@ __device__ __forceinline__ void st_elem(void* p, int dt, long long idx, float v)
   else reinterpret_cast<float*>(p)[idx] = v;
 }
 
-template <int MA, int MB>
+// Tile TM x TN per 256-thread block, (TM/16) x (TN/16) outputs per thread.  64x64 for large problems; 32x32 for the
+// small, latency-bound shapes (BASELINE config 1) so that the grid still covers the SMs.
+template <int MA, int MB, int TM, int TN>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda,
                                                        const float* __restrict__ B, int ldb, int M, int N, int K,
                                                        EpiParams ep) {
@@ -30,10 +32,11 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
   const int t = threadIdx.x;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int ty = t / 16, tx = t % 16;
-  float acc[4][4] = {};
+  constexpr int RM = TM / 16, RN = TN / 16;
+  float acc[RM][RN] = {};
   for (int k0 = 0; k0 < K; k0 += TK) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < (TM * TK) / 256; ++i) {
       const int idx = t + i * 256;
       int m, k;
       if (MA == kMajorK) { k = idx % TK; m = idx / TK; } else { m = idx % TM; k = idx / TM; }
@@ -41,6 +44,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       float v = 0.f;
       if (gm < M && gk < K) v = MA == kMajorK ? A[(long long)gm * lda + gk] : A[(long long)gk * lda + gm];
       As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < (TN * TK) / 256; ++i) {
+      const int idx = t + i * 256;
       int n, kk;
       if (MB == kMajorK) { kk = idx % TK; n = idx / TK; } else { n = idx % TN; kk = idx / TN; }
       const int gn = n0 + n, gk2 = k0 + kk;
@@ -51,27 +58,27 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
-      float a[4], b[4];
+      float a[RM], b[RN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < RM; ++i) a[i] = As[k][ty * RM + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+      for (int j = 0; j < RN; ++j) b[j] = Bs[k][tx * RN + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
     if (m >= M) continue;
     const int grp = ep.group_rows > 0 ? m / ep.group_rows : 0;
     float rs = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < RN; ++j) {
+      const int n = n0 + tx * RN + j;
       if (n >= N) continue;
       float v = acc[i][j] * ep.alpha;
       if (ep.raw) st_elem(ep.raw, ep.raw_dt, (long long)m * ep.raw_ld + n, v);
@@ -90,21 +97,28 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
   }
 }
 
-}  // namespace
-
-int gemm_f32(const GemmDesc& g, cudaStream_t stream) {
-  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(ED2_ERR_BAD_SHAPE, "gemm_f32: empty shape");
+template <int TM, int TN>
+void launch_f32(const GemmDesc& g, cudaStream_t stream) {
   dim3 grid((g.N + TN - 1) / TN, (g.M + TM - 1) / TM);
   const float* A = reinterpret_cast<const float*>(g.A);
   const float* B = reinterpret_cast<const float*>(g.B);
   if (g.major_a == kMajorK && g.major_b == kMajorK)
-    gemm_f32_kernel<kMajorK, kMajorK><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
+    gemm_f32_kernel<kMajorK, kMajorK, TM, TN><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
   else if (g.major_a == kMajorK && g.major_b == kMajorMN)
-    gemm_f32_kernel<kMajorK, kMajorMN><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
+    gemm_f32_kernel<kMajorK, kMajorMN, TM, TN><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
   else if (g.major_a == kMajorMN && g.major_b == kMajorK)
-    gemm_f32_kernel<kMajorMN, kMajorK><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
+    gemm_f32_kernel<kMajorMN, kMajorK, TM, TN><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
   else
-    gemm_f32_kernel<kMajorMN, kMajorMN><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
+    gemm_f32_kernel<kMajorMN, kMajorMN, TM, TN><<<grid, 256, 0, stream>>>(A, g.lda, B, g.ldb, g.M, g.N, g.K, g.ep);
+}
+
+}  // namespace
+
+int gemm_f32(const GemmDesc& g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(ED2_ERR_BAD_SHAPE, "gemm_f32: empty shape");
+  const long long tiles64 = (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
+  if (tiles64 >= 148) launch_f32<64, 64>(g, stream);
+  else launch_f32<32, 32>(g, stream);
   count_launch();
   return check_launch("gemm_f32");
 }
