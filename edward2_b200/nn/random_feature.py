@@ -108,7 +108,7 @@ class LaplaceRandomFeatureCovariance(m.Module):
         fused GEMM (row-sum epilogue for the diagonal)."""
         p = precision_matrix.value if hasattr(precision_matrix, "value") else precision_matrix
         chol = torch.linalg.cholesky(p.double())
-        sigma = torch.cholesky_inverse(chol).to(torch.float32)
+        sigma = torch.cholesky_inverse(chol).to(torch.float32).contiguous()
         phi = F.as_compute(gp_features, dtype)
         sig = sigma if dtype == torch.float32 else ops.cast(sigma, dtype)
         if diagonal_only:

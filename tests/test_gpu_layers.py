@@ -315,5 +315,5 @@ def test_two_layer_mlp_cross_layer_fusion(cuda, dtype, tol):
     assert rel_err(to_np(l1.bias.grad), g1["dbias"]) < tol
     # the presample() hint changes scheduling only
     (p1, p2, pout) = results[1]
-    assert rel_err(to_np(pout), to_np(out)) < 1e-6
-    assert rel_err(to_np(p1.kernel_initializer.mean.grad), to_np(m1.grad)) < 1e-5
+    assert rel_err(to_np(pout), to_np(out)) < (1e-6 if dtype == "float32" else tol)
+    assert rel_err(to_np(p1.kernel_initializer.mean.grad), to_np(m1.grad)) < (1e-5 if dtype == "float32" else tol)
