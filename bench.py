@@ -108,7 +108,7 @@ def run_reference(args):
                          "sample": f"{sample_batch}-row batches of the cfg2 MLP, {args.steps} fwd+bwd steps"},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -411,12 +411,30 @@ def run_ours(args):
                                           "step_tflops": flops_per_step(BATCH, True) * world / (flip["ms"] * 1e-3) / 1e12,
                                           "loss": flip["loss"]})},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else libraries print (e.g. NCCL's version banner) was
+    diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # stray prints of native libraries must not pollute the one-line contract
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
