@@ -311,6 +311,8 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
         loss_val = float(run_step().item())
+        if reducer is not None:
+            reducer.remove()
         return dict(ms=ms, e2e_ms=e2e_ms, launches=launches, loss=loss_val, graph=graph is not None, layers=layers)
 
     sampler = ClockSampler(local) if rank == 0 else None

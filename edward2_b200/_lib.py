@@ -110,6 +110,7 @@ class ReparamBwd(C.Structure):
         ("dmu", _vp), ("drho", _vp), ("dbias", _vp),
         ("kl_grad_scale", _f), ("prior_mean", _f), ("prior_std", _f), ("kl_upstream", _vp),
         ("gy_premasked", _i), ("x_is_relu", _i), ("prev_dbias", _vp),
+        ("phase", _i), ("dmu_lp", _vp), ("drho_lp", _vp),
     ]
 
 

@@ -319,23 +319,25 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
   if (a->gy_premasked) {
     gp = a->gy;  // the producer's dX epilogue already applied act'(y) and accumulated dbias
     gp_ld = a->gy_ld;
-  } else {
-    BwdOutArgs o{};
-    o.dt = a->dtype; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = a->batch; o.act = a->act; o.fast = 0;
-    o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld;
-    o.dz = a->gp; o.dz_ld = a->gp_ld;
-    o.dbias = a->dbias;
-    ED2_TRY(k_bwd_out(o, s));
   }
-  // dW = xᵀ gp lands in dmu; the finishing pass turns it into (dmu, drho) in place.
-  EpiParams e = epi_default();
-  e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
-  ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, gp, gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
-  // fork after dW: the finishing pass (CUDA cores) runs beside the dX GEMM (tensor cores).  The GEMM is enqueued
-  // FIRST so that its CTAs are resident before the side kernel's blocks fill the remaining registers of each SM.
-  ForkJoin fj(s, a->dx != nullptr);
-  int st = ED2_OK;
-  if (a->dx != nullptr) {
+  if (a->phase != 2) {
+    if (!a->gy_premasked) {
+      BwdOutArgs o{};
+      o.dt = a->dtype; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = a->batch; o.act = a->act; o.fast = 0;
+      o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld;
+      o.dz = a->gp; o.dz_ld = a->gp_ld;
+      o.dbias = a->dbias;
+      ED2_TRY(k_bwd_out(o, s));
+    }
+    // dW = xᵀ gp lands in dmu; the finishing pass turns it into (dmu, drho) in place (+ bf16 bucket copies).
+    EpiParams e = epi_default();
+    e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
+    ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, gp, gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
+    ED2_TRY(k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
+                                 a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
+                                 a->dtype == kBF16, s, a->dmu_lp, a->drho_lp));
+  }
+  if (a->phase != 1 && a->dx != nullptr) {
     EpiParams e2 = epi_default();
     e2.out = a->dx; e2.out_ld = a->dx_ld; e2.out_dt = a->dtype;
     if (a->x_is_relu && a->prev_dbias != nullptr) {
@@ -343,14 +345,9 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
       e2.mask_src = a->x; e2.mask_ld = a->x_ld; e2.mask_dt = a->dtype;
       e2.col_sum = a->prev_dbias; e2.col_sum_ld = a->in_dim;
     }
-    st = gemm_gwt(a->dtype, gp, gp_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s);
+    ED2_TRY(gemm_gwt(a->dtype, gp, gp_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s));
   }
-  if (st == ED2_OK)
-    st = k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
-                              a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
-                              a->dtype == kBF16, fj.side());
-  fj.join();
-  return st;
+  return ED2_OK;
 }
 
 // ------------------------------------------------------------------------------------------ Flipout

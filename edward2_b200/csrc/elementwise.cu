@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(kBlock) grad_finish_lean_kernel(const float* d
                                                                   const float* __restrict__ rho, uint64_t seed,
                                                                   uint64_t stream, const uint64_t* step, long long n,
                                                                   float klg_in, const double* kl_upstream, Prior p,
-                                                                  float* dmu, float* drho) {
+                                                                  float* dmu, float* drho, __nv_bfloat16* dmu_lp,
+                                                                  __nv_bfloat16* drho_lp) {
   const float klg = klg_in * (kl_upstream != nullptr ? static_cast<float>(*kl_upstream) : 1.f);
   const float inv_s2 = 1.f / (p.stddev * p.stddev);
   const uint64_t key = step != nullptr ? seed + __ldg(reinterpret_cast<const unsigned long long*>(step)) * 0x9E3779B97F4A7C15ull : seed;
@@ -296,6 +297,10 @@ __global__ void __launch_bounds__(kBlock) grad_finish_lean_kernel(const float* d
     }
     reinterpret_cast<float4*>(dmu)[b] = make_float4(om[0], om[1], om[2], om[3]);
     reinterpret_cast<float4*>(drho)[b] = make_float4(orr[0], orr[1], orr[2], orr[3]);
+    if (dmu_lp != nullptr) {  // bf16 copies for the all-reduce buckets, written while the values are in registers
+      reinterpret_cast<uint2*>(dmu_lp)[b] = make_uint2(pack2_bf16(om[0], om[1]), pack2_bf16(om[2], om[3]));
+      reinterpret_cast<uint2*>(drho_lp)[b] = make_uint2(pack2_bf16(orr[0], orr[1]), pack2_bf16(orr[2], orr[3]));
+    }
   }
 }
 
@@ -766,14 +771,22 @@ int k_normal_kl_bwd(const float* mu, const float* rho, long long n, Prior p, flo
 
 int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* mu, const float* rho, Noise eps,
                          long long n, float klg, const double* kl_upstream, Prior p, float* dmu, float* drho, bool fast,
-                         cudaStream_t s) {
+                         cudaStream_t s, void* dmu_lp, void* drho_lp) {
   if (n <= 0) return ED2_OK;
   const int g = std::min(grid_for((n + 3) / 4), side_grid_cap());
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (fast && eps.injected == nullptr && n % 4 == 0 && al16(d_mean) && al16(d_pert) && al16(mu) && al16(rho) && al16(dmu) && al16(drho)) {
-    grad_finish_lean_kernel<<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps.seed, eps.stream, eps.step, n, klg, kl_upstream, p, dmu, drho);
+    grad_finish_lean_kernel<<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps.seed, eps.stream, eps.step, n, klg, kl_upstream, p, dmu, drho,
+                                                 reinterpret_cast<__nv_bfloat16*>(dmu_lp), reinterpret_cast<__nv_bfloat16*>(drho_lp));
     count_launch();
     return check_launch("normal_grad_finish(lean)");
+  }
+  if (dmu_lp != nullptr) {  // general path: the bf16 copies are made by the cast kernel afterwards
+    int st = k_normal_grad_finish(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho, fast, s, nullptr, nullptr);
+    if (st != ED2_OK) return st;
+    st = k_cast2d(dmu, kF32, n, dmu_lp, kBF16, n, 1, n, s);
+    if (st != ED2_OK) return st;
+    return k_cast2d(drho, kF32, n, drho_lp, kBF16, n, 1, n, s);
   }
   if (fast) normal_grad_finish_kernel<true><<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
   else normal_grad_finish_kernel<false><<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);

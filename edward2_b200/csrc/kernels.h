@@ -25,7 +25,7 @@ int k_normal_kl_bwd(const float* mu, const float* rho, long long n, Prior p, flo
 // dmu = d_mean + kl*(mu-m)/s^2 ; drho = (d_pert*eps + kl*(sigma/s^2 - 1/sigma)) * sigmoid(rho)
 int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* mu, const float* rho, Noise eps,
                          long long n, float kl_grad_scale, const double* kl_upstream, Prior p, float* dmu, float* drho,
-                         bool fast, cudaStream_t s);
+                         bool fast, cudaStream_t s, void* dmu_lp = nullptr, void* drho_lp = nullptr);
 
 // ---- forward input preparation:  xo = x ∘ f  (f = alpha[e] | clip(mu+sigma*eps) | sign), dt in/out
 // mode 0: per-member vector fw_mu[e][cols] (BatchEnsemble alpha)

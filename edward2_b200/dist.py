@@ -46,16 +46,43 @@ class GradientAllReduce:
     gradient into a persistent bf16 bucket with the library's cast kernel, all-reduces the bucket, and `wait()` casts
     the sum back into `p.grad`."""
 
-    def __init__(self, params, group=None, average: bool = False, compress=None):
+    def __init__(self, params, group=None, average: bool = False, compress=None, early: bool = True):
         self.handles, self.group, self.average, self.compress = [], group, average, compress
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self._hooks, self._buckets = [], {}
+        self._hooks, self._buckets, self._early_done = [], {}, set()
+        self._ids = set()
         if self.world > 1:
             for p in params:
                 if p.requires_grad:
+                    self._ids.add(id(p))
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._hook))
+            if early and compress is not None:
+                from . import functional as F
+
+                F.GradSync.current = self
+
+    # -- early path: called by the layer's backward between its parameter-gradient phase and its dX GEMM -------------
+    def wants(self, p) -> bool:
+        return self.world > 1 and self.compress is not None and id(p) in self._ids and p.numel() >= 65536
+
+    def bucket(self, p):
+        b = self._buckets.get(id(p))
+        if b is None:
+            b = torch.empty(p.shape, dtype=self.compress, device=p.device)
+            self._buckets[id(p)] = b
+        return b
+
+    def early(self, p, grad, bucket):
+        """`bucket` already holds the bf16 copy of `grad` (written by the gradient-finishing kernel)."""
+        h = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        g2 = grad.reshape(-1, grad.shape[-1]) if grad.dim() > 1 else grad.reshape(1, -1)
+        self.handles.append((h, g2, bucket.reshape(g2.shape)))
+        self._early_done.add(id(p))
 
     def _hook(self, p):
+        if id(p) in self._early_done:  # its all-reduce is already in flight
+            self._early_done.discard(id(p))
+            return
         g = p.grad
         if self.average:
             g.div_(self.world)
@@ -63,10 +90,7 @@ class GradientAllReduce:
             from . import ops
 
             g2 = g.reshape(-1, g.shape[-1]) if g.dim() > 1 else g.reshape(1, -1)
-            b = self._buckets.get(id(p))
-            if b is None or b.shape != g2.shape:
-                b = torch.empty(g2.shape, dtype=self.compress, device=g.device)
-                self._buckets[id(p)] = b
+            b = self.bucket(p).reshape(g2.shape)
             ops.cast(g2, self.compress, out=b)
             h = dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self.handles.append((h, g2, b))
@@ -86,6 +110,10 @@ class GradientAllReduce:
         for h in self._hooks:
             h.remove()
         self._hooks.clear()
+        from . import functional as F
+
+        if F.GradSync.current is self:
+            F.GradSync.current = None
 
 
 def allreduce_precision_partial(partial: torch.Tensor, group=None) -> torch.Tensor:

@@ -184,6 +184,14 @@ class Rank1Dense(torch.autograd.Function):
         return dx, dw, dmu_r, drho_r, dmu_s, drho_s, dbias, None, None, None, None, None
 
 
+class GradSync:
+    """Hook point for data-parallel training: when set (edward2_b200.dist.GradientAllReduce installs itself), a layer's
+    backward is split so that the all-reduce of its parameter gradients is launched BEFORE its dX GEMM is enqueued and
+    overlaps it."""
+
+    current = None
+
+
 class ReluLink:
     """Cross-layer fusion token.  A layer whose fused activation is ReLU attaches one to its output tensor; the layer
     that consumes that tensor applies relu'(x) = (x > 0) and the bias-gradient column sums in its own dX GEMM epilogue
@@ -284,6 +292,15 @@ class ReparamDense(torch.autograd.Function):
         a.kl_grad_scale = kl_scale if gkl is not None else 0.0
         a.prior_mean, a.prior_std, a.kl_upstream = pm, ps, _p(up)
         a.gy_premasked, a.x_is_relu, a.prev_dbias = int(premasked), int(fuse_prev), _p(prev_dbias)
+        sync = GradSync.current
+        if sync is not None and sync.wants(mu):
+            # phase 1: parameter gradients (+ bf16 bucket copies) -> launch their all-reduce -> phase 2: dX GEMM
+            bmu, brho = sync.bucket(mu), sync.bucket(rho)
+            a.phase, a.dmu_lp, a.drho_lp = 1, _p(bmu), _p(brho)
+            _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd[params]")
+            sync.early(mu, dmu, bmu)
+            sync.early(rho, drho, brho)
+            a.phase = 2
         _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd")
         if fuse_prev:
             in_link.dx_ptr, in_link.dbias = dx.data_ptr(), prev_dbias

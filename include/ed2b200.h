@@ -256,6 +256,12 @@ typedef struct {
    * x_is_relu != 0: x is the output of a ReLU layer -> dx := dx ∘ (x > 0) in the dX epilogue and prev_dbias[in_dim]
    * (zeroed here) receives its column sums, i.e. the producing layer's bias gradient. */
   int gy_premasked; int x_is_relu; float* prev_dbias;
+  /* phase: 0 = whole backward; 1 = parameter gradients only (output-side pass, dW GEMM, finishing pass);
+   * 2 = input gradient only (dX GEMM; phase 1 must have run on the same stream).  The split lets a data-parallel
+   * caller launch the gradient all-reduce of this layer between the phases, so it overlaps the dX GEMM.
+   * dmu_lp / drho_lp (optional, bf16, [I][O] dense): copies of the gradients for bf16 all-reduce buckets, written by
+   * the finishing pass itself. */
+  int phase; void* dmu_lp; void* drho_lp;
 } ed2_reparam_bwd_args;
 int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream);
 
