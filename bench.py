@@ -165,6 +165,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and args.gemm_ctas > 0:
+        # leave SMs for the NCCL all-reduce kernels (read by libed2b200 at its first GEMM launch)
+        os.environ.setdefault("ED2_GEMM_MAX_CTAS", str(args.gemm_ctas))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     lib = _lib.load()
@@ -397,7 +400,8 @@ def run_ours(args):
                    "l2": "inputs > L2: one step touches ~0.6 GB (fp32 mu/rho + grads 400 MB, bf16 W 50 MB, activations)",
                    "cuda_graph": main["graph"], "kl_scale": KL_SCALE,
                    "grad_allreduce": None if world == 1 else ("fp32" if args.fp32_allreduce else "bf16 buckets") +
-                   ", per-parameter, overlapped with backward"},
+                   ", per-parameter, overlapped with backward",
+                   "gemm_ctas": int(os.environ.get("ED2_GEMM_MAX_CTAS", 148))},
         "e2e": {"value": global_batch / (main["e2e_ms"] * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": (x_host.numel() * 2 + y_host.numel() * 8) * world,
                 "d2h_bytes_per_step": 8 * world, "ms_per_step": main["e2e_ms"]},
@@ -444,6 +448,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--fp32-allreduce", action="store_true", help="all-reduce fp32 gradients instead of bf16 buckets")
+    ap.add_argument("--gemm-ctas", type=int, default=128, help="persistent GEMM CTAs when N > 1 (rest: NCCL)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-variants", action="store_true")
     args = ap.parse_args()

@@ -333,10 +333,12 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
     EpiParams e = epi_default();
     e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
     ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, gp, gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
-    ED2_TRY(k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
-                                 a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
-                                 a->dtype == kBF16, s, a->dmu_lp, a->drho_lp));
   }
+  // Whole-backward call: the finishing pass (CUDA cores) is forked onto the side stream and the dX GEMM (tensor
+  // cores) is enqueued first.  Split call (phase 1): the finishing pass stays on the caller's stream because the
+  // caller launches the gradient all-reduce right after it.
+  ForkJoin fj(s, a->phase == 0 && a->dx != nullptr);
+  int st = ED2_OK;
   if (a->phase != 1 && a->dx != nullptr) {
     EpiParams e2 = epi_default();
     e2.out = a->dx; e2.out_ld = a->dx_ld; e2.out_dt = a->dtype;
@@ -345,9 +347,14 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
       e2.mask_src = a->x; e2.mask_ld = a->x_ld; e2.mask_dt = a->dtype;
       e2.col_sum = a->prev_dbias; e2.col_sum_ld = a->in_dim;
     }
-    ED2_TRY(gemm_gwt(a->dtype, gp, gp_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s));
+    st = gemm_gwt(a->dtype, gp, gp_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s);
   }
-  return ED2_OK;
+  if (a->phase != 2 && st == ED2_OK)
+    st = k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
+                              a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
+                              a->dtype == kBF16, fj.side(), a->dmu_lp, a->drho_lp);
+  fj.join();
+  return st;
 }
 
 // ------------------------------------------------------------------------------------------ Flipout

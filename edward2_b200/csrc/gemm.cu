@@ -55,6 +55,12 @@ int num_sms() {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    // Data-parallel runs leave a few SMs to the NCCL kernels: a persistent GEMM CTA holds ~194 KB of shared memory, so
+    // a collective's CTAs cannot co-reside with it and would otherwise only run between GEMMs.
+    if (const char* e = std::getenv("ED2_GEMM_MAX_CTAS")) {
+      const int cap = std::atoi(e);
+      if (cap >= 2 && cap < n) n = cap & ~1;
+    }
   }
   return n;
 }
