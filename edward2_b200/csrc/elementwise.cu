@@ -19,13 +19,13 @@ constexpr int kBlock = 256;
 constexpr int kMaxGrid = 148 * 8;
 
 // Grid cap of the issue-bound sampling / finishing kernels.  They are meant to run on side streams BESIDE a GEMM
-// (tensor cores), so they must not fill an SM's register file: 2 resident blocks per SM leave room for a GEMM CTA.
+// (tensor cores), measured on B200: true co-residency with the persistent GEMM does not pay (the GEMM slows by as much as the side kernel gains), so the cap defaults to full occupancy; ED2_SIDE_BLOCKS_PER_SM lowers it for experiments.
 int side_grid_cap() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("ED2_SIDE_BLOCKS_PER_SM");
-    int b = e ? std::atoi(e) : 2;
-    if (b < 1 || b > 8) b = 2;
+    int b = e ? std::atoi(e) : 8;
+    if (b < 1 || b > 8) b = 8;
     v = 148 * b;
   }
   return v;
