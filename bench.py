@@ -187,7 +187,7 @@ def run_ours(args):
         layers = build_model(ed, flipout, device, step_counter)
         params = params_of(layers)
         reducer = None
-        if world > 1:
+        if world > 1 and not args.no_allreduce:
             # gradient all-reduce launched as soon as each parameter's gradient is final, overlapping the rest of
             # the backward pass (NCCL runs on its own stream); bf16 buckets halve the NVLink bytes
             from edward2_b200.dist import GradientAllReduce
@@ -449,6 +449,7 @@ def main():
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--fp32-allreduce", action="store_true", help="all-reduce fp32 gradients instead of bf16 buckets")
     ap.add_argument("--gemm-ctas", type=int, default=128, help="persistent GEMM CTAs when N > 1 (rest: NCCL)")
+    ap.add_argument("--no-allreduce", action="store_true", help="diagnostic only: skip the gradient all-reduce")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-variants", action="store_true")
     args = ap.parse_args()
