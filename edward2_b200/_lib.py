@@ -161,6 +161,7 @@ SIGNATURES = {
     "ed2_rank1_dense_bwd": (_i, [C.POINTER(Rank1Bwd), _vp]),
     "ed2_reparam_dense_fwd": (_i, [C.POINTER(ReparamFwd), _vp]),
     "ed2_reparam_dense_bwd": (_i, [C.POINTER(ReparamBwd), _vp]),
+    "ed2_normal_grad_finish": (_i, [_vp, _i, _vp, _vp, Noise, _ll, _f, _vp, _f, _f, _vp, _vp, _i, _vp]),
     "ed2_flipout_dense_fwd": (_i, [C.POINTER(FlipoutFwd), _vp]),
     "ed2_flipout_dense_bwd": (_i, [C.POINTER(FlipoutBwd), _vp]),
     "ed2_spectral_norm_update": (_i, [_vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),

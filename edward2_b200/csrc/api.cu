@@ -320,6 +320,20 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
     gp = a->gy;  // the producer's dX epilogue already applied act'(y) and accumulated dbias
     gp_ld = a->gy_ld;
   }
+  if (a->phase == 3) {
+    if (a->dmu_lp == nullptr) return set_error(ED2_ERR_BAD_ARG, "reparam_bwd phase 3 needs the bf16 bucket dmu_lp");
+    if (!a->gy_premasked) {
+      BwdOutArgs o{};
+      o.dt = a->dtype; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = a->batch; o.act = a->act; o.fast = 0;
+      o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld;
+      o.dz = a->gp; o.dz_ld = a->gp_ld;
+      o.dbias = a->dbias;
+      ED2_TRY(k_bwd_out(o, s));
+    }
+    EpiParams e = epi_default();
+    e.out = a->dmu_lp; e.out_ld = a->out_dim; e.out_dt = kBF16;
+    return gemm_xtg(a->dtype, a->x, a->x_ld, gp, gp_ld, a->batch, a->in_dim, a->out_dim, e, s);
+  }
   if (a->phase != 2) {
     if (!a->gy_premasked) {
       BwdOutArgs o{};
@@ -355,6 +369,14 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
                               a->dtype == kBF16, fj.side(), a->dmu_lp, a->drho_lp);
   fj.join();
   return st;
+}
+
+int ed2_normal_grad_finish(const void* dw, int dw_dtype, const float* mu, const float* rho, ed2_noise eps, long long n,
+                           float kl_grad_scale, const double* kl_upstream, float prior_mean, float prior_std,
+                           float* dmu, float* drho, int fast, void* stream) {
+  ED2_TRY(check_dt(dw_dtype));
+  return k_normal_grad_finish_any(dw, dw_dtype, mu, rho, N(eps), n, kl_grad_scale, kl_upstream,
+                                  Prior{prior_mean, prior_std}, dmu, drho, fast != 0, S(stream));
 }
 
 // ------------------------------------------------------------------------------------------ Flipout

@@ -304,6 +304,37 @@ __global__ void __launch_bounds__(kBlock) grad_finish_lean_kernel(const float* d
   }
 }
 
+// Finishing pass fed by a bf16 weight gradient (the all-reduced bucket of a data-parallel step).
+template <bool kFast>
+__global__ void __launch_bounds__(kBlock) grad_finish_bf16_kernel(const __nv_bfloat16* __restrict__ dw,
+                                                                  const float* __restrict__ mu,
+                                                                  const float* __restrict__ rho, Noise eps, long long n,
+                                                                  float klg_in, const double* kl_upstream, Prior p,
+                                                                  float* dmu, float* drho) {
+  const float klg = klg_in * (kl_upstream != nullptr ? static_cast<float>(*kl_upstream) : 1.f);
+  const float inv_s2 = 1.f / (p.stddev * p.stddev);
+  const long long nblk = (n + 3) >> 2;
+  for (long long b = blockIdx.x * (long long)kBlock + threadIdx.x; b < nblk; b += (long long)gridDim.x * kBlock) {
+    const long long i = b << 2;
+    const int valid = static_cast<int>(min(4LL, n - i));
+    float m[4], r[4], g[4], e[4], om[4], orr[4];
+    ld4(mu, kF32, i, valid, m);
+    ld4(rho, kF32, i, valid, r);
+    ld4(dw, kBF16, i, valid, g);
+    noise4<0, kFast>(eps, i, n, e);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ex;
+      const float sigma = kFast ? sigma_from_rho_fast(r[j], ex) : sigma_from_rho(r[j], ex);
+      const float sgm = __fdividef(ex, 1.f + ex);
+      om[j] = g[j] + klg * (m[j] - p.mean) * inv_s2;
+      orr[j] = (g[j] * e[j] + klg * (sigma * inv_s2 - __fdividef(1.f, sigma))) * sgm;
+    }
+    st4(dmu, kF32, i, valid, om);
+    st4(drho, kF32, i, valid, orr);
+  }
+}
+
 __global__ void normal_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ rho, long long n, Prior p,
                                      float scale, double* out) {
   const long long nblk = (n + 3) >> 2;
@@ -792,6 +823,22 @@ int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* 
   else normal_grad_finish_kernel<false><<<g, kBlock, 0, s>>>(d_mean, d_pert, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
   count_launch();
   return check_launch("normal_grad_finish");
+}
+
+int k_normal_grad_finish_any(const void* dw, int dw_dt, const float* mu, const float* rho, Noise eps, long long n,
+                             float klg, const double* kl_upstream, Prior p, float* dmu, float* drho, bool fast,
+                             cudaStream_t s) {
+  if (dw_dt == kF32) {
+    const float* d = reinterpret_cast<const float*>(dw);
+    return k_normal_grad_finish(d, d, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho, fast, s, nullptr, nullptr);
+  }
+  if (n <= 0) return ED2_OK;
+  const int g = std::min(grid_for((n + 3) / 4), side_grid_cap());
+  const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dw);
+  if (fast) grad_finish_bf16_kernel<true><<<g, kBlock, 0, s>>>(d, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
+  else grad_finish_bf16_kernel<false><<<g, kBlock, 0, s>>>(d, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
+  count_launch();
+  return check_launch("normal_grad_finish(bf16 dW)");
 }
 
 int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols, int rpm, int mode,

@@ -27,6 +27,11 @@ int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* 
                          long long n, float kl_grad_scale, const double* kl_upstream, Prior p, float* dmu, float* drho,
                          bool fast, cudaStream_t s, void* dmu_lp = nullptr, void* drho_lp = nullptr);
 
+// dW given in fp32 or bf16 (an all-reduced bucket); same dW feeds both the mean and the perturbation term
+int k_normal_grad_finish_any(const void* dw, int dw_dt, const float* mu, const float* rho, Noise eps, long long n,
+                             float kl_grad_scale, const double* kl_upstream, Prior p, float* dmu, float* drho, bool fast,
+                             cudaStream_t s);
+
 // ---- forward input preparation:  xo = x ∘ f  (f = alpha[e] | clip(mu+sigma*eps) | sign), dt in/out
 // mode 0: per-member vector fw_mu[e][cols] (BatchEnsemble alpha)
 // mode 1: per-example sampled fast weight clip(fw_mu[e] + softplus(fw_rho[e])*eps[b], -10, 10) (rank-1)

@@ -79,6 +79,14 @@ class GradientAllReduce:
         self.handles.append((h, g2, bucket.reshape(g2.shape)))
         self._early_done.add(id(p))
 
+    def early_raw(self, params, bucket, finish):
+        """All-reduce a raw bf16 weight-gradient bucket shared by several parameters (mean and stddev of one kernel);
+        `finish()` turns the reduced bucket into their fp32 gradients at wait()."""
+        h = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.handles.append((h, finish, None))
+        for p in params:
+            self._early_done.add(id(p))
+
     def _hook(self, p):
         if id(p) in self._early_done:  # its all-reduce is already in flight
             self._early_done.discard(id(p))
@@ -100,7 +108,9 @@ class GradientAllReduce:
     def wait(self):
         for h, g2, b in self.handles:
             h.wait()
-            if b is not None:
+            if callable(g2):
+                g2()  # deferred gradient-finishing pass on the reduced bucket
+            elif b is not None:
                 from . import ops
 
                 ops.cast(b, torch.float32, out=g2)

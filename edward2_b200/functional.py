@@ -294,12 +294,20 @@ class ReparamDense(torch.autograd.Function):
         a.gy_premasked, a.x_is_relu, a.prev_dbias = int(premasked), int(fuse_prev), _p(prev_dbias)
         sync = GradSync.current
         if sync is not None and sync.wants(mu):
-            # phase 1: parameter gradients (+ bf16 bucket copies) -> launch their all-reduce -> phase 2: dX GEMM
-            bmu, brho = sync.bucket(mu), sync.bucket(rho)
-            a.phase, a.dmu_lp, a.drho_lp = 1, _p(bmu), _p(brho)
-            _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd[params]")
-            sync.early(mu, dmu, bmu)
-            sync.early(rho, drho, brho)
+            # data parallel, every rank draws the same eps: reduce the RAW weight gradient (one bf16 tensor instead of
+            # dmu and drho) and finish after the reduction.  Phase 3: dW GEMM -> bf16 bucket; the all-reduce is launched
+            # before the dX GEMM is enqueued (phase 2) and overlaps it; the finishing pass runs at reducer.wait().
+            bucket = sync.bucket(mu)
+            a.phase, a.dmu_lp = 3, _p(bucket)
+            _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd[dW]")
+            noise, klg, kup, n_el, fast = eps.c(), a.kl_grad_scale, up, I * O, int(dtype == torch.bfloat16)
+
+            def finish(bucket=bucket, noise=noise, klg=klg, kup=kup, n_el=n_el, fast=fast):
+                _lib.check(lib.ed2_normal_grad_finish(bucket.data_ptr(), BF16, mu.data_ptr(), rho.data_ptr(), noise, n_el,
+                                                      klg, _p(kup), pm, ps, dmu.data_ptr(), drho.data_ptr(), fast,
+                                                      _lib.stream_ptr()), "ed2_normal_grad_finish")
+
+            sync.early_raw((mu, rho), bucket, finish)
             a.phase = 2
         _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd")
         if fuse_prev:

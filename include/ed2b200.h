@@ -260,10 +260,21 @@ typedef struct {
    * 2 = input gradient only (dX GEMM; phase 1 must have run on the same stream).  The split lets a data-parallel
    * caller launch the gradient all-reduce of this layer between the phases, so it overlaps the dX GEMM.
    * dmu_lp / drho_lp (optional, bf16, [I][O] dense): copies of the gradients for bf16 all-reduce buckets, written by
-   * the finishing pass itself. */
+   * the finishing pass itself.
+   * phase 3 = like 1 but WITHOUT the finishing pass: the dW GEMM writes the raw weight gradient as bf16 into dmu_lp
+   * (the all-reduce bucket); the caller reduces it and finishes with ed2_normal_grad_finish.  Valid when every rank
+   * draws the same eps (same seed), i.e. the data-parallel step reproduces the single-device global-batch step. */
   int phase; void* dmu_lp; void* drho_lp;
 } ed2_reparam_bwd_args;
 int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream);
+
+/* Gradient-finishing pass on its own: (dmu, drho) from a weight gradient dW [n] (fp32 or bf16, e.g. a bf16 bucket that
+ * was just all-reduced across data-parallel ranks, every rank having drawn the SAME eps):
+ *   dmu = dW + klg (mu - m) / s^2 ;  drho = (dW * eps + klg (sigma / s^2 - 1 / sigma)) * sigmoid(rho)
+ * with klg = kl_grad_scale * (*kl_upstream).  `fast` selects the hardware-approximate math of the bf16 compute mode. */
+int ed2_normal_grad_finish(const void* dw, int dw_dtype, const float* mu, const float* rho, ed2_noise eps, long long n,
+                           float kl_grad_scale, const double* kl_upstream, float prior_mean, float prior_std,
+                           float* dmu, float* drho, int fast, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DenseFlipout (edward2/tensorflow/layers/dense.py:255-285):
