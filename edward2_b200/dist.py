@@ -84,8 +84,6 @@ class GradientAllReduce:
         `finish()` turns the reduced bucket into their fp32 gradients at wait()."""
         h = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.handles.append((h, finish, None))
-        for p in params:
-            self._early_done.add(id(p))
 
     def _hook(self, p):
         if id(p) in self._early_done:  # its all-reduce is already in flight

@@ -302,18 +302,30 @@ class ReparamDense(torch.autograd.Function):
             _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd[dW]")
             noise, klg, kup, n_el, fast = eps.c(), a.kl_grad_scale, up, I * O, int(dtype == torch.bfloat16)
 
-            def finish(bucket=bucket, noise=noise, klg=klg, kup=kup, n_el=n_el, fast=fast):
+            def finish(bucket=bucket, noise=noise, klg=klg, kup=kup, n_el=n_el, fast=fast, dmu=dmu, drho=drho):
                 _lib.check(lib.ed2_normal_grad_finish(bucket.data_ptr(), BF16, mu.data_ptr(), rho.data_ptr(), noise, n_el,
                                                       klg, _p(kup), pm, ps, dmu.data_ptr(), drho.data_ptr(), fast,
                                                       _lib.stream_ptr()), "ed2_normal_grad_finish")
+                # these gradients bypass autograd's accumulation (backward returned None for them)
+                for p_, g_ in ((mu, dmu), (rho, drho)):
+                    if p_.grad is None:
+                        p_.grad = g_
+                    else:
+                        p_.grad += g_
+
+            deferred = True
 
             sync.early_raw((mu, rho), bucket, finish)
             a.phase = 2
+        else:
+            deferred = False
         _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd")
         if fuse_prev:
             in_link.dx_ptr, in_link.dbias = dx.data_ptr(), prev_dbias
         if dx is not None and dx.dtype != x_dtype:
             dx = dx.to(x_dtype)
+        if deferred:  # mean / stddev gradients are installed by the reducer after the all-reduce
+            return dx, None, None, dbias, None, None, None, None, None, None, None, None, None
         return dx, dmu, drho, dbias, None, None, None, None, None, None, None, None, None
 
 
