@@ -90,6 +90,8 @@ class GradientAllReduce:
             self._early_done.discard(id(p))
             return
         g = p.grad
+        if g is None:  # this parameter's gradient is installed later by a deferred finishing pass (early_raw)
+            return
         if self.average:
             g.div_(self.world)
         if self.compress is not None and g.is_cuda and g.dtype == torch.float32 and g.numel() >= 65536:
