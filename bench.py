@@ -448,7 +448,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--fp32-allreduce", action="store_true", help="all-reduce fp32 gradients instead of bf16 buckets")
-    ap.add_argument("--gemm-ctas", type=int, default=128, help="persistent GEMM CTAs when N > 1 (rest: NCCL)")
+    ap.add_argument("--gemm-ctas", type=int, default=0, help="persistent GEMM CTAs when N > 1 (rest: NCCL)")
     ap.add_argument("--no-allreduce", action="store_true", help="diagnostic only: skip the gradient all-reduce")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-variants", action="store_true")
