@@ -150,6 +150,7 @@ SIGNATURES = {
     "ed2_philox_sign": (_i, [_vp, _ll, _u64, _u64, _vp]),
     "ed2_philox_raw": (_i, [_vp, _ll, _u64, _u64, _vp]),
     "ed2_cast": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _ll, _vp]),
+    "ed2_split_bf16": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _i, _i, _vp]),
     "ed2_sample_normal_weights": (_i, [_vp, _vp, Noise, _ll, _ll, _i, _vp, _i, _i, _vp, _i, _vp, _f, _f, _f, _vp]),
     "ed2_normal_kl_fwd": (_i, [_vp, _vp, _ll, _f, _f, _f, _vp, _vp]),
     "ed2_normal_kl_bwd": (_i, [_vp, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp]),

@@ -157,6 +157,13 @@ int ed2_cast(const void* src, int sdt, int sld, void* dst, int ddt, int dld, lon
   return k_cast2d(src, sdt, sld, dst, ddt, dld, rows, cols, S(s));
 }
 
+int ed2_split_bf16(const void* src, int src_dtype, int src_ld, void* dst, int dst_ld, long long rows, int cols, int is_b,
+                   int nsplit, void* s) {
+  ED2_TRY(check_dt(src_dtype));
+  if (nsplit != 2 && nsplit != 3) return set_error(ED2_ERR_BAD_ARG, "split_bf16: nsplit must be 2 or 3");
+  return k_split_bf16(src, src_dtype, src_ld, dst, dst_ld, rows, cols, is_b, nsplit, S(s));
+}
+
 int ed2_sample_normal_weights(const float* mu, const float* rho, ed2_noise eps, long long rows, long long cols, int mode,
                               void* w, int w_dtype, int w_ld, void* mean_out, int mean_ld, double* kl_out,
                               float kl_scale, float prior_mean, float prior_std, void* s) {

@@ -157,6 +157,37 @@ __global__ void cast2d_kernel(const void* src, int sdt, long long sld, void* dst
   }
 }
 
+
+// fp32 -> split-bf16 operand for an fp32-grade tensor-core product: x = h + m + l with h = bf16(x), m = bf16(x - h),
+// l = bf16(x - h - m) (24 mantissa bits).  The three-term product sum_{i+j<=2} a_i b_j is evaluated by ONE bf16 GEMM
+// whose contraction axis is the concatenation   A' = [h|h|h|m|m|l],  B' = [h|m|l|h|m|h]   (K' = 6K; nsplit = 2 keeps
+// the 3 leading terms: A' = [h|h|m], B' = [h|m|h], 16 mantissa bits).  fp32 accumulation happens in TMEM.
+__global__ void split_bf16_kernel(const void* __restrict__ src, int sdt, long long sld, __nv_bfloat16* __restrict__ dst,
+                                  long long dld, long long rows, int cols, int is_b, int nsplit) {
+  const long long n = rows * cols;
+  const int terms = nsplit == 3 ? 6 : 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const float x = ld1(src, sdt, r * sld + c);
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    __nv_bfloat16* d = dst + r * dld + c;
+    if (nsplit == 3) {
+      const __nv_bfloat16 a6[6] = {h, h, h, m, m, l}, b6[6] = {h, m, l, h, m, h};
+#pragma unroll
+      for (int t = 0; t < 6; ++t) d[(long long)t * cols] = is_b ? b6[t] : a6[t];
+    } else {
+      const __nv_bfloat16 a3[3] = {h, h, m}, b3[3] = {h, m, h};
+#pragma unroll
+      for (int t = 0; t < 3; ++t) d[(long long)t * cols] = is_b ? b3[t] : a3[t];
+    }
+    (void)terms;
+  }
+}
+
 // ------------------------------------------------------------------------------------------- sampling + KL
 __device__ __forceinline__ float kl_elem(float mu, float sigma, float pm, float ps) {
   const float d = mu - pm;
@@ -741,6 +772,15 @@ int k_cast2d(const void* src, int sdt, long long sld, void* dst, int ddt, long l
   cast2d_kernel<<<grid_for(rows * ((cols + 3) / 4)), kBlock, 0, s>>>(src, sdt, sld, dst, ddt, dld, rows, cols);
   count_launch();
   return check_launch("cast2d");
+}
+
+int k_split_bf16(const void* src, int sdt, long long sld, void* dst, long long dld, long long rows, int cols, int is_b,
+                 int nsplit, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  split_bf16_kernel<<<grid_for(rows * cols), kBlock, 0, s>>>(src, sdt, sld, reinterpret_cast<__nv_bfloat16*>(dst), dld, rows,
+                                                             cols, is_b, nsplit);
+  count_launch();
+  return check_launch("split_bf16");
 }
 
 int k_sample_weights(const float* mu, const float* rho, Noise eps, long long rows, long long cols, int mode, void* w,

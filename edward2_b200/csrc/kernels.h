@@ -16,6 +16,8 @@ int k_philox_fill(int kind /*0 normal 1 uniform 2 sign*/, float* out, long long 
 int k_philox_raw(uint32_t* out, long long n_blocks, uint64_t seed, uint64_t stream, cudaStream_t s);
 int k_cast2d(const void* src, int sdt, long long sld, void* dst, int ddt, long long dld, long long rows,
              long long cols, cudaStream_t s);
+int k_split_bf16(const void* src, int sdt, long long sld, void* dst, long long dld, long long rows, int cols, int is_b,
+                 int nsplit, cudaStream_t s);
 int k_sample_weights(const float* mu, const float* rho, Noise eps, long long rows, long long cols, int mode, void* w,
                      int wdt, long long wld, void* mean_out, long long mean_ld, double* kl_out, float kl_scale,
                      Prior p, cudaStream_t s);

@@ -170,10 +170,16 @@ class DenseReparameterization(Layer):
         self._side_stream.wait_stream(main)
         with torch.cuda.stream(self._side_stream):
             nz = self._noise("eps", S_KERNEL)
-            _lib.check(_lib.load().ed2_sample_normal_weights(
+            lib = _lib.load()
+            split = self.compute_dtype == torch.bfloat16 and kl64 is not None
+            # bf16: lean sampling kernel first (the GEMM waits for it), the accurate KL reduction after it
+            _lib.check(lib.ed2_sample_normal_weights(
                 mean.data_ptr(), rho.data_ptr(), nz.c(), I, O, 0, w_lp.data_ptr(), _lib.dt_of(w_lp), _lib.ld(w_lp),
-                None, 0, None if kl64 is None else kl64.data_ptr(), kl_scale, pm, ps, _lib.stream_ptr()),
+                None, 0, None if (kl64 is None or split) else kl64.data_ptr(), kl_scale, pm, ps, _lib.stream_ptr()),
                 "ed2_sample_normal_weights")
+            if split:
+                _lib.check(lib.ed2_normal_kl_fwd(mean.data_ptr(), rho.data_ptr(), I * O, pm, ps, kl_scale,
+                                                 kl64.data_ptr(), _lib.stream_ptr()), "ed2_normal_kl_fwd")
         self._presampled = (w_lp, kl64, nz)
 
     def call(self, inputs, training=None):

@@ -221,3 +221,31 @@ def mean_field_logits(logits: torch.Tensor, var: torch.Tensor, mean_field_factor
                                          mean_field_factor, likelihood, out.data_ptr(), _lib.stream_ptr()),
                "ed2_mean_field_logits")
     return out
+
+
+def split_bf16(src: torch.Tensor, is_b: bool, nsplit: int = 3) -> torch.Tensor:
+    """[rows, cols] fp32 -> [rows, terms*cols] bf16 split operand (see ed2_split_bf16)."""
+    lib = _lib.load()
+    rows, cols = src.shape
+    terms = 6 if nsplit == 3 else 3
+    assert (terms * cols) % 8 == 0, "split operand pitch must be a multiple of 8 bf16"
+    out = torch.empty(rows, terms * cols, dtype=torch.bfloat16, device=src.device)
+    _lib.check(lib.ed2_split_bf16(src.data_ptr(), _lib.dt_of(src), _lib.ld(src), out.data_ptr(), terms * cols, rows, cols,
+                                  int(is_b), nsplit, _lib.stream_ptr()), "ed2_split_bf16")
+    return out
+
+
+def rff_fwd_split(x: torch.Tensor, wt_split: torch.Tensor, bias: torch.Tensor, scale: float, num_features: int,
+                  phi_dtype: torch.dtype, want_pre: bool, nsplit: int = 3):
+    """phi = scale * cos(x W + b) with an fp32-grade phase on the bf16 tensor cores: x (fp32 or bf16, [B, d]) is split
+    on the fly, wt_split = split_bf16(W^T, is_b=True) was made once (W is frozen)."""
+    lib = _lib.load()
+    xs = split_bf16(x, False, nsplit)
+    B, Kp = xs.shape
+    D = num_features
+    phi = _lib.empty_padded(B, D, phi_dtype, x.device)
+    pre = torch.empty(B, D, dtype=torch.float32, device=x.device) if want_pre else None
+    _lib.check(lib.ed2_rff_fwd(BF16, xs.data_ptr(), _lib.ld(xs), wt_split.data_ptr(), _lib.ld(wt_split), bias.data_ptr(),
+                               scale, B, Kp, D, phi.data_ptr(), _lib.ld(phi), _lib.dt_of(phi), _lib.ptr(pre),
+                               0 if pre is None else D, _lib.stream_ptr()), "ed2_rff_fwd[split]")
+    return phi, pre

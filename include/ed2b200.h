@@ -105,6 +105,14 @@ int ed2_philox_raw(uint32_t* out, long long n_blocks, uint64_t seed, uint64_t st
 int ed2_cast(const void* src, int src_dtype, int src_ld, void* dst, int dst_dtype, int dst_ld, long long rows,
              long long cols, void* s);
 
+/* Split an fp32 (or bf16) matrix [rows][cols] into bf16 terms laid out along the contraction axis, so that ONE bf16
+ * tensor-core GEMM with K' = 6K (nsplit = 3: 24 mantissa bits) or 3K (nsplit = 2: 16 bits) and fp32 accumulation
+ * evaluates an fp32-grade product:  is_b = 0 -> A' = [h|h|h|m|m|l] ([h|h|m]);  is_b = 1 -> B' = [h|m|l|h|m|h] ([h|m|h]).
+ * dst: bf16 [rows][dst_ld], dst_ld >= terms * cols.  Used for the random-feature phase x W + b, where bf16 operands
+ * would give ~0.1 rad of phase error with the TF defaults (SURVEY.md §7 hard part 6). */
+int ed2_split_bf16(const void* src, int src_dtype, int src_ld, void* dst, int dst_ld, long long rows, int cols, int is_b,
+                   int nsplit, void* s);
+
 /* TrainableNormal sample (edward2/tensorflow/initializers.py:500-511, constraints.py:62-63):
  *   sigma = softplus(rho) + 1e-7;  w = mu + sigma * eps   (mode 0)   or   delta = sigma * eps   (mode 1)
  * over `rows x cols` fp32 parameters with pitch cols; output `w` in w_dtype with pitch w_ld.  If kl_out is
