@@ -484,16 +484,24 @@ class LayerNorm(torch.autograd.Function):
 
 class RandomFourierFeatures(torch.autograd.Function):
     """phi = scale * cos(x W + b) with W, b frozen (random_feature.py:258-266; jax random_feature.py:209-214).
-    w_t: Wᵀ [D, d] and w: [d, D], both in the compute dtype (frozen copies made once by the layer)."""
+    w_t: W^T [D, d] and w: [d, D] in the compute dtype (frozen copies made once by the layer).
+    nsplit in (2, 3): the phase x W is evaluated at fp32 grade on the bf16 tensor cores through split operands
+    (w_t is then split_bf16(W^T, is_b=True) and w a bf16 copy used by the backward product)."""
 
     @staticmethod
-    def forward(ctx, x, w_t, w, bias, scale, dtype, phi_dtype):
-        xc = as_compute(x, dtype)
+    def forward(ctx, x, w_t, w, bias, scale, dtype, phi_dtype, nsplit=0):
         need = ctx.needs_input_grad[0]
-        phi, pre = ops.rff_fwd(xc, w_t, bias, scale, phi_dtype, want_pre=need)
+        if nsplit:
+            xc = x if (x.stride(1) == 1 and x.dtype in (torch.float32, torch.bfloat16)) else x.contiguous().float()
+            phi, pre = ops.rff_fwd_split(xc, w_t, bias, scale, w.shape[1], phi_dtype, need, nsplit)
+            bwd_dtype = torch.bfloat16
+        else:
+            xc = as_compute(x, dtype)
+            phi, pre = ops.rff_fwd(xc, w_t, bias, scale, phi_dtype, want_pre=need)
+            bwd_dtype = dtype
         if need:
             ctx.save_for_backward(pre, bias, w)
-            ctx.meta = (scale, x.dtype, dtype)
+            ctx.meta = (scale, x.dtype, bwd_dtype)
         return phi
 
     @staticmethod
@@ -504,7 +512,7 @@ class RandomFourierFeatures(torch.autograd.Function):
         dx = ops.rff_bwd(dphic, pre, bias, w, scale, dtype)
         if dx.dtype != x_dtype:
             dx = dx.to(x_dtype)
-        return dx, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None
 
 
 class _UnitGrad:

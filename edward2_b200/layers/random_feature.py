@@ -164,12 +164,20 @@ class _LayerNormalization(Layer):
 
 class _RandomFeature(Layer):
     """Dense(num_inducing, activation=cos, trainable=False) of random_feature.py:228-235, fused with the
-    sqrt(2/D) feature scale (:260-266) in the GEMM epilogue."""
+    sqrt(2/D) feature scale (:260-266) in the GEMM epilogue.
 
-    def __init__(self, units, kernel_initializer, bias_initializer, scale, **kwargs):
+    phase_precision: 'float32' evaluates x W + b at fp32 grade on the bf16 tensor cores (split operands, K' = 6K);
+    'bfloat16x2' keeps 16 mantissa bits (K' = 3K); 'native' uses the compute dtype as is.  With the TF defaults
+    (LayerNorm inputs, orthogonal features of stddev 1) the phase is O(sqrt(d)) radians, so bf16 operands alone would
+    put ~0.1 rad of error into the cosine (SURVEY.md §7 hard part 6)."""
+
+    def __init__(self, units, kernel_initializer, bias_initializer, scale, phase_precision="float32", **kwargs):
         super().__init__(**kwargs)
         self.units, self.scale = units, scale
         self.kernel_initializer, self.bias_initializer = kernel_initializer, bias_initializer
+        if phase_precision not in ("float32", "bfloat16x2", "native"):
+            raise ValueError(f"phase_precision must be 'float32', 'bfloat16x2' or 'native', got {phase_precision!r}")
+        self.phase_precision = phase_precision
 
     def build(self, input_shape):
         dev = self._device
@@ -181,13 +189,25 @@ class _RandomFeature(Layer):
 
     def _refresh(self):
         k = self.kernel
-        self._w = k if self.compute_dtype == torch.float32 else ops.cast(k, self.compute_dtype)
+        d = k.shape[0]
+        nsplit = {"float32": 3, "bfloat16x2": 2, "native": 0}[self.phase_precision]
+        # the exact-fp32 FFMA path is kept for small fp32 problems; split operands need a pitch multiple of 8
+        if nsplit and ((6 if nsplit == 3 else 3) * d) % 8 != 0:
+            nsplit = 0
+        if nsplit and self.compute_dtype == torch.float32 and d * self.units < (1 << 18):
+            nsplit = 0
+        self._nsplit = nsplit
         kt = k.t().contiguous()
-        self._wt = kt if self.compute_dtype == torch.float32 else ops.cast(kt, self.compute_dtype)
+        if nsplit:
+            self._wt = ops.split_bf16(kt, True, nsplit)
+            self._w = ops.cast(k, torch.bfloat16)
+        else:
+            self._w = k if self.compute_dtype == torch.float32 else ops.cast(k, self.compute_dtype)
+            self._wt = kt if self.compute_dtype == torch.float32 else ops.cast(kt, self.compute_dtype)
 
     def call(self, inputs):
         return F.RandomFourierFeatures.apply(inputs, self._wt, self._w, self.bias, self.scale, self.compute_dtype,
-                                             self.compute_dtype)
+                                             self.compute_dtype, self._nsplit)
 
 
 class RandomFeatureGaussianProcess(Layer):
@@ -202,7 +222,8 @@ class RandomFeatureGaussianProcess(Layer):
                  use_custom_random_features=True, custom_random_features_initializer=None,
                  custom_random_features_activation=None, l2_regularization=0.0, gp_cov_likelihood="gaussian",
                  return_gp_cov=True, return_random_features=False, dtype=None,
-                 name="random_feature_gaussian_process", data_parallel=False, **gp_output_kwargs):
+                 name="random_feature_gaussian_process", data_parallel=False, phase_precision="float32",
+                 **gp_output_kwargs):
         super().__init__(dtype=dtype, name=name)
         self.units, self.num_inducing = units, num_inducing
         self.normalize_input = normalize_input
@@ -233,14 +254,18 @@ class RandomFeatureGaussianProcess(Layer):
         self.gp_cov_ridge_penalty = gp_cov_ridge_penalty
         self.gp_cov_likelihood = gp_cov_likelihood
         self.data_parallel = data_parallel
+        self.phase_precision = phase_precision
 
     def build(self, input_shape):
         dt = self.compute_dtype
+        # the normalised input stays fp32 when the phase is evaluated at fp32 grade (it is split on the fly)
+        norm_dt = torch.float32 if self.phase_precision != "native" else dt
         if self.normalize_input:
-            self._input_norm_layer = _LayerNormalization(dtype=dt, name="gp_input_normalization")
+            self._input_norm_layer = _LayerNormalization(dtype=norm_dt, name="gp_input_normalization")
         scale = self.gp_feature_scale if self.scale_random_features else 1.0
         self._random_feature = _RandomFeature(self.num_inducing, self.custom_random_features_initializer,
-                                              self.random_features_bias_initializer, scale, dtype=dt,
+                                              self.random_features_bias_initializer, scale,
+                                              phase_precision=self.phase_precision, dtype=dt,
                                               name="gp_random_feature")
         if self.return_gp_cov:
             self._gp_cov_layer = LaplaceRandomFeatureCovariance(

@@ -34,11 +34,36 @@ class RandomFourierFeatures(m.Module):
     seed: int = 0
     dtype: Optional[Any] = None
     collection_name: str = "random_features"
+    phase_precision: str = "float32"   # 'float32' | 'bfloat16x2' | 'native' (see layers.random_feature._RandomFeature)
 
     def setup(self):
         if self.activation is not None and getattr(self.activation, "__name__", "") != "cos":
             raise NotImplementedError("only the cosine random-feature activation is fused")
+        if self.phase_precision not in ("float32", "bfloat16x2", "native"):
+            raise ValueError(f"phase_precision must be 'float32', 'bfloat16x2' or 'native', got {self.phase_precision!r}")
         self._feature_scale = math.sqrt(2.0 / self.features) if self.feature_scale is None else float(self.feature_scale)
+        self._operand_cache = {}
+
+    def _operands(self, k, dtype):
+        """Frozen-kernel operand copies (transposed / split / cast), cached per kernel tensor."""
+        key = (k.data_ptr(), k._version, dtype)
+        hit = self._operand_cache.get(key)
+        if hit is not None:
+            return hit
+        d = k.shape[0]
+        nsplit = {"float32": 3, "bfloat16x2": 2, "native": 0}[self.phase_precision]
+        if nsplit and ((6 if nsplit == 3 else 3) * d) % 8 != 0:
+            nsplit = 0
+        if nsplit and dtype == torch.float32 and d * self.features < (1 << 18):
+            nsplit = 0   # small fp32 problems stay on the exact-fp32 FFMA path
+        kt = k.t().contiguous()
+        if nsplit:
+            wt, w = ops.split_bf16(kt, True, nsplit), ops.cast(k, torch.bfloat16)
+        else:
+            w = k if dtype == torch.float32 else ops.cast(k, dtype)
+            wt = kt if dtype == torch.float32 else ops.cast(kt, dtype)
+        self._operand_cache = {key: (wt, w, nsplit)}
+        return wt, w, nsplit
 
     def __call__(self, inputs):
         dtype = _dt(self.dtype, inputs)
@@ -46,12 +71,9 @@ class RandomFourierFeatures(m.Module):
         rng = m.PRNG(self.seed)  # fixed seed overrides external rngs (random_feature.py:169,175)
         kernel = self.variable(self.collection_name, "kernel", lambda: self.kernel_init(rng.fold("kernel"), (d, self.features)))
         bias = self.variable(self.collection_name, "bias", lambda: self.bias_init(rng.fold("bias"), (self.features,)))
-        k = kernel.value
-        w = k if dtype == torch.float32 else ops.cast(k, dtype)
-        kt = k.t().contiguous()
-        wt = kt if dtype == torch.float32 else ops.cast(kt, dtype)
+        wt, w, nsplit = self._operands(kernel.value, dtype)
         x2 = inputs.reshape(-1, d)
-        phi = F.RandomFourierFeatures.apply(x2, wt, w, bias.value, self._feature_scale, dtype, dtype)
+        phi = F.RandomFourierFeatures.apply(x2, wt, w, bias.value, self._feature_scale, dtype, dtype, nsplit)
         return phi.reshape(*inputs.shape[:-1], self.features)
 
 
@@ -124,11 +146,13 @@ class _LayerNorm(m.Module):
     """flax nn.LayerNorm(use_bias=False, use_scale=False): epsilon 1e-6, no parameters."""
     epsilon: float = 1e-6
     dtype: Optional[Any] = None
+    keep_fp32: bool = False
 
     def __call__(self, inputs):
         dtype = _dt(self.dtype, inputs)
         x2 = inputs.reshape(-1, inputs.shape[-1])
-        return F.LayerNorm.apply(x2, None, None, float(self.epsilon), dtype).reshape(inputs.shape)
+        out_dtype = torch.float32 if self.keep_fp32 else dtype
+        return F.LayerNorm.apply(x2, None, None, float(self.epsilon), out_dtype).reshape(inputs.shape)
 
 
 class RandomFeatureGaussianProcess(m.Module):
@@ -141,9 +165,10 @@ class RandomFeatureGaussianProcess(m.Module):
     covmat_kwargs: Mapping[str, Any] = None
 
     def setup(self):
-        if self.normalize_input:
-            self.norm_layer = _LayerNorm(**(self.norm_kwargs or {}))
         self.hidden_layer = RandomFourierFeatures(features=self.hidden_features, **(self.hidden_kwargs or {}))
+        if self.normalize_input:
+            self.norm_layer = _LayerNorm(keep_fp32=self.hidden_layer.phase_precision != "native",
+                                         **(self.norm_kwargs or {}))
         self.output_layer = Dense(features=self.features, **(self.output_kwargs or {}))
         self.covmat_layer = LaplaceRandomFeatureCovariance(hidden_features=self.hidden_features,
                                                            **(self.covmat_kwargs or {}))

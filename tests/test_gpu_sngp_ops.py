@@ -158,3 +158,29 @@ def test_mean_field_logits_known_answers(cuda):
     np.testing.assert_allclose(to_np(d), logits / 2.0, atol=1e-4)
     with pytest.raises(ValueError):
         ed.layers.utils.mean_field_logits(lt, covmat, likelihood="gaussian")
+
+
+@pytest.mark.parametrize("nsplit,tol", [(3, 1e-5), (2, 2e-3)])
+def test_rff_split_bf16_phase_precision(cuda, nsplit, tol):
+    """fp32-grade random-feature phase on the bf16 tensor cores (split operands, K' = 6K / 3K), at the TF defaults where
+    the phase is ~sqrt(d) radians: nsplit=3 meets the fp32 tolerance, plain bf16 operands are off by >1e-2."""
+    from edward2_b200 import ops
+
+    rng = np.random.default_rng(9)
+    B, d, D = 264, 1024, 520
+    x = np.float32(og.layer_norm(rng.standard_normal((B, d)))).astype(np.float64)        # LayerNorm'd inputs
+    w = np.float32(rng.standard_normal((d, D))).astype(np.float64)                        # stddev-1 features
+    b = np.float32(rng.uniform(0, 2 * np.pi, D)).astype(np.float64)
+    scale = float(np.sqrt(2.0 / D))
+    xt, wt, bt = dev(x, torch.float32, cuda), dev(w, torch.float32, cuda), dev(b, torch.float32, cuda)
+    phi_ref, pre_ref = og.rff(x, w, b, scale)
+    w_split = ops.split_bf16(wt.t().contiguous(), True, nsplit)
+    phi, pre = ops.rff_fwd_split(xt, w_split, bt, scale, D, torch.float32, True, nsplit)
+    torch.cuda.synchronize()
+    assert rel_err(to_np(phi), phi_ref) < tol
+    assert np.abs(to_np(pre) + b - pre_ref).max() < (2e-4 if nsplit == 3 else 2e-2)
+    # plain bf16 operands: visibly wrong phase at these scales (why the split path is the default)
+    phi_bf16, _ = ops.rff_fwd(xt.to(torch.bfloat16), ops.cast(wt.t().contiguous(), torch.bfloat16), bt, scale,
+                              torch.float32, False)
+    torch.cuda.synchronize()
+    assert rel_err(to_np(phi_bf16), phi_ref) > 1e-2
