@@ -501,6 +501,175 @@ __global__ void scale_rows_kernel(const void* x, int dt, long long x_ld, long lo
   }
 }
 
+
+// ---- lean rank-1 kernels (bf16, Philox noise, 8-aligned): one thread owns 8 consecutive columns and walks down a
+// chunk of rows of ONE member, so the per-(member, column) quantities (mu, sigma, sigmoid(rho)) are computed once,
+// the noise is two Philox blocks per row, every access is a 16-byte vector, and the column reductions of the backward
+// passes are per-thread accumulators flushed with one atomic per column per block (no shared memory).
+constexpr int kLeanRows = 64;
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 v = __bfloat1622float2(h[t]);
+    f[2 * t] = v.x;
+    f[2 * t + 1] = v.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 q;
+  q.x = pack2_bf16(f[0], f[1]); q.y = pack2_bf16(f[2], f[3]); q.z = pack2_bf16(f[4], f[5]); q.w = pack2_bf16(f[6], f[7]);
+  return q;
+}
+__device__ __forceinline__ void normal8_fast(uint64_t key, uint64_t stream, long long idx, float (&e)[8]) {
+  float t[4];
+  philox_normal4<true>(key, stream, static_cast<uint64_t>(idx >> 2), t);
+  e[0] = t[0]; e[1] = t[1]; e[2] = t[2]; e[3] = t[3];
+  philox_normal4<true>(key, stream, static_cast<uint64_t>(idx >> 2) + 1, t);
+  e[4] = t[0]; e[5] = t[1]; e[6] = t[2]; e[7] = t[3];
+}
+__device__ __forceinline__ uint64_t lean_key(uint64_t seed, const uint64_t* step) {
+  return step != nullptr ? seed + __ldg(reinterpret_cast<const unsigned long long*>(step)) * 0x9E3779B97F4A7C15ull : seed;
+}
+struct LeanCols {
+  float m[8], sg[8], sgm[8];
+};
+__device__ __forceinline__ void load_cols(const float* mu, const float* rho, int e, int c, int cols, LeanCols& k) {
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(mu + (long long)e * cols + c));
+  const float4 a1 = __ldg(reinterpret_cast<const float4*>(mu + (long long)e * cols + c) + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(rho + (long long)e * cols + c));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(rho + (long long)e * cols + c) + 1);
+  const float mm[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float rr[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    k.m[j] = mm[j];
+    k.sg[j] = softplus_f(rr[j]) + kSoftplusEps;
+    k.sgm[j] = sigmoid_f(rr[j]);
+  }
+}
+
+// xo = x ∘ clip(mu[e] + sigma[e] eps, -10, 10)   (x == nullptr: write the factor itself)
+template <bool kHasX>
+__global__ void __launch_bounds__(kBlock) rank1_scale_lean_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int rpm,
+                                                                  int cols, const float* __restrict__ fw_mu,
+                                                                  const float* __restrict__ fw_rho, uint64_t seed,
+                                                                  uint64_t stream, const uint64_t* step,
+                                                                  __nv_bfloat16* __restrict__ out, int out_ld) {
+  const int c = (blockIdx.x * kBlock + threadIdx.x) * 8;
+  if (c >= cols) return;
+  const int chunks = (rpm + kLeanRows - 1) / kLeanRows;
+  const int e = blockIdx.y / chunks;
+  const long long row0 = (long long)e * rpm + (long long)(blockIdx.y - e * chunks) * kLeanRows;
+  const long long row1 = min((long long)(e + 1) * rpm, row0 + kLeanRows);
+  const uint64_t key = lean_key(seed, step);
+  LeanCols k;
+  load_cols(fw_mu, fw_rho, e, c, cols, k);
+  for (long long r = row0; r < row1; ++r) {
+    float en[8], f[8];
+    normal8_fast(key, stream, r * cols + c, en);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(fmaf(k.sg[j], en[j], k.m[j]), -kClip), kClip);
+    if (kHasX) {
+      float xv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * x_ld + c)), xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= xv[j];
+    }
+    *reinterpret_cast<uint4*>(out + r * out_ld + c) = pack8(f);
+  }
+}
+
+// rank-1 output side: gp = gy ∘ relu'(y); dz = gp ∘ s; ds = gp ∘ z ∘ 1[unclipped]; dmu_s, drho_s, dbias column sums
+__global__ void __launch_bounds__(kBlock) rank1_bwd_out_lean_kernel(BwdOutArgs a) {
+  const int c = (blockIdx.x * kBlock + threadIdx.x) * 8;
+  if (c >= a.cols) return;
+  const int chunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
+  const int e = blockIdx.y / chunks;
+  const long long row0 = (long long)e * a.rows_per_member + (long long)(blockIdx.y - e * chunks) * kLeanRows;
+  const long long row1 = min((long long)(e + 1) * a.rows_per_member, row0 + kLeanRows);
+  const uint64_t key = lean_key(a.eps_s.seed, a.eps_s.step);
+  LeanCols k;
+  load_cols(a.mu_s, a.rho_s, e, c, a.cols, k);
+  const __nv_bfloat16* gy = reinterpret_cast<const __nv_bfloat16*>(a.gy);
+  const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(a.y);
+  const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(a.z);
+  const __nv_bfloat16* sb = reinterpret_cast<const __nv_bfloat16*>(a.s_buf);
+  __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(a.dz);
+  float acc_mu[8] = {}, acc_rho[8] = {}, acc_b[8] = {};
+  for (long long r = row0; r < row1; ++r) {
+    float g[8], yv[8], zv[8], sv[8], en[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gy + r * a.gy_ld + c)), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * a.z_ld + c)), zv);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(sb + r * a.s_ld + c)), sv);
+    if (a.act == kActRelu) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(y + r * a.y_ld + c)), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+    }
+    normal8_fast(key, a.eps_s.stream, r * a.cols + c, en);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float raw = fmaf(k.sg[j], en[j], k.m[j]);
+      const float ds = (raw < -kClip || raw > kClip) ? 0.f : g[j] * zv[j];
+      acc_b[j] += g[j];
+      acc_mu[j] += ds;
+      acc_rho[j] += ds * en[j] * k.sgm[j];
+      o[j] = g[j] * sv[j];
+    }
+    *reinterpret_cast<uint4*>(dz + r * a.dz_ld + c) = pack8(o);
+  }
+  const long long base = (long long)e * a.cols + c;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(a.d_fast_mu + base + j, acc_mu[j]);
+    if (a.d_fast_rho != nullptr) atomicAdd(a.d_fast_rho + base + j, acc_rho[j]);
+    if (a.dbias != nullptr) atomicAdd(a.dbias + base + j, acc_b[j]);
+  }
+}
+
+// rank-1 input side: dx = dxr ∘ r; dr = dxr ∘ x ∘ 1[unclipped]; dmu_r, drho_r column sums
+__global__ void __launch_bounds__(kBlock) rank1_bwd_in_lean_kernel(BwdInArgs a) {
+  const int c = (blockIdx.x * kBlock + threadIdx.x) * 8;
+  if (c >= a.cols) return;
+  const int chunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
+  const int e = blockIdx.y / chunks;
+  const long long row0 = (long long)e * a.rows_per_member + (long long)(blockIdx.y - e * chunks) * kLeanRows;
+  const long long row1 = min((long long)(e + 1) * a.rows_per_member, row0 + kLeanRows);
+  const uint64_t key = lean_key(a.eps.seed, a.eps.step);
+  LeanCols k;
+  load_cols(a.fw_mu, a.fw_rho, e, c, a.cols, k);
+  const __nv_bfloat16* dxf = reinterpret_cast<const __nv_bfloat16*>(a.dxf);
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
+  __nv_bfloat16* dx = reinterpret_cast<__nv_bfloat16*>(a.dx);
+  float acc_mu[8] = {}, acc_rho[8] = {};
+  for (long long r = row0; r < row1; ++r) {
+    float d[8], xv[8], en[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dxf + r * a.dxf_ld + c)), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * a.x_ld + c)), xv);
+    normal8_fast(key, a.eps.stream, r * a.cols + c, en);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float raw = fmaf(k.sg[j], en[j], k.m[j]);
+      const bool clipped = raw < -kClip || raw > kClip;
+      const float df = clipped ? 0.f : d[j] * xv[j];
+      acc_mu[j] += df;
+      acc_rho[j] += df * en[j] * k.sgm[j];
+      o[j] = d[j] * fminf(fmaxf(raw, -kClip), kClip);
+    }
+    if (dx != nullptr) *reinterpret_cast<uint4*>(dx + r * a.dx_ld + c) = pack8(o);
+  }
+  const long long base = (long long)e * a.cols + c;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(a.d_fast_mu + base + j, acc_mu[j]);
+    if (a.d_fast_rho != nullptr) atomicAdd(a.d_fast_rho + base + j, acc_rho[j]);
+  }
+}
+
+__host__ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // Column-reduction tiles: a block owns 128 columns x up to kRowsPerBlock rows that all belong to one member.
 constexpr int kRowsPerBlock = 64;
 
@@ -886,6 +1055,22 @@ int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols
                  long long f_ld, cudaStream_t s) {
   if (rows <= 0 || cols <= 0) return ED2_OK;
   if (rpm <= 0) rpm = static_cast<int>(rows);
+  if (mode == 1 && dt == kBF16 && fw_rho != nullptr && nz.injected == nullptr && cols % 8 == 0 && rows % rpm == 0 &&
+      (x == nullptr || (x_ld % 8 == 0 && al16(x))) && al16(fw_mu) && al16(fw_rho) && (cols % 4 == 0) &&
+      ((x != nullptr && f_out == nullptr && xo_ld % 8 == 0 && al16(xo)) ||
+       (x == nullptr && f_out != nullptr && f_ld % 8 == 0 && al16(f_out)))) {
+    const int chunks = (rpm + kLeanRows - 1) / kLeanRows;
+    dim3 grid((cols / 8 + kBlock - 1) / kBlock, static_cast<unsigned>((rows / rpm) * chunks));
+    if (x != nullptr)
+      rank1_scale_lean_kernel<true><<<grid, kBlock, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), (int)x_ld, rpm, cols,
+                                                            fw_mu, fw_rho, nz.seed, nz.stream, nz.step,
+                                                            reinterpret_cast<__nv_bfloat16*>(xo), (int)xo_ld);
+    else
+      rank1_scale_lean_kernel<false><<<grid, kBlock, 0, s>>>(nullptr, 0, rpm, cols, fw_mu, fw_rho, nz.seed, nz.stream, nz.step,
+                                                             reinterpret_cast<__nv_bfloat16*>(f_out), (int)f_ld);
+    count_launch();
+    return check_launch("scale_rows(lean rank-1)");
+  }
   const int g = grid_for(rows * ((cols + 3) / 4));
   if (mode == 0) scale_rows_kernel<0><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld);
   else if (mode == 1) scale_rows_kernel<1><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld);
@@ -903,6 +1088,15 @@ int k_bwd_out(const BwdOutArgs& a_in, cudaStream_t s) {
   if (a.d_fast_mu) cudaMemsetAsync(a.d_fast_mu, 0, bytes, s);
   if (a.d_fast_rho) cudaMemsetAsync(a.d_fast_rho, 0, bytes, s);
   if (a.dbias) cudaMemsetAsync(a.dbias, 0, bytes, s);
+  if (a.fast == 2 && a.dt == kBF16 && a.rho_s != nullptr && a.eps_s.injected == nullptr && a.cols % 8 == 0 &&
+      a.gy_ld % 8 == 0 && a.y_ld % 8 == 0 && a.z_ld % 8 == 0 && a.s_ld % 8 == 0 && a.dz_ld % 8 == 0 && al16(a.gy) &&
+      al16(a.y) && al16(a.z) && al16(a.s_buf) && al16(a.dz) && al16(a.mu_s) && al16(a.rho_s) && a.d_fast_mu != nullptr) {
+    const int lchunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
+    dim3 lgrid((a.cols / 8 + kBlock - 1) / kBlock, members * lchunks);
+    rank1_bwd_out_lean_kernel<<<lgrid, kBlock, 0, s>>>(a);
+    count_launch();
+    return check_launch("bwd_out(lean rank-1)");
+  }
   const int chunks = (a.rows_per_member + kRowsPerBlock - 1) / kRowsPerBlock;
   dim3 grid((a.cols + 127) / 128, members * chunks);
   switch (a.fast) {
@@ -923,6 +1117,15 @@ int k_bwd_in(const BwdInArgs& a_in, cudaStream_t s) {
   const size_t bytes = sizeof(float) * (size_t)members * a.cols;
   if (a.d_fast_mu) cudaMemsetAsync(a.d_fast_mu, 0, bytes, s);
   if (a.d_fast_rho) cudaMemsetAsync(a.d_fast_rho, 0, bytes, s);
+  if (a.fast == 2 && a.dt == kBF16 && a.fw_rho != nullptr && a.eps.injected == nullptr && a.cols % 8 == 0 &&
+      a.dxf_ld % 8 == 0 && a.x_ld % 8 == 0 && (a.dx == nullptr || (a.dx_ld % 8 == 0 && al16(a.dx))) && al16(a.dxf) &&
+      al16(a.x) && al16(a.fw_mu) && al16(a.fw_rho) && a.d_fast_mu != nullptr) {
+    const int lchunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
+    dim3 lgrid((a.cols / 8 + kBlock - 1) / kBlock, members * lchunks);
+    rank1_bwd_in_lean_kernel<<<lgrid, kBlock, 0, s>>>(a);
+    count_launch();
+    return check_launch("bwd_in(lean rank-1)");
+  }
   const int chunks = (a.rows_per_member + kRowsPerBlock - 1) / kRowsPerBlock;
   dim3 grid((a.cols + 127) / 128, members * chunks);
   bwd_in_kernel<<<grid, kBlock, 0, s>>>(a);

@@ -404,7 +404,7 @@ class NormalKL(torch.autograd.Function):
         kl = ops.normal_kl(mu, rho, prior_mean, prior_std, scale)
         ctx.save_for_backward(mu, rho)
         ctx.meta = (prior_mean, prior_std, scale)
-        return kl.to(torch.float32)
+        return kl  # fp64 scalar, like the fused KL of the sampling pass
 
     @staticmethod
     def backward(ctx, g):

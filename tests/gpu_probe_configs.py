@@ -116,8 +116,8 @@ def cfg4():
     dev = "cuda"
     B = 2048
     mk = lambda u, act: ed.layers.DenseRank1(u, activation=act, ensemble_size=4, dtype="bfloat16",  # noqa: E731
-                                             alpha_regularizer=ed.regularizers.NormalKLDivergence(mean=1.0, stddev=0.1),
-                                             gamma_regularizer=ed.regularizers.NormalKLDivergence(mean=1.0, stddev=0.1))
+                                             alpha_regularizer=ed.regularizers.NormalKLDivergence(mean=1.0, stddev=0.1, scale_factor=1 / 50000),
+                                             gamma_regularizer=ed.regularizers.NormalKLDivergence(mean=1.0, stddev=0.1, scale_factor=1 / 50000))
     layers = [mk(8192, "relu"), mk(8192, "relu"), mk(1000, None)]
     x = torch.randn(B, 2048, device=dev).to(torch.bfloat16)
     y = torch.randint(0, 1000, (B,), device=dev)
@@ -128,10 +128,7 @@ def cfg4():
         h = x
         for l in layers:
             h = l(h)
-        loss = F.SoftmaxCrossEntropy.apply(h, y, B)
-        for l in layers:
-            for k in l.losses:
-                loss = loss + k / 50000.0
+        loss = F.SoftmaxCrossEntropy.apply(h, y, B, *[k for l in layers for k in l.losses])
         if params is None:
             params = [p for l in layers for p in l.parameters()]
         for p in params:
@@ -147,12 +144,12 @@ def cfg4():
     print(f"cfg4 rank-1 MLP per-GPU B=2048 bf16: {t:.3f} ms/step -> {B/t*1e3/1e6:.2f} M samples/s/GPU, {fl/t/1e9:.0f} TFLOP/s")
 
 
-def cfg5():
+def cfg5(phase_precision="float32"):
     """RFGP D=8192 on 4096-dim inputs, 8192 rows per GPU: RFF + precision update (train) and variance (eval)."""
     dev = "cuda"
     B, d, D = 8192, 4096, 8192
     gp = ed.layers.RandomFeatureGaussianProcess(10, num_inducing=D, gp_cov_momentum=-1, gp_cov_ridge_penalty=1e-3,
-                                                dtype="bfloat16",
+                                                dtype="bfloat16", phase_precision=phase_precision,
                                                 custom_random_features_initializer=ed.initializers.RandomNormal(stddev=1.0, seed=0))
     x = torch.randn(B, d, device=dev).to(torch.bfloat16)
     with torch.no_grad():
@@ -171,7 +168,7 @@ def cfg5():
 
     t = timeit(train, 3, 10)
     fl = 2 * B * d * D + 2 * B * D * D
-    print(f"cfg5 RFGP per-GPU B=8192 D=8192: train {t:.3f} ms -> {fl/t/1e9:.0f} TFLOP/s (RFF + full phi^T phi)")
+    print(f"cfg5 RFGP per-GPU B=8192 D=8192 phase={phase_precision}: train {t:.3f} ms -> {fl/t/1e9:.0f} TFLOP/s (RFF + full phi^T phi)")
     with torch.no_grad():
         cov.covariance_matrix.copy_(torch.eye(D, device=dev) * 1e-3)
         cov._needs_inverse = False
@@ -192,7 +189,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]
     for w in which:
         try:
-            {"cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}[w]()
+            {"cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "cfg5n": lambda: cfg5("native")}[w]()
         except Exception as ex:  # noqa: BLE001
             print(f"{w}: FAILED {type(ex).__name__}: {str(ex)[:300]}")
         torch.cuda.empty_cache()
