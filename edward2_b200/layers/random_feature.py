@@ -166,17 +166,20 @@ class _RandomFeature(Layer):
     """Dense(num_inducing, activation=cos, trainable=False) of random_feature.py:228-235, fused with the
     sqrt(2/D) feature scale (:260-266) in the GEMM epilogue.
 
-    phase_precision: 'float32' evaluates x W + b at fp32 grade on the bf16 tensor cores (split operands, K' = 6K);
-    'bfloat16x2' keeps 16 mantissa bits (K' = 3K); 'native' uses the compute dtype as is.  With the TF defaults
-    (LayerNorm inputs, orthogonal features of stddev 1) the phase is O(sqrt(d)) radians, so bf16 operands alone would
-    put ~0.1 rad of error into the cosine (SURVEY.md §7 hard part 6)."""
+    phase_precision: 'extended' (default) feeds the bf16 tensor cores with split operands x = h + m, W = h + m (16
+    mantissa bits, one GEMM with K' = 3K); 'extended3' adds a third term (24 bits, K' = 6K); 'native' uses the compute
+    dtype as is.  With the TF defaults (LayerNorm inputs, orthogonal features of stddev 1) the phase is O(sqrt(d))
+    radians, so bf16 operands alone put ~0.1 rad of error into the cosine (SURVEY.md §7 hard part 6).  Measured on
+    B200 at d = 1024: native 1.4e-1 of max|phi|, extended 1.9e-3, extended3 1.9e-3 — beyond 16 operand bits the error is
+    set by the tensor core's fp32 accumulation (it truncates; an FFMA reference is at ~3e-5), so 'extended' is the
+    default and fp32-exact features need dtype='float32' (FFMA path)."""
 
-    def __init__(self, units, kernel_initializer, bias_initializer, scale, phase_precision="float32", **kwargs):
+    def __init__(self, units, kernel_initializer, bias_initializer, scale, phase_precision="extended", **kwargs):
         super().__init__(**kwargs)
         self.units, self.scale = units, scale
         self.kernel_initializer, self.bias_initializer = kernel_initializer, bias_initializer
-        if phase_precision not in ("float32", "bfloat16x2", "native"):
-            raise ValueError(f"phase_precision must be 'float32', 'bfloat16x2' or 'native', got {phase_precision!r}")
+        if phase_precision not in ("extended", "extended3", "native"):
+            raise ValueError(f"phase_precision must be 'extended', 'extended3' or 'native', got {phase_precision!r}")
         self.phase_precision = phase_precision
 
     def build(self, input_shape):
@@ -190,7 +193,7 @@ class _RandomFeature(Layer):
     def _refresh(self):
         k = self.kernel
         d = k.shape[0]
-        nsplit = {"float32": 3, "bfloat16x2": 2, "native": 0}[self.phase_precision]
+        nsplit = {"extended": 2, "extended3": 3, "native": 0}[self.phase_precision]
         # the exact-fp32 FFMA path is kept for small fp32 problems; split operands need a pitch multiple of 8
         if nsplit and ((6 if nsplit == 3 else 3) * d) % 8 != 0:
             nsplit = 0
@@ -222,7 +225,7 @@ class RandomFeatureGaussianProcess(Layer):
                  use_custom_random_features=True, custom_random_features_initializer=None,
                  custom_random_features_activation=None, l2_regularization=0.0, gp_cov_likelihood="gaussian",
                  return_gp_cov=True, return_random_features=False, dtype=None,
-                 name="random_feature_gaussian_process", data_parallel=False, phase_precision="float32",
+                 name="random_feature_gaussian_process", data_parallel=False, phase_precision="extended",
                  **gp_output_kwargs):
         super().__init__(dtype=dtype, name=name)
         self.units, self.num_inducing = units, num_inducing

@@ -34,13 +34,13 @@ class RandomFourierFeatures(m.Module):
     seed: int = 0
     dtype: Optional[Any] = None
     collection_name: str = "random_features"
-    phase_precision: str = "float32"   # 'float32' | 'bfloat16x2' | 'native' (see layers.random_feature._RandomFeature)
+    phase_precision: str = "extended"   # 'extended' | 'extended3' | 'native' (see layers.random_feature._RandomFeature)
 
     def setup(self):
         if self.activation is not None and getattr(self.activation, "__name__", "") != "cos":
             raise NotImplementedError("only the cosine random-feature activation is fused")
-        if self.phase_precision not in ("float32", "bfloat16x2", "native"):
-            raise ValueError(f"phase_precision must be 'float32', 'bfloat16x2' or 'native', got {self.phase_precision!r}")
+        if self.phase_precision not in ("extended", "extended3", "native"):
+            raise ValueError(f"phase_precision must be 'extended', 'extended3' or 'native', got {self.phase_precision!r}")
         self._feature_scale = math.sqrt(2.0 / self.features) if self.feature_scale is None else float(self.feature_scale)
         self._operand_cache = {}
 
@@ -51,7 +51,7 @@ class RandomFourierFeatures(m.Module):
         if hit is not None:
             return hit
         d = k.shape[0]
-        nsplit = {"float32": 3, "bfloat16x2": 2, "native": 0}[self.phase_precision]
+        nsplit = {"extended": 2, "extended3": 3, "native": 0}[self.phase_precision]
         if nsplit and ((6 if nsplit == 3 else 3) * d) % 8 != 0:
             nsplit = 0
         if nsplit and dtype == torch.float32 and d * self.features < (1 << 18):

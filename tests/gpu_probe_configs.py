@@ -144,7 +144,7 @@ def cfg4():
     print(f"cfg4 rank-1 MLP per-GPU B=2048 bf16: {t:.3f} ms/step -> {B/t*1e3/1e6:.2f} M samples/s/GPU, {fl/t/1e9:.0f} TFLOP/s")
 
 
-def cfg5(phase_precision="float32"):
+def cfg5(phase_precision="extended"):
     """RFGP D=8192 on 4096-dim inputs, 8192 rows per GPU: RFF + precision update (train) and variance (eval)."""
     dev = "cuda"
     B, d, D = 8192, 4096, 8192
