@@ -192,7 +192,8 @@ def run_ours(args):
             # the backward pass (NCCL runs on its own stream); bf16 buckets halve the NVLink bytes
             from edward2_b200.dist import GradientAllReduce
 
-            reducer = GradientAllReduce(params, compress=None if args.fp32_allreduce else torch.bfloat16)
+            reducer = GradientAllReduce(params, compress=None if args.fp32_allreduce else torch.bfloat16,
+                                        exchange=args.grad_exchange)
         raw_step = make_step(layers, global_batch)
 
         def zero():
@@ -269,6 +270,20 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+
+        if args.trace and not flipout:
+            # kernel timeline of 3 steps (CUPTI through torch.profiler) for offline analysis; never a bench number
+            import contextlib
+
+            from torch.profiler import ProfilerActivity, profile
+
+            with (profile(activities=[ProfilerActivity.CUDA]) if rank == 0 else contextlib.nullcontext()) as prof:
+                for _ in range(3):
+                    run_step()
+                sync_all()
+            if rank == 0:
+                prof.export_chrome_trace(args.trace)
+            sync_all()
 
         e2e_ms = None
         if want_e2e:
@@ -399,8 +414,11 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}",
                    "l2": "inputs > L2: one step touches ~0.6 GB (fp32 mu/rho + grads 400 MB, bf16 W 50 MB, activations)",
                    "cuda_graph": main["graph"], "kl_scale": KL_SCALE,
-                   "grad_allreduce": None if world == 1 else ("fp32" if args.fp32_allreduce else "bf16 buckets") +
-                   ", per-parameter, overlapped with backward",
+                   "grad_allreduce": None if world == 1 else (
+                       "fp32 NCCL all-reduce per parameter, overlapped with backward" if args.fp32_allreduce else
+                       "raw bf16 dW through IPC peer memory: pull reduce-scatter + all-gather fused into the finishing "
+                       "pass (own kernels, no NCCL on the data path)" if args.grad_exchange == "peer" else
+                       "bf16 buckets, NCCL all-reduce per parameter, overlapped with backward"),
                    "gemm_ctas": int(os.environ.get("ED2_GEMM_MAX_CTAS", 148))},
         "e2e": {"value": global_batch / (main["e2e_ms"] * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": (x_host.numel() * 2 + y_host.numel() * 8) * world,
@@ -447,7 +465,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--trace", default="", help="write a chrome trace of 3 steps on rank 0 (diagnostics)")
     ap.add_argument("--fp32-allreduce", action="store_true", help="all-reduce fp32 gradients instead of bf16 buckets")
+    ap.add_argument("--grad-exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the raw bf16 weight gradients are summed over ranks")
     ap.add_argument("--gemm-ctas", type=int, default=0, help="persistent GEMM CTAs when N > 1 (rest: NCCL)")
     ap.add_argument("--no-allreduce", action="store_true", help="diagnostic only: skip the gradient all-reduce")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -114,6 +114,18 @@ class ReparamBwd(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
+
+
+class PeerExchange(C.Structure):
+    _fields_ = [
+        ("world", _i), ("rank", _i), ("n", _ll), ("chunk", _ll), ("small_n", _ll),
+        ("bucket", _vp * MAX_PEERS), ("reduced", _vp * MAX_PEERS), ("small_vec", _vp * MAX_PEERS),
+        ("flags", _vp * MAX_PEERS),
+    ]
+
+
 class FlipoutFwd(C.Structure):
     _fields_ = [
         ("dtype", _i), ("batch", _i), ("in_dim", _i), ("out_dim", _i), ("act", _i),
@@ -163,6 +175,13 @@ SIGNATURES = {
     "ed2_reparam_dense_fwd": (_i, [C.POINTER(ReparamFwd), _vp]),
     "ed2_reparam_dense_bwd": (_i, [C.POINTER(ReparamBwd), _vp]),
     "ed2_normal_grad_finish": (_i, [_vp, _i, _vp, _vp, Noise, _ll, _f, _vp, _f, _f, _vp, _vp, _i, _vp]),
+    "ed2_peer_alloc": (_i, [C.c_size_t, C.POINTER(_vp), _vp]),
+    "ed2_peer_open": (_i, [_vp, C.POINTER(_vp)]),
+    "ed2_peer_close": (_i, [_vp]),
+    "ed2_peer_free": (_i, [_vp]),
+    "ed2_peer_signal": (_i, [C.POINTER(PeerExchange), _vp, _vp]),
+    "ed2_peer_reduce_slice": (_i, [C.POINTER(PeerExchange), _i, _vp]),
+    "ed2_peer_grad_finish": (_i, [C.POINTER(PeerExchange), _vp, _vp, Noise, _f, _vp, _f, _f, _vp, _vp, _vp, _i, _vp]),
     "ed2_flipout_dense_fwd": (_i, [C.POINTER(FlipoutFwd), _vp]),
     "ed2_flipout_dense_bwd": (_i, [C.POINTER(FlipoutBwd), _vp]),
     "ed2_spectral_norm_update": (_i, [_vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),

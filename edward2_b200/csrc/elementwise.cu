@@ -10,6 +10,7 @@
 #include <cstdlib>
 
 #include "gemm_epilogue.h"
+#include "peer.cuh"
 #include "status.h"
 
 namespace ed2 {
@@ -363,6 +364,64 @@ __global__ void __launch_bounds__(kBlock) grad_finish_bf16_kernel(const __nv_bfl
     }
     st4(dmu, kF32, i, valid, om);
     st4(drho, kF32, i, valid, orr);
+  }
+}
+
+// Finishing pass of the peer-memory exchange (peer.cuh): the reduced bf16 gradient is read slice by slice from the
+// memory of the rank that owns (reduced) it — the all-gather half of the all-reduce never exists as a separate pass.
+template <bool kFast>
+__global__ void __launch_bounds__(kBlock, 6) grad_finish_peer_kernel(PeerExchange x, const float* __restrict__ mu,
+                                                                     const float* __restrict__ rho, Noise eps,
+                                                                     float klg_in, const double* kl_upstream, Prior p,
+                                                                     float* dmu, float* drho, float* small_out) {
+  unsigned long long* lw = peer::local_words(x);
+  const unsigned long long epoch = lw[0];
+  if (threadIdx.x < x.world)
+    peer::wait_flag(peer::reduced_flags(x, x.rank) + threadIdx.x, epoch, lw + 2, 0x200 + threadIdx.x);
+  __syncthreads();
+  const float klg = klg_in * (kl_upstream != nullptr ? static_cast<float>(*kl_upstream) : 1.f);
+  const float inv_s2 = 1.f / (p.stddev * p.stddev);
+  const uint64_t key = noise_key(eps);
+  const long long nblk = x.n >> 2;  // n is a multiple of 8; thread = 4 weights = one Philox block = one 8-byte load
+  const unsigned chunk4 = static_cast<unsigned>(x.chunk >> 2);
+  // half or more of the gradient loads cross NVLink (2-3 us): two of them stay in flight per thread ahead of the math
+  const long long stride = (long long)gridDim.x * kBlock;
+  auto load_dw = [&](long long b) -> uint2 {
+    if (b >= nblk) return make_uint2(0u, 0u);
+    const int owner = static_cast<int>(static_cast<unsigned>(b) / chunk4);
+    return peer::ld_sys_v2(reinterpret_cast<const __nv_bfloat16*>(x.reduced[owner]) + (b << 2));
+  };
+  const long long b0 = blockIdx.x * (long long)kBlock + threadIdx.x;
+  uint2 raw = load_dw(b0), raw1 = load_dw(b0 + stride);
+  for (long long b = b0; b < nblk; b += stride) {
+    const uint2 raw2 = load_dw(b + 2 * stride);
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu) + b), r4 = __ldg(reinterpret_cast<const float4*>(rho) + b);
+    float e[4];
+    philox_normal4<kFast>(key, eps.stream, static_cast<uint64_t>(b), e);
+    const float2 ga = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 gb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w}, g[4] = {ga.x, ga.y, gb.x, gb.y};
+    float om[4], orr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ex;
+      const float sigma = kFast ? sigma_from_rho_fast(r[j], ex) : sigma_from_rho(r[j], ex);
+      const float sgm = __fdividef(ex, 1.f + ex);
+      om[j] = g[j] + klg * (m[j] - p.mean) * inv_s2;
+      orr[j] = (g[j] * e[j] + klg * (sigma * inv_s2 - __fdividef(1.f, sigma))) * sgm;
+    }
+    reinterpret_cast<float4*>(dmu)[b] = make_float4(om[0], om[1], om[2], om[3]);
+    reinterpret_cast<float4*>(drho)[b] = make_float4(orr[0], orr[1], orr[2], orr[3]);
+    raw = raw1;
+    raw1 = raw2;
+  }
+  // companion vector (bias gradient): one-shot sum over ranks, same order on every rank
+  if (small_out != nullptr) {
+    for (long long j = blockIdx.x * (long long)kBlock + threadIdx.x; j < x.small_n; j += (long long)gridDim.x * kBlock) {
+      float s = 0.f;
+      for (int q = 0; q < x.world; ++q) s += peer::ld_sys_f32(x.small[q] + j);
+      small_out[j] = s;
+    }
   }
 }
 
@@ -1048,6 +1107,30 @@ int k_normal_grad_finish_any(const void* dw, int dw_dt, const float* mu, const f
   else grad_finish_bf16_kernel<false><<<g, kBlock, 0, s>>>(d, mu, rho, eps, n, klg, kl_upstream, p, dmu, drho);
   count_launch();
   return check_launch("normal_grad_finish(bf16 dW)");
+}
+
+int k_peer_grad_finish(const PeerExchange& x, const float* mu, const float* rho, Noise eps, float klg,
+                       const double* kl_upstream, Prior p, float* dmu, float* drho, float* small_out, bool fast,
+                       cudaStream_t s) {
+  if (x.world < 2 || x.world > kMaxPeers || x.n <= 0 || x.n % 8 != 0 || x.chunk % 8 != 0 || x.n >= (1LL << 33))
+    return set_error(ED2_ERR_BAD_ARG, "peer grad finish: bad exchange (world %d, n %lld, chunk %lld)", x.world, x.n, x.chunk);
+  if (eps.injected != nullptr) return set_error(ED2_ERR_BAD_ARG, "peer grad finish: needs in-kernel (Philox) noise");
+  // 5 resident blocks per SM (40 registers per thread would allow 6): 50 K registers, which leaves room for the last
+  // exchange's light owner pass (side stream, one 128-thread block per SM, <= 12 K registers) beside this kernel
+  const int g = std::min(grid_for(x.n / 4), 148 * 5);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(mu) || !al16(rho) || !al16(dmu) || !al16(drho))
+    return set_error(ED2_ERR_BAD_ARG, "peer grad finish: mu / rho / dmu / drho must be 16-byte aligned");
+  static const bool carve = [] {  // same shared-memory carveout as the GEMM: no SM reconfiguration between them
+    cudaFuncSetAttribute(grad_finish_peer_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(grad_finish_peer_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return true;
+  }();
+  (void)carve;
+  if (fast) grad_finish_peer_kernel<true><<<g, kBlock, 0, s>>>(x, mu, rho, eps, klg, kl_upstream, p, dmu, drho, small_out);
+  else grad_finish_peer_kernel<false><<<g, kBlock, 0, s>>>(x, mu, rho, eps, klg, kl_upstream, p, dmu, drho, small_out);
+  count_launch();
+  return check_launch("peer_grad_finish");
 }
 
 int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols, int rpm, int mode,

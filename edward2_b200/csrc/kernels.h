@@ -116,4 +116,26 @@ int k_softmax_xent(const void* logits, int dt, long long ld, const long long* la
                    const XentExtras& ex, cudaStream_t s);
 int k_scale_inplace(float* x, long long n, float a, cudaStream_t s);
 
+
+// ---- peer-memory gradient exchange of the data-parallel step (peer.cuh explains the layout; peer.cu, elementwise.cu)
+constexpr int kMaxPeers = 8;
+struct PeerExchange {
+  int world, rank;
+  long long n;      // elements of the exchanged bf16 gradient (multiple of 8)
+  long long chunk;  // elements per owner (multiple of 8); owner o reduces [o*chunk, min(n, (o+1)*chunk))
+  long long small_n;  // elements of the fp32 companion vector (0: none)
+  const void* bucket[kMaxPeers];
+  void* reduced[kMaxPeers];
+  const float* small[kMaxPeers];
+  unsigned long long* flags[kMaxPeers];
+};
+// publish this rank's bucket (+ copy `small_src` into the arena): epoch += 1, ready flag on every rank
+int k_peer_signal(const PeerExchange& x, const float* small_src, cudaStream_t s);
+// owner pass: wait for every rank's ready flag, pull + sum the owned slice (rank order), publish the reduced flag
+// light: small footprint (1 block x 128 threads per SM) for running beside the finishing pass instead of a GEMM
+int k_peer_reduce_slice(const PeerExchange& x, int light, cudaStream_t s);
+// finishing pass reading the reduced gradient slice by slice from its owners; small_out = sum over ranks of `small`
+int k_peer_grad_finish(const PeerExchange& x, const float* mu, const float* rho, Noise eps, float kl_grad_scale,
+                       const double* kl_upstream, Prior p, float* dmu, float* drho, float* small_out, bool fast,
+                       cudaStream_t s);
 }  // namespace ed2

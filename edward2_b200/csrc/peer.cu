@@ -1,0 +1,235 @@
+// Peer-memory gradient exchange (data-parallel step): IPC arena management, the "ready" signal and the owner's
+// reduce pass.  Replaces the NCCL all-reduce of the raw bf16 weight gradients: no extra SM-hungry kernels compete
+// with the persistent GEMM, nothing waits for a free SM, and the all-gather half of the exchange is folded into the
+// gradient-finishing pass (elementwise.cu: grad_finish_peer_kernel), which pulls each slice from its owner.
+#include "../../include/ed2b200.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "peer.cuh"
+#include "status.h"
+
+namespace ed2 {
+namespace {
+
+constexpr int kBlock = 256;
+
+__global__ void __launch_bounds__(kBlock) peer_signal_kernel(PeerExchange x, const float* __restrict__ small_src) {
+  // companion vector -> arena (peers read it after they have seen the flag)
+  float* dst = const_cast<float*>(x.small[x.rank]);
+  for (long long i = threadIdx.x; i < x.small_n; i += kBlock) dst[i] = small_src[i];
+  __shared__ unsigned long long epoch_s;
+  if (threadIdx.x == 0) {
+    unsigned long long* w = peer::local_words(x);
+    epoch_s = w[0] + 1;
+    w[0] = epoch_s;
+  }
+  __syncthreads();  // orders every thread's `small` stores before the releasing threads (CTA scope, cumulative)
+  // the bucket (written by the previous kernel) and `small` become visible to whoever acquires the flag
+  if (threadIdx.x < x.world) {
+    __threadfence_system();
+    peer::st_release_sys(peer::ready_flags(x, threadIdx.x) + x.rank, epoch_s);
+  }
+}
+
+__device__ __forceinline__ void acc8(float (&a)[8], const uint4& v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    a[2 * j] += f.x;
+    a[2 * j + 1] += f.y;
+  }
+}
+
+template <int kWorld>  // 0: run-time world size
+__global__ void __launch_bounds__(kBlock) peer_reduce_slice_kernel(PeerExchange x) {
+  constexpr int kW = kWorld > 0 ? kWorld : kMaxPeers;
+  const int world = kWorld > 0 ? kWorld : x.world;
+  unsigned long long* lw = peer::local_words(x);
+  const unsigned long long epoch = lw[0];
+  if (threadIdx.x < world) peer::wait_flag(peer::ready_flags(x, x.rank) + threadIdx.x, epoch, lw + 2, 0x100 + threadIdx.x);
+  __syncthreads();
+  const long long lo = x.rank * x.chunk, hi = min(x.n, lo + x.chunk);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(x.reduced[x.rank]);
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  // two 16-byte vectors per trip: 2 * world NVLink loads in flight per thread (the kernel is latency-bound)
+  for (long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < hi; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < hi;
+    uint4 v[kW], w[kW];
+#pragma unroll
+    for (int r = 0; r < kW; ++r)
+      if (r < world) {
+        v[r] = peer::ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(x.bucket[r]) + i);
+        if (two) w[r] = peer::ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(x.bucket[r]) + i2);
+      }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < kW; ++r)  // fixed rank order: every rank gets the same bits
+        if (r < world) acc8(a, h == 0 ? v[r] : w[r]);
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(a[2 * j], a[2 * j + 1]);
+      *reinterpret_cast<uint4*>(out + (h == 0 ? i : i2)) = o;
+    }
+  }
+  // last block out publishes the slice
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(lw + 1, 1ull);
+    if (t == gridDim.x - 1) {
+      lw[1] = 0;
+      __threadfence_system();  // every block's slice stores (observed through the counter) before the flags
+      for (int q = 0; q < world; ++q) peer::st_release_sys(peer::reduced_flags(x, q) + x.rank, epoch);
+    }
+  }
+}
+
+// Same shared-memory carveout as the persistent GEMM these kernels run beside: an SM cannot change its L1 / shared
+// split while blocks of the other configuration are resident, which would serialise the two kernels.
+void set_carveout() {
+  static const bool once = [] {
+    cudaFuncSetAttribute(peer_signal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(peer_reduce_slice_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(peer_reduce_slice_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(peer_reduce_slice_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(peer_reduce_slice_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return true;
+  }();
+  (void)once;
+}
+
+int check_exchange(const PeerExchange& x) {
+  if (x.world < 2 || x.world > kMaxPeers || x.rank < 0 || x.rank >= x.world)
+    return set_error(ED2_ERR_BAD_ARG, "peer exchange: world %d (2..%d) / rank %d", x.world, kMaxPeers, x.rank);
+  if (x.n <= 0 || x.n % 8 != 0 || x.chunk <= 0 || x.chunk % 8 != 0 || x.chunk * x.world < x.n)
+    return set_error(ED2_ERR_BAD_SHAPE, "peer exchange: n %lld and chunk %lld must be multiples of 8 covering n", x.n, x.chunk);
+  for (int r = 0; r < x.world; ++r)
+    if (x.bucket[r] == nullptr || x.reduced[r] == nullptr || x.flags[r] == nullptr || (x.small_n > 0 && x.small[r] == nullptr))
+      return set_error(ED2_ERR_BAD_ARG, "peer exchange: null pointer for rank %d", r);
+  return ED2_OK;
+}
+
+}  // namespace
+
+int k_peer_signal(const PeerExchange& x, const float* small_src, cudaStream_t s) {
+  int st = check_exchange(x);
+  if (st != ED2_OK) return st;
+  if (x.small_n > 0 && small_src == nullptr) return set_error(ED2_ERR_BAD_ARG, "peer signal: small_src is null");
+  set_carveout();
+  peer_signal_kernel<<<1, kBlock, 0, s>>>(x, small_src);
+  count_launch();
+  return check_launch("peer_signal");
+}
+
+int k_peer_reduce_slice(const PeerExchange& x, int light, cudaStream_t s) {
+  int st = check_exchange(x);
+  if (st != ED2_OK) return st;
+  set_carveout();
+  // The kernel runs on a side stream and mostly waits on NVLink.  Default footprint: 2 blocks x 256 threads per SM
+  // (beside the persistent GEMM, which leaves > 32 K registers); light: 1 block x 128 threads per SM (4 K registers),
+  // which fits beside the gradient-finishing pass at its full occupancy.
+  const int threads = light ? 128 : kBlock;
+  const long long vec = (x.chunk / 8 + threads - 1) / threads;
+  const int g = static_cast<int>(std::max<long long>(1, std::min<long long>(vec, light ? 148 : 148 * 2)));
+  switch (x.world) {
+    case 2: peer_reduce_slice_kernel<2><<<g, threads, 0, s>>>(x); break;
+    case 4: peer_reduce_slice_kernel<4><<<g, threads, 0, s>>>(x); break;
+    case 8: peer_reduce_slice_kernel<8><<<g, threads, 0, s>>>(x); break;
+    default: peer_reduce_slice_kernel<0><<<g, threads, 0, s>>>(x); break;
+  }
+  count_launch();
+  return check_launch("peer_reduce_slice");
+}
+
+}  // namespace ed2
+
+using namespace ed2;
+
+namespace {
+PeerExchange to_internal(const ed2_peer_exchange* e) {
+  PeerExchange x{};
+  x.world = e->world;
+  x.rank = e->rank;
+  x.n = e->n;
+  x.chunk = e->chunk;
+  x.small_n = e->small_n;
+  for (int r = 0; r < kMaxPeers && r < e->world; ++r) {
+    x.bucket[r] = e->bucket[r];
+    x.reduced[r] = e->reduced[r];
+    x.small[r] = e->small_vec[r];
+    x.flags[r] = reinterpret_cast<unsigned long long*>(e->flags[r]);
+  }
+  return x;
+}
+}  // namespace
+
+extern "C" {
+
+int ed2_peer_alloc(size_t bytes, void** ptr_out, void* handle_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == ED2_IPC_HANDLE_BYTES, "IPC handle size");
+  if (bytes == 0 || ptr_out == nullptr || handle_out == nullptr) return set_error(ED2_ERR_BAD_ARG, "ed2_peer_alloc: bad argument");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "ed2_peer_alloc: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return set_error(ED2_ERR_CUDA, "ed2_peer_alloc: %s", cudaGetErrorString(e));
+  }
+  std::memcpy(handle_out, &h, sizeof(h));
+  *ptr_out = p;
+  return ED2_OK;
+}
+
+int ed2_peer_open(const void* handle, void** ptr_out) {
+  if (handle == nullptr || ptr_out == nullptr) return set_error(ED2_ERR_BAD_ARG, "ed2_peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "ed2_peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  *ptr_out = p;
+  return ED2_OK;
+}
+
+int ed2_peer_close(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? ED2_OK : set_error(ED2_ERR_CUDA, "ed2_peer_close: %s", cudaGetErrorString(e));
+}
+
+int ed2_peer_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? ED2_OK : set_error(ED2_ERR_CUDA, "ed2_peer_free: %s", cudaGetErrorString(e));
+}
+
+int ed2_peer_signal(const ed2_peer_exchange* e, const float* small_src, void* stream) {
+  return k_peer_signal(to_internal(e), small_src, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ed2_peer_reduce_slice(const ed2_peer_exchange* e, int light, void* stream) {
+  return k_peer_reduce_slice(to_internal(e), light, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ed2_peer_grad_finish(const ed2_peer_exchange* e, const float* mu, const float* rho, ed2_noise eps, float kl_grad_scale,
+                         const double* kl_upstream, float prior_mean, float prior_std, float* dmu, float* drho,
+                         float* small_out, int fast, void* stream) {
+  return k_peer_grad_finish(to_internal(e), mu, rho, Noise{eps.injected, eps.seed, eps.stream, eps.step}, kl_grad_scale,
+                            kl_upstream, Prior{prior_mean, prior_std}, dmu, drho, small_out, fast != 0,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -38,6 +38,95 @@ def global_row_offset(rank: int, rows_per_rank: int) -> int:
     return rank * rows_per_rank
 
 
+class PeerArena:
+    """One cudaMalloc'ed arena on this rank, IPC-mapped into every peer of `group` (one NVLink / NVSwitch box).
+    `ptrs[r]` is the address of rank r's arena in THIS process.  Construction is collective."""
+
+    def __init__(self, nbytes: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self.lib, self.group = _lib.load(), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        local, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        _lib.check(self.lib.ed2_peer_alloc(nbytes, C.byref(local), handle), "ed2_peer_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.ptrs, self.nbytes = [], nbytes
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(local.value)
+            else:
+                p = C.c_void_p()
+                _lib.check(self.lib.ed2_peer_open(C.create_string_buffer(h, _lib.IPC_HANDLE_BYTES), C.byref(p)), "ed2_peer_open")
+                self.ptrs.append(p.value)
+        dist.barrier(group=group)  # every arena is zeroed and mapped before anyone writes a flag
+
+    def close(self):
+        if not self.ptrs:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self.lib.ed2_peer_close(p)
+        dist.barrier(group=self.group)
+        self.lib.ed2_peer_free(self.ptrs[self.rank])
+        self.ptrs = []
+
+
+class PeerExchange:
+    """The peer-memory exchange of ONE weight gradient (include/ed2b200.h: ed2_peer_*): arena layout
+    [bucket n bf16 | reduced n bf16 | small m fp32 | flags], 256-byte aligned regions."""
+
+    def __init__(self, n: int, small_n: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self.lib = _lib.load()
+        world = dist.get_world_size(group)
+        if world > _lib.MAX_PEERS or n % 8 != 0:
+            raise ValueError(f"peer exchange needs world <= {_lib.MAX_PEERS} and n % 8 == 0 (got {world}, {n})")
+        al = lambda b: (b + 255) // 256 * 256  # noqa: E731
+        off_reduced = al(2 * n)
+        off_small = off_reduced + al(2 * n)
+        off_flags = off_small + al(4 * max(small_n, 1))
+        self.arena = PeerArena(off_flags + al(8 * (2 * world + 3)), group)
+        chunk = ((n + world - 1) // world + 7) // 8 * 8
+        c = _lib.PeerExchange()
+        c.world, c.rank, c.n, c.chunk, c.small_n = world, self.arena.rank, n, chunk, small_n
+        for r, base in enumerate(self.arena.ptrs):
+            c.bucket[r], c.reduced[r] = base, base + off_reduced
+            c.small_vec[r], c.flags[r] = base + off_small, base + off_flags
+        self.c, self._ref = c, C.byref(c)
+        self.bucket_ptr = self.arena.ptrs[self.arena.rank]
+        self.n, self.small_n = n, small_n
+
+    def signal(self, small_src=None):
+        from . import _lib
+
+        _lib.check(self.lib.ed2_peer_signal(self._ref, None if small_src is None else small_src.data_ptr(),
+                                            _lib.stream_ptr()), "ed2_peer_signal")
+
+    def reduce_slice(self, light: bool = False):
+        from . import _lib
+
+        _lib.check(self.lib.ed2_peer_reduce_slice(self._ref, int(light), _lib.stream_ptr()), "ed2_peer_reduce_slice")
+
+    def grad_finish(self, mu, rho, noise, klg, kl_upstream, prior_mean, prior_std, dmu, drho, small_out, fast):
+        from . import _lib
+
+        _lib.check(self.lib.ed2_peer_grad_finish(
+            self._ref, mu.data_ptr(), rho.data_ptr(), noise, klg, None if kl_upstream is None else kl_upstream.data_ptr(),
+            prior_mean, prior_std, dmu.data_ptr(), drho.data_ptr(), None if small_out is None else small_out.data_ptr(),
+            int(fast), _lib.stream_ptr()), "ed2_peer_grad_finish")
+
+    def close(self):
+        self.arena.close()
+
+
 class GradientAllReduce:
     """Overlapped gradient all-reduce: a post-accumulate hook per parameter launches an async sum-all-reduce on the
     process group's own stream the moment that gradient is final; `wait()` joins them before the optimizer step.
@@ -46,8 +135,13 @@ class GradientAllReduce:
     gradient into a persistent bf16 bucket with the library's cast kernel, all-reduces the bucket, and `wait()` casts
     the sum back into `p.grad`."""
 
-    def __init__(self, params, group=None, average: bool = False, compress=None, early: bool = True):
+    def __init__(self, params, group=None, average: bool = False, compress=None, early: bool = True,
+                 exchange: str = "peer"):
+        """exchange='peer' (default when compress=bf16 and the ranks share one box): the raw bf16 weight gradients of
+        DenseReparameterization kernels and their bias gradients are exchanged through IPC-mapped peer memory by this
+        library's own kernels (PeerExchange) — no NCCL call on that path; 'nccl': async NCCL all-reduce of the bucket."""
         self.handles, self.group, self.average, self.compress = [], group, average, compress
+        self.exchange_mode, self._exchanges, self._side = exchange, {}, None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._hooks, self._buckets, self._early_done = [], {}, set()
         self._ids = set()
@@ -64,6 +158,38 @@ class GradientAllReduce:
     # -- early path: called by the layer's backward between its parameter-gradient phase and its dX GEMM -------------
     def wants(self, p) -> bool:
         return self.world > 1 and self.compress is not None and id(p) in self._ids and p.numel() >= 65536
+
+    def wants_peer(self, p) -> bool:
+        return (self.exchange_mode == "peer" and self.wants(p) and not self.average and p.numel() % 8 == 0
+                and p.shape[-1] % 8 == 0 and self.world <= 8)
+
+    def peer_exchange(self, p, small_n: int) -> PeerExchange:
+        """The (lazily built, collective) exchange of parameter `p`; every rank reaches this in the same order."""
+        ex = self._exchanges.get(id(p))
+        if ex is None or ex.small_n != small_n:
+            ex = PeerExchange(p.numel(), small_n, self.group)
+            self._exchanges[id(p)] = ex
+        return ex
+
+    def defer(self, finish, after=None):
+        """A finishing pass to run at wait(), once the CUDA event `after` has fired (peer exchange: there is no
+        communication handle to wait for)."""
+        self.handles.append((after, finish, None))
+
+    def on_side_stream(self, fn):
+        """Run `fn` (kernel launches) on the reducer's side stream, ordered after everything enqueued so far on the
+        current stream; returns the event that marks its completion.  Capturable in a CUDA graph."""
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(priority=-1)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            fn()
+            done = torch.cuda.Event()
+            done.record(self._side)
+        return done
 
     def bucket(self, p):
         b = self._buckets.get(id(p))
@@ -107,7 +233,10 @@ class GradientAllReduce:
 
     def wait(self):
         for h, g2, b in self.handles:
-            h.wait()
+            if isinstance(h, torch.cuda.Event):
+                torch.cuda.current_stream().wait_event(h)
+            elif h is not None:
+                h.wait()
             if callable(g2):
                 g2()  # deferred gradient-finishing pass on the reduced bucket
             elif b is not None:
@@ -124,6 +253,9 @@ class GradientAllReduce:
 
         if F.GradSync.current is self:
             F.GradSync.current = None
+        for ex in self._exchanges.values():
+            ex.close()
+        self._exchanges.clear()
 
 
 def allreduce_precision_partial(partial: torch.Tensor, group=None) -> torch.Tensor:

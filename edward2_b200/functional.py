@@ -241,6 +241,7 @@ class ReparamDense(torch.autograd.Function):
                      col_bias=bias.reshape(1, -1) if bias is not None else None)
             ctx.save_for_backward(xc, y, w_lp, mu, rho)
             ctx.meta = (act, dtype, bias is not None, x.dtype, eps, kl_scale, prior_mean, prior_std)
+            ctx.bias_ref = bias
             ctx.set_materialize_grads(False)
             return y, (kl64 if kl64 is not None else torch.zeros((), dtype=torch.float64, device=dev))
         a = _lib.ReparamFwd()
@@ -252,6 +253,7 @@ class ReparamDense(torch.autograd.Function):
         _lib.check(lib.ed2_reparam_dense_fwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_fwd")
         ctx.save_for_backward(xc, y, w_lp, mu, rho)
         ctx.meta = (act, dtype, bias is not None, x.dtype, eps, kl_scale, prior_mean, prior_std)
+        ctx.bias_ref = bias
         ctx.set_materialize_grads(False)
         # the KL stays fp64 (the accumulator's type): no conversion kernels on the step's critical path
         return y, (kl64 if kl64 is not None else torch.zeros((), dtype=torch.float64, device=dev))
@@ -293,33 +295,70 @@ class ReparamDense(torch.autograd.Function):
         a.prior_mean, a.prior_std, a.kl_upstream = pm, ps, _p(up)
         a.gy_premasked, a.x_is_relu, a.prev_dbias = int(premasked), int(fuse_prev), _p(prev_dbias)
         sync = GradSync.current
+        peer_mode = False
         if sync is not None and sync.wants(mu):
             # data parallel, every rank draws the same eps: reduce the RAW weight gradient (one bf16 tensor instead of
-            # dmu and drho) and finish after the reduction.  Phase 3: dW GEMM -> bf16 bucket; the all-reduce is launched
+            # dmu and drho) and finish after the reduction.  Phase 3: dW GEMM -> bf16 bucket; the exchange starts
             # before the dX GEMM is enqueued (phase 2) and overlaps it; the finishing pass runs at reducer.wait().
-            bucket = sync.bucket(mu)
-            a.phase, a.dmu_lp = 3, _p(bucket)
-            _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd[dW]")
             noise, klg, kup, n_el, fast = eps.c(), a.kl_grad_scale, up, I * O, int(dtype == torch.bfloat16)
+            bias_ref = getattr(ctx, "bias_ref", None)
+            peer_mode = sync.wants_peer(mu) and eps.c().injected is None
+            if peer_mode:
+                # peer-memory exchange (include/ed2b200.h: ed2_peer_*): the bucket lives in an IPC-mapped arena, peers
+                # pull their slice from it; the bias gradient rides along as the exchange's fp32 companion vector
+                with_bias = has_bias and bias_ref is not None and bias_ref.is_leaf and bias_ref.requires_grad
+                ex = sync.peer_exchange(mu, O if with_bias else 0)
+                a.phase, a.dmu_lp = 3, ex.bucket_ptr
+                _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd[dW]")
+                # publish + owner pass on the reducer's side stream: small, shared-memory-free kernels that co-reside with
+                # the dX GEMM enqueued next (they mostly wait on NVLink)
+                small_src = dbias if with_bias else None
 
-            def finish(bucket=bucket, noise=noise, klg=klg, kup=kup, n_el=n_el, fast=fast, dmu=dmu, drho=drho):
-                _lib.check(lib.ed2_normal_grad_finish(bucket.data_ptr(), BF16, mu.data_ptr(), rho.data_ptr(), noise, n_el,
-                                                      klg, _p(kup), pm, ps, dmu.data_ptr(), drho.data_ptr(), fast,
-                                                      _lib.stream_ptr()), "ed2_normal_grad_finish")
-                # these gradients bypass autograd's accumulation (backward returned None for them)
-                for p_, g_ in ((mu, dmu), (rho, drho)):
-                    if p_.grad is None:
-                        p_.grad = g_
-                    else:
-                        p_.grad += g_
+                def exchange(ex=ex, small_src=small_src, light=not need_dx):
+                    ex.signal(small_src)
+                    # no dX GEMM follows the first layer's dW: its owner pass runs beside the finishing passes
+                    ex.reduce_slice(light=light)
 
+                reduced_ev = sync.on_side_stream(exchange)
+                dbias_sum = torch.empty(O, dtype=torch.float32, device=dev) if with_bias else None
+
+                def finish(ex=ex, noise=noise, klg=klg, kup=kup, fast=fast, dmu=dmu, drho=drho, dbias_sum=dbias_sum,
+                           keep=small_src):  # `keep`: the side stream reads it; alive until the streams have joined
+                    ex.grad_finish(mu, rho, noise, klg, kup, pm, ps, dmu, drho, dbias_sum, fast)
+                    for p_, g_ in ((mu, dmu), (rho, drho), (bias_ref, dbias_sum)):
+                        if g_ is None:
+                            continue
+                        if p_.grad is None:
+                            p_.grad = g_
+                        else:
+                            p_.grad += g_
+
+                if with_bias:
+                    dbias = None  # installed by finish(); must not reach the per-parameter all-reduce hook
+            else:
+                bucket = sync.bucket(mu)
+                a.phase, a.dmu_lp = 3, _p(bucket)
+                _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd[dW]")
+
+                def finish(bucket=bucket, noise=noise, klg=klg, kup=kup, n_el=n_el, fast=fast, dmu=dmu, drho=drho):
+                    _lib.check(lib.ed2_normal_grad_finish(bucket.data_ptr(), BF16, mu.data_ptr(), rho.data_ptr(), noise, n_el,
+                                                          klg, _p(kup), pm, ps, dmu.data_ptr(), drho.data_ptr(), fast,
+                                                          _lib.stream_ptr()), "ed2_normal_grad_finish")
+                    # these gradients bypass autograd's accumulation (backward returned None for them)
+                    for p_, g_ in ((mu, dmu), (rho, drho)):
+                        if p_.grad is None:
+                            p_.grad = g_
+                        else:
+                            p_.grad += g_
+
+                sync.early_raw((mu, rho), bucket, finish)
             deferred = True
-
-            sync.early_raw((mu, rho), bucket, finish)
             a.phase = 2
         else:
             deferred = False
         _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd")
+        if peer_mode:
+            sync.defer(finish, after=reduced_ev)
         if fuse_prev:
             in_link.dx_ptr, in_link.dbias = dx.data_ptr(), prev_dbias
         if dx is not None and dx.dtype != x_dtype:

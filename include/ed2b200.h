@@ -285,6 +285,45 @@ int ed2_normal_grad_finish(const void* dw, int dw_dtype, const float* mu, const 
                            float* dmu, float* drho, int fast, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Peer-memory gradient exchange of the data-parallel step (one process per GPU on one NVLink / NVSwitch box).
+ * The reference leaves the gradient all-reduce to tf.distribute / optimizer.apply_gradients ("Gradient
+ * allreduce is implicit in strategy.run"; experimental/rank1_bnns/*: loss pre-divided by num_replicas_in_sync); here
+ * the exchange of a DenseReparameterization kernel's RAW bf16 weight gradient is part of the layer's backward:
+ *   1. the dW GEMM (ed2_reparam_dense_bwd phase 3) writes this rank's bucket, which lives in an IPC-mapped arena;
+ *   2. ed2_peer_signal publishes it (epoch flag written into every peer's memory, release at system scope);
+ *   3. ed2_peer_reduce_slice — each rank owns n / world elements: it pulls that slice from every rank's bucket over
+ *      NVLink, sums in rank order (fp32) and publishes the bf16 result (reduce-scatter by pull);
+ *   4. ed2_peer_grad_finish — the finishing pass of every rank reads each slice from its owner (all-gather by pull,
+ *      fused into the pass that needed dW anyway) and writes dmu / drho; it also sums the ranks' fp32 companion
+ *      vectors (`small`: the layer's bias gradient) one-shot.
+ * No collective library call is involved and every kernel can be captured in a CUDA graph (flags carry a step
+ * epoch).  A peer that never arrives makes the waiting kernel trap after 20 s instead of hanging the GPU.
+ * Arena helpers: ed2_peer_alloc (cudaMalloc + zero + cudaIpcGetMemHandle), ed2_peer_open / _close (map / unmap a
+ * peer's arena from its 64-byte handle), ed2_peer_free. */
+#define ED2_MAX_PEERS 8
+#define ED2_IPC_HANDLE_BYTES 64
+typedef struct {
+  int world, rank;
+  long long n;       /* elements of the exchanged bf16 gradient, multiple of 8 */
+  long long chunk;   /* elements per owner, multiple of 8, chunk * world >= n */
+  long long small_n; /* elements of the fp32 companion vector (0 = none) */
+  const void* bucket[ED2_MAX_PEERS];    /* [r]: rank r's raw bf16 gradient [n]              ([rank] = local memory) */
+  void* reduced[ED2_MAX_PEERS];         /* [r]: rank r's reduced buffer [n] (its own slice is valid)              */
+  const float* small_vec[ED2_MAX_PEERS];/* [r]: rank r's companion vector [small_n]                               */
+  void* flags[ED2_MAX_PEERS];           /* [r]: rank r's flag words, (2 * world + 3) x 8 bytes, zero-initialised   */
+} ed2_peer_exchange;
+int ed2_peer_alloc(size_t bytes, void** ptr_out, void* handle_out /* ED2_IPC_HANDLE_BYTES */);
+int ed2_peer_open(const void* handle, void** ptr_out);
+int ed2_peer_close(void* ptr);
+int ed2_peer_free(void* ptr);
+int ed2_peer_signal(const ed2_peer_exchange* e, const float* small_src, void* stream);
+int ed2_peer_reduce_slice(const ed2_peer_exchange* e, int light /* 1: small footprint, runs beside the finishing pass */,
+                          void* stream);
+int ed2_peer_grad_finish(const ed2_peer_exchange* e, const float* mu, const float* rho, ed2_noise eps, float kl_grad_scale,
+                         const double* kl_upstream, float prior_mean, float prior_std, float* dmu, float* drho,
+                         float* small_out, int fast, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * DenseFlipout (edward2/tensorflow/layers/dense.py:255-285):
  *   y = act( x·mu + ((x ∘ S)·Delta) ∘ T + b ),  Delta = sigma ∘ eps,  S [B][I], T [B][O].
  * S and T are noise tensors of kind "sign" (Philox draws ±1; injected values may be arbitrary floats — the

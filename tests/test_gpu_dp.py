@@ -39,7 +39,7 @@ def _step(layers, x, y, global_batch, F):
     return loss
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, exchange="peer", steps=1):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
@@ -65,9 +65,14 @@ def _worker(rank, world, port, out):
     for l in layers:
         l._calls = 7  # same Philox offset as the single-device run below
     params = [p for l in layers for p in l.parameters()]
-    red = GradientAllReduce(params, compress=torch.bfloat16)
-    _step(layers, xs, ys, B, F)
-    red.wait()
+    red = GradientAllReduce(params, compress=torch.bfloat16, exchange=exchange)
+    for _ in range(steps):  # repeated steps re-use the exchange buffers (flag epochs)
+        for p in params:
+            p.grad = None
+        for l in layers:
+            l._calls = 7
+        _step(layers, xs, ys, B, F)
+        red.wait()
     torch.cuda.synchronize()
     grads = {n: p.grad.float().cpu() for l_i, l in enumerate(layers) for n, p in ((f"{l_i}.{k}", v) for k, v in l.named_parameters())}
     red.remove()
@@ -95,12 +100,19 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_data_parallel_matches_global_batch():
-    if torch.cuda.device_count() < 2:
+@pytest.mark.parametrize("exchange,steps,world", [("peer", 1, 2), ("peer", 3, 2), ("nccl", 1, 2), ("peer", 2, 0)])
+def test_data_parallel_matches_global_batch(exchange, steps, world):
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
         pytest.skip("needs 2 GPUs")
+    if world == 0:  # every GPU of the box (power of two, <= 8)
+        world = 8 if n_dev >= 8 else 4 if n_dev >= 4 else 2
+        if world == 2:
+            pytest.skip("needs more than 2 GPUs")
     import torch.multiprocessing as mp
 
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, exchange, steps), nprocs=world, join=True)
     assert out.get("ok"), f"DP gradients differ from the global-batch step (worst rel err {out.get('worst')})"
+    print(f"[{exchange} x{steps}] worst rel err {out.get('worst'):.3e}")
