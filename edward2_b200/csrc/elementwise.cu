@@ -1111,13 +1111,15 @@ int k_normal_grad_finish_any(const void* dw, int dw_dt, const float* mu, const f
 
 int k_peer_grad_finish(const PeerExchange& x, const float* mu, const float* rho, Noise eps, float klg,
                        const double* kl_upstream, Prior p, float* dmu, float* drho, float* small_out, bool fast,
-                       cudaStream_t s) {
+                       int blocks_per_sm, cudaStream_t s) {
   if (x.world < 2 || x.world > kMaxPeers || x.n <= 0 || x.n % 8 != 0 || x.chunk % 8 != 0 || x.n >= (1LL << 33))
     return set_error(ED2_ERR_BAD_ARG, "peer grad finish: bad exchange (world %d, n %lld, chunk %lld)", x.world, x.n, x.chunk);
   if (eps.injected != nullptr) return set_error(ED2_ERR_BAD_ARG, "peer grad finish: needs in-kernel (Philox) noise");
-  // 5 resident blocks per SM (40 registers per thread would allow 6): 50 K registers, which leaves room for the last
-  // exchange's light owner pass (side stream, one 128-thread block per SM, <= 12 K registers) beside this kernel
-  const int g = std::min(grid_for(x.n / 4), 148 * 5);
+  // Persistent grid, 40 registers per thread (6 blocks per SM would fit an idle SM).  The caller says how many blocks
+  // per SM to launch: 3 when the pass runs on a side stream beside the persistent GEMM (29 K of the 64 K registers are
+  // taken), 5 when it runs alone (room for a concurrent owner pass of another exchange).
+  if (blocks_per_sm < 1 || blocks_per_sm > 6) blocks_per_sm = 5;
+  const int g = std::min(grid_for(x.n / 4), 148 * blocks_per_sm);
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(mu) || !al16(rho) || !al16(dmu) || !al16(drho))
     return set_error(ED2_ERR_BAD_ARG, "peer grad finish: mu / rho / dmu / drho must be 16-byte aligned");

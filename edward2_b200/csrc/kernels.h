@@ -137,5 +137,5 @@ int k_peer_reduce_slice(const PeerExchange& x, int light, cudaStream_t s);
 // finishing pass reading the reduced gradient slice by slice from its owners; small_out = sum over ranks of `small`
 int k_peer_grad_finish(const PeerExchange& x, const float* mu, const float* rho, Noise eps, float kl_grad_scale,
                        const double* kl_upstream, Prior p, float* dmu, float* drho, float* small_out, bool fast,
-                       cudaStream_t s);
+                       int blocks_per_sm, cudaStream_t s);
 }  // namespace ed2

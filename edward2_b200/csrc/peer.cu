@@ -226,9 +226,9 @@ int ed2_peer_reduce_slice(const ed2_peer_exchange* e, int light, void* stream) {
 
 int ed2_peer_grad_finish(const ed2_peer_exchange* e, const float* mu, const float* rho, ed2_noise eps, float kl_grad_scale,
                          const double* kl_upstream, float prior_mean, float prior_std, float* dmu, float* drho,
-                         float* small_out, int fast, void* stream) {
+                         float* small_out, int fast, int blocks_per_sm, void* stream) {
   return k_peer_grad_finish(to_internal(e), mu, rho, Noise{eps.injected, eps.seed, eps.stream, eps.step}, kl_grad_scale,
-                            kl_upstream, Prior{prior_mean, prior_std}, dmu, drho, small_out, fast != 0,
+                            kl_upstream, Prior{prior_mean, prior_std}, dmu, drho, small_out, fast != 0, blocks_per_sm,
                             reinterpret_cast<cudaStream_t>(stream));
 }
 

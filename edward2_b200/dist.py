@@ -115,13 +115,14 @@ class PeerExchange:
 
         _lib.check(self.lib.ed2_peer_reduce_slice(self._ref, int(light), _lib.stream_ptr()), "ed2_peer_reduce_slice")
 
-    def grad_finish(self, mu, rho, noise, klg, kl_upstream, prior_mean, prior_std, dmu, drho, small_out, fast):
+    def grad_finish(self, mu, rho, noise, klg, kl_upstream, prior_mean, prior_std, dmu, drho, small_out, fast,
+                    blocks_per_sm=5):
         from . import _lib
 
         _lib.check(self.lib.ed2_peer_grad_finish(
             self._ref, mu.data_ptr(), rho.data_ptr(), noise, klg, None if kl_upstream is None else kl_upstream.data_ptr(),
             prior_mean, prior_std, dmu.data_ptr(), drho.data_ptr(), None if small_out is None else small_out.data_ptr(),
-            int(fast), _lib.stream_ptr()), "ed2_peer_grad_finish")
+            int(fast), int(blocks_per_sm), _lib.stream_ptr()), "ed2_peer_grad_finish")
 
     def close(self):
         self.arena.close()
@@ -141,7 +142,7 @@ class GradientAllReduce:
         DenseReparameterization kernels and their bias gradients are exchanged through IPC-mapped peer memory by this
         library's own kernels (PeerExchange) — no NCCL call on that path; 'nccl': async NCCL all-reduce of the bucket."""
         self.handles, self.group, self.average, self.compress = [], group, average, compress
-        self.exchange_mode, self._exchanges, self._side = exchange, {}, None
+        self.exchange_mode, self._exchanges, self._side = exchange, {}, []
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._hooks, self._buckets, self._early_done = [], {}, set()
         self._ids = set()
@@ -171,24 +172,35 @@ class GradientAllReduce:
             self._exchanges[id(p)] = ex
         return ex
 
-    def defer(self, finish, after=None):
-        """A finishing pass to run at wait(), once the CUDA event `after` has fired (peer exchange: there is no
-        communication handle to wait for)."""
-        self.handles.append((after, finish, None))
+    def defer(self, finish, after=None, keep=None):
+        """At wait(): make the current stream wait for the CUDA event `after`, then run `finish` (if any).  `keep` holds
+        tensors that side-stream kernels read, alive until the streams have joined."""
+        self.handles.append((after, finish, keep))
 
-    def on_side_stream(self, fn):
-        """Run `fn` (kernel launches) on the reducer's side stream, ordered after everything enqueued so far on the
-        current stream; returns the event that marks its completion.  Capturable in a CUDA graph."""
+    def mark_done(self, *params):
+        """These parameters' gradients are reduced and installed by the caller this step: their hooks must not
+        all-reduce them again."""
+        for p in params:
+            if p is not None:
+                self._early_done.add(id(p))
+
+    def on_side_stream(self, fn, which: int = 0, after=None):
+        """Run `fn` (kernel launches) on side stream `which` of the reducer, ordered after everything enqueued so far on
+        the current stream (and after the event `after`); returns the event that marks its completion.  Capturable in a
+        CUDA graph as long as wait() joins the returned event back."""
         main = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream(priority=-1)
+        while len(self._side) <= which:
+            self._side.append(torch.cuda.Stream(priority=-1))
+        side = self._side[which]
         ev = torch.cuda.Event()
         ev.record(main)
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(ev)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            if after is not None:
+                side.wait_event(after)
             fn()
             done = torch.cuda.Event()
-            done.record(self._side)
+            done.record(side)
         return done
 
     def bucket(self, p):
@@ -233,10 +245,12 @@ class GradientAllReduce:
 
     def wait(self):
         for h, g2, b in self.handles:
-            if isinstance(h, torch.cuda.Event):
+            if isinstance(h, torch.cuda.Event):  # side-stream work of the peer exchange
                 torch.cuda.current_stream().wait_event(h)
-            elif h is not None:
-                h.wait()
+                if callable(g2):
+                    g2()
+                continue
+            h.wait()
             if callable(g2):
                 g2()  # deferred gradient-finishing pass on the reduced bucket
             elif b is not None:

@@ -314,27 +314,33 @@ class ReparamDense(torch.autograd.Function):
                 # the dX GEMM enqueued next (they mostly wait on NVLink)
                 small_src = dbias if with_bias else None
 
-                def exchange(ex=ex, small_src=small_src, light=not need_dx):
+                def exchange(ex=ex, small_src=small_src):
                     ex.signal(small_src)
-                    # no dX GEMM follows the first layer's dW: its owner pass runs beside the finishing passes
-                    ex.reduce_slice(light=light)
+                    ex.reduce_slice()
 
-                reduced_ev = sync.on_side_stream(exchange)
+                reduced_ev = sync.on_side_stream(exchange, which=0)
                 dbias_sum = torch.empty(O, dtype=torch.float32, device=dev) if with_bias else None
 
+                # the finishing pass (which pulls every slice from its owner) follows on a second side stream as soon as
+                # this rank's owner pass is done: beside the next GEMMs for the later layers, alone for the first layer
                 def finish(ex=ex, noise=noise, klg=klg, kup=kup, fast=fast, dmu=dmu, drho=drho, dbias_sum=dbias_sum,
-                           keep=small_src):  # `keep`: the side stream reads it; alive until the streams have joined
-                    ex.grad_finish(mu, rho, noise, klg, kup, pm, ps, dmu, drho, dbias_sum, fast)
-                    for p_, g_ in ((mu, dmu), (rho, drho), (bias_ref, dbias_sum)):
-                        if g_ is None:
-                            continue
-                        if p_.grad is None:
-                            p_.grad = g_
-                        else:
-                            p_.grad += g_
+                           bps=3 if need_dx else 5):
+                    ex.grad_finish(mu, rho, noise, klg, kup, pm, ps, dmu, drho, dbias_sum, fast, blocks_per_sm=bps)
+
+                done_ev = sync.on_side_stream(finish, which=1, after=reduced_ev)
+                # reducer.wait() joins the side streams; the tensors they read stay alive until then
+                sync.defer(None, after=done_ev, keep=(small_src, kup, dmu, drho, dbias_sum, mu, rho))
+                for p_, g_ in ((mu, dmu), (rho, drho), (bias_ref, dbias_sum)):  # these bypass autograd's accumulation
+                    if g_ is None:
+                        continue
+                    sync.mark_done(p_)
+                    if p_.grad is None:
+                        p_.grad = g_
+                    else:
+                        p_.grad += g_
 
                 if with_bias:
-                    dbias = None  # installed by finish(); must not reach the per-parameter all-reduce hook
+                    dbias = None  # its sum over ranks is installed above; it must not reach the per-parameter hook
             else:
                 bucket = sync.bucket(mu)
                 a.phase, a.dmu_lp = 3, _p(bucket)
@@ -357,8 +363,6 @@ class ReparamDense(torch.autograd.Function):
         else:
             deferred = False
         _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd")
-        if peer_mode:
-            sync.defer(finish, after=reduced_ev)
         if fuse_prev:
             in_link.dx_ptr, in_link.dbias = dx.data_ptr(), prev_dbias
         if dx is not None and dx.dtype != x_dtype:

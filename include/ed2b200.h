@@ -291,6 +291,7 @@ int ed2_normal_grad_finish(const void* dw, int dw_dtype, const float* mu, const 
  * the exchange of a DenseReparameterization kernel's RAW bf16 weight gradient is part of the layer's backward:
  *   1. the dW GEMM (ed2_reparam_dense_bwd phase 3) writes this rank's bucket, which lives in an IPC-mapped arena;
  *   2. ed2_peer_signal publishes it (epoch flag written into every peer's memory, release at system scope);
+ *      (2-4 run on side streams of the caller: 2 and 3 beside the layer's dX GEMM, 4 as soon as 3 has finished)
  *   3. ed2_peer_reduce_slice — each rank owns n / world elements: it pulls that slice from every rank's bucket over
  *      NVLink, sums in rank order (fp32) and publishes the bf16 result (reduce-scatter by pull);
  *   4. ed2_peer_grad_finish — the finishing pass of every rank reads each slice from its owner (all-gather by pull,
@@ -321,7 +322,8 @@ int ed2_peer_reduce_slice(const ed2_peer_exchange* e, int light /* 1: small foot
                           void* stream);
 int ed2_peer_grad_finish(const ed2_peer_exchange* e, const float* mu, const float* rho, ed2_noise eps, float kl_grad_scale,
                          const double* kl_upstream, float prior_mean, float prior_std, float* dmu, float* drho,
-                         float* small_out, int fast, void* stream);
+                         float* small_out, int fast, int blocks_per_sm /* persistent grid: 3 beside a GEMM, 5 alone */,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DenseFlipout (edward2/tensorflow/layers/dense.py:255-285):
