@@ -329,9 +329,12 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
         loss_val = float(run_step().item())
+        exchange = None
         if reducer is not None:
+            exchange = reducer.exchange_mode  # "nccl" if the peer-memory arena could not be built on this box
             reducer.remove()
-        return dict(ms=ms, e2e_ms=e2e_ms, launches=launches, loss=loss_val, graph=graph is not None, layers=layers)
+        return dict(ms=ms, e2e_ms=e2e_ms, launches=launches, loss=loss_val, graph=graph is not None, layers=layers,
+                    exchange=exchange)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -417,7 +420,7 @@ def run_ours(args):
                    "grad_allreduce": None if world == 1 else (
                        "fp32 NCCL all-reduce per parameter, overlapped with backward" if args.fp32_allreduce else
                        "raw bf16 dW through IPC peer memory: pull reduce-scatter + all-gather fused into the finishing "
-                       "pass (own kernels, no NCCL on the data path)" if args.grad_exchange == "peer" else
+                       "pass (own kernels, no NCCL on the data path)" if main.get("exchange") == "peer" else
                        "bf16 buckets, NCCL all-reduce per parameter, overlapped with backward"),
                    "gemm_ctas": int(os.environ.get("ED2_GEMM_MAX_CTAS", 148))},
         "e2e": {"value": global_batch / (main["e2e_ms"] * 1e-3), "unit": "samples/s",

@@ -49,19 +49,44 @@ class PeerArena:
 
         self.lib, self.group = _lib.load(), group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.ptrs, self.nbytes, err = [], nbytes, None
         local, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
-        _lib.check(self.lib.ed2_peer_alloc(nbytes, C.byref(local), handle), "ed2_peer_alloc")
+        try:
+            import os
+
+            if os.environ.get("ED2_PEER_DISABLE") == "1":  # test hook for the fallback below
+                raise RuntimeError("disabled by ED2_PEER_DISABLE")
+            _lib.check(self.lib.ed2_peer_alloc(nbytes, C.byref(local), handle), "ed2_peer_alloc")
+        except Exception as e:  # noqa: BLE001  (agreed on collectively below: no rank may skip a collective)
+            err, local = e, C.c_void_p()
         handles = [None] * self.world
-        dist.all_gather_object(handles, handle.raw, group=group)
-        self.ptrs, self.nbytes = [], nbytes
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                self.ptrs.append(local.value)
-            else:
-                p = C.c_void_p()
-                _lib.check(self.lib.ed2_peer_open(C.create_string_buffer(h, _lib.IPC_HANDLE_BYTES), C.byref(p)), "ed2_peer_open")
-                self.ptrs.append(p.value)
-        dist.barrier(group=group)  # every arena is zeroed and mapped before anyone writes a flag
+        dist.all_gather_object(handles, handle.raw if err is None else None, group=group)
+        opened = []
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        opened.append(local.value)
+                    else:
+                        p = C.c_void_p()
+                        _lib.check(self.lib.ed2_peer_open(C.create_string_buffer(h, _lib.IPC_HANDLE_BYTES), C.byref(p)),
+                                   "ed2_peer_open")
+                        opened.append(p.value)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer could not allocate its arena")
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # also: every arena is zeroed and mapped from here on
+        if int(ok.item()) == 0:
+            for r, p in enumerate(opened):
+                if r != self.rank:
+                    self.lib.ed2_peer_close(p)
+            dist.barrier(group=group)
+            if local.value:
+                self.lib.ed2_peer_free(local.value)
+            raise RuntimeError(f"peer-memory arena unavailable on this box: {err or 'a peer failed'}")
+        self.ptrs = opened
 
     def close(self):
         if not self.ptrs:
@@ -168,7 +193,14 @@ class GradientAllReduce:
         """The (lazily built, collective) exchange of parameter `p`; every rank reaches this in the same order."""
         ex = self._exchanges.get(id(p))
         if ex is None or ex.small_n != small_n:
-            ex = PeerExchange(p.numel(), small_n, self.group)
+            try:
+                ex = PeerExchange(p.numel(), small_n, self.group)
+            except RuntimeError as e:  # raised on EVERY rank (PeerArena agrees collectively): NCCL path from now on
+                import sys
+
+                sys.stderr.write(f"[edward2_b200.dist] {e}; falling back to the NCCL all-reduce of the bf16 buckets\n")
+                self.exchange_mode = "nccl"
+                return None
             self._exchanges[id(p)] = ex
         return ex
 

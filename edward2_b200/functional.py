@@ -304,10 +304,12 @@ class ReparamDense(torch.autograd.Function):
             bias_ref = getattr(ctx, "bias_ref", None)
             peer_mode = sync.wants_peer(mu) and eps.c().injected is None
             if peer_mode:
-                # peer-memory exchange (include/ed2b200.h: ed2_peer_*): the bucket lives in an IPC-mapped arena, peers
-                # pull their slice from it; the bias gradient rides along as the exchange's fp32 companion vector
                 with_bias = has_bias and bias_ref is not None and bias_ref.is_leaf and bias_ref.requires_grad
                 ex = sync.peer_exchange(mu, O if with_bias else 0)
+                peer_mode = ex is not None  # None: no peer memory on this box (agreed by all ranks) -> NCCL path
+            if peer_mode:
+                # peer-memory exchange (include/ed2b200.h: ed2_peer_*): the bucket lives in an IPC-mapped arena, peers
+                # pull their slice from it; the bias gradient rides along as the exchange's fp32 companion vector
                 a.phase, a.dmu_lp = 3, ex.bucket_ptr
                 _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd[dW]")
                 # publish + owner pass on the reducer's side stream: small, shared-memory-free kernels that co-reside with

@@ -41,6 +41,9 @@ def _step(layers, x, y, global_batch, F):
 
 def _worker(rank, world, port, out, exchange="peer", steps=1):
     sys.path.insert(0, ROOT)
+    if exchange == "peer-disabled":  # the arena cannot be built: every rank must agree to use the NCCL path
+        os.environ["ED2_PEER_DISABLE"] = "1"
+        exchange = "peer"
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
 
@@ -100,7 +103,8 @@ def _worker(rank, world, port, out, exchange="peer", steps=1):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange,steps,world", [("peer", 1, 2), ("peer", 3, 2), ("nccl", 1, 2), ("peer", 2, 0)])
+@pytest.mark.parametrize("exchange,steps,world", [("peer", 1, 2), ("peer", 3, 2), ("nccl", 1, 2), ("peer-disabled", 2, 2),
+                                                  ("peer", 2, 0)])
 def test_data_parallel_matches_global_batch(exchange, steps, world):
     n_dev = torch.cuda.device_count()
     if n_dev < 2:
