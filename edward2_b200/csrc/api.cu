@@ -303,7 +303,7 @@ int ed2_reparam_dense_fwd(const ed2_reparam_fwd_args* a, void* stream) {
   // bf16: the sampling pass is on the critical path (the GEMM needs W), the KL is not (only the loss needs it):
   // sample with hardware-approximate math and no KL, enqueue the GEMM, then run the accurate KL reduction on the
   // side stream beside the GEMM.  fp32 keeps the single precise pass with the KL fused in.
-  const bool split_kl = a->dtype == kBF16 && a->kl_out != nullptr;
+  const bool split_kl = a->dtype == kBF16 && a->kl_out != nullptr && !fused_kl_enabled();
   ED2_TRY(k_sample_weights(a->mu, a->rho, N(a->eps), a->in_dim, a->out_dim, 0, a->w_lp, a->dtype, a->w_ld, nullptr, 0,
                            split_kl ? nullptr : a->kl_out, a->kl_scale, prior, s));
   ForkJoin fj(s, split_kl);  // fork BEFORE the GEMM so the KL pass depends only on what precedes it
@@ -390,7 +390,7 @@ int ed2_normal_grad_finish(const void* dw, int dw_dtype, const float* mu, const 
 int ed2_flipout_dense_fwd(const ed2_flipout_fwd_args* a, void* stream) {
   ED2_TRY(check_dt(a->dtype));
   cudaStream_t s = S(stream);
-  const bool split_kl = a->dtype == kBF16 && a->kl_out != nullptr;
+  const bool split_kl = a->dtype == kBF16 && a->kl_out != nullptr && !fused_kl_enabled();
   ED2_TRY(k_sample_weights(a->mu, a->rho, N(a->eps), a->in_dim, a->out_dim, 1, a->delta_lp, a->dtype, a->delta_ld,
                            a->mu_lp, a->mu_ld, split_kl ? nullptr : a->kl_out, a->kl_scale,
                            Prior{a->prior_mean, a->prior_std}, s));

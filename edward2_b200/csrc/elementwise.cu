@@ -31,6 +31,18 @@ int side_grid_cap() {
   }
   return v;
 }
+}  // namespace
+
+// ED2_KL_FUSED=0 restores the separate, libm-accurate KL pass of the bf16 layers (api.cu forks it beside the GEMM).
+bool fused_kl_enabled() {
+  static const bool v = [] {
+    const char* e = std::getenv("ED2_KL_FUSED");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  return v;
+}
+
+namespace {
 constexpr float kSoftplusEps = 1e-7f;  // keras.backend.epsilon(), edward2/tensorflow/constraints.py:56-63
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
@@ -258,16 +270,20 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int kMode, bool kMean>
+template <int kMode, bool kMean, bool kKl>
 __global__ void __launch_bounds__(kBlock) sample_bf16_lean_kernel(const float* __restrict__ mu,
                                                                   const float* __restrict__ rho, uint64_t seed,
                                                                   uint64_t stream, const uint64_t* step, int rows,
                                                                   int cols, __nv_bfloat16* __restrict__ w, int wld,
-                                                                  __nv_bfloat16* __restrict__ mean_out, int mean_ld) {
+                                                                  __nv_bfloat16* __restrict__ mean_out, int mean_ld,
+                                                                  double* kl_out, float kl_scale, Prior p) {
   const int c = (blockIdx.x * kBlock + threadIdx.x) * 8;
-  if (c >= cols) return;
+  const bool active = c < cols;
+  if (!kKl && !active) return;
   const uint64_t key = step != nullptr ? seed + __ldg(reinterpret_cast<const unsigned long long*>(step)) * 0x9E3779B97F4A7C15ull : seed;
-  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+  const float log_ps = __logf(p.stddev), inv_2s2 = 0.5f / (p.stddev * p.stddev);
+  float kl = 0.f;
+  for (int r = blockIdx.y; active && r < rows; r += gridDim.y) {
     const long long i = (long long)r * cols + c;
     const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + i)), m1 = __ldg(reinterpret_cast<const float4*>(mu + i) + 1);
     const float4 r0 = __ldg(reinterpret_cast<const float4*>(rho + i)), r1 = __ldg(reinterpret_cast<const float4*>(rho + i) + 1);
@@ -287,16 +303,18 @@ __global__ void __launch_bounds__(kBlock) sample_bf16_lean_kernel(const float* _
       float ex;
       const float sigma = sigma_from_rho_fast(rh[j], ex);
       o[j] = kMode == 0 ? fmaf(sigma, e[j], m[j]) : sigma * e[j];
+      if (kKl) kl += kl_fast(m[j], sigma, p.mean, log_ps, inv_2s2);  // same mu / sigma registers: one lg2 + 4 FMA more
     }
     uint4 q;
     q.x = pack2_bf16(o[0], o[1]); q.y = pack2_bf16(o[2], o[3]); q.z = pack2_bf16(o[4], o[5]); q.w = pack2_bf16(o[6], o[7]);
     *reinterpret_cast<uint4*>(w + (long long)r * wld + c) = q;
     if (kMean) {
-      uint4 p;
-      p.x = pack2_bf16(m[0], m[1]); p.y = pack2_bf16(m[2], m[3]); p.z = pack2_bf16(m[4], m[5]); p.w = pack2_bf16(m[6], m[7]);
-      *reinterpret_cast<uint4*>(mean_out + (long long)r * mean_ld + c) = p;
+      uint4 pk;
+      pk.x = pack2_bf16(m[0], m[1]); pk.y = pack2_bf16(m[2], m[3]); pk.z = pack2_bf16(m[4], m[5]); pk.w = pack2_bf16(m[6], m[7]);
+      *reinterpret_cast<uint4*>(mean_out + (long long)r * mean_ld + c) = pk;
     }
   }
+  if (kKl) block_atomic_add(kl_out, kl, kl_scale);
 }
 
 // dmu = d_mean + klg (mu - m) / s^2 ;  drho = (d_pert * eps + klg (sigma / s^2 - 1 / sigma)) * sigmoid(rho)
@@ -1018,8 +1036,10 @@ int k_sample_weights(const float* mu, const float* rho, Noise eps, long long row
   const int gx = static_cast<int>((cols + 4 * kBlock - 1) / (4 * kBlock));
   const int gy = static_cast<int>(std::min<long long>(rows, std::max(1, side_grid_cap() / gx)));
   dim3 grid(gx, gy);
-  // bf16 output without the fused KL: hardware-approximate transcendentals (the result is rounded to 8 mantissa bits)
-  const bool fast = wdt == kBF16 && kl_out == nullptr;
+  // bf16 output: hardware-approximate transcendentals (the result is rounded to 8 mantissa bits).  The KL is either
+  // left to a separate accurate pass (kl_out == nullptr here) or, by default, reduced in the same lean kernel from the
+  // mu / sigma it already holds (fused_kl_enabled(): lg2-based, ~1e-6 relative on the sum).
+  const bool fast = wdt == kBF16 && (kl_out == nullptr || fused_kl_enabled());
   const bool lean = fast && eps.injected == nullptr && cols % 8 == 0 && wld % 8 == 0 && (mean_out == nullptr || mean_ld % 8 == 0) &&
                     (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(mu) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(rho) & 15) == 0 && (reinterpret_cast<uintptr_t>(mean_out) & 15) == 0;
@@ -1029,22 +1049,27 @@ int k_sample_weights(const float* mu, const float* rho, Noise eps, long long row
     dim3 lgrid(lgx, lgy);
     auto* wp = reinterpret_cast<__nv_bfloat16*>(w);
     auto* mp = reinterpret_cast<__nv_bfloat16*>(mean_out);
-    if (mode == 0 && mp == nullptr)
-      sample_bf16_lean_kernel<0, false><<<lgrid, kBlock, 0, s>>>(mu, rho, eps.seed, eps.stream, eps.step, (int)rows, (int)cols, wp, (int)wld, mp, (int)mean_ld);
-    else if (mode == 0)
-      sample_bf16_lean_kernel<0, true><<<lgrid, kBlock, 0, s>>>(mu, rho, eps.seed, eps.stream, eps.step, (int)rows, (int)cols, wp, (int)wld, mp, (int)mean_ld);
-    else if (mp == nullptr)
-      sample_bf16_lean_kernel<1, false><<<lgrid, kBlock, 0, s>>>(mu, rho, eps.seed, eps.stream, eps.step, (int)rows, (int)cols, wp, (int)wld, mp, (int)mean_ld);
-    else
-      sample_bf16_lean_kernel<1, true><<<lgrid, kBlock, 0, s>>>(mu, rho, eps.seed, eps.stream, eps.step, (int)rows, (int)cols, wp, (int)wld, mp, (int)mean_ld);
+#define ED2_LEAN(MODE, MEAN, KL)                                                                                      \
+  sample_bf16_lean_kernel<MODE, MEAN, KL><<<lgrid, kBlock, 0, s>>>(mu, rho, eps.seed, eps.stream, eps.step, (int)rows, \
+                                                                   (int)cols, wp, (int)wld, mp, (int)mean_ld, kl_out,  \
+                                                                   kl_scale, p)
+    const bool kl = kl_out != nullptr;
+    if (mode == 0 && mp == nullptr) { if (kl) ED2_LEAN(0, false, true); else ED2_LEAN(0, false, false); }
+    else if (mode == 0) { if (kl) ED2_LEAN(0, true, true); else ED2_LEAN(0, true, false); }
+    else if (mp == nullptr) { if (kl) ED2_LEAN(1, false, true); else ED2_LEAN(1, false, false); }
+    else { if (kl) ED2_LEAN(1, true, true); else ED2_LEAN(1, true, false); }
+#undef ED2_LEAN
     count_launch();
     return check_launch("sample_weights(lean)");
   }
+  if (kl_out == nullptr && fast) {
+    sample_weights_kernel<false, true><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld,
+                                                               mean_out, mean_ld, kl_out, kl_scale, p);
+    count_launch();
+    return check_launch("sample_weights");
+  }
   if (kl_out != nullptr)
     sample_weights_kernel<true, false><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld,
-                                                               mean_out, mean_ld, kl_out, kl_scale, p);
-  else if (fast)
-    sample_weights_kernel<false, true><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld,
                                                                mean_out, mean_ld, kl_out, kl_scale, p);
   else
     sample_weights_kernel<false, false><<<grid, kBlock, 0, s>>>(mu, rho, eps, (int)rows, (int)cols, mode, w, wdt, wld,

@@ -21,6 +21,8 @@ int k_split_bf16(const void* src, int sdt, long long sld, void* dst, long long d
 int k_sample_weights(const float* mu, const float* rho, Noise eps, long long rows, long long cols, int mode, void* w,
                      int wdt, long long wld, void* mean_out, long long mean_ld, double* kl_out, float kl_scale,
                      Prior p, cudaStream_t s);
+// bf16 layers: KL reduced inside the lean sampling kernel (default) instead of a separate accurate pass
+bool fused_kl_enabled();
 int k_normal_kl_fwd(const float* mu, const float* rho, long long n, Prior p, float scale, double* out, cudaStream_t s);
 int k_normal_kl_bwd(const float* mu, const float* rho, long long n, Prior p, float scale, const float* upstream,
                     float* dmu, float* drho, cudaStream_t s);

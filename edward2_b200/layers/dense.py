@@ -171,8 +171,11 @@ class DenseReparameterization(Layer):
         with torch.cuda.stream(self._side_stream):
             nz = self._noise("eps", S_KERNEL)
             lib = _lib.load()
-            split = self.compute_dtype == torch.bfloat16 and kl64 is not None
-            # bf16: lean sampling kernel first (the GEMM waits for it), the accurate KL reduction after it
+            import os
+
+            split = (self.compute_dtype == torch.bfloat16 and kl64 is not None
+                     and os.environ.get("ED2_KL_FUSED", "1") == "0")
+            # bf16: the lean sampling kernel reduces the KL itself; ED2_KL_FUSED=0: separate accurate KL pass after it
             _lib.check(lib.ed2_sample_normal_weights(
                 mean.data_ptr(), rho.data_ptr(), nz.c(), I, O, 0, w_lp.data_ptr(), _lib.dt_of(w_lp), _lib.ld(w_lp),
                 None, 0, None if (kl64 is None or split) else kl64.data_ptr(), kl_scale, pm, ps, _lib.stream_ptr()),
