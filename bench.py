@@ -137,9 +137,12 @@ def make_step(layers, global_batch):
     def step(x, labels):
         # scheduling hint: draw the kernel samples of the later layers on side streams now, so the issue-bound sampling
         # passes overlap the first layers' GEMMs (same Philox streams as without the hint)
+        # (the first layer's sample goes first and alone: the first GEMM waits for it; the others follow beside that GEMM)
+        if hasattr(layers[0], "presample"):
+            layers[0].presample()
         for l in layers[1:]:
             if hasattr(l, "presample"):
-                l.presample()
+                l.presample(after=layers[0])
         h = x
         for l in layers:
             h = l(h)

@@ -327,6 +327,10 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
     gp = a->gy;  // the producer's dX epilogue already applied act'(y) and accumulated dbias
     gp_ld = a->gy_ld;
   }
+  // The column-sum target of the dX epilogue is cleared up front (phases 0 / 1 / 3; phase 2 continues one of them):
+  // a memset between the dW and dX GEMMs would let the forked finishing pass grab every SM before the dX GEMM.
+  const bool fuse_prev = a->x_is_relu && a->prev_dbias != nullptr && a->dx != nullptr;
+  if (fuse_prev && a->phase != 2) cudaMemsetAsync(a->prev_dbias, 0, sizeof(float) * (size_t)a->in_dim, s);
   if (a->phase == 3) {
     if (a->dmu_lp == nullptr) return set_error(ED2_ERR_BAD_ARG, "reparam_bwd phase 3 needs the bf16 bucket dmu_lp");
     if (!a->gy_premasked) {
@@ -363,8 +367,7 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
   if (a->phase != 1 && a->dx != nullptr) {
     EpiParams e2 = epi_default();
     e2.out = a->dx; e2.out_ld = a->dx_ld; e2.out_dt = a->dtype;
-    if (a->x_is_relu && a->prev_dbias != nullptr) {
-      cudaMemsetAsync(a->prev_dbias, 0, sizeof(float) * (size_t)a->in_dim, s);
+    if (fuse_prev) {
       e2.mask_src = a->x; e2.mask_ld = a->x_ld; e2.mask_dt = a->dtype;
       e2.col_sum = a->prev_dbias; e2.col_sum_ld = a->in_dim;
     }

@@ -1029,10 +1029,36 @@ int k_split_bf16(const void* src, int sdt, long long sld, void* dst, long long d
   return check_launch("split_bf16");
 }
 
+// Kernels that are forked beside the persistent GEMM ask for the GEMM's shared-memory carveout: an SM cannot change its
+// L1 / shared split while blocks of the other configuration are resident, so a mismatch serialises the two kernels.
+template <typename K>
+void match_gemm_carveout(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+void set_side_carveouts() {
+  static const bool once = [] {
+    match_gemm_carveout(sample_bf16_lean_kernel<0, false, false>);
+    match_gemm_carveout(sample_bf16_lean_kernel<0, false, true>);
+    match_gemm_carveout(sample_bf16_lean_kernel<0, true, false>);
+    match_gemm_carveout(sample_bf16_lean_kernel<0, true, true>);
+    match_gemm_carveout(sample_bf16_lean_kernel<1, false, false>);
+    match_gemm_carveout(sample_bf16_lean_kernel<1, false, true>);
+    match_gemm_carveout(sample_bf16_lean_kernel<1, true, false>);
+    match_gemm_carveout(sample_bf16_lean_kernel<1, true, true>);
+    match_gemm_carveout(grad_finish_lean_kernel);
+    match_gemm_carveout(normal_grad_finish_kernel<true>);
+    match_gemm_carveout(normal_grad_finish_kernel<false>);
+    match_gemm_carveout(normal_kl_fwd_kernel);
+    return true;
+  }();
+  (void)once;
+}
+
 int k_sample_weights(const float* mu, const float* rho, Noise eps, long long rows, long long cols, int mode, void* w,
                      int wdt, long long wld, void* mean_out, long long mean_ld, double* kl_out, float kl_scale,
                      Prior p, cudaStream_t s) {
   if (rows <= 0 || cols <= 0) return ED2_OK;
+  set_side_carveouts();
   const int gx = static_cast<int>((cols + 4 * kBlock - 1) / (4 * kBlock));
   const int gy = static_cast<int>(std::min<long long>(rows, std::max(1, side_grid_cap() / gx)));
   dim3 grid(gx, gy);
@@ -1097,6 +1123,7 @@ int k_normal_grad_finish(const float* d_mean, const float* d_pert, const float* 
                          long long n, float klg, const double* kl_upstream, Prior p, float* dmu, float* drho, bool fast,
                          cudaStream_t s, void* dmu_lp, void* drho_lp) {
   if (n <= 0) return ED2_OK;
+  set_side_carveouts();
   const int g = std::min(grid_for((n + 3) / 4), side_grid_cap());
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (fast && eps.injected == nullptr && n % 4 == 0 && al16(d_mean) && al16(d_pert) && al16(mu) && al16(rho) && al16(dmu) && al16(drho)) {

@@ -147,10 +147,12 @@ class DenseReparameterization(Layer):
             return r.scale_factor, r.mean, r.stddev
         return 0.0, 0.0, 1.0
 
-    def presample(self):
+    def presample(self, after=None):
         """Optional: draw this call's kernel sample (and its KL) NOW on a side stream, so that the issue-bound sampling
         pass overlaps whatever the main stream is doing (typically the previous layer's GEMM).  The next `call` uses
-        it.  Purely a scheduling hint: the draw is the same Philox stream the un-hinted call would use."""
+        it.  Purely a scheduling hint: the draw is the same Philox stream the un-hinted call would use.
+        `after`: another layer whose presample must finish first (so that the first layer's sample, which the first
+        GEMM is waiting for, is not slowed by the later layers' sampling)."""
         if not self.built or not _is_trainable(self.kernel_initializer):
             return
         mean, rho = self._kernel_params()
@@ -168,6 +170,8 @@ class DenseReparameterization(Layer):
         w_lp = _lib.empty_padded(I, O, self.compute_dtype, dev)
         kl64 = torch.zeros((), dtype=torch.float64, device=dev) if kl_scale != 0 else None
         self._side_stream.wait_stream(main)
+        if after is not None and getattr(after, "_side_stream", None) is not None:
+            self._side_stream.wait_stream(after._side_stream)
         with torch.cuda.stream(self._side_stream):
             nz = self._noise("eps", S_KERNEL)
             lib = _lib.load()
@@ -238,7 +242,7 @@ class DenseFlipout(DenseReparameterization):
     """Bayesian dense layer estimated via Flipout (dense.py:227-285):
     y = act(x·mean + ((x∘S)·Delta)∘T + b), Delta = sigma∘eps, per-example sign tensors S [.., I] and T [.., O]."""
 
-    def presample(self):
+    def presample(self, after=None):
         """No-op: the Flipout forward samples inside its own call."""
 
     def call(self, inputs, training=None):
