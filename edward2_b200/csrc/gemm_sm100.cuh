@@ -224,7 +224,7 @@ __device__ __forceinline__ void col_sum_chunk(const EpiParams& ep, float (&v)[32
 }
 
 template <int kMajorA, int kMajorB, int BLOCK_N, int kCtaGroup>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(128)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, int M, int N, int K, EpiParams ep) {
   using Cfg = Config<BLOCK_N, kCtaGroup>;
@@ -368,6 +368,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int grp = ep.group_rows > 0 ? (m_ok ? m / ep.group_rows : 0) : 0;
       float row_acc = 0.f;
 
+      // ReLU-mask source (the producer layer's bf16 activations): its global loads are issued most of a 32-column chunk
+      // AHEAD of their use, otherwise every chunk exposes a full global-load latency and short-K GEMMs (the dX of the
+      // 1000-unit head) become epilogue-bound.
+      const bool mask_fast = ep.mask_src != nullptr && ep.mask_dt == kBF16 && m_ok && (ep.mask_ld & 7) == 0 &&
+                             (reinterpret_cast<uintptr_t>(ep.mask_src) & 15) == 0;
+      const uint4* mask_row = reinterpret_cast<const uint4*>(
+          reinterpret_cast<const __nv_bfloat16*>(ep.mask_src) + static_cast<long long>(m_ok ? m : 0) * ep.mask_ld + n0);
+      uint4 mq[4];
+      if (mask_fast && n0 + 32 <= N) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mq[j] = __ldg(mask_row + j);
+      }
+
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t vr[32];
@@ -421,11 +434,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
 
-        if (ep.mask_src != nullptr && active) {
+        if (mask_fast && n_valid == 32) {  // prefetched chunk
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&mq[j]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x = __bfloat1622float2(h[t]);
+              v[j * 8 + 2 * t] = x.x > 0.f ? v[j * 8 + 2 * t] : 0.f;
+              v[j * 8 + 2 * t + 1] = x.y > 0.f ? v[j * 8 + 2 * t + 1] : 0.f;
+            }
+          }
+        } else if (ep.mask_src != nullptr && active) {
           float s[32];
           load_row32(ep.mask_src, ep.mask_dt, static_cast<long long>(m) * ep.mask_ld, nc, n_valid, s);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = s[j] > 0.f ? v[j] : 0.f;
+        }
+        if (mask_fast && c + 1 < BLOCK_N / 32 && n0 + (c + 2) * 32 <= N) {
+          // next chunk's mask: in flight during this chunk's column sums / staged store and the next TMEM load
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mq[j] = __ldg(mask_row + (c + 1) * 4 + j);
         }
         if (ep.row_sum != nullptr && active) {
 #pragma unroll
