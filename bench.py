@@ -24,6 +24,7 @@ DIMS = [1024, 4096, 4096, 1000]
 BATCH = 4096
 KL_SCALE = 1.0 / 50000
 METRIC = "samples/sec fwd+bwd"
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 67.7e6  # (464.7 MB read + 76.7 MB written) / 8 launches, profiles/r01_ncu_summary.csv
 WORKLOAD = "cfg2: DenseReparameterization Bayesian MLP 1024-4096-4096-1000 + KL, batch 4096/GPU, bf16"
 
 
@@ -387,7 +388,12 @@ def run_ours(args):
         fl = flops_per_step(BATCH, False)
         achieved = fl / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "ed2::tc::gemm_bf16_kernel (8 launches per step)", "achieved": achieved,
-                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": None,
+                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
+                # DRAM bytes per GEMM launch (read + write, mean of the step's 8 launches) from the committed
+                # `ncu --set full` capture of this workload (profiles/r01_ncu_summary.csv); algorithmic operand + output
+                # bytes are 83.7 MB per launch, the difference is operands still resident in the 126 MB L2
+                "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch (ncu capture, profiles/)",
+                "algorithmic_bytes_per_launch": 83.7e6,
                 "peak_source": pk["src"], "gemm_ms_per_step": gemm_ms, "algorithmic_flops_per_step": fl,
                 "gemm_share_of_step": gemm_ms / main["ms"]}
         del bufs
