@@ -101,9 +101,23 @@ class PeerArena:
         self.ptrs = []
 
 
+def peer_layout(n: int, small_n: int, world: int) -> dict:
+    """Byte offsets of one exchange arena: [bucket n bf16 | reduced n bf16 | small m fp32 | flags], every region
+    256-byte aligned; `chunk` = elements per owner (multiple of 8 so that a 16-byte vector never straddles owners)."""
+    if n <= 0 or n % 8 != 0:
+        raise ValueError(f"peer exchange needs n % 8 == 0 (got {n})")
+    if not 2 <= world <= 8:
+        raise ValueError(f"peer exchange needs 2 <= world <= 8 (got {world})")
+    al = lambda b: (b + 255) // 256 * 256  # noqa: E731
+    off_reduced = al(2 * n)
+    off_small = off_reduced + al(2 * n)
+    off_flags = off_small + al(4 * max(small_n, 1))
+    return dict(bucket=0, reduced=off_reduced, small=off_small, flags=off_flags,
+                nbytes=off_flags + al(8 * (2 * world + 3)), chunk=((n + world - 1) // world + 7) // 8 * 8)
+
+
 class PeerExchange:
-    """The peer-memory exchange of ONE weight gradient (include/ed2b200.h: ed2_peer_*): arena layout
-    [bucket n bf16 | reduced n bf16 | small m fp32 | flags], 256-byte aligned regions."""
+    """The peer-memory exchange of ONE weight gradient (include/ed2b200.h: ed2_peer_*); arena layout: peer_layout()."""
 
     def __init__(self, n: int, small_n: int, group=None):
         import ctypes as C
@@ -112,19 +126,13 @@ class PeerExchange:
 
         self.lib = _lib.load()
         world = dist.get_world_size(group)
-        if world > _lib.MAX_PEERS or n % 8 != 0:
-            raise ValueError(f"peer exchange needs world <= {_lib.MAX_PEERS} and n % 8 == 0 (got {world}, {n})")
-        al = lambda b: (b + 255) // 256 * 256  # noqa: E731
-        off_reduced = al(2 * n)
-        off_small = off_reduced + al(2 * n)
-        off_flags = off_small + al(4 * max(small_n, 1))
-        self.arena = PeerArena(off_flags + al(8 * (2 * world + 3)), group)
-        chunk = ((n + world - 1) // world + 7) // 8 * 8
+        lay = peer_layout(n, small_n, world)
+        self.arena = PeerArena(lay["nbytes"], group)
         c = _lib.PeerExchange()
-        c.world, c.rank, c.n, c.chunk, c.small_n = world, self.arena.rank, n, chunk, small_n
+        c.world, c.rank, c.n, c.chunk, c.small_n = world, self.arena.rank, n, lay["chunk"], small_n
         for r, base in enumerate(self.arena.ptrs):
-            c.bucket[r], c.reduced[r] = base, base + off_reduced
-            c.small_vec[r], c.flags[r] = base + off_small, base + off_flags
+            c.bucket[r], c.reduced[r] = base + lay["bucket"], base + lay["reduced"]
+            c.small_vec[r], c.flags[r] = base + lay["small"], base + lay["flags"]
         self.c, self._ref = c, C.byref(c)
         self.bucket_ptr = self.arena.ptrs[self.arena.rank]
         self.n, self.small_n = n, small_n
@@ -176,9 +184,11 @@ class GradientAllReduce:
                 if p.requires_grad:
                     self._ids.add(id(p))
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._hook))
-            if early and compress is not None:
-                from . import functional as F
+            from . import functional as F
 
+            if not average:
+                F.GradSync.replicas = self.world  # KL gradients are added once, not once per rank (functional.GradSync)
+            if early and compress is not None:
                 F.GradSync.current = self
 
     # -- early path: called by the layer's backward between its parameter-gradient phase and its dX GEMM -------------
@@ -299,6 +309,8 @@ class GradientAllReduce:
 
         if F.GradSync.current is self:
             F.GradSync.current = None
+        if self.world > 1:
+            F.GradSync.replicas = 1
         for ex in self._exchanges.values():
             ex.close()
         self._exchanges.clear()

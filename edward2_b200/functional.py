@@ -190,6 +190,10 @@ class GradSync:
     overlaps it."""
 
     current = None
+    # Number of data-parallel replicas whose parameter gradients are SUMMED by the installed reducer (1: none).  The KL
+    # regulariser does not depend on the batch: on paths where every rank adds its own KL gradient before the sum, that
+    # gradient is divided by `replicas` so that the reduced gradient contains it exactly once (global-batch semantics).
+    replicas = 1
 
 
 class ReluLink:
@@ -291,7 +295,8 @@ class ReparamDense(torch.autograd.Function):
         a.mu, a.rho, a.eps = mu.data_ptr(), rho.data_ptr(), eps.c()
         a.gp, a.gp_ld, a.dx, a.dx_ld = _p(gp), _ldn(gp), _p(dx), _ldn(dx)
         a.dmu, a.drho, a.dbias = dmu.data_ptr(), drho.data_ptr(), (None if premasked else _p(dbias))
-        a.kl_grad_scale = kl_scale if gkl is not None else 0.0
+        klg_full = kl_scale if gkl is not None else 0.0
+        a.kl_grad_scale = klg_full / GradSync.replicas  # hook-summed path; the early paths below add it once, after
         a.prior_mean, a.prior_std, a.kl_upstream = pm, ps, _p(up)
         a.gy_premasked, a.x_is_relu, a.prev_dbias = int(premasked), int(fuse_prev), _p(prev_dbias)
         sync = GradSync.current
@@ -300,7 +305,7 @@ class ReparamDense(torch.autograd.Function):
             # data parallel, every rank draws the same eps: reduce the RAW weight gradient (one bf16 tensor instead of
             # dmu and drho) and finish after the reduction.  Phase 3: dW GEMM -> bf16 bucket; the exchange starts
             # before the dX GEMM is enqueued (phase 2) and overlaps it; the finishing pass runs at reducer.wait().
-            noise, klg, kup, n_el, fast = eps.c(), a.kl_grad_scale, up, I * O, int(dtype == torch.bfloat16)
+            noise, klg, kup, n_el, fast = eps.c(), klg_full, up, I * O, int(dtype == torch.bfloat16)
             bias_ref = getattr(ctx, "bias_ref", None)
             peer_mode = sync.wants_peer(mu) and eps.c().injected is None
             if peer_mode:
@@ -432,7 +437,7 @@ class FlipoutDense(torch.autograd.Function):
         a.tmp, a.tmp_ld = _p(tmp), 0 if tmp is None else tmp.stride(0)
         a.dx, a.dx_ld = _p(dx), _ldn(dx)
         a.dmu, a.drho, a.dbias = dmu.data_ptr(), drho.data_ptr(), _p(dbias)
-        a.kl_grad_scale = kl_scale if gkl is not None else 0.0
+        a.kl_grad_scale = (kl_scale if gkl is not None else 0.0) / GradSync.replicas  # summed over ranks by the hooks
         a.prior_mean, a.prior_std, a.kl_upstream = pm, ps, _p(up)
         _lib.check(lib.ed2_flipout_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_flipout_dense_bwd")
         if dx is not None and dx.dtype != x_dtype:
@@ -456,7 +461,8 @@ class NormalKL(torch.autograd.Function):
         mu, rho = ctx.saved_tensors
         pm, ps, scale = ctx.meta
         dmu, drho = torch.zeros_like(mu), torch.zeros_like(rho)
-        ops.normal_kl_bwd(mu, rho, dmu, drho, pm, ps, scale, upstream=g.to(torch.float32).reshape(1).contiguous())
+        ops.normal_kl_bwd(mu, rho, dmu, drho, pm, ps, scale / GradSync.replicas,  # hook-summed over the replicas
+                          upstream=g.to(torch.float32).reshape(1).contiguous())
         return dmu, drho, None, None, None
 
 
