@@ -316,6 +316,36 @@ class GradientAllReduce:
         self._exchanges.clear()
 
 
+class DeferredSum:
+    """A replicated tensor that receives rank-local LINEAR updates  x <- a * x + u_r  (the Laplace precision matrix:
+    P <- m P + (1-m) Phi_r^T Phi_r / B_global, or P + Phi_r^T Phi_r) and whose true value is the sum over ranks of what
+    each rank WOULD have added.  Instead of one all-reduce per training step, the ranks accumulate locally and the sum
+    is taken once, when the value is needed (the inverse at the train -> eval transition).  Linearity makes the result
+    identical (up to fp32 summation order) to all-reducing every step: rank 0 carries the value from before the window,
+    the other ranks start the window from zero, and  sum_r x_r  after any number of local updates is the global value.
+    Removes the per-step 268 MB exchange of the D = 8192 head from the training step."""
+
+    def __init__(self, tensor: torch.Tensor, group=None):
+        self.tensor, self.group, self.open = tensor, group, False
+
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def begin_local_update(self):
+        """Call before every rank-local update of the tensor."""
+        if self._world() > 1 and not self.open:
+            if dist.get_rank(self.group) != 0:
+                self.tensor.zero_()
+            self.open = True
+
+    def synchronize(self):
+        """Collective: after this every rank holds the global value.  No-op when nothing was accumulated."""
+        if self.open:
+            dist.all_reduce(self.tensor, op=dist.ReduceOp.SUM, group=self.group)
+            self.open = False
+        return self.tensor
+
+
 def allreduce_precision_partial(partial: torch.Tensor, group=None) -> torch.Tensor:
     """Sum the local ΦᵀΦ partials over ranks (in place); the blend P <- m P + (1-m) sum / B_global follows."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -24,7 +24,11 @@ class LaplaceRandomFeatureCovariance(Layer):
     Training: precision <- momentum * precision + (1 - momentum) * ΦᵀΦ / B  (momentum > 0), else precision + ΦᵀΦ;
     returns the identity.  Inference: lazily inverts (ridge I + precision) once per update and returns
     ridge * Φ Σ Φᵀ.  `data_parallel=True` all-reduces ΦᵀΦ over the default process group (NCCL) before the blend,
-    which reproduces the single-device global-batch result.
+    which reproduces the single-device global-batch result.  `data_parallel="deferred"` gives the same
+    result without any per-step communication: every rank blends its own ΦᵀΦ / B_global into a rank-local matrix and
+    the sum over ranks is taken once, when the covariance is needed (`dist.DeferredSum`; the update is linear in ΦᵀΦ).
+    In that mode `precision_matrix` holds a rank-local partial during training: call `synchronize_precision()` before
+    reading it directly (the layer does so itself before inverting, resetting or evaluating).
     """
 
     def __init__(self, momentum=0.999, ridge_penalty=1e-6, likelihood="gaussian", dtype=None,
@@ -46,7 +50,18 @@ class LaplaceRandomFeatureCovariance(Layer):
         self.register_buffer("if_update_covariance", torch.zeros((), dtype=torch.bool, device=dev))
         self._needs_inverse = False  # host mirror of if_update_covariance (avoids a device sync per call)
         self._cov_lp = None
+        self._deferred = None
+        if self.data_parallel == "deferred":
+            from ..dist import DeferredSum
+
+            self._deferred = DeferredSum(self.precision_matrix)
         self.built = True
+
+    def synchronize_precision(self):
+        """Collective no-op unless `data_parallel="deferred"` accumulated rank-local updates: sums them over ranks."""
+        if self._deferred is not None:
+            self._deferred.synchronize()
+        return self.precision_matrix
 
     # -- helpers -----------------------------------------------------------------------------------------------
     def _adjusted_features(self, gp_feature, logits):
@@ -70,7 +85,12 @@ class LaplaceRandomFeatureCovariance(Layer):
         """In-place ΦᵀΦ contraction on the tcgen05 GEMM with the momentum blend in its epilogue."""
         phi = F.as_compute(self._adjusted_features(gp_feature.detach(), logits), self.compute_dtype)
         B = phi.shape[0]
-        if self.data_parallel and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        multi = torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        if self._deferred is not None and multi:
+            self._deferred.begin_local_update()
+            ops.laplace_precision_update(phi, self.precision_matrix, self.momentum,
+                                         batch_total=B * torch.distributed.get_world_size())
+        elif self.data_parallel and multi:
             partial = torch.empty_like(self.precision_matrix)
             ops.laplace_precision_update(phi, self.precision_matrix, self.momentum, partial_out=partial)
             torch.distributed.all_reduce(partial)
@@ -80,12 +100,15 @@ class LaplaceRandomFeatureCovariance(Layer):
         return self.precision_matrix
 
     def reset_precision_matrix(self):
+        if self._deferred is not None:
+            self._deferred.open = False  # pending rank-local partials are discarded with the matrix
         self.precision_matrix.zero_()
 
     def update_feature_covariance_matrix(self):
         """random_feature.py:435-459.  The D^3 inverse is a library call (torch.linalg.inv), outside the measured
         path."""
         if self._needs_inverse:
+            self.synchronize_precision()
             d = self.precision_matrix.shape[0]
             eye = torch.eye(d, dtype=torch.float32, device=self.precision_matrix.device)
             self.covariance_matrix.copy_(torch.linalg.inv(self.ridge_penalty * eye + self.precision_matrix))

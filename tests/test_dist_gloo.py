@@ -61,6 +61,26 @@ def _worker(rank, world, port, out):
     for m in (0.9, -1.0):
         blended = m * p0 + (1 - m) * partial.numpy() / (E * n) if m > 0 else p0 + partial.numpy()
         ok &= np.allclose(blended, og.precision_update_tf(p0, phi, m))
+    # deferred sum (dist.DeferredSum): rank-local linear updates over several steps, ONE all-reduce at the end, equals
+    # the per-step global-batch recursion — with and without momentum, across two accumulation windows
+    for m in (0.9, -1.0):
+        p_ref = np.eye(D) * 0.3
+        p_loc = torch.tensor(np.eye(D) * 0.3)
+        ds = ed_dist.DeferredSum(p_loc)
+        for window in range(2):
+            for step in range(3):
+                phi_t = np.random.default_rng(100 * window + step).standard_normal((E * n, D))
+                p_ref = og.precision_update_tf(p_ref, phi_t, m)
+                ph = ed_dist.member_major_shard(torch.tensor(phi_t), E, rank, world)
+                ds.begin_local_update()
+                if m > 0:
+                    p_loc.mul_(m).add_((1 - m) / (E * n) * (ph.t() @ ph))
+                else:
+                    p_loc.add_(ph.t() @ ph)
+            ds.synchronize()
+            ok &= np.allclose(p_loc.numpy(), p_ref, rtol=1e-12, atol=1e-12)
+        ds.synchronize()  # nothing pending: must not double-count
+        ok &= np.allclose(p_loc.numpy(), p_ref, rtol=1e-12, atol=1e-12)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -123,3 +123,59 @@ def test_data_parallel_matches_global_batch(exchange, steps, world):
     mp.spawn(_worker, args=(world, _free_port(), out, exchange, steps), nprocs=world, join=True)
     assert out.get("ok"), f"DP gradients differ from the global-batch step (worst rel err {out.get('worst')})"
     print(f"[{exchange} x{steps}] worst rel err {out.get('worst'):.3e}")
+
+
+def _precision_worker(rank, world, port, out):
+    """LaplaceRandomFeatureCovariance over `world` ranks: per-step all-reduce (data_parallel=True) and the deferred sum
+    (data_parallel="deferred") both reproduce the single-device global-batch precision matrix and variance."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import edward2_b200 as ed
+
+    B, D, steps = 512, 256, 3
+    g = torch.Generator().manual_seed(1)
+    phis = [torch.randn(B, D, generator=g).to(torch.bfloat16) for _ in range(steps + 1)]
+    per = B // world
+    res = {}
+    for momentum in (0.9, -1.0):
+        mats = {}
+        for mode in (True, "deferred"):
+            cov = ed.layers.LaplaceRandomFeatureCovariance(momentum=momentum, ridge_penalty=1e-3, dtype="bfloat16",
+                                                           data_parallel=mode)
+            cov._device = dev
+            for s in range(steps):
+                cov(phis[s][rank * per:(rank + 1) * per].to(dev), training=True)
+            var, _ = cov.compute_predictive_variance(phis[steps][:per].to(dev))
+            mats[mode] = (cov.precision_matrix.float().cpu(), var.float().cpu())
+        if rank == 0:
+            ref = ed.layers.LaplaceRandomFeatureCovariance(momentum=momentum, ridge_penalty=1e-3, dtype="bfloat16")
+            ref._device = dev
+            for s in range(steps):
+                ref(phis[s].to(dev), training=True)
+            rvar, _ = ref.compute_predictive_variance(phis[steps][:per].to(dev))
+            rp = ref.precision_matrix.float().cpu()
+            for mode, (pm, var) in mats.items():
+                res[f"{momentum}/{mode}/P"] = float((pm - rp).abs().max() / rp.abs().max())
+                res[f"{momentum}/{mode}/var"] = float((var - rvar.float().cpu()).abs().max() / rvar.abs().max().cpu())
+    if rank == 0:
+        out["res"] = res
+    dist.destroy_process_group()
+
+
+def test_precision_matrix_data_parallel_and_deferred():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_precision_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = dict(out["res"])
+    print(res)
+    assert res and all(v < 1e-4 for k, v in res.items() if k.endswith("/P")), res  # bf16 operands, fp32 accumulate
+    assert all(v < 2e-2 for k, v in res.items() if k.endswith("/var")), res
