@@ -94,3 +94,43 @@ def test_peer_exchange_layout():
     for bad in [(12, 0, 2), (0, 0, 2), (64, 0, 1), (64, 0, 9)]:
         with pytest.raises(ValueError):
             peer_layout(*bad)
+
+
+def test_reference_variable_names_roundtrip():
+    """edward2_b200/checkpoint.py: variable names follow the reference (utils_test.py:36-39, dense.py:527-545,
+    random_feature.py:346-378) and a rename-only round trip restores every tensor."""
+    import pytest
+    import torch
+
+    import edward2_b200 as ed
+    from edward2_b200 import checkpoint
+
+    def built(layer, shape=(4, 16)):
+        layer._device = torch.device("cpu")
+        layer.build(shape)
+        return layer
+
+    dense = built(ed.layers.DenseReparameterization(8, name="dense"))
+    names = sorted(checkpoint.reference_variables(dense))
+    assert names == ["dense/bias:0", "dense/kernel/mean:0", "dense/kernel/stddev:0"]
+    be = built(ed.layers.DenseBatchEnsemble(8, ensemble_size=2, name="be"))
+    assert sorted(checkpoint.reference_variables(be)) == ["be/alpha:0", "be/ensemble_bias:0", "be/gamma:0", "be/kernel:0"]
+    r1 = built(ed.layers.DenseRank1(8, ensemble_size=2, name="r1"))
+    assert {"r1/alpha/mean:0", "r1/alpha/stddev:0", "r1/gamma/mean:0", "r1/gamma/stddev:0", "r1/kernel:0"} <= set(
+        checkpoint.reference_variables(r1))
+    cov = built(ed.layers.LaplaceRandomFeatureCovariance(name="gp_covariance"))
+    assert sorted(checkpoint.reference_variables(cov)) == [
+        "gp_covariance/gp_covariance_matrix:0", "gp_covariance/gp_precision_matrix:0", "gp_covariance/update_gp_covariance:0"]
+
+    src = checkpoint.reference_variables(dense)
+    other = built(ed.layers.DenseReparameterization(8, name="dense", seed=7))
+    numpy_vars = {k: (v + 1.0).numpy() for k, v in src.items()}  # arrays, as a reference checkpoint reader yields them
+    assert sorted(checkpoint.load_reference_variables(other, numpy_vars)) == sorted(src)
+    for k, v in checkpoint.reference_variables(other).items():
+        assert torch.equal(v, src[k] + 1.0)
+    with pytest.raises(KeyError):
+        checkpoint.load_reference_variables(other, {"dense/bias:0": numpy_vars["dense/bias:0"]})
+    with pytest.raises(ValueError):
+        checkpoint.load_reference_variables(other, {**numpy_vars, "dense/bias:0": numpy_vars["dense/bias:0"][:3]})
+    with pytest.raises(ValueError):
+        checkpoint.reference_variables(ed.layers.DenseReparameterization(8))
