@@ -210,7 +210,7 @@ def test_spectral_norm_variants_agree_and_converge():
     ws, _, _, _ = og.spectral_norm_tf(small, u, v, 200, 0.95)
     np.testing.assert_allclose(ws, small)
     w1, _, _, s1 = og.spectral_norm_tf(w, u, v, 1, 0.95, training=False)
-    assert abs(s1 - float(v.reshape(1, -1) @ w @ u.reshape(-1, 1))) < 1e-12
+    assert abs(s1 - float((v.reshape(1, -1) @ w @ u.reshape(-1, 1)).item())) < 1e-12
 
 
 def test_golden_vectors_pin_the_oracle():
@@ -228,3 +228,70 @@ def test_golden_vectors_pin_the_oracle():
     np.testing.assert_allclose(op.normal(2026, 3, 64), g["philox_normal"], rtol=1e-14)
     wn, _, _, sg = og.spectral_norm_tf(g["sn_w_in"], g["sn_u_in"], g["sn_v_in"], 2, 0.95, True)
     np.testing.assert_allclose(wn, g["sn_tf_w"], rtol=1e-12)
+
+
+def test_rank1_equals_member_loop_and_clip_gradient():
+    """dense_test.py:430-460: the vectorised rank-1 layer equals a per-member loop with per-example fast weights;
+    values beyond the [-10, 10] clip (dense.py:1109-1111) pass no gradient to mu / rho."""
+    rng = np.random.default_rng(3)
+    E, n, I, O = 2, 3, 4, 5
+    x, w = rng.standard_normal((E * n, I)), rng.standard_normal((I, O))
+    mu_r, rho_r = rng.standard_normal((E, I)), rng.standard_normal((E, I)) - 1
+    mu_s, rho_s = rng.standard_normal((E, O)), rng.standard_normal((E, O)) - 1
+    eps_r, eps_s, bias = rng.standard_normal((E * n, I)), rng.standard_normal((E * n, O)), rng.standard_normal((E, O))
+    y, _, _, _ = od.rank1_fwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, "relu")
+    rows = []
+    for e in range(E):
+        for i in range(n):
+            b = e * n + i
+            r = np.clip(mu_r[e] + od.stddev(rho_r[e]) * eps_r[b], -10, 10)
+            s = np.clip(mu_s[e] + od.stddev(rho_s[e]) * eps_s[b], -10, 10)
+            rows.append(np.maximum(((x[b] * r) @ w) * s + bias[e], 0.0))
+    np.testing.assert_allclose(y, np.stack(rows), rtol=1e-12, atol=1e-12)
+    # saturate one fast weight: its mean / rho gradient contribution from that example must vanish
+    mu_big = mu_r.copy()
+    mu_big[0, 0] = 50.0
+    g = od.rank1_bwd(x, w, mu_big, rho_r, eps_r, mu_s, rho_s, eps_s, bias, None, np.ones((E * n, O)))
+    assert g["dmu_r"][0, 0] == 0.0 and g["drho_r"][0, 0] == 0.0 and np.abs(g["dmu_r"][1]).sum() > 0
+
+
+def test_posterior_mean_forward_is_near_deterministic():
+    """dense_test.py:113-129: with the trainable-normal defaults (stddev = softplus(-3) ~ 0.049 only at init; the test
+    pins rho very negative) the sampled forward equals the mean forward to 1e-4; Flipout with zero perturbation too."""
+    rng = np.random.default_rng(4)
+    x, mu = rng.standard_normal((6, 5)), rng.standard_normal((5, 4))
+    rho = np.full((5, 4), -20.0)
+    eps = rng.standard_normal((5, 4))
+    y, _ = od.reparam_fwd(x, mu, rho, eps, None, None)
+    np.testing.assert_allclose(y, x @ mu, atol=1e-4)
+    s_in, s_out = np.sign(rng.standard_normal((6, 5))), np.sign(rng.standard_normal((6, 4)))
+    yf = od.flipout_fwd(x, mu, rho, eps, s_in, s_out, None, None)[0]
+    np.testing.assert_allclose(yf, x @ mu, atol=1e-4)
+
+
+def test_precision_ema_converges_and_exact_sum():
+    """random_feature_test.py (TF) :84-104: with momentum the precision matrix converges to E[phi^T phi / B]; with
+    momentum <= 0 it is the exact running sum; the JAX form (momentum None) starts from ridge * I."""
+    rng = np.random.default_rng(5)
+    D, B = 6, 4000
+    target = None
+    p = np.zeros((D, D))
+    for _ in range(400):
+        phi = rng.standard_normal((B, D)) * np.arange(1, D + 1)
+        p = og.precision_update_tf(p, phi, momentum=0.95)
+    target = np.diag(np.arange(1, D + 1) ** 2.0)
+    np.testing.assert_allclose(p, target, rtol=0.05, atol=0.3)
+    phis = [rng.standard_normal((8, D)) for _ in range(3)]
+    acc = np.zeros((D, D))
+    for ph in phis:
+        acc = og.precision_update_tf(acc, ph, momentum=-1.0)
+    np.testing.assert_allclose(acc, sum(ph.T @ ph for ph in phis), rtol=1e-12)
+    pj = 1e-3 * np.eye(D)
+    for ph in phis:
+        pj = og.precision_update_jax(pj, ph, momentum=None)
+    np.testing.assert_allclose(pj, 1e-3 * np.eye(D) + acc, rtol=1e-12)
+    # TF inverse of (ridge I + P) and the JAX Cholesky form of the same precision give the same variance
+    cov = og.covariance_tf(acc, 1e-3)
+    v_tf = og.predictive_variance(phis[0], cov, 1e-3)
+    v_jx = og.predictive_covariance_jax(phis[0], pj, 1e-3, diagonal_only=True)
+    np.testing.assert_allclose(v_tf, v_jx, rtol=1e-8)
