@@ -181,6 +181,7 @@ SIGNATURES = {
     "ed2_peer_free": (_i, [_vp]),
     "ed2_peer_signal": (_i, [C.POINTER(PeerExchange), _vp, _vp]),
     "ed2_peer_reduce_slice": (_i, [C.POINTER(PeerExchange), _i, _vp]),
+    "ed2_peer_gather_f32": (_i, [C.POINTER(PeerExchange), _vp, _vp]),
     "ed2_peer_grad_finish": (_i, [C.POINTER(PeerExchange), _vp, _vp, Noise, _f, _vp, _f, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "ed2_flipout_dense_fwd": (_i, [C.POINTER(FlipoutFwd), _vp]),
     "ed2_flipout_dense_bwd": (_i, [C.POINTER(FlipoutBwd), _vp]),

@@ -136,6 +136,8 @@ int k_peer_signal(const PeerExchange& x, const float* small_src, cudaStream_t s)
 // owner pass: wait for every rank's ready flag, pull + sum the owned slice (rank order), publish the reduced flag
 // light: small footprint (1 block x 128 threads per SM) for running beside the finishing pass instead of a GEMM
 int k_peer_reduce_slice(const PeerExchange& x, int light, cudaStream_t s);
+// plain finishing pass: out[i] = float(reduced gradient), slice by slice from its owners
+int k_peer_gather_f32(const PeerExchange& x, float* out, cudaStream_t s);
 // finishing pass reading the reduced gradient slice by slice from its owners; small_out = sum over ranks of `small`
 int k_peer_grad_finish(const PeerExchange& x, const float* mu, const float* rho, Noise eps, float kl_grad_scale,
                        const double* kl_upstream, Prior p, float* dmu, float* drho, float* small_out, bool fast,

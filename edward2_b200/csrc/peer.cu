@@ -95,11 +95,32 @@ __global__ void __launch_bounds__(kBlock) peer_reduce_slice_kernel(PeerExchange 
   }
 }
 
+// Plain finishing pass of the exchange for gradients that need no further arithmetic (deterministic kernels, or fp32
+// gradients that were cast into the bucket): out[i] = float(reduced[owner(i)][i]), every slice read from its owner.
+__global__ void __launch_bounds__(kBlock) peer_gather_f32_kernel(PeerExchange x, float* __restrict__ out) {
+  unsigned long long* lw = peer::local_words(x);
+  const unsigned long long epoch = lw[0];
+  if (threadIdx.x < x.world) peer::wait_flag(peer::reduced_flags(x, x.rank) + threadIdx.x, epoch, lw + 2, 0x300 + threadIdx.x);
+  __syncthreads();
+  const long long nvec = x.n >> 3;
+  const unsigned chunk8 = static_cast<unsigned>(x.chunk >> 3);
+  for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+    const int owner = static_cast<int>(static_cast<unsigned>(v) / chunk8);
+    const uint4 raw = peer::ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(x.reduced[owner]) + (v << 3));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]), c = __bfloat1622float2(h[2]),
+                 d = __bfloat1622float2(h[3]);
+    reinterpret_cast<float4*>(out)[2 * v] = make_float4(a.x, a.y, b.x, b.y);
+    reinterpret_cast<float4*>(out)[2 * v + 1] = make_float4(c.x, c.y, d.x, d.y);
+  }
+}
+
 // Same shared-memory carveout as the persistent GEMM these kernels run beside: an SM cannot change its L1 / shared
 // split while blocks of the other configuration are resident, which would serialise the two kernels.
 void set_carveout() {
   static const bool once = [] {
     cudaFuncSetAttribute(peer_signal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(peer_gather_f32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(peer_reduce_slice_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(peer_reduce_slice_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(peer_reduce_slice_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -150,6 +171,20 @@ int k_peer_reduce_slice(const PeerExchange& x, int light, cudaStream_t s) {
   }
   count_launch();
   return check_launch("peer_reduce_slice");
+}
+
+int k_peer_gather_f32(const PeerExchange& x, float* out, cudaStream_t s) {
+  int st = check_exchange(x);
+  if (st != ED2_OK) return st;
+  if (out == nullptr || (reinterpret_cast<uintptr_t>(out) & 15) != 0)
+    return set_error(ED2_ERR_BAD_ARG, "peer gather: out must be a 16-byte aligned device pointer");
+  if (x.n >= (1LL << 34)) return set_error(ED2_ERR_BAD_SHAPE, "peer gather: n too large");
+  set_carveout();
+  const long long blocks = (x.n / 8 + kBlock - 1) / kBlock;
+  const int g = static_cast<int>(std::max<long long>(1, std::min<long long>(blocks, 148 * 3)));
+  peer_gather_f32_kernel<<<g, kBlock, 0, s>>>(x, out);
+  count_launch();
+  return check_launch("peer_gather_f32");
 }
 
 }  // namespace ed2
@@ -222,6 +257,10 @@ int ed2_peer_signal(const ed2_peer_exchange* e, const float* small_src, void* st
 
 int ed2_peer_reduce_slice(const ed2_peer_exchange* e, int light, void* stream) {
   return k_peer_reduce_slice(to_internal(e), light, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ed2_peer_gather_f32(const ed2_peer_exchange* e, float* out, void* stream) {
+  return k_peer_gather_f32(to_internal(e), out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ed2_peer_grad_finish(const ed2_peer_exchange* e, const float* mu, const float* rho, ed2_noise eps, float kl_grad_scale,

@@ -157,6 +157,19 @@ class PeerExchange:
             prior_mean, prior_std, dmu.data_ptr(), drho.data_ptr(), None if small_out is None else small_out.data_ptr(),
             int(fast), int(blocks_per_sm), _lib.stream_ptr()), "ed2_peer_grad_finish")
 
+    def gather_f32(self, out):
+        from . import _lib
+
+        _lib.check(self.lib.ed2_peer_gather_f32(self._ref, out.data_ptr(), _lib.stream_ptr()), "ed2_peer_gather_f32")
+
+    def cast_into_bucket(self, grad2d):
+        """bf16(grad) -> this rank's bucket (the library's cast kernel, current stream)."""
+        from . import _lib
+
+        rows, cols = grad2d.shape
+        _lib.check(self.lib.ed2_cast(grad2d.data_ptr(), _lib.dt_of(grad2d), grad2d.stride(0), self.bucket_ptr, _lib.BF16,
+                                     cols, rows, cols, _lib.stream_ptr()), "ed2_cast")
+
     def close(self):
         self.arena.close()
 
@@ -170,12 +183,16 @@ class GradientAllReduce:
     the sum back into `p.grad`."""
 
     def __init__(self, params, group=None, average: bool = False, compress=None, early: bool = True,
-                 exchange: str = "peer"):
+                 exchange: str = "peer", hook_exchange: str = "nccl"):
         """exchange='peer' (default when compress=bf16 and the ranks share one box): the raw bf16 weight gradients of
         DenseReparameterization kernels and their bias gradients are exchanged through IPC-mapped peer memory by this
         library's own kernels (PeerExchange) — no NCCL call on that path; 'nccl': async NCCL all-reduce of the bucket."""
         self.handles, self.group, self.average, self.compress = [], group, average, compress
         self.exchange_mode, self._exchanges, self._side = exchange, {}, []
+        # hook_exchange='peer': large fp32 gradients that reach the per-parameter hook (deterministic kernels of
+        # DenseBatchEnsemble / DenseRank1 / Dense, Flipout's dmu / drho) are cast to bf16 into a peer arena and summed by
+        # the same signal / owner-pass kernels, then gathered back as fp32 — no NCCL call for them either.
+        self.hook_exchange = hook_exchange
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._hooks, self._buckets, self._early_done = [], {}, set()
         self._ids = set()
@@ -274,6 +291,21 @@ class GradientAllReduce:
             return
         if self.average:
             g.div_(self.world)
+        if (self.hook_exchange == "peer" and self.wants_peer(p) and g.is_cuda and g.dtype == torch.float32
+                and g.is_contiguous() and g.data_ptr() % 16 == 0):
+            ex = self.peer_exchange(p, 0)
+            if ex is not None:
+                g2 = g.reshape(-1, g.shape[-1]) if g.dim() > 1 else g.reshape(1, -1)
+                ex.cast_into_bucket(g2)
+
+                def exchange(ex=ex):
+                    ex.signal(None)
+                    ex.reduce_slice()
+
+                reduced_ev = self.on_side_stream(exchange, which=0)
+                done_ev = self.on_side_stream(lambda ex=ex, g=g: ex.gather_f32(g), which=1, after=reduced_ev)
+                self.defer(None, after=done_ev, keep=(g,))
+                return
         if self.compress is not None and g.is_cuda and g.dtype == torch.float32 and g.numel() >= 65536:
             from . import ops
 

@@ -320,6 +320,9 @@ int ed2_peer_free(void* ptr);
 int ed2_peer_signal(const ed2_peer_exchange* e, const float* small_src, void* stream);
 int ed2_peer_reduce_slice(const ed2_peer_exchange* e, int light /* 1: small footprint, runs beside the finishing pass */,
                           void* stream);
+/* plain finishing pass for gradients that need no further arithmetic (deterministic kernels; any fp32 gradient that was
+ * cast into the bucket with ed2_cast): out[n] fp32 = the reduced bf16 gradient, each slice read from its owner */
+int ed2_peer_gather_f32(const ed2_peer_exchange* e, float* out, void* stream);
 int ed2_peer_grad_finish(const ed2_peer_exchange* e, const float* mu, const float* rho, ed2_noise eps, float kl_grad_scale,
                          const double* kl_upstream, float prior_mean, float prior_std, float* dmu, float* drho,
                          float* small_out, int fast, int blocks_per_sm /* persistent grid: 3 beside a GEMM, 5 alone */,

@@ -68,7 +68,9 @@ def _worker(rank, world, port, out, exchange="peer", steps=1):
     for l in layers:
         l._calls = 7  # same Philox offset as the single-device run below
     params = [p for l in layers for p in l.parameters()]
-    if exchange == "fp32-hooks":  # per-parameter fp32 all-reduce: every rank adds its KL gradient / world before the sum
+    if exchange == "peer-hooks":  # generic hook path: fp32 dmu / drho cast to bf16, summed through peer memory
+        red = GradientAllReduce(params, compress=torch.bfloat16, exchange="peer", early=False, hook_exchange="peer")
+    elif exchange == "fp32-hooks":  # per-parameter fp32 all-reduce: every rank adds its KL gradient / world before the sum
         red = GradientAllReduce(params, compress=None)
     else:
         red = GradientAllReduce(params, compress=torch.bfloat16, exchange=exchange)
@@ -106,7 +108,7 @@ def _worker(rank, world, port, out, exchange="peer", steps=1):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange,steps,world", [("peer", 1, 2), ("peer", 3, 2), ("nccl", 1, 2), ("peer-disabled", 2, 2), ("fp32-hooks", 1, 2),
+@pytest.mark.parametrize("exchange,steps,world", [("peer", 1, 2), ("peer", 3, 2), ("nccl", 1, 2), ("peer-disabled", 2, 2), ("fp32-hooks", 1, 2), ("peer-hooks", 2, 2),
                                                   ("peer", 2, 0)])
 def test_data_parallel_matches_global_batch(exchange, steps, world):
     n_dev = torch.cuda.device_count()
