@@ -295,3 +295,79 @@ def test_precision_ema_converges_and_exact_sum():
     v_tf = og.predictive_variance(phis[0], cov, 1e-3)
     v_jx = og.predictive_covariance_jax(phis[0], pj, 1e-3, diagonal_only=True)
     np.testing.assert_allclose(v_tf, v_jx, rtol=1e-8)
+
+
+def test_conv_oracle_pinned_against_torch_and_reference_identities():
+    """oracle/conv.py (the next row): im2col restatement == torch conv2d in float64 for 'valid' / 'same'
+    and strides; BatchEnsemble conv == per-member loop (convolutional_test.py's loop identity); Flipout with zero
+    perturbation == mean conv; closed-form gradients == float64 autograd."""
+    import torch.nn.functional as tf_
+
+    from oracle import conv as oc
+
+    rng = np.random.default_rng(7)
+    B, H, W, C, K, kh, kw = 4, 7, 6, 3, 5, 3, 2
+    x, k = rng.standard_normal((B, H, W, C)), rng.standard_normal((kh, kw, C, K))
+    xt = torch.tensor(x).permute(0, 3, 1, 2)
+    kt = torch.tensor(k).permute(3, 2, 0, 1)
+    for strides, padding in (((1, 1), "valid"), ((2, 1), "valid"), ((1, 1), "same"), ((2, 2), "same")):
+        y = oc.conv2d(x, k, strides, padding)
+        if padding == "same":  # TF SAME: asymmetric padding, extra at the bottom / right
+            ho, pt, pb = oc._out_size(H, kh, strides[0], "same")
+            wo, pl, pr = oc._out_size(W, kw, strides[1], "same")
+            ref = tf_.conv2d(tf_.pad(xt, (pl, pr, pt, pb)), kt, stride=strides)
+        else:
+            ref = tf_.conv2d(xt, kt, stride=strides)
+        np.testing.assert_allclose(y, ref.permute(0, 2, 3, 1).numpy(), rtol=1e-12, atol=1e-12)
+
+    # BatchEnsemble conv == loop over members
+    E, n = 2, 2
+    alpha, gamma, bias = rng.standard_normal((E, C)), rng.standard_normal((E, K)), rng.standard_normal((E, K))
+    y = oc.batch_ensemble_conv2d(x, k, alpha, gamma, bias, "relu", (1, 1), "same")
+    loop = np.concatenate([np.maximum(oc.conv2d(x[e * n:(e + 1) * n] * alpha[e], k, (1, 1), "same") * gamma[e] + bias[e], 0)
+                           for e in range(E)])
+    np.testing.assert_allclose(y, loop, rtol=1e-12, atol=1e-12)
+
+    # Flipout: zero perturbation -> mean conv; Reparameterization: eps = 0 -> mean conv
+    mu, rho, eps = k, np.full(k.shape, -30.0), rng.standard_normal(k.shape)
+    s_in, s_out = np.sign(rng.standard_normal((B, C))), np.sign(rng.standard_normal((B, K)))
+    np.testing.assert_allclose(oc.flipout_conv2d(x, mu, rho, eps, s_in, s_out)[0], oc.conv2d(x, mu), atol=1e-4)  # sigma >= 1e-7
+    np.testing.assert_allclose(oc.reparam_conv2d(x, mu, rho - 0, np.zeros_like(eps))[0], oc.conv2d(x, mu), atol=1e-12)
+    # Flipout == per-example loop with W_b = mu + (s_in[b] outer s_out[b]) * delta
+    rho2 = rng.standard_normal(k.shape) - 2
+    yf, delta = oc.flipout_conv2d(x, mu, rho2, eps, s_in, s_out)
+    for b in range(B):
+        wb = mu + delta * s_in[b][None, None, :, None] * s_out[b][None, None, None, :]
+        np.testing.assert_allclose(yf[b:b + 1], oc.conv2d(x[b:b + 1], wb), rtol=1e-10, atol=1e-10)
+
+    # rank-1 conv == per-example loop
+    mu_r, rho_r = rng.standard_normal((E, C)), rng.standard_normal((E, C)) - 1
+    mu_s, rho_s = rng.standard_normal((E, K)), rng.standard_normal((E, K)) - 1
+    e_r, e_s = rng.standard_normal((B, C)), rng.standard_normal((B, K))
+    y1, r, s = oc.rank1_conv2d(x, k, mu_r, rho_r, e_r, mu_s, rho_s, e_s, bias, None, (1, 1), "valid")
+    for b in range(B):
+        np.testing.assert_allclose(y1[b:b + 1], oc.conv2d(x[b:b + 1] * r[b], k) * s[b] + bias[b // n], rtol=1e-12, atol=1e-12)
+
+    # closed-form gradients vs float64 autograd (through torch conv2d)
+    gy = rng.standard_normal(oc.conv2d(x, k, (2, 1), "valid").shape)
+    xt2 = torch.tensor(x, requires_grad=True)
+    mu_t, rho_t = torch.tensor(mu, requires_grad=True), torch.tensor(rho2, requires_grad=True)
+    bt = torch.tensor(bias[0], requires_grad=True)
+    w_t = mu_t + (torch.nn.functional.softplus(rho_t) + 1e-7) * torch.tensor(eps)
+    yt = torch.relu(tf_.conv2d(xt2.permute(0, 3, 1, 2), w_t.permute(3, 2, 0, 1), stride=(2, 1)).permute(0, 2, 3, 1) + bt)
+    (yt * torch.tensor(gy)).sum().backward()
+    g = oc.reparam_conv2d_bwd(x, mu, rho2, eps, bias[0], "relu", gy, (2, 1), "valid")
+    for a, b_ in ((g["dx"], xt2.grad), (g["dmu"], mu_t.grad), (g["drho"], rho_t.grad), (g["dbias"], bt.grad)):
+        np.testing.assert_allclose(a, b_.numpy(), rtol=1e-9, atol=1e-9)
+
+    xt3 = torch.tensor(x, requires_grad=True)
+    kt3, at3, gt3, bt3 = (torch.tensor(t, requires_grad=True) for t in (k, alpha, gamma, bias))
+    rep = lambda t: t.repeat_interleave(n, 0)[:, None, None, :]  # noqa: E731
+    z = tf_.conv2d((xt3 * rep(at3)).permute(0, 3, 1, 2), kt3.permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
+    yb = torch.relu(z * rep(gt3) + rep(bt3))
+    gy2 = rng.standard_normal(tuple(yb.shape))
+    (yb * torch.tensor(gy2)).sum().backward()
+    g = oc.batch_ensemble_conv2d_bwd(x, k, alpha, gamma, bias, "relu", gy2)
+    for a, b_ in ((g["dx"], xt3.grad), (g["dkernel"], kt3.grad), (g["dalpha"], at3.grad), (g["dgamma"], gt3.grad),
+                  (g["dbias"], bt3.grad)):
+        np.testing.assert_allclose(a, b_.numpy(), rtol=1e-9, atol=1e-9)
