@@ -97,14 +97,16 @@ def run_reference(args):
         return
     from oracle import torch_cpu
 
-    sample_batch = 512
+    # the config's own batch when the run stays within a few minutes (~1 s per 4096-row step on the GPU box's host
+    # cores), a 1024-row sample of it for long runs
+    sample_batch = BATCH if args.steps + args.warmup <= 40 else 1024
     sps, dt, threads = torch_cpu.time_bayesian_mlp(DIMS, sample_batch, False, max(1, args.steps), max(1, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "torch-CPU fp32 restatement of the reference's CPU path "
-                   "(TF/TFP/JAX not installable here); each step = a 512-row sample of the 4096-row batch"},
+                   f"(TF/TFP/JAX not installable here); each step = {sample_batch} rows of the 4096-row batch"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
                          "sample": f"{sample_batch}-row batches of the cfg2 MLP, {args.steps} fwd+bwd steps"},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
