@@ -412,9 +412,9 @@ def run_ours(args):
         try:
             from oracle import torch_cpu
 
-            sps, dt, threads = torch_cpu.time_bayesian_mlp(DIMS, 1024, False, steps=4, warmup=1)
+            sps, dt, threads = torch_cpu.time_bayesian_mlp(DIMS, BATCH, False, steps=4, warmup=1)
             cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                   "sample": "4 fwd+bwd steps on 1024-row batches of the cfg2 MLP (torch-CPU fp32 restatement)",
+                   "sample": f"4 fwd+bwd steps on {BATCH}-row batches of the cfg2 MLP (torch-CPU fp32 restatement)",
                    "s_per_step": dt}
         except Exception as e:  # noqa: BLE001
             cpu = {"error": str(e)[:200]}
