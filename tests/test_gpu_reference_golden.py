@@ -1,0 +1,136 @@
+"""GPU parity against the REFERENCE-generated fixture tests/golden/reference_vectors.npz (outputs of the unmodified
+edward2/jax/nn/{dense,random_feature,normalization,utils}.py executed under NumPy-backed jax / flax stand-ins by
+tests/golden/make_reference_golden.py).  The CUDA path is driven through the Flax-signature mirrors `edward2_b200.nn`
+with the reference's own variables loaded; tolerance is the fp32 bar (1e-5 tensor-scale relative error) unless a test
+states otherwise."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import rel_err, to_np
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FP32 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return np.load(os.path.join(GOLD, "reference_vectors.npz"))
+
+
+def _t(a, cuda, grad=False):
+    t = torch.tensor(np.asarray(a), dtype=torch.float32, device=cuda)
+    return t.requires_grad_(True) if grad else t
+
+
+def _ed():
+    import edward2_b200 as ed
+
+    return ed
+
+
+@pytest.mark.parametrize("tag", ["be2d", "be3d"])
+def test_batch_ensemble_vs_reference(cuda, ref, tag):
+    """jax/nn/dense.py:238-272 (einsum('E...C,EC,CD,ED->E...D') + bias + relu) on N-D inputs."""
+    ed = _ed()
+    E, O = ref[f"{tag}_alpha"].shape[0], ref[f"{tag}_kernel"].shape[1]
+    layer = ed.nn.DenseBatchEnsemble(features=O, ens_size=E, activation=torch.relu)
+    variables = {"params": {"kernel": _t(ref[f"{tag}_kernel"], cuda), "fast_weight_alpha": _t(ref[f"{tag}_alpha"], cuda),
+                            "fast_weight_gamma": _t(ref[f"{tag}_gamma"], cuda), "bias": _t(ref[f"{tag}_bias"], cuda)}}
+    y = layer.apply(variables, _t(ref[f"{tag}_x"], cuda))
+    assert tuple(y.shape) == ref[f"{tag}_y"].shape
+    assert rel_err(to_np(y), ref[f"{tag}_y"]) < FP32
+
+
+@pytest.mark.parametrize("tag,scale", [("rff_unit", 1.0), ("rff_auto", None)])
+def test_random_fourier_features_vs_reference(cuda, ref, tag, scale):
+    """jax/nn/random_feature.py:183-214."""
+    ed = _ed()
+    D = ref[f"{tag}_kernel"].shape[1]
+    layer = ed.nn.RandomFourierFeatures(features=D, feature_scale=scale)
+    variables = {"random_features": {"kernel": _t(ref[f"{tag}_kernel"], cuda), "bias": _t(ref[f"{tag}_bias"], cuda)}}
+    phi = layer.apply(variables, _t(ref[f"{tag}_x"], cuda))
+    assert rel_err(to_np(phi), ref[f"{tag}_phi"]) < FP32
+
+
+@pytest.mark.parametrize("tag,momentum,likelihood", [("cov_exact", None, "gaussian"), ("cov_mom", 0.9, "gaussian"),
+                                                     ("cov_logistic", None, "binary_logistic"),
+                                                     ("cov_poisson", 0.99, "poisson")])
+def test_laplace_covariance_vs_reference(cuda, ref, tag, momentum, likelihood):
+    """jax/nn/random_feature.py:307-309, :340-362, :393-404: two precision updates, then diagonal and full covariance."""
+    ed = _ed()
+    D, ridge = ref["cov_phi1"].shape[1], float(ref[f"{tag}_ridge"])
+    layer = ed.nn.LaplaceRandomFeatureCovariance(hidden_features=D, ridge_penalty=ridge, momentum=momentum,
+                                                 likelihood=likelihood)
+    v = layer.init(0, _t(ref["cov_phi1"], cuda), _t(ref["cov_logits1"], cuda))
+    assert rel_err(to_np(v["laplace_covariance"]["precision_matrix"]), ref[f"{tag}_p0"]) < 1e-7
+    r, v1 = layer.apply(v, _t(ref["cov_phi1"], cuda), _t(ref["cov_logits1"], cuda), mutable=["laplace_covariance"])
+    assert r is None
+    assert rel_err(to_np(v1["laplace_covariance"]["precision_matrix"]), ref[f"{tag}_p1"]) < FP32
+    _, v2 = layer.apply(v1, _t(ref["cov_phi2"], cuda), _t(ref["cov_logits2"], cuda), mutable=["laplace_covariance"])
+    assert rel_err(to_np(v2["laplace_covariance"]["precision_matrix"]), ref[f"{tag}_p2"]) < FP32
+    # predictive covariance with the reference's precision injected (the inverse is a library call; 1e-4 as in
+    # tests/test_gpu_nn.py)
+    vr = {"laplace_covariance": {"precision_matrix": _t(ref[f"{tag}_p2"], cuda)}}
+    var = layer.apply(vr, _t(ref["cov_phit"], cuda), None, diagonal_only=True)
+    cov = layer.apply(vr, _t(ref["cov_phit"], cuda), None, diagonal_only=False)
+    assert rel_err(to_np(var), ref[f"{tag}_var"]) < 1e-4
+    assert rel_err(to_np(cov), ref[f"{tag}_cov"]) < 1e-4
+
+
+def test_rfgp_end_to_end_vs_reference(cuda, ref):
+    """jax/nn/random_feature.py:112-140 with the reference's random features and output layer loaded."""
+    ed = _ed()
+    D, K = ref["gp_rff_kernel"].shape[1], ref["gp_out_kernel"].shape[1]
+    gp = ed.nn.RandomFeatureGaussianProcess(features=K, hidden_features=D, hidden_kwargs=dict(feature_scale=None),
+                                            covmat_kwargs=dict(ridge_penalty=1.0))
+    variables = {
+        "params": {"output_layer": {"kernel": _t(ref["gp_out_kernel"], cuda), "bias": _t(ref["gp_out_bias"], cuda)}},
+        "random_features": {"hidden_layer": {"kernel": _t(ref["gp_rff_kernel"], cuda), "bias": _t(ref["gp_rff_bias"], cuda)}},
+        "laplace_covariance": {"covmat_layer": {"precision_matrix": _t(np.eye(D), cuda)}},
+    }
+    (lg_a, cov_a), st1 = gp.apply(variables, _t(ref["gp_xa"], cuda), mutable=["laplace_covariance"])
+    assert cov_a is None
+    assert rel_err(to_np(lg_a), ref["gp_logits_a"]) < FP32
+    (_, _), st2 = gp.apply(dict(variables, **st1), _t(ref["gp_xb"], cuda), mutable=["laplace_covariance"])
+    assert rel_err(to_np(st2["laplace_covariance"]["covmat_layer"]["precision_matrix"]), ref["gp_precision"]) < FP32
+    full = dict(variables, **st2)
+    logits, var, feats = gp.apply(full, _t(ref["gp_xt"], cuda), return_random_features=True)
+    assert rel_err(to_np(feats), ref["gp_features"]) < FP32
+    assert rel_err(to_np(logits), ref["gp_logits"]) < FP32
+    assert rel_err(to_np(var), ref["gp_var"]) < 1e-4
+    _, cov = gp.apply(full, _t(ref["gp_xt"], cuda), return_full_covmat=True)
+    assert rel_err(to_np(cov), ref["gp_cov"]) < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["sn1", "sn3", "sn_small"])
+def test_spectral_normalization_vs_reference(cuda, ref, tag):
+    """jax/nn/normalization.py:123-185 over a Dense layer: updated u, v, the normalised kernel and the layer output."""
+    ed = _ed()
+    it, c = int(ref[f"{tag}_iters"]), float(ref[f"{tag}_c"])
+    O = ref[f"{tag}_w"].shape[1]
+    layer = ed.nn.SpectralNormalization(ed.nn.Dense(features=O), iteration=it, norm_multiplier=c)
+    variables = {"params": {"Dense": {"kernel": _t(ref[f"{tag}_w"], cuda), "bias": _t(ref[f"{tag}_b"], cuda)}},
+                 "spectral_stats": {"u": _t(ref[f"{tag}_u0"], cuda), "v": _t(ref[f"{tag}_v0"], cuda)}}
+    y, st = layer.apply(variables, _t(ref[f"{tag}_x"], cuda), training=True, mutable=["spectral_stats", "intermediates"])
+    assert rel_err(to_np(st["spectral_stats"]["u"]), ref[f"{tag}_u1"]) < FP32
+    assert rel_err(to_np(st["spectral_stats"]["v"]), ref[f"{tag}_v1"]) < FP32
+    assert rel_err(to_np(st["intermediates"]["w"]), ref[f"{tag}_what"]) < FP32
+    assert rel_err(to_np(y), ref[f"{tag}_y"]) < FP32
+    v2 = dict(variables, spectral_stats=st["spectral_stats"])
+    y_eval = layer.apply(v2, _t(ref[f"{tag}_x"], cuda), training=False)
+    assert rel_err(to_np(y_eval), ref[f"{tag}_y_eval"]) < FP32
+
+
+def test_mean_field_logits_vs_reference(cuda, ref):
+    """jax/nn/utils.py:54-101."""
+    ed = _ed()
+    lg, var = _t(ref["mf_logits"], cuda), _t(ref["mf_var"], cuda)
+    for lik in ("logistic", "binary_logistic", "poisson"):
+        out = ed.nn.mean_field_logits(lg, var, mean_field_factor=0.7, likelihood=lik)
+        assert rel_err(to_np(out), ref[f"mf_{lik}"]) < FP32
+    assert rel_err(to_np(ed.nn.mean_field_logits(lg, None, mean_field_factor=3.0)), ref["mf_nocov"]) < FP32
+    assert rel_err(to_np(ed.nn.mean_field_logits(lg, var, mean_field_factor=-1.0)), ref["mf_negative"]) < 1e-7

@@ -371,3 +371,107 @@ def test_conv_oracle_pinned_against_torch_and_reference_identities():
     for a, b_ in ((g["dx"], xt3.grad), (g["dkernel"], kt3.grad), (g["dalpha"], at3.grad), (g["dgamma"], gt3.grad),
                   (g["dbias"], bt3.grad)):
         np.testing.assert_allclose(a, b_.numpy(), rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Reference-generated fixture: tests/golden/reference_vectors.npz holds outputs of the UNMODIFIED reference files
+# edward2/jax/nn/{dense,random_feature,normalization,utils}.py executed under NumPy-backed jax / flax stand-ins
+# (tests/golden/make_reference_golden.py).  These tests pin the oracle to the reference itself.
+@pytest.fixture(scope="module")
+def ref():
+    return np.load(os.path.join(GOLD, "reference_vectors.npz"))
+
+
+REF_TOL = 1e-12  # both sides are float64 evaluations of the same formulas
+
+
+def _close(a, b, tol=REF_TOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max()), np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("tag", ["be2d", "be3d"])
+def test_reference_batch_ensemble(ref, tag):
+    """jax/nn/dense.py:238-272 run as shipped; N-D inputs are [E*n, ..., I] with the member axis leading."""
+    x = ref[f"{tag}_x"]
+    E = ref[f"{tag}_alpha"].shape[0]
+    # the oracle takes member-major 2-D rows: [E, n, ..., I] -> [E * n * ..., I] keeps each member's rows contiguous
+    xe = x.reshape((E, -1) + x.shape[1:])
+    x2 = xe.reshape(E, -1, x.shape[-1]).reshape(-1, x.shape[-1])
+    y, _ = od.batch_ensemble_fwd(x2, ref[f"{tag}_kernel"], ref[f"{tag}_alpha"], ref[f"{tag}_gamma"], ref[f"{tag}_bias"], "relu")
+    _close(y.reshape(ref[f"{tag}_y"].shape), ref[f"{tag}_y"])
+
+
+@pytest.mark.parametrize("tag,scale", [("rff_unit", 1.0), ("rff_auto", None)])
+def test_reference_random_fourier_features(ref, tag, scale):
+    """jax/nn/random_feature.py:183-214."""
+    D = ref[f"{tag}_kernel"].shape[1]
+    phi, _ = og.rff(ref[f"{tag}_x"], ref[f"{tag}_kernel"], ref[f"{tag}_bias"], np.sqrt(2.0 / D) if scale is None else scale)
+    _close(phi, ref[f"{tag}_phi"])
+
+
+@pytest.mark.parametrize("tag,momentum,likelihood", [("cov_exact", None, "gaussian"), ("cov_mom", 0.9, "gaussian"),
+                                                     ("cov_logistic", None, "binary_logistic"),
+                                                     ("cov_poisson", 0.99, "poisson")])
+def test_reference_laplace_covariance(ref, tag, momentum, likelihood):
+    """jax/nn/random_feature.py:307-309 (initial precision), :340-362 (update), :393-404 (predictive covariance)."""
+    ridge = float(ref[f"{tag}_ridge"])
+    D = ref["cov_phi1"].shape[1]
+    _close(ridge * np.eye(D), ref[f"{tag}_p0"])
+    p1 = og.precision_update_jax(ref[f"{tag}_p0"], ref["cov_phi1"], momentum, ref["cov_logits1"], likelihood)
+    _close(p1, ref[f"{tag}_p1"])
+    p2 = og.precision_update_jax(p1, ref["cov_phi2"], momentum, ref["cov_logits2"], likelihood)
+    _close(p2, ref[f"{tag}_p2"])
+    _close(og.predictive_covariance_jax(ref["cov_phit"], p2, ridge, True), ref[f"{tag}_var"], 1e-10)
+    _close(og.predictive_covariance_jax(ref["cov_phit"], p2, ridge, False), ref[f"{tag}_cov"], 1e-10)
+    # the TF form of the same quantity (tensorflow/layers/random_feature.py:447-459,482-485) for momentum-free updates:
+    # TF keeps P without the ridge and adds it at inversion time
+    if momentum is None:
+        sigma = og.covariance_tf(p2 - ridge * np.eye(D), ridge)
+        _close(og.predictive_covariance_tf(ref["cov_phit"], sigma, ridge), ref[f"{tag}_cov"], 1e-9)
+        _close(og.predictive_variance(ref["cov_phit"], sigma, ridge), ref[f"{tag}_var"], 1e-9)
+
+
+def test_reference_rfgp_end_to_end(ref):
+    """jax/nn/random_feature.py:112-140: LayerNorm -> RFF -> Dense, two precision updates, predictive variance."""
+    D = ref["gp_rff_kernel"].shape[1]
+    scale = np.sqrt(2.0 / D)
+
+    def feats(x):
+        return og.rff(og.layer_norm(x, eps=1e-6), ref["gp_rff_kernel"], ref["gp_rff_bias"], scale)[0]
+
+    pa, pb, pt = feats(ref["gp_xa"]), feats(ref["gp_xb"]), feats(ref["gp_xt"])
+    _close(pt, ref["gp_features"], 1e-11)
+    _close(og.gp_output(pa, ref["gp_out_kernel"], ref["gp_out_bias"]), ref["gp_logits_a"], 1e-11)
+    p = og.precision_update_jax(og.precision_update_jax(np.eye(D), pa), pb)
+    _close(p, ref["gp_precision"], 1e-11)
+    _close(og.gp_output(pt, ref["gp_out_kernel"], ref["gp_out_bias"]), ref["gp_logits"], 1e-11)
+    _close(og.predictive_covariance_jax(pt, p, 1.0, True), ref["gp_var"], 1e-10)
+    _close(og.predictive_covariance_jax(pt, p, 1.0, False), ref["gp_cov"], 1e-10)
+
+
+@pytest.mark.parametrize("tag", ["sn1", "sn3", "sn_small"])
+def test_reference_spectral_normalization(ref, tag):
+    """jax/nn/normalization.py:123-185 over flax Dense: power iterations, sigma, w / max(sigma / c, 1)."""
+    w, u0, v0 = ref[f"{tag}_w"], ref[f"{tag}_u0"], ref[f"{tag}_v0"]
+    it, c = int(ref[f"{tag}_iters"]), float(ref[f"{tag}_c"])
+    w_hat, u1, v1, _ = og.spectral_norm_jax(w, u0, v0, it, c, training=True)
+    _close(u1, ref[f"{tag}_u1"], 1e-11)
+    _close(v1, ref[f"{tag}_v1"], 1e-11)
+    _close(w_hat, ref[f"{tag}_what"], 1e-11)
+    _close(ref[f"{tag}_x"] @ w_hat + ref[f"{tag}_b"], ref[f"{tag}_y"], 1e-11)
+    w_eval, u2, v2, _ = og.spectral_norm_jax(w, u1, v1, it, c, training=False)
+    assert np.array_equal(u2, np.asarray(u1).reshape(-1)) and np.array_equal(v2, np.asarray(v1).reshape(-1))
+    _close(w_eval, ref[f"{tag}_what_eval"], 1e-11)
+    if tag == "sn_small":  # spectral norm already below the bound: the kernel is returned unchanged
+        _close(w_hat, w)
+
+
+def test_reference_mean_field_logits(ref):
+    """jax/nn/utils.py:54-101."""
+    lg, var = ref["mf_logits"], ref["mf_var"]
+    for lik in ("logistic", "binary_logistic", "poisson"):
+        _close(og.mean_field_logits(lg, var, 0.7, lik), ref[f"mf_{lik}"])
+    _close(og.mean_field_logits(lg, None, 3.0), ref["mf_nocov"])
+    _close(og.mean_field_logits(lg, var, -1.0), ref["mf_negative"])
