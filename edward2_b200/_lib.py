@@ -22,7 +22,8 @@ _vp, _i, _f, _ll, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_uint6
 
 
 class Noise(C.Structure):
-    _fields_ = [("injected", _vp), ("seed", _u64), ("stream", _u64), ("step", _vp)]
+    _fields_ = [("injected", _vp), ("seed", _u64), ("stream", _u64), ("step", _vp),
+                ("row0", _ll), ("rows_per_group_local", _i), ("rows_per_group_global", _i)]
 
 
 class GemmDesc(C.Structure):
@@ -74,6 +75,8 @@ class Rank1Fwd(C.Structure):
         ("mu_s", _vp), ("rho_s", _vp), ("eps_s", Noise),
         ("bias", _vp),
         ("y", _vp), ("y_ld", _i), ("xr", _vp), ("xr_ld", _i), ("s_buf", _vp), ("s_ld", _i), ("z", _vp), ("z_ld", _i),
+        ("additive", _i), ("clip_lo", _f), ("clip_hi", _f),
+        ("rho_b", _vp), ("eps_b", Noise), ("bias_buf", _vp), ("bias_ld", _i),
     ]
 
 
@@ -87,6 +90,8 @@ class Rank1Bwd(C.Structure):
         ("mu_s", _vp), ("rho_s", _vp), ("eps_s", Noise),
         ("dz", _vp), ("dz_ld", _i), ("dxr", _vp), ("dxr_ld", _i), ("dx", _vp), ("dx_ld", _i),
         ("dw", _vp), ("dmu_r", _vp), ("drho_r", _vp), ("dmu_s", _vp), ("drho_s", _vp), ("dbias", _vp),
+        ("additive", _i), ("clip_lo", _f), ("clip_hi", _f),
+        ("rho_b", _vp), ("eps_b", Noise), ("drho_b", _vp),
     ]
 
 
@@ -259,8 +264,12 @@ def ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
-def noise(injected: torch.Tensor | None = None, seed: int = 0, stream: int = 0, step: torch.Tensor | None = None) -> Noise:
+def noise(injected: torch.Tensor | None = None, seed: int = 0, stream: int = 0, step: torch.Tensor | None = None,
+          rows: tuple[int, int, int] | None = None) -> Noise:
+    """`rows` = (row0, rows_per_group_local, rows_per_group_global): the data-parallel row mapping of a per-example
+    noise tensor (ed2_noise in include/ed2b200.h); None = identity."""
     n = Noise()
+    n.row0, n.rows_per_group_local, n.rows_per_group_global = rows if rows is not None else (0, 0, 0)
     if injected is not None:
         assert injected.dtype == torch.float32 and injected.is_contiguous() and injected.is_cuda
         n.injected = injected.data_ptr()

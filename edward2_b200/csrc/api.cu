@@ -13,7 +13,15 @@ using namespace ed2;
 namespace {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-inline Noise N(const ed2_noise& n) { return Noise{n.injected, n.seed, n.stream, n.step}; }
+inline Noise N(const ed2_noise& n) {
+  return Noise{n.injected, n.seed, n.stream, n.step, n.row0, n.rows_per_group_local, n.rows_per_group_global};
+}
+inline FastOpts opts_of(int additive, float lo, float hi) {
+  FastOpts o;
+  if (lo != 0.f || hi != 0.f) { o.clip_lo = lo; o.clip_hi = hi; }
+  o.additive = additive;
+  return o;
+}
 
 #define ED2_TRY(expr)            \
   do {                           \
@@ -252,16 +260,41 @@ int ed2_rank1_dense_fwd(const ed2_rank1_fwd_args* a, void* stream) {
   ED2_TRY(check_dt(a->dtype));
   if (a->ensemble_size <= 0 || a->batch % a->ensemble_size != 0)
     return set_error(ED2_ERR_BAD_SHAPE, "batch %d is not divisible by ensemble_size %d", a->batch, a->ensemble_size);
+  if (a->rho_b != nullptr && (a->bias == nullptr || a->bias_buf == nullptr))
+    return set_error(ED2_ERR_BAD_ARG, "rank1_fwd: a sampled bias needs its mean (bias) and the bias_buf workspace");
   cudaStream_t s = S(stream);
   const int rpm = a->batch / a->ensemble_size;
+  const FastOpts fo = opts_of(a->additive, a->clip_lo, a->clip_hi);
   ED2_TRY(k_scale_rows(a->x, a->dtype, a->x_ld, a->batch, a->in_dim, rpm, 1, a->mu_r, a->rho_r, N(a->eps_r), a->xr,
-                       a->xr_ld, nullptr, 0, s));
+                       a->xr_ld, nullptr, 0, s, fo));
+  FastOpts fs = fo;
+  fs.additive = 0;  // the factor itself is written; the epilogue multiplies or adds it
   ED2_TRY(k_scale_rows(nullptr, a->dtype, 0, a->batch, a->out_dim, rpm, 1, a->mu_s, a->rho_s, N(a->eps_s), nullptr, 0,
-                       a->s_buf, a->s_ld, s));
+                       a->s_buf, a->s_ld, s, fs));
   EpiParams e = epi_default();
   e.group_rows = rpm;
-  e.elem_scale = a->s_buf; e.elem_scale_ld = a->s_ld; e.elem_scale_dt = a->dtype;
-  e.col_bias = a->bias; e.col_bias_ld = a->out_dim;
+  if (a->additive) {
+    e.addend = a->s_buf; e.addend_ld = a->s_ld; e.addend_dt = a->dtype;
+  } else {
+    e.elem_scale = a->s_buf; e.elem_scale_ld = a->s_ld; e.elem_scale_dt = a->dtype;
+  }
+  if (a->rho_b != nullptr) {
+    // bias[b,:] = mean[e] + sigma_b[e] * eps_b[b,:], unclipped (dense.py:1131-1139), materialised once per call
+    FastOpts fb;
+    fb.clip_lo = -3.0e38f; fb.clip_hi = 3.0e38f;
+    if (a->additive) {
+      // two per-example addends (s and the bias sample): bias_buf = s_buf + bias sample, one addend slot in the epilogue
+      fb.additive = 1;
+      ED2_TRY(k_scale_rows(a->s_buf, a->dtype, a->s_ld, a->batch, a->out_dim, rpm, 1, a->bias, a->rho_b, N(a->eps_b),
+                           a->bias_buf, a->bias_ld, nullptr, 0, s, fb));
+    } else {
+      ED2_TRY(k_scale_rows(nullptr, a->dtype, 0, a->batch, a->out_dim, rpm, 1, a->bias, a->rho_b, N(a->eps_b), nullptr, 0,
+                           a->bias_buf, a->bias_ld, s, fb));
+    }
+    e.addend = a->bias_buf; e.addend_ld = a->bias_ld; e.addend_dt = a->dtype;
+  } else {
+    e.col_bias = a->bias; e.col_bias_ld = a->out_dim;
+  }
   e.act = a->act;
   e.out = a->y; e.out_ld = a->y_ld; e.out_dt = a->dtype;
   e.raw = a->z; e.raw_ld = a->z_ld; e.raw_dt = a->dtype;
@@ -277,6 +310,8 @@ int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream) {
   o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld; o.z = a->z; o.z_ld = a->z_ld;
   o.s_buf = a->s_buf; o.s_ld = a->s_ld;
   o.mu_s = a->mu_s; o.rho_s = a->rho_s; o.eps_s = N(a->eps_s);
+  o.opts = opts_of(a->additive, a->clip_lo, a->clip_hi);
+  o.rho_b = a->rho_b; o.eps_b = N(a->eps_b); o.d_bias_rho = a->rho_b ? a->drho_b : nullptr;
   o.dz = a->dz; o.dz_ld = a->dz_ld;
   o.d_fast_mu = a->dmu_s; o.d_fast_rho = a->rho_s ? a->drho_s : nullptr; o.dbias = a->dbias;
   ED2_TRY(k_bwd_out(o, s));
@@ -290,6 +325,7 @@ int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream) {
   i.dt = a->dtype; i.rows = a->batch; i.cols = a->in_dim; i.rows_per_member = rpm; i.fast = 2;
   i.dxf = a->dxr; i.dxf_ld = a->dxr_ld; i.x = a->x; i.x_ld = a->x_ld;
   i.fw_mu = a->mu_r; i.fw_rho = a->rho_r; i.eps = N(a->eps_r);
+  i.opts = opts_of(a->additive, a->clip_lo, a->clip_hi);
   i.dx = a->dx; i.dx_ld = a->dx_ld;
   i.d_fast_mu = a->dmu_r; i.d_fast_rho = a->rho_r ? a->drho_r : nullptr;
   return k_bwd_in(i, s);

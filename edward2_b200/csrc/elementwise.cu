@@ -516,15 +516,15 @@ __global__ void __launch_bounds__(kBlock) normal_grad_finish_kernel(const float*
 }
 
 // ------------------------------------------------------------------------------------------- fast weights
-constexpr float kClip = 10.f;  // edward2/tensorflow/layers/dense.py:1109-1111
+constexpr float kClip = 10.f;  // reference default, edward2/tensorflow/layers/dense.py:1025-1026 (lean kernels)
 
 // factor for 4 consecutive columns c..c+3 of row `row` (member e)
 template <int kMode>
 __device__ __forceinline__ void fast_factor4(const float* fw_mu, const float* fw_rho, const Noise& nz, long long row,
                                              int e, int c, int cols, int valid, float (&f)[4], float (&raw)[4],
-                                             float (&en)[4], bool fast = false) {
+                                             float (&en)[4], bool fast = false, float lo = -kClip, float hi = kClip) {
   if (kMode == 2) {
-    const long long idx = row * cols + c;
+    const long long idx = noise_idx(nz, row, cols, c);
     if ((idx & 3) == 0) noise4<1>(nz, idx, (long long)1 << 62, f);
     else
       for (int j = 0; j < 4; ++j) f[j] = j < valid ? noise1<1>(nz, idx + j) : 0.f;
@@ -539,7 +539,7 @@ __device__ __forceinline__ void fast_factor4(const float* fw_mu, const float* fw
   }
   float r[4];
   ld4(fw_rho, kF32, (long long)e * cols + c, valid, r);
-  const long long idx = row * cols + c;
+  const long long idx = noise_idx(nz, row, cols, c);
   if ((idx & 3) == 0) {
     // bf16 compute mode: hardware-approximate Box-Muller (the factor is rounded to bf16 before use)
     if (fast) noise4<0, true>(nz, idx, (long long)1 << 62, en);
@@ -550,14 +550,14 @@ __device__ __forceinline__ void fast_factor4(const float* fw_mu, const float* fw
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     raw[j] = fmaf(softplus_f(r[j]) + kSoftplusEps, en[j], m[j]);
-    f[j] = fminf(fmaxf(raw[j], -kClip), kClip);
+    f[j] = fminf(fmaxf(raw[j], lo), hi);
   }
 }
 
 template <int kMode>
 __global__ void scale_rows_kernel(const void* x, int dt, long long x_ld, long long rows, int cols, int rpm,
                                   const float* fw_mu, const float* fw_rho, Noise nz, void* xo, long long xo_ld,
-                                  void* f_out, long long f_ld) {
+                                  void* f_out, long long f_ld, FastOpts fo) {
   const long long gpr = (cols + 3) >> 2;
   const long long total = rows * gpr;
   for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
@@ -566,12 +566,12 @@ __global__ void scale_rows_kernel(const void* x, int dt, long long x_ld, long lo
     const int valid = min(4, cols - c);
     const int e = static_cast<int>(r / rpm);
     float f[4], raw[4], en[4];
-    fast_factor4<kMode>(fw_mu, fw_rho, nz, r, e, c, cols, valid, f, raw, en, dt == kBF16);
+    fast_factor4<kMode>(fw_mu, fw_rho, nz, r, e, c, cols, valid, f, raw, en, dt == kBF16, fo.clip_lo, fo.clip_hi);
     if (x != nullptr) {
       float xv[4];
       ld4(x, dt, r * x_ld + c, valid, xv);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) xv[j] *= f[j];
+      for (int j = 0; j < 4; ++j) xv[j] = fo.additive ? xv[j] + f[j] : xv[j] * f[j];
       st4(xo, dt, r * xo_ld + c, valid, xv);
     }
     if (f_out != nullptr) st4(f_out, dt, r * f_ld + c, valid, f);
@@ -631,8 +631,7 @@ __device__ __forceinline__ void load_cols(const float* mu, const float* rho, int
 template <bool kHasX>
 __global__ void __launch_bounds__(kBlock) rank1_scale_lean_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int rpm,
                                                                   int cols, const float* __restrict__ fw_mu,
-                                                                  const float* __restrict__ fw_rho, uint64_t seed,
-                                                                  uint64_t stream, const uint64_t* step,
+                                                                  const float* __restrict__ fw_rho, Noise nz,
                                                                   __nv_bfloat16* __restrict__ out, int out_ld) {
   const int c = (blockIdx.x * kBlock + threadIdx.x) * 8;
   if (c >= cols) return;
@@ -640,12 +639,12 @@ __global__ void __launch_bounds__(kBlock) rank1_scale_lean_kernel(const __nv_bfl
   const int e = blockIdx.y / chunks;
   const long long row0 = (long long)e * rpm + (long long)(blockIdx.y - e * chunks) * kLeanRows;
   const long long row1 = min((long long)(e + 1) * rpm, row0 + kLeanRows);
-  const uint64_t key = lean_key(seed, step);
+  const uint64_t key = lean_key(nz.seed, nz.step);
   LeanCols k;
   load_cols(fw_mu, fw_rho, e, c, cols, k);
   for (long long r = row0; r < row1; ++r) {
     float en[8], f[8];
-    normal8_fast(key, stream, r * cols + c, en);
+    normal8_fast(key, nz.stream, noise_row(nz, r) * cols + c, en);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(fmaf(k.sg[j], en[j], k.m[j]), -kClip), kClip);
     if (kHasX) {
@@ -685,7 +684,7 @@ __global__ void __launch_bounds__(kBlock) rank1_bwd_out_lean_kernel(BwdOutArgs a
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
     }
-    normal8_fast(key, a.eps_s.stream, r * a.cols + c, en);
+    normal8_fast(key, a.eps_s.stream, noise_row(a.eps_s, r) * a.cols + c, en);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float raw = fmaf(k.sg[j], en[j], k.m[j]);
@@ -725,7 +724,7 @@ __global__ void __launch_bounds__(kBlock) rank1_bwd_in_lean_kernel(BwdInArgs a) 
     float d[8], xv[8], en[8], o[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(dxf + r * a.dxf_ld + c)), d);
     unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * a.x_ld + c)), xv);
-    normal8_fast(key, a.eps.stream, r * a.cols + c, en);
+    normal8_fast(key, a.eps.stream, noise_row(a.eps, r) * a.cols + c, en);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float raw = fmaf(k.sg[j], en[j], k.m[j]);
@@ -752,29 +751,32 @@ constexpr int kRowsPerBlock = 64;
 
 __device__ __forceinline__ void reduce_cols_and_add(float (&a0)[4], float (&a1)[4], float (&a2)[4], bool use0, bool use1,
                                                     bool use2, float* o0, float* o1, float* o2, long long base, int c,
-                                                    int cols) {
-  __shared__ float red[3][kBlock / 32][128 + 4];
+                                                    int cols, const float* a3 = nullptr, float* o3 = nullptr) {
+  __shared__ float red[4][kBlock / 32][128 + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     red[0][warp][lane * 4 + j] = a0[j];
     red[1][warp][lane * 4 + j] = a1[j];
     red[2][warp][lane * 4 + j] = a2[j];
+    red[3][warp][lane * 4 + j] = a3 != nullptr ? a3[j] : 0.f;
   }
   __syncthreads();
   if (threadIdx.x < 128) {
     const int cc = c - lane * 4 + threadIdx.x;  // block's first column + threadIdx.x
     if (cc < cols) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
       for (int w = 0; w < kBlock / 32; ++w) {
         s0 += red[0][w][threadIdx.x];
         s1 += red[1][w][threadIdx.x];
         s2 += red[2][w][threadIdx.x];
+        s3 += red[3][w][threadIdx.x];
       }
       if (use0) atomicAdd(o0 + base + cc, s0);
       if (use1) atomicAdd(o1 + base + cc, s1);
       if (use2) atomicAdd(o2 + base + cc, s2);
+      if (o3 != nullptr) atomicAdd(o3 + base + cc, s3);
     }
   }
 }
@@ -789,8 +791,15 @@ __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
   const long long row_end = min((long long)(e + 1) * a.rows_per_member, row0 + kRowsPerBlock);
   const int c = blockIdx.x * 128 + lane * 4;
   const int valid = max(0, min(4, a.cols - c));
-  float acc_mu[4] = {0, 0, 0, 0}, acc_rho[4] = {0, 0, 0, 0}, acc_b[4] = {0, 0, 0, 0};
-  float gam[4] = {1, 1, 1, 1}, mus[4], rhos[4], sig_s[4], sgm_s[4];
+  float acc_mu[4] = {0, 0, 0, 0}, acc_rho[4] = {0, 0, 0, 0}, acc_b[4] = {0, 0, 0, 0}, acc_brho[4] = {0, 0, 0, 0};
+  float gam[4] = {1, 1, 1, 1}, mus[4], rhos[4], sig_s[4], sgm_s[4], sgm_b[4] = {0, 0, 0, 0};
+  const bool sampled_bias = kFast == 2 && a.rho_b != nullptr && a.d_bias_rho != nullptr;
+  if (valid > 0 && sampled_bias) {
+    float rb[4];
+    ld4(a.rho_b, kF32, (long long)e * a.cols + c, valid, rb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sgm_b[j] = sigmoid_f(rb[j]);
+  }
   if (valid > 0) {
     if (kFast == 1) ld4(a.gamma, kF32, (long long)e * a.cols + c, valid, gam);
     if (kFast == 2) {
@@ -850,11 +859,28 @@ __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
         for (int j = 0; j < 4; ++j) { dz[j] = g[j] * gam[j]; acc_mu[j] += g[j] * z[j]; }
       } else if (kFast == 2) {
         float z[4], sv[4];
-        ld4(a.z, a.dt, r * a.z_ld + c, valid, z);
-        ld4(a.s_buf, a.dt, r * a.s_ld + c, valid, sv);
+        if (a.opts.additive) {  // y = z + s + b: dz = gp, ds = gp
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { z[j] = 1.f; sv[j] = 1.f; }
+        } else {
+          ld4(a.z, a.dt, r * a.z_ld + c, valid, z);
+          ld4(a.s_buf, a.dt, r * a.s_ld + c, valid, sv);
+        }
+        if (sampled_bias) {
+          float eb[4];
+          const long long bidx = noise_idx(a.eps_b, r, a.cols, c);
+          if ((bidx & 3) == 0) {
+            if (a.dt == kBF16) noise4<0, true>(a.eps_b, bidx, (long long)1 << 62, eb);
+            else noise4<0>(a.eps_b, bidx, (long long)1 << 62, eb);
+          } else {
+            for (int j = 0; j < 4; ++j) eb[j] = j < valid ? noise1<0>(a.eps_b, bidx + j) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc_brho[j] += g[j] * eb[j] * sgm_b[j];
+        }
         if (a.rho_s != nullptr) {
           float en[4];
-          const long long idx = r * a.cols + c;
+          const long long idx = noise_idx(a.eps_s, r, a.cols, c);
           if ((idx & 3) == 0) {
             if (a.dt == kBF16) noise4<0, true>(a.eps_s, idx, (long long)1 << 62, en);
             else noise4<0>(a.eps_s, idx, (long long)1 << 62, en);
@@ -864,7 +890,7 @@ __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float raw = fmaf(sig_s[j], en[j], mus[j]);
-            const float pass = (raw < -kClip || raw > kClip) ? 0.f : 1.f;
+            const float pass = (raw < a.opts.clip_lo || raw > a.opts.clip_hi) ? 0.f : 1.f;
             const float ds = g[j] * z[j] * pass;
             acc_mu[j] += ds;
             acc_rho[j] += ds * en[j] * sgm_s[j];
@@ -876,7 +902,7 @@ __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
         }
       } else {  // flipout: dz = gp, dz2 = gp ∘ T
         float tt[4];
-        const long long idx = r * a.cols + c;
+        const long long idx = noise_idx(a.sign_out, r, a.cols, c);
         if ((idx & 3) == 0) noise4<1>(a.sign_out, idx, (long long)1 << 62, tt);
         else
           for (int j = 0; j < 4; ++j) tt[j] = j < valid ? noise1<1>(a.sign_out, idx + j) : 0.f;
@@ -889,7 +915,8 @@ __global__ void __launch_bounds__(kBlock) bwd_out_kernel(BwdOutArgs a) {
     }
   }
   reduce_cols_and_add(acc_mu, acc_rho, acc_b, a.d_fast_mu != nullptr, a.d_fast_rho != nullptr, a.dbias != nullptr,
-                      a.d_fast_mu, a.d_fast_rho, a.dbias, (long long)e * a.cols, c, a.cols);
+                      a.d_fast_mu, a.d_fast_rho, a.dbias, (long long)e * a.cols, c, a.cols,
+                      sampled_bias ? acc_brho : nullptr, sampled_bias ? a.d_bias_rho : nullptr);
 }
 
 __global__ void __launch_bounds__(kBlock) bwd_in_kernel(BwdInArgs a) {
@@ -915,14 +942,16 @@ __global__ void __launch_bounds__(kBlock) bwd_in_kernel(BwdInArgs a) {
       ld4(a.dxf, a.dt, r * a.dxf_ld + c, valid, d);
       ld4(a.x, a.dt, r * a.x_ld + c, valid, xv);
       if (a.fast == 1) fast_factor4<0>(a.fw_mu, nullptr, a.eps, r, e, c, a.cols, valid, f, raw, en);
-      else fast_factor4<1>(a.fw_mu, a.fw_rho, a.eps, r, e, c, a.cols, valid, f, raw, en, a.dt == kBF16);
+      else fast_factor4<1>(a.fw_mu, a.fw_rho, a.eps, r, e, c, a.cols, valid, f, raw, en, a.dt == kBF16,
+                           a.opts.clip_lo, a.opts.clip_hi);
+      const bool add = a.fast == 2 && a.opts.additive;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float pass = (a.fast == 2 && a.fw_rho != nullptr && (raw[j] < -kClip || raw[j] > kClip)) ? 0.f : 1.f;
-        const float df = d[j] * xv[j] * pass;
+        const float pass = (a.fast == 2 && a.fw_rho != nullptr && (raw[j] < a.opts.clip_lo || raw[j] > a.opts.clip_hi)) ? 0.f : 1.f;
+        const float df = (add ? d[j] : d[j] * xv[j]) * pass;
         acc_mu[j] += df;
         acc_rho[j] += df * en[j] * sgm[j];
-        d[j] *= f[j];
+        if (!add) d[j] *= f[j];
       }
       if (a.dx != nullptr) st4(a.dx, a.dt, r * a.dx_ld + c, valid, d);
     }
@@ -938,9 +967,9 @@ __global__ void fill_noise_kernel(Noise nz, void* out, int dt, long long ld, lon
   for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
     const long long r = g / gpr, c = (g - r * gpr) << 2;
     const int valid = static_cast<int>(min(4LL, cols - c));
-    const long long idx = r * cols + c;
+    const long long idx = noise_idx(nz, r, cols, c);
     float e[4];
-    if ((idx & 3) == 0) noise4<kKind>(nz, idx, rows * cols, e);
+    if ((idx & 3) == 0) noise4<kKind>(nz, idx, nz.injected != nullptr ? rows * cols : (long long)1 << 62, e);
     else
       for (int j = 0; j < 4; ++j) e[j] = j < valid ? noise1<kKind>(nz, idx + j) : 0.f;
     st4(out, dt, r * ld + c, valid, e);
@@ -1189,10 +1218,11 @@ int k_peer_grad_finish(const PeerExchange& x, const float* mu, const float* rho,
 
 int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols, int rpm, int mode,
                  const float* fw_mu, const float* fw_rho, Noise nz, void* xo, long long xo_ld, void* f_out,
-                 long long f_ld, cudaStream_t s) {
+                 long long f_ld, cudaStream_t s, FastOpts fo) {
   if (rows <= 0 || cols <= 0) return ED2_OK;
   if (rpm <= 0) rpm = static_cast<int>(rows);
-  if (mode == 1 && dt == kBF16 && fw_rho != nullptr && nz.injected == nullptr && cols % 8 == 0 && rows % rpm == 0 &&
+  const bool default_opts = fo.clip_lo == -kClip && fo.clip_hi == kClip && !fo.additive;
+  if (default_opts && mode == 1 && dt == kBF16 && fw_rho != nullptr && nz.injected == nullptr && cols % 8 == 0 && rows % rpm == 0 &&
       (x == nullptr || (x_ld % 8 == 0 && al16(x))) && al16(fw_mu) && al16(fw_rho) && (cols % 4 == 0) &&
       ((x != nullptr && f_out == nullptr && xo_ld % 8 == 0 && al16(xo)) ||
        (x == nullptr && f_out != nullptr && f_ld % 8 == 0 && al16(f_out)))) {
@@ -1200,18 +1230,18 @@ int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols
     dim3 grid((cols / 8 + kBlock - 1) / kBlock, static_cast<unsigned>((rows / rpm) * chunks));
     if (x != nullptr)
       rank1_scale_lean_kernel<true><<<grid, kBlock, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), (int)x_ld, rpm, cols,
-                                                            fw_mu, fw_rho, nz.seed, nz.stream, nz.step,
+                                                            fw_mu, fw_rho, nz,
                                                             reinterpret_cast<__nv_bfloat16*>(xo), (int)xo_ld);
     else
-      rank1_scale_lean_kernel<false><<<grid, kBlock, 0, s>>>(nullptr, 0, rpm, cols, fw_mu, fw_rho, nz.seed, nz.stream, nz.step,
+      rank1_scale_lean_kernel<false><<<grid, kBlock, 0, s>>>(nullptr, 0, rpm, cols, fw_mu, fw_rho, nz,
                                                              reinterpret_cast<__nv_bfloat16*>(f_out), (int)f_ld);
     count_launch();
     return check_launch("scale_rows(lean rank-1)");
   }
   const int g = grid_for(rows * ((cols + 3) / 4));
-  if (mode == 0) scale_rows_kernel<0><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld);
-  else if (mode == 1) scale_rows_kernel<1><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld);
-  else scale_rows_kernel<2><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld);
+  if (mode == 0) scale_rows_kernel<0><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld, fo);
+  else if (mode == 1) scale_rows_kernel<1><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld, fo);
+  else scale_rows_kernel<2><<<g, kBlock, 0, s>>>(x, dt, x_ld, rows, cols, rpm, fw_mu, fw_rho, nz, xo, xo_ld, f_out, f_ld, fo);
   count_launch();
   return check_launch("scale_rows");
 }
@@ -1225,7 +1255,9 @@ int k_bwd_out(const BwdOutArgs& a_in, cudaStream_t s) {
   if (a.d_fast_mu) cudaMemsetAsync(a.d_fast_mu, 0, bytes, s);
   if (a.d_fast_rho) cudaMemsetAsync(a.d_fast_rho, 0, bytes, s);
   if (a.dbias) cudaMemsetAsync(a.dbias, 0, bytes, s);
-  if (a.fast == 2 && a.dt == kBF16 && a.rho_s != nullptr && a.eps_s.injected == nullptr && a.cols % 8 == 0 &&
+  if (a.d_bias_rho) cudaMemsetAsync(a.d_bias_rho, 0, bytes, s);
+  const bool default_opts = a.opts.clip_lo == -kClip && a.opts.clip_hi == kClip && !a.opts.additive && a.rho_b == nullptr;
+  if (default_opts && a.fast == 2 && a.dt == kBF16 && a.rho_s != nullptr && a.eps_s.injected == nullptr && a.cols % 8 == 0 &&
       a.gy_ld % 8 == 0 && a.y_ld % 8 == 0 && a.z_ld % 8 == 0 && a.s_ld % 8 == 0 && a.dz_ld % 8 == 0 && al16(a.gy) &&
       al16(a.y) && al16(a.z) && al16(a.s_buf) && al16(a.dz) && al16(a.mu_s) && al16(a.rho_s) && a.d_fast_mu != nullptr) {
     const int lchunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
@@ -1254,7 +1286,8 @@ int k_bwd_in(const BwdInArgs& a_in, cudaStream_t s) {
   const size_t bytes = sizeof(float) * (size_t)members * a.cols;
   if (a.d_fast_mu) cudaMemsetAsync(a.d_fast_mu, 0, bytes, s);
   if (a.d_fast_rho) cudaMemsetAsync(a.d_fast_rho, 0, bytes, s);
-  if (a.fast == 2 && a.dt == kBF16 && a.fw_rho != nullptr && a.eps.injected == nullptr && a.cols % 8 == 0 &&
+  const bool default_opts = a.opts.clip_lo == -kClip && a.opts.clip_hi == kClip && !a.opts.additive;
+  if (default_opts && a.fast == 2 && a.dt == kBF16 && a.fw_rho != nullptr && a.eps.injected == nullptr && a.cols % 8 == 0 &&
       a.dxf_ld % 8 == 0 && a.x_ld % 8 == 0 && (a.dx == nullptr || (a.dx_ld % 8 == 0 && al16(a.dx))) && al16(a.dxf) &&
       al16(a.x) && al16(a.fw_mu) && al16(a.fw_rho) && a.d_fast_mu != nullptr) {
     const int lchunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;

@@ -41,15 +41,23 @@ int k_normal_grad_finish_any(const void* dw, int dw_dt, const float* mu, const f
 // mode 1: per-example sampled fast weight clip(fw_mu[e] + softplus(fw_rho[e])*eps[b], -10, 10) (rank-1)
 // mode 2: per-example sign noise (Flipout sign_input)
 // s_out (optional, modes 0/1): the factor itself written as a [rows][cols] tensor in dt (rank-1 `s`).
+// opts: clip bounds of the sampled factor (mode 1; edward2/tensorflow/layers/dense.py:1108-1110) and the additive
+// variant xo = x + f (dense.py:1126-1127).
+struct FastOpts {
+  float clip_lo = -10.f, clip_hi = 10.f;
+  int additive = 0;
+};
 int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols, int rows_per_member, int mode,
                  const float* fw_mu, const float* fw_rho, Noise nz, void* xo, long long xo_ld, void* f_out,
-                 long long f_ld, cudaStream_t s);
+                 long long f_ld, cudaStream_t s, FastOpts opts = FastOpts());
 
 // ---- backward preparation on the output side of a layer:
 //   gp = gy ∘ act'(y)
 //   plain (fast == 0): dz = gp                   dbias[n]    = Σ_m gp
 //   BE    (fast == 1): dz = gp ∘ gamma[e]        dgamma[e,n] = Σ gp ∘ z     dbias[e,n] = Σ gp
-//   rank1 (fast == 2): dz = gp ∘ s[b,n]          dmu_s[e,n]  = Σ gp∘z∘1[|s_raw|<=10]   drho_s likewise ∘ eps ∘ sigmoid(rho)
+//   rank1 (fast == 2): dz = gp ∘ s[b,n]          dmu_s[e,n]  = Σ gp∘z∘1[lo<=s_raw<=hi]   drho_s likewise ∘ eps ∘ sigmoid(rho)
+//        additive:     dz = gp                   dmu_s[e,n]  = Σ gp∘1[lo<=s_raw<=hi]
+//        sampled bias (rho_b != nullptr): d_bias_rho[e,n] = Σ gp ∘ eps_b ∘ sigmoid(rho_b)   (dbias = Σ gp is d mu_b)
 //   flipout (fast == 3): dz = gp,  dz2 = gp ∘ T[b,n]   dbias[n] = Σ gp
 struct BwdOutArgs {
   int dt;
@@ -64,6 +72,8 @@ struct BwdOutArgs {
   const void* s_buf; long long s_ld;
   const float* gamma;           // BE
   const float* mu_s; const float* rho_s; Noise eps_s;  // rank-1
+  FastOpts opts;                                       // rank-1 clip bounds / additive variant
+  const float* rho_b; Noise eps_b; float* d_bias_rho;  // rank-1 per-example sampled bias (dense.py:1131-1139)
   Noise sign_out;               // flipout (injected fp32 or philox sign)
   void* dz; long long dz_ld;
   void* dz2; long long dz2_ld;
@@ -85,6 +95,7 @@ struct BwdInArgs {
   const void* dxf; long long dxf_ld;
   const void* x; long long x_ld;
   const float* fw_mu; const float* fw_rho; Noise eps;
+  FastOpts opts;
   void* dx; long long dx_ld;  // may be nullptr
   float* d_fast_mu; float* d_fast_rho;
 };

@@ -115,7 +115,24 @@ struct Noise {
   uint64_t seed;
   uint64_t stream;
   const uint64_t* step;   // optional device counter: key = seed + step[0] * 0x9E3779B97F4A7C15 (CUDA-graph replays)
+  // Row mapping of a per-example noise tensor [rows][cols] under data parallelism (ed2_noise in include/ed2b200.h):
+  // local row m is row noise_row(m) of the GLOBAL batch, so the draw depends on the global row only.
+  long long row0;
+  int rpg_local;   // rows per group (ensemble member) held locally; 0 = ungrouped
+  int rpg_global;  // rows per group in the global batch
 };
+
+__host__ __device__ __forceinline__ long long noise_row(const Noise& nz, long long m) {
+  if (nz.rpg_local > 0) {
+    const long long g = m / nz.rpg_local;
+    return m + g * static_cast<long long>(nz.rpg_global - nz.rpg_local) + nz.row0;
+  }
+  return m + nz.row0;
+}
+// flat element index of (local row m, column c) of a [rows][cols] noise tensor: injected tensors are indexed locally
+__host__ __device__ __forceinline__ long long noise_idx(const Noise& nz, long long m, long long cols, long long c) {
+  return (nz.injected != nullptr ? m : noise_row(nz, m)) * cols + c;
+}
 
 __device__ __forceinline__ uint64_t noise_key(const Noise& nz) {
   return nz.step != nullptr ? nz.seed + __ldg(reinterpret_cast<const unsigned long long*>(nz.step)) * 0x9E3779B97F4A7C15ull

@@ -34,8 +34,49 @@ def member_major_unshard(parts, ensemble_size: int) -> torch.Tensor:
 
 
 def global_row_offset(rank: int, rows_per_rank: int) -> int:
-    """Philox offsets are functions of the GLOBAL row index so results do not depend on the number of ranks."""
+    """First global row (within a member's block) of the rows a rank holds: Philox offsets are functions of the GLOBAL
+    row index so results do not depend on the number of ranks (used by Layer._row_map)."""
     return rank * rows_per_rank
+
+
+def shard_noise(module, rank: int | None = None, world: int | None = None, group=None):
+    """Tell every layer under `module` which slice of the global batch this process holds (the member_major_shard
+    layout: rows [rank * n/world, (rank + 1) * n/world) of every ensemble member; for layers without members, of the
+    whole batch).  From then on the per-example noise tensors of DenseRank1 (eps_alpha / eps_gamma / eps_bias) and
+    DenseFlipout (sign_input / sign_output) are drawn for the GLOBAL row — ed2_noise.row0 / rows_per_group_* — so
+    `world` ranks reproduce the single-device global-batch draw bit for bit.  Per-weight noise (one eps per kernel
+    element) is identical on every rank by construction.  Also sets a common Philox seed discipline check: the layers'
+    seeds must be equal across ranks (they derive from construction order); verified here when a process group exists."""
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    from .layers.base import Layer
+
+    layers = [m for m in module.modules() if isinstance(m, Layer)]
+    for m in layers:
+        m.data_shard = (int(rank), int(world))
+    if dist.is_initialized() and dist.get_world_size(group) > 1 and layers:
+        check_noise_keys(layers, group)
+    return module
+
+
+def check_noise_keys(layers, group=None):
+    """Raise if the (seed, call count) pairs that key the layers' Philox streams differ between ranks: the raw-dW
+    exchange finishes drho = dW_sum∘eps∘sigmoid(rho) locally and is only correct when every rank drew the same eps."""
+    keys = [(m.seed & 0x7FFFFFFFFFFFFFFF, m._calls) for m in layers]
+    flat = torch.tensor([v for k in keys for v in k], dtype=torch.int64)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    lo, hi = flat.to(dev), flat.to(dev)
+    lo, hi = lo.clone(), hi.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if not torch.equal(lo, hi):
+        bad = [layers[i // 2].layer_name for i in torch.nonzero(lo != hi).flatten().tolist()]
+        raise RuntimeError(f"Philox keys differ across data-parallel ranks for layers {sorted(set(bad))}: build the "
+                           f"model identically on every rank and call it the same number of times (or pass a shared "
+                           f"step_counter)")
 
 
 class PeerArena:

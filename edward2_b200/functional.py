@@ -54,13 +54,15 @@ class Randomness:
     """A noise tensor: injected values (parity tests) or a Philox (seed, stream) pair."""
 
     def __init__(self, injected: torch.Tensor | None = None, seed: int = 0, stream: int = 0,
-                 step: torch.Tensor | None = None):
+                 step: torch.Tensor | None = None, rows: tuple[int, int, int] | None = None):
         self.injected = None if injected is None else injected.to(torch.float32).contiguous()
         self.seed, self.stream = int(seed), int(stream)
         self.step = step  # int64 device scalar folded into the Philox key (see ed2_noise.step)
+        # data-parallel row mapping of a PER-EXAMPLE noise tensor: (row0, rows_per_group_local, rows_per_group_global)
+        self.rows = rows
 
     def c(self) -> _lib.Noise:
-        return _lib.noise(self.injected, self.seed, self.stream, self.step)
+        return _lib.noise(self.injected, self.seed, self.stream, self.step, self.rows)
 
 
 # ------------------------------------------------------------------------------------------------- BatchEnsemble
@@ -118,7 +120,10 @@ class BatchEnsembleDense(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------- Rank-1
 class Rank1Dense(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, kernel, mu_r, rho_r, mu_s, rho_s, bias, act, ensemble_size, dtype, eps_r, eps_s):
+    def forward(ctx, x, kernel, mu_r, rho_r, mu_s, rho_s, bias, act, ensemble_size, dtype, eps_r, eps_s,
+                additive=False, clip=(-10.0, 10.0), rho_b=None, eps_b=None):
+        """additive: (x + r) W + s (dense.py:1126-1127); clip: (min, max)_perturbation_value (dense.py:1108-1110);
+        rho_b / eps_b: per-example sampled ensemble bias, `bias` being its mean (dense.py:1131-1139)."""
         lib = _lib.load()
         B, I = x.shape
         O = kernel.shape[1]
@@ -128,7 +133,12 @@ class Rank1Dense(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         y, xr, s_buf = _new(B, O, dtype, dev), _new(B, I, dtype, dev), _new(B, O, dtype, dev)
         z = _new(B, O, dtype, dev) if need_grad else None
+        bias_buf = _new(B, O, dtype, dev) if rho_b is not None else None
         a = _lib.Rank1Fwd()
+        a.additive, a.clip_lo, a.clip_hi = int(bool(additive)), float(clip[0]), float(clip[1])
+        if rho_b is not None:
+            a.rho_b, a.eps_b = rho_b.data_ptr(), eps_b.c()
+            a.bias_buf, a.bias_ld = bias_buf.data_ptr(), _lib.ld(bias_buf)
         a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), B, I, O, ensemble_size, act
         a.x, a.x_ld, a.w_lp, a.w_ld = xc.data_ptr(), _lib.ld(xc), w_lp.data_ptr(), _lib.ld(w_lp)
         a.mu_r, a.rho_r, a.eps_r = mu_r.data_ptr(), _p(rho_r), eps_r.c()
@@ -144,8 +154,11 @@ class Rank1Dense(torch.autograd.Function):
                 saved.append(rho_r)
             if rho_s is not None:
                 saved.append(rho_s)
+            if rho_b is not None:
+                saved.append(rho_b)
             ctx.save_for_backward(*saved)
             ctx.meta = (act, ensemble_size, dtype, bias is not None, x.dtype, eps_r, eps_s)
+            ctx.opts = (bool(additive), (float(clip[0]), float(clip[1])), rho_b is not None, eps_b)
         return y
 
     @staticmethod
@@ -156,6 +169,8 @@ class Rank1Dense(torch.autograd.Function):
         rest = saved[8:]
         rho_r = rest.pop(0) if ctx.has_rho[0] else None
         rho_s = rest.pop(0) if ctx.has_rho[1] else None
+        additive, clip, has_rho_b, eps_b = ctx.opts
+        rho_b = rest.pop(0) if has_rho_b else None
         act, E, dtype, has_bias, x_dtype, eps_r, eps_s = ctx.meta
         B, I = xc.shape
         O = y.shape[1]
@@ -169,7 +184,11 @@ class Rank1Dense(torch.autograd.Function):
         drho_r = torch.empty(E, I, **f32) if rho_r is not None else None
         drho_s = torch.empty(E, O, **f32) if rho_s is not None else None
         dbias = torch.empty(E, O, **f32) if has_bias else None
+        drho_b = torch.empty(E, O, **f32) if rho_b is not None else None
         a = _lib.Rank1Bwd()
+        a.additive, a.clip_lo, a.clip_hi = int(additive), clip[0], clip[1]
+        if rho_b is not None:
+            a.rho_b, a.eps_b, a.drho_b = rho_b.data_ptr(), eps_b.c(), drho_b.data_ptr()
         a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), B, I, O, E, act
         a.gy, a.gy_ld, a.y, a.y_ld, a.z, a.z_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y), z.data_ptr(), _lib.ld(z)
         a.x, a.x_ld, a.xr, a.xr_ld = xc.data_ptr(), _lib.ld(xc), xr.data_ptr(), _lib.ld(xr)
@@ -181,7 +200,7 @@ class Rank1Dense(torch.autograd.Function):
         _lib.check(lib.ed2_rank1_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_rank1_dense_bwd")
         if dx is not None and dx.dtype != x_dtype:
             dx = dx.to(x_dtype)
-        return dx, dw, dmu_r, drho_r, dmu_s, drho_s, dbias, None, None, None, None, None
+        return dx, dw, dmu_r, drho_r, dmu_s, drho_s, dbias, None, None, None, None, None, None, None, drho_b, None
 
 
 class GradSync:
@@ -199,14 +218,26 @@ class GradSync:
 class ReluLink:
     """Cross-layer fusion token.  A layer whose fused activation is ReLU attaches one to its output tensor; the layer
     that consumes that tensor applies relu'(x) = (x > 0) and the bias-gradient column sums in its own dX GEMM epilogue
-    and records the result here, so the producing layer's backward can skip its output-side pass.  Matching is by the
-    gradient tensor's data pointer: anything else (fan-out, intermediate ops, dtype casts) falls back to the unfused
-    path, which is always correct because the ReLU mask is idempotent."""
+    and records the result here, so the producing layer's backward can skip its output-side pass.  The producer takes
+    the shortcut only when the gradient it receives IS the recorded tensor, unmodified: same storage, same shape and
+    the same version counter.  The link keeps a reference to that tensor, so autograd can never accumulate a second
+    consumer's gradient into it in place (its input buffer only steals tensors nobody else holds) — with fan-out
+    (residual / skip connections) the sum is a new tensor and the unfused path runs, which is always correct because
+    the ReLU mask is idempotent."""
 
-    __slots__ = ("dx_ptr", "dbias")
+    __slots__ = ("dx", "dx_version", "dbias", "fused")
 
     def __init__(self):
-        self.dx_ptr, self.dbias = None, None
+        self.dx, self.dx_version, self.dbias = None, None, None
+        self.fused = False  # set when the producer's backward took the shortcut (tests / diagnostics)
+
+    def record(self, dx, dbias):
+        self.dx, self.dx_version, self.dbias = dx, dx._version, dbias
+
+    def matches(self, gy, shape) -> bool:
+        d = self.dx
+        return (d is not None and gy.data_ptr() == d.data_ptr() and gy.shape == d.shape == shape
+                and gy.dtype == d.dtype and gy._version == self.dx_version and d._version == self.dx_version)
 
 
 def take_link(t: torch.Tensor):
@@ -274,8 +305,9 @@ class ReparamDense(torch.autograd.Function):
         if gy is None:
             gy = torch.zeros(B, O, dtype=dtype, device=dev)
         gyc = as_compute(gy, dtype)
-        premasked = (out_link is not None and out_link.dx_ptr is not None and out_link.dx_ptr == gyc.data_ptr()
-                     and gyc.shape == y.shape)
+        premasked = out_link is not None and out_link.matches(gyc, y.shape)
+        if out_link is not None:
+            out_link.fused = premasked
         gp = None if premasked else _new(B, O, dtype, dev)
         need_dx = ctx.needs_input_grad[0]
         dx = _new(B, I, dtype, dev) if need_dx else None
@@ -371,7 +403,9 @@ class ReparamDense(torch.autograd.Function):
             deferred = False
         _lib.check(lib.ed2_reparam_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_reparam_dense_bwd")
         if fuse_prev:
-            in_link.dx_ptr, in_link.dbias = dx.data_ptr(), prev_dbias
+            in_link.record(dx, prev_dbias)
+        if out_link is not None:
+            out_link.dx = None  # consumed (or not applicable): drop the reference
         if dx is not None and dx.dtype != x_dtype:
             dx = dx.to(x_dtype)
         if deferred:  # mean / stddev gradients are installed by the reducer after the all-reduce

@@ -121,6 +121,19 @@ class HeNormal(Initializer):
         return _truncated_normal(shape, 0.0, std, _gen(self.seed))
 
 
+class GlorotNormal(Initializer):
+    """tf.keras.initializers.GlorotNormal: truncated normal with stddev sqrt(2 / (fan_in + fan_out)) (variance-
+    corrected for the +-2 sigma truncation, as Keras does)."""
+
+    def __init__(self, seed=None):
+        self.seed = seed
+
+    def __call__(self, shape, dtype=None):
+        fi, fo = _fans(shape)
+        std = math.sqrt(2.0 / (fi + fo)) / 0.87962566103423978
+        return _truncated_normal(shape, 0.0, std, _gen(self.seed))
+
+
 class RandomSign(Initializer):
     """+-1 with P(+1) = probs (edward2/tensorflow/initializers.py:667-694; jax/nn/utils.py:28-51)."""
 
@@ -240,19 +253,25 @@ class TrainableNormal(TrainableInitializer):
 
 
 class TrainableHeNormal(TrainableNormal):
-    """initializers.py:531-560: stddev initialised so that sigma = sqrt(2 / fan_in)."""
+    """initializers.py:531-560: mean ~ he_normal(seed); stddev keeps the TrainableNormal default TruncN(-3, 0.1)."""
 
-    def build(self, shape, device=None):
-        fi, _ = _fans(shape)
-        self.stddev_initializer = Constant(_softplus_inverse(math.sqrt(2.0 / fi)))
-        super().build(shape, device)
+    def __init__(self, seed=None, **kwargs):
+        kwargs.pop("mean_initializer", None)
+        super().__init__(mean_initializer=HeNormal(seed), seed=seed, **kwargs)
+
+    def get_config(self):
+        return {"seed": self.seed}
 
 
 class TrainableGlorotNormal(TrainableNormal):
-    def build(self, shape, device=None):
-        fi, fo = _fans(shape)
-        self.stddev_initializer = Constant(_softplus_inverse(math.sqrt(2.0 / (fi + fo))))
-        super().build(shape, device)
+    """initializers.py:563-590: mean ~ GlorotNormal(seed); stddev keeps the TrainableNormal default."""
+
+    def __init__(self, seed=None, **kwargs):
+        kwargs.pop("mean_initializer", None)
+        super().__init__(mean_initializer=GlorotNormal(seed), seed=seed, **kwargs)
+
+    def get_config(self):
+        return {"seed": self.seed}
 
 
 def _softplus_inverse(y):
@@ -261,7 +280,7 @@ def _softplus_inverse(y):
 
 _ALIASES = {
     "zeros": Zeros, "zero": Zeros, "ones": Ones, "one": Ones,
-    "glorot_uniform": GlorotUniform, "he_normal": HeNormal,
+    "glorot_uniform": GlorotUniform, "glorot_normal": GlorotNormal, "he_normal": HeNormal,
     "random_normal": RandomNormal, "normal": RandomNormal, "random_uniform": RandomUniform,
     "truncated_normal": TruncatedNormal, "orthogonal": Orthogonal,
     "random_sign": RandomSign, "orthogonal_random_features": OrthogonalRandomFeatures,

@@ -41,6 +41,10 @@ class Layer(nn.Module):
         self._injected = {}
         self._extra_losses = []
         self.step_counter = None  # optional int64 device scalar advanced by the caller once per step
+        # Data-parallel placement of this process's batch rows (edward2_b200.dist.shard_noise sets it on every layer):
+        # (rank, world).  Per-example noise is then drawn for the GLOBAL row, so the sharded run reproduces the
+        # single-device global-batch draw.
+        self.data_shard = None
 
     # -- Keras surface -------------------------------------------------------------------------------------
     def build(self, input_shape):
@@ -71,15 +75,27 @@ class Layer(nn.Module):
         self._injected = dict(noise)
         return self
 
-    def _noise(self, name: str, stream: int):
+    def _row_map(self, per_example):
+        """ed2_noise row mapping of a per-example noise tensor whose local groups hold `per_example` rows each (one
+        group = one ensemble member; ungrouped layers pass the local batch): with data_shard = (rank, world) this
+        process holds rows [rank * per_example, (rank + 1) * per_example) of every group of the global batch."""
+        if per_example is None or self.data_shard is None:
+            return None
+        rank, world = self.data_shard
+        if world <= 1:
+            return None
+        return (rank * per_example, per_example, per_example * world)
+
+    def _noise(self, name: str, stream: int, per_example: int | None = None):
         from .. import functional as F
 
         if name in self._injected and self._injected[name] is not None:
             return F.Randomness(self._injected[name])
+        rows = self._row_map(per_example)
         if self.step_counter is not None:  # device-side step: fresh noise on every CUDA-graph replay
-            return F.Randomness(seed=self.seed, stream=stream, step=self.step_counter)
+            return F.Randomness(seed=self.seed, stream=stream, step=self.step_counter, rows=rows)
         key = (self.seed + self._calls * GOLDEN) & MASK64
-        return F.Randomness(seed=key, stream=stream)
+        return F.Randomness(seed=key, stream=stream, rows=rows)
 
 
 def flatten_batch(x: torch.Tensor):

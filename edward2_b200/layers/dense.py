@@ -14,7 +14,7 @@ from .. import constraints, functional as F, initializers, ops, regularizers
 from .base import Layer, flatten_batch
 
 # Philox stream ids of the noise tensors of one layer call
-S_KERNEL, S_BIAS, S_SIGN_IN, S_SIGN_OUT, S_R, S_S = 0, 1, 2, 3, 4, 5
+S_KERNEL, S_BIAS, S_SIGN_IN, S_SIGN_OUT, S_R, S_S, S_B = 0, 1, 2, 3, 4, 5, 6
 
 
 def _is_trainable(init) -> bool:
@@ -253,7 +253,8 @@ class DenseFlipout(DenseReparameterization):
         bias = self._bias_value()
         kl_scale, pm, ps = self._fused_kl_args()
         y, kl = F.FlipoutDense.apply(x, mean, rho, bias, self._act, self.compute_dtype, self._noise("eps", S_KERNEL),
-                                     self._noise("sign_input", S_SIGN_IN), self._noise("sign_output", S_SIGN_OUT),
+                                     self._noise("sign_input", S_SIGN_IN, per_example=x.shape[0]),
+                                     self._noise("sign_output", S_SIGN_OUT, per_example=x.shape[0]),
                                      kl_scale, pm, ps)
         if kl_scale != 0.0:
             self._kl.set(kl, mean, rho)
@@ -331,10 +332,11 @@ class DenseRank1(Layer):
                  gamma_constraint=None, kernel_constraint=None, bias_constraint=None, use_additive_perturbation=False,
                  min_perturbation_value=-10, max_perturbation_value=10, ensemble_size=1, **kwargs):
         super().__init__(**kwargs)
-        if use_additive_perturbation:
-            raise NotImplementedError("additive perturbations (dense.py:1126-1127) are not built yet")
-        if (min_perturbation_value, max_perturbation_value) != (-10, 10):
-            raise NotImplementedError("the fused kernels clip at the reference defaults [-10, 10]")
+        if not float(min_perturbation_value) < float(max_perturbation_value):
+            raise ValueError("min_perturbation_value must be below max_perturbation_value")
+        self.use_additive_perturbation = bool(use_additive_perturbation)
+        self.min_perturbation_value = min_perturbation_value
+        self.max_perturbation_value = max_perturbation_value
         self.units, self.ensemble_size = int(units), int(ensemble_size)
         self.ensemble_activation = activation
         self._act = ops.act_id(activation)
@@ -343,8 +345,6 @@ class DenseRank1(Layer):
         self.gamma_initializer = initializers.get(gamma_initializer)
         self.kernel_initializer = initializers.get(kernel_initializer)
         self.ensemble_bias_initializer = initializers.get(bias_initializer)
-        if _is_trainable(self.ensemble_bias_initializer):
-            raise NotImplementedError("per-example sampled ensemble bias (dense.py:1131-1139) is not built yet")
         self.alpha_regularizer = regularizers.get(alpha_regularizer)
         self.gamma_regularizer = regularizers.get(gamma_regularizer)
         self.kernel_regularizer = regularizers.get(kernel_regularizer)
@@ -356,7 +356,7 @@ class DenseRank1(Layer):
         self.kernel = nn.Parameter(self.kernel_initializer((in_dim, self.units)).to(dev))
         self.alpha = _make_weight(self, "alpha", (E, in_dim), self.alpha_initializer, dev)
         self.gamma = _make_weight(self, "gamma", (E, self.units), self.gamma_initializer, dev)
-        self.ensemble_bias = (nn.Parameter(self.ensemble_bias_initializer((E, self.units)).to(dev))
+        self.ensemble_bias = (_make_weight(self, "ensemble_bias", (E, self.units), self.ensemble_bias_initializer, dev)
                               if self.use_ensemble_bias else None)
         self.built = True
 
@@ -370,9 +370,16 @@ class DenseRank1(Layer):
             raise ValueError(f"batch size {inputs.shape[0]} is not divisible by ensemble_size {self.ensemble_size}")
         mu_r, rho_r = self._fast(self.alpha_initializer, self.alpha)
         mu_s, rho_s = self._fast(self.gamma_initializer, self.gamma)
-        return F.Rank1Dense.apply(inputs, self.kernel, mu_r, rho_r, mu_s, rho_s, self.ensemble_bias, self._act,
-                                  self.ensemble_size, self.compute_dtype, self._noise("eps_alpha", S_R),
-                                  self._noise("eps_gamma", S_S))
+        bias, rho_b = (self._fast(self.ensemble_bias_initializer, self.ensemble_bias)
+                       if self.use_ensemble_bias else (None, None))
+        per = inputs.shape[0] // self.ensemble_size
+        return F.Rank1Dense.apply(inputs, self.kernel, mu_r, rho_r, mu_s, rho_s, bias, self._act,
+                                  self.ensemble_size, self.compute_dtype,
+                                  self._noise("eps_alpha", S_R, per_example=per),
+                                  self._noise("eps_gamma", S_S, per_example=per),
+                                  self.use_additive_perturbation,
+                                  (self.min_perturbation_value, self.max_perturbation_value), rho_b,
+                                  self._noise("eps_bias", S_B, per_example=per) if rho_b is not None else None)
 
     @property
     def losses(self):
@@ -383,8 +390,9 @@ class DenseRank1(Layer):
             out.append(self.gamma_regularizer(self.gamma_initializer))
         if self.kernel_regularizer is not None:
             out.append(self.kernel_regularizer(self.kernel))
-        if self.ensemble_bias_regularizer is not None and self.ensemble_bias is not None:
-            out.append(self.ensemble_bias_regularizer(self.ensemble_bias))
+        if self.ensemble_bias_regularizer is not None and self.use_ensemble_bias:
+            out.append(self.ensemble_bias_regularizer(
+                self.ensemble_bias_initializer if _is_trainable(self.ensemble_bias_initializer) else self.ensemble_bias))
         return out
 
     def get_config(self):
@@ -393,6 +401,11 @@ class DenseRank1(Layer):
                    use_ensemble_bias=self.use_ensemble_bias,
                    alpha_initializer=initializers.serialize(self.alpha_initializer),
                    gamma_initializer=initializers.serialize(self.gamma_initializer),
+                   ensemble_bias_initializer=initializers.serialize(self.ensemble_bias_initializer),
                    alpha_regularizer=regularizers.serialize(self.alpha_regularizer),
-                   gamma_regularizer=regularizers.serialize(self.gamma_regularizer))
+                   gamma_regularizer=regularizers.serialize(self.gamma_regularizer),
+                   ensemble_bias_regularizer=regularizers.serialize(self.ensemble_bias_regularizer),
+                   use_additive_perturbation=self.use_additive_perturbation,
+                   min_perturbation_value=self.min_perturbation_value,
+                   max_perturbation_value=self.max_perturbation_value)
         return cfg

@@ -49,13 +49,27 @@ class LaplaceRandomFeatureCovariance(Layer):
         self.register_buffer("covariance_matrix", torch.zeros(d, d, dtype=torch.float32, device=dev))
         self.register_buffer("if_update_covariance", torch.zeros((), dtype=torch.bool, device=dev))
         self._needs_inverse = False  # host mirror of if_update_covariance (avoids a device sync per call)
-        self._cov_lp = None
+        self._flag_version = self.if_update_covariance._version
+        self._cov_lp, self._cov_lp_version = None, None
         self._deferred = None
         if self.data_parallel == "deferred":
             from ..dist import DeferredSum
 
             self._deferred = DeferredSum(self.precision_matrix)
         self.built = True
+
+    def _set_flag(self, value: bool):
+        self._needs_inverse = value
+        self.if_update_covariance.fill_(value)
+        self._flag_version = self.if_update_covariance._version
+
+    def _sync_flag(self):
+        """`if_update_covariance` written from outside (load_state_dict / checkpoint.load_reference_variables copy_
+        into the buffer and bump its version): re-derive the host mirror from the restored value — one device read,
+        only on that occasion."""
+        if self.if_update_covariance._version != self._flag_version:
+            self._needs_inverse = bool(self.if_update_covariance.item())
+            self._flag_version = self.if_update_covariance._version
 
     def synchronize_precision(self):
         """Collective no-op unless `data_parallel="deferred"` accumulated rank-local updates: sums them over ranks."""
@@ -107,20 +121,39 @@ class LaplaceRandomFeatureCovariance(Layer):
     def update_feature_covariance_matrix(self):
         """random_feature.py:435-459.  The D^3 inverse is a library call (torch.linalg.inv), outside the measured
         path."""
+        self._sync_flag()
         if self._needs_inverse:
             self.synchronize_precision()
-            d = self.precision_matrix.shape[0]
-            eye = torch.eye(d, dtype=torch.float32, device=self.precision_matrix.device)
-            self.covariance_matrix.copy_(torch.linalg.inv(self.ridge_penalty * eye + self.precision_matrix))
-            self._cov_lp = None
+            a = self.precision_matrix.clone()
+            a.diagonal().add_(self.ridge_penalty)
+            self.covariance_matrix.copy_(torch.linalg.inv(a))
         return self.covariance_matrix
 
     def _covariance_lp(self):
         if self.compute_dtype == torch.float32:
             return self.covariance_matrix
-        if self._cov_lp is None:
+        # keyed on the buffer's version: the inverse above, load_state_dict and any other in-place write bump it
+        if self._cov_lp is None or self._cov_lp_version != self.covariance_matrix._version:
             self._cov_lp = ops.cast(self.covariance_matrix, self.compute_dtype)
+            self._cov_lp_version = self.covariance_matrix._version
         return self._cov_lp
+
+    _EYE_CACHE = {}
+
+    @classmethod
+    def _identity(cls, n, device):
+        """random_feature.py:531 returns tf.eye(batch_size) from every training call.  The matrix is constant: a dense
+        copy is cached per (n, device) up to 1 GiB (no per-step write of B*B*4 bytes); beyond that (B = 65536 would be
+        17 GB, SURVEY.md §7 hard part 9) a sparse COO identity with the same shape / dtype is returned."""
+        key = (int(n), str(device))
+        if key not in cls._EYE_CACHE:
+            if 4 * n * n <= (1 << 30):
+                cls._EYE_CACHE[key] = torch.eye(n, dtype=torch.float32, device=device)
+            else:
+                idx = torch.arange(n, device=device)
+                cls._EYE_CACHE[key] = torch.sparse_coo_tensor(torch.stack([idx, idx]), torch.ones(n, device=device),
+                                                              (n, n)).coalesce()
+        return cls._EYE_CACHE[key]
 
     def compute_predictive_covariance(self, gp_feature):
         """random_feature.py:461-485: Φ (Σ Φᵀ ridge), full [B, B] — two GEMMs."""
@@ -135,8 +168,8 @@ class LaplaceRandomFeatureCovariance(Layer):
         """diag of compute_predictive_covariance without forming [B, B] (one GEMM with a row-sum epilogue), with
         optional fused mean-field logits.  Returns (variance [B], adjusted logits or None)."""
         self.update_feature_covariance_matrix()
-        self._needs_inverse = False
-        self.if_update_covariance.fill_(False)
+        if self._needs_inverse:
+            self._set_flag(False)
         phi = F.as_compute(gp_feature.detach(), self.compute_dtype)
         lk = 1 if likelihood == "poisson" else 0
         return ops.predictive_variance(phi, self._covariance_lp(), self.ridge_penalty, logits, mean_field_factor, lk)
@@ -153,13 +186,12 @@ class LaplaceRandomFeatureCovariance(Layer):
         training = self._get_training_value(training)
         if training:
             self.update_feature_precision_matrix(gp_feature=inputs, logits=logits)
-            self._needs_inverse = True
-            self.if_update_covariance.fill_(True)
-            # random_feature.py:531 returns tf.eye(batch_size): materialised here too (B*B*4 bytes)
-            return torch.eye(batch_size, dtype=torch.float32, device=inputs.device)
+            if not self._needs_inverse or self.if_update_covariance._version != self._flag_version:
+                self._set_flag(True)
+            return self._identity(batch_size, inputs.device)
         self.update_feature_covariance_matrix()
-        self._needs_inverse = False
-        self.if_update_covariance.fill_(False)
+        if self._needs_inverse:
+            self._set_flag(False)
         return self.compute_predictive_covariance(gp_feature=inputs)
 
     def get_config(self):
@@ -213,8 +245,12 @@ class _RandomFeature(Layer):
         self._refresh()
         self.built = True
 
+    def _cache_key(self):
+        return (self.kernel.data_ptr(), self.kernel._version, self.kernel.dtype)
+
     def _refresh(self):
         k = self.kernel
+        self._key = self._cache_key()
         d = k.shape[0]
         nsplit = {"extended": 2, "extended3": 3, "native": 0}[self.phase_precision]
         # the exact-fp32 FFMA path is kept for small fp32 problems; split operands need a pitch multiple of 8
@@ -232,6 +268,8 @@ class _RandomFeature(Layer):
             self._wt = kt if self.compute_dtype == torch.float32 else ops.cast(kt, self.compute_dtype)
 
     def call(self, inputs):
+        if self._key != self._cache_key():  # kernel restored from a checkpoint: rebuild the operand copies
+            self._refresh()
         return F.RandomFourierFeatures.apply(inputs, self._wt, self._w, self.bias, self.scale, self.compute_dtype,
                                              self.compute_dtype, self._nsplit)
 

@@ -49,6 +49,17 @@ typedef struct {
   uint64_t stream;
   const uint64_t* step;  /* optional DEVICE counter folded into the key: seed + step[0] * 0x9E3779B97F4A7C15, so a
                             captured CUDA graph draws fresh noise on every replay */
+  /* Row mapping of PER-EXAMPLE noise tensors [rows][cols] (rank-1 eps_r / eps_s / eps_b, Flipout sign_in / sign_out)
+   * under data parallelism: the Philox element index of local (row m, column c) is global_row(m) * cols + c with
+   *   global_row(m) = m + row0                                                     (rows_per_group_local == 0)
+   *   global_row(m) = g * rows_per_group_global + row0 + (m - g * rows_per_group_local),  g = m / rows_per_group_local
+   * so that a rank holding rows [row0, row0 + n_local) of every ensemble member (member-major layout,
+   * edward2/tensorflow/layers/dense.py:572-573, 1101-1102) draws exactly the noise the single-device global batch
+   * would draw for those rows.  All zero = identity (single device, and every per-weight noise tensor).  Injected
+   * tensors are always indexed by the LOCAL row. */
+  long long row0;
+  int rows_per_group_local;
+  int rows_per_group_global;
 } ed2_noise;
 
 const char* ed2_version(void);
@@ -186,10 +197,14 @@ typedef struct {
 int ed2_be_dense_bwd(const ed2_be_bwd_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * DenseRank1 (edward2/tensorflow/layers/dense.py:1096-1144), multiplicative perturbations:
- *   r[b,:] = clip(mu_r[e] + sigma_r[e]*eps_r[b,:], -10, 10)   (per example, when sampled)
- *   y = act( ((x ∘ r) W) ∘ s + bias[e] )
- * If rho_r (rho_s) is NULL the fast weight is deterministic: r[b,:] = mu_r[e]. */
+ * DenseRank1 (edward2/tensorflow/layers/dense.py:1096-1144):
+ *   r[b,:] = clip(mu_r[e] + sigma_r[e]*eps_r[b,:], clip_lo, clip_hi)   (per example, when sampled; s likewise)
+ *   y = act( ((x ∘ r) W) ∘ s + bias )        multiplicative (default)
+ *   y = act( ((x + r) W) + s + bias )        additive != 0 (dense.py:1126-1127)
+ *   bias[b,:] = bias[e]                                       (rho_b == NULL)
+ *   bias[b,:] = bias[e] + sigma_b[e]*eps_b[b,:], unclipped    (rho_b != NULL: per-example sampled, dense.py:1131-1139)
+ * If rho_r (rho_s) is NULL the fast weight is deterministic: r[b,:] = mu_r[e].
+ * clip_lo == clip_hi == 0 selects the reference defaults [-10, 10] (dense.py:1025-1026). */
 typedef struct {
   int dtype;
   int batch, in_dim, out_dim, ensemble_size;
@@ -203,6 +218,9 @@ typedef struct {
   void* xr; int xr_ld;      /* saved x∘r */
   void* s_buf; int s_ld;    /* saved s [B][out_dim] in dtype */
   void* z; int z_ld;        /* saved (x∘r)W; may be NULL for inference */
+  int additive; float clip_lo, clip_hi;
+  const float* rho_b; ed2_noise eps_b;   /* per-example sampled bias: bias = mean [E][out_dim], rho_b [E][out_dim] */
+  void* bias_buf; int bias_ld;           /* workspace [B][out_dim] in dtype, required when rho_b != NULL */
 } ed2_rank1_fwd_args;
 int ed2_rank1_dense_fwd(const ed2_rank1_fwd_args* a, void* stream);
 
@@ -224,6 +242,8 @@ typedef struct {
   void* dx; int dx_ld;
   float* dw;
   float* dmu_r; float* drho_r; float* dmu_s; float* drho_s; float* dbias; /* drho_* / dbias may be NULL */
+  int additive; float clip_lo, clip_hi;
+  const float* rho_b; ed2_noise eps_b; float* drho_b;  /* sampled bias: dbias is d(bias mean), drho_b [E][out_dim] */
 } ed2_rank1_bwd_args;
 int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream);
 

@@ -103,9 +103,10 @@ def batch_ensemble_bwd(x, w, alpha, gamma, bias, act, gy, y_mask=None):
 
 
 # ------------------------------------------------------------------------------------------- DenseRank1
-def rank1_factors(mu, rho, eps, E):
-    """Per-example fast weights (dense.py:1105-1112): clip(mu[e] + sigma[e] * eps[b], -10, 10); rho None ->
-    deterministic broadcast (dense.py:1114).  Returns (factor [B, D], pass-through mask, eps)."""
+def rank1_factors(mu, rho, eps, E, clip=(-CLIP, CLIP)):
+    """Per-example fast weights (dense.py:1105-1112): clip(mu[e] + sigma[e] * eps[b], min, max); rho None ->
+    deterministic broadcast (dense.py:1114).  Returns (factor [B, D], pass-through mask, eps).  clip=None: unclipped
+    (the per-example ensemble bias, dense.py:1131-1137)."""
     B = eps.shape[0] if eps is not None else None
     if rho is None:
         n = B // E
@@ -115,46 +116,73 @@ def rank1_factors(mu, rho, eps, E):
     m = np.repeat(np.asarray(mu, dtype=np.float64), n, axis=0)
     s = np.repeat(stddev(rho), n, axis=0)
     raw = m + s * np.asarray(eps, dtype=np.float64)
-    mask = ((raw >= -CLIP) & (raw <= CLIP)).astype(np.float64)  # tf.clip_by_value gradient (3p)
-    return np.clip(raw, -CLIP, CLIP), mask, np.asarray(eps, dtype=np.float64)
+    if clip is None:
+        return raw, np.ones_like(raw), np.asarray(eps, dtype=np.float64)
+    lo, hi = clip
+    mask = ((raw >= lo) & (raw <= hi)).astype(np.float64)  # tf.clip_by_value gradient (3p)
+    return np.clip(raw, lo, hi), mask, np.asarray(eps, dtype=np.float64)
 
 
-def rank1_fwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias=None, act=None):
-    """edward2/tensorflow/layers/dense.py:1096-1144, multiplicative perturbations (:1128-1129).
-    eps_r [B, I] / eps_s [B, O] (ignored when the matching rho is None; pass a zeros array for the shape)."""
+def rank1_fwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias=None, act=None, additive=False, clip=(-CLIP, CLIP),
+              rho_b=None, eps_b=None):
+    """edward2/tensorflow/layers/dense.py:1096-1144: multiplicative (:1128-1129) or additive (:1126-1127)
+    perturbations, clip bounds (:1108-1110, :1118-1120), deterministic or per-example sampled bias (:1131-1139).
+    eps_r [B, I] / eps_s [B, O] / eps_b [B, O] (ignored when the matching rho is None; pass zeros for the shape)."""
     x = np.asarray(x, dtype=np.float64)
     E = mu_r.shape[0]
     n = x.shape[0] // E
-    r, _, _ = rank1_factors(mu_r, rho_r, eps_r, E)
-    s, _, _ = rank1_factors(mu_s, rho_s, eps_s, E)
-    z = (x * r) @ np.asarray(w, dtype=np.float64)
-    pre = z * s
+    r, _, _ = rank1_factors(mu_r, rho_r, eps_r, E, clip)
+    s, _, _ = rank1_factors(mu_s, rho_s, eps_s, E, clip)
+    w = np.asarray(w, dtype=np.float64)
+    if additive:
+        z = (x + r) @ w
+        pre = z + s
+    else:
+        z = (x * r) @ w
+        pre = z * s
     if bias is not None:
-        pre = pre + np.repeat(np.asarray(bias, dtype=np.float64), n, axis=0)
+        if rho_b is not None:
+            b, _, _ = rank1_factors(bias, rho_b, eps_b, E, None)
+            pre = pre + b
+        else:
+            pre = pre + np.repeat(np.asarray(bias, dtype=np.float64), n, axis=0)
     return activation(pre, act), z, r, s
 
 
-def rank1_bwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act, gy, y_mask=None):
+def rank1_bwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act, gy, y_mask=None, additive=False,
+              clip=(-CLIP, CLIP), rho_b=None, eps_b=None):
     x = np.asarray(x, dtype=np.float64)
     w = np.asarray(w, dtype=np.float64)
     E = mu_r.shape[0]
     n = x.shape[0] // E
-    y, z, r, s = rank1_fwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act)
-    _, mask_r, er = rank1_factors(mu_r, rho_r, eps_r, E)
-    _, mask_s, es = rank1_factors(mu_s, rho_s, eps_s, E)
+    y, z, r, s = rank1_fwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act, additive, clip, rho_b, eps_b)
+    _, mask_r, er = rank1_factors(mu_r, rho_r, eps_r, E, clip)
+    _, mask_s, es = rank1_factors(mu_s, rho_s, eps_s, E, clip)
     gp = activation_grad(y if y_mask is None else y_mask, np.asarray(gy, dtype=np.float64), act)
-    dz = gp * s
-    ds = gp * z * mask_s
+    if additive:
+        dz = gp
+        ds = gp * mask_s
+    else:
+        dz = gp * s
+        ds = gp * z * mask_s
     dmu_s = ds.reshape(E, n, -1).sum(1)
     drho_s = None if rho_s is None else (ds * es).reshape(E, n, -1).sum(1) * sigmoid(rho_s)
     dbias = gp.reshape(E, n, -1).sum(1)
-    dw = (x * r).T @ dz
+    drho_b = None
+    if rho_b is not None:
+        drho_b = (gp * np.asarray(eps_b, dtype=np.float64)).reshape(E, n, -1).sum(1) * sigmoid(rho_b)
     dxr = dz @ w.T
-    dx = dxr * r
-    dr = dxr * x * mask_r
+    if additive:
+        dw = (x + r).T @ dz
+        dx = dxr
+        dr = dxr * mask_r
+    else:
+        dw = (x * r).T @ dz
+        dx = dxr * r
+        dr = dxr * x * mask_r
     dmu_r = dr.reshape(E, n, -1).sum(1)
     drho_r = None if rho_r is None else (dr * er).reshape(E, n, -1).sum(1) * sigmoid(rho_r)
-    return dict(dx=dx, dw=dw, dmu_r=dmu_r, drho_r=drho_r, dmu_s=dmu_s, drho_s=drho_s, dbias=dbias)
+    return dict(dx=dx, dw=dw, dmu_r=dmu_r, drho_r=drho_r, dmu_s=dmu_s, drho_s=drho_s, dbias=dbias, drho_b=drho_b)
 
 
 # ------------------------------------------------------------------------------------------- DenseReparameterization

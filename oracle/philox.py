@@ -79,3 +79,22 @@ def normal(seed, stream, n):
 def sign(seed, stream, n):
     x = blocks(seed, stream, (n + 3) // 4).reshape(-1)[:n]
     return np.where((x >> np.uint32(31)) != 0, 1.0, -1.0)
+
+
+def global_rows(n_local_rows, row0=0, rows_per_group_local=0, rows_per_group_global=0):
+    """Row mapping of per-example noise tensors under data parallelism (ed2_noise in include/ed2b200.h,
+    `noise_row` in edward2_b200/csrc/philox.cuh): global row of every local row."""
+    m = np.arange(n_local_rows, dtype=np.int64)
+    if rows_per_group_local > 0:
+        g = m // rows_per_group_local
+        return m + g * (rows_per_group_global - rows_per_group_local) + row0
+    return m + row0
+
+
+def per_example(kind, seed, stream, rows, cols, row0=0, rows_per_group_local=0, rows_per_group_global=0):
+    """[rows, cols] per-example noise (kind 'normal' | 'sign') of a rank holding `rows` local rows: element (m, c) is
+    element global_row(m) * cols + c of the stream, i.e. the rows of the single-device global-batch tensor."""
+    gr = global_rows(rows, row0, rows_per_group_local, rows_per_group_global)
+    total = int(gr.max() + 1) * cols if rows else 0
+    flat = {"normal": normal, "sign": sign}[kind](seed, stream, total)
+    return flat.reshape(-1, cols)[gr]

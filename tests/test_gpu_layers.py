@@ -294,7 +294,7 @@ def test_two_layer_mlp_cross_layer_fusion(cuda, dtype, tol):
         out = l2(h)
         out.backward(gy)
         torch.cuda.synchronize()
-        assert link.dx_ptr is not None, "the fused dX epilogue path was not taken"
+        assert link.fused, "the fused dX epilogue path was not taken"
         results.append((l1, l2, out))
     (l1, l2, out) = results[0]
     m1, r1 = l1.kernel_initializer.params()
@@ -317,3 +317,75 @@ def test_two_layer_mlp_cross_layer_fusion(cuda, dtype, tol):
     (p1, p2, pout) = results[1]
     assert rel_err(to_np(pout), to_np(out)) < (1e-6 if dtype == "float32" else tol)
     assert rel_err(to_np(p1.kernel_initializer.mean.grad), to_np(m1.grad)) < (1e-5 if dtype == "float32" else tol)
+
+
+def test_relu_link_falls_back_under_fan_out(cuda):
+    """A ReLU layer whose output feeds the next DenseReparameterization AND a skip connection: autograd sums the two
+    gradients, the producer must not treat the sum as pre-masked (functional.ReluLink.matches).  Gradients equal the
+    oracle's chain with the skip term included."""
+    ed = _ed()
+    from edward2_b200 import functional as F
+
+    rng = np.random.default_rng(12)
+    B, I, H = 72, 40, 136
+    x = torch.tensor(rng.standard_normal((B, I)), dtype=torch.float32, device=cuda)
+    eps1 = torch.tensor(rng.standard_normal((I, H)), dtype=torch.float32, device=cuda)
+    eps2 = torch.tensor(rng.standard_normal((H, H)), dtype=torch.float32, device=cuda)
+    gy = torch.tensor(rng.standard_normal((B, H)), dtype=torch.float32, device=cuda)
+    mk = lambda seed: ed.layers.DenseReparameterization(  # noqa: E731
+        H, activation="relu" if seed == 1 else None, seed=seed, kernel_regularizer=None,
+        kernel_initializer=ed.initializers.TrainableNormal(
+            mean_initializer=ed.initializers.RandomNormal(stddev=0.1, seed=seed),
+            stddev_initializer=ed.initializers.TruncatedNormal(-3.0, 0.1, seed=seed + 10)))
+    for order in (0, 1):  # both arrival orders of the two gradient contributions
+        l1, l2 = mk(1), mk(2)
+        l1.inject(eps=eps1)
+        l2.inject(eps=eps2)
+        h = l1(x)
+        link = F.take_link(h)
+        out = (l2(h) + 0.5 * h) if order == 0 else (0.5 * h + l2(h))
+        out.backward(gy)
+        torch.cuda.synchronize()
+        assert link is not None and not link.fused
+        m1, r1 = l1.kernel_initializer.params()
+        m2, r2 = l2.kernel_initializer.params()
+        h_ref, _ = od.reparam_fwd(to_np(x), to_np(m1), to_np(r1), to_np(eps1), to_np(l1.bias), "relu")
+        g2 = od.reparam_bwd(h_ref, to_np(m2), to_np(r2), to_np(eps2), to_np(l2.bias), None, to_np(gy))
+        g1 = od.reparam_bwd(to_np(x), to_np(m1), to_np(r1), to_np(eps1), to_np(l1.bias), "relu",
+                            g2["dx"] + 0.5 * to_np(gy))
+        assert rel_err(to_np(m1.grad), g1["dmu"]) < 1e-5
+        assert rel_err(to_np(r1.grad), g1["drho"]) < 1e-5
+        assert rel_err(to_np(l1.bias.grad), g1["dbias"]) < 1e-5
+
+
+def test_sngp_head_restores_from_state_dict(cuda):
+    """Loading a checkpoint with a DIFFERENT random-feature kernel and a mid-training covariance state must change the
+    forward: the operand caches of the RFF layer and the host mirror of `if_update_covariance` follow the restored
+    buffers (random_feature.py:346-378 variable set)."""
+    ed = _ed()
+    torch.manual_seed(0)
+    x = torch.randn(64, 24, device=cuda)
+
+    def make(seed):
+        return ed.layers.RandomFeatureGaussianProcess(
+            3, num_inducing=128, gp_cov_momentum=-1, gp_cov_ridge_penalty=1.0,
+            custom_random_features_initializer=ed.initializers.OrthogonalRandomFeatures(stddev=1.0, seed=seed))
+
+    src, dst = make(1), make(2)
+    src.train()
+    for _ in range(2):
+        src(x)  # precision accumulated, if_update_covariance == True, covariance not yet inverted
+    dst.eval()
+    logits_before, cov_before = dst(x)
+    dst.load_state_dict(src.state_dict())
+    logits_after, cov_after = dst(x)
+    src.eval()
+    logits_src, cov_src = src(x)
+    torch.cuda.synchronize()
+    assert rel_err(to_np(logits_after), to_np(logits_src)) < 1e-6
+    assert rel_err(to_np(cov_after), to_np(cov_src)) < 1e-5
+    assert rel_err(to_np(cov_before), to_np(cov_src)) > 1e-2  # the restore really changed the result
+    # training identity: cached, still the identity
+    src.train()
+    eye = src(x)[1]
+    assert eye.shape == (64, 64) and torch.equal(eye, torch.eye(64, device=cuda))

@@ -76,6 +76,14 @@ def test_initializer_statistics():
     np.testing.assert_allclose(g - np.diag(np.diag(g)), 0, atol=1e-3)
     c = ed.constraints.Softplus()(torch.tensor([-100.0, 0.0]))
     assert (c > 0).all()
+    # initializers.py:531-590: He / Glorot scale the MEAN; the stddev keeps the TruncN(-3, 0.1) default (sigma ~ 0.049)
+    for cls, std in ((ed.initializers.TrainableHeNormal, (2 / 400) ** 0.5),
+                     (ed.initializers.TrainableGlorotNormal, (2 / 700) ** 0.5)):
+        t = cls(seed=3)
+        t.build((400, 300))
+        m, r = t.params()
+        assert abs(float(m.std()) - std) < 0.05 * std, (cls.__name__, float(m.std()), std)
+        np.testing.assert_allclose(float(torch.nn.functional.softplus(r).mean()), 0.0486, atol=5e-3)
 
 
 def test_peer_exchange_layout():

@@ -475,3 +475,67 @@ def test_reference_mean_field_logits(ref):
         _close(og.mean_field_logits(lg, var, 0.7, lik), ref[f"mf_{lik}"])
     _close(og.mean_field_logits(lg, None, 3.0), ref["mf_nocov"])
     _close(og.mean_field_logits(lg, var, -1.0), ref["mf_negative"])
+
+
+@pytest.mark.parametrize("additive", [False, True])
+@pytest.mark.parametrize("sampled_bias", [False, True])
+def test_rank1_variants_match_autograd_and_member_loop(additive, sampled_bias):
+    """dense.py:1096-1144 with use_additive_perturbation (:1126-1127), custom clip bounds (:1108-1110) and the
+    per-example sampled bias (:1131-1139): the oracle's forward equals a literal per-example loop, and its closed-form
+    gradients equal float64 autograd of an op-for-op torch restatement."""
+    rng = np.random.default_rng(5)
+    E, n, I, O = 2, 4, 5, 6
+    B = E * n
+    clip = (-0.8, 1.3)
+    x, w = rng.standard_normal((B, I)), rng.standard_normal((I, O))
+    mu_r, rho_r = rng.standard_normal((E, I)), rng.standard_normal((E, I)) - 1
+    mu_s, rho_s = rng.standard_normal((E, O)), rng.standard_normal((E, O)) - 1
+    eps_r, eps_s, eps_b = rng.standard_normal((B, I)), rng.standard_normal((B, O)), rng.standard_normal((B, O))
+    bias, rho_b = rng.standard_normal((E, O)), (rng.standard_normal((E, O)) - 1 if sampled_bias else None)
+    gy = rng.standard_normal((B, O))
+    kw = dict(additive=additive, clip=clip, rho_b=rho_b, eps_b=eps_b if sampled_bias else None)
+    y, _, _, _ = od.rank1_fwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, "relu", **kw)
+    rows = []
+    for e in range(E):
+        for i in range(n):
+            b = e * n + i
+            r = np.clip(mu_r[e] + od.stddev(rho_r[e]) * eps_r[b], *clip)
+            s = np.clip(mu_s[e] + od.stddev(rho_s[e]) * eps_s[b], *clip)
+            bb = bias[e] + (od.stddev(rho_b[e]) * eps_b[b] if sampled_bias else 0.0)
+            pre = ((x[b] + r) @ w + s) if additive else ((x[b] * r) @ w) * s
+            rows.append(np.maximum(pre + bb, 0.0))
+    np.testing.assert_allclose(y, np.stack(rows), rtol=1e-12, atol=1e-12)
+
+    T = lambda a: torch.tensor(a, dtype=torch.float64, requires_grad=True)  # noqa: E731
+    tx, tw, tmr, trr, tms, trs, tb = (T(a) for a in (x, w, mu_r, rho_r, mu_s, rho_s, bias))
+    trb = T(rho_b) if sampled_bias else None
+    sp = lambda r: torch.nn.functional.softplus(r) + 1e-7  # noqa: E731
+    rep = lambda a: a.repeat_interleave(n, 0)  # noqa: E731
+    r = torch.clamp(rep(tmr) + rep(sp(trr)) * torch.tensor(eps_r), *clip)
+    s = torch.clamp(rep(tms) + rep(sp(trs)) * torch.tensor(eps_s), *clip)
+    pre = ((tx + r) @ tw + s) if additive else ((tx * r) @ tw) * s
+    pre = pre + rep(tb) + (rep(sp(trb)) * torch.tensor(eps_b) if sampled_bias else 0.0)
+    torch.relu(pre).backward(torch.tensor(gy))
+    g = od.rank1_bwd(x, w, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, "relu", gy, **kw)
+    for name, t in (("dx", tx), ("dw", tw), ("dmu_r", tmr), ("drho_r", trr), ("dmu_s", tms), ("drho_s", trs),
+                    ("dbias", tb)):
+        np.testing.assert_allclose(g[name], t.grad.numpy(), rtol=1e-10, atol=1e-12, err_msg=name)
+    if sampled_bias:
+        np.testing.assert_allclose(g["drho_b"], trb.grad.numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_per_example_noise_is_a_function_of_the_global_row():
+    """ed2_noise row mapping (include/ed2b200.h): the rows a rank draws under the member-major shard
+    are exactly the matching rows of the single-device global tensor, for every world size."""
+    E, n, cols = 4, 12, 7
+    full = op.per_example("normal", 9, 4, E * n, cols)
+    np.testing.assert_array_equal(full, op.normal(9, 4, E * n * cols).reshape(E * n, cols))
+    for world in (1, 2, 3, 4):
+        per = n // world
+        for rank in range(world):
+            local = op.per_example("normal", 9, 4, E * per, cols, rank * per, per, n)
+            want = full.reshape(E, n, cols)[:, rank * per:(rank + 1) * per].reshape(E * per, cols)
+            np.testing.assert_array_equal(local, want)
+    # ungrouped (Flipout signs): a rank's rows are a contiguous block of the global batch
+    s_full = op.per_example("sign", 3, 2, 24, 5)
+    np.testing.assert_array_equal(op.per_example("sign", 3, 2, 8, 5, 16, 0, 0), s_full[16:24])
