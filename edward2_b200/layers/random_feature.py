@@ -349,6 +349,8 @@ class RandomFeatureGaussianProcess(Layer):
         self._gp_cov_layer.reset_precision_matrix()
 
     def call(self, inputs, global_step=None, training=None):
+        if training is None:
+            training = self.training  # sub-layers are built lazily: they must follow THIS module's train / eval mode
         x, lead = flatten_batch(inputs)
         gp_inputs = x
         if self.normalize_input:
