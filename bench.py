@@ -1,11 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — samples/s for one forward + backward step of the Edward2 stochastic-weight hot path on B200.
+"""bench.py — samples/s for one forward + backward step of the Edward2 stochastic-weight / SNGP hot path on B200.
 
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` (under torchrun for N > 1)
-prints ONE JSON line from rank 0.  Workload at N=1 = BASELINE.json configs[1]: Bayesian MLP 1024-4096-4096-1000,
-batch 4096, bf16 compute, DenseReparameterization layers with the analytic KL regularizer (the DenseFlipout variant
-of the same config is measured in the same run and reported under "variants").  `--impl reference` times the
-torch-CPU restatement of the reference's CPU path (oracle/torch_cpu.py; the reference itself cannot run here).
+prints ONE JSON line from rank 0.
+
+Headline workload = BASELINE.json configs[3], the BatchEnsemble-family config that carries the scaling target:
+  cfg4: DenseRank1 MLP 2048-8192-8192-1000, ensemble_size 4, sampled r/s (in-kernel Philox, global-row offsets),
+        2048 rows per GPU (weak scaling: 16384 rows on 8 GPUs), bf16 compute, KL(alpha, gamma || N(1, 0.1)).
+The same run also measures, at N = 1, every other configuration of BASELINE.json (cfg1 BatchEnsemble MLP, cfg2
+Reparameterization and Flipout MLPs, cfg3 SNGP head train/eval, cfg5 per-GPU shard train/eval) and reports each
+under "configs" with its own ms_per_step, roofline and CPU baseline.
+
+`--impl reference` times the torch-CPU restatement of the reference's CPU path for the headline workload
+(oracle/torch_cpu.py; TensorFlow / TFP / JAX are not installable here, so the reference itself cannot run).
 """
 from __future__ import annotations
 
@@ -20,31 +27,28 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DIMS = [1024, 4096, 4096, 1000]
-BATCH = 4096
 KL_SCALE = 1.0 / 50000
 METRIC = "samples/sec fwd+bwd"
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 67.7e6  # (464.7 MB read + 76.7 MB written) / 8 launches, profiles/r01_ncu_summary.csv
-WORKLOAD = "cfg2: DenseReparameterization Bayesian MLP 1024-4096-4096-1000 + KL, batch 4096/GPU, bf16"
+HEADLINE = "cfg4"
+# DRAM bytes per tcgen05 GEMM launch from the committed `ncu --set full` captures (profiles/); None = not captured
+NCU_TRAFFIC = {"cfg2_reparam": 67.7e6}
 
 
-def flops_per_step(batch: int, flipout: bool) -> float:
-    """fwd + dW for every layer, dX for layers 2..L; Flipout doubles every product."""
+def mlp_flops(dims, batch, mult=1.0):
+    """fwd + dW for every layer, dX for layers 2..L."""
     f = 0.0
-    for li, (i, o) in enumerate(zip(DIMS[:-1], DIMS[1:])):
-        f += 2.0 * batch * i * o * 2          # forward + dW
-        if li > 0:
-            f += 2.0 * batch * i * o          # dX
-    return f * (2.0 if flipout else 1.0)
+    for li, (i, o) in enumerate(zip(dims[:-1], dims[1:])):
+        f += 2.0 * batch * i * o * (3 if li > 0 else 2)
+    return f * mult
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(bf16=d.get("bf16_tflops_sustained", 1400.0), bf16_burst=d.get("bf16_tflops", 1590.0),
-                    hbm=d.get("hbm_gbs", 6650.0), src="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+        return dict(bf16_sustained=d.get("bf16_tflops_sustained", 1400.0), bf16=d.get("bf16_tflops", 1590.0),
+                    hbm=d.get("hbm_gbs", 6650.0), src="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_sustained=1400.0, bf16=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -90,75 +94,288 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Workloads.  Each builds its layers on `device` and returns a dict:
+#   step(x, y) -> loss tensor (one forward + backward, or one eval pass), params, batch (rows per GPU), in_dim,
+#   x_dtype, classes, flops (algorithmic FLOPs per GPU per step), cpu(steps) -> (samples/s, s/step,
+#   threads, sample description), gemm_kernel (name fragment of the dominant kernel), dtype
+# ------------------------------------------------------------------------------------------------------------------
+CFG4_DIMS = [2048, 8192, 8192, 1000]
+CFG2_DIMS = [1024, 4096, 4096, 1000]
+CFG1_DIMS = [784, 512, 512, 10]
+
+
+def _warm_build(layers, x0):
+    import torch
+
+    h = x0
+    with torch.no_grad():
+        for l in layers:
+            h = l(h)
+
+
+def wl_cfg4(ed, device, step_counter, rank, world):
+    import torch
+
+    from edward2_b200 import functional as F
+
+    E, B = 4, 2048
+    mk = lambda u, act, li: ed.layers.DenseRank1(  # noqa: E731
+        u, activation=act, ensemble_size=E, dtype="bfloat16", seed=2026 + li,
+        alpha_initializer=ed.initializers.TrainableNormal(
+            mean_initializer=ed.initializers.RandomSign(seed=10 + li),
+            stddev_initializer=ed.initializers.Constant(-3.4402)),  # softplus^-1(sqrt(p/(1-p))), p = 1e-3
+        gamma_initializer=ed.initializers.TrainableNormal(
+            mean_initializer=ed.initializers.RandomSign(seed=20 + li),
+            stddev_initializer=ed.initializers.Constant(-3.4402)),
+        alpha_regularizer=ed.regularizers.NormalKLDivergence(mean=1.0, stddev=0.1, scale_factor=KL_SCALE),
+        gamma_regularizer=ed.regularizers.NormalKLDivergence(mean=1.0, stddev=0.1, scale_factor=KL_SCALE))
+    layers = [mk(8192, "relu", 0), mk(8192, "relu", 1), mk(1000, None, 2)]
+    _warm_build(layers, torch.zeros(8, CFG4_DIMS[0], dtype=torch.bfloat16, device=device))
+    for l in layers:
+        l.step_counter = step_counter
+    model = torch.nn.ModuleList(layers)
+    if world > 1:
+        from edward2_b200.dist import shard_noise
+
+        shard_noise(model, rank, world)  # r / s noise is drawn for the GLOBAL row: same result for any N
+    gb = B * world
+
+    def step(x, y):
+        h = x
+        for l in layers:
+            h = l(h)
+        loss = F.SoftmaxCrossEntropy.apply(h, y, gb, *[k for l in layers for k in l.losses])
+        F.backward(loss)
+        return loss.detach()
+
+    def cpu(steps):
+        from oracle import torch_cpu
+
+        sps, dt, th = torch_cpu.time_rank1_mlp(CFG4_DIMS, B, steps, warmup=1, ensemble_size=E)
+        return sps, dt, th, f"{steps} fwd+bwd steps on {B}-row batches of the cfg4 rank-1 MLP (torch-CPU fp32 restatement)"
+
+    return dict(step=step, params=list(model.parameters()), batch=B, in_dim=CFG4_DIMS[0], x_dtype=torch.bfloat16,
+                classes=1000, flops=mlp_flops(CFG4_DIMS, B), cpu=cpu, dtype="bf16", modules=model,
+                workload="cfg4: DenseRank1 MLP 2048-8192-8192-1000, ensemble_size 4, sampled r/s + KL, "
+                         "2048 rows/GPU (16384 on 8 GPUs), bf16")
+
+
+def wl_cfg2(flipout):
+    def build(ed, device, step_counter, rank, world):
+        import torch
+
+        from edward2_b200 import functional as F
+
+        B = 4096
+        cls = ed.layers.DenseFlipout if flipout else ed.layers.DenseReparameterization
+        layers = []
+        for li, units in enumerate(CFG2_DIMS[1:]):
+            reg = ed.regularizers.NormalKLDivergence(scale_factor=KL_SCALE)
+            layers.append(cls(units, activation="relu" if li < 2 else None, kernel_regularizer=reg, dtype="bfloat16",
+                              seed=2026 + li))
+        _warm_build(layers, torch.zeros(8, CFG2_DIMS[0], dtype=torch.bfloat16, device=device))
+        for l in layers:
+            l.step_counter = step_counter
+        model = torch.nn.ModuleList(layers)
+        if world > 1:
+            from edward2_b200.dist import shard_noise
+
+            shard_noise(model, rank, world)
+        gb = B * world
+
+        def step(x, y):
+            # scheduling hint: draw the kernel samples on side streams so the issue-bound sampling passes overlap the
+            # first layers' GEMMs (same Philox streams as without the hint)
+            layers[0].presample()
+            for l in layers[1:]:
+                l.presample(after=layers[0])
+            h = x
+            for l in layers:
+                h = l(h)
+            loss = F.SoftmaxCrossEntropy.apply(h, y, gb, *[l.losses[0] for l in layers])
+            F.backward(loss)
+            return loss.detach()
+
+        def cpu(steps):
+            from oracle import torch_cpu
+
+            sps, dt, th = torch_cpu.time_bayesian_mlp(CFG2_DIMS, B, flipout, steps, warmup=1)
+            return sps, dt, th, f"{steps} fwd+bwd steps on {B}-row batches (torch-CPU fp32 restatement)"
+
+        return dict(step=step, params=list(model.parameters()), batch=B, in_dim=CFG2_DIMS[0], x_dtype=torch.bfloat16,
+                    classes=1000, flops=mlp_flops(CFG2_DIMS, B, 2.0 if flipout else 1.0), cpu=cpu, dtype="bf16",
+                    modules=model,
+                    workload=f"cfg2: {'DenseFlipout' if flipout else 'DenseReparameterization'} Bayesian MLP "
+                             f"1024-4096-4096-1000 + KL, batch 4096/GPU, bf16")
+
+    return build
+
+
+def wl_cfg1(ed, device, step_counter, rank, world):
+    import torch
+
+    from edward2_b200 import functional as F
+
+    E, B = 4, 128
+    mk = lambda u, act: ed.layers.DenseBatchEnsemble(u, ensemble_size=E, activation=act,  # noqa: E731
+                                                     alpha_initializer="random_sign", gamma_initializer="random_sign")
+    layers = [mk(512, "relu"), mk(512, "relu"), mk(10, None)]
+    _warm_build(layers, torch.zeros(8, 784, device=device))
+    model = torch.nn.ModuleList(layers)
+
+    def step(x, y):
+        h = x
+        for l in layers:
+            h = l(h)
+        loss = F.SoftmaxCrossEntropy.apply(h, y, B)
+        F.backward(loss)
+        return loss.detach()
+
+    def cpu(steps):
+        from oracle import torch_cpu
+
+        sps, dt, th = torch_cpu.time_batch_ensemble_mlp(CFG1_DIMS, B, max(steps, 50), warmup=5, ensemble_size=E)
+        return sps, dt, th, f"{max(steps, 50)} fwd+bwd steps on the config's own 128-row batch (torch-CPU fp32 restatement)"
+
+    return dict(step=step, params=list(model.parameters()), batch=B, in_dim=784, x_dtype=torch.float32, classes=10,
+                flops=mlp_flops(CFG1_DIMS, B), cpu=cpu, dtype="f32", modules=model, bound="launch latency",
+                min_bytes=9e6,
+                workload="cfg1: DenseBatchEnsemble MLP 784-512-512-10, ensemble_size 4, batch 128, fp32")
+
+
+def wl_sngp(kind, train):
+    """cfg3: 2 x SpectralNormalization(Dense 512, relu) + RFGP(D=1024, 10 classes), batch 8192.
+    cfg5 (per-GPU shard): RFGP D=8192 on 4096-dim inputs, 8192 rows per GPU, exact-sum precision."""
+
+    def build(ed, device, step_counter, rank, world):
+        import torch
+
+        from edward2_b200 import functional as F
+
+        if kind == "cfg3":
+            B, d, D, widths, mom = 8192, 512, 1024, [512, 512], 0.999
+        else:
+            B, d, D, widths, mom = 8192, 4096, 8192, [], -1
+        backbone = [ed.layers.SpectralNormalization(ed.layers.Dense(w, activation="relu", dtype="bfloat16"),
+                                                    norm_multiplier=0.95) for w in widths]
+        gp = ed.layers.RandomFeatureGaussianProcess(
+            10, num_inducing=D, gp_cov_momentum=mom, gp_cov_ridge_penalty=1e-3, dtype="bfloat16",
+            data_parallel="deferred" if (world > 1 and kind == "cfg5") else False)
+        model = torch.nn.ModuleList(backbone + [gp])
+        x0 = torch.randn(256, d, device=device).to(torch.bfloat16)
+        model.train()
+        with torch.no_grad():
+            h = x0
+            for l in backbone:
+                h = l(h, training=True)
+            gp(h, training=True)
+        cov = gp._gp_cov_layer
+        gb = B * world
+
+        if train:
+            def step(x, y):
+                h = x
+                for l in backbone:
+                    h = l(h, training=True)
+                logits, _ = gp(h, training=True)
+                loss = F.SoftmaxCrossEntropy.apply(logits, y, gb)
+                F.backward(loss)
+                return loss.detach()
+        else:
+            model.eval()  # the one-off D^3 inverse happens in the first (untimed, pre-capture) call
+
+            def step(x, y):
+                with torch.no_grad():
+                    h = x
+                    for l in backbone:
+                        h = l(h, training=False)
+                    gp_in = gp._input_norm_layer(h)
+                    phi = gp._random_feature(gp_in)
+                    logits = gp._gp_output_layer(phi).float() + gp._gp_output_bias
+                    var, adj = cov.compute_predictive_variance(phi, logits, mean_field_factor=3.141592653589793 / 8.0)
+                return adj.sum()
+
+        bb = sum(2.0 * B * a * b for a, b in zip([d] + widths[:-1], widths))
+        rff, out, pp = 2.0 * B * (widths[-1] if widths else d) * D, 2.0 * B * D * 10, 2.0 * B * D * D
+        if train:
+            # fwd + dW + dX of the backbone (dX for layer 2 only), RFF fwd + dX, output layer fwd+dW+dX, full ΦᵀΦ
+            n_dx = max(0, len(widths) - 1)
+            flops = bb * 2 + (bb / max(1, len(widths))) * n_dx + rff * (2 if widths else 1) + out * 3 + pp
+        else:
+            flops = bb + rff + out + pp
+
+        def cpu(steps):
+            from oracle import torch_cpu
+
+            rows = B if kind == "cfg3" else 1024
+            r = torch_cpu.time_sngp(d, widths, D, 10, mom, 1e-3, rows, steps, warmup=1)["train" if train else "eval"]
+            return r[0], r[1], r[2], (f"{steps} {'train' if train else 'eval'} steps on {rows}-row batches "
+                                      f"(torch-CPU fp32 restatement{'' if rows == B else ', linear in rows'})")
+
+        return dict(step=step, params=list(model.parameters()), batch=B, in_dim=d, x_dtype=torch.bfloat16, classes=10,
+                    flops=flops, cpu=cpu, dtype="bf16", modules=model, no_grad=not train,
+                    workload=(f"{kind} {'train' if train else 'eval'}: " + (
+                        "2x SpectralNormalization(Dense 512, relu) + RFGP(D=1024, 10 classes) + Laplace precision, batch 8192"
+                        if kind == "cfg3" else
+                        "RFGP D=8192 on 4096-dim inputs, 8192 rows per GPU (65536 on 8), exact-sum precision") +
+                        (", predictive variance + mean-field logits" if not train else "") + ", bf16"))
+
+    return build
+
+
+WORKLOADS = {
+    "cfg4": wl_cfg4, "cfg2_reparam": wl_cfg2(False), "cfg2_flipout": wl_cfg2(True), "cfg1": wl_cfg1,
+    "cfg3_train": wl_sngp("cfg3", True), "cfg3_eval": wl_sngp("cfg3", False),
+    "cfg5_train": wl_sngp("cfg5", True), "cfg5_eval": wl_sngp("cfg5", False),
+}
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """`--impl reference`: the reference's CPU path, restated (kind "port"), on this box's host cores."""
+    """`--impl reference`: the reference's CPU path for the headline workload, restated (kind "port"), on this box's
+    host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import torch_cpu
 
-    # the config's own batch when the run stays within a few minutes (~1 s per 4096-row step on the GPU box's host
-    # cores), a 1024-row sample of it for long runs
-    sample_batch = BATCH if args.steps + args.warmup <= 40 else 1024
-    sps, dt, threads = torch_cpu.time_bayesian_mlp(DIMS, sample_batch, False, max(1, args.steps), max(1, args.warmup))
+    B = 2048
+    steps = max(1, min(args.steps, 30))
+    sps, dt, threads = torch_cpu.time_rank1_mlp(CFG4_DIMS, B, steps, warmup=max(1, min(args.warmup, 3)), ensemble_size=4)
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "torch-CPU fp32 restatement of the reference's CPU path "
-                   f"(TF/TFP/JAX not installable here); each step = {sample_batch} rows of the 4096-row batch"},
+        "config": {"workload": "cfg4: DenseRank1 MLP 2048-8192-8192-1000, ensemble_size 4, sampled r/s + KL, "
+                               "2048 rows/GPU (16384 on 8 GPUs), bf16",
+                   "note": "torch-CPU fp32 restatement of the reference's CPU path (TF/TFP/JAX not installable here); "
+                           f"each step = one {B}-row batch ({steps} timed steps)"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample_batch}-row batches of the cfg2 MLP, {args.steps} fwd+bwd steps"},
+                         "sample": f"{steps} fwd+bwd steps on {B}-row batches of the cfg4 rank-1 MLP"},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def build_model(ed, flipout: bool, device, step_counter):
+def kernel_times(run_step, steps=3):
+    """Per-kernel device time (us per step) of `steps` steps, from CUPTI through torch.profiler.  Diagnostics for the
+    roofline object only — never a bench value."""
     import torch
+    from torch.profiler import ProfilerActivity, profile
 
-    cls = ed.layers.DenseFlipout if flipout else ed.layers.DenseReparameterization
-    layers = []
-    for li, units in enumerate(DIMS[1:]):
-        reg = ed.regularizers.NormalKLDivergence(scale_factor=KL_SCALE)
-        layers.append(cls(units, activation="relu" if li < len(DIMS) - 2 else None, kernel_regularizer=reg,
-                          dtype="bfloat16", seed=2026 + li))
-    x0 = torch.zeros(8, DIMS[0], dtype=torch.bfloat16, device=device)
-    h = x0
-    with torch.no_grad():
-        for l in layers:
-            h = l(h)
-    for l in layers:
-        l.step_counter = step_counter
-    return layers
-
-
-def make_step(layers, global_batch):
-    from edward2_b200 import functional as F
-
-    def step(x, labels):
-        # scheduling hint: draw the kernel samples of the later layers on side streams now, so the issue-bound sampling
-        # passes overlap the first layers' GEMMs (same Philox streams as without the hint)
-        # (the first layer's sample goes first and alone: the first GEMM waits for it; the others follow beside that GEMM)
-        if hasattr(layers[0], "presample"):
-            layers[0].presample()
-        for l in layers[1:]:
-            if hasattr(l, "presample"):
-                l.presample(after=layers[0])
-        h = x
-        for l in layers:
-            h = l(h)
-        # cross-entropy + the layers' KL regularisers, summed by one kernel
-        loss = F.SoftmaxCrossEntropy.apply(h, labels, global_batch, *[l.losses[0] for l in layers])
-        F.backward(loss)
-        return loss.detach()
-
-    return step
-
-
-def params_of(layers):
-    return [p for l in layers for p in l.parameters()]
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            run_step()
+        torch.cuda.synchronize()
+    out = {}
+    for ev in prof.key_averages():
+        t = getattr(ev, "device_time_total", None)
+        if t is None:
+            t = getattr(ev, "cuda_time_total", 0.0)
+        if t:
+            out[ev.key] = (out.get(ev.key, (0.0, 0))[0] + t / steps, out.get(ev.key, (0.0, 0))[1] + ev.count / steps)
+    return out
 
 
 def run_ours(args):
@@ -166,13 +383,12 @@ def run_ours(args):
     import torch.distributed as dist
 
     import edward2_b200 as ed
-    from edward2_b200 import _lib, ops
+    from edward2_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and args.gemm_ctas > 0:
-        # leave SMs for the NCCL all-reduce kernels (read by libed2b200 at its first GEMM launch)
         os.environ.setdefault("ED2_GEMM_MAX_CTAS", str(args.gemm_ctas))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -180,34 +396,27 @@ def run_ours(args):
     _lib.check(lib.ed2_check_device(local), "ed2_check_device")
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    global_batch = BATCH * world
     pk = peaks()
 
-    gen = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(BATCH, DIMS[0], generator=gen).to(torch.bfloat16).pin_memory()
-    y_host = torch.randint(0, DIMS[-1], (BATCH,), generator=gen).pin_memory()
-    x_dev, y_dev = x_host.to(device), y_host.to(device)
-    step_counter = torch.zeros((), dtype=torch.int64, device=device)
-
-    def measure(flipout: bool, steps: int, warmup: int, want_e2e: bool):
-        layers = build_model(ed, flipout, device, step_counter)
-        params = params_of(layers)
+    def measure(name: str, steps: int, warmup: int, want_e2e: bool, want_kernels: bool):
+        step_counter = torch.zeros((), dtype=torch.int64, device=device)
+        wl = WORKLOADS[name](ed, device, step_counter, rank, world)
+        B, params = wl["batch"], wl["params"]
+        gen = torch.Generator().manual_seed(1234 + rank)
+        x_host = torch.randn(B, wl["in_dim"], generator=gen).to(wl["x_dtype"]).pin_memory()
+        y_host = torch.randint(0, wl["classes"], (B,), generator=gen).pin_memory()
+        x_dev, y_dev = x_host.to(device), y_host.to(device)
         reducer = None
-        if world > 1 and not args.no_allreduce:
-            # gradient all-reduce launched as soon as each parameter's gradient is final, overlapping the rest of
-            # the backward pass (NCCL runs on its own stream); bf16 buckets halve the NVLink bytes
+        if world > 1 and not args.no_allreduce and not wl.get("no_grad"):
             from edward2_b200.dist import GradientAllReduce
 
             reducer = GradientAllReduce(params, compress=None if args.fp32_allreduce else torch.bfloat16,
-                                        exchange=args.grad_exchange)
-        raw_step = make_step(layers, global_batch)
+                                        exchange=args.grad_exchange, hook_exchange=args.hook_exchange)
+        raw_step = wl["step"]
 
         def zero():
             for p in params:
                 p.grad = None
-
-        use_graph = args.graph in ("on", "auto")
-        graph, static_loss = None, None
 
         def eager_step(x, y):
             zero()
@@ -217,10 +426,10 @@ def run_ours(args):
                 reducer.wait()
             return loss
 
+        use_graph = args.graph in ("on", "auto")
+        graph, static_loss = None, None
         x_static, y_static = x_dev.clone(), y_dev.clone()
-        # every pre-capture step runs on the capture-side stream so that autograd's AccumulateGrad nodes are bound
-        # to it (a node created on the legacy stream would invalidate the capture)
-        # high priority: when an SM has room, a GEMM CTA of the main stream is placed before side-stream blocks
+        # every pre-capture step runs on the capture-side stream so that autograd's AccumulateGrad nodes are bound to it
         side = torch.cuda.Stream(priority=-1) if use_graph else torch.cuda.current_stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -239,10 +448,10 @@ def run_ours(args):
                 with torch.cuda.graph(graph, stream=side):
                     step_counter.add_(1)
                     static_loss = raw_step(x_static, y_static)
-                    if reducer is not None:  # join the NCCL all-reduces into the captured step
+                    if reducer is not None:
                         reducer.wait()
             except Exception as e:  # noqa: BLE001  (e.g. a collective that cannot be captured) -> eager steps
-                sys.stderr.write(f"[bench] CUDA-graph capture failed, running eagerly: {str(e)[:300]}\n")
+                sys.stderr.write(f"[bench] {name}: CUDA-graph capture failed, running eagerly: {str(e)[:300]}\n")
                 graph, static_loss = None, None
                 if reducer is not None:
                     reducer.handles.clear()
@@ -269,29 +478,25 @@ def run_ours(args):
             run_step()
         e1.record()
         sync_all()
-        ms = e0.elapsed_time(e1) / steps
-        # kernels of libed2b200 launched in the timed region (a graph replay re-launches the captured ones)
-        launches = launches_per_step * steps
-        t = torch.tensor([ms], device=device)
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        res = dict(ms=ms, launches=launches_per_step * steps, graph=graph is not None, batch=B, flops=wl["flops"],
+                   workload=wl["workload"], dtype=wl["dtype"], wl=wl, e2e_ms=None, kernels=None,
+                   h2d=(x_host.numel() * x_host.element_size() + y_host.numel() * 8), exchange=None)
 
-        if args.trace and not flipout:
-            # kernel timeline of 3 steps (CUPTI through torch.profiler) for offline analysis; never a bench number
-            import contextlib
-
-            from torch.profiler import ProfilerActivity, profile
-
-            with (profile(activities=[ProfilerActivity.CUDA]) if rank == 0 else contextlib.nullcontext()) as prof:
-                for _ in range(3):
-                    run_step()
-                sync_all()
-            if rank == 0:
-                prof.export_chrome_trace(args.trace)
+        if want_kernels:
+            try:
+                res["kernels"] = kernel_times(run_step, 3)
+                if args.dump_kernels and rank == 0:
+                    with open(args.dump_kernels, "a") as f:
+                        f.write(json.dumps({"workload": name, "ms_per_step": ms, "kernels_us_count_per_step": {
+                            k: [round(v[0], 2), round(v[1], 2)] for k, v in sorted(res["kernels"].items(), key=lambda kv: -kv[1][0])}}) + "\n")
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"[bench] {name}: kernel timeline unavailable: {str(e)[:200]}\n")
             sync_all()
 
-        e2e_ms = None
         if want_e2e:
             # end to end through the public layer API with HOST buffers: every step copies ITS batch from pinned host
             # memory (H2D on a copy stream into one of two staging slots, overlapping the previous step's compute),
@@ -333,121 +538,106 @@ def run_ours(args):
             t = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-        loss_val = float(run_step().item())
-        exchange = None
+            res["e2e_ms"] = float(t.item())
+        res["loss"] = float(run_step().item())
         if reducer is not None:
-            exchange = reducer.exchange_mode  # "nccl" if the peer-memory arena could not be built on this box
+            res["exchange"] = {"raw_dw": reducer.exchange_mode, "hook": reducer.hook_exchange}
             reducer.remove()
-        return dict(ms=ms, e2e_ms=e2e_ms, launches=launches, loss=loss_val, graph=graph is not None, layers=layers,
-                    exchange=exchange)
+        return res
+
+    def roofline_of(name, r):
+        """Dominant kernel = the tcgen05 GEMM: algorithmic FLOPs of the step ÷ the GEMM launches' summed device time
+        INSIDE the measured step (CUPTI), against the burst bf16 peak (conservative; the sustained figure is given too).
+        cfg1 is launch-bound fp32 (FFMA SGEMM): reported against HBM on its minimum traffic."""
+        wl = r["wl"]
+        k = r.get("kernels") or {}
+        gemm = [(n, v) for n, v in k.items() if "gemm_bf16_kernel" in n or "gemm_f32" in n or "sgemm" in n.lower()]
+        gemm_us = sum(v[0] for _, v in gemm)
+        n_launch = sum(v[1] for _, v in gemm)
+        total_us = sum(v[0] for v in k.values())
+        if wl.get("bound") == "launch latency":
+            ach = wl["min_bytes"] / (r["ms"] * 1e-3) / 1e9
+            return {"bound": "hbm", "kernel": "whole step (launch-bound, one CUDA graph)", "achieved": ach,
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+                    "note": "minimum traffic 9 MB/step (SURVEY.md §8d); the step is launch-latency bound",
+                    "kernel_us_per_step": total_us or None, "peak_source": pk["src"]}
+        if not gemm_us:
+            ach = wl["flops"] / (r["ms"] * 1e-3) / 1e12
+            return {"bound": "tensor", "kernel": "whole step (no kernel timeline)", "achieved": ach, "peak": pk["bf16"],
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16"], "traffic": None, "peak_source": pk["src"]}
+        ach = wl["flops"] / (gemm_us * 1e-6) / 1e12
+        return {"bound": "tensor", "kernel": f"ed2::tc::gemm_bf16_kernel ({n_launch:.0f} launches per step, timed in-step)",
+                "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
+                "frac_of_sustained": ach / pk["bf16_sustained"], "traffic": NCU_TRAFFIC.get(name),
+                "traffic_unit": "bytes/launch (ncu --set full capture, profiles/)" if NCU_TRAFFIC.get(name) else None,
+                "gemm_us_per_step": gemm_us, "all_kernels_us_per_step": total_us,
+                "gemm_share_of_kernel_time": gemm_us / total_us if total_us else None,
+                "algorithmic_flops_per_step": wl["flops"], "peak_source": pk["src"] + ", burst bf16"}
+
+    def cpu_of(r, steps):
+        try:
+            sps, dt, th, sample = r["wl"]["cpu"](steps)
+            return {"value": sps, "unit": "samples/s", "cores": th, "kind": "port", "sample": sample, "s_per_step": dt}
+        except Exception as e:  # noqa: BLE001
+            return {"error": str(e)[:200]}
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    main = measure(False, args.steps, args.warmup, True)
+    head = measure(args.workload, args.steps, args.warmup, True, True)
     clocks = sampler.stop() if sampler else None
-    del main["layers"]
+    head_roof = roofline_of(args.workload, head)
+    head_cpu = cpu_of(head, 3) if (rank == 0 and world == 1 and not args.skip_cpu) else None
+    head.pop("wl")
     torch.cuda.empty_cache()
-    flip = None
-    if not args.skip_variants:
-        try:
-            flip = measure(True, max(3, args.steps // 2), 3, False)
-            del flip["layers"]
-        except Exception as e:  # noqa: BLE001
-            flip = {"error": str(e)[:200]}
-        torch.cuda.empty_cache()
 
-    # ---- roofline of the dominant kernel (tcgen05 GEMM): the 8 GEMM launches of one step, timed alone
-    roof = None
-    try:
-        shapes = []
-        for li, (i, o) in enumerate(zip(DIMS[:-1], DIMS[1:])):
-            shapes.append(("fwd", BATCH, o, i, ops.MAJOR_K, ops.MAJOR_MN))
-            shapes.append(("dW", i, o, BATCH, ops.MAJOR_MN, ops.MAJOR_MN))
-            if li > 0:
-                shapes.append(("dX", BATCH, i, o, ops.MAJOR_K, ops.MAJOR_K))
-        bufs = []
-        for (_, m, n, k, ma, mb) in shapes:
-            a = torch.randn((m, k) if ma == ops.MAJOR_K else (k, m), device=device).to(torch.bfloat16)
-            b = torch.randn((n, k) if mb == ops.MAJOR_K else (k, n), device=device).to(torch.bfloat16)
-            out = _lib.empty_padded(m, n, torch.float32 if _ == "dW" else torch.bfloat16, device)
-            bufs.append((a, b, out))
-        def gemms():
-            for (_, m, n, k, ma, mb), (a, b, out) in zip(shapes, bufs):
-                ops.gemm(a, b, m, n, k, major_a=ma, major_b=mb, out=out)
-        for _ in range(3):
-            gemms()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            gemms()
-        e1.record()
-        torch.cuda.synchronize()
-        gemm_ms = e0.elapsed_time(e1) / reps
-        fl = flops_per_step(BATCH, False)
-        achieved = fl / (gemm_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "ed2::tc::gemm_bf16_kernel (8 launches per step)", "achieved": achieved,
-                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
-                # DRAM bytes per GEMM launch (read + write, mean of the step's 8 launches) from the committed
-                # `ncu --set full` capture of this workload (profiles/r01_ncu_summary.csv); algorithmic operand + output
-                # bytes are 83.7 MB per launch, the difference is operands still resident in the 126 MB L2
-                "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch (ncu capture, profiles/)",
-                "algorithmic_bytes_per_launch": 83.7e6,
-                "peak_source": pk["src"], "gemm_ms_per_step": gemm_ms, "algorithmic_flops_per_step": fl,
-                "gemm_share_of_step": gemm_ms / main["ms"]}
-        del bufs
-    except Exception as e:  # noqa: BLE001
-        roof = {"error": str(e)[:200]}
+    others = {}
+    if world == 1 and not args.skip_variants:
+        for name in WORKLOADS:
+            if name == args.workload or (args.only and name not in args.only.split(",")):
+                continue
+            try:
+                r = measure(name, max(5, args.steps // 2), 3, False, True)
+                entry = {"workload": r["workload"], "ms_per_step": r["ms"], "value": r["batch"] / (r["ms"] * 1e-3),
+                         "unit": "samples/s", "dtype": r["dtype"], "cuda_graph": r["graph"],
+                         "gpu_launches_per_step": r["launches"] // max(5, args.steps // 2),
+                         "step_tflops": r["flops"] / (r["ms"] * 1e-3) / 1e12,
+                         "step_frac_of_burst_peak": r["flops"] / (r["ms"] * 1e-3) / 1e12 / pk["bf16"],
+                         "roofline": roofline_of(name, r), "loss": r["loss"]}
+                if not args.skip_cpu:
+                    entry["cpu_baseline"] = cpu_of(r, 2)
+                others[name] = entry
+                del r
+            except Exception as e:  # noqa: BLE001
+                others[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    cpu = None
-    if world == 1 and not args.skip_cpu:
-        try:
-            from oracle import torch_cpu
-
-            sps, dt, threads = torch_cpu.time_bayesian_mlp(DIMS, BATCH, False, steps=4, warmup=1)
-            cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                   "sample": f"4 fwd+bwd steps on {BATCH}-row batches of the cfg2 MLP (torch-CPU fp32 restatement)",
-                   "s_per_step": dt}
-        except Exception as e:  # noqa: BLE001
-            cpu = {"error": str(e)[:200]}
-
-    value = global_batch / (main["ms"] * 1e-3)
-    fl = flops_per_step(BATCH, False)
+    gb = head["batch"] * world
     line = {
-        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": main["ms"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}",
-                   "l2": "inputs > L2: one step touches ~0.6 GB (fp32 mu/rho + grads 400 MB, bf16 W 50 MB, activations)",
-                   "cuda_graph": main["graph"], "kl_scale": KL_SCALE,
-                   "grad_allreduce": None if world == 1 else (
-                       "fp32 NCCL all-reduce per parameter, overlapped with backward" if args.fp32_allreduce else
-                       "raw bf16 dW through IPC peer memory: pull reduce-scatter + all-gather fused into the finishing "
-                       "pass (own kernels, no NCCL on the data path)" if main.get("exchange") == "peer" else
-                       "bf16 buckets, NCCL all-reduce per parameter, overlapped with backward"),
+        "metric": METRIC, "value": gb / (head["ms"] * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": head["ms"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+        "config": {"workload": head["workload"], "global_batch": gb, "parallelism": f"dp{world}",
+                   "l2": "inputs > L2: one cfg4 step touches ~1.1 GB (fp32 kernels + grads 737 MB, bf16 kernels 184 MB, "
+                         "activations) against a 126 MB L2",
+                   "cuda_graph": head["graph"], "kl_scale": KL_SCALE,
+                   "grad_allreduce": None if world == 1 else head["exchange"],
                    "gemm_ctas": int(os.environ.get("ED2_GEMM_MAX_CTAS", 148))},
-        "e2e": {"value": global_batch / (main["e2e_ms"] * 1e-3), "unit": "samples/s",
-                "h2d_bytes_per_step": (x_host.numel() * 2 + y_host.numel() * 8) * world,
-                "d2h_bytes_per_step": 8 * world, "ms_per_step": main["e2e_ms"]},
-        "gpu_launches": main["launches"],
+        "e2e": {"value": gb / (head["e2e_ms"] * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": head["h2d"] * world,
+                "d2h_bytes_per_step": 8 * world, "ms_per_step": head["e2e_ms"]},
+        "gpu_launches": head["launches"],
         "clocks": clocks,
-        "roofline": roof,
-        "cpu_baseline": cpu,
-        "step_tflops": fl * world / (main["ms"] * 1e-3) / 1e12,
-        "step_frac_of_tensor_peak": fl / (main["ms"] * 1e-3) / 1e12 / pk["bf16"],
-        "loss": main["loss"],
-        "variants": {"flipout": None if flip is None else (
-            flip if "error" in flip else {"value": global_batch / (flip["ms"] * 1e-3), "ms_per_step": flip["ms"],
-                                          "step_tflops": flops_per_step(BATCH, True) * world / (flip["ms"] * 1e-3) / 1e12,
-                                          "loss": flip["loss"]})},
+        "roofline": head_roof,
+        "cpu_baseline": head_cpu,
+        "step_tflops": head["flops"] * world / (head["ms"] * 1e-3) / 1e12,
+        "step_frac_of_burst_peak": head["flops"] / (head["ms"] * 1e-3) / 1e12 / pk["bf16"],
+        "loss": head["loss"],
+        "configs": others,
     }
     emit(line)
     if world > 1:
@@ -478,13 +668,18 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS),
+                    help="headline workload of the line (default cfg4); the others are reported under 'configs' at N=1")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
-    ap.add_argument("--trace", default="", help="write a chrome trace of 3 steps on rank 0 (diagnostics)")
     ap.add_argument("--fp32-allreduce", action="store_true", help="all-reduce fp32 gradients instead of bf16 buckets")
     ap.add_argument("--grad-exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: how the raw bf16 weight gradients are summed over ranks")
+                    help="N > 1: how raw bf16 weight gradients (Reparameterization kernels) are summed over ranks")
+    ap.add_argument("--hook-exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how gradients reaching the per-parameter hook (rank-1 / BatchEnsemble kernels) are summed")
     ap.add_argument("--gemm-ctas", type=int, default=0, help="persistent GEMM CTAs when N > 1 (rest: NCCL)")
     ap.add_argument("--no-allreduce", action="store_true", help="diagnostic only: skip the gradient all-reduce")
+    ap.add_argument("--dump-kernels", default="", help="append per-kernel in-step device times (CUPTI) to this file")
+    ap.add_argument("--only", default="", help="comma-separated subset of the N=1 'configs' block (diagnostics)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-variants", action="store_true")
     args = ap.parse_args()

@@ -251,7 +251,10 @@ class GradientAllReduce:
 
     # -- early path: called by the layer's backward between its parameter-gradient phase and its dX GEMM -------------
     def wants(self, p) -> bool:
-        return self.world > 1 and self.compress is not None and id(p) in self._ids and p.numel() >= 65536
+        # average=True is applied by the per-parameter hook only: the raw-dW paths (which finish dmu / drho after the
+        # exchange) are sum-only, so an averaging reducer keeps every parameter on the hook path
+        return (self.world > 1 and self.compress is not None and not self.average and id(p) in self._ids
+                and p.numel() >= 65536)
 
     def wants_peer(self, p) -> bool:
         return (self.exchange_mode == "peer" and self.wants(p) and not self.average and p.numel() % 8 == 0
