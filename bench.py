@@ -131,6 +131,7 @@ def wl_cfg4(ed, device, step_counter, rank, world):
         gamma_regularizer=ed.regularizers.NormalKLDivergence(mean=1.0, stddev=0.1, scale_factor=KL_SCALE))
     layers = [mk(8192, "relu", 0), mk(8192, "relu", 1), mk(1000, None, 2)]
     _warm_build(layers, torch.zeros(8, CFG4_DIMS[0], dtype=torch.bfloat16, device=device))
+    layers[0].feeds(layers[1]).feeds(layers[2])  # stacked rank-1 layers: cross-layer epilogue fusion (Rank1Link)
     for l in layers:
         l.step_counter = step_counter
     model = torch.nn.ModuleList(layers)
@@ -455,6 +456,8 @@ def run_ours(args):
                 graph, static_loss = None, None
                 if reducer is not None:
                     reducer.handles.clear()
+                    for ex in reducer._exchanges.values():
+                        ex._pending = False
                 torch.cuda.synchronize()
 
         def run_step():

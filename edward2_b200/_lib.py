@@ -77,6 +77,8 @@ class Rank1Fwd(C.Structure):
         ("y", _vp), ("y_ld", _i), ("xr", _vp), ("xr_ld", _i), ("s_buf", _vp), ("s_ld", _i), ("z", _vp), ("z_ld", _i),
         ("additive", _i), ("clip_lo", _f), ("clip_hi", _f),
         ("rho_b", _vp), ("eps_b", Noise), ("bias_buf", _vp), ("bias_ld", _i),
+        ("fast_ws", _vp), ("xr_ready", _i),
+        ("next_mu_r", _vp), ("next_rho_r", _vp), ("next_eps_r", Noise), ("next_xr", _vp), ("next_xr_ld", _i),
     ]
 
 
@@ -92,6 +94,10 @@ class Rank1Bwd(C.Structure):
         ("dw", _vp), ("dmu_r", _vp), ("drho_r", _vp), ("dmu_s", _vp), ("drho_s", _vp), ("dbias", _vp),
         ("additive", _i), ("clip_lo", _f), ("clip_hi", _f),
         ("rho_b", _vp), ("eps_b", Noise), ("drho_b", _vp),
+        ("fast_ws", _vp), ("dz_ready", _i),
+        ("prev_z", _vp), ("prev_z_ld", _i), ("prev_mu_s", _vp), ("prev_rho_s", _vp), ("prev_eps_s", Noise),
+        ("prev_act", _i), ("prev_dz", _vp), ("prev_dz_ld", _i),
+        ("prev_dmu_s", _vp), ("prev_drho_s", _vp), ("prev_dbias", _vp),
     ]
 
 
@@ -177,6 +183,8 @@ SIGNATURES = {
     "ed2_be_dense_bwd": (_i, [C.POINTER(BeBwd), _vp]),
     "ed2_rank1_dense_fwd": (_i, [C.POINTER(Rank1Fwd), _vp]),
     "ed2_rank1_dense_bwd": (_i, [C.POINTER(Rank1Bwd), _vp]),
+    "ed2_rank1_fusable": (_i, [_i, _i, _i]),
+    "ed2_rank1_workspace_floats": (_ll, [_i, _i, _i]),
     "ed2_reparam_dense_fwd": (_i, [C.POINTER(ReparamFwd), _vp]),
     "ed2_reparam_dense_bwd": (_i, [C.POINTER(ReparamBwd), _vp]),
     "ed2_normal_grad_finish": (_i, [_vp, _i, _vp, _vp, Noise, _ll, _f, _vp, _f, _f, _vp, _vp, _i, _vp]),

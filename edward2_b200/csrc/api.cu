@@ -7,6 +7,7 @@
 #include "gemm.h"
 #include "kernels.h"
 #include "status.h"
+#include <algorithm>
 
 using namespace ed2;
 
@@ -28,6 +29,15 @@ inline FastOpts opts_of(int additive, float lo, float hi) {
     int _st = (expr);            \
     if (_st != ED2_OK) return _st; \
   } while (0)
+
+FastSide fast_side(const float* mu, const float* sg, const float* sgm, const ed2_noise& n) {
+  FastSide f{};
+  f.mu = mu; f.sg = sg; f.sgm = sgm;
+  f.seed = n.seed; f.stream = n.stream; f.step = reinterpret_cast<const unsigned long long*>(n.step);
+  f.row0 = n.row0; f.rpg_local = n.rows_per_group_local; f.rpg_global = n.rows_per_group_global;
+  return f;
+}
+inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 EpiParams epi_default() {
   EpiParams e{};
@@ -265,8 +275,45 @@ int ed2_rank1_dense_fwd(const ed2_rank1_fwd_args* a, void* stream) {
   cudaStream_t s = S(stream);
   const int rpm = a->batch / a->ensemble_size;
   const FastOpts fo = opts_of(a->additive, a->clip_lo, a->clip_hi);
-  ED2_TRY(k_scale_rows(a->x, a->dtype, a->x_ld, a->batch, a->in_dim, rpm, 1, a->mu_r, a->rho_r, N(a->eps_r), a->xr,
-                       a->xr_ld, nullptr, 0, s, fo));
+  if (!a->xr_ready)
+    ED2_TRY(k_scale_rows(a->x, a->dtype, a->x_ld, a->batch, a->in_dim, rpm, 1, a->mu_r, a->rho_r, N(a->eps_r), a->xr,
+                         a->xr_ld, nullptr, 0, s, fo));
+  const bool fused = a->fast_ws != nullptr && a->s_buf == nullptr && a->dtype == kBF16 && !a->additive && a->rho_b == nullptr &&
+                     a->eps_s.injected == nullptr && (a->next_mu_r == nullptr || a->next_eps_r.injected == nullptr) &&
+                     gemm_rank1_fusable(a->batch, a->out_dim, rpm) && al16p(a->mu_s) &&
+                     (a->bias == nullptr || al16p(a->bias)) && (a->next_mu_r == nullptr || al16p(a->next_mu_r));
+  if (fused) {
+    const long long slot = static_cast<long long>(a->ensemble_size) * std::max(a->in_dim, a->out_dim);
+    const long long n = static_cast<long long>(a->ensemble_size) * a->out_dim;
+    float* ws = a->fast_ws;
+    if (a->rho_s != nullptr) ED2_TRY(k_fast_prep(a->rho_s, n, ws, ws + slot, s));
+    if (a->next_mu_r != nullptr && a->next_rho_r != nullptr) ED2_TRY(k_fast_prep(a->next_rho_r, n, ws + 2 * slot, ws + 3 * slot, s));
+    Rank1Epi r{};
+    r.s = fast_side(a->mu_s, a->rho_s ? ws : nullptr, ws + slot, a->eps_s);
+    if (a->next_mu_r != nullptr) {
+      r.r = fast_side(a->next_mu_r, a->next_rho_r ? ws + 2 * slot : nullptr, ws + 3 * slot, a->next_eps_r);
+      r.out2 = a->next_xr; r.out2_ld = a->next_xr_ld;
+    }
+    r.clip_lo = fo.clip_lo; r.clip_hi = fo.clip_hi;
+    EpiParams e = epi_default();
+    e.group_rows = rpm;
+    e.col_bias = a->bias; e.col_bias_ld = a->out_dim;
+    e.act = a->act;
+    e.out = a->y; e.out_ld = a->y_ld; e.out_dt = a->dtype;
+    e.raw = a->z; e.raw_ld = a->z_ld; e.raw_dt = a->dtype;
+    GemmDesc g{};
+    g.A = a->xr; g.lda = a->xr_ld; g.major_a = kMajorK;
+    g.B = a->w_lp; g.ldb = a->w_ld; g.major_b = kMajorMN;
+    g.M = a->batch; g.N = a->out_dim; g.K = a->in_dim;
+    g.ep = e; g.epi_mode = kEpiRank1Fwd; g.r1 = &r;
+    return gemm_bf16(g, s);
+  }
+  if (a->next_mu_r != nullptr)
+    return set_error(ED2_ERR_BAD_ARG, "rank1_fwd: next_* needs the fused path (fast_ws, s_buf == NULL, ed2_rank1_fusable)");
+  if (a->s_buf == nullptr)
+    return set_error(ED2_ERR_BAD_ARG, "rank1_fwd: s_buf is required on the unfused path (this call does not qualify for "
+                                      "the fused one: ED2_BF16, Philox noise, multiplicative, deterministic bias, "
+                                      "ed2_rank1_fusable(batch, out_dim, E))");
   FastOpts fs = fo;
   fs.additive = 0;  // the factor itself is written; the epilogue multiplies or adds it
   ED2_TRY(k_scale_rows(nullptr, a->dtype, 0, a->batch, a->out_dim, rpm, 1, a->mu_s, a->rho_s, N(a->eps_s), nullptr, 0,
@@ -314,10 +361,55 @@ int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream) {
   o.rho_b = a->rho_b; o.eps_b = N(a->eps_b); o.d_bias_rho = a->rho_b ? a->drho_b : nullptr;
   o.dz = a->dz; o.dz_ld = a->dz_ld;
   o.d_fast_mu = a->dmu_s; o.d_fast_rho = a->rho_s ? a->drho_s : nullptr; o.dbias = a->dbias;
-  ED2_TRY(k_bwd_out(o, s));
+  if (!a->dz_ready) ED2_TRY(k_bwd_out(o, s));
   EpiParams e = epi_default();
   e.out = a->dw; e.out_ld = a->out_dim; e.out_dt = kF32;
   ED2_TRY(gemm_xtg(a->dtype, a->xr, a->xr_ld, a->dz, a->dz_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  const bool has_prev = a->prev_mu_s != nullptr;
+  const bool fused = a->fast_ws != nullptr && a->dtype == kBF16 && !a->additive && a->eps_r.injected == nullptr &&
+                     (!has_prev || a->prev_eps_s.injected == nullptr) && gemm_rank1_fusable(a->batch, a->in_dim, rpm) &&
+                     al16p(a->mu_r) && al16p(a->x) && a->x_ld % 8 == 0 &&
+                     (!has_prev || (al16p(a->prev_mu_s) && al16p(a->prev_z) && a->prev_z_ld % 8 == 0));
+  if (fused) {
+    const long long slot = static_cast<long long>(a->ensemble_size) * std::max(a->in_dim, a->out_dim);
+    const long long n = static_cast<long long>(a->ensemble_size) * a->in_dim;
+    const size_t bytes = sizeof(float) * static_cast<size_t>(n);
+    float* ws = a->fast_ws;
+    if (a->rho_r != nullptr) ED2_TRY(k_fast_prep(a->rho_r, n, ws, ws + slot, s));
+    if (has_prev && a->prev_rho_s != nullptr) ED2_TRY(k_fast_prep(a->prev_rho_s, n, ws + 2 * slot, ws + 3 * slot, s));
+    cudaMemsetAsync(a->dmu_r, 0, bytes, s);
+    if (a->rho_r != nullptr) cudaMemsetAsync(a->drho_r, 0, bytes, s);
+    Rank1Epi r{};
+    r.r = fast_side(a->mu_r, a->rho_r ? ws : nullptr, ws + slot, a->eps_r);
+    r.clip_lo = o.opts.clip_lo; r.clip_hi = o.opts.clip_hi;
+    r.x = a->x; r.x_ld = a->x_ld;
+    r.dmu_r = a->dmu_r; r.drho_r = a->rho_r ? a->drho_r : nullptr;
+    EpiParams e2 = epi_default();
+    e2.group_rows = rpm;
+    if (has_prev) {
+      if (a->prev_z == nullptr || a->prev_dz == nullptr || a->prev_dmu_s == nullptr)
+        return set_error(ED2_ERR_BAD_ARG, "rank1_bwd: prev_z, prev_dz and prev_dmu_s are required with prev_mu_s");
+      cudaMemsetAsync(a->prev_dmu_s, 0, bytes, s);
+      if (a->prev_rho_s != nullptr) cudaMemsetAsync(a->prev_drho_s, 0, bytes, s);
+      if (a->prev_dbias != nullptr) cudaMemsetAsync(a->prev_dbias, 0, bytes, s);
+      r.s = fast_side(a->prev_mu_s, a->prev_rho_s ? ws + 2 * slot : nullptr, ws + 3 * slot, a->prev_eps_s);
+      r.z_prev = a->prev_z; r.z_prev_ld = a->prev_z_ld; r.prev_act = a->prev_act;
+      r.dmu_s = a->prev_dmu_s; r.drho_s = a->prev_rho_s ? a->prev_drho_s : nullptr; r.dbias = a->prev_dbias;
+      e2.out = a->prev_dz; e2.out_ld = a->prev_dz_ld; e2.out_dt = kBF16;
+      r.out2 = a->dx; r.out2_ld = a->dx_ld;
+    } else {
+      e2.out = a->dx; e2.out_ld = a->dx_ld; e2.out_dt = kBF16;
+    }
+    GemmDesc g{};
+    g.A = a->dz; g.lda = a->dz_ld; g.major_a = kMajorK;
+    g.B = a->w_lp; g.ldb = a->w_ld; g.major_b = kMajorK;
+    g.M = a->batch; g.N = a->in_dim; g.K = a->out_dim;
+    g.ep = e2; g.epi_mode = kEpiRank1Bwd; g.r1 = &r;
+    return gemm_bf16(g, s);
+  }
+  if (has_prev)
+    return set_error(ED2_ERR_BAD_ARG, "rank1_bwd: prev_* needs the fused path (fast_ws and ed2_rank1_fusable(batch, in_dim, E))");
+  if (a->dxr == nullptr) return set_error(ED2_ERR_BAD_ARG, "rank1_bwd: dxr workspace is required on the unfused path");
   EpiParams e2 = epi_default();
   e2.out = a->dxr; e2.out_ld = a->dxr_ld; e2.out_dt = a->dtype;
   ED2_TRY(gemm_gwt(a->dtype, a->dz, a->dz_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s));
@@ -329,6 +421,15 @@ int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream) {
   i.dx = a->dx; i.dx_ld = a->dx_ld;
   i.d_fast_mu = a->dmu_r; i.d_fast_rho = a->rho_r ? a->drho_r : nullptr;
   return k_bwd_in(i, s);
+}
+
+int ed2_rank1_fusable(int batch, int cols, int ensemble_size) {
+  if (ensemble_size <= 0 || batch % ensemble_size != 0) return 0;
+  return gemm_rank1_fusable(batch, cols, batch / ensemble_size) ? 1 : 0;
+}
+
+long long ed2_rank1_workspace_floats(int ensemble_size, int in_dim, int out_dim) {
+  return 4LL * ensemble_size * std::max(in_dim, out_dim);
 }
 
 // ------------------------------------------------------------------------------------------ Reparameterization

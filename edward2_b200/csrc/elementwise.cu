@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kBlock, 6) grad_finish_peer_kernel(PeerExchang
   if (small_out != nullptr) {
     for (long long j = blockIdx.x * (long long)kBlock + threadIdx.x; j < x.small_n; j += (long long)gridDim.x * kBlock) {
       float s = 0.f;
-      for (int q = 0; q < x.world; ++q) s += peer::ld_sys_f32(x.small[q] + j);
+      for (int q = 0; q < x.world; ++q) s += peer::ld_sys_f32(x.small[q] + (epoch & 1ull) * x.small_n + j);
       small_out[j] = s;
     }
   }
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(kBlock) rank1_bwd_out_lean_kernel(BwdOutArgs a
     float g[8], yv[8], zv[8], sv[8], en[8], o[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(gy + r * a.gy_ld + c)), g);
     unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * a.z_ld + c)), zv);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(sb + r * a.s_ld + c)), sv);
+    if (sb != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(sb + r * a.s_ld + c)), sv);
     if (a.act == kActRelu) {
       unpack8(__ldg(reinterpret_cast<const uint4*>(y + r * a.y_ld + c)), yv);
 #pragma unroll
@@ -692,7 +692,8 @@ __global__ void __launch_bounds__(kBlock) rank1_bwd_out_lean_kernel(BwdOutArgs a
       acc_b[j] += g[j];
       acc_mu[j] += ds;
       acc_rho[j] += ds * en[j] * k.sgm[j];
-      o[j] = g[j] * sv[j];
+      // s was not saved (fused forward): it is the clipped draw itself
+      o[j] = g[j] * (sb != nullptr ? sv[j] : fminf(fmaxf(raw, -kClip), kClip));
     }
     *reinterpret_cast<uint4*>(dz + r * a.dz_ld + c) = pack8(o);
   }
@@ -1216,6 +1217,21 @@ int k_peer_grad_finish(const PeerExchange& x, const float* mu, const float* rho,
   return check_launch("peer_grad_finish");
 }
 
+__global__ void fast_prep_kernel(const float* __restrict__ rho, long long n, float* __restrict__ sg, float* __restrict__ sgm) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float r = __ldg(rho + i);
+    sg[i] = softplus_f(r) + kSoftplusEps;
+    sgm[i] = sigmoid_f(r);
+  }
+}
+
+int k_fast_prep(const float* rho, long long n, float* sg, float* sgm, cudaStream_t s) {
+  if (n <= 0) return ED2_OK;
+  fast_prep_kernel<<<static_cast<int>(std::min<long long>((n + kBlock - 1) / kBlock, 1024)), kBlock, 0, s>>>(rho, n, sg, sgm);
+  count_launch();
+  return check_launch("fast_prep");
+}
+
 int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols, int rpm, int mode,
                  const float* fw_mu, const float* fw_rho, Noise nz, void* xo, long long xo_ld, void* f_out,
                  long long f_ld, cudaStream_t s, FastOpts fo) {
@@ -1258,14 +1274,16 @@ int k_bwd_out(const BwdOutArgs& a_in, cudaStream_t s) {
   if (a.d_bias_rho) cudaMemsetAsync(a.d_bias_rho, 0, bytes, s);
   const bool default_opts = a.opts.clip_lo == -kClip && a.opts.clip_hi == kClip && !a.opts.additive && a.rho_b == nullptr;
   if (default_opts && a.fast == 2 && a.dt == kBF16 && a.rho_s != nullptr && a.eps_s.injected == nullptr && a.cols % 8 == 0 &&
-      a.gy_ld % 8 == 0 && a.y_ld % 8 == 0 && a.z_ld % 8 == 0 && a.s_ld % 8 == 0 && a.dz_ld % 8 == 0 && al16(a.gy) &&
-      al16(a.y) && al16(a.z) && al16(a.s_buf) && al16(a.dz) && al16(a.mu_s) && al16(a.rho_s) && a.d_fast_mu != nullptr) {
+      a.gy_ld % 8 == 0 && a.y_ld % 8 == 0 && a.z_ld % 8 == 0 && (a.s_buf == nullptr || (a.s_ld % 8 == 0 && al16(a.s_buf))) &&
+      a.dz_ld % 8 == 0 && al16(a.gy) && al16(a.y) && al16(a.z) && al16(a.dz) && al16(a.mu_s) && al16(a.rho_s) && a.d_fast_mu != nullptr) {
     const int lchunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
     dim3 lgrid((a.cols / 8 + kBlock - 1) / kBlock, members * lchunks);
     rank1_bwd_out_lean_kernel<<<lgrid, kBlock, 0, s>>>(a);
     count_launch();
     return check_launch("bwd_out(lean rank-1)");
   }
+  if (a.fast == 2 && a.s_buf == nullptr && !a.opts.additive)
+    return set_error(ED2_ERR_BAD_ARG, "rank-1 backward: s_buf is required on the general (non-lean) path");
   const int chunks = (a.rows_per_member + kRowsPerBlock - 1) / kRowsPerBlock;
   dim3 grid((a.cols + 127) / 128, members * chunks);
   switch (a.fast) {

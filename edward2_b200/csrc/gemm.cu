@@ -65,11 +65,11 @@ int num_sms() {
   return n;
 }
 
-template <int MA, int MB, int BN, int CG>
+template <int MA, int MB, int BN, int CG, int EPI = kEpiGeneric>
 int launch_one(const GemmDesc& g, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                cudaStream_t stream) {
-  using Cfg = tc::Config<BN, CG>;
-  auto kern = tc::gemm_bf16_kernel<MA, MB, BN, CG>;
+  using Cfg = tc::Config<BN, CG, EPI>;
+  auto kern = tc::gemm_bf16_kernel<MA, MB, BN, CG, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -98,7 +98,8 @@ int launch_one(const GemmDesc& g, const CUtensorMap& ta, const CUtensorMap& tb, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, g.M, g.N, g.K, g.ep);
+  static const Rank1Epi kNoRank1{};
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, g.M, g.N, g.K, g.ep, g.r1 != nullptr ? *g.r1 : kNoRank1);
   if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return ED2_OK;
@@ -126,6 +127,11 @@ int default_cta_group() {
 
 }  // namespace
 
+bool gemm_rank1_fusable(int M, int N, int group_rows) {
+  // one 2-CTA 256x256 configuration; every warp's 32 rows must belong to one member; 4-column noise blocks
+  return M > 128 && N % 8 == 0 && (group_rows == 0 || group_rows % 32 == 0);
+}
+
 int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
   GemmDesc g = g_in;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(ED2_ERR_BAD_SHAPE, "gemm: empty shape %d %d %d", g.M, g.N, g.K);
@@ -135,6 +141,12 @@ int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
   int bn = g.block_n ? g.block_n : (g.N > 128 ? 256 : 128);
   int cg = g.cta_group ? g.cta_group : default_cta_group();
   if (cg == 2 && g.M <= 128) cg = 1;
+  if (g.epi_mode != kEpiGeneric) {
+    if (g.r1 == nullptr || !gemm_rank1_fusable(g.M, g.N, g.ep.group_rows))
+      return set_error(ED2_ERR_BAD_ARG, "gemm: fused rank-1 epilogue not available for M=%d N=%d group_rows=%d", g.M,
+                       g.N, g.ep.group_rows);
+    bn = 256; cg = 2;
+  }
   const int load_n = bn / cg;
 
   CUtensorMap ta, tb, to;
@@ -148,11 +160,20 @@ int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
 
   const int oes = g.ep.out_dt == kBF16 ? 2 : 4;
   g.ep.out_tma = 0;
-  if (g.ep.out == nullptr && g.ep.row_sum == nullptr) return set_error(ED2_ERR_BAD_ARG, "gemm: out is null");
+  if (g.ep.out == nullptr && g.ep.row_sum == nullptr && g.epi_mode != kEpiRank1Bwd)
+    return set_error(ED2_ERR_BAD_ARG, "gemm: out is null");
   if (g.ep.out != nullptr && !g.no_tma_store && tma_ok(g.ep.out, g.ep.out_ld, oes)) {
     if (make_map(&to, g.ep.out, g.ep.out_dt, g.M, g.N, g.ep.out_ld, tc::kBlockM, 128 / oes)) g.ep.out_tma = 1;
   }
 
+  if (g.epi_mode == kEpiRank1Fwd) {
+    if (g.major_a != kMajorK || g.major_b != kMajorMN) return set_error(ED2_ERR_BAD_ARG, "rank-1 fwd epilogue: layout");
+    return launch_one<kMajorK, kMajorMN, 256, 2, kEpiRank1Fwd>(g, ta, tb, to, stream);
+  }
+  if (g.epi_mode == kEpiRank1Bwd) {
+    if (g.major_a != kMajorK || g.major_b != kMajorK) return set_error(ED2_ERR_BAD_ARG, "rank-1 bwd epilogue: layout");
+    return launch_one<kMajorK, kMajorK, 256, 2, kEpiRank1Bwd>(g, ta, tb, to, stream);
+  }
   if (g.major_a == kMajorK && g.major_b == kMajorK) return dispatch_cfg<kMajorK, kMajorK>(g, bn, cg, ta, tb, to, stream);
   if (g.major_a == kMajorK && g.major_b == kMajorMN) return dispatch_cfg<kMajorK, kMajorMN>(g, bn, cg, ta, tb, to, stream);
   if (g.major_a == kMajorMN && g.major_b == kMajorK) return dispatch_cfg<kMajorMN, kMajorK>(g, bn, cg, ta, tb, to, stream);

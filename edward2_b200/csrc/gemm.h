@@ -18,7 +18,12 @@ struct GemmDesc {
   int cta_group;     // 0 = auto, else 1 | 2
   int max_ctas;      // 0 = all SMs
   int no_tma_store;  // force the direct-store epilogue (testing)
+  int epi_mode = kEpiGeneric;       // kEpiRank1Fwd / kEpiRank1Bwd: fused rank-1 epilogue described by *r1
+  const Rank1Epi* r1 = nullptr;
 };
+
+// true when gemm_bf16 can run the fused rank-1 epilogue for this shape (else the caller takes the unfused path)
+bool gemm_rank1_fusable(int M, int N, int group_rows);
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);  // tcgen05 tensor cores
 int gemm_f32(const GemmDesc& g, cudaStream_t stream);   // fp32 FFMA path

@@ -50,4 +50,39 @@ struct EpiParams {
   int col_sum_ld;
 };
 
+// ---- fused rank-1 epilogues (DenseRank1, edward2/tensorflow/layers/dense.py:1096-1144) -------------------------------
+// One per-example fast-weight stream f[m,n] = clip(mu[e,n] + sg[e,n] * eps(m,n), lo, hi), e = m / group_rows, with eps
+// regenerated from Philox by GLOBAL row (philox.cuh Noise row mapping).  sg == nullptr: deterministic f = mu[e,n].
+struct FastSide {
+  const float* mu;            // [E][N]
+  const float* sg;            // [E][N] softplus(rho) + 1e-7, precomputed (k_fast_prep); nullptr = deterministic
+  const float* sgm;           // [E][N] sigmoid(rho)            (backward only)
+  unsigned long long seed, stream;
+  const unsigned long long* step;
+  long long row0;
+  int rpg_local, rpg_global;
+};
+
+enum : int { kEpiGeneric = 0, kEpiRank1Fwd = 1, kEpiRank1Bwd = 2 };
+
+// kEpiRank1Fwd  (GEMM = (x∘r) W, M = batch, N = out_dim):
+//   z = acc -> raw;  y = act(z * s[m,n] + col_bias[e,n]) -> out;  out2 = bf16(y) * r_next[m,n]   (out2 optional: the
+//   NEXT layer's x∘r, so that layer needs no scale pass)
+// kEpiRank1Bwd  (GEMM = dz Wᵀ, M = batch, N = in_dim of this layer = out_dim of the producer):
+//   dxr = acc;  dx = dxr * r[m,n];  dr = dxr * x * 1[r unclipped]  ->  dmu_r[e,n] += dr, drho_r[e,n] += dr*eps_r*sgm_r
+//   without a producer:  dx -> out (optional)
+//   with a producer (s.mu != nullptr; its y is this layer's x, its z = z_prev):
+//     dx -> out2 (optional);  gp = bf16(dx) * act'(x);  dz_prev = gp * s[m,n] -> out;
+//     ds = gp * z_prev * 1[s unclipped] -> dmu_s, drho_s;  dbias[e,n] += gp
+struct Rank1Epi {
+  FastSide s, r;
+  float clip_lo, clip_hi;
+  void* out2; int out2_ld;            // bf16
+  const void* x; int x_ld;            // bf16 [M][N]   (bwd)
+  const void* z_prev; int z_prev_ld;  // bf16 [M][N]   (bwd, producer)
+  int prev_act;
+  float* dmu_r; float* drho_r;        // [E][N] fp32, zero-initialised by the caller (atomics)
+  float* dmu_s; float* drho_s; float* dbias;
+};
+
 }  // namespace ed2

@@ -51,6 +51,9 @@ int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols
                  const float* fw_mu, const float* fw_rho, Noise nz, void* xo, long long xo_ld, void* f_out,
                  long long f_ld, cudaStream_t s, FastOpts opts = FastOpts());
 
+// sg = softplus(rho) + 1e-7, sgm = sigmoid(rho): the per-(member, column) tables the fused rank-1 GEMM epilogues read
+int k_fast_prep(const float* rho, long long n, float* sg, float* sgm, cudaStream_t s);
+
 // ---- backward preparation on the output side of a layer:
 //   gp = gy ∘ act'(y)
 //   plain (fast == 0): dz = gp                   dbias[n]    = Σ_m gp

@@ -19,15 +19,18 @@ namespace {
 constexpr int kBlock = 256;
 
 __global__ void __launch_bounds__(kBlock) peer_signal_kernel(PeerExchange x, const float* __restrict__ small_src) {
-  // companion vector -> arena (peers read it after they have seen the flag)
-  float* dst = const_cast<float*>(x.small[x.rank]);
-  for (long long i = threadIdx.x; i < x.small_n; i += kBlock) dst[i] = small_src[i];
   __shared__ unsigned long long epoch_s;
   if (threadIdx.x == 0) {
     unsigned long long* w = peer::local_words(x);
     epoch_s = w[0] + 1;
     w[0] = epoch_s;
   }
+  __syncthreads();
+  // companion vector -> arena slot (epoch & 1): a peer that is still in its finishing pass of epoch e reads slot e & 1
+  // while this rank may already publish epoch e + 1 into the other slot (it cannot reach e + 2 before every peer has
+  // finished e: its own finishing pass of e + 1 waits for every owner's reduced flag of e + 1)
+  float* dst = const_cast<float*>(x.small[x.rank]) + (epoch_s & 1ull) * x.small_n;
+  for (long long i = threadIdx.x; i < x.small_n; i += kBlock) dst[i] = small_src[i];
   __syncthreads();  // orders every thread's `small` stores before the releasing threads (CTA scope, cumulative)
   // the bucket (written by the previous kernel) and `small` become visible to whoever acquires the flag
   if (threadIdx.x < x.world) {

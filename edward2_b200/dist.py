@@ -143,8 +143,9 @@ class PeerArena:
 
 
 def peer_layout(n: int, small_n: int, world: int) -> dict:
-    """Byte offsets of one exchange arena: [bucket n bf16 | reduced n bf16 | small m fp32 | flags], every region
-    256-byte aligned; `chunk` = elements per owner (multiple of 8 so that a 16-byte vector never straddles owners)."""
+    """Byte offsets of one exchange arena: [bucket n bf16 | reduced n bf16 | small 2 x m fp32 | flags], every region
+    256-byte aligned; `chunk` = elements per owner (multiple of 8 so that a 16-byte vector never straddles owners).
+    `small` is double-buffered by epoch parity: a lagging peer still reads epoch e while this rank publishes e + 1."""
     if n <= 0 or n % 8 != 0:
         raise ValueError(f"peer exchange needs n % 8 == 0 (got {n})")
     if not 2 <= world <= 8:
@@ -152,7 +153,7 @@ def peer_layout(n: int, small_n: int, world: int) -> dict:
     al = lambda b: (b + 255) // 256 * 256  # noqa: E731
     off_reduced = al(2 * n)
     off_small = off_reduced + al(2 * n)
-    off_flags = off_small + al(4 * max(small_n, 1))
+    off_flags = off_small + al(2 * 4 * max(small_n, 1))
     return dict(bucket=0, reduced=off_reduced, small=off_small, flags=off_flags,
                 nbytes=off_flags + al(8 * (2 * world + 3)), chunk=((n + world - 1) // world + 7) // 8 * 8)
 
@@ -177,10 +178,16 @@ class PeerExchange:
         self.c, self._ref = c, C.byref(c)
         self.bucket_ptr = self.arena.ptrs[self.arena.rank]
         self.n, self.small_n = n, small_n
+        self._pending = False  # set by signal(), cleared when the reducer has joined the exchange (wait())
 
     def signal(self, small_src=None):
         from . import _lib
 
+        if self._pending:
+            raise RuntimeError("PeerExchange.signal() called again before the previous exchange was joined "
+                               "(GradientAllReduce.wait()): two backward passes per step (gradient accumulation, a "
+                               "shared layer) would overwrite a bucket peers may still be pulling — use exchange='nccl'")
+        self._pending = True
         _lib.check(self.lib.ed2_peer_signal(self._ref, None if small_src is None else small_src.data_ptr(),
                                             _lib.stream_ptr()), "ed2_peer_signal")
 
@@ -376,6 +383,8 @@ class GradientAllReduce:
 
                 ops.cast(b, torch.float32, out=g2)
         self.handles.clear()
+        for ex in self._exchanges.values():
+            ex._pending = False
 
     def remove(self):
         for h in self._hooks:

@@ -118,89 +118,195 @@ class BatchEnsembleDense(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------- Rank-1
+class Rank1Link:
+    """Cross-layer fusion token of a DenseRank1 chain (attached to a layer's output tensor).
+
+    Forward: the producing layer's GEMM epilogue can already write the CONSUMER's x∘r (`xr_next`, drawn from the
+    consumer's own Philox stream) so the consumer needs no scale pass; `xr_key` identifies the fast weights and the
+    noise stream it was drawn with.  Backward: the consumer's dX GEMM epilogue runs the producer's output side
+    (gp = dx∘act'(y), dz = gp∘s, the dmu_s / drho_s / dbias column sums) and records the results here; the producer
+    uses them only when the gradient it receives IS the recorded dx tensor, unmodified (same rule as ReluLink)."""
+
+    __slots__ = ("y_ptr", "z", "mu_s", "rho_s", "eps_s", "act", "has_bias", "ensemble_size", "clip", "fusable",
+                 "xr_next", "xr_key", "dx", "dx_version", "dz", "dmu_s", "drho_s", "dbias", "fused")
+
+    def __init__(self):
+        for k in self.__slots__:
+            setattr(self, k, None)
+        self.fused = False
+
+    def record(self, dx, dz, dmu_s, drho_s, dbias):
+        self.dx, self.dx_version = dx, dx._version
+        self.dz, self.dmu_s, self.drho_s, self.dbias = dz, dmu_s, drho_s, dbias
+
+    def matches(self, gy, shape) -> bool:
+        d = self.dx
+        return (d is not None and gy.data_ptr() == d.data_ptr() and gy.shape == d.shape == shape
+                and gy.dtype == d.dtype and gy._version == self.dx_version and d._version == self.dx_version)
+
+
+def _noise_key(nz):
+    return (nz.seed, nz.stream, None if nz.step is None else nz.step.data_ptr(), nz.rows)
+
+
+def rank1_xr_key(x, mu_r, rho_r, eps_r):
+    return (x.data_ptr(), tuple(x.shape), mu_r.data_ptr(), mu_r._version,
+            None if rho_r is None else (rho_r.data_ptr(), rho_r._version), _noise_key(eps_r))
+
+
+_DEFAULT_CLIP = (-10.0, 10.0)
+RANK1_FUSION = True  # module switch for A/B tests: False forces the unfused kernels
+
+
 class Rank1Dense(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernel, mu_r, rho_r, mu_s, rho_s, bias, act, ensemble_size, dtype, eps_r, eps_s,
-                additive=False, clip=(-10.0, 10.0), rho_b=None, eps_b=None):
+                additive=False, clip=(-10.0, 10.0), rho_b=None, eps_b=None, in_link=None, out_link=None,
+                next_fast=None):
         """additive: (x + r) W + s (dense.py:1126-1127); clip: (min, max)_perturbation_value (dense.py:1108-1110);
-        rho_b / eps_b: per-example sampled ensemble bias, `bias` being its mean (dense.py:1131-1139)."""
+        rho_b / eps_b: per-example sampled ensemble bias, `bias` being its mean (dense.py:1131-1139).
+        in_link / out_link / next_fast: cross-layer fusion (Rank1Link); next_fast = (mu_r, rho_r, eps_r) of the layer
+        that will consume the output."""
         lib = _lib.load()
         B, I = x.shape
         O = kernel.shape[1]
         dev = x.device
+        E = ensemble_size
         xc = as_compute(x, dtype)
         w_lp = kernel if dtype == torch.float32 else ops.cast(kernel, dtype)
         need_grad = any(ctx.needs_input_grad)
-        y, xr, s_buf = _new(B, O, dtype, dev), _new(B, I, dtype, dev), _new(B, O, dtype, dev)
+        clip = (float(clip[0]), float(clip[1]))
+        # fused epilogues (include/ed2b200.h: ed2_rank1_fusable): s is drawn inside the GEMM epilogue and regenerated
+        # by the backward, so no s tensor exists
+        plain = (dtype == torch.bfloat16 and not additive and rho_b is None and clip == _DEFAULT_CLIP)
+        plain = plain and RANK1_FUSION
+        fused = (plain and rho_s is not None and eps_s.injected is None and O % 8 == 0
+                 and bool(lib.ed2_rank1_fusable(B, O, E)))
+        y = _new(B, O, dtype, dev)
         z = _new(B, O, dtype, dev) if need_grad else None
+        s_buf = None if fused else _new(B, O, dtype, dev)
         bias_buf = _new(B, O, dtype, dev) if rho_b is not None else None
         a = _lib.Rank1Fwd()
-        a.additive, a.clip_lo, a.clip_hi = int(bool(additive)), float(clip[0]), float(clip[1])
+        a.additive, a.clip_lo, a.clip_hi = int(bool(additive)), clip[0], clip[1]
         if rho_b is not None:
             a.rho_b, a.eps_b = rho_b.data_ptr(), eps_b.c()
             a.bias_buf, a.bias_ld = bias_buf.data_ptr(), _lib.ld(bias_buf)
-        a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), B, I, O, ensemble_size, act
+        xr = None
+        if (in_link is not None and in_link.xr_next is not None and xc.data_ptr() == x.data_ptr()
+                and in_link.xr_key == rank1_xr_key(xc, mu_r, rho_r, eps_r)):
+            xr, a.xr_ready = in_link.xr_next, 1  # written by the producer's epilogue
+            in_link.xr_next = None
+        if xr is None:
+            xr = _new(B, I, dtype, dev)
+        ws = None
+        if fused:
+            ws = torch.empty(int(lib.ed2_rank1_workspace_floats(E, I, O)), dtype=torch.float32, device=dev)
+            a.fast_ws = ws.data_ptr()
+            if next_fast is not None and next_fast[2].injected is None and out_link is not None:
+                nmu, nrho, neps = next_fast
+                xr_next = _new(B, O, dtype, dev)
+                a.next_mu_r, a.next_rho_r, a.next_eps_r = nmu.data_ptr(), _p(nrho), neps.c()
+                a.next_xr, a.next_xr_ld = xr_next.data_ptr(), _lib.ld(xr_next)
+                out_link.xr_next, out_link.xr_key = xr_next, rank1_xr_key(y, nmu, nrho, neps)
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), B, I, O, E, act
         a.x, a.x_ld, a.w_lp, a.w_ld = xc.data_ptr(), _lib.ld(xc), w_lp.data_ptr(), _lib.ld(w_lp)
         a.mu_r, a.rho_r, a.eps_r = mu_r.data_ptr(), _p(rho_r), eps_r.c()
         a.mu_s, a.rho_s, a.eps_s = mu_s.data_ptr(), _p(rho_s), eps_s.c()
         a.bias = _p(bias)
         a.y, a.y_ld, a.xr, a.xr_ld = y.data_ptr(), _lib.ld(y), xr.data_ptr(), _lib.ld(xr)
-        a.s_buf, a.s_ld, a.z, a.z_ld = s_buf.data_ptr(), _lib.ld(s_buf), _p(z), _ldn(z)
+        a.s_buf, a.s_ld, a.z, a.z_ld = _p(s_buf), _ldn(s_buf), _p(z), _ldn(z)
         _lib.check(lib.ed2_rank1_dense_fwd(C.byref(a), _lib.stream_ptr()), "ed2_rank1_dense_fwd")
+        if out_link is not None:
+            out_link.y_ptr, out_link.z, out_link.mu_s, out_link.rho_s, out_link.eps_s = y.data_ptr(), z, mu_s, rho_s, eps_s
+            out_link.act, out_link.has_bias, out_link.ensemble_size, out_link.clip = act, bias is not None, E, clip
+            out_link.fusable = fused and need_grad
+        if xc.data_ptr() != x.data_ptr():
+            in_link = None  # the producer's tensors must describe the very tensor this layer reads
         if need_grad:
-            saved = [xc, xr, s_buf, z, y, w_lp, mu_r, mu_s]
-            ctx.has_rho = (rho_r is not None, rho_s is not None)
-            if rho_r is not None:
-                saved.append(rho_r)
-            if rho_s is not None:
-                saved.append(rho_s)
-            if rho_b is not None:
-                saved.append(rho_b)
+            saved = [xc, xr, z, y, w_lp, mu_r, mu_s]
+            ctx.has = (rho_r is not None, rho_s is not None, rho_b is not None, s_buf is not None)
+            for t in (rho_r, rho_s, rho_b, s_buf):
+                if t is not None:
+                    saved.append(t)
             ctx.save_for_backward(*saved)
-            ctx.meta = (act, ensemble_size, dtype, bias is not None, x.dtype, eps_r, eps_s)
-            ctx.opts = (bool(additive), (float(clip[0]), float(clip[1])), rho_b is not None, eps_b)
+            ctx.meta = (act, E, dtype, bias is not None, x.dtype, eps_r, eps_s)
+            ctx.opts = (bool(additive), clip, eps_b, plain)
+            ctx.links = (in_link, out_link)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         lib = _lib.load()
         saved = list(ctx.saved_tensors)
-        xc, xr, s_buf, z, y, w_lp, mu_r, mu_s = saved[:8]
-        rest = saved[8:]
-        rho_r = rest.pop(0) if ctx.has_rho[0] else None
-        rho_s = rest.pop(0) if ctx.has_rho[1] else None
-        additive, clip, has_rho_b, eps_b = ctx.opts
-        rho_b = rest.pop(0) if has_rho_b else None
+        xc, xr, z, y, w_lp, mu_r, mu_s = saved[:7]
+        rest = saved[7:]
+        rho_r = rest.pop(0) if ctx.has[0] else None
+        rho_s = rest.pop(0) if ctx.has[1] else None
+        rho_b = rest.pop(0) if ctx.has[2] else None
+        s_buf = rest.pop(0) if ctx.has[3] else None
+        additive, clip, eps_b, plain = ctx.opts
+        in_link, out_link = ctx.links
         act, E, dtype, has_bias, x_dtype, eps_r, eps_s = ctx.meta
         B, I = xc.shape
         O = y.shape[1]
         dev = xc.device
         gyc = as_compute(gy, dtype)
-        dz, dxr = _new(B, O, dtype, dev), _new(B, I, dtype, dev)
-        dx = _new(B, I, dtype, dev) if ctx.needs_input_grad[0] else None
         f32 = dict(dtype=torch.float32, device=dev)
-        dw = torch.empty(I, O, **f32)
-        dmu_r, dmu_s = torch.empty(E, I, **f32), torch.empty(E, O, **f32)
-        drho_r = torch.empty(E, I, **f32) if rho_r is not None else None
-        drho_s = torch.empty(E, O, **f32) if rho_s is not None else None
-        dbias = torch.empty(E, O, **f32) if has_bias else None
-        drho_b = torch.empty(E, O, **f32) if rho_b is not None else None
         a = _lib.Rank1Bwd()
+        # output side already done by the consumer's dX epilogue?
+        ready = out_link is not None and out_link.matches(gyc, y.shape)
+        if out_link is not None:
+            out_link.fused = ready
+        if ready:
+            dz, dmu_s, drho_s, dbias = out_link.dz, out_link.dmu_s, out_link.drho_s, out_link.dbias
+            a.dz_ready = 1
+        else:
+            dz = _new(B, O, dtype, dev)
+            dmu_s = torch.empty(E, O, **f32)
+            drho_s = torch.empty(E, O, **f32) if rho_s is not None else None
+            dbias = torch.empty(E, O, **f32) if has_bias else None
+        if out_link is not None:
+            out_link.dx = out_link.dz = None  # consumed (or not applicable)
+        need_dx = ctx.needs_input_grad[0]
+        dx = _new(B, I, dtype, dev) if need_dx else None
+        fused_in = (plain and eps_r.injected is None and I % 8 == 0 and bool(lib.ed2_rank1_fusable(B, I, E)))
+        dxr = None if fused_in else _new(B, I, dtype, dev)
+        dw = torch.empty(I, O, **f32)
+        dmu_r = torch.empty(E, I, **f32)
+        drho_r = torch.empty(E, I, **f32) if rho_r is not None else None
+        drho_b = torch.empty(E, O, **f32) if rho_b is not None else None
         a.additive, a.clip_lo, a.clip_hi = int(additive), clip[0], clip[1]
         if rho_b is not None:
             a.rho_b, a.eps_b, a.drho_b = rho_b.data_ptr(), eps_b.c(), drho_b.data_ptr()
+        prev = None
+        if fused_in:
+            ws = torch.empty(int(lib.ed2_rank1_workspace_floats(E, I, O)), dtype=torch.float32, device=dev)
+            a.fast_ws = ws.data_ptr()
+            lk = in_link
+            if (lk is not None and lk.fusable and need_dx and dx.dtype == x_dtype and lk.y_ptr == xc.data_ptr()
+                    and lk.ensemble_size == E and lk.clip == clip and lk.eps_s.injected is None and lk.z is not None):
+                prev = dict(dz=_new(B, I, dtype, dev), dmu_s=torch.empty(E, I, **f32),
+                            drho_s=torch.empty(E, I, **f32) if lk.rho_s is not None else None,
+                            dbias=torch.empty(E, I, **f32) if lk.has_bias else None)
+                a.prev_z, a.prev_z_ld = lk.z.data_ptr(), _lib.ld(lk.z)
+                a.prev_mu_s, a.prev_rho_s, a.prev_eps_s, a.prev_act = lk.mu_s.data_ptr(), _p(lk.rho_s), lk.eps_s.c(), lk.act
+                a.prev_dz, a.prev_dz_ld = prev["dz"].data_ptr(), _lib.ld(prev["dz"])
+                a.prev_dmu_s, a.prev_drho_s, a.prev_dbias = prev["dmu_s"].data_ptr(), _p(prev["drho_s"]), _p(prev["dbias"])
         a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), B, I, O, E, act
         a.gy, a.gy_ld, a.y, a.y_ld, a.z, a.z_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y), z.data_ptr(), _lib.ld(z)
         a.x, a.x_ld, a.xr, a.xr_ld = xc.data_ptr(), _lib.ld(xc), xr.data_ptr(), _lib.ld(xr)
-        a.s_buf, a.s_ld, a.w_lp, a.w_ld = s_buf.data_ptr(), _lib.ld(s_buf), w_lp.data_ptr(), _lib.ld(w_lp)
+        a.s_buf, a.s_ld, a.w_lp, a.w_ld = _p(s_buf), _ldn(s_buf), w_lp.data_ptr(), _lib.ld(w_lp)
         a.mu_r, a.rho_r, a.eps_r = mu_r.data_ptr(), _p(rho_r), eps_r.c()
         a.mu_s, a.rho_s, a.eps_s = mu_s.data_ptr(), _p(rho_s), eps_s.c()
-        a.dz, a.dz_ld, a.dxr, a.dxr_ld, a.dx, a.dx_ld = dz.data_ptr(), _lib.ld(dz), dxr.data_ptr(), _lib.ld(dxr), _p(dx), _ldn(dx)
+        a.dz, a.dz_ld, a.dxr, a.dxr_ld, a.dx, a.dx_ld = dz.data_ptr(), _lib.ld(dz), _p(dxr), _ldn(dxr), _p(dx), _ldn(dx)
         a.dw, a.dmu_r, a.drho_r, a.dmu_s, a.drho_s, a.dbias = dw.data_ptr(), dmu_r.data_ptr(), _p(drho_r), dmu_s.data_ptr(), _p(drho_s), _p(dbias)
         _lib.check(lib.ed2_rank1_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_rank1_dense_bwd")
+        if prev is not None:
+            in_link.record(dx, prev["dz"], prev["dmu_s"], prev["drho_s"], prev["dbias"])
         if dx is not None and dx.dtype != x_dtype:
             dx = dx.to(x_dtype)
-        return dx, dw, dmu_r, drho_r, dmu_s, drho_s, dbias, None, None, None, None, None, None, None, drho_b, None
+        return (dx, dw, dmu_r, drho_r, dmu_s, drho_s, dbias, None, None, None, None, None, None, None, drho_b, None,
+                None, None, None)
 
 
 class GradSync:

@@ -363,6 +363,27 @@ class DenseRank1(Layer):
     def _fast(self, init, param):
         return init.params() if _is_trainable(init) else (param, None)
 
+    def feeds(self, consumer):
+        """Scheduling hint for stacked rank-1 layers: this layer's output goes straight into `consumer` (another
+        DenseRank1 with the same ensemble_size).  The GEMM epilogue of this layer then also writes the consumer's
+        x∘r — drawn from the consumer's own Philox stream — and the consumer's backward runs this layer's output side in
+        its dX epilogue, so neither costs a pass over HBM (functional.Rank1Link).  Results are unchanged; any other use
+        of the output falls back to the unfused kernels.  Returns `consumer` so chains read l1.feeds(l2).feeds(l3)."""
+        import weakref
+
+        self._consumer = weakref.ref(consumer) if consumer is not None else None
+        return consumer
+
+    def _next_fast(self, per):
+        ref = getattr(self, "_consumer", None)
+        nxt = ref() if ref is not None else None
+        if (not isinstance(nxt, DenseRank1) or not nxt.built or nxt.ensemble_size != self.ensemble_size
+                or nxt.use_additive_perturbation or nxt.compute_dtype != self.compute_dtype
+                or nxt.kernel.shape[0] != self.units):
+            return None
+        mu_r, rho_r = nxt._fast(nxt.alpha_initializer, nxt.alpha)
+        return mu_r, rho_r, nxt._noise("eps_alpha", S_R, per_example=per)
+
     def call(self, inputs, training=None):
         if inputs.dim() != 2:  # dense.py:1100: restricted to 2-D inputs
             raise ValueError("DenseRank1 takes [ensemble_size * examples_per_model, features]")
@@ -373,13 +394,18 @@ class DenseRank1(Layer):
         bias, rho_b = (self._fast(self.ensemble_bias_initializer, self.ensemble_bias)
                        if self.use_ensemble_bias else (None, None))
         per = inputs.shape[0] // self.ensemble_size
-        return F.Rank1Dense.apply(inputs, self.kernel, mu_r, rho_r, mu_s, rho_s, bias, self._act,
-                                  self.ensemble_size, self.compute_dtype,
-                                  self._noise("eps_alpha", S_R, per_example=per),
-                                  self._noise("eps_gamma", S_S, per_example=per),
-                                  self.use_additive_perturbation,
-                                  (self.min_perturbation_value, self.max_perturbation_value), rho_b,
-                                  self._noise("eps_bias", S_B, per_example=per) if rho_b is not None else None)
+        in_link = getattr(inputs, "_ed2_rank1_link", None)
+        out_link = F.Rank1Link()
+        y = F.Rank1Dense.apply(inputs, self.kernel, mu_r, rho_r, mu_s, rho_s, bias, self._act,
+                               self.ensemble_size, self.compute_dtype,
+                               self._noise("eps_alpha", S_R, per_example=per),
+                               self._noise("eps_gamma", S_S, per_example=per),
+                               self.use_additive_perturbation,
+                               (self.min_perturbation_value, self.max_perturbation_value), rho_b,
+                               self._noise("eps_bias", S_B, per_example=per) if rho_b is not None else None,
+                               in_link, out_link, self._next_fast(per))
+        y._ed2_rank1_link = out_link
+        return y
 
     @property
     def losses(self):

@@ -221,8 +221,25 @@ typedef struct {
   int additive; float clip_lo, clip_hi;
   const float* rho_b; ed2_noise eps_b;   /* per-example sampled bias: bias = mean [E][out_dim], rho_b [E][out_dim] */
   void* bias_buf; int bias_ld;           /* workspace [B][out_dim] in dtype, required when rho_b != NULL */
+  /* ---- fused path (see ed2_rank1_fusable): s — and the NEXT layer's r — are drawn inside the GEMM epilogue, once per
+   * output element, so neither s nor the next layer's x∘r costs a pass over HBM.
+   *   fast_ws   caller workspace of ed2_rank1_workspace_floats() floats; NULL selects the unfused path (s_buf required).
+   *             On the fused path s_buf may be NULL (the backward regenerates s).
+   *   xr_ready  xr already holds x∘r: the producer layer wrote it through its next_xr.
+   *   next_*    fast weights of the layer that consumes y ([E][out_dim]; next_rho_r NULL = deterministic) and the
+   *             buffer next_xr [B][out_dim] that receives bf16(y) ∘ r_next.  next_mu_r NULL: not produced. */
+  float* fast_ws;
+  int xr_ready;
+  const float* next_mu_r; const float* next_rho_r; ed2_noise next_eps_r;
+  void* next_xr; int next_xr_ld;
 } ed2_rank1_fwd_args;
 int ed2_rank1_dense_fwd(const ed2_rank1_fwd_args* a, void* stream);
+
+/* 1 when the fused rank-1 epilogues apply to a layer call of this shape in ED2_BF16 with Philox noise, multiplicative
+ * perturbations and a deterministic bias (forward: cols = out_dim; backward dX side: cols = in_dim). */
+int ed2_rank1_fusable(int batch, int cols, int ensemble_size);
+/* floats of workspace one fused forward or backward call needs */
+long long ed2_rank1_workspace_floats(int ensemble_size, int in_dim, int out_dim);
 
 typedef struct {
   int dtype;
@@ -244,6 +261,18 @@ typedef struct {
   float* dmu_r; float* drho_r; float* dmu_s; float* drho_s; float* dbias; /* drho_* / dbias may be NULL */
   int additive; float clip_lo, clip_hi;
   const float* rho_b; ed2_noise eps_b; float* drho_b;  /* sampled bias: dbias is d(bias mean), drho_b [E][out_dim] */
+  /* ---- fused path (fast_ws != NULL and ed2_rank1_fusable(batch, in_dim, E)): the dX GEMM epilogue computes
+   * dx = dxr ∘ r and the dmu_r / drho_r column sums itself (dxr is never written; dxr may be NULL), and — when the
+   * PRODUCER layer's tensors are given (prev_mu_s != NULL; its output y is this layer's x) — also the producer's
+   * output side:  gp = dx ∘ act'(x),  prev_dz = gp ∘ s_prev,  prev_dmu_s / prev_drho_s / prev_dbias.
+   *   dz_ready  this layer's dz, dmu_s, drho_s, dbias were already produced that way by ITS consumer: skip that pass
+   *             (gy, y, z, s_buf are then unused). */
+  float* fast_ws;
+  int dz_ready;
+  const void* prev_z; int prev_z_ld;
+  const float* prev_mu_s; const float* prev_rho_s; ed2_noise prev_eps_s; int prev_act;
+  void* prev_dz; int prev_dz_ld;
+  float* prev_dmu_s; float* prev_drho_s; float* prev_dbias;
 } ed2_rank1_bwd_args;
 int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream);
 
@@ -330,7 +359,7 @@ typedef struct {
   long long small_n; /* elements of the fp32 companion vector (0 = none) */
   const void* bucket[ED2_MAX_PEERS];    /* [r]: rank r's raw bf16 gradient [n]              ([rank] = local memory) */
   void* reduced[ED2_MAX_PEERS];         /* [r]: rank r's reduced buffer [n] (its own slice is valid)              */
-  const float* small_vec[ED2_MAX_PEERS];/* [r]: rank r's companion vector [small_n]                               */
+  const float* small_vec[ED2_MAX_PEERS];/* [r]: rank r's companion vector, TWO slots [2][small_n] (slot = epoch & 1) */
   void* flags[ED2_MAX_PEERS];           /* [r]: rank r's flag words, (2 * world + 3) x 8 bytes, zero-initialised   */
 } ed2_peer_exchange;
 int ed2_peer_alloc(size_t bytes, void** ptr_out, void* handle_out /* ED2_IPC_HANDLE_BYTES */);

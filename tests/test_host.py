@@ -96,7 +96,7 @@ def test_peer_exchange_layout():
     for n, m, w in [(4096 * 1000, 1000, 8), (1024 * 4096, 4096, 2), (264 * 512, 0, 4), (8, 0, 8), (4096 * 1000, 1000, 3)]:
         lay = peer_layout(n, m, w)
         assert lay["bucket"] == 0 and lay["reduced"] >= 2 * n and lay["small"] >= lay["reduced"] + 2 * n
-        assert lay["flags"] >= lay["small"] + 4 * m and lay["nbytes"] >= lay["flags"] + 8 * (2 * w + 3)
+        assert lay["flags"] >= lay["small"] + 2 * 4 * m and  lay["nbytes"] >= lay["flags"] + 8 * (2 * w + 3)
         assert all(lay[k] % 256 == 0 for k in ("reduced", "small", "flags", "nbytes"))
         assert lay["chunk"] % 8 == 0 and lay["chunk"] * w >= n and lay["chunk"] * (w - 1) < n + 8 * w
     for bad in [(12, 0, 2), (0, 0, 2), (64, 0, 1), (64, 0, 9)]:
