@@ -88,7 +88,7 @@ int launch_one(const GemmDesc& g, const CUtensorMap& ta, const CUtensorMap& tb, 
   clusters = std::min(clusters, num_tiles);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
-  cfg.blockDim = dim3(tc::kThreads);
+  cfg.blockDim = dim3(Cfg::kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -128,8 +128,9 @@ int default_cta_group() {
 }  // namespace
 
 bool gemm_rank1_fusable(int M, int N, int group_rows) {
-  // one 2-CTA 256x256 configuration; every warp's 32 rows must belong to one member; 4-column noise blocks
-  return M > 128 && N % 8 == 0 && (group_rows == 0 || group_rows % 32 == 0);
+  // one 2-CTA 256x256 configuration; the 128 rows of a CTA's tile must belong to one member (its per-column
+  // parameters are staged once per tile); 4-column noise blocks, 8-column vector stores
+  return M > 128 && N % 8 == 0 && (group_rows == 0 || group_rows % 128 == 0);
 }
 
 int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {

@@ -22,7 +22,6 @@
 #include <cstdio>
 
 #include "gemm_epilogue.h"
-#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace ed2 {
@@ -40,23 +39,31 @@ constexpr int kNumStoreBufs = 2;
 // on side streams and must be able to co-reside with a GEMM CTA (tensor cores + TMA leave the CUDA cores idle).
 constexpr int kSmemBudget = 195 * 1024;
 
-// Fused rank-1 epilogues own the SM (there are no side-stream elementwise kernels left to co-reside with) and the
-// backward one needs a per-warp transposition buffer for its five column reductions: [5 sums][32 rows][8 + 1 cols].
+constexpr int kR1EpiWarps = 8;
+constexpr int kR1EpiThreads = kR1EpiWarps * 32;
+constexpr int kR1Threads = 128 + kR1EpiThreads;  // 4 control warps + 8 epilogue warps
+constexpr int kR1Chunk = 16;                     // accumulator columns per TMEM load
+constexpr int kR1StoreBufs = 4;                  // 2 per epilogue group, 128 rows x 64 bf16 columns each
+constexpr int kR1TableFloats = 6 * 256;          // mu_s, sg_s, sgm_s, mu_r, sg_r, sgm_r for the tile's 256 columns
+constexpr int kR1TableBytes = 2 * kR1TableFloats * 4;  // double-buffered by tile parity
+
+// The fused rank-1 epilogues (gemm_rank1_epi.cuh) own the SM — there are no side-stream elementwise kernels left to
+// co-reside with — and carry four staging buffers (two per epilogue group) plus the per-tile parameter tables.
 constexpr int kSmemBudgetFused = 226 * 1024;
-constexpr int kRedCols = 8;
-constexpr int kRedPitch = kRedCols + 1;
-constexpr int kRedSums = 5;
-constexpr int kRedBytesPerWarp = kRedSums * 32 * kRedPitch * 4;
 
 template <int BLOCK_N, int kCtaGroup, int kEpi = kEpiGeneric>
 struct Config {
+  static constexpr bool kFused = kEpi != kEpiGeneric;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kLoadN = BLOCK_N / kCtaGroup;
   static constexpr int kBBytes = kLoadN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kRedBytes = kEpi == kEpiRank1Bwd ? (kEpiThreads / 32) * kRedBytesPerWarp : 0;
-  static constexpr int kFixedBytes = kNumStoreBufs * kStoreBufBytes + 1024 /*barriers*/ + 1024 /*align slack*/ + kRedBytes;
-  static constexpr int kStagesRaw = ((kEpi == kEpiGeneric ? kSmemBudget : kSmemBudgetFused) - kFixedBytes) / kStageBytes;
+  static constexpr int kStoreBufs = kFused ? kR1StoreBufs : kNumStoreBufs;
+  static constexpr int kTableBytes = kFused ? kR1TableBytes : 0;
+  static constexpr int kNumThreads = kFused ? kR1Threads : kThreads;
+  static constexpr int kEpiThreadsTotal = kFused ? kR1EpiThreads : kEpiThreads;
+  static constexpr int kFixedBytes = kStoreBufs * kStoreBufBytes + 1024 /*barriers*/ + 1024 /*align slack*/ + kTableBytes;
+  static constexpr int kStagesRaw = ((kFused ? kSmemBudgetFused : kSmemBudget) - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages; 256 or 512 (power of two)
@@ -127,6 +134,12 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n) {
   c.n_blk = r / gsize;
   return c;
 }
+
+}  // namespace tc
+}  // namespace ed2
+#include "gemm_rank1_epi.cuh"
+namespace ed2 {
+namespace tc {
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -233,111 +246,8 @@ __device__ __forceinline__ void col_sum_chunk(const EpiParams& ep, float (&v)[32
   }
 }
 
-
-// ---- fused rank-1 epilogue helpers ------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t fast_key(const FastSide& f) {
-  return f.step != nullptr ? f.seed + __ldg(f.step) * 0x9E3779B97F4A7C15ull : f.seed;
-}
-__device__ __forceinline__ long long fast_row(const FastSide& f, long long m) {
-  if (f.rpg_local > 0) {
-    const long long g = m / f.rpg_local;
-    return m + g * static_cast<long long>(f.rpg_global - f.rpg_local) + f.row0;
-  }
-  return m + f.row0;
-}
-// 4 consecutive factors of one row: columns n..n+3 (n % 4 == 0) of member row `mu_e` / `sg_e` (already offset by e*N).
-// idx = global_row * N + n.  pass = 1 where the raw draw lies inside [lo, hi] (tf.clip_by_value gradient).
-__device__ __forceinline__ void fast_gen4(const float* mu_e, const float* sg_e, uint64_t key, uint64_t stream,
-                                          long long idx, int n, float lo, float hi, float (&fac)[4], float (&eps)[4],
-                                          float (&pass)[4]) {
-  const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mu_e + n));
-  const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
-  if (sg_e != nullptr) {
-    const float4 sg4 = __ldg(reinterpret_cast<const float4*>(sg_e + n));
-    const float sg[4] = {sg4.x, sg4.y, sg4.z, sg4.w};
-    philox_normal4<true>(key, stream, static_cast<uint64_t>(idx >> 2), eps);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float raw = fmaf(sg[i], eps[i], mu[i]);
-      fac[i] = fminf(fmaxf(raw, lo), hi);
-      pass[i] = (raw < lo || raw > hi) ? 0.f : 1.f;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { fac[i] = mu[i]; eps[i] = 0.f; pass[i] = 1.f; }
-  }
-}
-// eps for 32 consecutive columns (8 Philox blocks) in ONE straight-line section: no branches, so the eight independent
-// 10-round chains interleave and a single epilogue warp per scheduler keeps issuing (the chains are latency-bound).
-__device__ __forceinline__ void fast_noise32(uint64_t key, uint64_t stream, long long idx, float (&eps)[32]) {
-  uint32_t x[8][4];
-#pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    const uint64_t blk = static_cast<uint64_t>(idx >> 2) + b;
-    x[b][0] = static_cast<uint32_t>(blk);
-    x[b][1] = static_cast<uint32_t>(blk >> 32);
-    x[b][2] = static_cast<uint32_t>(stream);
-    x[b][3] = static_cast<uint32_t>(stream >> 32);
-  }
-  uint32_t k0 = static_cast<uint32_t>(key), k1 = static_cast<uint32_t>(key >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-#pragma unroll
-    for (int b = 0; b < 8; ++b) philox_round(x[b], k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-#pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    box_muller_fast(x[b][0], x[b][1], eps[4 * b], eps[4 * b + 1]);
-    box_muller_fast(x[b][2], x[b][3], eps[4 * b + 2], eps[4 * b + 3]);
-  }
-}
-// factor / pass-through mask of one element from its draw
-__device__ __forceinline__ float fast_apply(float mu, float sg, float eps, float lo, float hi, float& pass) {
-  const float raw = fmaf(sg, eps, mu);
-  pass = (raw < lo || raw > hi) ? 0.f : 1.f;
-  return fminf(fmaxf(raw, lo), hi);
-}
-// 32 per-column parameters of a member row (uniform across the warp: one transaction per float4)
-__device__ __forceinline__ void load_cols32(const float* p, int n0, int nq, float (&o)[32], float fill) {
-#pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    if (b < nq) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(p + n0) + b);
-      o[4 * b] = q.x; o[4 * b + 1] = q.y; o[4 * b + 2] = q.z; o[4 * b + 3] = q.w;
-    } else {
-      o[4 * b] = fill; o[4 * b + 1] = fill; o[4 * b + 2] = fill; o[4 * b + 3] = fill;
-    }
-  }
-}
-
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const float2 v = __bfloat1622float2(h[t]);
-    f[2 * t] = v.x;
-    f[2 * t + 1] = v.y;
-  }
-}
-// 32 packed bf16 (16 words) of one row to global memory; nq = number of valid 4-column blocks
-__device__ __forceinline__ void store_packed32(void* base, long long row_off, int n0, int nq, const uint32_t (&pk)[16]) {
-  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + row_off + n0;
-  if (nq == 8 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      reinterpret_cast<uint4*>(p)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-  } else {
-#pragma unroll
-    for (int b = 0; b < 8; ++b)
-      if (b < nq) reinterpret_cast<uint2*>(p)[b] = make_uint2(pk[2 * b], pk[2 * b + 1]);
-  }
-}
-
 template <int kMajorA, int kMajorB, int BLOCK_N, int kCtaGroup, int kEpi = kEpiGeneric>
-__global__ void __maxnreg__(kEpi == kEpiGeneric ? 128 : (kEpi == kEpiRank1Bwd ? 255 : 232))
+__global__ void __maxnreg__(kEpi == kEpiGeneric ? 128 : 168)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, int M, int N, int K, EpiParams ep,
                  const __grid_constant__ Rank1Epi r1) {
@@ -354,13 +264,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + kStages * Cfg::kABytes;
   uint8_t* smem_store = smem_b + kStages * Cfg::kBBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + kNumStoreBufs * kStoreBufBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + Cfg::kStoreBufs * kStoreBufBytes);
+  [[maybe_unused]] uint8_t* smem_table = reinterpret_cast<uint8_t*>(bars) + 1024;
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  [[maybe_unused]] uint8_t* smem_red = reinterpret_cast<uint8_t*>(bars) + 1024;  // rank-1 backward column-sum staging
 
   const int warp_idx = __shfl_sync(0xffffffff, threadIdx.x / 32, 0);
   const uint32_t lane = ptx::lane_id();
@@ -381,7 +291,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);                         // one tcgen05.commit
-      ptx::mbar_init(&tmem_empty_bar[i], kCtaGroup * kEpiThreads);  // every epilogue thread of the pair
+      ptx::mbar_init(&tmem_empty_bar[i], kCtaGroup * Cfg::kEpiThreadsTotal);  // every epilogue thread of the pair
     }
     ptx::fence_barrier_init();
   } else if (warp_idx == 2) {
@@ -463,6 +373,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     }
+  } else if (warp_idx >= 4 && kEpi != kEpiGeneric) {
+    // ------------------------------------------------------------------ fused rank-1 epilogue (256 threads)
+    if constexpr (kEpi != kEpiGeneric)
+      rank1_epilogue<kEpi, BLOCK_N, kCtaGroup>(tm_out, ep, r1, M, N, tmem_base, tmem_full_bar, tmem_empty_bar, smem_store,
+                                               smem_table, warp_idx, lane, cta_rank, cluster_id, num_clusters, num_m, num_n);
   } else if (warp_idx >= 4) {
     // ------------------------------------------------------------------ epilogue (128 threads)
     const int ew = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quadrant this warp may read
@@ -482,45 +397,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       ptx::tc_fence_after();
       const int grp = ep.group_rows > 0 ? (m_ok ? m / ep.group_rows : 0) : 0;
       float row_acc = 0.f;
-
-      // fused rank-1 epilogues: per-row noise bases and the member's parameter rows
-      [[maybe_unused]] uint64_t key_s = 0, key_r = 0;
-      [[maybe_unused]] long long nrow_s = 0, nrow_r = 0;
-      [[maybe_unused]] const float *mu_s = nullptr, *sg_s = nullptr, *mu_r = nullptr, *sg_r = nullptr;
-      [[maybe_unused]] const bool has_s = r1.s.mu != nullptr, has_r = r1.r.mu != nullptr;
-      if constexpr (kEpi != kEpiGeneric) {
-        const long long eoff = static_cast<long long>(grp) * N;
-        if (has_s) {
-          key_s = fast_key(r1.s);
-          nrow_s = fast_row(r1.s, m_ok ? m : 0) * N;
-          mu_s = r1.s.mu + eoff;
-          sg_s = r1.s.sg != nullptr ? r1.s.sg + eoff : nullptr;
-        }
-        if (has_r) {
-          key_r = fast_key(r1.r);
-          nrow_r = fast_row(r1.r, m_ok ? m : 0) * N;
-          mu_r = r1.r.mu + eoff;
-          sg_r = r1.r.sg != nullptr ? r1.r.sg + eoff : nullptr;
-        }
-      }
-      // rank-1 backward: this layer's input x (= the producer's y) and the producer's z, one 32-column chunk ahead
-      [[maybe_unused]] uint4 xq[4], zq[4];
-      [[maybe_unused]] const uint4* x_row = nullptr;
-      [[maybe_unused]] const uint4* z_row = nullptr;
-      if constexpr (kEpi == kEpiRank1Bwd) {
-        x_row = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(r1.x) +
-                                               static_cast<long long>(m_ok ? m : 0) * r1.x_ld + n0);
-        if (has_s)
-          z_row = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(r1.z_prev) +
-                                                 static_cast<long long>(m_ok ? m : 0) * r1.z_prev_ld + n0);
-        if (m_ok && n0 + 32 <= N) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            xq[j] = __ldg(x_row + j);
-            if (has_s) zq[j] = __ldg(z_row + j);
-          }
-        }
-      }
 
       // ReLU-mask source (the producer layer's bf16 activations): its global loads are issued most of a 32-column chunk
       // AHEAD of their use, otherwise every chunk exposes a full global-load latency and short-K GEMMs (the dX of the
@@ -556,170 +432,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (ep.raw != nullptr && active)
           store_row32(ep.raw, ep.raw_dt, static_cast<long long>(m) * ep.raw_ld, nc, n_valid, v);
 
-        if constexpr (kEpi == kEpiRank1Fwd) {
-          // y = act(z * s + bias[e]);  out2 = bf16(y) * r_next  — s and r_next drawn here, once per element
-          const int nq = active ? (n_valid >> 2) : 0;
-          {
-            float f[32];  // eps_s, then s in place
-            if (has_s && sg_s != nullptr) {
-              fast_noise32(key_s, r1.s.stream, nrow_s + nc, f);
-              float mu[32], sg[32];
-              load_cols32(mu_s, nc, nq, mu, 1.f);
-              load_cols32(sg_s, nc, nq, sg, 0.f);
-              float ps;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fast_apply(mu[j], sg[j], f[j], r1.clip_lo, r1.clip_hi, ps);
-            } else if (has_s) {
-              load_cols32(mu_s, nc, nq, f, 1.f);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = 1.f;
-            }
-            float bs[32];
-            if (ep.col_bias != nullptr) load_cols32(ep.col_bias + static_cast<long long>(grp) * ep.col_bias_ld, nc, nq, bs, 0.f);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float y = ep.col_bias != nullptr ? fmaf(v[j], f[j], bs[j]) : v[j] * f[j];
-              if (ep.act == kActRelu) y = fmaxf(y, 0.f);
-              v[j] = y;
-            }
-          }
-          if (r1.out2 != nullptr) {
-            float f[32];
-            if (has_r && sg_r != nullptr) {
-              fast_noise32(key_r, r1.r.stream, nrow_r + nc, f);
-              float mu[32], sg[32];
-              load_cols32(mu_r, nc, nq, mu, 1.f);
-              load_cols32(sg_r, nc, nq, sg, 0.f);
-              float pr;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fast_apply(mu[j], sg[j], f[j], r1.clip_lo, r1.clip_hi, pr);
-            } else if (has_r) {
-              load_cols32(mu_r, nc, nq, f, 1.f);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = 1.f;
-            }
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(bf16_round(v[2 * j]) * f[2 * j], bf16_round(v[2 * j + 1]) * f[2 * j + 1]);
-            if (active) store_packed32(r1.out2, static_cast<long long>(m) * r1.out2_ld, nc, nq, pk);
-          }
-        } else if constexpr (kEpi == kEpiRank1Bwd) {
-          const int nq = active ? (n_valid >> 2) : 0;
-          const bool pre = m_ok && n_valid == 32;  // prefetched operands are valid
-          float* red = reinterpret_cast<float*>(smem_red) + ew * (kRedSums * 32 * kRedPitch) + lane * kRedPitch;
-          const int warp_row0 = m0 + ew * 32;
-          const bool relu_prev = r1.prev_act == kActRelu;
-          // draws of this chunk, straight-line (see fast_noise32); factors, masks and operands are formed per 8-column
-          // strip below (keeps the live state at eps_r, eps_s, the accumulator chunk and the packed operands)
-          float er[32], es[32];
-          const bool samp_r = sg_r != nullptr, samp_s = has_s && sg_s != nullptr;
-          if (samp_r) fast_noise32(key_r, r1.r.stream, nrow_r + nc, er);
-          if (samp_s) fast_noise32(key_s, r1.s.stream, nrow_s + nc, es);
-          uint32_t pk[16];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int ns = nc + 8 * q4;           // first column of the strip
-            const bool strip_ok = ns < N;         // N % 8 == 0: a strip is entirely inside or outside
-            float mur[8], sgr[8], mus[8], sgs[8], xs[8], zs[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { mur[i] = 1.f; sgr[i] = 0.f; mus[i] = 1.f; sgs[i] = 0.f; xs[i] = 0.f; zs[i] = 0.f; }
-            if (strip_ok) {
-              const float4 a0 = __ldg(reinterpret_cast<const float4*>(mu_r + ns)), a1 = __ldg(reinterpret_cast<const float4*>(mu_r + ns) + 1);
-              mur[0] = a0.x; mur[1] = a0.y; mur[2] = a0.z; mur[3] = a0.w; mur[4] = a1.x; mur[5] = a1.y; mur[6] = a1.z; mur[7] = a1.w;
-              if (samp_r) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(sg_r + ns)), b1 = __ldg(reinterpret_cast<const float4*>(sg_r + ns) + 1);
-                sgr[0] = b0.x; sgr[1] = b0.y; sgr[2] = b0.z; sgr[3] = b0.w; sgr[4] = b1.x; sgr[5] = b1.y; sgr[6] = b1.z; sgr[7] = b1.w;
-              }
-              if (has_s) {
-                const float4 c0 = __ldg(reinterpret_cast<const float4*>(mu_s + ns)), c1 = __ldg(reinterpret_cast<const float4*>(mu_s + ns) + 1);
-                mus[0] = c0.x; mus[1] = c0.y; mus[2] = c0.z; mus[3] = c0.w; mus[4] = c1.x; mus[5] = c1.y; mus[6] = c1.z; mus[7] = c1.w;
-                if (samp_s) {
-                  const float4 d0 = __ldg(reinterpret_cast<const float4*>(sg_s + ns)), d1 = __ldg(reinterpret_cast<const float4*>(sg_s + ns) + 1);
-                  sgs[0] = d0.x; sgs[1] = d0.y; sgs[2] = d0.z; sgs[3] = d0.w; sgs[4] = d1.x; sgs[5] = d1.y; sgs[6] = d1.z; sgs[7] = d1.w;
-                }
-              }
-              if (pre) {
-                unpack_bf16x8(xq[q4], xs);
-                if (has_s) unpack_bf16x8(zq[q4], zs);
-              } else if (m_ok) {
-                unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(r1.x) + static_cast<long long>(m) * r1.x_ld + ns)), xs);
-                if (has_s)
-                  unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(r1.z_prev) + static_cast<long long>(m) * r1.z_prev_ld + ns)), zs);
-              }
-            }
-            float dxs[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = 8 * q4 + i;
-              const float e_r = samp_r ? er[j] : 0.f, e_s = samp_s ? es[j] : 0.f;
-              float p_r, p_s;
-              const float f_r = fast_apply(mur[i], sgr[i], e_r, r1.clip_lo, r1.clip_hi, p_r);
-              const float dxr = (active && strip_ok) ? v[j] : 0.f;
-              const float dx = dxr * (samp_r ? f_r : mur[i]);
-              const float dr = dxr * xs[i] * (samp_r ? p_r : 1.f);
-              red[0 * 32 * kRedPitch + i] = dr;
-              red[1 * 32 * kRedPitch + i] = dr * e_r;
-              if (has_s) {
-                const float f_s = fast_apply(mus[i], sgs[i], e_s, r1.clip_lo, r1.clip_hi, p_s);
-                const float dxb = bf16_round(dx);
-                const float gp = relu_prev ? (xs[i] > 0.f ? dxb : 0.f) : dxb;
-                const float ds = gp * zs[i] * (samp_s ? p_s : 1.f);
-                red[2 * 32 * kRedPitch + i] = ds;
-                red[3 * 32 * kRedPitch + i] = ds * e_s;
-                red[4 * 32 * kRedPitch + i] = gp;
-                v[j] = gp * (samp_s ? f_s : mus[i]);  // dz of the producer -> out
-              } else {
-                v[j] = dx;                             // -> out (optional)
-              }
-              dxs[i] = dx;
-            }
-#pragma unroll
-            for (int t2 = 0; t2 < 4; ++t2) pk[4 * q4 + t2] = pack_bf16(dxs[2 * t2], dxs[2 * t2 + 1]);
-            // column sums of this 8-column strip over the warp's 32 rows: lane -> (column lane & 7, row group lane >> 3)
-            __syncwarp();
-            {
-              const float* rd = reinterpret_cast<float*>(smem_red) + ew * (kRedSums * 32 * kRedPitch) +
-                                ((lane >> 3) * 8) * kRedPitch + (lane & 7);
-              float t[kRedSums];
-#pragma unroll
-              for (int q = 0; q < kRedSums; ++q) {
-                t[q] = 0.f;
-                if (q < 2 || has_s) {
-#pragma unroll
-                  for (int rr = 0; rr < 8; ++rr) t[q] += rd[q * 32 * kRedPitch + rr * kRedPitch];
-                  t[q] += __shfl_xor_sync(0xffffffffu, t[q], 8);
-                  t[q] += __shfl_xor_sync(0xffffffffu, t[q], 16);
-                }
-              }
-              const int ncol = nc + 8 * q4 + static_cast<int>(lane & 7);
-              if (ncol < N && warp_row0 < M) {
-                const int e = ep.group_rows > 0 ? warp_row0 / ep.group_rows : 0;
-                const long long o = static_cast<long long>(e) * N + ncol;
-                const int rg = lane >> 3;
-                // every lane holds all five totals of its column: row group g issues the atomic of sum g (and group 0 of sum 4)
-                if (rg == 0) atomicAdd(r1.dmu_r + o, t[0]);
-                if (rg == 1 && r1.drho_r != nullptr) atomicAdd(r1.drho_r + o, t[1] * __ldg(r1.r.sgm + o));
-                if (has_s) {
-                  if (rg == 2) atomicAdd(r1.dmu_s + o, t[2]);
-                  if (rg == 3 && r1.drho_s != nullptr) atomicAdd(r1.drho_s + o, t[3] * __ldg(r1.s.sgm + o));
-                  if (rg == 0 && r1.dbias != nullptr) atomicAdd(r1.dbias + o, t[4]);
-                }
-              }
-            }
-            __syncwarp();
-          }
-          if (has_s && r1.out2 != nullptr && active)
-            store_packed32(r1.out2, static_cast<long long>(m) * r1.out2_ld, nc, nq, pk);
-          if (m_ok && c + 1 < BLOCK_N / 32 && n0 + (c + 2) * 32 <= N) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              xq[j] = __ldg(x_row + (c + 1) * 4 + j);
-              if (has_s) zq[j] = __ldg(z_row + (c + 1) * 4 + j);
-            }
-          }
-        } else {
         if (active) {
           if (ep.elem_scale != nullptr) {
             float s[32];
@@ -778,7 +490,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) row_acc += (j < n_valid ? v[j] : 0.f);
         }
-        }  // generic epilogue math
         if (!ep.out_tma) {
           if (active && ep.out != nullptr)
             store_row32(ep.out, ep.out_dt, static_cast<long long>(m) * ep.out_ld, nc, n_valid, v);
