@@ -140,12 +140,20 @@ def wl_cfg4(ed, device, step_counter, rank, world):
 
         shard_noise(model, rank, world)  # r / s noise is drawn for the GLOBAL row: same result for any N
     gb = B * world
+    side = torch.cuda.Stream(device=device)
 
     def step(x, y):
+        # scheduling hint: the fast weights' KL regularisers depend on parameters only — evaluated on a side stream
+        # (their backward then runs there too), their small kernels fill the tails of the persistent GEMMs
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            kls = [k for l in layers for k in l.losses]
         h = x
         for l in layers:
             h = l(h)
-        loss = F.SoftmaxCrossEntropy.apply(h, y, gb, *[k for l in layers for k in l.losses])
+        main.wait_stream(side)
+        loss = F.SoftmaxCrossEntropy.apply(h, y, gb, *kls)
         F.backward(loss)
         return loss.detach()
 

@@ -375,10 +375,9 @@ int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream) {
     const long long n = static_cast<long long>(a->ensemble_size) * a->in_dim;
     const size_t bytes = sizeof(float) * static_cast<size_t>(n);
     float* ws = a->fast_ws;
-    if (a->rho_r != nullptr) ED2_TRY(k_fast_prep(a->rho_r, n, ws, ws + slot, s));
-    if (has_prev && a->prev_rho_s != nullptr) ED2_TRY(k_fast_prep(a->prev_rho_s, n, ws + 2 * slot, ws + 3 * slot, s));
-    cudaMemsetAsync(a->dmu_r, 0, bytes, s);
-    if (a->rho_r != nullptr) cudaMemsetAsync(a->drho_r, 0, bytes, s);
+    // one launch per side: sigma / sigmoid tables + zeroing of the column-sum accumulators the epilogue adds into
+    ED2_TRY(k_fast_prep(a->rho_r, n, ws, ws + slot, s, a->dmu_r, a->rho_r != nullptr ? a->drho_r : nullptr));
+    (void)bytes;
     Rank1Epi r{};
     r.r = fast_side(a->mu_r, a->rho_r ? ws : nullptr, ws + slot, a->eps_r);
     r.clip_lo = o.opts.clip_lo; r.clip_hi = o.opts.clip_hi;
@@ -389,9 +388,8 @@ int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream) {
     if (has_prev) {
       if (a->prev_z == nullptr || a->prev_dz == nullptr || a->prev_dmu_s == nullptr)
         return set_error(ED2_ERR_BAD_ARG, "rank1_bwd: prev_z, prev_dz and prev_dmu_s are required with prev_mu_s");
-      cudaMemsetAsync(a->prev_dmu_s, 0, bytes, s);
-      if (a->prev_rho_s != nullptr) cudaMemsetAsync(a->prev_drho_s, 0, bytes, s);
-      if (a->prev_dbias != nullptr) cudaMemsetAsync(a->prev_dbias, 0, bytes, s);
+      ED2_TRY(k_fast_prep(a->prev_rho_s, n, ws + 2 * slot, ws + 3 * slot, s, a->prev_dmu_s,
+                          a->prev_rho_s != nullptr ? a->prev_drho_s : nullptr, a->prev_dbias));
       r.s = fast_side(a->prev_mu_s, a->prev_rho_s ? ws + 2 * slot : nullptr, ws + 3 * slot, a->prev_eps_s);
       r.z_prev = a->prev_z; r.z_prev_ld = a->prev_z_ld; r.prev_act = a->prev_act;
       r.dmu_s = a->prev_dmu_s; r.drho_s = a->prev_rho_s ? a->prev_drho_s : nullptr; r.dbias = a->prev_dbias;

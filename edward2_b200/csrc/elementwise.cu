@@ -583,7 +583,13 @@ __global__ void scale_rows_kernel(const void* x, int dt, long long x_ld, long lo
 // chunk of rows of ONE member, so the per-(member, column) quantities (mu, sigma, sigmoid(rho)) are computed once,
 // the noise is two Philox blocks per row, every access is a 16-byte vector, and the column reductions of the backward
 // passes are per-thread accumulators flushed with one atomic per column per block (no shared memory).
-constexpr int kLeanRows = 64;
+constexpr int kLeanRows = 64;  // upper bound; the host shrinks it until the grid fills the GPU (lean_rows_for)
+inline int lean_rows_for(long long rows, int cols) {
+  const long long col_blocks = (cols / 8 + kBlock - 1) / kBlock;
+  int r = kLeanRows;
+  while (r > 4 && (rows / r) * col_blocks < 148 * 6) r >>= 1;
+  return r;
+}
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
@@ -632,13 +638,14 @@ template <bool kHasX>
 __global__ void __launch_bounds__(kBlock) rank1_scale_lean_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int rpm,
                                                                   int cols, const float* __restrict__ fw_mu,
                                                                   const float* __restrict__ fw_rho, Noise nz,
-                                                                  __nv_bfloat16* __restrict__ out, int out_ld) {
+                                                                  __nv_bfloat16* __restrict__ out, int out_ld,
+                                                                  int lean_rows) {
   const int c = (blockIdx.x * kBlock + threadIdx.x) * 8;
   if (c >= cols) return;
-  const int chunks = (rpm + kLeanRows - 1) / kLeanRows;
+  const int chunks = (rpm + lean_rows - 1) / lean_rows;
   const int e = blockIdx.y / chunks;
-  const long long row0 = (long long)e * rpm + (long long)(blockIdx.y - e * chunks) * kLeanRows;
-  const long long row1 = min((long long)(e + 1) * rpm, row0 + kLeanRows);
+  const long long row0 = (long long)e * rpm + (long long)(blockIdx.y - e * chunks) * lean_rows;
+  const long long row1 = min((long long)(e + 1) * rpm, row0 + lean_rows);
   const uint64_t key = lean_key(nz.seed, nz.step);
   LeanCols k;
   load_cols(fw_mu, fw_rho, e, c, cols, k);
@@ -661,10 +668,10 @@ __global__ void __launch_bounds__(kBlock) rank1_scale_lean_kernel(const __nv_bfl
 __global__ void __launch_bounds__(kBlock) rank1_bwd_out_lean_kernel(BwdOutArgs a) {
   const int c = (blockIdx.x * kBlock + threadIdx.x) * 8;
   if (c >= a.cols) return;
-  const int chunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
+  const int chunks = (a.rows_per_member + a.lean_rows - 1) / a.lean_rows;
   const int e = blockIdx.y / chunks;
-  const long long row0 = (long long)e * a.rows_per_member + (long long)(blockIdx.y - e * chunks) * kLeanRows;
-  const long long row1 = min((long long)(e + 1) * a.rows_per_member, row0 + kLeanRows);
+  const long long row0 = (long long)e * a.rows_per_member + (long long)(blockIdx.y - e * chunks) * a.lean_rows;
+  const long long row1 = min((long long)(e + 1) * a.rows_per_member, row0 + a.lean_rows);
   const uint64_t key = lean_key(a.eps_s.seed, a.eps_s.step);
   LeanCols k;
   load_cols(a.mu_s, a.rho_s, e, c, a.cols, k);
@@ -710,10 +717,10 @@ __global__ void __launch_bounds__(kBlock) rank1_bwd_out_lean_kernel(BwdOutArgs a
 __global__ void __launch_bounds__(kBlock) rank1_bwd_in_lean_kernel(BwdInArgs a) {
   const int c = (blockIdx.x * kBlock + threadIdx.x) * 8;
   if (c >= a.cols) return;
-  const int chunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
+  const int chunks = (a.rows_per_member + a.lean_rows - 1) / a.lean_rows;
   const int e = blockIdx.y / chunks;
-  const long long row0 = (long long)e * a.rows_per_member + (long long)(blockIdx.y - e * chunks) * kLeanRows;
-  const long long row1 = min((long long)(e + 1) * a.rows_per_member, row0 + kLeanRows);
+  const long long row0 = (long long)e * a.rows_per_member + (long long)(blockIdx.y - e * chunks) * a.lean_rows;
+  const long long row1 = min((long long)(e + 1) * a.rows_per_member, row0 + a.lean_rows);
   const uint64_t key = lean_key(a.eps.seed, a.eps.step);
   LeanCols k;
   load_cols(a.fw_mu, a.fw_rho, e, c, a.cols, k);
@@ -1217,17 +1224,24 @@ int k_peer_grad_finish(const PeerExchange& x, const float* mu, const float* rho,
   return check_launch("peer_grad_finish");
 }
 
-__global__ void fast_prep_kernel(const float* __restrict__ rho, long long n, float* __restrict__ sg, float* __restrict__ sgm) {
+__global__ void fast_prep_kernel(const float* __restrict__ rho, long long n, float* __restrict__ sg, float* __restrict__ sgm,
+                                 float* __restrict__ z0, float* __restrict__ z1, float* __restrict__ z2) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float r = __ldg(rho + i);
-    sg[i] = softplus_f(r) + kSoftplusEps;
-    sgm[i] = sigmoid_f(r);
+    if (rho != nullptr) {
+      const float r = __ldg(rho + i);
+      sg[i] = softplus_f(r) + kSoftplusEps;
+      sgm[i] = sigmoid_f(r);
+    }
+    if (z0 != nullptr) z0[i] = 0.f;
+    if (z1 != nullptr) z1[i] = 0.f;
+    if (z2 != nullptr) z2[i] = 0.f;
   }
 }
 
-int k_fast_prep(const float* rho, long long n, float* sg, float* sgm, cudaStream_t s) {
+int k_fast_prep(const float* rho, long long n, float* sg, float* sgm, cudaStream_t s, float* z0, float* z1, float* z2) {
   if (n <= 0) return ED2_OK;
-  fast_prep_kernel<<<static_cast<int>(std::min<long long>((n + kBlock - 1) / kBlock, 1024)), kBlock, 0, s>>>(rho, n, sg, sgm);
+  if (rho == nullptr && z0 == nullptr && z1 == nullptr && z2 == nullptr) return ED2_OK;
+  fast_prep_kernel<<<static_cast<int>(std::min<long long>((n + kBlock - 1) / kBlock, 1024)), kBlock, 0, s>>>(rho, n, sg, sgm, z0, z1, z2);
   count_launch();
   return check_launch("fast_prep");
 }
@@ -1242,15 +1256,16 @@ int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols
       (x == nullptr || (x_ld % 8 == 0 && al16(x))) && al16(fw_mu) && al16(fw_rho) && (cols % 4 == 0) &&
       ((x != nullptr && f_out == nullptr && xo_ld % 8 == 0 && al16(xo)) ||
        (x == nullptr && f_out != nullptr && f_ld % 8 == 0 && al16(f_out)))) {
-    const int chunks = (rpm + kLeanRows - 1) / kLeanRows;
+    const int lean_rows = lean_rows_for(rows, cols);
+    const int chunks = (rpm + lean_rows - 1) / lean_rows;
     dim3 grid((cols / 8 + kBlock - 1) / kBlock, static_cast<unsigned>((rows / rpm) * chunks));
     if (x != nullptr)
       rank1_scale_lean_kernel<true><<<grid, kBlock, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), (int)x_ld, rpm, cols,
                                                             fw_mu, fw_rho, nz,
-                                                            reinterpret_cast<__nv_bfloat16*>(xo), (int)xo_ld);
+                                                            reinterpret_cast<__nv_bfloat16*>(xo), (int)xo_ld, lean_rows);
     else
       rank1_scale_lean_kernel<false><<<grid, kBlock, 0, s>>>(nullptr, 0, rpm, cols, fw_mu, fw_rho, nz,
-                                                             reinterpret_cast<__nv_bfloat16*>(f_out), (int)f_ld);
+                                                             reinterpret_cast<__nv_bfloat16*>(f_out), (int)f_ld, lean_rows);
     count_launch();
     return check_launch("scale_rows(lean rank-1)");
   }
@@ -1276,7 +1291,8 @@ int k_bwd_out(const BwdOutArgs& a_in, cudaStream_t s) {
   if (default_opts && a.fast == 2 && a.dt == kBF16 && a.rho_s != nullptr && a.eps_s.injected == nullptr && a.cols % 8 == 0 &&
       a.gy_ld % 8 == 0 && a.y_ld % 8 == 0 && a.z_ld % 8 == 0 && (a.s_buf == nullptr || (a.s_ld % 8 == 0 && al16(a.s_buf))) &&
       a.dz_ld % 8 == 0 && al16(a.gy) && al16(a.y) && al16(a.z) && al16(a.dz) && al16(a.mu_s) && al16(a.rho_s) && a.d_fast_mu != nullptr) {
-    const int lchunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
+    a.lean_rows = lean_rows_for(a.rows, a.cols);
+    const int lchunks = (a.rows_per_member + a.lean_rows - 1) / a.lean_rows;
     dim3 lgrid((a.cols / 8 + kBlock - 1) / kBlock, members * lchunks);
     rank1_bwd_out_lean_kernel<<<lgrid, kBlock, 0, s>>>(a);
     count_launch();
@@ -1308,7 +1324,8 @@ int k_bwd_in(const BwdInArgs& a_in, cudaStream_t s) {
   if (default_opts && a.fast == 2 && a.dt == kBF16 && a.fw_rho != nullptr && a.eps.injected == nullptr && a.cols % 8 == 0 &&
       a.dxf_ld % 8 == 0 && a.x_ld % 8 == 0 && (a.dx == nullptr || (a.dx_ld % 8 == 0 && al16(a.dx))) && al16(a.dxf) &&
       al16(a.x) && al16(a.fw_mu) && al16(a.fw_rho) && a.d_fast_mu != nullptr) {
-    const int lchunks = (a.rows_per_member + kLeanRows - 1) / kLeanRows;
+    a.lean_rows = lean_rows_for(a.rows, a.cols);
+    const int lchunks = (a.rows_per_member + a.lean_rows - 1) / a.lean_rows;
     dim3 lgrid((a.cols / 8 + kBlock - 1) / kBlock, members * lchunks);
     rank1_bwd_in_lean_kernel<<<lgrid, kBlock, 0, s>>>(a);
     count_launch();

@@ -52,7 +52,9 @@ int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols
                  long long f_ld, cudaStream_t s, FastOpts opts = FastOpts());
 
 // sg = softplus(rho) + 1e-7, sgm = sigmoid(rho): the per-(member, column) tables the fused rank-1 GEMM epilogues read
-int k_fast_prep(const float* rho, long long n, float* sg, float* sgm, cudaStream_t s);
+// (rho may be null: tables not needed); z0..z2: optional [n] fp32 accumulators zeroed by the same launch
+int k_fast_prep(const float* rho, long long n, float* sg, float* sgm, cudaStream_t s, float* z0 = nullptr,
+                float* z1 = nullptr, float* z2 = nullptr);
 
 // ---- backward preparation on the output side of a layer:
 //   gp = gy ∘ act'(y)
@@ -76,6 +78,7 @@ struct BwdOutArgs {
   const float* gamma;           // BE
   const float* mu_s; const float* rho_s; Noise eps_s;  // rank-1
   FastOpts opts;                                       // rank-1 clip bounds / additive variant
+  int lean_rows = 0;                                   // rows per block of the lean kernels (set by k_bwd_out)
   const float* rho_b; Noise eps_b; float* d_bias_rho;  // rank-1 per-example sampled bias (dense.py:1131-1139)
   Noise sign_out;               // flipout (injected fp32 or philox sign)
   void* dz; long long dz_ld;
@@ -99,6 +102,7 @@ struct BwdInArgs {
   const void* x; long long x_ld;
   const float* fw_mu; const float* fw_rho; Noise eps;
   FastOpts opts;
+  int lean_rows = 0;          // rows per block of the lean kernel (set by k_bwd_in)
   void* dx; long long dx_ld;  // may be nullptr
   float* d_fast_mu; float* d_fast_rho;
 };
