@@ -685,7 +685,7 @@ def main():
     ap.add_argument("--fp32-allreduce", action="store_true", help="all-reduce fp32 gradients instead of bf16 buckets")
     ap.add_argument("--grad-exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how raw bf16 weight gradients (Reparameterization kernels) are summed over ranks")
-    ap.add_argument("--hook-exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--hook-exchange", default="dma", choices=["dma", "peer", "nccl"],
                     help="N > 1: how gradients reaching the per-parameter hook (rank-1 / BatchEnsemble kernels) are summed")
     ap.add_argument("--gemm-ctas", type=int, default=0, help="persistent GEMM CTAs when N > 1 (rest: NCCL)")
     ap.add_argument("--no-allreduce", action="store_true", help="diagnostic only: skip the gradient all-reduce")

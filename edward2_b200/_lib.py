@@ -98,6 +98,7 @@ class Rank1Bwd(C.Structure):
         ("prev_z", _vp), ("prev_z_ld", _i), ("prev_mu_s", _vp), ("prev_rho_s", _vp), ("prev_eps_s", Noise),
         ("prev_act", _i), ("prev_dz", _vp), ("prev_dz_ld", _i),
         ("prev_dmu_s", _vp), ("prev_drho_s", _vp), ("prev_dbias", _vp),
+        ("dw_lp", _vp), ("dw_done_event", _vp),
     ]
 
 
@@ -193,6 +194,9 @@ SIGNATURES = {
     "ed2_peer_close": (_i, [_vp]),
     "ed2_peer_free": (_i, [_vp]),
     "ed2_peer_signal": (_i, [C.POINTER(PeerExchange), _vp, _vp]),
+    "ed2_peer_flag": (_i, [C.POINTER(PeerExchange), _i, _vp]),
+    "ed2_peer_wait": (_i, [C.POINTER(PeerExchange), _i, _vp]),
+    "ed2_dma_copy": (_i, [_vp, _vp, C.c_size_t, _vp]),
     "ed2_peer_reduce_slice": (_i, [C.POINTER(PeerExchange), _i, _vp]),
     "ed2_peer_gather_f32": (_i, [C.POINTER(PeerExchange), _vp, _vp]),
     "ed2_peer_grad_finish": (_i, [C.POINTER(PeerExchange), _vp, _vp, Noise, _f, _vp, _f, _f, _vp, _vp, _vp, _i, _i, _vp]),

@@ -363,8 +363,17 @@ int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream) {
   o.d_fast_mu = a->dmu_s; o.d_fast_rho = a->rho_s ? a->drho_s : nullptr; o.dbias = a->dbias;
   if (!a->dz_ready) ED2_TRY(k_bwd_out(o, s));
   EpiParams e = epi_default();
-  e.out = a->dw; e.out_ld = a->out_dim; e.out_dt = kF32;
+  if (a->dw_lp != nullptr) {
+    if (a->dtype != kBF16) return set_error(ED2_ERR_BAD_ARG, "rank1_bwd: dw_lp needs ED2_BF16");
+    e.out = a->dw_lp; e.out_ld = a->out_dim; e.out_dt = kBF16;
+  } else {
+    e.out = a->dw; e.out_ld = a->out_dim; e.out_dt = kF32;
+  }
   ED2_TRY(gemm_xtg(a->dtype, a->xr, a->xr_ld, a->dz, a->dz_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  if (a->dw_done_event != nullptr) {
+    cudaError_t ce = cudaEventRecord(reinterpret_cast<cudaEvent_t>(a->dw_done_event), s);
+    if (ce != cudaSuccess) return set_error(ED2_ERR_CUDA, "rank1_bwd: cudaEventRecord: %s", cudaGetErrorString(ce));
+  }
   const bool has_prev = a->prev_mu_s != nullptr;
   const bool fused = a->fast_ws != nullptr && a->dtype == kBF16 && !a->additive && a->eps_r.injected == nullptr &&
                      (!has_prev || a->prev_eps_s.injected == nullptr) && gemm_rank1_fusable(a->batch, a->in_dim, rpm) &&

@@ -151,6 +151,8 @@ struct PeerExchange {
 };
 // publish this rank's bucket (+ copy `small_src` into the arena): epoch += 1, ready flag on every rank
 int k_peer_signal(const PeerExchange& x, const float* small_src, cudaStream_t s);
+int k_peer_flag(const PeerExchange& x, int which, cudaStream_t s);
+int k_peer_wait(const PeerExchange& x, int which, cudaStream_t s);
 // owner pass: wait for every rank's ready flag, pull + sum the owned slice (rank order), publish the reduced flag
 // light: small footprint (1 block x 128 threads per SM) for running beside the finishing pass instead of a GEMM
 int k_peer_reduce_slice(const PeerExchange& x, int light, cudaStream_t s);

@@ -39,6 +39,26 @@ __global__ void __launch_bounds__(kBlock) peer_signal_kernel(PeerExchange x, con
   }
 }
 
+// publish the CURRENT epoch into flag section `which` (0: ready, 1: reduced) of every rank — used by the copy-engine
+// exchange, where the data movement is a DMA the flag must follow in stream order
+__global__ void peer_flag_kernel(PeerExchange x, int which) {
+  if (threadIdx.x < x.world) {
+    const unsigned long long epoch = peer::local_words(x)[0];
+    __threadfence_system();
+    peer::st_release_sys(x.flags[threadIdx.x] + which * x.world + x.rank, epoch);
+  }
+}
+
+// Wait until flag section `which` of THIS rank carries the current epoch from every rank.  One warp, <= 32 registers:
+// it fits beside a persistent GEMM CTA that owns the rest of the SM, so waiting for a peer never keeps a GEMM CTA from
+// becoming resident (the heavy reduce / convert kernels are enqueued behind it and start only when their data is here).
+__global__ void __maxnreg__(32) peer_wait_kernel(PeerExchange x, int which) {
+  unsigned long long* lw = peer::local_words(x);
+  const unsigned long long epoch = lw[0];
+  if (threadIdx.x < x.world)
+    peer::wait_flag(x.flags[x.rank] + which * x.world + threadIdx.x, epoch, lw + 2, 0x400 + which * 0x100 + threadIdx.x);
+}
+
 __device__ __forceinline__ void acc8(float (&a)[8], const uint4& v) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -156,6 +176,29 @@ int k_peer_signal(const PeerExchange& x, const float* small_src, cudaStream_t s)
   return check_launch("peer_signal");
 }
 
+int k_peer_flag(const PeerExchange& x, int which, cudaStream_t s) {
+  int st = check_exchange(x);
+  if (st != ED2_OK) return st;
+  if (which != 0 && which != 1) return set_error(ED2_ERR_BAD_ARG, "peer flag: which must be 0 (ready) or 1 (reduced)");
+  peer_flag_kernel<<<1, 32, 0, s>>>(x, which);
+  count_launch();
+  return check_launch("peer_flag");
+}
+
+int k_peer_wait(const PeerExchange& x, int which, cudaStream_t s) {
+  int st = check_exchange(x);
+  if (st != ED2_OK) return st;
+  if (which != 0 && which != 1) return set_error(ED2_ERR_BAD_ARG, "peer wait: which must be 0 (ready) or 1 (reduced)");
+  static const bool once = [] {
+    cudaFuncSetAttribute(peer_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return true;
+  }();
+  (void)once;
+  peer_wait_kernel<<<1, 32, 0, s>>>(x, which);
+  count_launch();
+  return check_launch("peer_wait");
+}
+
 int k_peer_reduce_slice(const PeerExchange& x, int light, cudaStream_t s) {
   int st = check_exchange(x);
   if (st != ED2_OK) return st;
@@ -252,6 +295,22 @@ int ed2_peer_close(void* ptr) {
 int ed2_peer_free(void* ptr) {
   cudaError_t e = cudaFree(ptr);
   return e == cudaSuccess ? ED2_OK : set_error(ED2_ERR_CUDA, "ed2_peer_free: %s", cudaGetErrorString(e));
+}
+
+int ed2_peer_flag(const ed2_peer_exchange* e, int which, void* stream) {
+  return k_peer_flag(to_internal(e), which, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ed2_peer_wait(const ed2_peer_exchange* e, int which, void* stream) {
+  return k_peer_wait(to_internal(e), which, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ed2_dma_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return ED2_OK;
+  if (dst == nullptr || src == nullptr) return set_error(ED2_ERR_BAD_ARG, "dma_copy: null pointer");
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "dma_copy: %s", cudaGetErrorString(e));
+  return ED2_OK;
 }
 
 int ed2_peer_signal(const ed2_peer_exchange* e, const float* small_src, void* stream) {

@@ -222,6 +222,103 @@ class PeerExchange:
         self.arena.close()
 
 
+def dma_layout(n: int, world: int) -> dict:
+    """Byte offsets of one copy-engine exchange arena:
+    [bucket W*chunk bf16 | recv W*chunk bf16 | gathered W*chunk bf16 | flags | scratch flags], 256-byte aligned."""
+    if n <= 0 or n % 8 != 0:
+        raise ValueError(f"dma exchange needs n % 8 == 0 (got {n})")
+    if not 2 <= world <= 8:
+        raise ValueError(f"dma exchange needs 2 <= world <= 8 (got {world})")
+    al = lambda b: (b + 255) // 256 * 256  # noqa: E731
+    chunk = ((n + world - 1) // world + 7) // 8 * 8
+    region = al(2 * chunk * world)
+    fl = al(8 * (2 * world + 3))
+    return dict(bucket=0, recv=region, gathered=2 * region, flags=3 * region, scratch=3 * region + fl,
+                nbytes=3 * region + 2 * fl, chunk=chunk)
+
+
+class DmaExchange:
+    """Sum of ONE bf16 gradient over the ranks of a box with the data moved by the COPY ENGINES (include/ed2b200.h:
+    ed2_dma_copy / ed2_peer_flag): reduce-scatter = every rank DMA-pushes slice q of its bucket into rank q's receive
+    slots, the owner sums its slots from LOCAL memory; all-gather = the owner DMA-pushes the reduced slice into every
+    rank's gathered buffer, which is converted to fp32 locally.  No SM takes part in the transfers, so they overlap the
+    persistent GEMMs (which own every SM of the fused rank-1 step) instead of queueing behind them."""
+
+    def __init__(self, n: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self.lib = _lib.load()
+        world = dist.get_world_size(group)
+        lay = dma_layout(n, world)
+        self.arena = PeerArena(lay["nbytes"], group)
+        rank, ptrs = self.arena.rank, self.arena.ptrs
+        self.n, self.small_n, self.world, self.rank, self.chunk, self.lay = n, 0, world, rank, lay["chunk"], lay
+        me = ptrs[rank]
+        lo = rank * lay["chunk"]
+        real, local = _lib.PeerExchange(), _lib.PeerExchange()
+        for c in (real, local):
+            c.world, c.rank, c.n, c.chunk, c.small_n = world, rank, n, lay["chunk"], 0
+        for r, base in enumerate(ptrs):
+            real.bucket[r], real.reduced[r], real.flags[r] = base + lay["bucket"], base + lay["gathered"], base + lay["flags"]
+            real.small_vec[r] = base + lay["flags"]
+            # local view: index i of "rank r's bucket" (i in my owned slice) -> my receive slot r
+            local.bucket[r] = (me + lay["bucket"]) if r == rank else (me + lay["recv"] + 2 * (r * lay["chunk"] - lo))
+            local.reduced[r] = me + lay["gathered"]
+            local.flags[r] = (me + lay["flags"]) if r == rank else (me + lay["scratch"])
+            local.small_vec[r] = me + lay["flags"]
+        self.real, self.local = real, local
+        self._real, self._local = C.byref(real), C.byref(local)
+        self.bucket_ptr = me + lay["bucket"]
+        self._pending = False
+
+    def cast_into_bucket(self, grad2d):
+        from . import _lib
+
+        rows, cols = grad2d.shape
+        _lib.check(self.lib.ed2_cast(grad2d.data_ptr(), _lib.dt_of(grad2d), grad2d.stride(0), self.bucket_ptr, _lib.BF16,
+                                     cols, rows, cols, _lib.stream_ptr()), "ed2_cast")
+
+    def _slice(self, q):
+        lo = q * self.chunk
+        return lo, max(0, min(self.n, lo + self.chunk) - lo)
+
+    def scatter_reduce(self):
+        """Current stream: push my bucket's slices to their owners, publish, sum my slice, push it to everyone."""
+        from . import _lib
+
+        if self._pending:
+            raise RuntimeError("DmaExchange started again before the previous exchange was joined (GradientAllReduce.wait())")
+        self._pending = True
+        lay, me, st = self.lay, self.arena.ptrs[self.rank], _lib.stream_ptr()
+        for d in range(1, self.world):  # staggered peers: no two ranks target the same receiver at the same time
+            q = (self.rank + d) % self.world
+            lo, cnt = self._slice(q)
+            if cnt:
+                _lib.check(self.lib.ed2_dma_copy(self.arena.ptrs[q] + lay["recv"] + 2 * self.rank * self.chunk,
+                                                 me + lay["bucket"] + 2 * lo, 2 * cnt, st), "ed2_dma_copy")
+        _lib.check(self.lib.ed2_peer_signal(self._real, None, st), "ed2_peer_signal")
+        _lib.check(self.lib.ed2_peer_wait(self._real, 0, st), "ed2_peer_wait")  # one warp: holds no SM while peers push
+        _lib.check(self.lib.ed2_peer_reduce_slice(self._local, 0, st), "ed2_peer_reduce_slice")
+        lo, cnt = self._slice(self.rank)
+        for d in range(1, self.world):
+            q = (self.rank + d) % self.world
+            if cnt:
+                _lib.check(self.lib.ed2_dma_copy(self.arena.ptrs[q] + lay["gathered"] + 2 * lo,
+                                                 me + lay["gathered"] + 2 * lo, 2 * cnt, st), "ed2_dma_copy")
+        _lib.check(self.lib.ed2_peer_flag(self._real, 1, st), "ed2_peer_flag")
+
+    def gather_f32(self, out):
+        from . import _lib
+
+        _lib.check(self.lib.ed2_peer_wait(self._real, 1, _lib.stream_ptr()), "ed2_peer_wait")
+        _lib.check(self.lib.ed2_peer_gather_f32(self._local, out.data_ptr(), _lib.stream_ptr()), "ed2_peer_gather_f32")
+
+    def close(self):
+        self.arena.close()
+
+
 class GradientAllReduce:
     """Overlapped gradient all-reduce: a post-accumulate hook per parameter launches an async sum-all-reduce on the
     process group's own stream the moment that gradient is final; `wait()` joins them before the optimizer step.
@@ -241,6 +338,9 @@ class GradientAllReduce:
         # DenseBatchEnsemble / DenseRank1 / Dense, Flipout's dmu / drho) are cast to bf16 into a peer arena and summed by
         # the same signal / owner-pass kernels, then gathered back as fp32 — no NCCL call for them either.
         self.hook_exchange = hook_exchange
+        # gradients below 64 K elements are packed and summed by ONE all-reduce at wait() instead of one NCCL call each
+        # (a rank-1 MLP has 15 of them per step; each call is a kernel that must find SMs between persistent GEMMs)
+        self.flat_small, self._small, self._flat = True, [], {}
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._hooks, self._buckets, self._early_done = [], {}, set()
         self._ids = set()
@@ -265,7 +365,7 @@ class GradientAllReduce:
 
     def wants_peer(self, p) -> bool:
         return (self.exchange_mode == "peer" and self.wants(p) and not self.average and p.numel() % 8 == 0
-                and p.shape[-1] % 8 == 0 and self.world <= 8)
+                and p.shape[-1] % 8 == 0 and self.world <= 8)  # (also the gate of the hook-path peer / dma exchanges)
 
     def peer_exchange(self, p, small_n: int) -> PeerExchange:
         """The (lazily built, collective) exchange of parameter `p`; every rank reaches this in the same order."""
@@ -282,6 +382,38 @@ class GradientAllReduce:
             self._exchanges[id(p)] = ex
         return ex
 
+    def dma_exchange(self, p):
+        """The (lazily built, collective) copy-engine exchange of parameter `p`."""
+        ex = self._exchanges.get(id(p))
+        if ex is None:
+            try:
+                ex = DmaExchange(p.numel(), self.group)
+            except RuntimeError as e:  # raised on EVERY rank (PeerArena agrees collectively): NCCL path from now on
+                import sys
+
+                sys.stderr.write(f"[edward2_b200.dist] {e}; falling back to the NCCL all-reduce of the bf16 buckets\n")
+                self.hook_exchange = "nccl"
+                return None
+            self._exchanges[id(p)] = ex
+        return ex
+
+    def wants_dma(self, p) -> bool:
+        return self.hook_exchange == "dma" and self.wants_peer(p)
+
+    def exchange_bucket(self, p, ex, after=None):
+        """`ex`'s bucket already holds this rank's bf16 gradient of `p` (written by the layer's dW GEMM): run the
+        exchange on the side streams and install the summed fp32 gradient as p.grad (bypassing the hook).  `after`:
+        event recorded right behind the dW GEMM — the exchange then overlaps whatever the layer enqueued after it."""
+        g = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+        reduced_ev = self.on_side_stream(ex.scatter_reduce, which=0, fork=after)
+        done_ev = self.on_side_stream(lambda: ex.gather_f32(g), which=1, after=reduced_ev)
+        self.defer(None, after=done_ev, keep=(g,))
+        self.mark_done(p)
+        if p.grad is None:
+            p.grad = g
+        else:  # accumulate only once the sum has landed
+            self.defer(lambda: p.grad.add_(g), after=done_ev, keep=(g,))
+
     def defer(self, finish, after=None, keep=None):
         """At wait(): make the current stream wait for the CUDA event `after`, then run `finish` (if any).  `keep` holds
         tensors that side-stream kernels read, alive until the streams have joined."""
@@ -294,7 +426,7 @@ class GradientAllReduce:
             if p is not None:
                 self._early_done.add(id(p))
 
-    def on_side_stream(self, fn, which: int = 0, after=None):
+    def on_side_stream(self, fn, which: int = 0, after=None, fork=None):
         """Run `fn` (kernel launches) on side stream `which` of the reducer, ordered after everything enqueued so far on
         the current stream (and after the event `after`); returns the event that marks its completion.  Capturable in a
         CUDA graph as long as wait() joins the returned event back."""
@@ -302,10 +434,11 @@ class GradientAllReduce:
         while len(self._side) <= which:
             self._side.append(torch.cuda.Stream(priority=-1))
         side = self._side[which]
-        ev = torch.cuda.Event()
-        ev.record(main)
+        if fork is None:  # ordered after everything enqueued so far on the current stream
+            fork = torch.cuda.Event()
+            fork.record(main)
         with torch.cuda.stream(side):
-            side.wait_event(ev)
+            side.wait_event(fork)
             if after is not None:
                 side.wait_event(after)
             fn()
@@ -342,6 +475,16 @@ class GradientAllReduce:
             return
         if self.average:
             g.div_(self.world)
+        if (self.hook_exchange == "dma" and self.wants_peer(p) and g.is_cuda and g.dtype == torch.float32
+                and g.is_contiguous() and g.data_ptr() % 16 == 0):
+            ex = self.dma_exchange(p)
+            if ex is not None:
+                g2 = g.reshape(-1, g.shape[-1]) if g.dim() > 1 else g.reshape(1, -1)
+                ex.cast_into_bucket(g2)
+                reduced_ev = self.on_side_stream(ex.scatter_reduce, which=0)
+                done_ev = self.on_side_stream(lambda ex=ex, g=g: ex.gather_f32(g), which=1, after=reduced_ev)
+                self.defer(None, after=done_ev, keep=(g,))
+                return
         if (self.hook_exchange == "peer" and self.wants_peer(p) and g.is_cuda and g.dtype == torch.float32
                 and g.is_contiguous() and g.data_ptr() % 16 == 0):
             ex = self.peer_exchange(p, 0)
@@ -357,6 +500,10 @@ class GradientAllReduce:
                 done_ev = self.on_side_stream(lambda ex=ex, g=g: ex.gather_f32(g), which=1, after=reduced_ev)
                 self.defer(None, after=done_ev, keep=(g,))
                 return
+        if g.is_cuda and g.dtype == torch.float32 and g.numel() < 65536 and self.flat_small:
+            # small gradients (fast weights, biases): packed into ONE flat fp32 buffer, one all-reduce at wait()
+            self._small.append((p, g))
+            return
         if self.compress is not None and g.is_cuda and g.dtype == torch.float32 and g.numel() >= 65536:
             from . import ops
 
@@ -368,7 +515,25 @@ class GradientAllReduce:
         else:
             self.handles.append((dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True), None, None))
 
+    def _reduce_small(self):
+        if not self._small:
+            return
+        total = sum(g.numel() for _, g in self._small)
+        flat = self._flat.get(total)
+        if flat is None:
+            flat = self._flat[total] = torch.empty(total, dtype=torch.float32, device=self._small[0][1].device)
+        views, o = [], 0
+        for _, g in self._small:
+            views.append(flat[o:o + g.numel()].view(g.shape))
+            o += g.numel()
+        torch._foreach_copy_(views, [g for _, g in self._small])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        for (p, _), v in zip(self._small, views):
+            p.grad = v  # the summed gradient lives in the flat buffer until the next step's reduction
+        self._small.clear()
+
     def wait(self):
+        self._reduce_small()
         for h, g2, b in self.handles:
             if isinstance(h, torch.cuda.Event):  # side-stream work of the peer exchange
                 torch.cuda.current_stream().wait_event(h)

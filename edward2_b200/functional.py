@@ -232,6 +232,7 @@ class Rank1Dense(torch.autograd.Function):
             ctx.meta = (act, E, dtype, bias is not None, x.dtype, eps_r, eps_s)
             ctx.opts = (bool(additive), clip, eps_b, plain)
             ctx.links = (in_link, out_link)
+            ctx.kernel_ref = kernel
         return y
 
     @staticmethod
@@ -271,7 +272,19 @@ class Rank1Dense(torch.autograd.Function):
         dx = _new(B, I, dtype, dev) if need_dx else None
         fused_in = (plain and eps_r.injected is None and I % 8 == 0 and bool(lib.ed2_rank1_fusable(B, I, E)))
         dxr = None if fused_in else _new(B, I, dtype, dev)
-        dw = torch.empty(I, O, **f32)
+        # data parallel with the copy-engine exchange: the dW GEMM writes bf16 straight into the exchange bucket
+        sync, dma_ex = GradSync.current, None
+        kernel_ref = getattr(ctx, "kernel_ref", None)
+        if (sync is not None and kernel_ref is not None and dtype == torch.bfloat16 and kernel_ref.is_leaf
+                and getattr(sync, "wants_dma", None) is not None and sync.wants_dma(kernel_ref)):
+            dma_ex = sync.dma_exchange(kernel_ref)
+        dw = torch.empty(I, O, **f32) if dma_ex is None else None
+        dw_ev = None
+        if dma_ex is not None:
+            a.dw_lp = dma_ex.bucket_ptr
+            dw_ev = torch.cuda.Event()
+            dw_ev.record()  # materialises the handle (re-recorded by the library right after the dW GEMM)
+            a.dw_done_event = dw_ev.cuda_event
         dmu_r = torch.empty(E, I, **f32)
         drho_r = torch.empty(E, I, **f32) if rho_r is not None else None
         drho_b = torch.empty(E, O, **f32) if rho_b is not None else None
@@ -299,8 +312,11 @@ class Rank1Dense(torch.autograd.Function):
         a.mu_r, a.rho_r, a.eps_r = mu_r.data_ptr(), _p(rho_r), eps_r.c()
         a.mu_s, a.rho_s, a.eps_s = mu_s.data_ptr(), _p(rho_s), eps_s.c()
         a.dz, a.dz_ld, a.dxr, a.dxr_ld, a.dx, a.dx_ld = dz.data_ptr(), _lib.ld(dz), _p(dxr), _ldn(dxr), _p(dx), _ldn(dx)
-        a.dw, a.dmu_r, a.drho_r, a.dmu_s, a.drho_s, a.dbias = dw.data_ptr(), dmu_r.data_ptr(), _p(drho_r), dmu_s.data_ptr(), _p(drho_s), _p(dbias)
+        a.dw, a.dmu_r, a.drho_r, a.dmu_s, a.drho_s, a.dbias = _p(dw), dmu_r.data_ptr(), _p(drho_r), dmu_s.data_ptr(), _p(drho_s), _p(dbias)
         _lib.check(lib.ed2_rank1_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_rank1_dense_bwd")
+        if dma_ex is not None:
+            # dw stays None: the summed gradient is installed by the reducer; the exchange starts behind the dW GEMM
+            sync.exchange_bucket(kernel_ref, dma_ex, after=dw_ev)
         if prev is not None:
             in_link.record(dx, prev["dz"], prev["dmu_s"], prev["drho_s"], prev["dbias"])
         if dx is not None and dx.dtype != x_dtype:

@@ -257,7 +257,7 @@ typedef struct {
   void* dz; int dz_ld;
   void* dxr; int dxr_ld;
   void* dx; int dx_ld;
-  float* dw;
+  float* dw;                /* fp32 [in_dim][out_dim]; may be NULL when dw_lp is given */
   float* dmu_r; float* drho_r; float* dmu_s; float* drho_s; float* dbias; /* drho_* / dbias may be NULL */
   int additive; float clip_lo, clip_hi;
   const float* rho_b; ed2_noise eps_b; float* drho_b;  /* sampled bias: dbias is d(bias mean), drho_b [E][out_dim] */
@@ -273,6 +273,11 @@ typedef struct {
   const float* prev_mu_s; const float* prev_rho_s; ed2_noise prev_eps_s; int prev_act;
   void* prev_dz; int prev_dz_ld;
   float* prev_dmu_s; float* prev_drho_s; float* prev_dbias;
+  /* data parallel: when non-NULL the dW GEMM writes the kernel gradient as ED2_BF16 [in_dim][out_dim] (pitch out_dim)
+   * straight into this buffer — the gradient-exchange bucket — instead of fp32 `dw` */
+  void* dw_lp;
+  void* dw_done_event;  /* optional cudaEvent_t recorded on `stream` right after the dW GEMM is enqueued: the caller's
+                           exchange of dW then overlaps the dX GEMM that follows */
 } ed2_rank1_bwd_args;
 int ed2_rank1_dense_bwd(const ed2_rank1_bwd_args* a, void* stream);
 
@@ -367,6 +372,19 @@ int ed2_peer_open(const void* handle, void** ptr_out);
 int ed2_peer_close(void* ptr);
 int ed2_peer_free(void* ptr);
 int ed2_peer_signal(const ed2_peer_exchange* e, const float* small_src, void* stream);
+/* Copy-engine variant of the exchange (edward2_b200/dist.py DmaExchange): the slices travel by DMA (ed2_dma_copy =
+ * cudaMemcpyAsync between IPC-mapped arenas: no SM is involved, so the transfers overlap the persistent GEMMs that own
+ * every SM), the sums and the fp32 conversion read LOCAL memory only.  Per gradient: push slice q of the bucket into
+ * rank q's receive slot, ed2_peer_signal (ready flags); ed2_peer_reduce_slice on a LOCAL view (bucket[r] = the receive
+ * slots) sums the owned slice; push it into every rank's gathered buffer, ed2_peer_flag(which = 1); ed2_peer_gather_f32
+ * on a local view converts the gathered bf16 gradient.  ed2_peer_flag publishes the current epoch into flag section
+ * `which` (0 ready, 1 reduced) of every rank, after everything enqueued before it on `stream`. */
+int ed2_peer_flag(const ed2_peer_exchange* e, int which, void* stream);
+/* one-warp kernel that returns when flag section `which` of this rank carries the current epoch from every rank: small
+ * enough to sit beside a persistent GEMM CTA, so that the heavy kernels enqueued behind it start only when their data
+ * has arrived and never hold SMs while waiting for a peer */
+int ed2_peer_wait(const ed2_peer_exchange* e, int which, void* stream);
+int ed2_dma_copy(void* dst, const void* src, size_t bytes, void* stream);
 int ed2_peer_reduce_slice(const ed2_peer_exchange* e, int light /* 1: small footprint, runs beside the finishing pass */,
                           void* stream);
 /* plain finishing pass for gradients that need no further arithmetic (deterministic kernels; any fp32 gradient that was
