@@ -284,6 +284,35 @@ class DmaExchange:
         lo = q * self.chunk
         return lo, max(0, min(self.n, lo + self.chunk) - lo)
 
+    _copy_streams = {}  # device index -> streams the DMA pushes fan out over (one copy engine each)
+    N_COPY_STREAMS = 4
+
+    def _fan_out(self, copies):
+        """Issue the (dst, src, bytes) DMA copies over several streams forked from / joined back into the current one:
+        independent copies then run on different copy engines (a single stream would serialise them on one)."""
+        from . import _lib
+
+        copies = [c for c in copies if c[2] > 0]
+        if not copies:
+            return
+        cur = torch.cuda.current_stream()
+        if len(copies) == 1:
+            _lib.check(self.lib.ed2_dma_copy(*copies[0], cur.cuda_stream), "ed2_dma_copy")
+            return
+        dev = torch.cuda.current_device()
+        pool = DmaExchange._copy_streams.setdefault(dev, [torch.cuda.Stream(priority=-1) for _ in range(self.N_COPY_STREAMS)])
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        used = pool[:min(len(pool), len(copies))]
+        for st in used:
+            st.wait_event(fork)
+        for i, (dst, src, nbytes) in enumerate(copies):
+            _lib.check(self.lib.ed2_dma_copy(dst, src, nbytes, used[i % len(used)].cuda_stream), "ed2_dma_copy")
+        for st in used:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+
     def scatter_reduce(self):
         """Current stream: push my bucket's slices to their owners, publish, sum my slice, push it to everyone."""
         from . import _lib
@@ -291,23 +320,21 @@ class DmaExchange:
         if self._pending:
             raise RuntimeError("DmaExchange started again before the previous exchange was joined (GradientAllReduce.wait())")
         self._pending = True
-        lay, me, st = self.lay, self.arena.ptrs[self.rank], _lib.stream_ptr()
+        lay, me = self.lay, self.arena.ptrs[self.rank]
+        pushes = []
         for d in range(1, self.world):  # staggered peers: no two ranks target the same receiver at the same time
             q = (self.rank + d) % self.world
             lo, cnt = self._slice(q)
-            if cnt:
-                _lib.check(self.lib.ed2_dma_copy(self.arena.ptrs[q] + lay["recv"] + 2 * self.rank * self.chunk,
-                                                 me + lay["bucket"] + 2 * lo, 2 * cnt, st), "ed2_dma_copy")
+            pushes.append((self.arena.ptrs[q] + lay["recv"] + 2 * self.rank * self.chunk, me + lay["bucket"] + 2 * lo, 2 * cnt))
+        self._fan_out(pushes)
+        st = _lib.stream_ptr()
         _lib.check(self.lib.ed2_peer_signal(self._real, None, st), "ed2_peer_signal")
         _lib.check(self.lib.ed2_peer_wait(self._real, 0, st), "ed2_peer_wait")  # one warp: holds no SM while peers push
         _lib.check(self.lib.ed2_peer_reduce_slice(self._local, 0, st), "ed2_peer_reduce_slice")
         lo, cnt = self._slice(self.rank)
-        for d in range(1, self.world):
-            q = (self.rank + d) % self.world
-            if cnt:
-                _lib.check(self.lib.ed2_dma_copy(self.arena.ptrs[q] + lay["gathered"] + 2 * lo,
-                                                 me + lay["gathered"] + 2 * lo, 2 * cnt, st), "ed2_dma_copy")
-        _lib.check(self.lib.ed2_peer_flag(self._real, 1, st), "ed2_peer_flag")
+        self._fan_out([(self.arena.ptrs[(self.rank + d) % self.world] + lay["gathered"] + 2 * lo, me + lay["gathered"] + 2 * lo,
+                        2 * cnt) for d in range(1, self.world)])
+        _lib.check(self.lib.ed2_peer_flag(self._real, 1, _lib.stream_ptr()), "ed2_peer_flag")
 
     def gather_f32(self, out):
         from . import _lib
