@@ -170,6 +170,7 @@ SIGNATURES = {
     "ed2_check_device": (_i, [_i]),
     "ed2_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
     "ed2_philox_normal": (_i, [_vp, _ll, _u64, _u64, _vp]),
+    "ed2_philox_normal_fast": (_i, [_vp, _ll, _u64, _u64, _vp]),
     "ed2_philox_uniform": (_i, [_vp, _ll, _u64, _u64, _vp]),
     "ed2_philox_sign": (_i, [_vp, _ll, _u64, _u64, _vp]),
     "ed2_philox_raw": (_i, [_vp, _ll, _u64, _u64, _vp]),

@@ -165,6 +165,7 @@ int ed2_gemm(const ed2_gemm_desc* d, void* stream) {
 }
 
 int ed2_philox_normal(float* out, long long n, uint64_t seed, uint64_t stream, void* s) { return k_philox_fill(0, out, n, seed, stream, S(s)); }
+int ed2_philox_normal_fast(float* out, long long n, uint64_t seed, uint64_t stream, void* s) { return k_philox_fill(3, out, n, seed, stream, S(s)); }
 int ed2_philox_uniform(float* out, long long n, uint64_t seed, uint64_t stream, void* s) { return k_philox_fill(1, out, n, seed, stream, S(s)); }
 int ed2_philox_sign(float* out, long long n, uint64_t seed, uint64_t stream, void* s) { return k_philox_fill(2, out, n, seed, stream, S(s)); }
 int ed2_philox_raw(uint32_t* out, long long nb, uint64_t seed, uint64_t stream, void* s) { return k_philox_raw(out, nb, seed, stream, S(s)); }

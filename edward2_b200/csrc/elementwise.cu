@@ -140,6 +140,7 @@ __global__ void philox_fill_kernel(float* out, long long n, uint64_t seed, uint6
   for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
     float e[4];
     if (kKind == 0) philox_normal4(seed, stream, b, e);
+    else if (kKind == 3) philox_normal4<true>(seed, stream, b, e);  // hardware-approximate Box-Muller (bf16 paths)
     else if (kKind == 1) philox_uniform4(seed, stream, b, e);
     else philox_sign4(seed, stream, b, e);
     const long long i = b << 2;
@@ -1037,6 +1038,7 @@ int k_philox_fill(int kind, float* out, long long n, uint64_t seed, uint64_t str
   const int g = grid_for((n + 3) / 4);
   if (kind == 0) philox_fill_kernel<0><<<g, kBlock, 0, s>>>(out, n, seed, stream);
   else if (kind == 1) philox_fill_kernel<1><<<g, kBlock, 0, s>>>(out, n, seed, stream);
+  else if (kind == 3) philox_fill_kernel<3><<<g, kBlock, 0, s>>>(out, n, seed, stream);
   else philox_fill_kernel<2><<<g, kBlock, 0, s>>>(out, n, seed, stream);
   count_launch();
   return check_launch("philox_fill");

@@ -8,7 +8,7 @@
 //   outputs  = 4 x uint32 -> the 4 consecutive elements 4*block .. 4*block+3 of the stream
 // so the value of element i depends only on (seed, stream, i): forward, backward and any tiling regenerate
 // the same epsilon without storing it (SURVEY.md §7 hard part 3).
-//   uniform  u = ((x >> 8) + 0.5) * 2^-24            in (0, 1), exactly representable
+//   uniform  u = ((x >> 8) + 0.5) * 2^-24            in (0, 1) (fp32 rounds the top half of the range to 2^-24 steps)
 //   normal   Box-Muller on (x0,x1) -> (z0,z1), (x2,x3) -> (z2,z3)
 //   sign     +1 if bit 31 of x is set else -1        (P(+1) = 1/2)
 #pragma once
@@ -98,7 +98,9 @@ __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t stream, 
   uint32_t x[4];
   philox_block(seed, stream, block, x);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) u[i] = u32_to_uniform(x[i]);
+  // (x >> 8) + 0.5 needs 25 bits above 2^23: the top value rounds to 2^24 in fp32, i.e. u == 1.  Box-Muller does not
+  // care (log 1 = 0, angle 2 pi); the uniform STREAM promises the open interval, so it is clamped to 1 - 2^-24.
+  for (int i = 0; i < 4; ++i) u[i] = fminf(u32_to_uniform(x[i]), 0.99999994f);
 }
 
 __device__ __forceinline__ void philox_sign4(uint64_t seed, uint64_t stream, uint64_t block, float (&s)[4]) {

@@ -66,7 +66,8 @@ def philox(kind: str, n: int, seed: int, stream: int, device="cuda") -> torch.Te
         _lib.check(lib.ed2_philox_raw(out.data_ptr(), n, seed, stream, _lib.stream_ptr()), "philox_raw")
         return out
     out = torch.empty(n, dtype=torch.float32, device=device)
-    fn = {"normal": lib.ed2_philox_normal, "uniform": lib.ed2_philox_uniform, "sign": lib.ed2_philox_sign}[kind]
+    fn = {"normal": lib.ed2_philox_normal, "normal_fast": lib.ed2_philox_normal_fast, "uniform": lib.ed2_philox_uniform,
+          "sign": lib.ed2_philox_sign}[kind]
     _lib.check(fn(out.data_ptr(), n, seed, stream, _lib.stream_ptr()), f"philox_{kind}")
     return out
 

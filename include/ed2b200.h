@@ -106,6 +106,9 @@ int ed2_gemm(const ed2_gemm_desc* desc, void* stream);
  * Replaces tf.random.* / tfp Normal.sample at edward2/tensorflow/random_variable.py:161-174 and
  * edward2/tensorflow/layers/dense.py:261-270. */
 int ed2_philox_normal(float* out, long long n, uint64_t seed, uint64_t stream, void* s);
+/* the same stream through the hardware-approximate Box-Muller (lg2 / sin / cos / sqrt.approx) that every bf16 path
+ * uses — the lean sampling / finishing kernels and the fused rank-1 GEMM epilogues — exposed for the statistical tests */
+int ed2_philox_normal_fast(float* out, long long n, uint64_t seed, uint64_t stream, void* s);
 int ed2_philox_uniform(float* out, long long n, uint64_t seed, uint64_t stream, void* s);
 int ed2_philox_sign(float* out, long long n, uint64_t seed, uint64_t stream, void* s);
 int ed2_philox_raw(uint32_t* out, long long n_blocks, uint64_t seed, uint64_t stream, void* s);

@@ -138,3 +138,129 @@ def test_cfg3_cfg5_sngp_full_size(cuda):
     var, _ = ops.predictive_variance(phi, sigma, 1e-3)
     torch.cuda.synchronize()
     assert rel_err(to_np(var)[rows], og.predictive_variance(pr, to_np(sigma), 1e-3)) < 2e-2
+
+
+def _bf(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float32).to(torch.bfloat16).double().numpy()
+
+
+@pytest.mark.parametrize("flipout", [False, True])
+def test_cfg2_layer_full_size_forward_and_backward(cuda, flipout):
+    """cfg2 layer 4096 -> 4096 at batch 4096, bf16, in-kernel Philox — forward AND backward against the oracle on
+    sampled rows / columns (the oracle is evaluated with the kernel's own ReLU pattern and bf16-rounded operands):
+    y[rows], dx[rows], dmu[rows_in, :], drho[rows_in, :], dbias."""
+    import edward2_b200 as ed
+    from edward2_b200.layers import dense as ld
+    from oracle import philox as op
+
+    B, I, O = 4096, 4096, 4096
+    cls = ed.layers.DenseFlipout if flipout else ed.layers.DenseReparameterization
+    layer = cls(O, activation="relu", dtype="bfloat16", seed=404, kernel_regularizer=None,
+                kernel_initializer=ed.initializers.TrainableNormal(
+                    mean_initializer=ed.initializers.RandomNormal(stddev=1.0 / 64, seed=1),
+                    stddev_initializer=ed.initializers.TruncatedNormal(-4.0, 0.1, seed=2)))
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(B, I, generator=gen, device=cuda).to(torch.bfloat16).requires_grad_(True)
+    gy = torch.randn(B, O, generator=gen, device=cuda).to(torch.bfloat16)
+    with torch.no_grad():
+        layer(x[:8])  # build
+    layer._calls = 0
+    y = layer(x)
+    y.backward(gy)
+    torch.cuda.synchronize()
+    mu, rho = (to_np(t) for t in layer.kernel_initializer.params())
+    key = layer.seed
+    eps = op.normal(key, ld.S_KERNEL, I * O).reshape(I, O)
+    sigma = od.stddev(rho)
+    rows, cin = _rows(B, 48, 7), _rows(I, 48, 8)
+    xs, yk, gyn = to_np(x), to_np(y), to_np(gy)
+    gp = gyn * (yk > 0)                                   # the kernel's own activation pattern
+    bias = to_np(layer.bias)
+    if flipout:
+        s_in = op.sign(key, ld.S_SIGN_IN, B * I).reshape(B, I)
+        s_out = op.sign(key, ld.S_SIGN_OUT, B * O).reshape(B, O)
+        mub, dlt = _bf(mu), _bf(sigma * eps)
+        y_ref = np.maximum(xs[rows] @ mub + ((xs[rows] * s_in[rows]) @ dlt) * s_out[rows] + bias, 0)
+        dx_ref = gp[rows] @ mub.T + ((gp[rows] * s_out[rows]) @ dlt.T) * s_in[rows]
+        dmu_ref = xs[:, cin].T @ gp
+        ddelta = (xs[:, cin] * s_in[:, cin]).T @ (gp * s_out)
+        drho_ref = ddelta * eps[cin] * od.sigmoid(rho[cin])
+    else:
+        w = _bf(mu + sigma * eps)
+        y_ref = np.maximum(xs[rows] @ w + bias, 0)
+        dx_ref = gp[rows] @ w.T
+        dmu_ref = xs[:, cin].T @ gp
+        drho_ref = dmu_ref * eps[cin] * od.sigmoid(rho[cin])
+    gmu, grho = layer.kernel_initializer.params()[0].grad, layer.kernel_initializer.params()[1].grad
+    assert rel_err(yk[rows], y_ref) < 2e-2
+    assert rel_err(to_np(x.grad)[rows], dx_ref) < 2e-2
+    assert rel_err(to_np(gmu)[cin], dmu_ref) < 2e-2
+    assert rel_err(to_np(grho)[cin], drho_ref) < 2e-2
+    assert rel_err(to_np(layer.bias.grad), gp.sum(0)) < 2e-2
+
+
+def test_cfg4_rank1_chain_full_size_forward_and_backward(cuda):
+    """cfg4 layers 2 and 3 (8192 -> 8192 relu -> 1000) at the per-GPU batch 2048, E = 4, bf16, in-kernel Philox with
+    the fused epilogues (feeds hint): forward and backward against the oracle on sampled rows / columns."""
+    import edward2_b200 as ed
+    from edward2_b200.layers import dense as ld
+    from oracle import philox as op
+
+    E, B, I, H, O = 4, 2048, 8192, 8192, 1000
+    n = B // E
+    mk = lambda u, act, s: ed.layers.DenseRank1(  # noqa: E731
+        u, activation=act, ensemble_size=E, dtype="bfloat16", seed=500 + s,
+        kernel_initializer=ed.initializers.RandomNormal(stddev=1.0 / 90, seed=s),
+        alpha_initializer=ed.initializers.TrainableNormal(mean_initializer=ed.initializers.RandomSign(seed=10 + s),
+                                                          stddev_initializer=ed.initializers.Constant(-2.5)),
+        gamma_initializer=ed.initializers.TrainableNormal(mean_initializer=ed.initializers.RandomSign(seed=20 + s),
+                                                          stddev_initializer=ed.initializers.Constant(-2.5)))
+    l2, l3 = mk(H, "relu", 1), mk(O, None, 2)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(B, I, generator=gen, device=cuda).abs().to(torch.bfloat16).requires_grad_(True)
+    gy = torch.randn(B, O, generator=gen, device=cuda).to(torch.bfloat16)
+    with torch.no_grad():
+        l3(l2(x[:E * 8]))
+    l2.feeds(l3)
+    l2._calls = l3._calls = 0
+    h = l2(x)
+    h.retain_grad()
+    y = l3(h)
+    y.backward(gy)
+    torch.cuda.synchronize()
+    assert h._ed2_rank1_link.fused
+    rows = _rows(B, 24, 11)
+    for layer, inp, out, gin, nin, nout, act in ((l3, h, y, gy, H, O, None), (l2, x, h, h.grad, I, H, "relu")):
+        key = layer.seed
+        cin = _rows(nin, 24, 12)
+        eps_r = op.normal(key, ld.S_R, B * nin).reshape(B, nin)
+        eps_s = op.normal(key, ld.S_S, B * nout).reshape(B, nout)
+        mu_r, rho_r = (to_np(t) for t in layer.alpha_initializer.params())
+        mu_s, rho_s = (to_np(t) for t in layer.gamma_initializer.params())
+        wb = to_np(layer.kernel.detach().to(torch.bfloat16))
+        member = np.arange(B) // n
+        r = np.clip(mu_r[member] + od.stddev(rho_r)[member] * eps_r, -10, 10)
+        s = np.clip(mu_s[member] + od.stddev(rho_s)[member] * eps_s, -10, 10)
+        xin, yk, g = to_np(inp), to_np(out), to_np(gin)
+        xr = _bf(xin * r)
+        bias = to_np(layer.ensemble_bias)[member]
+        pre = (xr[rows] @ wb) * s[rows] + bias[rows]
+        assert rel_err(yk[rows], np.maximum(pre, 0) if act else pre) < 2e-2
+        gp = g * (yk > 0) if act else g
+        dz = _bf(gp * s)
+        assert rel_err(to_np(layer.kernel.grad)[cin], xr[:, cin].T @ dz) < 2e-2
+        dxr = dz[rows] @ wb.T
+        assert rel_err(to_np(inp.grad)[rows], dxr * r[rows]) < 2e-2
+        # fast-weight gradients on the sampled input columns: needs dxr for ALL rows on those columns
+        dxr_c = dz @ wb[cin].T
+        dr = dxr_c * xin[:, cin]
+        dmu_r = dr.reshape(E, n, -1).sum(1)
+        drho_r = (dr * eps_r[:, cin]).reshape(E, n, -1).sum(1) * od.sigmoid(rho_r[:, cin])
+        assert rel_err(to_np(layer.alpha_initializer.params()[0].grad)[:, cin], dmu_r) < 2e-2
+        assert rel_err(to_np(layer.alpha_initializer.params()[1].grad)[:, cin], drho_r) < 2e-2
+        z = xr @ wb[:, :256]                                   # output side on the first 256 output columns
+        ds = gp[:, :256] * _bf(z)
+        assert rel_err(to_np(layer.gamma_initializer.params()[0].grad)[:, :256], ds.reshape(E, n, -1).sum(1)) < 2e-2
+        assert rel_err(to_np(layer.gamma_initializer.params()[1].grad)[:, :256],
+                       (ds * eps_s[:, :256]).reshape(E, n, -1).sum(1) * od.sigmoid(rho_s[:, :256])) < 2e-2
+        assert rel_err(to_np(layer.ensemble_bias.grad), gp.reshape(E, n, -1).sum(1)) < 2e-2
