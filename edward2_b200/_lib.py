@@ -44,6 +44,7 @@ class GemmDesc(C.Structure):
         ("mask_src", _vp), ("mask_ld", _i), ("mask_dtype", _i),
         ("col_sum", _vp), ("col_sum_ld", _i),
         ("block_n", _i), ("cta_group", _i), ("max_ctas", _i), ("no_tma_store", _i),
+        ("accumulate", _i), ("lower_only", _i),
     ]
 
 

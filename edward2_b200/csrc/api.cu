@@ -161,6 +161,12 @@ int ed2_gemm(const ed2_gemm_desc* d, void* stream) {
   e.mask_src = d->mask_src; e.mask_ld = d->mask_ld; e.mask_dt = d->mask_dtype;
   e.col_sum = d->col_sum; e.col_sum_ld = d->col_sum_ld;
   g.block_n = d->block_n; g.cta_group = d->cta_group; g.max_ctas = d->max_ctas; g.no_tma_store = d->no_tma_store;
+  g.ep.lower_only = d->lower_only;
+  if (d->accumulate) {
+    if (d->dtype != kBF16 || d->out_dtype != kF32) return set_error(ED2_ERR_BAD_ARG, "gemm: accumulate needs ED2_BF16 operands and an fp32 out");
+    g.ep.alpha = d->alpha;
+    return gemm_bf16_accumulate(g, S(stream));
+  }
   return gemm(d->dtype, g, S(stream));
 }
 
@@ -658,6 +664,27 @@ int ed2_laplace_precision_update(int dtype, const void* phi, int phi_ld, int bat
   g.B = phi; g.ldb = phi_ld; g.major_b = kMajorMN;
   g.M = num_features; g.N = num_features; g.K = batch;
   g.ep = epi_default();
+  cudaStream_t s = S(stream);
+  // PhiT Phi is symmetric: only the tiles on or below the diagonal are computed (SYRK), the strict upper triangle is
+  // mirrored afterwards; with few output tiles and a long K (D = 1024: 10 tiles for 74 SM pairs) the K loop is split and
+  // the slices accumulate with fp32 atomics
+  const bool bf16_path = dtype == kBF16;
+  g.ep.lower_only = bf16_path ? 1 : 0;
+  g.ep.split_k = bf16_path ? -1 : 0;
+  float* target = partial_out != nullptr ? partial_out : precision;
+  const long long nn = static_cast<long long>(num_features) * num_features;
+  const float a = (partial_out == nullptr && momentum > 0.f) ? (1.f - momentum) / static_cast<float>(batch_total) : 1.f;
+  if (bf16_path) {
+    // accumulate form for every case: target <- base, then += a * PhiT Phi by the GEMM
+    if (partial_out != nullptr) cudaMemsetAsync(partial_out, 0, sizeof(float) * nn, s);
+    else if (momentum > 0.f) ED2_TRY(k_scale_inplace(precision, nn, momentum, s));
+    g.ep.alpha = a;
+    g.ep.out = target; g.ep.out_ld = num_features; g.ep.out_dt = kF32;
+    // split_k == 1 after the automatic choice: plain store epilogue needs the addend form instead of atomics
+    g.ep.split_k = -1;
+    ED2_TRY(gemm_bf16_accumulate(g, s));
+    return k_mirror_lower(target, num_features, s);
+  }
   if (partial_out != nullptr) {
     g.ep.out = partial_out; g.ep.out_ld = num_features; g.ep.out_dt = kF32;
   } else {
@@ -669,7 +696,7 @@ int ed2_laplace_precision_update(int dtype, const void* phi, int phi_ld, int bat
     }
     g.ep.out = precision; g.ep.out_ld = num_features; g.ep.out_dt = kF32;
   }
-  return gemm(dtype, g, S(stream));
+  return gemm(dtype, g, s);
 }
 
 int ed2_precision_blend(float* precision, const float* summed, int num_features, float momentum, long long batch_total,

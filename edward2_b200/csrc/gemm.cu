@@ -82,7 +82,8 @@ int launch_one(const GemmDesc& g, const CUtensorMap& ta, const CUtensorMap& tb, 
     attr_set = true;
   }
   const int tile_m = tc::kBlockM * CG;
-  const int num_tiles = ((g.M + tile_m - 1) / tile_m) * ((g.N + BN - 1) / BN);
+  const int nm = (g.M + tile_m - 1) / tile_m;
+  const int num_tiles = (g.ep.lower_only ? nm * (nm + 1) / 2 : nm * ((g.N + BN - 1) / BN)) * std::max(1, g.ep.split_k);
   int clusters = num_sms() / CG;
   if (g.max_ctas > 0) clusters = std::min(clusters, std::max(1, g.max_ctas / CG));
   clusters = std::min(clusters, num_tiles);
@@ -133,6 +134,13 @@ bool gemm_rank1_fusable(int M, int N, int group_rows) {
   return M > 128 && N % 8 == 0 && (group_rows == 0 || group_rows % 128 == 0);
 }
 
+int gemm_bf16_accumulate(const GemmDesc& g_in, cudaStream_t stream) {
+  GemmDesc g = g_in;
+  g.ep.split_k = -1;
+  g.accumulate = 1;
+  return gemm_bf16(g, stream);
+}
+
 int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
   GemmDesc g = g_in;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(ED2_ERR_BAD_SHAPE, "gemm: empty shape %d %d %d", g.M, g.N, g.K);
@@ -148,6 +156,23 @@ int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
                        g.N, g.ep.group_rows);
     bn = 256; cg = 2;
   }
+  if (g.ep.lower_only) {
+    if (g.M != g.N || g.epi_mode != kEpiGeneric) return set_error(ED2_ERR_BAD_ARG, "gemm: lower_only needs a square generic product");
+    if (!(cg == 2 && bn == 256) && !(cg == 1 && bn == 128)) { cg = g.M > 128 ? 2 : 1; bn = cg == 2 ? 256 : 128; }
+  }
+  if (g.ep.split_k < 0) {  // auto: enough K slices to give every SM pair a work unit, each at least 8 k-blocks long
+    const int tile_m = tc::kBlockM * cg;
+    const int nm = (g.M + tile_m - 1) / tile_m, nn = (g.N + bn - 1) / bn;
+    const int tiles = g.ep.lower_only ? nm * (nm + 1) / 2 : nm * nn;
+    const int units = num_sms() / cg;
+    const int num_kb = (g.K + tc::kBlockK - 1) / tc::kBlockK;
+    int sk = 1;
+    if (tiles * 2 <= units) sk = std::max(1, std::min(units / tiles, num_kb / 8));
+    g.ep.split_k = sk;
+  }
+  if (g.accumulate && g.ep.split_k <= 1) {  // out += alpha * AB without K slices: read-modify-write in the epilogue
+    g.ep.addend = g.ep.out; g.ep.addend_ld = g.ep.out_ld; g.ep.addend_dt = g.ep.out_dt; g.ep.beta = 1.f;
+  }
   const int load_n = bn / cg;
 
   CUtensorMap ta, tb, to;
@@ -161,6 +186,13 @@ int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
 
   const int oes = g.ep.out_dt == kBF16 ? 2 : 4;
   g.ep.out_tma = 0;
+  if (g.ep.split_k > 1) {
+    const int num_kb = (g.K + tc::kBlockK - 1) / tc::kBlockK;
+    g.ep.split_k = std::min(g.ep.split_k, num_kb);
+    if (g.ep.out == nullptr || g.ep.out_dt != kF32 || g.epi_mode != kEpiGeneric)
+      return set_error(ED2_ERR_BAD_ARG, "gemm: split_k accumulates into an fp32 out");
+    g.no_tma_store = 1;
+  }
   if (g.ep.out == nullptr && g.ep.row_sum == nullptr && g.epi_mode != kEpiRank1Bwd)
     return set_error(ED2_ERR_BAD_ARG, "gemm: out is null");
   if (g.ep.out != nullptr && !g.no_tma_store && tma_ok(g.ep.out, g.ep.out_ld, oes)) {

@@ -18,6 +18,7 @@ struct GemmDesc {
   int cta_group;     // 0 = auto, else 1 | 2
   int max_ctas;      // 0 = all SMs
   int no_tma_store;  // force the direct-store epilogue (testing)
+  int accumulate = 0;               // out (fp32, pre-initialised) += alpha * A B   (see gemm_bf16_accumulate)
   int epi_mode = kEpiGeneric;       // kEpiRank1Fwd / kEpiRank1Bwd: fused rank-1 epilogue described by *r1
   const Rank1Epi* r1 = nullptr;
 };
@@ -26,6 +27,9 @@ struct GemmDesc {
 bool gemm_rank1_fusable(int M, int N, int group_rows);
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);  // tcgen05 tensor cores
+// out += alpha * A B into a pre-initialised fp32 `out`: K slices with atomics when the product has few output tiles and
+// a long K, otherwise one read-modify-write epilogue (ep.lower_only honoured)
+int gemm_bf16_accumulate(const GemmDesc& g, cudaStream_t stream);
 int gemm_f32(const GemmDesc& g, cudaStream_t stream);   // fp32 FFMA path
 int gemm(int dtype, const GemmDesc& g, cudaStream_t stream);
 

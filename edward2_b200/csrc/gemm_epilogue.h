@@ -48,6 +48,13 @@ struct EpiParams {
   int mask_dt;
   float* col_sum;
   int col_sum_ld;
+  // ---- work decomposition (generic epilogue only)
+  int split_k;     // > 1: the K loop of every tile is cut into split_k slices, each a separate work unit whose epilogue
+                   //      ADDS alpha * partial into fp32 `out` with atomics (out pre-initialised by the caller; no other
+                   //      epilogue term, no TMA store).  For products with few output tiles and a long K (PhiT Phi at
+                   //      D = 1024, the weight gradients of narrow layers).
+  int lower_only;  // 1: square output, only tiles on or below the diagonal are computed (SYRK: PhiT Phi is symmetric;
+                   //      the caller mirrors the strict lower triangle afterwards)
 };
 
 // ---- fused rank-1 epilogues (DenseRank1, edward2/tensorflow/layers/dense.py:1096-1144) -------------------------------

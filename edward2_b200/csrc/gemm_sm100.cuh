@@ -141,6 +141,17 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n) {
 namespace ed2 {
 namespace tc {
 
+// t-th tile of the lower triangle (diagonal included) of a square nt x nt tile grid, row by row
+__device__ __forceinline__ TileCoord tri_coord(int t) {
+  int m = static_cast<int>((sqrtf(8.f * static_cast<float>(t) + 1.f) - 1.f) * 0.5f);
+  while ((m + 1) * (m + 2) / 2 <= t) ++m;
+  while (m * (m + 1) / 2 > t) --m;
+  TileCoord c;
+  c.m_blk = m;
+  c.n_blk = t - m * (m + 1) / 2;
+  return c;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -304,20 +315,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   const int num_m = (M + kTileM - 1) / kTileM;
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m * num_n;
   const int num_kb = (K + kBlockK - 1) / kBlockK;
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
+  // work units: (tile, K slice).  lower_only enumerates the lower triangle; split_k cuts the K loop (host guarantees
+  // split_k <= num_kb, so no slice is empty)
+  const bool tri = ep.lower_only != 0;
+  const int tiles_mn = tri ? num_m * (num_m + 1) / 2 : num_m * num_n;
+  const int split_k = ep.split_k > 1 ? ep.split_k : 1;
+  const int kb_per = (num_kb + split_k - 1) / split_k;
+  const int num_tiles = tiles_mn * split_k;
+  auto unit_tile = [&](int u) -> TileCoord { const int tt = u % tiles_mn; return tri ? tri_coord(tt) : tile_coord(tt, num_m, num_n); };
+  auto unit_kb0 = [&](int u) -> int { return (u / tiles_mn) * kb_per; };
+  auto unit_kb1 = [&](int u) -> int { return min(num_kb, (u / tiles_mn) * kb_per + kb_per); };
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const TileCoord tc = tile_coord(t, num_m, num_n);
+        const TileCoord tc = unit_tile(t);
         const int m0 = tc.m_blk * kTileM + cta_rank * kBlockM;
         const int n0 = tc.n_blk * BLOCK_N + cta_rank * Cfg::kLoadN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = unit_kb0(t), kb_end = unit_kb1(t); kb < kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           const int k0 = kb * kBlockK;
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
@@ -357,7 +377,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_first = unit_kb0(t), kb_end = unit_kb1(t);
+        for (int kb = kb_first; kb < kb_end; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint64_t da = operand_desc<kMajorA>(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
@@ -365,10 +386,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             ptx::umma<kCtaGroup, false>(tmem_d, da + k * desc_k_step<kMajorA>(), db + k * desc_k_step<kMajorB>(),
-                                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                                        idesc, (kb > kb_first || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit<kCtaGroup>(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit<kCtaGroup>(&tmem_full_bar[acc]);
+          if (kb == kb_end - 1) ptx::umma_commit<kCtaGroup>(&tmem_full_bar[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -386,7 +407,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint32_t store_buf = 0;
     int iter = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
-      const TileCoord tc = tile_coord(t, num_m, num_n);
+      const TileCoord tc = unit_tile(t);
       const int m0 = tc.m_blk * kTileM + cta_rank * kBlockM;
       const int n0 = tc.n_blk * BLOCK_N;
       const int m = m0 + row;
@@ -429,6 +450,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]) * ep.alpha;
 
+        if (split_k > 1) {  // K-slice partial: out += alpha * partial (fp32 atomics), nothing else
+          if (active) {
+            float* o = reinterpret_cast<float*>(ep.out) + static_cast<long long>(m) * ep.out_ld + nc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < n_valid) atomicAdd(o + j, v[j]);
+          }
+          continue;
+        }
         if (ep.raw != nullptr && active)
           store_row32(ep.raw, ep.raw_dt, static_cast<long long>(m) * ep.raw_ld, nc, n_valid, v);
 

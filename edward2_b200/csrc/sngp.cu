@@ -344,6 +344,30 @@ int k_layernorm_bwd(const void* x, int xdt, long long x_ld, const void* dy, int 
   return check_launch("layernorm_bwd");
 }
 
+// P[i][j] = P[j][i] for i < j: completes a matrix whose lower triangle was computed (SYRK); 32 x 32 tiles via smem
+__global__ void mirror_lower_kernel(float* __restrict__ p, int n) {
+  __shared__ float tile[32][33];
+  const int bj = blockIdx.x, bi = blockIdx.y;  // source tile (rows bi*32.., cols bj*32..), only bj <= bi
+  if (bj > bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    tile[r][tx] = (i < n && j < n) ? p[(long long)i * n + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj * 32 + r, j = bi * 32 + tx;  // destination: transposed position
+    if (i < n && j < n && i < j) p[(long long)i * n + j] = tile[tx][r];
+  }
+}
+
+int k_mirror_lower(float* p, int n, cudaStream_t s) {
+  const int nb = (n + 31) / 32;
+  mirror_lower_kernel<<<dim3(nb, nb), kBlock, 0, s>>>(p, n);
+  count_launch();
+  return check_launch("mirror_lower");
+}
+
 int k_precision_blend(float* precision, const float* summed, long long n, float momentum, long long batch_total,
                       cudaStream_t s) {
   precision_blend_kernel<<<grid_for(n), kBlock, 0, s>>>(precision, summed, n, momentum, 1.f / (float)batch_total);

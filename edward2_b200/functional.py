@@ -652,8 +652,13 @@ class Dense(torch.autograd.Function):
         gp = _new(B, O, dtype, dev)
         dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
         ops.act_bwd(gyc, y, gp, dbias, act)
-        dw = torch.empty(I, O, dtype=torch.float32, device=dev)
-        ops.gemm(xc, gp, I, O, B, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=dw)
+        if dtype == torch.bfloat16 and I * O <= (1 << 20) and B >= 2048:
+            # narrow layer, long batch: few output tiles — K slices accumulate into a zeroed dW (ed2_gemm accumulate)
+            dw = torch.zeros(I, O, dtype=torch.float32, device=dev)
+            ops.gemm(xc, gp, I, O, B, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=dw, accumulate=True)
+        else:
+            dw = torch.empty(I, O, dtype=torch.float32, device=dev)
+            ops.gemm(xc, gp, I, O, B, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=dw)
         if has_scale:
             dw = dw * w_scale
         dx = None

@@ -25,7 +25,8 @@ def act_id(activation) -> int:
 def gemm(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int, *, major_a=MAJOR_K, major_b=MAJOR_MN,
          out: torch.Tensor | None = None, out_dtype: torch.dtype | None = None, alpha=1.0, beta=1.0, act=ACT_NONE,
          act_scale=1.0, group_rows=0, elem_scale=None, col_scale=None, addend=None, col_bias=None, raw=None,
-         row_sum=None, want_out=True, block_n=0, cta_group=0, max_ctas=0, no_tma_store=0) -> torch.Tensor | None:
+         row_sum=None, want_out=True, block_n=0, cta_group=0, max_ctas=0, no_tma_store=0, accumulate=False,
+         lower_only=False) -> torch.Tensor | None:
     """out = act(((alpha*A·B) ∘ elem_scale ∘ col_scale[g]) + beta*addend + col_bias[g]); see ed2b200.h."""
     lib = _lib.load()
     d = _lib.GemmDesc()
@@ -55,6 +56,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int, *, major_a=MA
         assert row_sum.dtype == torch.float32
         d.row_sum = row_sum.data_ptr()
     d.block_n, d.cta_group, d.max_ctas, d.no_tma_store = block_n, cta_group, max_ctas, no_tma_store
+    d.accumulate, d.lower_only = int(accumulate), int(lower_only)
     _lib.check(lib.ed2_gemm(C.byref(d), _lib.stream_ptr()), "ed2_gemm")
     return out
 

@@ -97,6 +97,9 @@ typedef struct {
   float* col_sum; int col_sum_ld;                     /* col_sum[g(m), n] += sum_m out[m,n] (fp32 atomics) */
   /* tuning / test knobs, 0 = automatic */
   int block_n, cta_group, max_ctas, no_tma_store;
+  int accumulate;  /* 1 (ED2_BF16, fp32 out): out += alpha * A B into a PRE-INITIALISED out; products with few output tiles
+                      and a long K are cut into K slices that accumulate with fp32 atomics so that every SM has work */
+  int lower_only;  /* 1: square product, only the tiles on or below the diagonal are computed (symmetric results) */
 } ed2_gemm_desc;
 
 int ed2_gemm(const ed2_gemm_desc* desc, void* stream);

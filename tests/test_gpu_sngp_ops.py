@@ -188,3 +188,41 @@ def test_rff_split_bf16_phase_precision(cuda, nsplit, tol):
                               torch.float32, False)
     torch.cuda.synchronize()
     assert rel_err(to_np(phi_bf16), phi_ref) > 1e-2
+
+
+@pytest.mark.parametrize("shape", [(8192, 1024), (4096, 520), (2048, 2048)])
+@pytest.mark.parametrize("momentum", [0.999, -1.0])
+def test_precision_update_syrk_split_k(cuda, shape, momentum):
+    """The bf16 precision update computes only the lower triangle (SYRK) — in K slices with fp32 atomics when the
+    output has few tiles — and mirrors it: result equals the oracle update, exactly symmetric, over repeated steps."""
+    from edward2_b200 import ops
+
+    B, D = shape
+    rng = np.random.default_rng(5)
+    P = torch.tensor(rng.standard_normal((D, D)), dtype=torch.float32, device=cuda)
+    P = (P + P.t()).contiguous()
+    ref = to_np(P)
+    for step in range(2):
+        phi = torch.tensor(rng.standard_normal((B, D)) * 0.05, dtype=torch.float32, device=cuda).to(torch.bfloat16)
+        ops.laplace_precision_update(phi, P, momentum, batch_total=B)
+        pn = to_np(phi)
+        ref = (momentum * ref + (1 - momentum) * (pn.T @ pn) / B) if momentum > 0 else ref + pn.T @ pn
+    torch.cuda.synchronize()
+    assert rel_err(to_np(P), ref) < 1e-4
+    assert torch.equal(P, P.t())
+
+
+def test_gemm_accumulate_split_k(cuda):
+    """ed2_gemm accumulate: out += alpha * A^T B on a narrow output with a long K (split-K atomics) and on a wide one
+    (read-modify-write epilogue)."""
+    from edward2_b200 import ops
+
+    rng = np.random.default_rng(6)
+    for (K, M, N) in ((8192, 512, 512), (4096, 264, 136), (512, 2048, 2048)):
+        a = torch.tensor(rng.standard_normal((K, M)), dtype=torch.float32, device=cuda).to(torch.bfloat16)
+        b = torch.tensor(rng.standard_normal((K, N)), dtype=torch.float32, device=cuda).to(torch.bfloat16)
+        out = torch.tensor(rng.standard_normal((M, N)), dtype=torch.float32, device=cuda)
+        want = to_np(out) + 0.5 * to_np(a).T @ to_np(b)
+        ops.gemm(a, b, M, N, K, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=out, alpha=0.5, accumulate=True)
+        torch.cuda.synchronize()
+        assert rel_err(to_np(out), want) < 1e-5, (K, M, N)
