@@ -298,8 +298,7 @@ def wl_sngp(kind, train):
                     h = x
                     for l in backbone:
                         h = l(h, training=False)
-                    gp_in = gp._input_norm_layer(h)
-                    phi = gp._random_feature(gp_in)
+                    phi = gp.features(h)
                     logits = gp._gp_output_layer(phi).float() + gp._gp_output_bias
                     var, adj = cov.compute_predictive_variance(phi, logits, mean_field_factor=3.141592653589793 / 8.0)
                 return adj.sum()
@@ -309,7 +308,8 @@ def wl_sngp(kind, train):
         if train:
             # fwd + dW + dX of the backbone (dX for layer 2 only), RFF fwd + dX, output layer fwd+dW+dX, full ΦᵀΦ
             n_dx = max(0, len(widths) - 1)
-            flops = bb * 2 + (bb / max(1, len(widths))) * n_dx + rff * (2 if widths else 1) + out * 3 + pp
+            # (the RFF dX product runs in both configs: LayerNormalization's gamma / beta are trainable, TF semantics)
+            flops = bb * 2 + (bb / max(1, len(widths))) * n_dx + rff * 2 + out * 3 + pp
         else:
             flops = bb + rff + out + pp
 

@@ -207,8 +207,9 @@ SIGNATURES = {
     "ed2_spectral_norm_update": (_i, [_vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "ed2_input_normalize": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _vp, _f, _i, _f, _vp]),
     "ed2_layernorm_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _f, _vp, _i, _i, _vp, _vp, _vp]),
-    "ed2_rff_fwd": (_i, [_i, _vp, _i, _vp, _i, _vp, _f, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
-    "ed2_rff_bwd": (_i, [_i, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _f, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "ed2_rff_fwd": (_i, [_i, _vp, _i, _vp, _i, _vp, _f, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "ed2_rff_bwd": (_i, [_i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "ed2_layernorm_split": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _vp, _vp, _f, _vp]),
     "ed2_laplace_precision_update": (_i, [_i, _vp, _i, _i, _i, _f, _ll, _vp, _vp, _vp]),
     "ed2_precision_blend": (_i, [_vp, _vp, _i, _f, _ll, _vp]),
     "ed2_predictive_variance": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _i, _f, _i, _vp, _vp]),

@@ -641,8 +641,15 @@ int ed2_layernorm_bwd(const void* x, int x_dtype, int x_ld, const void* dy, int 
                          dbeta, S(stream));
 }
 
+int ed2_layernorm_split(const void* x, int x_dtype, int x_ld, void* out, int out_ld, long long rows, int cols,
+                        const float* gamma, const float* beta, float eps, void* stream) {
+  ED2_TRY(check_dt(x_dtype));
+  return k_layernorm_split(x, x_dtype, x_ld, out, out_ld, rows, cols, gamma, beta, eps, S(stream));
+}
+
 int ed2_rff_fwd(int dtype, const void* x, int x_ld, const void* wt, int wt_ld, const float* bias, float scale, int batch,
-                int in_dim, int num_features, void* phi, int phi_ld, int phi_dtype, float* pre, int pre_ld, void* stream) {
+                int in_dim, int num_features, void* phi, int phi_ld, int phi_dtype, void* pre, int pre_ld, int pre_mode,
+                void* stream) {
   ED2_TRY(check_dt(dtype));
   GemmDesc g{};
   g.A = x; g.lda = x_ld; g.major_a = kMajorK;
@@ -652,7 +659,10 @@ int ed2_rff_fwd(int dtype, const void* x, int x_ld, const void* wt, int wt_ld, c
   g.ep.col_bias = bias; g.ep.col_bias_ld = num_features;
   g.ep.act = kActCos; g.ep.act_scale = scale;
   g.ep.out = phi; g.ep.out_ld = phi_ld; g.ep.out_dt = phi_dtype;
-  g.ep.raw = pre; g.ep.raw_ld = pre_ld; g.ep.raw_dt = kF32;
+  // pre_mode 0: the fp32 phase x W (bias not included);  1: -scale * sin(x W + b) in bf16, the derivative factor
+  g.ep.raw = pre; g.ep.raw_ld = pre_ld; g.ep.raw_dt = pre_mode == 1 ? kBF16 : kF32;
+  g.ep.raw_neg_sin = pre_mode == 1 ? 1 : 0;
+  if (pre_mode == 1 && dtype != kBF16) return set_error(ED2_ERR_BAD_ARG, "rff_fwd: pre_mode 1 needs the ED2_BF16 GEMM");
   return gemm(dtype, g, S(stream));
 }
 
@@ -729,12 +739,18 @@ int ed2_mean_field_logits(const float* logits, const float* var, int batch, int 
   return k_mean_field(logits, var, batch, num_classes, mean_field_factor, likelihood, 1.f, out, S(stream));
 }
 
-int ed2_rff_bwd(int dtype, const void* dphi, int dphi_ld, int dphi_dtype, const float* pre, int pre_ld,
+int ed2_rff_bwd(int dtype, const void* dphi, int dphi_ld, int dphi_dtype, const void* pre, int pre_ld, int pre_mode,
                 const float* bias, const void* w, int w_ld, float scale, int batch, int in_dim, int num_features,
                 void* gpre, int gpre_ld, void* dx, int dx_ld, int dx_dtype, void* stream) {
   ED2_TRY(check_dt(dtype));
   cudaStream_t s = S(stream);
-  ED2_TRY(k_rff_bwd_prep(dphi, dphi_dtype, dphi_ld, pre, pre_ld, bias, scale, batch, num_features, gpre, dtype, gpre_ld, s));
+  if (pre_mode == 1) {
+    if (dtype != kBF16 || dphi_dtype != kBF16) return set_error(ED2_ERR_BAD_ARG, "rff_bwd: pre_mode 1 is the ED2_BF16 path");
+    ED2_TRY(k_mul_bf16(dphi, dphi_ld, pre, pre_ld, gpre, gpre_ld, batch, num_features, s));
+  } else {
+    ED2_TRY(k_rff_bwd_prep(dphi, dphi_dtype, dphi_ld, reinterpret_cast<const float*>(pre), pre_ld, bias, scale, batch,
+                           num_features, gpre, dtype, gpre_ld, s));
+  }
   EpiParams e = epi_default();
   e.out = dx; e.out_ld = dx_ld; e.out_dt = dx_dtype;
   return gemm_gwt(dtype, gpre, gpre_ld, w, w_ld, batch, in_dim, num_features, e, s);

@@ -42,6 +42,8 @@ struct EpiParams {
   void* raw;
   int raw_ld;
   int raw_dt;
+  int raw_neg_sin;  // with act == kActCos: raw receives -sin(v) * act_scale (the derivative factor of the random-feature
+                    // map, written next to phi) instead of the pre-activation
   float* row_sum;
   const void* mask_src;
   int mask_ld;

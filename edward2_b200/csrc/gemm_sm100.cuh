@@ -459,7 +459,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           continue;
         }
-        if (ep.raw != nullptr && active)
+        if (ep.raw != nullptr && active && !ep.raw_neg_sin)
           store_row32(ep.raw, ep.raw_dt, static_cast<long long>(m) * ep.raw_ld, nc, n_valid, v);
 
         if (active) {
@@ -488,6 +488,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (ep.act == kActRelu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (ep.act == kActCos && ep.raw_neg_sin && ep.raw != nullptr) {
+            // phi = cos(v) * scale -> out,  -sin(v) * scale -> raw: one range reduction for both (sincosf), the raw tile
+            // is stored in 8-column pieces so that only 8 extra registers are live
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              float sn[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float sv, cv;
+                sincosf(v[8 * j8 + j], &sv, &cv);
+                v[8 * j8 + j] = cv * ep.act_scale;
+                sn[j] = -sv * ep.act_scale;
+              }
+              const int nv = n_valid - 8 * j8;
+              if (nv > 0) {
+                if (ep.raw_dt == kBF16) {
+                  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.raw) + static_cast<long long>(m) * ep.raw_ld + nc + 8 * j8;
+                  if (nv >= 8 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(sn[0], sn[1]), pack_bf16(sn[2], sn[3]), pack_bf16(sn[4], sn[5]), pack_bf16(sn[6], sn[7]));
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                      if (j < nv) p[j] = __float2bfloat16_rn(sn[j]);
+                  }
+                } else {
+                  float* p = reinterpret_cast<float*>(ep.raw) + static_cast<long long>(m) * ep.raw_ld + nc + 8 * j8;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (j < nv) p[j] = sn[j];
+                }
+              }
+            }
           } else if (ep.act == kActCos) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = cosf(v[j]) * ep.act_scale;

@@ -53,6 +53,10 @@ int k_scale_rows(const void* x, int dt, long long x_ld, long long rows, int cols
 
 // sg = softplus(rho) + 1e-7, sgm = sigmoid(rho): the per-(member, column) tables the fused rank-1 GEMM epilogues read
 // (rho may be null: tables not needed); z0..z2: optional [n] fp32 accumulators zeroed by the same launch
+int k_layernorm_split(const void* x, int xdt, long long x_ld, void* out, long long out_ld, long long rows, int cols,
+                      const float* gamma, const float* beta, float eps, cudaStream_t s);
+int k_mul_bf16(const void* a, long long a_ld, const void* b, long long b_ld, void* out, long long out_ld, long long rows,
+               int cols, cudaStream_t s);
 int k_mirror_lower(float* p, int n, cudaStream_t s);          // P[i][j] = P[j][i], i < j (after a lower-triangle SYRK)
 int k_fast_prep(const float* rho, long long n, float* sg, float* sgm, cudaStream_t s, float* z0 = nullptr,
                 float* z1 = nullptr, float* z2 = nullptr);

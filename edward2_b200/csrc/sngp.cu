@@ -270,6 +270,97 @@ __global__ void rff_bwd_prep_kernel(const void* dphi, int ddt, long long dphi_ld
   }
 }
 
+// LayerNorm forward that writes the bf16 SPLIT A-operand of the fp32-grade random-feature GEMM directly:
+//   y = (x - mean) * rsqrt(var + eps) * gamma + beta;   h = bf16(y), m = bf16(y - h);   out row = [h | h | m]
+// (the 2-term split of ed2_split_bf16, is_b = 0) — one pass over x instead of LayerNorm -> fp32 tensor -> split.
+// One warp per row, 8 columns per lane per trip (cols % 8 == 0), the row is re-read from L1 / L2 for the three passes.
+__device__ __forceinline__ void ld8(const void* p, int dt, long long off, float (&f)[8]) {
+  if (dt == kBF16) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + off));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 v = __bfloat1622float2(h[t]);
+      f[2 * t] = v.x; f[2 * t + 1] = v.y;
+    }
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + off));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + off) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
+  uint4 q;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+  q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+  q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+  return q;
+}
+
+__global__ void __launch_bounds__(kBlock) layernorm_split_kernel(const void* __restrict__ x, int xdt, long long x_ld,
+                                                                 __nv_bfloat16* __restrict__ out, long long out_ld,
+                                                                 long long rows, int cols, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps) {
+  const long long warp = (blockIdx.x * (long long)kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * kBlock) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float s = 0.f;
+    for (int c = lane * 8; c < cols; c += 256) {
+      float f[8];
+      ld8(x, xdt, r * x_ld + c, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[j];
+    }
+    const float mean = warp_sum(s) / cols;
+    float q = 0.f;
+    for (int c = lane * 8; c < cols; c += 256) {
+      float f[8];
+      ld8(x, xdt, r * x_ld + c, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; q += d * d; }
+    }
+    const float inv = rsqrtf(warp_sum(q) / cols + eps);
+    __nv_bfloat16* o = out + r * out_ld;
+    for (int c = lane * 8; c < cols; c += 256) {
+      float f[8], g[8], b[8], hi[8], lo[8];
+      ld8(x, xdt, r * x_ld + c, f);
+      if (gamma != nullptr) ld8(gamma, kF32, c, g);
+      if (beta != nullptr) ld8(beta, kF32, c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = (f[j] - mean) * inv;
+        if (gamma != nullptr) v *= g[j];
+        if (beta != nullptr) v += b[j];
+        hi[j] = __bfloat162float(__float2bfloat16_rn(v));
+        lo[j] = v - hi[j];
+      }
+      const uint4 ph = pack8_bf16(hi), pl = pack8_bf16(lo);
+      *reinterpret_cast<uint4*>(o + c) = ph;
+      *reinterpret_cast<uint4*>(o + cols + c) = ph;
+      *reinterpret_cast<uint4*>(o + 2LL * cols + c) = pl;
+    }
+  }
+}
+
+// out = a ∘ b, bf16, 8 elements per thread-trip (the backward of the random-feature map: dphi ∘ (-sin * scale))
+__global__ void __launch_bounds__(kBlock) mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld,
+                                                          const __nv_bfloat16* __restrict__ b, long long b_ld,
+                                                          __nv_bfloat16* __restrict__ out, long long out_ld, long long rows,
+                                                          int cols) {
+  const long long vpr = cols >> 3, n = rows * vpr;
+  for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    const long long r = i / vpr, c = (i - r * vpr) << 3;
+    float fa[8], fb[8];
+    ld8(a, kBF16, r * a_ld + c, fa);
+    ld8(b, kBF16, r * b_ld + c, fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fa[j] *= fb[j];
+    *reinterpret_cast<uint4*>(out + r * out_ld + c) = pack8_bf16(fa);
+  }
+}
+
 int grid_for(long long n) {
   long long g = (n + kBlock - 1) / kBlock;
   if (g < 1) g = 1;
@@ -325,6 +416,29 @@ int k_input_normalize(const void* x, int xdt, long long x_ld, void* y, int ydt, 
 }
 
 
+int k_layernorm_split(const void* x, int xdt, long long x_ld, void* out, long long out_ld, long long rows, int cols,
+                      const float* gamma, const float* beta, float eps, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  if (cols % 8 != 0 || out_ld % 8 != 0 || x_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return set_error(ED2_ERR_BAD_ARG, "layernorm_split: needs cols %% 8 == 0 and 16-byte aligned rows");
+  const int g = static_cast<int>(std::min<long long>(148 * 8, (rows + 7) / 8));
+  layernorm_split_kernel<<<g, kBlock, 0, s>>>(x, xdt, x_ld, reinterpret_cast<__nv_bfloat16*>(out), out_ld, rows, cols, gamma, beta, eps);
+  count_launch();
+  return check_launch("layernorm_split");
+}
+
+int k_mul_bf16(const void* a, long long a_ld, const void* b, long long b_ld, void* out, long long out_ld, long long rows,
+               int cols, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return ED2_OK;
+  if (cols % 8 != 0 || a_ld % 8 != 0 || b_ld % 8 != 0 || out_ld % 8 != 0)
+    return set_error(ED2_ERR_BAD_ARG, "mul_bf16: needs 8-element aligned rows");
+  mul_bf16_kernel<<<grid_for(rows * (cols / 8)), kBlock, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a), a_ld,
+                                                                  reinterpret_cast<const __nv_bfloat16*>(b), b_ld,
+                                                                  reinterpret_cast<__nv_bfloat16*>(out), out_ld, rows, cols);
+  count_launch();
+  return check_launch("mul_bf16");
+}
+
 int k_layernorm_bwd(const void* x, int xdt, long long x_ld, const void* dy, int dydt, long long dy_ld, long long rows,
                     int cols, const float* gamma, float eps, void* dx, int dxdt, long long dx_ld, float* dgamma,
                     float* dbeta, cudaStream_t s) {
@@ -332,8 +446,10 @@ int k_layernorm_bwd(const void* x, int xdt, long long x_ld, const void* dy, int 
   if (cols > 8192) return set_error(ED2_ERR_BAD_SHAPE, "layernorm_bwd: feature dimension %d > 8192", cols);
   if (dgamma) cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, s);
   if (dbeta) cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, s);
-  const int g = static_cast<int>(std::min<long long>(148 * 2, (rows + 7) / 8));
   const size_t smem = 2 * sizeof(float) * (size_t)cols;
+  // one warp per row and latency-bound: as many blocks per SM as the per-block column accumulators leave room for
+  const int per_sm = static_cast<int>(std::max<size_t>(2, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1024))));
+  const int g = static_cast<int>(std::min<long long>(148LL * per_sm, (rows + 7) / 8));
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 8192);

@@ -727,6 +727,37 @@ class RandomFourierFeatures(torch.autograd.Function):
         return dx, None, None, None, None, None, None, None
 
 
+class NormalizedRFF(torch.autograd.Function):
+    """LayerNormalization + random Fourier features as one unit (random_feature.py:250-266 with normalize_input=True
+    and the 2-term split phase): the LayerNorm pass writes the bf16 split A-operand of the feature GEMM directly, the
+    GEMM epilogue writes phi and -scale*sin(phase); the backward is dphi∘(-scale*sin) -> one GEMM -> LayerNorm backward.
+    No fp32 normalised tensor, no fp32 phase tensor, no separate split / sin passes."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, wt_split, w, bias, scale, phi_dtype):
+        xc = x if (x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.float32, torch.bfloat16) and _aligned(x)) \
+            else ops.cast(x.contiguous().float(), torch.float32)
+        need = any(ctx.needs_input_grad[:3])
+        xs = ops.layernorm_split(xc, gamma, beta, eps)
+        phi, nsin = ops.rff_fwd_split(xs, wt_split, bias, scale, w.shape[1], phi_dtype, need, 2, presplit=True)
+        if need:
+            ctx.save_for_backward(xc, gamma if gamma is not None else torch.empty(0, device=x.device), nsin, bias, w)
+            ctx.meta = (eps, gamma is not None, beta is not None, x.dtype, scale)
+        return phi
+
+    @staticmethod
+    def backward(ctx, dphi):
+        xc, gamma, nsin, bias, w = ctx.saved_tensors
+        eps, has_gamma, has_beta, x_dtype, scale = ctx.meta
+        dphic = dphi if (dphi.stride(1) == 1 and dphi.dtype in (torch.float32, torch.bfloat16)) else dphi.contiguous().float()
+        dxn = ops.rff_bwd(dphic, nsin, bias, w, scale, torch.bfloat16)
+        dx, dgamma, dbeta = ops.layernorm_bwd(xc, dxn, gamma if has_gamma else None, eps,
+                                              want_dx=ctx.needs_input_grad[0], want_params=has_gamma or has_beta)
+        if dx is not None and dx.dtype != x_dtype:
+            dx = dx.to(x_dtype)
+        return dx, (dgamma if has_gamma else None), (dbeta if has_beta else None), None, None, None, None, None, None
+
+
 class _UnitGrad:
     """Cached constant 1.0 used as the root gradient by `backward(loss)`: our loss node recognises it by identity and
     skips the (B x classes) multiply by the upstream scalar."""

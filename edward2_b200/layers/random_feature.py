@@ -348,18 +348,30 @@ class RandomFeatureGaussianProcess(Layer):
     def reset_covariance_matrix(self):
         self._gp_cov_layer.reset_precision_matrix()
 
-    def call(self, inputs, global_step=None, training=None):
-        if training is None:
-            training = self.training  # sub-layers are built lazily: they must follow THIS module's train / eval mode
-        x, lead = flatten_batch(inputs)
+    def features(self, x):
+        """Random features of a 2-D batch: input normalisation / scaling + cos(xW + b) * scale (random_feature.py:250-266)."""
         gp_inputs = x
+        rf = self._random_feature
+        if (self.normalize_input and self._input_norm_layer.built and rf.built and rf._nsplit == 2
+                and x.shape[-1] % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16)):
+            # fused unit: LayerNorm writes the split operand, the GEMM epilogue writes phi and -scale*sin(phase)
+            if rf._key != rf._cache_key():
+                rf._refresh()
+            ln = self._input_norm_layer
+            return F.NormalizedRFF.apply(x, ln.gamma, ln.beta, ln.epsilon, rf._wt, rf._w, rf.bias, rf.scale, rf.compute_dtype)
         if self.normalize_input:
             gp_inputs = self._input_norm_layer(gp_inputs)
         elif self.gp_input_scale is not None:
             gp_inputs = ops.input_normalize(F.as_compute(gp_inputs.detach(), self.compute_dtype), self.compute_dtype,
                                             scale_only=True, scale=self.gp_input_scale) \
                 if not gp_inputs.requires_grad else gp_inputs * self.gp_input_scale
-        gp_feature = self._random_feature(gp_inputs)
+        return self._random_feature(gp_inputs)
+
+    def call(self, inputs, global_step=None, training=None):
+        if training is None:
+            training = self.training  # sub-layers are built lazily: they must follow THIS module's train / eval mode
+        x, lead = flatten_batch(inputs)
+        gp_feature = self.features(x)
         gp_output = self._gp_output_layer(gp_feature).float() + self._gp_output_bias
         model_output = [gp_output.reshape(*lead, self.units)]
         if self.return_gp_cov:

@@ -159,7 +159,7 @@ def rff_fwd(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, scale: float,
     pre = torch.empty(B, D, dtype=torch.float32, device=x.device) if want_pre else None
     _lib.check(lib.ed2_rff_fwd(_lib.dt_of(x), x.data_ptr(), _lib.ld(x), wt.data_ptr(), _lib.ld(wt), bias.data_ptr(),
                                scale, B, d, D, phi.data_ptr(), _lib.ld(phi), _lib.dt_of(phi), _lib.ptr(pre),
-                               0 if pre is None else D, _lib.stream_ptr()), "ed2_rff_fwd")
+                               0 if pre is None else D, 0, _lib.stream_ptr()), "ed2_rff_fwd")
     return phi, pre
 
 
@@ -171,7 +171,10 @@ def rff_bwd(dphi: torch.Tensor, pre: torch.Tensor, bias: torch.Tensor, w: torch.
     d = w.shape[0]
     gpre = _lib.empty_padded(B, D, w.dtype, w.device)
     dx = _lib.empty_padded(B, d, dx_dtype, w.device)
-    _lib.check(lib.ed2_rff_bwd(_lib.dt_of(w), dphi.data_ptr(), _lib.ld(dphi), _lib.dt_of(dphi), pre.data_ptr(), D,
+    mode = 1 if pre.dtype == torch.bfloat16 else 0  # bf16: -scale*sin(xW+b) written by the forward (pre_mode 1)
+    if mode == 1 and dphi.dtype != torch.bfloat16:
+        dphi = cast(dphi, torch.bfloat16)
+    _lib.check(lib.ed2_rff_bwd(_lib.dt_of(w), dphi.data_ptr(), _lib.ld(dphi), _lib.dt_of(dphi), pre.data_ptr(), _lib.ld(pre), mode,
                                bias.data_ptr(), w.data_ptr(), _lib.ld(w), scale, B, d, D, gpre.data_ptr(),
                                _lib.ld(gpre), dx.data_ptr(), _lib.ld(dx), _lib.dt_of(dx), _lib.stream_ptr()),
                "ed2_rff_bwd")
@@ -238,17 +241,28 @@ def split_bf16(src: torch.Tensor, is_b: bool, nsplit: int = 3) -> torch.Tensor:
     return out
 
 
+def layernorm_split(x: torch.Tensor, gamma=None, beta=None, eps=1e-3) -> torch.Tensor:
+    """LayerNorm(x) written directly as the 2-term bf16 split A-operand [rows, 3 * cols] (ed2_layernorm_split)."""
+    lib = _lib.load()
+    rows, cols = x.shape
+    out = torch.empty(rows, 3 * cols, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.ed2_layernorm_split(x.data_ptr(), _lib.dt_of(x), _lib.ld(x), out.data_ptr(), 3 * cols, rows, cols,
+                                       _lib.ptr(gamma), _lib.ptr(beta), eps, _lib.stream_ptr()), "ed2_layernorm_split")
+    return out
+
+
 def rff_fwd_split(x: torch.Tensor, wt_split: torch.Tensor, bias: torch.Tensor, scale: float, num_features: int,
-                  phi_dtype: torch.dtype, want_pre: bool, nsplit: int = 3):
+                  phi_dtype: torch.dtype, want_pre: bool, nsplit: int = 3, presplit: bool = False):
     """phi = scale * cos(x W + b) with an fp32-grade phase on the bf16 tensor cores: x (fp32 or bf16, [B, d]) is split
     on the fly, wt_split = split_bf16(W^T, is_b=True) was made once (W is frozen)."""
     lib = _lib.load()
-    xs = split_bf16(x, False, nsplit)
+    xs = x if presplit else split_bf16(x, False, nsplit)
     B, Kp = xs.shape
     D = num_features
-    phi = _lib.empty_padded(B, D, phi_dtype, x.device)
-    pre = torch.empty(B, D, dtype=torch.float32, device=x.device) if want_pre else None
+    phi = _lib.empty_padded(B, D, phi_dtype, xs.device)
+    # the backward needs only -scale*sin(phase): bf16, written by the same epilogue (ed2_rff_fwd pre_mode 1)
+    pre = _lib.empty_padded(B, D, torch.bfloat16, xs.device) if want_pre else None
     _lib.check(lib.ed2_rff_fwd(BF16, xs.data_ptr(), _lib.ld(xs), wt_split.data_ptr(), _lib.ld(wt_split), bias.data_ptr(),
                                scale, B, Kp, D, phi.data_ptr(), _lib.ld(phi), _lib.dt_of(phi), _lib.ptr(pre),
-                               0 if pre is None else D, _lib.stream_ptr()), "ed2_rff_fwd[split]")
+                               0 if pre is None else _lib.ld(pre), 1, _lib.stream_ptr()), "ed2_rff_fwd[split]")
     return phi, pre

@@ -475,13 +475,20 @@ int ed2_layernorm_bwd(const void* x, int x_dtype, int x_ld, const void* dy, int 
 /* Random Fourier features (edward2/tensorflow/layers/random_feature.py:258-266;
  * edward2/jax/nn/random_feature.py:209-214):  phi = cos(x W + b) * scale.
  * wt: the frozen projection stored TRANSPOSED, [D][in_dim] in `dtype` (K-major B operand).
- * pre (optional): fp32 [B][D] receives x W (without the bias) for the backward pass. */
+ * pre (optional, [B][D], for the backward pass): pre_mode 0 — fp32, receives the phase x W (without the bias);
+ * pre_mode 1 (ED2_BF16 GEMM) — bf16, receives -scale * sin(x W + b), the derivative factor of the feature map, from the
+ * same range reduction that produced phi: half the bytes of the fp32 phase and no sin pass in the backward. */
 int ed2_rff_fwd(int dtype, const void* x, int x_ld, const void* wt, int wt_ld, const float* bias, float scale,
-                int batch, int in_dim, int num_features, void* phi, int phi_ld, int phi_dtype, float* pre,
-                int pre_ld, void* stream);
+                int batch, int in_dim, int num_features, void* phi, int phi_ld, int phi_dtype, void* pre,
+                int pre_ld, int pre_mode, void* stream);
+/* LayerNorm forward written straight into the bf16 SPLIT A-operand of the fp32-grade feature GEMM (the 2-term split of
+ * ed2_split_bf16 with is_b = 0): out [rows][3 * cols] = [h | h | m], h = bf16(y), m = bf16(y - h),
+ * y = (x - mean) rsqrt(var + eps) gamma + beta.  cols % 8 == 0. */
+int ed2_layernorm_split(const void* x, int x_dtype, int x_ld, void* out, int out_ld, long long rows, int cols,
+                        const float* gamma, const float* beta, float eps, void* stream);
 /* dx = (-scale * sin(pre + b) ∘ dphi) Wᵀ  (W and b are frozen: only the input gradient exists).
  * w: [in_dim][D] in `dtype`; gpre: workspace [B][D] in `dtype`. */
-int ed2_rff_bwd(int dtype, const void* dphi, int dphi_ld, int dphi_dtype, const float* pre, int pre_ld,
+int ed2_rff_bwd(int dtype, const void* dphi, int dphi_ld, int dphi_dtype, const void* pre, int pre_ld, int pre_mode /* as written by ed2_rff_fwd */,
                 const float* bias, const void* w, int w_ld, float scale, int batch, int in_dim, int num_features,
                 void* gpre, int gpre_ld, void* dx, int dx_ld, int dx_dtype, void* stream);
 
