@@ -31,7 +31,9 @@ KL_SCALE = 1.0 / 50000
 METRIC = "samples/sec fwd+bwd"
 HEADLINE = "cfg4"
 # DRAM bytes per tcgen05 GEMM launch from the committed `ncu --set full` captures (profiles/); None = not captured
-NCU_TRAFFIC = {"cfg2_reparam": 67.7e6}
+NCU_TRAFFIC = {"cfg2_reparam": 67.7e6,   # profiles/r01_ncu_summary.csv (8 launches; 83.7 MB algorithmic per launch)
+               "cfg4": 164.7e6}          # profiles/r02_ncu_rank1_fused_summary.csv (9 launches; 168 MB algorithmic)
+NCU_ALGO_BYTES = {"cfg2_reparam": 83.7e6, "cfg4": 168.0e6}
 
 
 def mlp_flops(dims, batch, mult=1.0):
@@ -581,6 +583,7 @@ def run_ours(args):
                 "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
                 "frac_of_sustained": ach / pk["bf16_sustained"], "traffic": NCU_TRAFFIC.get(name),
                 "traffic_unit": "bytes/launch (ncu --set full capture, profiles/)" if NCU_TRAFFIC.get(name) else None,
+                "algorithmic_bytes_per_launch": NCU_ALGO_BYTES.get(name),
                 "gemm_us_per_step": gemm_us, "all_kernels_us_per_step": total_us,
                 "gemm_share_of_kernel_time": gemm_us / total_us if total_us else None,
                 "algorithmic_flops_per_step": wl["flops"], "peak_source": pk["src"] + ", burst bf16"}
