@@ -142,3 +142,26 @@ def test_reference_variable_names_roundtrip():
         checkpoint.load_reference_variables(other, {**numpy_vars, "dense/bias:0": numpy_vars["dense/bias:0"][:3]})
     with pytest.raises(ValueError):
         checkpoint.reference_variables(ed.layers.DenseReparameterization(8))
+
+
+@pytest.mark.parametrize("shim", ["jax_ffi_shim.cc", "tf_op_shim.cc"])
+def test_shims_type_check(shim):
+    """The jax.ffi / TensorFlow-op shims cannot be built here (no jaxlib / TensorFlow headers): they are compiled with
+    -fsyntax-only against shims/mock/, which reproduces the API shapes — every argument struct field must exist in
+    include/ed2b200.h, every entry point must be called with its declared signature, every jax handler must match its
+    binding (static_assert in the mock's XLA_FFI_DEFINE_HANDLER_SYMBOL)."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "shims", "mock"),
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "shims", shim)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    src = open(os.path.join(ROOT, "shims", shim)).read()
+    for entry in ("ed2_be_dense_fwd", "ed2_be_dense_bwd", "ed2_rank1_dense_fwd", "ed2_rank1_dense_bwd",
+                  "ed2_reparam_dense_fwd", "ed2_reparam_dense_bwd", "ed2_flipout_dense_fwd", "ed2_flipout_dense_bwd",
+                  "ed2_rff_fwd", "ed2_laplace_precision_update", "ed2_predictive_variance", "ed2_spectral_norm_update"):
+        assert entry + "(" in src, f"{shim} does not bind {entry}"
