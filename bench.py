@@ -510,6 +510,20 @@ def run_ours(args):
                 sys.stderr.write(f"[bench] {name}: kernel timeline unavailable: {str(e)[:200]}\n")
             sync_all()
 
+        if args.trace and name == args.workload:
+            # kernel timeline of 3 steps (CUPTI through torch.profiler) for offline analysis; never a bench number
+            import contextlib
+
+            from torch.profiler import ProfilerActivity, profile
+
+            with (profile(activities=[ProfilerActivity.CUDA]) if rank == 0 else contextlib.nullcontext()) as prof:
+                for _ in range(3):
+                    run_step()
+                sync_all()
+            if rank == 0:
+                prof.export_chrome_trace(args.trace)
+            sync_all()
+
         if want_e2e:
             # end to end through the public layer API with HOST buffers: every step copies ITS batch from pinned host
             # memory (H2D on a copy stream into one of two staging slots, overlapping the previous step's compute),
@@ -692,6 +706,7 @@ def main():
                     help="N > 1: how gradients reaching the per-parameter hook (rank-1 / BatchEnsemble kernels) are summed")
     ap.add_argument("--gemm-ctas", type=int, default=0, help="persistent GEMM CTAs when N > 1 (rest: NCCL)")
     ap.add_argument("--no-allreduce", action="store_true", help="diagnostic only: skip the gradient all-reduce")
+    ap.add_argument("--trace", default="", help="write a chrome trace of 3 steps of the headline workload on rank 0 (diagnostics)")
     ap.add_argument("--dump-kernels", default="", help="append per-kernel in-step device times (CUPTI) to this file")
     ap.add_argument("--only", default="", help="comma-separated subset of the N=1 'configs' block (diagnostics)")
     ap.add_argument("--skip-cpu", action="store_true")

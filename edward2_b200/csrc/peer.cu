@@ -39,6 +39,22 @@ __global__ void __launch_bounds__(kBlock) peer_signal_kernel(PeerExchange x, con
   }
 }
 
+// peer_signal_kernel without a companion vector: epoch += 1, ready flag on every rank.  One warp, <= 32 registers, so it
+// fits beside a persistent GEMM CTA (see peer_wait_kernel).
+__global__ void __maxnreg__(32) peer_signal_small_kernel(PeerExchange x) {
+  unsigned long long* w = peer::local_words(x);
+  unsigned long long epoch = 0;
+  if (threadIdx.x == 0) {
+    epoch = w[0] + 1;
+    w[0] = epoch;
+  }
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  if (threadIdx.x < x.world) {
+    __threadfence_system();
+    peer::st_release_sys(peer::ready_flags(x, threadIdx.x) + x.rank, epoch);
+  }
+}
+
 // publish the CURRENT epoch into flag section `which` (0: ready, 1: reduced) of every rank — used by the copy-engine
 // exchange, where the data movement is a DMA the flag must follow in stream order
 __global__ void peer_flag_kernel(PeerExchange x, int which) {
@@ -143,6 +159,8 @@ __global__ void __launch_bounds__(kBlock) peer_gather_f32_kernel(PeerExchange x,
 void set_carveout() {
   static const bool once = [] {
     cudaFuncSetAttribute(peer_signal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(peer_signal_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(peer_flag_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(peer_gather_f32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(peer_reduce_slice_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(peer_reduce_slice_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -171,7 +189,10 @@ int k_peer_signal(const PeerExchange& x, const float* small_src, cudaStream_t s)
   if (st != ED2_OK) return st;
   if (x.small_n > 0 && small_src == nullptr) return set_error(ED2_ERR_BAD_ARG, "peer signal: small_src is null");
   set_carveout();
-  peer_signal_kernel<<<1, kBlock, 0, s>>>(x, small_src);
+  // without a companion vector the kernel only bumps the epoch and writes <= 8 flags: one warp, which fits beside a
+  // persistent GEMM CTA that owns the rest of the SM (a 256-thread block would wait for that GEMM's tail)
+  if (x.small_n > 0) peer_signal_kernel<<<1, kBlock, 0, s>>>(x, small_src);
+  else peer_signal_small_kernel<<<1, 32, 0, s>>>(x);
   count_launch();
   return check_launch("peer_signal");
 }

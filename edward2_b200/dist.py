@@ -272,6 +272,7 @@ class DmaExchange:
         self._real, self._local = C.byref(real), C.byref(local)
         self.bucket_ptr = me + lay["bucket"]
         self._pending = False
+        self._pool = None
 
     def cast_into_bucket(self, grad2d):
         from . import _lib
@@ -284,7 +285,6 @@ class DmaExchange:
         lo = q * self.chunk
         return lo, max(0, min(self.n, lo + self.chunk) - lo)
 
-    _copy_streams = {}  # device index -> streams the DMA pushes fan out over (one copy engine each)
     N_COPY_STREAMS = 4
 
     def _fan_out(self, copies):
@@ -295,12 +295,16 @@ class DmaExchange:
         copies = [c for c in copies if c[2] > 0]
         if not copies:
             return
+        # (measured on B200: one engine at a time serves this GPU's peer writes at ~0.47 TB/s — cutting a copy into pieces
+        # on several streams does not add bandwidth, profiles/r02_trace_n2_dma.txt — so copies are not split; the streams
+        # only keep pushes to DIFFERENT peers independent of each other)
         cur = torch.cuda.current_stream()
         if len(copies) == 1:
             _lib.check(self.lib.ed2_dma_copy(*copies[0], cur.cuda_stream), "ed2_dma_copy")
             return
-        dev = torch.cuda.current_device()
-        pool = DmaExchange._copy_streams.setdefault(dev, [torch.cuda.Stream(priority=-1) for _ in range(self.N_COPY_STREAMS)])
+        if self._pool is None:  # per exchange: the chains of different layers never wait on each other's copies
+            self._pool = [torch.cuda.Stream(priority=-1) for _ in range(self.N_COPY_STREAMS)]
+        pool = self._pool
         fork = torch.cuda.Event()
         fork.record(cur)
         used = pool[:min(len(pool), len(copies))]
@@ -432,8 +436,11 @@ class GradientAllReduce:
         exchange on the side streams and install the summed fp32 gradient as p.grad (bypassing the hook).  `after`:
         event recorded right behind the dW GEMM — the exchange then overlaps whatever the layer enqueued after it."""
         g = torch.empty(p.shape, dtype=torch.float32, device=p.device)
-        reduced_ev = self.on_side_stream(ex.scatter_reduce, which=0, fork=after)
-        done_ev = self.on_side_stream(lambda: ex.gather_f32(g), which=1, after=reduced_ev)
+        # every exchange has its own pair of side streams: the chain of a later (smaller) layer does not queue behind an
+        # earlier layer's second DMA phase
+        lane = 2 + 2 * (list(self._exchanges).index(id(p)) % 3)
+        reduced_ev = self.on_side_stream(ex.scatter_reduce, which=lane, fork=after)
+        done_ev = self.on_side_stream(lambda: ex.gather_f32(g), which=lane + 1, after=reduced_ev)
         self.defer(None, after=done_ev, keep=(g,))
         self.mark_done(p)
         if p.grad is None:
