@@ -2,7 +2,11 @@
 // matvecs over the weight matrix), input LayerNorm, the precision-matrix momentum blend and mean-field logits.
 #include "kernels.h"
 
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
 
 #include "gemm_epilogue.h"
 #include "status.h"
@@ -361,6 +365,151 @@ __global__ void __launch_bounds__(kBlock) mul_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Whole spectral-norm update of a small kernel in ONE launch: a cluster of 8 CTAs keeps W resident in distributed shared
+// memory (CTA c owns in_dim / 8 rows), so W is read from HBM once and written once; both matvecs, both l2-normalisations,
+// sigma and the scaling pass run out of shared memory, with cluster barriers + DSMEM reads for the cross-CTA sums.
+// Replaces 7 launches (matvec_rows, l2_normalize, memset, matvec_cols, l2_normalize, sigma, scale_w) that are pure
+// launch latency at the SNGP backbone's sizes (512 x 512 = 1 MB).  Same arithmetic order per element as those kernels
+// up to the summation order of the dot products.
+constexpr int kSnCluster = 8;
+constexpr int kSnThreads = 512;
+
+__device__ __forceinline__ float sn_block_sum(float v, float* red) {  // red: kSnThreads / 32 + 1 floats
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < kSnThreads / 32 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[kSnThreads / 32] = t;
+  }
+  __syncthreads();
+  const float r = red[kSnThreads / 32];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __cluster_dims__(kSnCluster, 1, 1) __launch_bounds__(kSnThreads)
+spectral_norm_cluster_kernel(const float* __restrict__ w, int in_dim, int out_dim, float* __restrict__ u,
+                             float* __restrict__ v, int iterations, float c, int mode, int update_uv, float* w_out,
+                             __nv_bfloat16* w_lp, long long lp_ld, float* sigma_out, float* scal) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float sm[];
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int rows = in_dim / kSnCluster, r0 = rank * rows;
+  float* ws = sm;                                  // [rows][out_dim]   this CTA's rows of W
+  float* su = ws + (size_t)rows * out_dim;         // [out_dim]         current u
+  float* part = su + out_dim;                      // [out_dim]         this CTA's partial of v W
+  float* ucopy = part + out_dim;                   // [out_dim]         final u (kept while su receives v W)
+  float* sv = ucopy + out_dim;                     // [rows]            this CTA's slice of v
+  float* red = sv + rows;                          // block-sum scratch [17]
+  float* xch = red + 32;                           // [8] cluster-visible scalars (partial sums of squares)
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+  for (int i = t * 4; i < rows * out_dim; i += kSnThreads * 4)
+    *reinterpret_cast<float4*>(ws + i) = __ldg(reinterpret_cast<const float4*>(w + (size_t)r0 * out_dim + i));
+  for (int o = t; o < out_dim; o += kSnThreads) su[o] = u[o];
+  for (int i = t; i < rows; i += kSnThreads) sv[i] = v[r0 + i];
+  __syncthreads();
+
+  auto cluster_sum = [&](float local, int slot) -> float {  // sum of `local` (one value per CTA) over the cluster
+    if (t == 0) xch[slot] = local;
+    cluster.sync();
+    float tot = 0.f;
+    for (int q = 0; q < kSnCluster; ++q) tot += *cluster.map_shared_rank(xch + slot, q);
+    cluster.sync();  // everyone has read before the slot is reused
+    return tot;
+  };
+  // u_raw = v W for the current v: partial over this CTA's rows, then every CTA sums the partials of all CTAs (DSMEM)
+  auto vw = [&]() {
+    for (int o = t; o < out_dim; o += kSnThreads) {
+      float acc = 0.f;
+      for (int i = 0; i < rows; ++i) acc = fmaf(sv[i], ws[(size_t)i * out_dim + o], acc);
+      part[o] = acc;
+    }
+    cluster.sync();
+    for (int o = t; o < out_dim; o += kSnThreads) {
+      float acc = 0.f;
+      for (int q = 0; q < kSnCluster; ++q) acc += cluster.map_shared_rank(part, q)[o];
+      su[o] = acc;  // u_raw (replicated in every CTA)
+    }
+    cluster.sync();  // partials consumed
+  };
+
+  const int iters = update_uv ? iterations : 0;
+  for (int it = 0; it < iters; ++it) {
+    // v_raw = u W^T (own rows), v = l2n(v_raw)
+    float sq = 0.f;
+    for (int i = warp; i < rows; i += kSnThreads / 32) {
+      float acc = 0.f;
+      for (int o = lane * 4; o < out_dim; o += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(ws + (size_t)i * out_dim + o);
+        const float4 b = *reinterpret_cast<const float4*>(su + o);
+        acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) { sv[i] = acc; sq += acc * acc; }
+    }
+    sq = sn_block_sum(sq, red);
+    const float inv_v = rsqrtf(fmaxf(cluster_sum(sq, 0), 1e-12f));
+    for (int i = t; i < rows; i += kSnThreads) sv[i] *= inv_v;
+    __syncthreads();
+    // u_raw = v W, u = l2n(u_raw)
+    vw();
+    float squ = 0.f;
+    for (int o = t; o < out_dim; o += kSnThreads) squ += su[o] * su[o];
+    squ = sn_block_sum(squ, red);  // su is replicated: every CTA computes the same total
+    const float inv_u = rsqrtf(fmaxf(squ, 1e-12f));
+    for (int o = t; o < out_dim; o += kSnThreads) su[o] *= inv_u;
+    __syncthreads();
+  }
+  // sigma = v W u^T with the final u, v (normalization.py:381): keep u, recompute v W
+  if (iters > 0) {
+    if (rank == 0)
+      for (int o = t; o < out_dim; o += kSnThreads) u[o] = su[o];
+    for (int i = t; i < rows; i += kSnThreads) v[r0 + i] = sv[i];
+  }
+  for (int o = t; o < out_dim; o += kSnThreads) ucopy[o] = su[o];
+  __syncthreads();
+  vw();
+  float acc_s = 0.f;
+  for (int o = t; o < out_dim; o += kSnThreads) acc_s += ucopy[o] * su[o];
+  const float sg = sn_block_sum(acc_s, red);
+  float factor;
+  if (mode == 0) factor = (c / sg) < 1.f ? (c / sg) : 1.f;   // normalization.py:387-390
+  else factor = 1.f / fmaxf(sg / c, 1.f);                    // jax/nn/normalization.py:175-178
+  if (rank == 0 && t == 0) {
+    scal[0] = sg;
+    scal[1] = factor;
+    if (sigma_out != nullptr) *sigma_out = sg;
+  }
+  if (w_out != nullptr || w_lp != nullptr) {
+    const float div = fmaxf(sg / c, 1.f);
+    for (int i = t * 4; i < rows * out_dim; i += kSnThreads * 4) {
+      float4 x = *reinterpret_cast<const float4*>(ws + i);
+      float y[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = mode == 0 ? (factor < 1.f ? factor * y[j] : y[j]) : y[j] / div;
+      if (w_out != nullptr) *reinterpret_cast<float4*>(w_out + (size_t)r0 * out_dim + i) = make_float4(y[0], y[1], y[2], y[3]);
+      if (w_lp != nullptr) {
+        const int r = i / out_dim, cc = i - r * out_dim;
+        __nv_bfloat16* p = w_lp + (size_t)(r0 + r) * lp_ld + cc;
+        p[0] = __float2bfloat16_rn(y[0]); p[1] = __float2bfloat16_rn(y[1]);
+        p[2] = __float2bfloat16_rn(y[2]); p[3] = __float2bfloat16_rn(y[3]);
+      }
+    }
+  }
+  cluster.sync();  // no CTA exits while a peer may still read its shared memory
+}
+
+size_t sn_cluster_smem(int in_dim, int out_dim) {
+  const size_t rows = in_dim / kSnCluster;
+  return sizeof(float) * (rows * out_dim + 3 * (size_t)out_dim + rows + 32 + 8);
+}
+
 int grid_for(long long n) {
   long long g = (n + kBlock - 1) / kBlock;
   if (g < 1) g = 1;
@@ -377,6 +526,23 @@ int k_spectral_norm(const float* w, int in_dim, int out_dim, float* u, float* v,
   float* v_raw = ws;
   float* u_raw = ws + in_dim;
   float* scal = u_raw + out_dim;
+  // small kernels: one cluster launch with W resident in distributed shared memory
+  static const bool fused_ok = [] { const char* e = std::getenv("ED2_SN_FUSED"); return e == nullptr || std::atoi(e) != 0; }();
+  if (fused_ok && in_dim % kSnCluster == 0 && out_dim % 4 == 0 && sn_cluster_smem(in_dim, out_dim) <= 200 * 1024 &&
+      (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (w_out == nullptr || (reinterpret_cast<uintptr_t>(w_out) & 15) == 0) &&
+      (w_out_lp == nullptr || w_lp_ld % 4 == 0)) {
+    const size_t smem = sn_cluster_smem(in_dim, out_dim);
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(spectral_norm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    spectral_norm_cluster_kernel<<<kSnCluster, kSnThreads, smem, s>>>(w, in_dim, out_dim, u, v, iterations, c, mode, update_uv,
+                                                                      w_out, reinterpret_cast<__nv_bfloat16*>(w_out_lp),
+                                                                      w_lp_ld, sigma_out, scal);
+    count_launch();
+    return check_launch("spectral_norm(cluster)");
+  }
   const int row_grid = std::min(148 * 4, (in_dim + 7) / 8);
   dim3 col_grid((out_dim + 127) / 128, (in_dim + kSlabRows - 1) / kSlabRows);
   int launches = 0;
