@@ -163,6 +163,33 @@ class FlipoutBwd(C.Structure):
     ]
 
 
+class FlipoutFusedFwd(C.Structure):
+    _fields_ = [
+        ("batch", _i), ("in_dim", _i), ("out_dim", _i), ("act", _i),
+        ("x", _vp), ("x_ld", _i), ("xs", _vp), ("xs_ld", _i), ("xs_ready", _i),
+        ("sign_in", Noise), ("sign_out", Noise),
+        ("mu_lp", _vp), ("mu_ld", _i), ("delta_lp", _vp), ("delta_ld", _i),
+        ("bias", _vp), ("y", _vp), ("y_ld", _i),
+        ("next_xs", _vp), ("next_xs_ld", _i), ("next_sign_in", Noise),
+    ]
+
+
+class FlipoutFusedBwd(C.Structure):
+    _fields_ = [
+        ("batch", _i), ("in_dim", _i), ("out_dim", _i), ("act", _i), ("premade", _i),
+        ("gy", _vp), ("gy_ld", _i), ("y", _vp), ("y_ld", _i),
+        ("gp", _vp), ("gp_ld", _i), ("gt", _vp), ("gt_ld", _i),
+        ("x", _vp), ("x_ld", _i), ("xs", _vp), ("xs_ld", _i),
+        ("mu_lp", _vp), ("mu_ld", _i), ("delta_lp", _vp), ("delta_ld", _i),
+        ("mu", _vp), ("rho", _vp), ("eps", Noise), ("sign_in", Noise), ("sign_out", Noise),
+        ("dmu", _vp), ("drho", _vp), ("dbias", _vp),
+        ("kl_grad_scale", _f), ("prior_mean", _f), ("prior_std", _f), ("kl_upstream", _vp),
+        ("dx", _vp), ("dx_ld", _i),
+        ("prev_relu", _i), ("prev_gp", _vp), ("prev_gp_ld", _i), ("prev_gt", _vp), ("prev_gt_ld", _i),
+        ("prev_sign_out", Noise), ("prev_dbias", _vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/ed2b200.h declares
 SIGNATURES = {
     "ed2_version": (C.c_char_p, []),
@@ -204,6 +231,9 @@ SIGNATURES = {
     "ed2_peer_grad_finish": (_i, [C.POINTER(PeerExchange), _vp, _vp, Noise, _f, _vp, _f, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "ed2_flipout_dense_fwd": (_i, [C.POINTER(FlipoutFwd), _vp]),
     "ed2_flipout_dense_bwd": (_i, [C.POINTER(FlipoutBwd), _vp]),
+    "ed2_flipout_fused_fwd": (_i, [C.POINTER(FlipoutFusedFwd), _vp]),
+    "ed2_flipout_fused_bwd": (_i, [C.POINTER(FlipoutFusedBwd), _vp]),
+    "ed2_flipout_fusable": (_i, [_i, _i, _i]),
     "ed2_spectral_norm_update": (_i, [_vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "ed2_input_normalize": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _vp, _f, _i, _f, _vp]),
     "ed2_layernorm_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _f, _vp, _i, _i, _vp, _vp, _vp]),

@@ -616,6 +616,95 @@ int ed2_flipout_dense_bwd(const ed2_flipout_bwd_args* a, void* stream) {
   return ED2_OK;
 }
 
+// Fused Flipout: one dual-accumulator launch per product pair (gemm_flipout.cuh)
+namespace {
+int sign_side(const ed2_noise& n, int batch, SignSide* out, const char* what) {
+  if (n.injected != nullptr) return set_error(ED2_ERR_BAD_ARG, "flipout_fused: %s must be a Philox stream (injected signs take the unfused call)", what);
+  // Flipout batches are ungrouped: a single group covering the local batch is the same mapping (global row = row0 + m)
+  if (n.rows_per_group_local != 0 && n.rows_per_group_local < batch)
+    return set_error(ED2_ERR_BAD_ARG, "flipout_fused: %s must be ungrouped (rows_per_group_local %d < batch %d)", what, n.rows_per_group_local, batch);
+  out->seed = n.seed; out->stream = n.stream; out->step = reinterpret_cast<const unsigned long long*>(n.step);
+  out->row0 = n.row0; out->on = 1;
+  return ED2_OK;
+}
+}  // namespace
+
+int ed2_flipout_fusable(int batch, int in_dim, int out_dim) {
+  return (gemm_flipout_fusable(batch, out_dim, in_dim) && gemm_flipout_fusable(batch, in_dim, out_dim)) ? 1 : 0;
+}
+
+int ed2_flipout_fused_fwd(const ed2_flipout_fused_fwd_args* a, void* stream) {
+  cudaStream_t s = S(stream);
+  if (!ed2_flipout_fusable(a->batch, a->in_dim, a->out_dim))
+    return set_error(ED2_ERR_BAD_SHAPE, "flipout_fused_fwd: shape %d x %d -> %d does not qualify (ed2_flipout_fusable)", a->batch, a->in_dim, a->out_dim);
+  FlipoutGemm g{};
+  ED2_TRY(sign_side(a->sign_out, a->batch, &g.epi.sa, "sign_out"));
+  if (!a->xs_ready)
+    ED2_TRY(k_scale_rows(a->x, kBF16, a->x_ld, a->batch, a->in_dim, a->batch, 2, nullptr, nullptr, N(a->sign_in), a->xs,
+                         a->xs_ld, nullptr, 0, s));
+  g.A0 = a->x; g.lda0 = a->x_ld; g.A1 = a->xs; g.lda1 = a->xs_ld;
+  g.B0 = a->mu_lp; g.ldb0 = a->mu_ld; g.B1 = a->delta_lp; g.ldb1 = a->delta_ld; g.major_b = kMajorMN;
+  g.M = a->batch; g.N = a->out_dim; g.K = a->in_dim;
+  g.out = a->y; g.out_ld = a->y_ld;
+  g.epi.bias = a->bias; g.epi.act = a->act;
+  if (a->next_xs != nullptr) {
+    ED2_TRY(sign_side(a->next_sign_in, a->batch, &g.epi.sb, "next_sign_in"));
+    g.epi.out2 = a->next_xs; g.epi.out2_ld = a->next_xs_ld;
+  }
+  return gemm_flipout(g, s);
+}
+
+int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream) {
+  cudaStream_t s = S(stream);
+  if (!ed2_flipout_fusable(a->batch, a->in_dim, a->out_dim))
+    return set_error(ED2_ERR_BAD_SHAPE, "flipout_fused_bwd: shape %d x %d -> %d does not qualify (ed2_flipout_fusable)", a->batch, a->in_dim, a->out_dim);
+  const bool want_dx = a->dx != nullptr || a->prev_gp != nullptr;
+  FlipoutGemm g{};
+  if (want_dx) {
+    ED2_TRY(sign_side(a->sign_in, a->batch, &g.epi.sa, "sign_in"));
+    if (a->prev_gt != nullptr) ED2_TRY(sign_side(a->prev_sign_out, a->batch, &g.epi.sb, "prev_sign_out"));
+    if (a->prev_dbias != nullptr) cudaMemsetAsync(a->prev_dbias, 0, sizeof(float) * (size_t)a->in_dim, s);
+  }
+  if (!a->premade) {
+    BwdOutArgs o{};
+    o.dt = kBF16; o.rows = a->batch; o.cols = a->out_dim; o.rows_per_member = a->batch; o.act = a->act; o.fast = 3;
+    o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld;
+    o.sign_out = N(a->sign_out);
+    o.dz = a->gp; o.dz_ld = a->gp_ld; o.dz2 = a->gt; o.dz2_ld = a->gt_ld;
+    o.dbias = a->dbias;
+    ED2_TRY(k_bwd_out(o, s));
+  }
+  EpiParams e = epi_default();
+  e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
+  ED2_TRY(gemm_xtg(kBF16, a->x, a->x_ld, a->gp, a->gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
+  EpiParams e1 = epi_default();
+  e1.out = a->drho; e1.out_ld = a->out_dim; e1.out_dt = kF32;
+  ED2_TRY(gemm_xtg(kBF16, a->xs, a->xs_ld, a->gt, a->gt_ld, a->batch, a->in_dim, a->out_dim, e1, s));
+  // the finishing pass (CUDA cores) runs on the side stream beside the dX launch (tensor cores)
+  ForkJoin fj(s, want_dx);
+  int st = ED2_OK;
+  if (want_dx) {
+    g.A0 = a->gp; g.lda0 = a->gp_ld; g.A1 = a->gt; g.lda1 = a->gt_ld;
+    g.B0 = a->mu_lp; g.ldb0 = a->mu_ld; g.B1 = a->delta_lp; g.ldb1 = a->delta_ld; g.major_b = kMajorK;
+    g.M = a->batch; g.N = a->in_dim; g.K = a->out_dim;
+    if (a->prev_gp != nullptr) {
+      g.out = a->prev_gp; g.out_ld = a->prev_gp_ld;
+      if (a->prev_relu) { g.epi.mask_src = a->x; g.epi.mask_ld = a->x_ld; }
+      if (a->prev_gt != nullptr) { g.epi.out2 = a->prev_gt; g.epi.out2_ld = a->prev_gt_ld; }
+      g.epi.col_sum = a->prev_dbias;
+    } else {
+      g.out = a->dx; g.out_ld = a->dx_ld;
+    }
+    st = gemm_flipout(g, s);
+  }
+  if (st == ED2_OK)
+    st = k_normal_grad_finish(a->dmu, a->drho, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
+                              a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
+                              true, fj.side());
+  fj.join();
+  return st;
+}
+
 // ------------------------------------------------------------------------------------------ SNGP head
 int ed2_spectral_norm_update(const float* w, int in_dim, int out_dim, float* u, float* v, int iterations,
                              float norm_multiplier, int mode, int update_uv, float* w_out, void* w_out_lp, int w_lp_ld,

@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "gemm_sm100.cuh"
+#include "gemm_flipout.cuh"
 #include "status.h"
 
 namespace ed2 {
@@ -211,6 +212,77 @@ int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
   if (g.major_a == kMajorK && g.major_b == kMajorMN) return dispatch_cfg<kMajorK, kMajorMN>(g, bn, cg, ta, tb, to, stream);
   if (g.major_a == kMajorMN && g.major_b == kMajorK) return dispatch_cfg<kMajorMN, kMajorK>(g, bn, cg, ta, tb, to, stream);
   return dispatch_cfg<kMajorMN, kMajorMN>(g, bn, cg, ta, tb, to, stream);
+}
+
+bool gemm_flipout_fusable(int M, int N, int K) { return M > 128 && N % 8 == 0 && K % 8 == 0; }
+
+namespace {
+template <int MB>
+int launch_flipout(const FlipoutGemm& g, const CUtensorMap& ta0, const CUtensorMap& ta1, const CUtensorMap& tb0,
+                   const CUtensorMap& tb1, const CUtensorMap& to, int out_tma, cudaStream_t stream) {
+  auto kern = tc::gemm_flipout_kernel<MB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFoSmemBytes);
+    if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "cudaFuncSetAttribute(flipout smem=%d): %s", tc::kFoSmemBytes,
+                                           cudaGetErrorString(e));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_set = true;
+  }
+  const int nm = (g.M + 2 * tc::kBlockM - 1) / (2 * tc::kBlockM);
+  const int nn = (g.N + tc::kFoBlockN - 1) / tc::kFoBlockN;
+  const int clusters = std::min(num_sms() / 2, nm * nn);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(tc::kFoThreads);
+  cfg.dynamicSmemBytes = tc::kFoSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta0, ta1, tb0, tb1, to, g.M, g.N, g.K, g.out, g.out_ld, out_tma, g.epi);
+  if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "flipout gemm launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return ED2_OK;
+}
+}  // namespace
+
+int gemm_flipout(const FlipoutGemm& g, cudaStream_t stream) {
+  if (!gemm_flipout_fusable(g.M, g.N, g.K))
+    return set_error(ED2_ERR_BAD_SHAPE, "flipout gemm: needs M > 128 and N, K multiples of 8 (M=%d N=%d K=%d)", g.M, g.N, g.K);
+  if (!tma_ok(g.A0, g.lda0, 2) || !tma_ok(g.A1, g.lda1, 2) || !tma_ok(g.B0, g.ldb0, 2) || !tma_ok(g.B1, g.ldb1, 2))
+    return set_error(ED2_ERR_BAD_ARG, "flipout gemm: operands must be 16-byte aligned with a pitch that is a multiple of 8 bf16");
+  if (g.out == nullptr && g.epi.out2 == nullptr && g.epi.col_sum == nullptr)
+    return set_error(ED2_ERR_BAD_ARG, "flipout gemm: no output");
+  if (g.epi.out2 != nullptr && (!tma_ok(g.epi.out2, g.epi.out2_ld, 2)))
+    return set_error(ED2_ERR_BAD_ARG, "flipout gemm: out2 must be 16-byte aligned with a pitch that is a multiple of 8 bf16");
+  if (g.epi.mask_src != nullptr && !tma_ok(g.epi.mask_src, g.epi.mask_ld, 2))
+    return set_error(ED2_ERR_BAD_ARG, "flipout gemm: mask_src must be 16-byte aligned with a pitch that is a multiple of 8 bf16");
+  if (g.epi.bias != nullptr && (reinterpret_cast<uintptr_t>(g.epi.bias) & 15) != 0)
+    return set_error(ED2_ERR_BAD_ARG, "flipout gemm: bias must be 16-byte aligned");
+  CUtensorMap ta0, ta1, tb0, tb1, to;
+  std::memset(&to, 0, sizeof(to));
+  bool ok = make_map(&ta0, g.A0, kBF16, g.M, g.K, g.lda0, tc::kBlockM, tc::kBlockK) &&
+            make_map(&ta1, g.A1, kBF16, g.M, g.K, g.lda1, tc::kBlockM, tc::kBlockK);
+  if (g.major_b == kMajorK) {
+    ok = ok && make_map(&tb0, g.B0, kBF16, g.N, g.K, g.ldb0, tc::kFoBlockN / 2, tc::kBlockK) &&
+         make_map(&tb1, g.B1, kBF16, g.N, g.K, g.ldb1, tc::kFoBlockN / 2, tc::kBlockK);
+  } else {
+    ok = ok && make_map(&tb0, g.B0, kBF16, g.K, g.N, g.ldb0, tc::kBlockK, 64) &&
+         make_map(&tb1, g.B1, kBF16, g.K, g.N, g.ldb1, tc::kBlockK, 64);
+  }
+  if (!ok) return set_error(ED2_ERR_CUDA, "cuTensorMapEncodeTiled failed for a flipout GEMM operand");
+  int out_tma = 0;
+  if (g.out != nullptr) {
+    if (!tma_ok(g.out, g.out_ld, 2)) return set_error(ED2_ERR_BAD_ARG, "flipout gemm: out must be 16-byte aligned, pitch % 8 == 0");
+    if (make_map(&to, g.out, kBF16, g.M, g.N, g.out_ld, tc::kBlockM, 64)) out_tma = 1;
+  }
+  if (g.major_b == kMajorK) return launch_flipout<kMajorK>(g, ta0, ta1, tb0, tb1, to, out_tma, stream);
+  return launch_flipout<kMajorMN>(g, ta0, ta1, tb0, tb1, to, out_tma, stream);
 }
 
 }  // namespace ed2

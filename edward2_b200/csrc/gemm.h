@@ -33,4 +33,19 @@ int gemm_bf16_accumulate(const GemmDesc& g, cudaStream_t stream);
 int gemm_f32(const GemmDesc& g, cudaStream_t stream);   // fp32 FFMA path
 int gemm(int dtype, const GemmDesc& g, cudaStream_t stream);
 
+// DenseFlipout as one launch with two TMEM accumulators (gemm_flipout.cuh): out = post(A0 B0 + (A1 B1) ∘ sa), bf16.
+// A0 / A1 are K-major [M][K]; B0 / B1 share one layout (K-major [N][K] or MN-major [K][N]).
+struct FlipoutGemm {
+  const void* A0; int lda0;
+  const void* A1; int lda1;
+  const void* B0; int ldb0;
+  const void* B1; int ldb1;
+  int major_b;
+  int M, N, K;
+  void* out; int out_ld;  // bf16, optional when epi.out2 / epi.col_sum carry the result
+  FlipoutEpi epi;
+};
+bool gemm_flipout_fusable(int M, int N, int K);
+int gemm_flipout(const FlipoutGemm& g, cudaStream_t stream);
+
 }  // namespace ed2

@@ -94,4 +94,24 @@ struct Rank1Epi {
   float* dmu_s; float* drho_s; float* dbias;
 };
 
+// ---- fused Flipout (DenseFlipout, edward2/tensorflow/layers/dense.py:255-285): gemm_flipout.cuh ------------------------
+// A per-example sign stream [rows][N]: element (m, n) = +1 when bit 31 of Philox word (row0 + m) * N + n is set
+// (philox.cuh stream contract, identical to the materialised sign tensors of the unfused path).
+struct SignSide {
+  unsigned long long seed, stream;
+  const unsigned long long* step;
+  long long row0;
+  int on;
+};
+//   v = acc0 + acc1 * sa[m,n] + bias[n];  v = act(v);  v = mask_src[m,n] > 0 ? v : 0;  out = bf16(v)
+//   out2 = out * sb[m,n] (optional);  col_sum[n] += sum_m out (optional, fp32 atomics)
+struct FlipoutEpi {
+  SignSide sa, sb;
+  const float* bias;
+  int act;
+  const void* mask_src; int mask_ld;  // bf16 [M][N]
+  void* out2; int out2_ld;            // bf16 [M][N]
+  float* col_sum;                     // [N], zero-initialised by the caller
+};
+
 }  // namespace ed2

@@ -601,6 +601,155 @@ class FlipoutDense(torch.autograd.Function):
         return dx, dmu, drho, dbias, None, None, None, None, None, None, None, None
 
 
+class FlipoutLink:
+    """Cross-layer fusion token of a DenseFlipout stack (attached to a layer's output tensor).
+
+    Forward: the producing layer's dual-accumulator epilogue also writes the CONSUMER's second operand x∘S
+    (`xs_next`, signs drawn from the consumer's own sign_input stream, identified by `xs_key`), so the consumer runs no
+    sign pass.  Backward: the consumer's dX epilogue applies the producer's activation mask and sign_output stream and
+    records gp = dx∘act'(y), gt = gp∘T and the bias-gradient column sums here; the producer uses them only when the
+    gradient it receives IS the recorded tensor, unmodified (same rule as ReluLink — fan-out falls back)."""
+
+    __slots__ = ("act", "sign_out", "has_bias", "xs_next", "xs_key", "dx", "dx_version", "gt", "dbias", "fused")
+
+    def __init__(self):
+        for k in self.__slots__:
+            setattr(self, k, None)
+        self.fused = False
+
+    def record(self, dx, gt, dbias):
+        self.dx, self.dx_version, self.gt, self.dbias = dx, dx._version, gt, dbias
+
+    def matches(self, gy, shape) -> bool:
+        d = self.dx
+        return (d is not None and gy.data_ptr() == d.data_ptr() and gy.shape == d.shape == shape
+                and gy.dtype == d.dtype and gy._version == self.dx_version and d._version == self.dx_version)
+
+
+def flipout_xs_key(x, sign_in):
+    return (x.data_ptr(), tuple(x.shape), x._version, _noise_key(sign_in))
+
+
+FLIPOUT_FUSION = True  # module switch for A/B tests: False forces the two-GEMM kernels
+
+
+def flipout_fusable(x, mu, dtype, sign_in, sign_out) -> bool:
+    if not FLIPOUT_FUSION or dtype != torch.bfloat16 or sign_in.injected is not None or sign_out.injected is not None:
+        return False
+    B, I = x.shape
+    return bool(_lib.load().ed2_flipout_fusable(B, I, mu.shape[1]))
+
+
+class FlipoutDenseFused(torch.autograd.Function):
+    """DenseFlipout on the dual-accumulator kernel (include/ed2b200.h: ed2_flipout_fused_fwd / _bwd): bf16, Philox
+    signs.  `presampled` = (mu_lp, delta_lp, kl64) drawn ahead of time by layer.presample(), else drawn here."""
+
+    @staticmethod
+    def forward(ctx, x, mu, rho, bias, act, eps, sign_in, sign_out, kl_scale, prior_mean, prior_std, in_link, out_link,
+                next_sign, presampled):
+        lib = _lib.load()
+        dtype = torch.bfloat16
+        B, I = x.shape
+        O = mu.shape[1]
+        dev = x.device
+        xc = as_compute(x, dtype)
+        if xc.data_ptr() != x.data_ptr():
+            in_link = None
+        if presampled is not None:
+            mu_lp, delta_lp, kl64 = presampled
+        else:
+            mu_lp, delta_lp = _new(I, O, dtype, dev), _new(I, O, dtype, dev)
+            kl64 = torch.zeros((), dtype=torch.float64, device=dev) if kl_scale != 0 else None
+            _lib.check(lib.ed2_sample_normal_weights(
+                mu.data_ptr(), rho.data_ptr(), eps.c(), I, O, 1, delta_lp.data_ptr(), BF16, _lib.ld(delta_lp),
+                mu_lp.data_ptr(), _lib.ld(mu_lp), _p(kl64), kl_scale, prior_mean, prior_std, _lib.stream_ptr()),
+                "ed2_sample_normal_weights")
+        xs_ready = (in_link is not None and in_link.xs_next is not None
+                    and in_link.xs_key == flipout_xs_key(xc, sign_in))
+        xs = in_link.xs_next if xs_ready else _new(B, I, dtype, dev)
+        y = _new(B, O, dtype, dev)
+        a = _lib.FlipoutFusedFwd()
+        a.batch, a.in_dim, a.out_dim, a.act = B, I, O, act
+        a.x, a.x_ld, a.xs, a.xs_ld, a.xs_ready = xc.data_ptr(), _lib.ld(xc), xs.data_ptr(), _lib.ld(xs), int(xs_ready)
+        a.sign_in, a.sign_out = sign_in.c(), sign_out.c()
+        a.mu_lp, a.mu_ld, a.delta_lp, a.delta_ld = mu_lp.data_ptr(), _lib.ld(mu_lp), delta_lp.data_ptr(), _lib.ld(delta_lp)
+        a.bias, a.y, a.y_ld = _p(bias), y.data_ptr(), _lib.ld(y)
+        xs_next = None
+        if out_link is not None and next_sign is not None and next_sign.injected is None and O % 8 == 0:
+            xs_next = _new(B, O, dtype, dev)
+            a.next_xs, a.next_xs_ld, a.next_sign_in = xs_next.data_ptr(), _lib.ld(xs_next), next_sign.c()
+        _lib.check(lib.ed2_flipout_fused_fwd(C.byref(a), _lib.stream_ptr()), "ed2_flipout_fused_fwd")
+        if out_link is not None:
+            out_link.act, out_link.sign_out, out_link.has_bias = act, sign_out, bias is not None
+            out_link.xs_next = xs_next
+            out_link.xs_key = flipout_xs_key(y, next_sign) if xs_next is not None else None
+        ctx.save_for_backward(xc, xs, y, mu_lp, delta_lp, mu, rho)
+        ctx.meta = (act, bias is not None, x.dtype, eps, sign_in, sign_out, kl_scale, prior_mean, prior_std)
+        ctx.links = (in_link, out_link)
+        ctx.set_materialize_grads(False)
+        # the KL stays fp64 (the accumulator's type): no conversion kernel on the step's critical path
+        return y, (kl64 if kl64 is not None else torch.zeros((), dtype=torch.float64, device=dev))
+
+    @staticmethod
+    def backward(ctx, gy, gkl):
+        lib = _lib.load()
+        xc, xs, y, mu_lp, delta_lp, mu, rho = ctx.saved_tensors
+        act, has_bias, x_dtype, eps, sign_in, sign_out, kl_scale, pm, ps = ctx.meta
+        in_link, out_link = ctx.links
+        dtype = torch.bfloat16
+        B, I = xc.shape
+        O = y.shape[1]
+        dev = xc.device
+        if gy is None:
+            gy = torch.zeros(B, O, dtype=dtype, device=dev)
+        gyc = as_compute(gy, dtype)
+        premade = out_link is not None and out_link.matches(gyc, y.shape) and out_link.gt is not None
+        if out_link is not None:
+            out_link.fused = premade
+        a = _lib.FlipoutFusedBwd()
+        a.batch, a.in_dim, a.out_dim, a.act, a.premade = B, I, O, act, int(premade)
+        if premade:
+            gp, gt = gyc, out_link.gt
+            dbias = out_link.dbias if has_bias else None
+        else:
+            gp, gt = _new(B, O, dtype, dev), _new(B, O, dtype, dev)
+            dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
+            a.gy, a.gy_ld, a.y, a.y_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y)
+            a.dbias = _p(dbias)
+        a.gp, a.gp_ld, a.gt, a.gt_ld = gp.data_ptr(), _lib.ld(gp), gt.data_ptr(), _lib.ld(gt)
+        a.x, a.x_ld, a.xs, a.xs_ld = xc.data_ptr(), _lib.ld(xc), xs.data_ptr(), _lib.ld(xs)
+        a.mu_lp, a.mu_ld, a.delta_lp, a.delta_ld = mu_lp.data_ptr(), _lib.ld(mu_lp), delta_lp.data_ptr(), _lib.ld(delta_lp)
+        a.mu, a.rho, a.eps, a.sign_in, a.sign_out = mu.data_ptr(), rho.data_ptr(), eps.c(), sign_in.c(), sign_out.c()
+        dmu = torch.empty(I, O, dtype=torch.float32, device=dev)
+        drho = torch.empty(I, O, dtype=torch.float32, device=dev)
+        a.dmu, a.drho = dmu.data_ptr(), drho.data_ptr()
+        up = (gkl if gkl.dtype == torch.float64 else gkl.to(torch.float64)).reshape(1) if gkl is not None else None
+        a.kl_grad_scale = (kl_scale if gkl is not None else 0.0) / GradSync.replicas
+        a.prior_mean, a.prior_std, a.kl_upstream = pm, ps, _p(up)
+        need_dx = ctx.needs_input_grad[0]
+        dx = None
+        prev = (need_dx and in_link is not None and in_link.sign_out is not None and x_dtype == dtype
+                and in_link.act in (ops.ACT_NONE, ops.ACT_RELU))
+        if prev:
+            dx = _new(B, I, dtype, dev)
+            prev_gt = _new(B, I, dtype, dev)
+            prev_dbias = torch.empty(I, dtype=torch.float32, device=dev) if in_link.has_bias else None
+            a.prev_relu = int(in_link.act == ops.ACT_RELU)
+            a.prev_gp, a.prev_gp_ld, a.prev_gt, a.prev_gt_ld = dx.data_ptr(), _lib.ld(dx), prev_gt.data_ptr(), _lib.ld(prev_gt)
+            a.prev_sign_out, a.prev_dbias = in_link.sign_out.c(), _p(prev_dbias)
+        elif need_dx:
+            dx = _new(B, I, dtype, dev)
+            a.dx, a.dx_ld = dx.data_ptr(), _lib.ld(dx)
+        _lib.check(lib.ed2_flipout_fused_bwd(C.byref(a), _lib.stream_ptr()), "ed2_flipout_fused_bwd")
+        if prev:
+            in_link.record(dx, prev_gt, prev_dbias)
+        if out_link is not None:
+            out_link.dx = out_link.gt = None  # consumed (or not applicable): drop the references
+        if dx is not None and dx.dtype != x_dtype:
+            dx = dx.to(x_dtype)
+        return dx, dmu, drho, dbias, None, None, None, None, None, None, None, None, None, None, None
+
+
 # ------------------------------------------------------------------------------------------------- KL regulariser
 class NormalKL(torch.autograd.Function):
     """scale * sum KL(N(mu, softplus(rho)+1e-7) || N(m, s)) as a 0-dim fp32 tensor (regularizers.py:175-186)."""

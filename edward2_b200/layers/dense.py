@@ -243,18 +243,87 @@ class DenseFlipout(DenseReparameterization):
     y = act(x·mean + ((x∘S)·Delta)∘T + b), Delta = sigma∘eps, per-example sign tensors S [.., I] and T [.., O]."""
 
     def presample(self, after=None):
-        """No-op: the Flipout forward samples inside its own call."""
+        """Optional scheduling hint (fused bf16 path only): draw this call's mean / perturbation operands and the KL NOW on
+        a side stream, beside whatever the main stream is doing.  Same Philox stream as the un-hinted call."""
+        if not self.built or not _is_trainable(self.kernel_initializer) or self.compute_dtype != torch.bfloat16:
+            return
+        mean, rho = self._kernel_params()
+        if rho is None or "eps" in self._injected:
+            return
+        from .. import _lib
+
+        kl_scale, pm, ps = self._fused_kl_args()
+        dev = mean.device
+        I, O = mean.shape
+        if not hasattr(self, "_side_stream"):
+            self._side_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        mu_lp = _lib.empty_padded(I, O, self.compute_dtype, dev)
+        delta_lp = _lib.empty_padded(I, O, self.compute_dtype, dev)
+        kl64 = torch.zeros((), dtype=torch.float64, device=dev) if kl_scale != 0 else None
+        self._side_stream.wait_stream(main)
+        if after is not None and getattr(after, "_side_stream", None) is not None:
+            self._side_stream.wait_stream(after._side_stream)
+        with torch.cuda.stream(self._side_stream):
+            nz = self._noise("eps", S_KERNEL)
+            _lib.check(_lib.load().ed2_sample_normal_weights(
+                mean.data_ptr(), rho.data_ptr(), nz.c(), I, O, 1, delta_lp.data_ptr(), _lib.dt_of(delta_lp),
+                _lib.ld(delta_lp), mu_lp.data_ptr(), _lib.ld(mu_lp), None if kl64 is None else kl64.data_ptr(),
+                kl_scale, pm, ps, _lib.stream_ptr()), "ed2_sample_normal_weights")
+        self._presampled = (mu_lp, delta_lp, kl64, nz)
+
+    def feeds(self, consumer):
+        """Scheduling hint for stacked Flipout layers: this layer's output goes straight into `consumer` (another
+        DenseFlipout).  This layer's GEMM epilogue then also writes the consumer's x∘S — signs from the consumer's own
+        sign_input stream — and the consumer's dX epilogue runs this layer's output side (activation mask, sign_output,
+        bias gradient), so neither costs a pass over HBM (functional.FlipoutLink).  Results are unchanged; any other use
+        of the output falls back.  Returns `consumer` so chains read l1.feeds(l2).feeds(l3)."""
+        import weakref
+
+        self._consumer = weakref.ref(consumer) if consumer is not None else None
+        return consumer
+
+    def _next_sign(self, rows):
+        ref = getattr(self, "_consumer", None)
+        nxt = ref() if ref is not None else None
+        if (not isinstance(nxt, DenseFlipout) or not nxt.built or nxt.compute_dtype != self.compute_dtype
+                or "sign_input" in nxt._injected or nxt._kernel_params()[0].shape[0] != self.units):
+            return None
+        return nxt._noise("sign_input", S_SIGN_IN, per_example=rows)
 
     def call(self, inputs, training=None):
         mean, rho = self._kernel_params()
         if rho is None:  # dense.py:256-257: not a random variable -> parent behaviour
             return super().call(inputs)
+        in_link = getattr(inputs, "_ed2_flipout_link", None)
         x, lead = flatten_batch(inputs)
         bias = self._bias_value()
         kl_scale, pm, ps = self._fused_kl_args()
-        y, kl = F.FlipoutDense.apply(x, mean, rho, bias, self._act, self.compute_dtype, self._noise("eps", S_KERNEL),
-                                     self._noise("sign_input", S_SIGN_IN, per_example=x.shape[0]),
-                                     self._noise("sign_output", S_SIGN_OUT, per_example=x.shape[0]),
+        eps = self._noise("eps", S_KERNEL)
+        sign_in = self._noise("sign_input", S_SIGN_IN, per_example=x.shape[0])
+        sign_out = self._noise("sign_output", S_SIGN_OUT, per_example=x.shape[0])
+        pre = getattr(self, "_presampled", None)
+        self._presampled = None
+        if (eps.injected is None and not _is_trainable(self.bias_initializer)
+                and F.flipout_fusable(x, mean, self.compute_dtype, sign_in, sign_out)):
+            chain = len(lead) == 1
+            out_link = F.FlipoutLink() if chain else None
+            presampled = None
+            if pre is not None:
+                torch.cuda.current_stream().wait_stream(self._side_stream)
+                presampled, eps = pre[:3], pre[3]
+            y, kl = F.FlipoutDenseFused.apply(x, mean, rho, bias, self._act, eps, sign_in, sign_out, kl_scale, pm, ps,
+                                              in_link if chain else None, out_link,
+                                              self._next_sign(x.shape[0]) if chain else None, presampled)
+            if kl_scale != 0.0:
+                self._kl.set(kl, mean, rho)
+            if chain:
+                y._ed2_flipout_link = out_link
+                return y
+            return y.reshape(*lead, self.units)
+        if pre is not None:  # a hint that cannot be honoured on the two-GEMM path: wait for it, then draw as usual
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+        y, kl = F.FlipoutDense.apply(x, mean, rho, bias, self._act, self.compute_dtype, eps, sign_in, sign_out,
                                      kl_scale, pm, ps)
         if kl_scale != 0.0:
             self._kl.set(kl, mean, rho)

@@ -445,6 +445,64 @@ typedef struct {
 } ed2_flipout_bwd_args;
 int ed2_flipout_dense_bwd(const ed2_flipout_bwd_args* a, void* stream);
 
+/* Fused DenseFlipout (bf16, Philox signs): ONE tcgen05 launch with two TMEM accumulators computes
+ *   y = act( x·mu_lp + ((x∘S)·delta_lp) ∘ T + b )
+ * with T regenerated from Philox in the epilogue — the fp32 perturbation [B][O] and the sign tensors never exist in
+ * HBM (the call above writes and re-reads them).  mu_lp / delta_lp are drawn beforehand by
+ * ed2_sample_normal_weights(mode 1) (any stream; typically a side stream beside the previous layer's GEMM).
+ * Stacks: with next_xs != NULL the epilogue also writes y∘S_next — the NEXT Flipout layer's second operand, drawn from
+ * that layer's sign_in stream — so only the first layer of a stack runs a sign pass (xs_ready == 0). */
+typedef struct {
+  int batch, in_dim, out_dim;
+  int act;                                  /* ED2_ACT_NONE | ED2_ACT_RELU */
+  const void* x; int x_ld;                  /* [B][I] bf16 */
+  void* xs; int xs_ld;                      /* [B][I] bf16 x∘S: input when xs_ready, else written from sign_in */
+  int xs_ready;
+  ed2_noise sign_in; ed2_noise sign_out;    /* Philox streams (injected must be NULL) */
+  const void* mu_lp; int mu_ld;             /* [I][O] bf16 */
+  const void* delta_lp; int delta_ld;       /* [I][O] bf16 */
+  const float* bias;                        /* [O] or NULL; 16-byte aligned */
+  void* y; int y_ld;                        /* [B][O] bf16 */
+  void* next_xs; int next_xs_ld;            /* optional [B][O] bf16: y ∘ S_next */
+  ed2_noise next_sign_in;
+} ed2_flipout_fused_fwd_args;
+int ed2_flipout_fused_fwd(const ed2_flipout_fused_fwd_args* a, void* stream);
+
+/* Backward of the fused call.  gp = gy∘act'(y) and gt = gp∘T are either computed here from (gy, y) (premade == 0) or were
+ * already written by the CONSUMER layer's fused backward (premade == 1: gp / gt / dbias are inputs).
+ *   dmu  = xᵀ gp,  dDelta = (x∘S)ᵀ gt   -> finishing pass (eps regenerated, KL gradient) -> dmu, drho
+ *   dx   = gp·mu_lpᵀ + (gt·delta_lpᵀ) ∘ S                                  one dual-accumulator launch
+ * With a producer (prev_gp != NULL; this layer's x is the producer's output, ReLU when prev_relu): the dX epilogue
+ * writes prev_gp = dx∘1[x > 0] (or dx), prev_gt = prev_gp∘T_prev (the producer's sign_out stream) and accumulates the
+ * producer's bias gradient into prev_dbias (zeroed here), so the producer's backward runs with premade == 1. */
+typedef struct {
+  int batch, in_dim, out_dim;
+  int act;
+  int premade;
+  const void* gy; int gy_ld;
+  const void* y; int y_ld;
+  void* gp; int gp_ld;                       /* [B][O] bf16 */
+  void* gt; int gt_ld;                       /* [B][O] bf16 */
+  const void* x; int x_ld;
+  const void* xs; int xs_ld;
+  const void* mu_lp; int mu_ld;
+  const void* delta_lp; int delta_ld;
+  const float* mu; const float* rho; ed2_noise eps;
+  ed2_noise sign_in; ed2_noise sign_out;
+  float* dmu; float* drho; float* dbias;     /* dbias: output unless premade */
+  float kl_grad_scale; float prior_mean; float prior_std;
+  const double* kl_upstream;
+  void* dx; int dx_ld;                       /* [B][I] bf16, optional (no producer) */
+  int prev_relu;
+  void* prev_gp; int prev_gp_ld;             /* optional [B][I] bf16 */
+  void* prev_gt; int prev_gt_ld;
+  ed2_noise prev_sign_out;
+  float* prev_dbias;                         /* [I] or NULL */
+} ed2_flipout_fused_bwd_args;
+int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream);
+/* 1 when the fused calls accept this shape (batch > 128, in_dim and out_dim multiples of 8) */
+int ed2_flipout_fusable(int batch, int in_dim, int out_dim);
+
 /* ------------------------------------------------------------------------------------------------
  * SNGP head.
  * SpectralNormalization (edward2/tensorflow/layers/normalization.py:369-391;
