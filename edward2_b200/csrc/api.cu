@@ -630,7 +630,10 @@ int sign_side(const ed2_noise& n, int batch, SignSide* out, const char* what) {
 }  // namespace
 
 int ed2_flipout_fusable(int batch, int in_dim, int out_dim) {
-  return (gemm_flipout_fusable(batch, out_dim, in_dim) && gemm_flipout_fusable(batch, in_dim, out_dim)) ? 1 : 0;
+  // the three products: x·W [B x O, K = I], g·Wᵀ [B x I, K = O], xᵀ·g [I x O, K = B]; a 256-row pair tile needs a batch
+  // that fills it
+  return (batch > 128 && gemm_flipout_fusable(batch, out_dim, in_dim) && gemm_flipout_fusable(batch, in_dim, out_dim) &&
+          gemm_flipout_fusable(in_dim, out_dim, batch)) ? 1 : 0;
 }
 
 int ed2_flipout_fused_fwd(const ed2_flipout_fused_fwd_args* a, void* stream) {
@@ -674,15 +677,22 @@ int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream) {
     o.dbias = a->dbias;
     ED2_TRY(k_bwd_out(o, s));
   }
-  EpiParams e = epi_default();
-  e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
-  ED2_TRY(gemm_xtg(kBF16, a->x, a->x_ld, a->gp, a->gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
-  EpiParams e1 = epi_default();
-  e1.out = a->drho; e1.out_ld = a->out_dim; e1.out_dt = kF32;
-  ED2_TRY(gemm_xtg(kBF16, a->xs, a->xs_ld, a->gt, a->gt_ld, a->batch, a->in_dim, a->out_dim, e1, s));
-  // the finishing pass (CUDA cores) runs on the side stream beside the dX launch (tensor cores)
-  ForkJoin fj(s, want_dx);
-  int st = ED2_OK;
+  // both weight-gradient products in ONE launch, finished in its epilogue (eps regenerated, KL gradient added): the raw
+  // fp32 gradients are never written
+  {
+    FlipoutGemm w{};
+    w.mode = 1; w.major_a = kMajorMN; w.major_b = kMajorMN;
+    w.A0 = a->x; w.lda0 = a->x_ld; w.A1 = a->xs; w.lda1 = a->xs_ld;
+    w.B0 = a->gp; w.ldb0 = a->gp_ld; w.B1 = a->gt; w.ldb1 = a->gt_ld;
+    w.M = a->in_dim; w.N = a->out_dim; w.K = a->batch;
+    if (a->eps.injected != nullptr) return set_error(ED2_ERR_BAD_ARG, "flipout_fused_bwd: eps must be a Philox stream");
+    w.epi.sa.seed = a->eps.seed; w.epi.sa.stream = a->eps.stream;
+    w.epi.sa.step = reinterpret_cast<const unsigned long long*>(a->eps.step); w.epi.sa.on = 1;
+    w.epi.mu = a->mu; w.epi.rho = a->rho; w.epi.dmu = a->dmu; w.epi.drho = a->drho;
+    w.epi.klg = a->kl_grad_scale; w.epi.kl_upstream = a->kl_upstream;
+    w.epi.prior_mean = a->prior_mean; w.epi.prior_std = a->prior_std;
+    ED2_TRY(gemm_flipout(w, s));
+  }
   if (want_dx) {
     g.A0 = a->gp; g.lda0 = a->gp_ld; g.A1 = a->gt; g.lda1 = a->gt_ld;
     g.B0 = a->mu_lp; g.ldb0 = a->mu_ld; g.B1 = a->delta_lp; g.ldb1 = a->delta_ld; g.major_b = kMajorK;
@@ -695,14 +705,9 @@ int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream) {
     } else {
       g.out = a->dx; g.out_ld = a->dx_ld;
     }
-    st = gemm_flipout(g, s);
+    ED2_TRY(gemm_flipout(g, s));
   }
-  if (st == ED2_OK)
-    st = k_normal_grad_finish(a->dmu, a->drho, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
-                              a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
-                              true, fj.side());
-  fj.join();
-  return st;
+  return ED2_OK;
 }
 
 // ------------------------------------------------------------------------------------------ SNGP head

@@ -142,7 +142,7 @@ __global__ void philox_fill_kernel(float* out, long long n, uint64_t seed, uint6
     if (kKind == 0) philox_normal4(seed, stream, b, e);
     else if (kKind == 3) philox_normal4<true>(seed, stream, b, e);  // hardware-approximate Box-Muller (bf16 paths)
     else if (kKind == 1) philox_uniform4(seed, stream, b, e);
-    else philox_sign4(seed, stream, b, e);
+    else philox_sign4(seed, stream, static_cast<uint64_t>(b) << 2, e);
     const long long i = b << 2;
     const int valid = static_cast<int>(min(4LL, n - i));
     st4(out, kF32, i, valid, e);

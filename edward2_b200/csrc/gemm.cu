@@ -214,13 +214,13 @@ int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
   return dispatch_cfg<kMajorMN, kMajorMN>(g, bn, cg, ta, tb, to, stream);
 }
 
-bool gemm_flipout_fusable(int M, int N, int K) { return M > 128 && N % 8 == 0 && K % 8 == 0; }
+bool gemm_flipout_fusable(int M, int N, int K) { return M > 0 && N % 8 == 0 && K % 8 == 0; }
 
 namespace {
-template <int MB>
+template <int MA, int MB, int MODE>
 int launch_flipout(const FlipoutGemm& g, const CUtensorMap& ta0, const CUtensorMap& ta1, const CUtensorMap& tb0,
                    const CUtensorMap& tb1, const CUtensorMap& to, int out_tma, cudaStream_t stream) {
-  auto kern = tc::gemm_flipout_kernel<MB>;
+  auto kern = tc::gemm_flipout_kernel<MA, MB, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFoSmemBytes);
@@ -244,7 +244,12 @@ int launch_flipout(const FlipoutGemm& g, const CUtensorMap& ta0, const CUtensorM
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta0, ta1, tb0, tb1, to, g.M, g.N, g.K, g.out, g.out_ld, out_tma, g.epi);
+  // band height of the rasterisation (gemm_flipout.cuh: tile_coord_g): ~sqrt(clusters / 2) M-blocks, or one wave per
+  // band when the output is narrow
+  int group = 8;
+  if (nn * group < clusters) group = (clusters + nn - 1) / nn;
+  group = std::max(1, std::min(group, nm));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta0, ta1, tb0, tb1, to, g.M, g.N, g.K, g.out, g.out_ld, out_tma, group, g.epi);
   if (e != cudaSuccess) return set_error(ED2_ERR_CUDA, "flipout gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return ED2_OK;
@@ -253,9 +258,26 @@ int launch_flipout(const FlipoutGemm& g, const CUtensorMap& ta0, const CUtensorM
 
 int gemm_flipout(const FlipoutGemm& g, cudaStream_t stream) {
   if (!gemm_flipout_fusable(g.M, g.N, g.K))
-    return set_error(ED2_ERR_BAD_SHAPE, "flipout gemm: needs M > 128 and N, K multiples of 8 (M=%d N=%d K=%d)", g.M, g.N, g.K);
+    return set_error(ED2_ERR_BAD_SHAPE, "flipout gemm: needs N, K multiples of 8 (M=%d N=%d K=%d)", g.M, g.N, g.K);
   if (!tma_ok(g.A0, g.lda0, 2) || !tma_ok(g.A1, g.lda1, 2) || !tma_ok(g.B0, g.ldb0, 2) || !tma_ok(g.B1, g.ldb1, 2))
     return set_error(ED2_ERR_BAD_ARG, "flipout gemm: operands must be 16-byte aligned with a pitch that is a multiple of 8 bf16");
+  if (g.mode == 1) {
+    if (g.major_a != kMajorMN || g.major_b != kMajorMN) return set_error(ED2_ERR_BAD_ARG, "flipout gemm: weight-gradient mode takes MN-major operands");
+    if (g.epi.mu == nullptr || g.epi.rho == nullptr || g.epi.dmu == nullptr || g.epi.drho == nullptr)
+      return set_error(ED2_ERR_BAD_ARG, "flipout gemm: weight-gradient mode needs mu / rho / dmu / drho");
+    for (const void* p : {static_cast<const void*>(g.epi.mu), static_cast<const void*>(g.epi.rho),
+                          static_cast<const void*>(g.epi.dmu), static_cast<const void*>(g.epi.drho)})
+      if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) return set_error(ED2_ERR_BAD_ARG, "flipout gemm: mu / rho / dmu / drho must be 16-byte aligned");
+    CUtensorMap ta0, ta1, tb0, tb1, to;
+    std::memset(&to, 0, sizeof(to));
+    const bool ok = make_map(&ta0, g.A0, kBF16, g.K, g.M, g.lda0, tc::kBlockK, 64) &&
+                    make_map(&ta1, g.A1, kBF16, g.K, g.M, g.lda1, tc::kBlockK, 64) &&
+                    make_map(&tb0, g.B0, kBF16, g.K, g.N, g.ldb0, tc::kBlockK, 64) &&
+                    make_map(&tb1, g.B1, kBF16, g.K, g.N, g.ldb1, tc::kBlockK, 64);
+    if (!ok) return set_error(ED2_ERR_CUDA, "cuTensorMapEncodeTiled failed for a flipout GEMM operand");
+    return launch_flipout<kMajorMN, kMajorMN, 1>(g, ta0, ta1, tb0, tb1, to, 0, stream);
+  }
+  if (g.major_a != kMajorK) return set_error(ED2_ERR_BAD_ARG, "flipout gemm: the summed mode takes K-major A operands");
   if (g.out == nullptr && g.epi.out2 == nullptr && g.epi.col_sum == nullptr)
     return set_error(ED2_ERR_BAD_ARG, "flipout gemm: no output");
   if (g.epi.out2 != nullptr && (!tma_ok(g.epi.out2, g.epi.out2_ld, 2)))
@@ -281,8 +303,8 @@ int gemm_flipout(const FlipoutGemm& g, cudaStream_t stream) {
     if (!tma_ok(g.out, g.out_ld, 2)) return set_error(ED2_ERR_BAD_ARG, "flipout gemm: out must be 16-byte aligned, pitch % 8 == 0");
     if (make_map(&to, g.out, kBF16, g.M, g.N, g.out_ld, tc::kBlockM, 64)) out_tma = 1;
   }
-  if (g.major_b == kMajorK) return launch_flipout<kMajorK>(g, ta0, ta1, tb0, tb1, to, out_tma, stream);
-  return launch_flipout<kMajorMN>(g, ta0, ta1, tb0, tb1, to, out_tma, stream);
+  if (g.major_b == kMajorK) return launch_flipout<kMajorK, kMajorK, 0>(g, ta0, ta1, tb0, tb1, to, out_tma, stream);
+  return launch_flipout<kMajorK, kMajorMN, 0>(g, ta0, ta1, tb0, tb1, to, out_tma, stream);
 }
 
 }  // namespace ed2

@@ -44,6 +44,8 @@ struct FlipoutGemm {
   int M, N, K;
   void* out; int out_ld;  // bf16, optional when epi.out2 / epi.col_sum carry the result
   FlipoutEpi epi;
+  int major_a = kMajorK;
+  int mode = 0;           // 1: weight-gradient pair finished in the epilogue (epi.mu / rho / dmu / drho; A and B MN-major)
 };
 bool gemm_flipout_fusable(int M, int N, int K);
 int gemm_flipout(const FlipoutGemm& g, cudaStream_t stream);

@@ -112,6 +112,13 @@ struct FlipoutEpi {
   const void* mask_src; int mask_ld;  // bf16 [M][N]
   void* out2; int out2_ld;            // bf16 [M][N]
   float* col_sum;                     // [N], zero-initialised by the caller
+  // ---- weight-gradient mode (gemm_flipout.cuh kMode 1): sa carries the eps stream of the kernel posterior
+  //   dmu[m,n] = acc0 + klg (mu - prior_mean) / prior_std^2
+  //   drho[m,n] = (acc1 * eps[m,n] + klg (sigma / prior_std^2 - 1 / sigma)) * sigmoid(rho)
+  const float* mu; const float* rho;  // [M][N] fp32 contiguous
+  float* dmu; float* drho;            // [M][N] fp32 contiguous
+  float klg; const double* kl_upstream;
+  float prior_mean, prior_std;
 };
 
 }  // namespace ed2

@@ -36,23 +36,51 @@ __device__ __forceinline__ uint64_t sign_key(const SignSide& s) {
   return s.step != nullptr ? s.seed + __ldg(s.step) * 0x9E3779B97F4A7C15ull : s.seed;
 }
 
-// Raw Philox words of 16 consecutive sign elements of one row for one or two streams (idx % 4 == 0); the sign of
-// element j is +1 when bit 31 of word j is set (philox.cuh stream contract).  One straight-line section: the 4 (or 8)
-// independent 10-round chains interleave.
+// Grouped rasterisation with a run-time band height: consecutive tiles walk down `group` M-blocks before moving to
+// the next N-block.  The DRAM traffic of one wave of C concurrent tiles is (unique M-blocks x 256 + unique N-blocks x
+// 128) rows of K elements per product, minimal for a band ~ sqrt(C / 2) high (measured with the fixed 16-block band of
+// the generic kernel: 503 MB read for 134 MB of operands at 4096^3, L2 hit rate 69 %); the host picks the band.
+__device__ __forceinline__ TileCoord tile_coord_g(int t, int num_m, int num_n, int group) {
+  const int per_group = group * num_n;
+  const int g = t / per_group;
+  const int first_m = g * group;
+  const int gsize = min(group, num_m - first_m);
+  const int r = t - g * per_group;
+  TileCoord c;
+  c.m_blk = first_m + r % gsize;
+  c.n_blk = r / gsize;
+  return c;
+}
+
+// 64 consecutive sign bits of one row, starting at stream element idx (idx % 8 == 0), for one or two streams: bit j of
+// the result is 1 when element idx + j is +1 (philox.cuh: one bit per element, 128 elements per Philox block).  The two
+// blocks that can hold them are evaluated together (2 or 4 independent 10-round chains interleave).
+__device__ __forceinline__ uint64_t extract64(const uint32_t (&w)[8], uint32_t p) {
+  const uint32_t sh = p & 31u;
+  uint32_t a, b, c;
+  switch (p >> 5) {
+    case 0: a = w[0]; b = w[1]; c = w[2]; break;
+    case 1: a = w[1]; b = w[2]; c = w[3]; break;
+    case 2: a = w[2]; b = w[3]; c = w[4]; break;
+    default: a = w[3]; b = w[4]; c = w[5]; break;
+  }
+  const uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 template <bool kTwo>
-__device__ __forceinline__ void sign_words16(uint64_t key_a, uint64_t stream_a, long long idx_a, uint32_t (&wa)[16],
-                                             uint64_t key_b, uint64_t stream_b, long long idx_b, uint32_t (&wb)[16]) {
-  constexpr int kChains = kTwo ? 8 : 4;
+__device__ __forceinline__ void sign_bits64(uint64_t key_a, uint64_t stream_a, long long idx_a, uint64_t& bits_a,
+                                            uint64_t key_b, uint64_t stream_b, long long idx_b, uint64_t& bits_b) {
+  constexpr int kChains = kTwo ? 4 : 2;
   uint32_t x[kChains][4], k0[kTwo ? 2 : 1], k1[kTwo ? 2 : 1];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const uint64_t blk = static_cast<uint64_t>(idx_a >> 2) + b;
+  for (int b = 0; b < 2; ++b) {
+    const uint64_t blk = (static_cast<uint64_t>(idx_a) >> 7) + b;
     x[b][0] = static_cast<uint32_t>(blk); x[b][1] = static_cast<uint32_t>(blk >> 32);
     x[b][2] = static_cast<uint32_t>(stream_a); x[b][3] = static_cast<uint32_t>(stream_a >> 32);
     if constexpr (kTwo) {
-      const uint64_t blk2 = static_cast<uint64_t>(idx_b >> 2) + b;
-      x[4 + b][0] = static_cast<uint32_t>(blk2); x[4 + b][1] = static_cast<uint32_t>(blk2 >> 32);
-      x[4 + b][2] = static_cast<uint32_t>(stream_b); x[4 + b][3] = static_cast<uint32_t>(stream_b >> 32);
+      const uint64_t blk2 = (static_cast<uint64_t>(idx_b) >> 7) + b;
+      x[2 + b][0] = static_cast<uint32_t>(blk2); x[2 + b][1] = static_cast<uint32_t>(blk2 >> 32);
+      x[2 + b][2] = static_cast<uint32_t>(stream_b); x[2 + b][3] = static_cast<uint32_t>(stream_b >> 32);
     }
   }
   k0[0] = static_cast<uint32_t>(key_a); k1[0] = static_cast<uint32_t>(key_a >> 32);
@@ -60,29 +88,43 @@ __device__ __forceinline__ void sign_words16(uint64_t key_a, uint64_t stream_a, 
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 2; ++b) {
       philox_round(x[b], k0[0], k1[0]);
-      if constexpr (kTwo) philox_round(x[4 + b], k0[1], k1[1]);
+      if constexpr (kTwo) philox_round(x[2 + b], k0[1], k1[1]);
     }
     k0[0] += 0x9E3779B9u; k1[0] += 0xBB67AE85u;
     if constexpr (kTwo) { k0[1] += 0x9E3779B9u; k1[1] += 0xBB67AE85u; }
   }
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      wa[4 * b + i] = x[b][i];
-      if constexpr (kTwo) wb[4 * b + i] = x[4 + b][i];
-    }
+  {
+    const uint32_t w[8] = {x[0][0], x[0][1], x[0][2], x[0][3], x[1][0], x[1][1], x[1][2], x[1][3]};
+    bits_a = extract64(w, static_cast<uint32_t>(idx_a) & 127u);
+  }
+  if constexpr (kTwo) {
+    const uint32_t w[8] = {x[2][0], x[2][1], x[2][2], x[2][3], x[3][0], x[3][1], x[3][2], x[3][3]};
+    bits_b = extract64(w, static_cast<uint32_t>(idx_b) & 127u);
   }
 }
 
-template <int kMajorB>
+// bf16-path softplus (elementwise.cu: sigma_from_rho_fast — the finishing pass must see the forward's sigma)
+__device__ __forceinline__ float fo_sigma_from_rho_fast(float rho, float& e) {
+  e = __expf(fminf(rho, 80.f));
+  const float sp = e < 2.44140625e-4f ? e : __logf(1.f + e);
+  return (rho > 20.f ? rho : sp) + 1e-7f;
+}
+
+// kMode 0: the summed epilogue above.
+// kMode 1: the two WEIGHT-GRADIENT products of a Flipout layer in one launch, finished in the epilogue:
+//   acc0 = xᵀ·gp, acc1 = (x∘S)ᵀ·(gp∘T)   (A MN-major: the activations are read transposed by the TMA descriptors)
+//   dmu[i,o]  = acc0 + klg (mu - m) / s²
+//   drho[i,o] = (acc1 · eps[i,o] + klg (sigma / s² - 1 / sigma)) · sigmoid(rho)     eps regenerated from Philox
+//   — the arithmetic of grad_finish_lean_kernel, so the fp32 raw gradients are never written and re-read (24 B per
+//   weight) and the two products share one tile grid (512 tiles = 6.9 waves of 74 pairs instead of 2 x 3.46).
+template <int kMajorA, int kMajorB, int kMode>
 __global__ void __maxnreg__(168)
 gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                     const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ CUtensorMap tm_b1,
                     const __grid_constant__ CUtensorMap tm_out, int M, int N, int K, void* out, int out_ld, int out_tma,
-                    const __grid_constant__ FlipoutEpi fe) {
+                    int raster_group, const __grid_constant__ FlipoutEpi fe) {
   constexpr int kTileM = kBlockM * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -141,15 +183,23 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
     if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const TileCoord tc = tile_coord(t, num_m, num_n);
+        const TileCoord tc = tile_coord_g(t, num_m, num_n, raster_group);
         const int m0 = tc.m_blk * kTileM + cta_rank * kBlockM;
         const int n0 = tc.n_blk * kFoBlockN + cta_rank * (kFoBlockN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           const int k0 = kb * kBlockK;
           uint64_t* fb = &full_bar[stage];
-          ptx::tma_load_2d_pair(smem_a0 + stage * kFoABytes, &tm_a0, fb, k0, m0);
-          ptx::tma_load_2d_pair(smem_a1 + stage * kFoABytes, &tm_a1, fb, k0, m0);
+          if constexpr (kMajorA == kMajorK) {
+            ptx::tma_load_2d_pair(smem_a0 + stage * kFoABytes, &tm_a0, fb, k0, m0);
+            ptx::tma_load_2d_pair(smem_a1 + stage * kFoABytes, &tm_a1, fb, k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kBlockM / 64; ++i) {
+              ptx::tma_load_2d_pair(smem_a0 + stage * kFoABytes + i * (kBlockK * 128), &tm_a0, fb, m0 + i * 64, k0);
+              ptx::tma_load_2d_pair(smem_a1 + stage * kFoABytes + i * (kBlockK * 128), &tm_a1, fb, m0 + i * 64, k0);
+            }
+          }
           if constexpr (kMajorB == kMajorK) {
             ptx::tma_load_2d_pair(smem_b0 + stage * kFoBBytes, &tm_b0, fb, k0, n0);
             ptx::tma_load_2d_pair(smem_b1 + stage * kFoBBytes, &tm_b1, fb, k0, n0);
@@ -166,7 +216,7 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
   } else if (warp_idx == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
     if (is_leader && ptx::elect_one()) {
-      constexpr uint32_t idesc = make_idesc<kMajorK, kMajorB>(kTileM, kFoBlockN);
+      constexpr uint32_t idesc = make_idesc<kMajorA, kMajorB>(kTileM, kFoBlockN);
       uint32_t stage = 0, phase = 0;
       int iter = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
@@ -179,15 +229,15 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint64_t da0 = operand_desc<kMajorK>(ptx::smem_u32(smem_a0 + stage * kFoABytes));
-          const uint64_t da1 = operand_desc<kMajorK>(ptx::smem_u32(smem_a1 + stage * kFoABytes));
+          const uint64_t da0 = operand_desc<kMajorA>(ptx::smem_u32(smem_a0 + stage * kFoABytes));
+          const uint64_t da1 = operand_desc<kMajorA>(ptx::smem_u32(smem_a1 + stage * kFoABytes));
           const uint64_t db0 = operand_desc<kMajorB>(ptx::smem_u32(smem_b0 + stage * kFoBBytes));
           const uint64_t db1 = operand_desc<kMajorB>(ptx::smem_u32(smem_b1 + stage * kFoBBytes));
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-            ptx::umma<2, false>(tmem_d0, da0 + k * desc_k_step<kMajorK>(), db0 + k * desc_k_step<kMajorB>(), idesc, accum);
-            ptx::umma<2, false>(tmem_d1, da1 + k * desc_k_step<kMajorK>(), db1 + k * desc_k_step<kMajorB>(), idesc, accum);
+            ptx::umma<2, false>(tmem_d0, da0 + k * desc_k_step<kMajorA>(), db0 + k * desc_k_step<kMajorB>(), idesc, accum);
+            ptx::umma<2, false>(tmem_d1, da1 + k * desc_k_step<kMajorA>(), db1 + k * desc_k_step<kMajorB>(), idesc, accum);
           }
           ptx::umma_commit<2>(&empty_bar[stage]);
           if (kb == num_kb - 1) ptx::umma_commit<2>(&tmem_full_bar[acc]);
@@ -196,6 +246,70 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
       }
     }
   } else if (warp_idx >= 4) {
+   if constexpr (kMode == 1) {
+    // ------------------------------------------------------------------ weight-gradient epilogue (8 warps)
+    const int grp_id = (warp_idx - 4) >> 2;
+    const int ew = warp_idx & 3;
+    const int row = ew * 32 + lane;
+    const uint64_t key_e = sign_key(fe.sa);  // sa carries the eps stream in this mode
+    const float klg = fe.klg * (fe.kl_upstream != nullptr ? static_cast<float>(*fe.kl_upstream) : 1.f);
+    const float inv_s2 = 1.f / (fe.prior_std * fe.prior_std);
+    int iter = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
+      const TileCoord tcd = tile_coord_g(t, num_m, num_n, raster_group);
+      const int m0 = tcd.m_blk * kTileM + cta_rank * kBlockM;
+      const int n0 = tcd.n_blk * kFoBlockN;
+      const int m = m0 + row;
+      const bool m_ok = m < M;
+      const uint32_t acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const long long row_off = static_cast<long long>(m_ok ? m : 0) * N;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int tcol = grp_id * 64 + cc * 16;
+        const int nc = n0 + tcol;
+        // parameters of this chunk: in flight during the TMEM load and the Philox rounds
+        float4 mq[4], rq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = m_ok && nc + 4 * j < N;  // N % 4 == 0
+          mq[j] = ok ? __ldg(reinterpret_cast<const float4*>(fe.mu + row_off + nc) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rq[j] = ok ? __ldg(reinterpret_cast<const float4*>(fe.rho + row_off + nc) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t a0[16], a1[16];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * (2 * kFoBlockN) + tcol;
+        tmem_ld_32x16(taddr, a0);
+        tmem_ld_32x16(taddr + kFoBlockN, a1);
+        ptx::tmem_ld_wait();
+        if (cc == 3) {
+          ptx::tc_fence_before();
+          if (is_leader) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          else ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        }
+        float e[16], unused[16];
+        noise16<false>(key_e, fe.sa.stream, row_off + nc, e, 0, 0, 0, unused);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float mm[4] = {mq[j].x, mq[j].y, mq[j].z, mq[j].w}, rr[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
+          float om[4], orr[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float ex;
+            const float sigma = fo_sigma_from_rho_fast(rr[i], ex);
+            const float sgm = __fdividef(ex, 1.f + ex);
+            om[i] = __uint_as_float(a0[4 * j + i]) + klg * (mm[i] - fe.prior_mean) * inv_s2;
+            orr[i] = (__uint_as_float(a1[4 * j + i]) * e[4 * j + i] + klg * (sigma * inv_s2 - __fdividef(1.f, sigma))) * sgm;
+          }
+          if (m_ok && nc + 4 * j < N) {
+            reinterpret_cast<float4*>(fe.dmu + row_off + nc)[j] = make_float4(om[0], om[1], om[2], om[3]);
+            reinterpret_cast<float4*>(fe.drho + row_off + nc)[j] = make_float4(orr[0], orr[1], orr[2], orr[3]);
+          }
+        }
+      }
+    }
+   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int grp_id = (warp_idx - 4) >> 2;
     const int ew = warp_idx & 3;
@@ -209,7 +323,7 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
     const bool has_mask = fe.mask_src != nullptr;
     int iter = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
-      const TileCoord tcd = tile_coord(t, num_m, num_n);
+      const TileCoord tcd = tile_coord_g(t, num_m, num_n, raster_group);
       const int m0 = tcd.m_blk * kTileM + cta_rank * kBlockM;
       const int n0 = tcd.n_blk * kFoBlockN;
       const int m = m0 + row;
@@ -236,6 +350,10 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
         if (store_leader) ptx::tma_store_wait_read<0>();
         ptx::named_bar_sync(bar_id, 128);
       }
+      // this thread's 64 sign bits per stream (its row, the group's 64 columns): before the accumulator wait
+      uint64_t bits_a = 0, bits_b = 0;
+      if (has_sb) sign_bits64<true>(key_a, fe.sa.stream, nrow_a + ncol0, bits_a, key_b, fe.sb.stream, nrow_b + ncol0, bits_b);
+      else sign_bits64<false>(key_a, fe.sa.stream, nrow_a + ncol0, bits_a, 0, 0, 0, bits_b);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
 
@@ -243,6 +361,8 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
       for (int cc = 0; cc < 4; ++cc) {
         const int tcol = grp_id * 64 + cc * 16;
         const int nc = n0 + tcol;
+        const uint32_t na = ~static_cast<uint32_t>(bits_a >> (16 * cc));  // bit j set: element j is -1
+        const uint32_t nb = ~static_cast<uint32_t>(bits_b >> (16 * cc));
         uint32_t a0[16], a1[16];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * (2 * kFoBlockN) + tcol;
         tmem_ld_32x16(taddr, a0);
@@ -257,14 +377,10 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
         const bool full = n_valid == 16;
         const bool active = m_ok && n_valid > 0;
 
-        uint32_t wa[16], wb[16];
-        if (has_sb) sign_words16<true>(key_a, fe.sa.stream, nrow_a + nc, wa, key_b, fe.sb.stream, nrow_b + nc, wb);
-        else sign_words16<false>(key_a, fe.sa.stream, nrow_a + nc, wa, 0, 0, 0, wb);
-
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          v[j] = __uint_as_float(a0[j]) + __uint_as_float(a1[j] ^ (~wa[j] & 0x80000000u));
+          v[j] = __uint_as_float(a0[j]) + __uint_as_float(a1[j] ^ ((na >> j) << 31));
         if (fe.bias != nullptr) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -302,7 +418,7 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
           uint32_t p2[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            p2[j] = pk[j] ^ (((~wb[2 * j] >> 16) & 0x8000u) | (~wb[2 * j + 1] & 0x80000000u));
+            p2[j] = pk[j] ^ ((((nb >> (2 * j)) & 1u) << 15) | ((nb >> (2 * j + 1)) << 31));
           uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(fe.out2) + static_cast<long long>(m) * fe.out2_ld + nc);
           p[0] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
           if (full) p[1] = make_uint4(p2[4], p2[5], p2[6], p2[7]);
@@ -346,6 +462,7 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
       }
     }
     if (out_tma && store_leader) ptx::tma_store_wait_all<0>();
+   }
   }
 
   ptx::tc_fence_before();

@@ -10,7 +10,10 @@
 // the same epsilon without storing it (SURVEY.md §7 hard part 3).
 //   uniform  u = ((x >> 8) + 0.5) * 2^-24            in (0, 1) (fp32 rounds the top half of the range to 2^-24 steps)
 //   normal   Box-Muller on (x0,x1) -> (z0,z1), (x2,x3) -> (z2,z3)
-//   sign     +1 if bit 31 of x is set else -1        (P(+1) = 1/2)
+//   sign     ONE BIT per element: element i is bit (i % 32) of word (i / 32) % 4 of block i / 128; +1 if set else -1
+//            (P(+1) = 1/2).  A tile epilogue that regenerates the signs of 64 consecutive columns of a row needs one
+//            or two Philox blocks instead of sixteen (gemm_flipout.cuh), which is what keeps the short-K Flipout
+//            launches tensor-bound.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -103,11 +106,14 @@ __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t stream, 
   for (int i = 0; i < 4; ++i) u[i] = fminf(u32_to_uniform(x[i]), 0.99999994f);
 }
 
-__device__ __forceinline__ void philox_sign4(uint64_t seed, uint64_t stream, uint64_t block, float (&s)[4]) {
+// signs of the 4 consecutive elements idx .. idx+3 (idx % 4 == 0: they share one word of one block)
+__device__ __forceinline__ void philox_sign4(uint64_t seed, uint64_t stream, uint64_t idx, float (&s)[4]) {
   uint32_t x[4];
-  philox_block(seed, stream, block, x);
+  philox_block(seed, stream, idx >> 7, x);
+  const uint32_t wsel = static_cast<uint32_t>(idx >> 5) & 3u;
+  const uint32_t w = (wsel == 0 ? x[0] : wsel == 1 ? x[1] : wsel == 2 ? x[2] : x[3]) >> (static_cast<uint32_t>(idx) & 31u);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) s[i] = (x[i] >> 31) ? 1.0f : -1.0f;
+  for (int i = 0; i < 4; ++i) s[i] = ((w >> i) & 1u) ? 1.0f : -1.0f;
 }
 
 // Noise source for one tensor: either an injected array (parity tests inject the reference's draws) or a
@@ -150,7 +156,7 @@ __device__ __forceinline__ void noise4(const Noise& nz, long long idx, long long
   } else if constexpr (kKind == 0) {
     philox_normal4<kFast>(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
   } else {
-    philox_sign4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
+    philox_sign4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx), e);
   }
 }
 
@@ -160,7 +166,7 @@ __device__ __forceinline__ float noise1(const Noise& nz, long long idx) {
   if (nz.injected != nullptr) return __ldg(nz.injected + idx);
   float e[4];
   if constexpr (kKind == 0) philox_normal4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
-  else philox_sign4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx >> 2), e);
+  else philox_sign4(noise_key(nz), nz.stream, static_cast<uint64_t>(idx) & ~3ull, e);
   return e[idx & 3];
 }
 

@@ -470,7 +470,8 @@ int ed2_flipout_fused_fwd(const ed2_flipout_fused_fwd_args* a, void* stream);
 
 /* Backward of the fused call.  gp = gy∘act'(y) and gt = gp∘T are either computed here from (gy, y) (premade == 0) or were
  * already written by the CONSUMER layer's fused backward (premade == 1: gp / gt / dbias are inputs).
- *   dmu  = xᵀ gp,  dDelta = (x∘S)ᵀ gt   -> finishing pass (eps regenerated, KL gradient) -> dmu, drho
+ *   dmu  = xᵀ gp,  dDelta = (x∘S)ᵀ gt   one dual-accumulator launch whose epilogue regenerates eps and adds the KL
+ *                                        gradient -> dmu, drho (the raw fp32 products are never written)
  *   dx   = gp·mu_lpᵀ + (gt·delta_lpᵀ) ∘ S                                  one dual-accumulator launch
  * With a producer (prev_gp != NULL; this layer's x is the producer's output, ReLU when prev_relu): the dX epilogue
  * writes prev_gp = dx∘1[x > 0] (or dx), prev_gt = prev_gp∘T_prev (the producer's sign_out stream) and accumulates the
@@ -500,7 +501,7 @@ typedef struct {
   float* prev_dbias;                         /* [I] or NULL */
 } ed2_flipout_fused_bwd_args;
 int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream);
-/* 1 when the fused calls accept this shape (batch > 128, in_dim and out_dim multiples of 8) */
+/* 1 when the fused calls accept this shape (batch > 128, batch, in_dim and out_dim multiples of 8) */
 int ed2_flipout_fusable(int batch, int in_dim, int out_dim);
 
 /* ------------------------------------------------------------------------------------------------

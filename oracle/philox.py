@@ -77,8 +77,10 @@ def normal(seed, stream, n):
 
 
 def sign(seed, stream, n):
-    x = blocks(seed, stream, (n + 3) // 4).reshape(-1)[:n]
-    return np.where((x >> np.uint32(31)) != 0, 1.0, -1.0)
+    """One bit per element: element i = bit (i % 32) of word (i // 32) % 4 of block i // 128 (philox.cuh)."""
+    x = blocks(seed, stream, (n + 127) // 128).reshape(-1)  # uint32 words, 32 elements each
+    bits = (x[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & np.uint32(1)
+    return np.where(bits.reshape(-1)[:n] != 0, 1.0, -1.0)
 
 
 def global_rows(n_local_rows, row0=0, rows_per_group_local=0, rows_per_group_global=0):
