@@ -151,9 +151,17 @@ def wl_cfg4(ed, device, step_counter, rank, world):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             kls = [k for l in layers for k in l.losses]
+        # ... and so do the bf16 working copies of the kernels: each is cast on a side stream while the PREVIOUS layer's
+        # GEMM runs (queued right after that GEMM so its CTAs are placed first; the cast takes the SMs the GEMM grid
+        # leaves free)
+        start = torch.cuda.Event()
+        start.record(main)
+        layers[0].precast(ready=start)
         h = x
-        for l in layers:
+        for i, l in enumerate(layers):
             h = l(h)
+            if i + 1 < len(layers):
+                layers[i + 1].precast(after=layers[i] if i == 0 else None, ready=start)
         main.wait_stream(side)
         loss = F.SoftmaxCrossEntropy.apply(h, y, gb, *kls)
         F.backward(loss)

@@ -88,6 +88,13 @@ int launch_one(const GemmDesc& g, const CUtensorMap& ta, const CUtensorMap& tb, 
   int clusters = num_sms() / CG;
   if (g.max_ctas > 0) clusters = std::min(clusters, std::max(1, g.max_ctas / CG));
   clusters = std::min(clusters, num_tiles);
+  // the smallest grid that needs the same number of waves: 256 tiles on 74 SM pairs are 4 waves, and so they are on 64
+  // pairs — the 20 SMs left over run the side-stream kernels (weight casts, KL, the gradient exchange) that cannot
+  // co-reside with a persistent GEMM CTA
+  {
+    const int waves = (num_tiles + clusters - 1) / clusters;
+    clusters = (num_tiles + waves - 1) / waves;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(Cfg::kNumThreads);

@@ -162,18 +162,24 @@ class Rank1Dense(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernel, mu_r, rho_r, mu_s, rho_s, bias, act, ensemble_size, dtype, eps_r, eps_s,
                 additive=False, clip=(-10.0, 10.0), rho_b=None, eps_b=None, in_link=None, out_link=None,
-                next_fast=None):
+                next_fast=None, precast=None):
         """additive: (x + r) W + s (dense.py:1126-1127); clip: (min, max)_perturbation_value (dense.py:1108-1110);
         rho_b / eps_b: per-example sampled ensemble bias, `bias` being its mean (dense.py:1131-1139).
         in_link / out_link / next_fast: cross-layer fusion (Rank1Link); next_fast = (mu_r, rho_r, eps_r) of the layer
-        that will consume the output."""
+        that will consume the output.  precast: the compute-dtype copy of `kernel`, made ahead of time on a side stream
+        by layer.precast()."""
         lib = _lib.load()
         B, I = x.shape
         O = kernel.shape[1]
         dev = x.device
         E = ensemble_size
         xc = as_compute(x, dtype)
-        w_lp = kernel if dtype == torch.float32 else ops.cast(kernel, dtype)
+        if dtype == torch.float32:
+            w_lp = kernel
+        elif precast is not None and precast.dtype == dtype and precast.shape == kernel.shape:
+            w_lp = precast
+        else:
+            w_lp = ops.cast(kernel, dtype)
         need_grad = any(ctx.needs_input_grad)
         clip = (float(clip[0]), float(clip[1]))
         # fused epilogues (include/ed2b200.h: ed2_rank1_fusable): s is drawn inside the GEMM epilogue and regenerated
@@ -322,7 +328,7 @@ class Rank1Dense(torch.autograd.Function):
         if dx is not None and dx.dtype != x_dtype:
             dx = dx.to(x_dtype)
         return (dx, dw, dmu_r, drho_r, dmu_s, drho_s, dbias, None, None, None, None, None, None, None, drho_b, None,
-                None, None, None)
+                None, None, None, None)
 
 
 class GradSync:

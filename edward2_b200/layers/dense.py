@@ -443,6 +443,26 @@ class DenseRank1(Layer):
         self._consumer = weakref.ref(consumer) if consumer is not None else None
         return consumer
 
+    def precast(self, after=None, ready=None):
+        """Optional scheduling hint: make the compute-dtype copy of the kernel NOW on a side stream (it depends on the
+        parameter only), so the bandwidth-bound cast runs beside the previous layers' GEMMs instead of preceding this
+        layer's.  `after`: a layer whose precast must finish first.  `ready`: a CUDA event after which the parameter
+        holds its current value (e.g. recorded at the start of the step); without it the copy waits for everything
+        queued on the current stream so far.  The next `call` uses the copy."""
+        if not self.built or self.compute_dtype == torch.float32:
+            return
+        dev = self.kernel.device
+        if not hasattr(self, "_cast_stream"):
+            self._cast_stream = torch.cuda.Stream(device=dev)
+        if ready is not None:
+            self._cast_stream.wait_event(ready)
+        else:
+            self._cast_stream.wait_stream(torch.cuda.current_stream(dev))
+        if after is not None and getattr(after, "_cast_stream", None) is not None:
+            self._cast_stream.wait_stream(after._cast_stream)
+        with torch.cuda.stream(self._cast_stream):
+            self._precast = (ops.cast(self.kernel.detach(), self.compute_dtype), self.kernel._version)
+
     def _next_fast(self, per):
         ref = getattr(self, "_consumer", None)
         nxt = ref() if ref is not None else None
@@ -465,6 +485,12 @@ class DenseRank1(Layer):
         per = inputs.shape[0] // self.ensemble_size
         in_link = getattr(inputs, "_ed2_rank1_link", None)
         out_link = F.Rank1Link()
+        pre, self._precast = getattr(self, "_precast", None), None
+        w_pre = None
+        if pre is not None:
+            torch.cuda.current_stream().wait_stream(self._cast_stream)
+            if pre[1] == self.kernel._version:  # the parameter was not updated since the copy was made
+                w_pre = pre[0]
         y = F.Rank1Dense.apply(inputs, self.kernel, mu_r, rho_r, mu_s, rho_s, bias, self._act,
                                self.ensemble_size, self.compute_dtype,
                                self._noise("eps_alpha", S_R, per_example=per),
@@ -472,7 +498,7 @@ class DenseRank1(Layer):
                                self.use_additive_perturbation,
                                (self.min_perturbation_value, self.max_perturbation_value), rho_b,
                                self._noise("eps_bias", S_B, per_example=per) if rho_b is not None else None,
-                               in_link, out_link, self._next_fast(per))
+                               in_link, out_link, self._next_fast(per), w_pre)
         y._ed2_rank1_link = out_link
         return y
 
