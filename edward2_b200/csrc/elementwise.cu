@@ -289,13 +289,7 @@ __global__ void __launch_bounds__(kBlock) sample_bf16_lean_kernel(const float* _
     const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + i)), m1 = __ldg(reinterpret_cast<const float4*>(mu + i) + 1);
     const float4 r0 = __ldg(reinterpret_cast<const float4*>(rho + i)), r1 = __ldg(reinterpret_cast<const float4*>(rho + i) + 1);
     float e[8];
-    {
-      float t[4];
-      philox_normal4<true>(key, stream, static_cast<uint64_t>(i >> 2), t);
-      e[0] = t[0]; e[1] = t[1]; e[2] = t[2]; e[3] = t[3];
-      philox_normal4<true>(key, stream, static_cast<uint64_t>(i >> 2) + 1, t);
-      e[4] = t[0]; e[5] = t[1]; e[6] = t[2]; e[7] = t[3];
-    }
+    philox_normal8<true>(key, stream, static_cast<uint64_t>(i >> 3), e);  // i % 8 == 0: one Philox block
     const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
     const float rh[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
     float o[8];
@@ -607,11 +601,15 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return q;
 }
 __device__ __forceinline__ void normal8_fast(uint64_t key, uint64_t stream, long long idx, float (&e)[8]) {
-  float t[4];
-  philox_normal4<true>(key, stream, static_cast<uint64_t>(idx >> 2), t);
-  e[0] = t[0]; e[1] = t[1]; e[2] = t[2]; e[3] = t[3];
-  philox_normal4<true>(key, stream, static_cast<uint64_t>(idx >> 2) + 1, t);
-  e[4] = t[0]; e[5] = t[1]; e[6] = t[2]; e[7] = t[3];
+  if ((idx & 7) == 0) {
+    philox_normal8<true>(key, stream, static_cast<uint64_t>(idx >> 3), e);
+  } else {  // idx % 4 == 0: halves of two blocks
+    float t[4];
+    philox_normal4<true>(key, stream, static_cast<uint64_t>(idx >> 2), t);
+    e[0] = t[0]; e[1] = t[1]; e[2] = t[2]; e[3] = t[3];
+    philox_normal4<true>(key, stream, static_cast<uint64_t>(idx >> 2) + 1, t);
+    e[4] = t[0]; e[5] = t[1]; e[6] = t[2]; e[7] = t[3];
+  }
 }
 __device__ __forceinline__ uint64_t lean_key(uint64_t seed, const uint64_t* step) {
   return step != nullptr ? seed + __ldg(reinterpret_cast<const unsigned long long*>(step)) * 0x9E3779B97F4A7C15ull : seed;

@@ -45,22 +45,23 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "memory");
 }
 
-// eps of 16 consecutive columns of one row for up to two streams, as ONE straight-line section: the 4 (or 8)
-// independent 10-round Philox chains interleave.  idx = global_row * N + column (column % 4 == 0).
+// eps of 16 consecutive columns of one row for up to two streams, as ONE straight-line section: the 2 (or 4)
+// independent 10-round Philox chains interleave (8 normals per block, philox.cuh).  idx = global_row * N + column with
+// idx % 8 == 0 (N % 8 == 0, column % 16 == 0).
 template <bool kTwo>
 __device__ __forceinline__ void noise16(uint64_t key_a, uint64_t stream_a, long long idx_a, float (&ea)[16],
                                         uint64_t key_b, uint64_t stream_b, long long idx_b, float (&eb)[16]) {
-  constexpr int kChains = kTwo ? 8 : 4;
-  uint32_t x[kChains][4], k0[kChains > 4 ? 2 : 1], k1[kChains > 4 ? 2 : 1];
+  constexpr int kChains = kTwo ? 4 : 2;
+  uint32_t x[kChains][4], k0[kTwo ? 2 : 1], k1[kTwo ? 2 : 1];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const uint64_t blk = static_cast<uint64_t>(idx_a >> 2) + b;
+  for (int b = 0; b < 2; ++b) {
+    const uint64_t blk = static_cast<uint64_t>(idx_a >> 3) + b;
     x[b][0] = static_cast<uint32_t>(blk); x[b][1] = static_cast<uint32_t>(blk >> 32);
     x[b][2] = static_cast<uint32_t>(stream_a); x[b][3] = static_cast<uint32_t>(stream_a >> 32);
     if constexpr (kTwo) {
-      const uint64_t blk2 = static_cast<uint64_t>(idx_b >> 2) + b;
-      x[4 + b][0] = static_cast<uint32_t>(blk2); x[4 + b][1] = static_cast<uint32_t>(blk2 >> 32);
-      x[4 + b][2] = static_cast<uint32_t>(stream_b); x[4 + b][3] = static_cast<uint32_t>(stream_b >> 32);
+      const uint64_t blk2 = static_cast<uint64_t>(idx_b >> 3) + b;
+      x[2 + b][0] = static_cast<uint32_t>(blk2); x[2 + b][1] = static_cast<uint32_t>(blk2 >> 32);
+      x[2 + b][2] = static_cast<uint32_t>(stream_b); x[2 + b][3] = static_cast<uint32_t>(stream_b >> 32);
     }
   }
   k0[0] = static_cast<uint32_t>(key_a); k1[0] = static_cast<uint32_t>(key_a >> 32);
@@ -68,20 +69,19 @@ __device__ __forceinline__ void noise16(uint64_t key_a, uint64_t stream_a, long 
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 2; ++b) {
       philox_round(x[b], k0[0], k1[0]);
-      if constexpr (kTwo) philox_round(x[4 + b], k0[1], k1[1]);
+      if constexpr (kTwo) philox_round(x[2 + b], k0[1], k1[1]);
     }
     k0[0] += 0x9E3779B9u; k1[0] += 0xBB67AE85u;
     if constexpr (kTwo) { k0[1] += 0x9E3779B9u; k1[1] += 0xBB67AE85u; }
   }
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    box_muller_fast(x[b][0], x[b][1], ea[4 * b], ea[4 * b + 1]);
-    box_muller_fast(x[b][2], x[b][3], ea[4 * b + 2], ea[4 * b + 3]);
-    if constexpr (kTwo) {
-      box_muller_fast(x[4 + b][0], x[4 + b][1], eb[4 * b], eb[4 * b + 1]);
-      box_muller_fast(x[4 + b][2], x[4 + b][3], eb[4 * b + 2], eb[4 * b + 3]);
+  for (int b = 0; b < 2; ++b) {
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      box_muller_fast(x[b][w], ea[8 * b + 2 * w], ea[8 * b + 2 * w + 1]);
+      if constexpr (kTwo) box_muller_fast(x[2 + b][w], eb[8 * b + 2 * w], eb[8 * b + 2 * w + 1]);
     }
   }
 }

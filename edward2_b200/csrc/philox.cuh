@@ -9,7 +9,11 @@
 // so the value of element i depends only on (seed, stream, i): forward, backward and any tiling regenerate
 // the same epsilon without storing it (SURVEY.md §7 hard part 3).
 //   uniform  u = ((x >> 8) + 0.5) * 2^-24            in (0, 1) (fp32 rounds the top half of the range to 2^-24 steps)
-//   normal   Box-Muller on (x0,x1) -> (z0,z1), (x2,x3) -> (z2,z3)
+//   normal   EIGHT per block: element i lives in block i / 8; word w = (i / 2) % 4 of that block gives the pair
+//            (z_2w, z_2w+1) = Box-Muller(u0, u1) with the 16-bit uniforms u0 = (hi16(x_w) + 0.5) 2^-16,
+//            u1 = (lo16(x_w) + 0.5) 2^-16  (|z| <= 4.86; the radius takes 65536 values, the angle 65536).  The ten
+//            Philox rounds are ~3/4 of the instructions of a draw, so halving the blocks per normal is what the
+//            issue-bound consumers (GEMM epilogues that regenerate per-example noise, the sampling pass) pay for.
 //   sign     ONE BIT per element: element i is bit (i % 32) of word (i / 32) % 4 of block i / 128; +1 if set else -1
 //            (P(+1) = 1/2).  A tile epilogue that regenerates the signs of 64 consecutive columns of a row needs one
 //            or two Philox blocks instead of sixteen (gemm_flipout.cuh), which is what keeps the short-K Flipout
@@ -61,8 +65,13 @@ __host__ __device__ __forceinline__ float u32_to_uniform(uint32_t x) {
   return (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
 }
 
-__device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& z0, float& z1) {
-  const float u0 = u32_to_uniform(x0), u1 = u32_to_uniform(x1);
+__host__ __device__ __forceinline__ float u16_to_uniform(uint32_t h) {
+  return (static_cast<float>(h) + 0.5f) * 1.52587890625e-05f;  // 2^-16, exact in fp32
+}
+
+// one 32-bit word -> two normals (16-bit uniforms from its high and low halves)
+__device__ __forceinline__ void box_muller(uint32_t x, float& z0, float& z1) {
+  const float u0 = u16_to_uniform(x >> 16), u1 = u16_to_uniform(x & 0xFFFFu);
   float r;  // sqrt.approx (1 ulp): the IEEE sqrtf costs a fix-up sequence and a slow-path call per draw
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * logf(u0)));
   float s, c;
@@ -71,11 +80,10 @@ __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& z0, 
   z1 = r * s;
 }
 
-// Same Box-Muller pair from hardware approximations (lg2 / sin / cos): abs error ~1e-6 (up to ~1e-4 for the 1e-6 of
-// draws with u0 within 1e-6 of 1) -- used when the sampled tensor is rounded to bf16 anyway.  The angle is shifted to
-// (-pi, pi), where __sincosf is accurate: cos(2 pi u) = -cos(2 pi u - pi).
-__device__ __forceinline__ void box_muller_fast(uint32_t x0, uint32_t x1, float& z0, float& z1) {
-  const float u0 = u32_to_uniform(x0), u1 = u32_to_uniform(x1);
+// Same pair from hardware approximations (lg2 / sin / cos): abs error ~1e-6 -- used when the sampled tensor is rounded
+// to bf16 anyway.  The angle is shifted to (-pi, pi), where __sincosf is accurate: cos(2 pi u) = -cos(2 pi u - pi).
+__device__ __forceinline__ void box_muller_fast(uint32_t x, float& z0, float& z1) {
+  const float u0 = u16_to_uniform(x >> 16), u1 = u16_to_uniform(x & 0xFFFFu);
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u0)));
   float s, c;
@@ -84,16 +92,32 @@ __device__ __forceinline__ void box_muller_fast(uint32_t x0, uint32_t x1, float&
   z1 = -r * s;
 }
 
+// the 8 normals of Philox block `block8` (elements 8*block8 .. 8*block8+7)
 template <bool kFast = false>
-__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t block, float (&z)[4]) {
+__device__ __forceinline__ void philox_normal8(uint64_t seed, uint64_t stream, uint64_t block8, float (&z)[8]) {
   uint32_t x[4];
-  philox_block(seed, stream, block, x);
+  philox_block(seed, stream, block8, x);
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    if constexpr (kFast) box_muller_fast(x[w], z[2 * w], z[2 * w + 1]);
+    else box_muller(x[w], z[2 * w], z[2 * w + 1]);
+  }
+}
+
+// the 4 normals 4*block4 .. 4*block4+3: one half of Philox block block4 / 2 (callers that consume 8 consecutive
+// elements use philox_normal8 and pay for the block once)
+template <bool kFast = false>
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t block4, float (&z)[4]) {
+  uint32_t x[4];
+  philox_block(seed, stream, block4 >> 1, x);
+  const bool hi = (block4 & 1) != 0;
+  const uint32_t w0 = hi ? x[2] : x[0], w1 = hi ? x[3] : x[1];
   if constexpr (kFast) {
-    box_muller_fast(x[0], x[1], z[0], z[1]);
-    box_muller_fast(x[2], x[3], z[2], z[3]);
+    box_muller_fast(w0, z[0], z[1]);
+    box_muller_fast(w1, z[2], z[3]);
   } else {
-    box_muller(x[0], x[1], z[0], z[1]);
-    box_muller(x[2], x[3], z[2], z[3]);
+    box_muller(w0, z[0], z[1]);
+    box_muller(w1, z[2], z[3]);
   }
 }
 
@@ -101,8 +125,8 @@ __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t stream, 
   uint32_t x[4];
   philox_block(seed, stream, block, x);
 #pragma unroll
-  // (x >> 8) + 0.5 needs 25 bits above 2^23: the top value rounds to 2^24 in fp32, i.e. u == 1.  Box-Muller does not
-  // care (log 1 = 0, angle 2 pi); the uniform STREAM promises the open interval, so it is clamped to 1 - 2^-24.
+  // (x >> 8) + 0.5 needs 25 bits above 2^23: the top value rounds to 2^24 in fp32, i.e. u == 1; the uniform STREAM
+  // promises the open interval, so it is clamped to 1 - 2^-24.
   for (int i = 0; i < 4; ++i) u[i] = fminf(u32_to_uniform(x[i]), 0.99999994f);
 }
 

@@ -66,13 +66,13 @@ def uniform(seed, stream, n):
 
 
 def normal(seed, stream, n):
-    """Box-Muller on (x0,x1)->(z0,z1), (x2,x3)->(z2,z3) of each block (float64 evaluation of the fp32 recipe)."""
-    x = blocks(seed, stream, (n + 3) // 4)
-    u = _u32_to_uniform(x)
-    r0 = np.sqrt(-2.0 * np.log(u[:, 0]))
-    r1 = np.sqrt(-2.0 * np.log(u[:, 2]))
-    z = np.stack([r0 * np.cos(2 * np.pi * u[:, 1]), r0 * np.sin(2 * np.pi * u[:, 1]),
-                  r1 * np.cos(2 * np.pi * u[:, 3]), r1 * np.sin(2 * np.pi * u[:, 3])], axis=-1)
+    """Eight normals per block (philox.cuh): word w of block i // 8 gives (z_2w, z_2w+1) = Box-Muller(u0, u1) with the
+    16-bit uniforms u0 = (hi16 + 0.5) / 65536, u1 = (lo16 + 0.5) / 65536 (float64 evaluation of the fp32 recipe)."""
+    x = blocks(seed, stream, (n + 7) // 8).reshape(-1)
+    u0 = ((x >> np.uint32(16)).astype(np.float64) + 0.5) * 2.0 ** -16
+    u1 = ((x & np.uint32(0xFFFF)).astype(np.float64) + 0.5) * 2.0 ** -16
+    r = np.sqrt(-2.0 * np.log(u0))
+    z = np.stack([r * np.cos(2 * np.pi * u1), r * np.sin(2 * np.pi * u1)], axis=-1)
     return z.reshape(-1)[:n]
 
 
