@@ -190,6 +190,11 @@ class FlipoutFusedBwd(C.Structure):
     ]
 
 
+class ConvGeometry(C.Structure):
+    _fields_ = [("batch", _i), ("height", _i), ("width", _i), ("channels", _i),
+                ("kh", _i), ("kw", _i), ("sh", _i), ("sw", _i), ("same", _i)]
+
+
 # name -> (restype, argtypes); every symbol include/ed2b200.h declares
 SIGNATURES = {
     "ed2_version": (C.c_char_p, []),
@@ -234,6 +239,15 @@ SIGNATURES = {
     "ed2_flipout_fused_fwd": (_i, [C.POINTER(FlipoutFusedFwd), _vp]),
     "ed2_flipout_fused_bwd": (_i, [C.POINTER(FlipoutFusedBwd), _vp]),
     "ed2_flipout_fusable": (_i, [_i, _i, _i]),
+    "ed2_conv_out_size": (_i, [C.POINTER(ConvGeometry), C.POINTER(_i), C.POINTER(_i)]),
+    "ed2_im2col": (_i, [C.POINTER(ConvGeometry), _vp, _i, _vp, _ll, _vp]),
+    "ed2_col2im": (_i, [C.POINTER(ConvGeometry), _vp, _i, _ll, _vp, _i, _vp]),
+    "ed2_expand_table": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ed2_expand_table_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ed2_rank1_factors": (_i, [_vp, _vp, Noise, _i, _i, _i, _f, _f, _vp, _vp]),
+    "ed2_rank1_factors_bwd": (_i, [_vp, _vp, _vp, Noise, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
+    "ed2_noise_table": (_i, [_i, Noise, _vp, _i, _ll, _ll, _ll, _vp]),
+    "ed2_normal_grad_finish2": (_i, [_vp, _vp, _vp, _vp, Noise, _ll, _f, _vp, _f, _f, _vp, _vp, _i, _vp]),
     "ed2_spectral_norm_update": (_i, [_vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "ed2_input_normalize": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _vp, _f, _i, _f, _vp]),
     "ed2_layernorm_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _f, _vp, _i, _i, _vp, _vp, _vp]),

@@ -710,6 +710,62 @@ int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream) {
   return ED2_OK;
 }
 
+// ------------------------------------------------------------------------------------------ Conv2D support
+namespace {
+ConvArgs conv_args(const ed2_conv_geometry* g) {
+  return ConvArgs{g->batch, g->height, g->width, g->channels, g->kh, g->kw, g->sh, g->sw, g->same};
+}
+}  // namespace
+
+int ed2_conv_out_size(const ed2_conv_geometry* g, int* out_h, int* out_w) {
+  if (g == nullptr || out_h == nullptr || out_w == nullptr) return set_error(ED2_ERR_BAD_ARG, "conv_out_size: null argument");
+  return k_conv_out_size(conv_args(g), out_h, out_w);
+}
+int ed2_im2col(const ed2_conv_geometry* g, const void* x, int dtype, void* cols, long long cols_ld, void* stream) {
+  ED2_TRY(check_dt(dtype));
+  return k_im2col(conv_args(g), x, dtype, cols, cols_ld, S(stream));
+}
+int ed2_col2im(const ed2_conv_geometry* g, const void* dcols, int dtype, long long cols_ld, void* dx, int dx_dtype,
+               void* stream) {
+  ED2_TRY(check_dt(dtype));
+  ED2_TRY(check_dt(dx_dtype));
+  return k_col2im(conv_args(g), dcols, dtype, cols_ld, dx, dx_dtype, S(stream));
+}
+int ed2_expand_table(const float* src, float* out, int batch, int channels, int rows_per_entry, int reps, void* stream) {
+  return k_expand_table(src, out, batch, channels, rows_per_entry, reps, S(stream));
+}
+int ed2_expand_table_bwd(const float* dout, float* dsrc, int batch, int channels, int rows_per_entry, int reps, void* stream) {
+  return k_expand_table_bwd(dout, dsrc, batch, channels, rows_per_entry, reps, S(stream));
+}
+int ed2_rank1_factors(const float* mu, const float* rho, ed2_noise eps, int batch, int ensemble_size, int channels,
+                      float clip_lo, float clip_hi, float* f, void* stream) {
+  if (ensemble_size <= 0 || batch % ensemble_size != 0)
+    return set_error(ED2_ERR_BAD_SHAPE, "batch %d is not divisible by ensemble_size %d", batch, ensemble_size);
+  FastOpts fo;
+  fo.clip_lo = clip_lo; fo.clip_hi = clip_hi;
+  return k_scale_rows(nullptr, kF32, 0, batch, channels, batch / ensemble_size, rho != nullptr ? 1 : 0, mu, rho, N(eps), nullptr,
+                      0, f, channels, S(stream), fo);
+}
+int ed2_rank1_factors_bwd(const float* df, const float* mu, const float* rho, ed2_noise eps, int batch, int ensemble_size,
+                          int channels, float clip_lo, float clip_hi, float* dmu, float* drho, void* stream) {
+  if (ensemble_size <= 0 || batch % ensemble_size != 0)
+    return set_error(ED2_ERR_BAD_SHAPE, "batch %d is not divisible by ensemble_size %d", batch, ensemble_size);
+  return k_rank1_factor_bwd(df, mu, rho, N(eps), ensemble_size, batch / ensemble_size, channels, clip_lo, clip_hi, dmu, drho,
+                            S(stream));
+}
+int ed2_noise_table(int kind, ed2_noise nz, void* out, int dtype, long long ld, long long rows, long long cols, void* stream) {
+  ED2_TRY(check_dt(dtype));
+  if (kind != 0 && kind != 1) return set_error(ED2_ERR_BAD_ARG, "noise_table: kind must be 0 (normal) or 1 (sign)");
+  if (nz.injected != nullptr) return set_error(ED2_ERR_BAD_ARG, "noise_table: the descriptor holds injected values already");
+  return k_fill_noise(kind, N(nz), out, dtype, ld, rows, cols, S(stream));
+}
+int ed2_normal_grad_finish2(const float* d_mean, const float* d_pert, const float* mu, const float* rho, ed2_noise eps,
+                            long long n, float kl_grad_scale, const double* kl_upstream, float prior_mean, float prior_std,
+                            float* dmu, float* drho, int fast, void* stream) {
+  return k_normal_grad_finish(d_mean, d_pert, mu, rho, N(eps), n, kl_grad_scale, kl_upstream, Prior{prior_mean, prior_std},
+                              dmu, drho, fast != 0, S(stream));
+}
+
 // ------------------------------------------------------------------------------------------ SNGP head
 int ed2_spectral_norm_update(const float* w, int in_dim, int out_dim, float* u, float* v, int iterations,
                              float norm_multiplier, int mode, int update_uv, float* w_out, void* w_out_lp, int w_lp_ld,

@@ -1,0 +1,247 @@
+// Conv2D stochastic-weight layers (edward2/tensorflow/layers/convolutional.py:32,167,560,2056) on the dense hot path.
+//
+// In every variant the per-example factors are vectors over CHANNELS, broadcast over the spatial axes
+// (Flipout signs [B,1,1,C] :235-249, BatchEnsemble alpha/gamma :681-699, rank-1 r/s :1976-1989).  A convolution
+// restated on the patch matrix  cols[(b,ho,wo), (i,j,c)] = x[b, ho*sh+i-pt, wo*sw+j-pl, c]  is therefore a DENSE
+// BatchEnsemble-style product with one "member" per example:  y = act((cols ∘ tile(f_in[b])) W ∘ f_out[b] + bias[b])
+// with W = kernel reshaped [kh*kw*Cin, Cout] — exactly what ed2_be_dense_fwd/_bwd, ed2_reparam_dense_* compute on the
+// tcgen05 GEMM with rows-per-member = Ho*Wo.  This file holds what the dense path lacks: the patch gather (im2col), its
+// adjoint (col2im, gather form: no atomics), the expansion of per-member / per-example channel tables to the patch
+// layout and its adjoint, and the rank-1 factor table with its gradient.  NHWC ("channels_last"), dilation 1.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "gemm_epilogue.h"
+#include "kernels.h"
+#include "philox.cuh"
+#include "status.h"
+
+namespace ed2 {
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ float ldv(const void* p, int dt, long long i) {
+  return dt == kBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void stv(void* p, int dt, long long i, float v) {
+  if (dt == kBF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+
+struct ConvGeom {
+  int B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo;
+};
+
+// One thread per (patch row m, kernel tap t, channel vector): kVec channels (16 bytes) moved as one vector, zero-filled
+// outside the image.  Consecutive threads walk the channels of one tap, then the taps of one patch: reads and writes
+// are both contiguous runs of C elements.
+template <int kVec, typename V>
+__global__ void __launch_bounds__(kBlock) im2col_vec_kernel(const V* __restrict__ x, V* __restrict__ cols, long long cols_ldv,
+                                                           ConvGeom g) {
+  const int cv = g.C / kVec;
+  const long long per_row = static_cast<long long>(g.kh) * g.kw * cv;
+  const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * per_row;
+  for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < total; idx += (long long)gridDim.x * kBlock) {
+    const long long m = idx / per_row;
+    const int rem = static_cast<int>(idx - m * per_row);
+    const int t = rem / cv, c = rem - t * cv;
+    const int i = t / g.kw, j = t - i * g.kw;
+    const int wo = static_cast<int>(m % g.Wo);
+    const long long bh = m / g.Wo;
+    const int ho = static_cast<int>(bh % g.Ho), b = static_cast<int>(bh / g.Ho);
+    const int h = ho * g.sh + i - g.pt, w = wo * g.sw + j - g.pl;
+    V v{};
+    if (h >= 0 && h < g.H && w >= 0 && w < g.W) v = __ldg(x + ((static_cast<long long>(b) * g.H + h) * g.W + w) * cv + c);
+    cols[m * cols_ldv + static_cast<long long>(t) * cv + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) im2col_kernel(const void* __restrict__ x, int dt, void* __restrict__ cols,
+                                                       long long cols_ld, ConvGeom g) {
+  const long long per_row = static_cast<long long>(g.kh) * g.kw * g.C;
+  const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * per_row;
+  for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < total; idx += (long long)gridDim.x * kBlock) {
+    const long long m = idx / per_row;
+    const int rem = static_cast<int>(idx - m * per_row);
+    const int t = rem / g.C, c = rem - t * g.C;
+    const int i = t / g.kw, j = t - i * g.kw;
+    const int wo = static_cast<int>(m % g.Wo);
+    const long long bh = m / g.Wo;
+    const int ho = static_cast<int>(bh % g.Ho), b = static_cast<int>(bh / g.Ho);
+    const int h = ho * g.sh + i - g.pt, w = wo * g.sw + j - g.pl;
+    float v = 0.f;
+    if (h >= 0 && h < g.H && w >= 0 && w < g.W) v = ldv(x, dt, ((static_cast<long long>(b) * g.H + h) * g.W + w) * g.C + c);
+    stv(cols, dt, m * cols_ld + rem, v);
+  }
+}
+
+// Adjoint of im2col in gather form: dx[b,h,w,c] = sum over the taps (i,j) whose patch (ho,wo) covers (h,w) of
+// dcols[(b,ho,wo), (i,j,c)] — fp32 accumulation, every output element written once, no atomics.
+__global__ void __launch_bounds__(kBlock) col2im_kernel(const void* __restrict__ dcols, int dt, long long cols_ld,
+                                                       void* __restrict__ dx, int dx_dt, ConvGeom g) {
+  const long long total = static_cast<long long>(g.B) * g.H * g.W * g.C;
+  for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < total; idx += (long long)gridDim.x * kBlock) {
+    const int c = static_cast<int>(idx % g.C);
+    long long r = idx / g.C;
+    const int w = static_cast<int>(r % g.W);
+    r /= g.W;
+    const int h = static_cast<int>(r % g.H), b = static_cast<int>(r / g.H);
+    float acc = 0.f;
+    for (int i = 0; i < g.kh; ++i) {
+      const int hh = h + g.pt - i;
+      if (hh < 0 || hh % g.sh != 0) continue;
+      const int ho = hh / g.sh;
+      if (ho >= g.Ho) continue;
+      for (int j = 0; j < g.kw; ++j) {
+        const int ww = w + g.pl - j;
+        if (ww < 0 || ww % g.sw != 0) continue;
+        const int wo = ww / g.sw;
+        if (wo >= g.Wo) continue;
+        const long long m = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
+        acc += ldv(dcols, dt, m * cols_ld + (static_cast<long long>(i) * g.kw + j) * g.C + c);
+      }
+    }
+    stv(dx, dx_dt, idx, acc);
+  }
+}
+
+// out[b][t*C + c] = src[b / rows_per_entry][c], t < reps   (per-member or per-example channel table -> patch layout)
+__global__ void expand_table_kernel(const float* __restrict__ src, float* __restrict__ out, int B, int C, int rows_per_entry,
+                                    int reps) {
+  const long long total = static_cast<long long>(B) * reps * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    const int b = static_cast<int>(idx / (static_cast<long long>(reps) * C));
+    out[idx] = __ldg(src + static_cast<long long>(b / rows_per_entry) * C + c);
+  }
+}
+// adjoint: dsrc[e][c] = sum_{b in entry e} sum_t dout[b][t*C + c]   (one thread per (e, c); the tables are tiny)
+__global__ void expand_table_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dsrc, int entries, int C,
+                                        int rows_per_entry, int reps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= entries * C) return;
+  const int e = idx / C, c = idx - e * C;
+  float acc = 0.f;
+  for (int b = e * rows_per_entry; b < (e + 1) * rows_per_entry; ++b)
+    for (int t = 0; t < reps; ++t) acc += dout[(static_cast<long long>(b) * reps + t) * C + c];
+  dsrc[idx] = acc;
+}
+
+// gradient of the rank-1 factor table f[b][c] = clip(mu[e][c] + sigma[e][c] * eps[b][c], lo, hi), e = b / n:
+//   dmu[e][c] = sum_b df * 1[unclipped];  drho[e][c] = sum_b df * 1[unclipped] * eps * sigmoid(rho)
+__global__ void rank1_factor_bwd_kernel(const float* __restrict__ df, const float* __restrict__ mu, const float* __restrict__ rho,
+                                        Noise eps, int E, int n, int C, float lo, float hi, float* __restrict__ dmu,
+                                        float* __restrict__ drho) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= E * C) return;
+  const int e = idx / C, c = idx - e * C;
+  const float m = mu[idx];
+  const float rh = rho != nullptr ? rho[idx] : 0.f;
+  const float sigma = rho != nullptr ? (rh > 20.f ? rh : log1pf(expf(rh))) + 1e-7f : 0.f;
+  const float sgm = 1.f / (1.f + expf(-rh));
+  float am = 0.f, ar = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const long long b = static_cast<long long>(e) * n + i;
+    const float ev = rho != nullptr ? noise1<0>(eps, noise_idx(eps, b, C, c)) : 0.f;
+    const float raw = fmaf(sigma, ev, m);
+    const float pass = (raw < lo || raw > hi) ? 0.f : 1.f;
+    const float d = df[b * C + c] * pass;
+    am += d;
+    ar += d * ev;
+  }
+  dmu[idx] = am;
+  if (drho != nullptr) drho[idx] = ar * sgm;
+}
+
+int grid_for(long long work) {
+  long long g = (work + kBlock - 1) / kBlock;
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(g, 148 * 16)));
+}
+
+int geom(const ConvArgs& a, ConvGeom* g) {
+  if (a.batch <= 0 || a.height <= 0 || a.width <= 0 || a.channels <= 0 || a.kh <= 0 || a.kw <= 0 || a.sh <= 0 || a.sw <= 0)
+    return set_error(ED2_ERR_BAD_SHAPE, "conv: non-positive dimension");
+  auto out = [](int n, int k, int s, int same, int* o, int* p0) {
+    if (!same) { *o = (n - k) / s + 1; *p0 = 0; return; }
+    *o = (n + s - 1) / s;  // TF 'SAME': extra padding goes to the bottom / right
+    const int total = std::max((*o - 1) * s + k - n, 0);
+    *p0 = total / 2;
+  };
+  g->B = a.batch; g->H = a.height; g->W = a.width; g->C = a.channels; g->kh = a.kh; g->kw = a.kw; g->sh = a.sh; g->sw = a.sw;
+  out(a.height, a.kh, a.sh, a.same, &g->Ho, &g->pt);
+  out(a.width, a.kw, a.sw, a.same, &g->Wo, &g->pl);
+  if (g->Ho <= 0 || g->Wo <= 0) return set_error(ED2_ERR_BAD_SHAPE, "conv: kernel larger than the 'valid' input");
+  return ED2_OK;
+}
+
+}  // namespace
+
+int k_conv_out_size(const ConvArgs& a, int* ho, int* wo) {
+  ConvGeom g;
+  const int st = geom(a, &g);
+  if (st != ED2_OK) return st;
+  *ho = g.Ho; *wo = g.Wo;
+  return ED2_OK;
+}
+
+int k_im2col(const ConvArgs& a, const void* x, int dt, void* cols, long long cols_ld, cudaStream_t s) {
+  ConvGeom g;
+  const int st = geom(a, &g);
+  if (st != ED2_OK) return st;
+  const long long K = static_cast<long long>(g.kh) * g.kw * g.C;
+  if (cols_ld < K) return set_error(ED2_ERR_BAD_ARG, "im2col: cols_ld %lld < kh*kw*C %lld", cols_ld, K);
+  const long long rows = static_cast<long long>(g.B) * g.Ho * g.Wo;
+  const int vec = dt == kBF16 ? 8 : 4;
+  const bool aligned = g.C % vec == 0 && cols_ld % vec == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(cols) & 15) == 0;
+  if (aligned) {
+    const long long work = rows * g.kh * g.kw * (g.C / vec);
+    if (dt == kBF16)
+      im2col_vec_kernel<8, uint4><<<grid_for(work), kBlock, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(cols), cols_ld / 8, g);
+    else
+      im2col_vec_kernel<4, float4><<<grid_for(work), kBlock, 0, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(cols), cols_ld / 4, g);
+  } else {
+    im2col_kernel<<<grid_for(rows * K), kBlock, 0, s>>>(x, dt, cols, cols_ld, g);
+  }
+  count_launch();
+  return check_launch("im2col");
+}
+
+int k_col2im(const ConvArgs& a, const void* dcols, int dt, long long cols_ld, void* dx, int dx_dt, cudaStream_t s) {
+  ConvGeom g;
+  const int st = geom(a, &g);
+  if (st != ED2_OK) return st;
+  const long long total = static_cast<long long>(g.B) * g.H * g.W * g.C;
+  col2im_kernel<<<grid_for(total), kBlock, 0, s>>>(dcols, dt, cols_ld, dx, dx_dt, g);
+  count_launch();
+  return check_launch("col2im");
+}
+
+int k_expand_table(const float* src, float* out, int B, int C, int rows_per_entry, int reps, cudaStream_t s) {
+  if (B <= 0 || C <= 0 || rows_per_entry <= 0 || reps <= 0 || B % rows_per_entry != 0)
+    return set_error(ED2_ERR_BAD_SHAPE, "expand_table: B=%d rows_per_entry=%d reps=%d C=%d", B, rows_per_entry, reps, C);
+  expand_table_kernel<<<grid_for(static_cast<long long>(B) * reps * C), kBlock, 0, s>>>(src, out, B, C, rows_per_entry, reps);
+  count_launch();
+  return check_launch("expand_table");
+}
+
+int k_expand_table_bwd(const float* dout, float* dsrc, int B, int C, int rows_per_entry, int reps, cudaStream_t s) {
+  if (B <= 0 || C <= 0 || rows_per_entry <= 0 || reps <= 0 || B % rows_per_entry != 0)
+    return set_error(ED2_ERR_BAD_SHAPE, "expand_table_bwd: B=%d rows_per_entry=%d reps=%d C=%d", B, rows_per_entry, reps, C);
+  const int entries = B / rows_per_entry;
+  expand_table_bwd_kernel<<<(entries * C + kBlock - 1) / kBlock, kBlock, 0, s>>>(dout, dsrc, entries, C, rows_per_entry, reps);
+  count_launch();
+  return check_launch("expand_table_bwd");
+}
+
+int k_rank1_factor_bwd(const float* df, const float* mu, const float* rho, Noise eps, int E, int n, int C, float lo, float hi,
+                       float* dmu, float* drho, cudaStream_t s) {
+  if (E <= 0 || n <= 0 || C <= 0) return set_error(ED2_ERR_BAD_SHAPE, "rank1_factor_bwd: empty");
+  rank1_factor_bwd_kernel<<<(E * C + kBlock - 1) / kBlock, kBlock, 0, s>>>(df, mu, rho, eps, E, n, C, lo, hi, dmu, drho);
+  count_launch();
+  return check_launch("rank1_factor_bwd");
+}
+
+}  // namespace ed2

@@ -167,4 +167,22 @@ int k_peer_gather_f32(const PeerExchange& x, float* out, cudaStream_t s);
 int k_peer_grad_finish(const PeerExchange& x, const float* mu, const float* rho, Noise eps, float kl_grad_scale,
                        const double* kl_upstream, Prior p, float* dmu, float* drho, float* small_out, bool fast,
                        int blocks_per_sm, cudaStream_t s);
+// ---- Conv2D variants on the dense path (conv.cu): NHWC, dilation 1, padding 'valid' (same = 0) or TF 'SAME' (same = 1)
+struct ConvArgs {
+  int batch, height, width, channels;
+  int kh, kw, sh, sw;
+  int same;
+};
+int k_conv_out_size(const ConvArgs& a, int* ho, int* wo);
+// cols[(b,ho,wo)][(i,j,c)] = x[b][ho*sh+i-pt][wo*sw+j-pl][c] (zero outside); x contiguous NHWC, cols pitch cols_ld
+int k_im2col(const ConvArgs& a, const void* x, int dt, void* cols, long long cols_ld, cudaStream_t s);
+// adjoint (gather form): dx[b][h][w][c] = sum of the patch entries that read it
+int k_col2im(const ConvArgs& a, const void* dcols, int dt, long long cols_ld, void* dx, int dx_dt, cudaStream_t s);
+// out[b][t*C + c] = src[b / rows_per_entry][c] (t < reps) and its adjoint; fp32 tables
+int k_expand_table(const float* src, float* out, int B, int C, int rows_per_entry, int reps, cudaStream_t s);
+int k_expand_table_bwd(const float* dout, float* dsrc, int B, int C, int rows_per_entry, int reps, cudaStream_t s);
+// gradient of the rank-1 factor table f[b][c] = clip(mu[e][c] + softplus(rho[e][c]) eps[b][c]) (rho may be null)
+int k_rank1_factor_bwd(const float* df, const float* mu, const float* rho, Noise eps, int E, int n, int C, float lo, float hi,
+                       float* dmu, float* drho, cudaStream_t s);
+
 }  // namespace ed2

@@ -756,6 +756,187 @@ class FlipoutDenseFused(torch.autograd.Function):
         return dx, dmu, drho, dbias, None, None, None, None, None, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------- Conv2D support
+def conv_geometry(x_shape, kernel_size, strides, padding) -> _lib.ConvGeometry:
+    g = _lib.ConvGeometry()
+    g.batch, g.height, g.width, g.channels = (int(v) for v in x_shape)
+    g.kh, g.kw = (int(v) for v in kernel_size)
+    g.sh, g.sw = (int(v) for v in strides)
+    g.same = int(padding == "same")
+    return g
+
+
+def conv_out_size(g: _lib.ConvGeometry):
+    ho, wo = C.c_int(), C.c_int()
+    _lib.check(_lib.load().ed2_conv_out_size(C.byref(g), C.byref(ho), C.byref(wo)), "ed2_conv_out_size")
+    return ho.value, wo.value
+
+
+class Im2Col(torch.autograd.Function):
+    """x [B, H, W, C] (NHWC) -> patch matrix [B*Ho*Wo, kh*kw*C] in the compute dtype (include/ed2b200.h: ed2_im2col); the
+    backward is the gather-form adjoint ed2_col2im."""
+
+    @staticmethod
+    def forward(ctx, x, kernel_size, strides, padding, dtype):
+        lib = _lib.load()
+        xc = x.contiguous()
+        if xc.dtype != dtype:
+            xc = xc.to(dtype)
+        g = conv_geometry(xc.shape, kernel_size, strides, padding)
+        ho, wo = conv_out_size(g)
+        K = g.kh * g.kw * g.channels
+        cols = _new(g.batch * ho * wo, K, dtype, x.device)
+        _lib.check(lib.ed2_im2col(C.byref(g), xc.data_ptr(), _compute_dt(dtype), cols.data_ptr(), _lib.ld(cols),
+                                  _lib.stream_ptr()), "ed2_im2col")
+        ctx.geom, ctx.x_dtype, ctx.dtype = g, x.dtype, dtype
+        return cols
+
+    @staticmethod
+    def backward(ctx, dcols):
+        lib = _lib.load()
+        g = ctx.geom
+        dc = as_compute(dcols, ctx.dtype)
+        dx = torch.empty(g.batch, g.height, g.width, g.channels, dtype=ctx.x_dtype, device=dcols.device)
+        _lib.check(lib.ed2_col2im(C.byref(g), dc.data_ptr(), _compute_dt(ctx.dtype), _lib.ld(dc), dx.data_ptr(),
+                                  _compute_dt(ctx.x_dtype), _lib.stream_ptr()), "ed2_col2im")
+        return dx, None, None, None, None
+
+
+class ExpandTable(torch.autograd.Function):
+    """out[b, t*C + c] = src[b // rows_per_entry, c] for t < reps: a per-member / per-example channel table laid out for
+    the patch matrix (reps = kh*kw) or for the output channels (reps = 1); fp32."""
+
+    @staticmethod
+    def forward(ctx, src, batch, rows_per_entry, reps):
+        lib = _lib.load()
+        s32 = src.to(torch.float32).contiguous()
+        Cn = s32.shape[-1]
+        out = torch.empty(batch, reps * Cn, dtype=torch.float32, device=src.device)
+        _lib.check(lib.ed2_expand_table(s32.data_ptr(), out.data_ptr(), batch, Cn, rows_per_entry, reps,
+                                        _lib.stream_ptr()), "ed2_expand_table")
+        ctx.meta = (batch, Cn, rows_per_entry, reps, src.shape, src.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        batch, Cn, rpe, reps, shape, dt = ctx.meta
+        d = dout.to(torch.float32).contiguous()
+        dsrc = torch.empty(batch // rpe, Cn, dtype=torch.float32, device=dout.device)
+        _lib.check(lib.ed2_expand_table_bwd(d.data_ptr(), dsrc.data_ptr(), batch, Cn, rpe, reps, _lib.stream_ptr()),
+                   "ed2_expand_table_bwd")
+        return dsrc.reshape(shape).to(dt), None, None, None
+
+
+class Rank1Factors(torch.autograd.Function):
+    """Per-example rank-1 factor table f[b, c] = clip(mu[e, c] + sigma[e, c] * eps[b, c], lo, hi), e = b // (B / E)
+    (convolutional.py:1976-1989); rho None: f = mu[e]."""
+
+    @staticmethod
+    def forward(ctx, mu, rho, eps, batch, ensemble_size, clip):
+        lib = _lib.load()
+        E, Cn = mu.shape
+        f = torch.empty(batch, Cn, dtype=torch.float32, device=mu.device)
+        _lib.check(lib.ed2_rank1_factors(mu.data_ptr(), _p(rho), eps.c(), batch, ensemble_size, Cn, float(clip[0]),
+                                         float(clip[1]), f.data_ptr(), _lib.stream_ptr()), "ed2_rank1_factors")
+        ctx.save_for_backward(mu, rho) if rho is not None else ctx.save_for_backward(mu)
+        ctx.meta = (eps, batch, ensemble_size, clip, rho is not None)
+        return f
+
+    @staticmethod
+    def backward(ctx, df):
+        lib = _lib.load()
+        eps, batch, E, clip, has_rho = ctx.meta
+        mu = ctx.saved_tensors[0]
+        rho = ctx.saved_tensors[1] if has_rho else None
+        d = df.to(torch.float32).contiguous()
+        dmu = torch.empty_like(mu)
+        drho = torch.empty_like(rho) if has_rho else None
+        _lib.check(lib.ed2_rank1_factors_bwd(d.data_ptr(), mu.data_ptr(), _p(rho), eps.c(), batch, E, mu.shape[1],
+                                             float(clip[0]), float(clip[1]), dmu.data_ptr(), _p(drho),
+                                             _lib.stream_ptr()), "ed2_rank1_factors_bwd")
+        return dmu, drho, None, None, None, None
+
+
+class FlipoutPatches(torch.autograd.Function):
+    """Conv2DFlipout on the patch matrix (convolutional.py:225-249): with per-example sign VECTORS S [B, Cin], T [B, Cout]
+    broadcast over the spatial axes,   y = act(cols·mean + ((cols ∘ tile(S[b]))·Delta) ∘ T[b] + bias).
+    The perturbation product is the BatchEnsemble call with one member per example (alpha = tile(S), gamma = T) on the
+    sampled Delta = sigma∘eps; the mean product adds it in its epilogue.  Returns (y, kl)."""
+
+    @staticmethod
+    def forward(ctx, cols, mu, rho, bias, s_tab, t_tab, rows_per_example, act, dtype, eps, kl_scale, prior_mean, prior_std):
+        lib = _lib.load()
+        M, K = cols.shape
+        O = mu.shape[1]
+        dev = cols.device
+        Bn = M // rows_per_example
+        xc = as_compute(cols, dtype)
+        mu_lp, delta_lp = _new(K, O, dtype, dev), _new(K, O, dtype, dev)
+        kl64 = torch.zeros((), dtype=torch.float64, device=dev)
+        _lib.check(lib.ed2_sample_normal_weights(
+            mu.data_ptr(), rho.data_ptr(), eps.c(), K, O, 1, delta_lp.data_ptr(), _compute_dt(dtype), _lib.ld(delta_lp),
+            mu_lp.data_ptr(), _lib.ld(mu_lp), kl64.data_ptr() if kl_scale != 0 else None, kl_scale, prior_mean, prior_std,
+            _lib.stream_ptr()), "ed2_sample_normal_weights")
+        pert, xs, z = _new(M, O, dtype, dev), _new(M, K, dtype, dev), _new(M, O, dtype, dev)
+        a = _lib.BeFwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), M, K, O, Bn, ops.ACT_NONE
+        a.x, a.x_ld, a.w_lp, a.w_ld = xc.data_ptr(), _lib.ld(xc), delta_lp.data_ptr(), _lib.ld(delta_lp)
+        a.alpha, a.gamma, a.bias = s_tab.data_ptr(), t_tab.data_ptr(), None
+        a.y, a.y_ld, a.xa, a.xa_ld, a.z, a.z_ld = pert.data_ptr(), _lib.ld(pert), xs.data_ptr(), _lib.ld(xs), z.data_ptr(), _lib.ld(z)
+        _lib.check(lib.ed2_be_dense_fwd(C.byref(a), _lib.stream_ptr()), "ed2_be_dense_fwd")
+        y = _new(M, O, dtype, dev)
+        ops.gemm(xc, mu_lp, M, O, K, major_a=ops.MAJOR_K, major_b=ops.MAJOR_MN, out=y, act=act, addend=pert,
+                 col_bias=bias.reshape(1, -1) if bias is not None else None)
+        ctx.save_for_backward(xc, xs, z, pert, y, mu_lp, delta_lp, mu, rho, s_tab, t_tab)
+        ctx.meta = (act, dtype, bias is not None, cols.dtype, eps, kl_scale, prior_mean, prior_std, Bn)
+        ctx.set_materialize_grads(False)
+        return y, kl64
+
+    @staticmethod
+    def backward(ctx, gy, gkl):
+        lib = _lib.load()
+        xc, xs, z, pert, y, mu_lp, delta_lp, mu, rho, s_tab, t_tab = ctx.saved_tensors
+        act, dtype, has_bias, x_dtype, eps, kl_scale, pm, ps, Bn = ctx.meta
+        M, K = xc.shape
+        O = y.shape[1]
+        dev = xc.device
+        if gy is None:
+            gy = torch.zeros(M, O, dtype=dtype, device=dev)
+        gyc = as_compute(gy, dtype)
+        gp = _new(M, O, dtype, dev)
+        dbias = torch.empty(O, dtype=torch.float32, device=dev) if has_bias else None
+        ops.act_bwd(gyc, y, gp, dbias, act)
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_mean = torch.empty(K, O, **f32)
+        ops.gemm(xc, gp, K, O, M, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=d_mean)
+        need_dx = ctx.needs_input_grad[0]
+        dz, dxa = _new(M, O, dtype, dev), _new(M, K, dtype, dev)
+        dx2 = _new(M, K, dtype, dev) if need_dx else None
+        d_pert, dalpha, dgamma = torch.empty(K, O, **f32), torch.empty(Bn, K, **f32), torch.empty(Bn, O, **f32)
+        a = _lib.BeBwd()
+        a.dtype, a.batch, a.in_dim, a.out_dim, a.ensemble_size, a.act = _compute_dt(dtype), M, K, O, Bn, ops.ACT_NONE
+        a.gy, a.gy_ld, a.y, a.y_ld, a.z, a.z_ld = gp.data_ptr(), _lib.ld(gp), pert.data_ptr(), _lib.ld(pert), z.data_ptr(), _lib.ld(z)
+        a.x, a.x_ld, a.xa, a.xa_ld, a.w_lp, a.w_ld = xc.data_ptr(), _lib.ld(xc), xs.data_ptr(), _lib.ld(xs), delta_lp.data_ptr(), _lib.ld(delta_lp)
+        a.alpha, a.gamma = s_tab.data_ptr(), t_tab.data_ptr()
+        a.dz, a.dz_ld, a.dxa, a.dxa_ld, a.dx, a.dx_ld = dz.data_ptr(), _lib.ld(dz), dxa.data_ptr(), _lib.ld(dxa), _p(dx2), _ldn(dx2)
+        a.dw, a.dalpha, a.dgamma, a.dbias = d_pert.data_ptr(), dalpha.data_ptr(), dgamma.data_ptr(), None
+        _lib.check(lib.ed2_be_dense_bwd(C.byref(a), _lib.stream_ptr()), "ed2_be_dense_bwd")
+        dx = None
+        if need_dx:  # dcols = gp·meanᵀ + ((gp∘T)·Deltaᵀ) ∘ tile(S): the second term rides in as the addend
+            dx = _new(M, K, dtype, dev)
+            ops.gemm(gp, mu_lp, M, K, O, major_a=ops.MAJOR_K, major_b=ops.MAJOR_K, out=dx, addend=dx2)
+            if dx.dtype != x_dtype:
+                dx = dx.to(x_dtype)
+        dmu, drho = torch.empty_like(mu), torch.empty_like(rho)
+        up = (gkl if gkl.dtype == torch.float64 else gkl.to(torch.float64)).reshape(1) if gkl is not None else None
+        klg = (kl_scale if gkl is not None else 0.0) / GradSync.replicas
+        _lib.check(lib.ed2_normal_grad_finish2(d_mean.data_ptr(), d_pert.data_ptr(), mu.data_ptr(), rho.data_ptr(), eps.c(),
+                                               K * O, klg, _p(up), pm, ps, dmu.data_ptr(), drho.data_ptr(),
+                                               int(dtype == torch.bfloat16), _lib.stream_ptr()), "ed2_normal_grad_finish2")
+        return dx, dmu, drho, dbias, None, None, None, None, None, None, None, None, None
+
+
 # ------------------------------------------------------------------------------------------------- KL regulariser
 class NormalKL(torch.autograd.Function):
     """scale * sum KL(N(mu, softplus(rho)+1e-7) || N(m, s)) as a 0-dim fp32 tensor (regularizers.py:175-186)."""

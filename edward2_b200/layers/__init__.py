@@ -1,11 +1,12 @@
 """TF / Keras call signatures of the reference (`ed.layers.*`) on libed2b200."""
 from . import utils
 from .base import Layer
+from .convolutional import Conv2DBatchEnsemble, Conv2DFlipout, Conv2DRank1, Conv2DReparameterization
 from .dense import Dense, DenseBatchEnsemble, DenseFlipout, DenseRank1, DenseReparameterization
 from .normalization import SpectralNormalization
 from .random_feature import LaplaceRandomFeatureCovariance, RandomFeatureGaussianProcess
 
 __all__ = [
-    "Layer", "Dense", "DenseBatchEnsemble", "DenseFlipout", "DenseRank1", "DenseReparameterization",
+    "Layer", "Conv2DBatchEnsemble", "Conv2DFlipout", "Conv2DRank1", "Conv2DReparameterization", "Dense", "DenseBatchEnsemble", "DenseFlipout", "DenseRank1", "DenseReparameterization",
     "SpectralNormalization", "LaplaceRandomFeatureCovariance", "RandomFeatureGaussianProcess", "utils",
 ]

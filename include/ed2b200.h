@@ -505,6 +505,46 @@ int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream);
 int ed2_flipout_fusable(int batch, int in_dim, int out_dim);
 
 /* ------------------------------------------------------------------------------------------------
+ * Conv2D stochastic-weight layers (edward2/tensorflow/layers/convolutional.py:32 Conv2DReparameterization, :167
+ * Conv2DFlipout, :560 Conv2DBatchEnsemble, :2056 Conv2DRank1).  Their per-example factors are channel vectors broadcast
+ * over the spatial axes (:235-249, :681-699, :1976-1989), so on the patch matrix
+ *   cols[(b,ho,wo)][(i,j,c)] = x[b][ho*sh+i-pt][wo*sw+j-pl][c]
+ * every variant is the dense call of the same family with rows-per-member = Ho*Wo and one "member" per example:
+ *   ed2_be_dense_fwd(cols, W[kh*kw*Cin][Cout], alpha = tile(f_in[b]), gamma = f_out[b], bias[b], ensemble_size = B)
+ *   ed2_reparam_dense_fwd(cols, mu / rho reshaped [kh*kw*Cin][Cout])
+ * These entry points are what the dense path lacks.  NHWC, dilation 1, same = 0 'valid' | 1 TF 'SAME'. */
+typedef struct {
+  int batch, height, width, channels;
+  int kh, kw, sh, sw;
+  int same;
+} ed2_conv_geometry;
+int ed2_conv_out_size(const ed2_conv_geometry* g, int* out_h, int* out_w);
+/* x contiguous NHWC `dtype`; cols [B*Ho*Wo][cols_ld] `dtype`, cols_ld >= kh*kw*C */
+int ed2_im2col(const ed2_conv_geometry* g, const void* x, int dtype, void* cols, long long cols_ld, void* stream);
+/* adjoint of ed2_im2col in gather form (no atomics): dx contiguous NHWC `dx_dtype` */
+int ed2_col2im(const ed2_conv_geometry* g, const void* dcols, int dtype, long long cols_ld, void* dx, int dx_dtype,
+               void* stream);
+/* out[b][t*C + c] = src[b / rows_per_entry][c], t < reps: a per-member ([E][C], rows_per_entry = B / E) or per-example
+ * ([B][C], rows_per_entry = 1) channel table laid out for the patch matrix (reps = kh*kw) or the output (reps = 1) */
+int ed2_expand_table(const float* src, float* out, int batch, int channels, int rows_per_entry, int reps, void* stream);
+int ed2_expand_table_bwd(const float* dout, float* dsrc, int batch, int channels, int rows_per_entry, int reps, void* stream);
+/* rank-1 per-example factor table f[b][c] = clip(mu[e][c] + (softplus(rho[e][c]) + 1e-7) eps[b][c], lo, hi), e = b / (B / E)
+ * (convolutional.py:1976-1989; rho == NULL: f = mu[e]) and its gradient:
+ *   dmu[e][c] = sum_b df 1[unclipped],  drho[e][c] = sum_b df 1[unclipped] eps sigmoid(rho) */
+int ed2_rank1_factors(const float* mu, const float* rho, ed2_noise eps, int batch, int ensemble_size, int channels,
+                      float clip_lo, float clip_hi, float* f, void* stream);
+int ed2_rank1_factors_bwd(const float* df, const float* mu, const float* rho, ed2_noise eps, int batch, int ensemble_size,
+                          int channels, float clip_lo, float clip_hi, float* dmu, float* drho, void* stream);
+/* a per-example noise TABLE out[rows][cols] (`dtype`, pitch ld) from a noise descriptor — kind 0 normal, 1 sign — with
+ * the descriptor's row mapping and device step applied (the sign vectors of Conv2DFlipout, convolutional.py:235-249) */
+int ed2_noise_table(int kind, ed2_noise nz, void* out, int dtype, long long ld, long long rows, long long cols, void* stream);
+/* the two-input finishing pass of a Flipout-style pair of weight gradients (d_mean = xᵀgp, d_pert = (x∘S)ᵀ(gp∘T)), in place
+ * or not:  dmu = d_mean + KL',  drho = (d_pert eps + KL') sigmoid(rho) */
+int ed2_normal_grad_finish2(const float* d_mean, const float* d_pert, const float* mu, const float* rho, ed2_noise eps,
+                            long long n, float kl_grad_scale, const double* kl_upstream, float prior_mean, float prior_std,
+                            float* dmu, float* drho, int fast, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SNGP head.
  * SpectralNormalization (edward2/tensorflow/layers/normalization.py:369-391;
  * edward2/jax/nn/normalization.py:159-178).  w [I][O] fp32, u [O], v [I] (updated in place).

@@ -147,3 +147,39 @@ def batch_ensemble_conv2d_bwd(x, kernel, alpha, gamma, bias, act, gy, strides=(1
     dxa, dk = conv2d_bwd(x * a, kernel, gp * g, strides, padding)
     per_member = lambda t: t.sum((1, 2)).reshape(E, n, -1).sum(1)  # noqa: E731
     return dict(dx=dxa * a, dkernel=dk, dalpha=per_member(dxa * x), dgamma=per_member(gp * z), dbias=per_member(gp))
+
+
+def flipout_conv2d_bwd(x, mu, rho, eps, sign_in, sign_out, bias, act, gy, strides=(1, 1), padding="valid", y_mask=None):
+    """Closed-form gradients of flipout_conv2d (convolutional.py:225-249): the mean and the perturbation convolutions are
+    separate linear maps of x; Delta = sigma∘eps gives drho = dDelta ∘ eps ∘ sigmoid(rho)."""
+    x = np.asarray(x, dtype=np.float64)
+    si = np.asarray(sign_in, dtype=np.float64)[:, None, None, :]
+    so = np.asarray(sign_out, dtype=np.float64)[:, None, None, :]
+    y, delta = flipout_conv2d(x, mu, rho, eps, sign_in, sign_out, bias, act, strides, padding)
+    gp = od.activation_grad(y if y_mask is None else y_mask, np.asarray(gy, dtype=np.float64), act)
+    dx1, dmean = conv2d_bwd(x, mu, gp, strides, padding)
+    dxs, ddelta = conv2d_bwd(x * si, delta, gp * so, strides, padding)
+    return dict(dx=dx1 + dxs * si, dmu=dmean, drho=ddelta * np.asarray(eps, dtype=np.float64) * od.sigmoid(rho),
+                dbias=gp.sum((0, 1, 2)))
+
+
+def rank1_conv2d_bwd(x, kernel, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act, gy, strides=(1, 1), padding="valid",
+                     y_mask=None):
+    """Closed-form gradients of rank1_conv2d (multiplicative; convolutional.py:1968-2020): the dense rank-1 algebra
+    (oracle/dense.py:rank1_bwd) with the per-example factors broadcast over, and their gradients summed over, the
+    spatial axes."""
+    x = np.asarray(x, dtype=np.float64)
+    E = mu_r.shape[0]
+    n = x.shape[0] // E
+    r, mask_r, er = od.rank1_factors(mu_r, rho_r, eps_r, E)
+    s, mask_s, es = od.rank1_factors(mu_s, rho_s, eps_s, E)
+    z = conv2d(x * r[:, None, None, :], kernel, strides, padding)
+    y, _, _ = rank1_conv2d(x, kernel, mu_r, rho_r, eps_r, mu_s, rho_s, eps_s, bias, act, strides, padding)
+    gp = od.activation_grad(y if y_mask is None else y_mask, np.asarray(gy, dtype=np.float64), act)
+    dxr, dk = conv2d_bwd(x * r[:, None, None, :], kernel, gp * s[:, None, None, :], strides, padding)
+    ds = (gp * z).sum((1, 2)) * mask_s
+    dr = (dxr * x).sum((1, 2)) * mask_r
+    member = lambda t: t.reshape(E, n, -1).sum(1)  # noqa: E731
+    return dict(dx=dxr * r[:, None, None, :], dkernel=dk, dmu_r=member(dr),
+                drho_r=None if rho_r is None else member(dr * er) * od.sigmoid(rho_r), dmu_s=member(ds),
+                drho_s=None if rho_s is None else member(ds * es) * od.sigmoid(rho_s), dbias=member(gp.sum((1, 2))))

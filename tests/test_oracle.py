@@ -372,6 +372,32 @@ def test_conv_oracle_pinned_against_torch_and_reference_identities():
                   (g["dbias"], bt3.grad)):
         np.testing.assert_allclose(a, b_.numpy(), rtol=1e-9, atol=1e-9)
 
+    # Flipout conv and rank-1 conv: closed-form gradients vs float64 autograd
+    sp = lambda t: torch.nn.functional.softplus(t) + 1e-7  # noqa: E731
+    conv = lambda a, w: tf_.conv2d(a.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1)).permute(0, 2, 3, 1)  # noqa: E731
+    xt4 = torch.tensor(x, requires_grad=True)
+    mu4, rho4, b4 = torch.tensor(mu, requires_grad=True), torch.tensor(rho2, requires_grad=True), torch.tensor(bias[0], requires_grad=True)
+    si, so = torch.tensor(s_in)[:, None, None, :], torch.tensor(s_out)[:, None, None, :]
+    yf4 = torch.relu(conv(xt4, mu4) + conv(xt4 * si, sp(rho4) * torch.tensor(eps)) * so + b4)
+    gy4 = rng.standard_normal(tuple(yf4.shape))
+    (yf4 * torch.tensor(gy4)).sum().backward()
+    g = oc.flipout_conv2d_bwd(x, mu, rho2, eps, s_in, s_out, bias[0], "relu", gy4)
+    for a, b_ in ((g["dx"], xt4.grad), (g["dmu"], mu4.grad), (g["drho"], rho4.grad), (g["dbias"], b4.grad)):
+        np.testing.assert_allclose(a, b_.numpy(), rtol=1e-9, atol=1e-9)
+
+    xt5, kt5 = torch.tensor(x, requires_grad=True), torch.tensor(k, requires_grad=True)
+    mr, rr, ms, rs, bb = (torch.tensor(t, requires_grad=True) for t in (mu_r, rho_r, mu_s, rho_s, bias))
+    rep1 = lambda t: t.repeat_interleave(n, 0)  # noqa: E731
+    r_t = torch.clamp(rep1(mr) + rep1(sp(rr)) * torch.tensor(e_r), -10, 10)[:, None, None, :]
+    s_t = torch.clamp(rep1(ms) + rep1(sp(rs)) * torch.tensor(e_s), -10, 10)[:, None, None, :]
+    y5 = torch.relu(conv(xt5 * r_t, kt5) * s_t + rep1(bb)[:, None, None, :])
+    gy5 = rng.standard_normal(tuple(y5.shape))
+    (y5 * torch.tensor(gy5)).sum().backward()
+    g = oc.rank1_conv2d_bwd(x, k, mu_r, rho_r, e_r, mu_s, rho_s, e_s, bias, "relu", gy5)
+    for a, b_ in ((g["dx"], xt5.grad), (g["dkernel"], kt5.grad), (g["dmu_r"], mr.grad), (g["drho_r"], rr.grad),
+                  (g["dmu_s"], ms.grad), (g["drho_s"], rs.grad), (g["dbias"], bb.grad)):
+        np.testing.assert_allclose(a, b_.numpy(), rtol=1e-9, atol=1e-9)
+
 
 # ------------------------------------------------------------------------------------------------------------------
 # Reference-generated fixture: tests/golden/reference_vectors.npz holds outputs of the UNMODIFIED reference files
