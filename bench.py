@@ -345,8 +345,55 @@ def wl_sngp(kind, train):
     return build
 
 
+def wl_conv_rank1(ed, device, step_counter, rank, world):
+    """SURVEY.md §8f-1 (next row): two stacked Conv2DRank1 3x3 'same' layers at the width / resolution of a WRN-28-10
+    group (160 channels, 32x32; experimental/rank1_bnns/cifar_model.py), batch 64, ensemble_size 4, bf16."""
+    import torch
+
+    from edward2_b200 import functional as F
+
+    E, B, H, W, Cn = 4, 64, 32, 32, 160
+    mk = lambda act, li: ed.layers.Conv2DRank1(  # noqa: E731
+        Cn, 3, padding="same", activation=act, ensemble_size=E, dtype="bfloat16", seed=3030 + li,
+        alpha_initializer=ed.initializers.TrainableNormal(
+            mean_initializer=ed.initializers.RandomSign(seed=10 + li), stddev_initializer=ed.initializers.Constant(-3.4402)),
+        gamma_initializer=ed.initializers.TrainableNormal(
+            mean_initializer=ed.initializers.RandomSign(seed=20 + li), stddev_initializer=ed.initializers.Constant(-3.4402)),
+        alpha_regularizer=ed.regularizers.NormalKLDivergence(mean=1.0, stddev=0.1, scale_factor=KL_SCALE),
+        gamma_regularizer=ed.regularizers.NormalKLDivergence(mean=1.0, stddev=0.1, scale_factor=KL_SCALE))
+    layers = [mk("relu", 0), mk(None, 1)]
+    with torch.no_grad():
+        h = torch.zeros(E, H, W, Cn, dtype=torch.bfloat16, device=device)
+        for l in layers:
+            h = l(h)
+    for l in layers:
+        l.step_counter = step_counter
+    model = torch.nn.ModuleList(layers)
+
+    def step(x, y):
+        h = x.view(B, H, W, Cn)
+        for l in layers:
+            h = l(h)
+        logits = h.float().mean(dim=(1, 2))  # synthetic head: global average pool (harness plumbing, not the layer path)
+        loss = F.SoftmaxCrossEntropy.apply(logits, y, B * world, *[k for l in layers for k in l.losses])
+        F.backward(loss)
+        return loss.detach()
+
+    def cpu(steps):
+        from oracle import torch_cpu
+
+        sps, dt, th = torch_cpu.time_rank1_conv(B, H, W, Cn, 2, steps, warmup=1, ensemble_size=E)
+        return sps, dt, th, f"{steps} fwd+bwd steps on {B}-image batches (torch-CPU fp32 restatement, F.conv2d)"
+
+    per_layer = 2.0 * B * H * W * 9 * Cn * Cn
+    return dict(step=step, params=list(model.parameters()), batch=B, in_dim=H * W * Cn, x_dtype=torch.bfloat16, classes=Cn,
+                flops=5 * per_layer, cpu=cpu, dtype="bf16", modules=model,
+                workload="conv (SURVEY §8f-1): 2 x Conv2DRank1 3x3 'same', 160 channels, 32x32, batch 64, ensemble_size 4, "
+                         "bf16; im2col + dense rank-1 path; fwd + dW of both layers + dX of the second")
+
+
 WORKLOADS = {
-    "cfg4": wl_cfg4, "cfg2_reparam": wl_cfg2(False), "cfg2_flipout": wl_cfg2(True), "cfg1": wl_cfg1,
+    "cfg4": wl_cfg4, "conv_rank1": wl_conv_rank1, "cfg2_reparam": wl_cfg2(False), "cfg2_flipout": wl_cfg2(True), "cfg1": wl_cfg1,
     "cfg3_train": wl_sngp("cfg3", True), "cfg3_eval": wl_sngp("cfg3", False),
     "cfg5_train": wl_sngp("cfg5", True), "cfg5_eval": wl_sngp("cfg5", False),
 }

@@ -195,6 +195,25 @@ class ConvGeometry(C.Structure):
                 ("kh", _i), ("kw", _i), ("sh", _i), ("sw", _i), ("same", _i)]
 
 
+class ConvFactorFwd(C.Structure):
+    _fields_ = [
+        ("geom", ConvGeometry), ("dtype", _i), ("out_channels", _i), ("act", _i),
+        ("x", _vp), ("w_lp", _vp), ("w_ld", _i), ("f_in", _vp), ("f_out", _vp), ("bias", _vp),
+        ("xa", _vp), ("xa_ld", _i), ("y", _vp), ("y_ld", _i), ("z", _vp), ("z_ld", _i),
+    ]
+
+
+class ConvFactorBwd(C.Structure):
+    _fields_ = [
+        ("geom", ConvGeometry), ("dtype", _i), ("out_channels", _i), ("act", _i),
+        ("gy", _vp), ("gy_ld", _i), ("y", _vp), ("y_ld", _i), ("z", _vp), ("z_ld", _i),
+        ("x", _vp), ("xa", _vp), ("xa_ld", _i), ("w_lp", _vp), ("w_ld", _i),
+        ("f_in", _vp), ("f_out", _vp),
+        ("dz", _vp), ("dz_ld", _i), ("dxa", _vp), ("dxa_ld", _i), ("gimg", _vp), ("dx", _vp),
+        ("dw", _vp), ("df_in", _vp), ("df_out", _vp), ("dbias", _vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/ed2b200.h declares
 SIGNATURES = {
     "ed2_version": (C.c_char_p, []),
@@ -242,6 +261,8 @@ SIGNATURES = {
     "ed2_conv_out_size": (_i, [C.POINTER(ConvGeometry), C.POINTER(_i), C.POINTER(_i)]),
     "ed2_im2col": (_i, [C.POINTER(ConvGeometry), _vp, _i, _vp, _ll, _vp]),
     "ed2_col2im": (_i, [C.POINTER(ConvGeometry), _vp, _i, _ll, _vp, _i, _vp]),
+    "ed2_conv_factor_fwd": (_i, [C.POINTER(ConvFactorFwd), _vp]),
+    "ed2_conv_factor_bwd": (_i, [C.POINTER(ConvFactorBwd), _vp]),
     "ed2_expand_table": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ed2_expand_table_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ed2_rank1_factors": (_i, [_vp, _vp, Noise, _i, _i, _i, _f, _f, _vp, _vp]),

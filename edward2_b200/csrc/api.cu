@@ -80,6 +80,14 @@ int gemm_xtg(int dt, const void* x, int x_ld, const void* gz, int g_ld, int B, i
   g.B = gz; g.ldb = g_ld; g.major_b = kMajorMN;
   g.M = I; g.N = O; g.K = B;
   g.ep = ep;
+  // narrow weight gradient over a long batch axis (conv layers on the patch matrix: [9C x Cout] with K = B*Ho*Wo): a
+  // handful of output tiles would leave most SM pairs idle — K slices accumulate with fp32 atomics into a zeroed output
+  const long long tiles = ((I + 255) / 256) * static_cast<long long>((O + 255) / 256);
+  if (dt == kBF16 && ep.out_dt == kF32 && ep.out != nullptr && tiles * 4 <= 74 && B >= 4096 && ep.addend == nullptr &&
+      ep.col_sum == nullptr && ep.raw == nullptr && ep.act == kActNone && ep.out_ld == O) {
+    cudaMemsetAsync(ep.out, 0, sizeof(float) * static_cast<size_t>(I) * O, s);
+    return gemm_bf16_accumulate(g, s);
+  }
   return gemm(dt, g, s);
 }
 
@@ -731,6 +739,50 @@ int ed2_col2im(const ed2_conv_geometry* g, const void* dcols, int dtype, long lo
   ED2_TRY(check_dt(dx_dtype));
   return k_col2im(conv_args(g), dcols, dtype, cols_ld, dx, dx_dtype, S(stream));
 }
+int ed2_conv_factor_fwd(const ed2_conv_factor_fwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  cudaStream_t s = S(stream);
+  const ConvArgs g = conv_args(&a->geom);
+  int ho = 0, wo = 0;
+  ED2_TRY(k_conv_out_size(g, &ho, &wo));
+  const int M = g.batch * ho * wo, K = g.kh * g.kw * g.channels;
+  ED2_TRY(k_im2col(g, a->x, a->dtype, a->xa, a->xa_ld, s, a->f_in));
+  EpiParams e = epi_default();
+  e.group_rows = ho * wo;
+  e.col_scale = a->f_out; e.col_scale_ld = a->out_channels;
+  e.col_bias = a->bias; e.col_bias_ld = a->out_channels;
+  e.act = a->act;
+  e.out = a->y; e.out_ld = a->y_ld; e.out_dt = a->dtype;
+  e.raw = a->z; e.raw_ld = a->z_ld; e.raw_dt = a->dtype;
+  return gemm_xw(a->dtype, a->xa, a->xa_ld, a->w_lp, a->w_ld, M, K, a->out_channels, e, s);
+}
+
+int ed2_conv_factor_bwd(const ed2_conv_factor_bwd_args* a, void* stream) {
+  ED2_TRY(check_dt(a->dtype));
+  cudaStream_t s = S(stream);
+  const ConvArgs g = conv_args(&a->geom);
+  int ho = 0, wo = 0;
+  ED2_TRY(k_conv_out_size(g, &ho, &wo));
+  const int M = g.batch * ho * wo, K = g.kh * g.kw * g.channels, O = a->out_channels;
+  BwdOutArgs o{};
+  o.dt = a->dtype; o.rows = M; o.cols = O; o.rows_per_member = ho * wo; o.act = a->act; o.fast = 1;
+  o.gy = a->gy; o.gy_ld = a->gy_ld; o.y = a->y; o.y_ld = a->y_ld; o.z = a->z; o.z_ld = a->z_ld;
+  o.gamma = a->f_out;
+  o.dz = a->dz; o.dz_ld = a->dz_ld;
+  o.d_fast_mu = a->df_out; o.dbias = a->dbias;
+  ED2_TRY(k_bwd_out(o, s));
+  EpiParams e = epi_default();
+  e.out = a->dw; e.out_ld = O; e.out_dt = kF32;
+  ED2_TRY(gemm_xtg(a->dtype, a->xa, a->xa_ld, a->dz, a->dz_ld, M, K, O, e, s));
+  if (a->dxa == nullptr) return ED2_OK;
+  EpiParams e2 = epi_default();
+  e2.out = a->dxa; e2.out_ld = a->dxa_ld; e2.out_dt = a->dtype;
+  ED2_TRY(gemm_gwt(a->dtype, a->dz, a->dz_ld, a->w_lp, a->w_ld, M, K, O, e2, s));
+  if (a->f_in == nullptr && a->dx != nullptr) return k_col2im(g, a->dxa, a->dtype, a->dxa_ld, a->dx, a->dtype, s);
+  ED2_TRY(k_col2im(g, a->dxa, a->dtype, a->dxa_ld, a->gimg, a->dtype, s));
+  return k_conv_scale_reduce(g, a->gimg, a->x, a->dtype, a->f_in, a->dx, a->dtype, a->df_in, s);
+}
+
 int ed2_expand_table(const float* src, float* out, int batch, int channels, int rows_per_entry, int reps, void* stream) {
   return k_expand_table(src, out, batch, channels, rows_per_entry, reps, S(stream));
 }

@@ -37,9 +37,23 @@ struct ConvGeom {
 // One thread per (patch row m, kernel tap t, channel vector): kVec channels (16 bytes) moved as one vector, zero-filled
 // outside the image.  Consecutive threads walk the channels of one tap, then the taps of one patch: reads and writes
 // are both contiguous runs of C elements.
+// x ∘ fac[b][c..c+7] for a vector of 8 bf16 / 4 fp32 channels (fac fp32)
+__device__ __forceinline__ uint4 scale_vec(uint4 v, const float* __restrict__ f) {
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 a = __bfloat1622float2(h[t]);
+    h[t] = __floats2bfloat162_rn(a.x * __ldg(f + 2 * t), a.y * __ldg(f + 2 * t + 1));
+  }
+  return v;
+}
+__device__ __forceinline__ float4 scale_vec(float4 v, const float* __restrict__ f) {
+  return make_float4(v.x * __ldg(f), v.y * __ldg(f + 1), v.z * __ldg(f + 2), v.w * __ldg(f + 3));
+}
+
 template <int kVec, typename V>
 __global__ void __launch_bounds__(kBlock) im2col_vec_kernel(const V* __restrict__ x, V* __restrict__ cols, long long cols_ldv,
-                                                           ConvGeom g) {
+                                                           ConvGeom g, const float* __restrict__ fac = nullptr) {
   const int cv = g.C / kVec;
   const long long per_row = static_cast<long long>(g.kh) * g.kw * cv;
   const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * per_row;
@@ -53,13 +67,16 @@ __global__ void __launch_bounds__(kBlock) im2col_vec_kernel(const V* __restrict_
     const int ho = static_cast<int>(bh % g.Ho), b = static_cast<int>(bh / g.Ho);
     const int h = ho * g.sh + i - g.pt, w = wo * g.sw + j - g.pl;
     V v{};
-    if (h >= 0 && h < g.H && w >= 0 && w < g.W) v = __ldg(x + ((static_cast<long long>(b) * g.H + h) * g.W + w) * cv + c);
+    if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
+      v = __ldg(x + ((static_cast<long long>(b) * g.H + h) * g.W + w) * cv + c);
+      if (fac != nullptr) v = scale_vec(v, fac + static_cast<long long>(b) * g.C + c * kVec);
+    }
     cols[m * cols_ldv + static_cast<long long>(t) * cv + c] = v;
   }
 }
 
 __global__ void __launch_bounds__(kBlock) im2col_kernel(const void* __restrict__ x, int dt, void* __restrict__ cols,
-                                                       long long cols_ld, ConvGeom g) {
+                                                       long long cols_ld, ConvGeom g, const float* __restrict__ fac = nullptr) {
   const long long per_row = static_cast<long long>(g.kh) * g.kw * g.C;
   const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * per_row;
   for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < total; idx += (long long)gridDim.x * kBlock) {
@@ -72,7 +89,10 @@ __global__ void __launch_bounds__(kBlock) im2col_kernel(const void* __restrict__
     const int ho = static_cast<int>(bh % g.Ho), b = static_cast<int>(bh / g.Ho);
     const int h = ho * g.sh + i - g.pt, w = wo * g.sw + j - g.pl;
     float v = 0.f;
-    if (h >= 0 && h < g.H && w >= 0 && w < g.W) v = ldv(x, dt, ((static_cast<long long>(b) * g.H + h) * g.W + w) * g.C + c);
+    if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
+      v = ldv(x, dt, ((static_cast<long long>(b) * g.H + h) * g.W + w) * g.C + c);
+      if (fac != nullptr) v *= __ldg(fac + static_cast<long long>(b) * g.C + c);
+    }
     stv(cols, dt, m * cols_ld + rem, v);
   }
 }
@@ -104,6 +124,75 @@ __global__ void __launch_bounds__(kBlock) col2im_kernel(const void* __restrict__
       }
     }
     stv(dx, dx_dt, idx, acc);
+  }
+}
+
+// bf16 patch gradients, C % 8 == 0: one thread owns 8 consecutive channels of one pixel (16-byte loads per tap)
+__global__ void __launch_bounds__(kBlock) col2im_bf16x8_kernel(const uint4* __restrict__ dcols, long long cols_ldv,
+                                                              void* __restrict__ dx, int dx_dt, ConvGeom g) {
+  const int cv = g.C / 8;
+  const long long total = static_cast<long long>(g.B) * g.H * g.W * cv;
+  for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < total; idx += (long long)gridDim.x * kBlock) {
+    const int c = static_cast<int>(idx % cv);
+    long long r = idx / cv;
+    const int w = static_cast<int>(r % g.W);
+    r /= g.W;
+    const int h = static_cast<int>(r % g.H), b = static_cast<int>(r / g.H);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < g.kh; ++i) {
+      const int hh = h + g.pt - i;
+      if (hh < 0 || hh % g.sh != 0) continue;
+      const int ho = hh / g.sh;
+      if (ho >= g.Ho) continue;
+      for (int j = 0; j < g.kw; ++j) {
+        const int ww = w + g.pl - j;
+        if (ww < 0 || ww % g.sw != 0) continue;
+        const int wo = ww / g.sw;
+        if (wo >= g.Wo) continue;
+        const long long m = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
+        const uint4 q = __ldg(dcols + m * cols_ldv + (static_cast<long long>(i) * g.kw + j) * cv + c);
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __bfloat1622float2(hp[t]);
+          acc[2 * t] += f.x;
+          acc[2 * t + 1] += f.y;
+        }
+      }
+    }
+    if (dx_dt == kBF16) {
+      uint4 o;
+      __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) op[t] = __floats2bfloat162_rn(acc[2 * t], acc[2 * t + 1]);
+      reinterpret_cast<uint4*>(dx)[idx] = o;
+    } else {
+      float4* o = reinterpret_cast<float4*>(dx) + idx * 2;
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
+// Image-space tail of a factorised convolution's backward: g = gradient w.r.t. the SCALED image x∘fac (from col2im).
+//   dx[b,h,w,c] = g * fac[b,c];   dfac[b,c] += sum_{h,w} g * x      (dfac zeroed by the caller)
+// Block = one image b and a slab of pixels; thread = one channel (coalesced rows of C), one atomic per thread.
+__global__ void __launch_bounds__(kBlock) conv_scale_reduce_kernel(const void* __restrict__ gimg, const void* __restrict__ x,
+                                                                  int dt, const float* __restrict__ fac, void* __restrict__ dx,
+                                                                  int dx_dt, float* __restrict__ dfac, int HW, int C,
+                                                                  int pixels_per_block) {
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pixels_per_block, p1 = min(HW, p0 + pixels_per_block);
+  for (int c = threadIdx.x; c < C; c += kBlock) {
+    const float f = fac != nullptr ? __ldg(fac + static_cast<long long>(b) * C + c) : 1.f;
+    float acc = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const long long i = (static_cast<long long>(b) * HW + p) * C + c;
+      const float gv = ldv(gimg, dt, i);
+      acc += gv * ldv(x, dt, i);
+      if (dx != nullptr) stv(dx, dx_dt, i, gv * f);
+    }
+    if (dfac != nullptr) atomicAdd(dfac + static_cast<long long>(b) * C + c, acc);
   }
 }
 
@@ -186,7 +275,7 @@ int k_conv_out_size(const ConvArgs& a, int* ho, int* wo) {
   return ED2_OK;
 }
 
-int k_im2col(const ConvArgs& a, const void* x, int dt, void* cols, long long cols_ld, cudaStream_t s) {
+int k_im2col(const ConvArgs& a, const void* x, int dt, void* cols, long long cols_ld, cudaStream_t s, const float* fac) {
   ConvGeom g;
   const int st = geom(a, &g);
   if (st != ED2_OK) return st;
@@ -199,11 +288,11 @@ int k_im2col(const ConvArgs& a, const void* x, int dt, void* cols, long long col
   if (aligned) {
     const long long work = rows * g.kh * g.kw * (g.C / vec);
     if (dt == kBF16)
-      im2col_vec_kernel<8, uint4><<<grid_for(work), kBlock, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(cols), cols_ld / 8, g);
+      im2col_vec_kernel<8, uint4><<<grid_for(work), kBlock, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(cols), cols_ld / 8, g, fac);
     else
-      im2col_vec_kernel<4, float4><<<grid_for(work), kBlock, 0, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(cols), cols_ld / 4, g);
+      im2col_vec_kernel<4, float4><<<grid_for(work), kBlock, 0, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(cols), cols_ld / 4, g, fac);
   } else {
-    im2col_kernel<<<grid_for(rows * K), kBlock, 0, s>>>(x, dt, cols, cols_ld, g);
+    im2col_kernel<<<grid_for(rows * K), kBlock, 0, s>>>(x, dt, cols, cols_ld, g, fac);
   }
   count_launch();
   return check_launch("im2col");
@@ -214,9 +303,27 @@ int k_col2im(const ConvArgs& a, const void* dcols, int dt, long long cols_ld, vo
   const int st = geom(a, &g);
   if (st != ED2_OK) return st;
   const long long total = static_cast<long long>(g.B) * g.H * g.W * g.C;
+  if (dt == kBF16 && g.C % 8 == 0 && cols_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dcols) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+    col2im_bf16x8_kernel<<<grid_for(total / 8), kBlock, 0, s>>>(reinterpret_cast<const uint4*>(dcols), cols_ld / 8, dx, dx_dt, g);
+    count_launch();
+    return check_launch("col2im");
+  }
   col2im_kernel<<<grid_for(total), kBlock, 0, s>>>(dcols, dt, cols_ld, dx, dx_dt, g);
   count_launch();
   return check_launch("col2im");
+}
+
+int k_conv_scale_reduce(const ConvArgs& a, const void* gimg, const void* x, int dt, const float* fac, void* dx, int dx_dt,
+                        float* dfac, cudaStream_t s) {
+  const int HW = a.height * a.width, C = a.channels;
+  if (dfac != nullptr) cudaMemsetAsync(dfac, 0, sizeof(float) * static_cast<size_t>(a.batch) * C, s);
+  int ppb = 32;
+  while (ppb > 4 && static_cast<long long>(a.batch) * ((HW + ppb - 1) / ppb) < 148 * 4) ppb >>= 1;
+  dim3 grid((HW + ppb - 1) / ppb, a.batch);
+  conv_scale_reduce_kernel<<<grid, kBlock, 0, s>>>(gimg, x, dt, fac, dx, dx_dt, dfac, HW, C, ppb);
+  count_launch();
+  return check_launch("conv_scale_reduce");
 }
 
 int k_expand_table(const float* src, float* out, int B, int C, int rows_per_entry, int reps, cudaStream_t s) {

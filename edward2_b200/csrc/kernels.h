@@ -175,7 +175,12 @@ struct ConvArgs {
 };
 int k_conv_out_size(const ConvArgs& a, int* ho, int* wo);
 // cols[(b,ho,wo)][(i,j,c)] = x[b][ho*sh+i-pt][wo*sw+j-pl][c] (zero outside); x contiguous NHWC, cols pitch cols_ld
-int k_im2col(const ConvArgs& a, const void* x, int dt, void* cols, long long cols_ld, cudaStream_t s);
+// fac (optional): per-example channel factors [B][C] fp32 applied while gathering (cols = im2col(x ∘ fac[b]))
+int k_im2col(const ConvArgs& a, const void* x, int dt, void* cols, long long cols_ld, cudaStream_t s,
+             const float* fac = nullptr);
+// image-space tail of a factorised convolution's backward: dx = gimg ∘ fac[b], dfac[b][c] = sum_hw gimg * x
+int k_conv_scale_reduce(const ConvArgs& a, const void* gimg, const void* x, int dt, const float* fac, void* dx, int dx_dt,
+                        float* dfac, cudaStream_t s);
 // adjoint (gather form): dx[b][h][w][c] = sum of the patch entries that read it
 int k_col2im(const ConvArgs& a, const void* dcols, int dt, long long cols_ld, void* dx, int dx_dt, cudaStream_t s);
 // out[b][t*C + c] = src[b / rows_per_entry][c] (t < reps) and its adjoint; fp32 tables

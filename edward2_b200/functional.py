@@ -802,6 +802,73 @@ class Im2Col(torch.autograd.Function):
         return dx, None, None, None, None
 
 
+class ConvFactorized(torch.autograd.Function):
+    """y[b] = act(conv(x[b] ∘ f_in[b], W) ∘ f_out[b] + bias[b]) with per-example channel tables f_in [B, Cin], f_out / bias
+    [B, Cout] (include/ed2b200.h: ed2_conv_factor_fwd / _bwd): Conv2DBatchEnsemble and Conv2DRank1.  Returns y [M, Cout]."""
+
+    @staticmethod
+    def forward(ctx, x, kernel2d, f_in, f_out, bias_tab, kernel_size, strides, padding, act, dtype):
+        lib = _lib.load()
+        dev = x.device
+        xc = x.contiguous()
+        if xc.dtype != dtype:
+            xc = xc.to(dtype)
+        g = conv_geometry(xc.shape, kernel_size, strides, padding)
+        ho, wo = conv_out_size(g)
+        M, K, O = g.batch * ho * wo, g.kh * g.kw * g.channels, kernel2d.shape[1]
+        w_lp = kernel2d if dtype == torch.float32 else ops.cast(kernel2d, dtype)
+        xa, y, z = _new(M, K, dtype, dev), _new(M, O, dtype, dev), _new(M, O, dtype, dev)
+        a = _lib.ConvFactorFwd()
+        a.geom, a.dtype, a.out_channels, a.act = g, _compute_dt(dtype), O, act
+        a.x, a.w_lp, a.w_ld = xc.data_ptr(), w_lp.data_ptr(), _lib.ld(w_lp)
+        a.f_in, a.f_out, a.bias = _p(f_in), f_out.data_ptr(), _p(bias_tab)
+        a.xa, a.xa_ld, a.y, a.y_ld, a.z, a.z_ld = xa.data_ptr(), _lib.ld(xa), y.data_ptr(), _lib.ld(y), z.data_ptr(), _lib.ld(z)
+        _lib.check(lib.ed2_conv_factor_fwd(C.byref(a), _lib.stream_ptr()), "ed2_conv_factor_fwd")
+        ctx.save_for_backward(xc, xa, y, z, w_lp, f_out, *([f_in] if f_in is not None else []))
+        ctx.meta = (g, act, dtype, bias_tab is not None, x.dtype, f_in is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        g, act, dtype, has_bias, x_dtype, has_fin = ctx.meta
+        xc, xa, y, z, w_lp, f_out = ctx.saved_tensors[:6]
+        f_in = ctx.saved_tensors[6] if has_fin else None
+        dev = xc.device
+        M, O = y.shape
+        K = xa.shape[1]
+        gyc = as_compute(gy, dtype)
+        need_dx = ctx.needs_input_grad[0]
+        need_fin = has_fin and ctx.needs_input_grad[2]
+        f32 = dict(dtype=torch.float32, device=dev)
+        dz = _new(M, O, dtype, dev)
+        dw = torch.empty(K, O, **f32)
+        df_out = torch.empty(g.batch, O, **f32)
+        dbias = torch.empty(g.batch, O, **f32) if has_bias else None
+        a = _lib.ConvFactorBwd()
+        a.geom, a.dtype, a.out_channels, a.act = g, _compute_dt(dtype), O, act
+        a.gy, a.gy_ld, a.y, a.y_ld, a.z, a.z_ld = gyc.data_ptr(), _lib.ld(gyc), y.data_ptr(), _lib.ld(y), z.data_ptr(), _lib.ld(z)
+        a.x, a.xa, a.xa_ld, a.w_lp, a.w_ld = xc.data_ptr(), xa.data_ptr(), _lib.ld(xa), w_lp.data_ptr(), _lib.ld(w_lp)
+        a.f_in, a.f_out = _p(f_in), f_out.data_ptr()
+        a.dz, a.dz_ld = dz.data_ptr(), _lib.ld(dz)
+        dx = df_in = None
+        if need_dx or need_fin:
+            dxa = _new(M, K, dtype, dev)
+            gimg = torch.empty(tuple(xc.shape), dtype=dtype, device=dev)
+            a.dxa, a.dxa_ld, a.gimg = dxa.data_ptr(), _lib.ld(dxa), gimg.data_ptr()
+            if need_dx:
+                dx = torch.empty(tuple(xc.shape), dtype=dtype, device=dev)
+                a.dx = dx.data_ptr()
+            if has_fin:
+                df_in = torch.empty(g.batch, g.channels, **f32)
+                a.df_in = df_in.data_ptr()
+        a.dw, a.df_out, a.dbias = dw.data_ptr(), df_out.data_ptr(), _p(dbias)
+        _lib.check(lib.ed2_conv_factor_bwd(C.byref(a), _lib.stream_ptr()), "ed2_conv_factor_bwd")
+        if dx is not None and dx.dtype != x_dtype:
+            dx = dx.to(x_dtype)
+        return dx, dw, df_in, df_out, dbias, None, None, None, None, None
+
+
 class ExpandTable(torch.autograd.Function):
     """out[b, t*C + c] = src[b // rows_per_entry, c] for t < reps: a per-member / per-example channel table laid out for
     the patch matrix (reps = kh*kw) or for the output channels (reps = 1); fp32."""

@@ -46,6 +46,9 @@ class _Conv2DBase(Layer):
         ho, wo = F.conv_out_size(g)
         return cols, ho, wo
 
+    def _out_hw(self, x):
+        return F.conv_out_size(F.conv_geometry(x.shape, self.kernel_size, self.strides, self.padding))
+
     def _conv_config(self):
         return dict(filters=self.filters, kernel_size=self.kernel_size, strides=self.strides, padding=self.padding,
                     data_format=self.data_format, dilation_rate=(1, 1), activation=self.activation)
@@ -204,14 +207,12 @@ class Conv2DBatchEnsemble(_Conv2DBase):
             raise ValueError(f"batch size {B} is not divisible by ensemble_size {E}")
         n = B // E
         kh, kw = self.kernel_size
-        cols, ho, wo = self._patches(inputs)
-        K = cols.shape[1]
-        a_tab = F.ExpandTable.apply(self.alpha, B, n, kh * kw)
+        a_tab = F.ExpandTable.apply(self.alpha, B, n, 1)
         g_tab = F.ExpandTable.apply(self.gamma, B, n, 1)
         b_tab = F.ExpandTable.apply(self.ensemble_bias, B, n, 1) if self.ensemble_bias is not None else None
-        y = F.BatchEnsembleDense.apply(cols, self.kernel.reshape(K, self.filters), a_tab, g_tab, b_tab, self._act, B,
-                                       self.compute_dtype)
-        return y.reshape(B, ho, wo, self.filters)
+        y = F.ConvFactorized.apply(inputs, self.kernel.reshape(kh * kw * inputs.shape[-1], self.filters), a_tab, g_tab,
+                                   b_tab, self.kernel_size, self.strides, self.padding, self._act, self.compute_dtype)
+        return y.reshape(B, *self._out_hw(inputs), self.filters)
 
     @property
     def losses(self):
@@ -288,13 +289,10 @@ class Conv2DRank1(_Conv2DBase):
         mu_s, rho_s = self._fast(self.gamma_initializer, self.gamma)
         r = F.Rank1Factors.apply(mu_r, rho_r, self._noise("eps_alpha", S_R, per_example=n), B, E, clip)
         s = F.Rank1Factors.apply(mu_s, rho_s, self._noise("eps_gamma", S_S, per_example=n), B, E, clip)
-        cols, ho, wo = self._patches(inputs)
-        K = cols.shape[1]
-        a_tab = F.ExpandTable.apply(r, B, 1, kh * kw)
         b_tab = F.ExpandTable.apply(self.ensemble_bias, B, n, 1) if self.ensemble_bias is not None else None
-        y = F.BatchEnsembleDense.apply(cols, self.kernel.reshape(K, self.filters), a_tab, s, b_tab, self._act, B,
-                                       self.compute_dtype)
-        return y.reshape(B, ho, wo, self.filters)
+        y = F.ConvFactorized.apply(inputs, self.kernel.reshape(kh * kw * inputs.shape[-1], self.filters), r, s, b_tab,
+                                   self.kernel_size, self.strides, self.padding, self._act, self.compute_dtype)
+        return y.reshape(B, *self._out_hw(inputs), self.filters)
 
     @property
     def losses(self):

@@ -524,6 +524,38 @@ int ed2_im2col(const ed2_conv_geometry* g, const void* x, int dtype, void* cols,
 /* adjoint of ed2_im2col in gather form (no atomics): dx contiguous NHWC `dx_dtype` */
 int ed2_col2im(const ed2_conv_geometry* g, const void* dcols, int dtype, long long cols_ld, void* dx, int dx_dtype,
                void* stream);
+/* Factorised convolution (Conv2DBatchEnsemble :681-699, Conv2DRank1 :1976-2020, multiplicative):
+ *   y[b] = act( conv(x[b] ∘ f_in[b], W) ∘ f_out[b] + bias[b] ),   f_in [B][Cin], f_out / bias [B][Cout] fp32 tables
+ * forward : xa = im2col(x ∘ f_in) in ONE gather, then the tcgen05 GEMM xa·W with the per-example scale / bias / activation
+ *           in its epilogue (rows-per-member = Ho*Wo); z = the un-scaled product (saved for the backward).
+ * backward: dz = gy∘act'(y)∘f_out with df_out / dbias reduced per example, dW = xaᵀ·dz (K slices when the output is a
+ *           handful of tiles), dxa = dz·Wᵀ, image-space gradient by col2im, then dx = g∘f_in and df_in = sum_hw g∘x. */
+typedef struct {
+  ed2_conv_geometry geom;
+  int dtype, out_channels, act;
+  const void* x;                      /* [B][H][W][Cin] dtype, contiguous */
+  const void* w_lp; int w_ld;         /* [kh*kw*Cin][Cout] dtype */
+  const float* f_in;                  /* [B][Cin] or NULL */
+  const float* f_out;                 /* [B][Cout] */
+  const float* bias;                  /* [B][Cout] or NULL */
+  void* xa; int xa_ld;                /* [B*Ho*Wo][kh*kw*Cin] dtype: saved */
+  void* y; int y_ld; void* z; int z_ld;  /* [B*Ho*Wo][Cout] dtype */
+} ed2_conv_factor_fwd_args;
+int ed2_conv_factor_fwd(const ed2_conv_factor_fwd_args* a, void* stream);
+typedef struct {
+  ed2_conv_geometry geom;
+  int dtype, out_channels, act;
+  const void* gy; int gy_ld; const void* y; int y_ld; const void* z; int z_ld;
+  const void* x; const void* xa; int xa_ld; const void* w_lp; int w_ld;
+  const float* f_in; const float* f_out;
+  void* dz; int dz_ld;                /* workspace [B*Ho*Wo][Cout] dtype */
+  void* dxa; int dxa_ld;              /* workspace [B*Ho*Wo][kh*kw*Cin] dtype (NULL: no input-side gradients) */
+  void* gimg;                         /* workspace [B][H][W][Cin] dtype */
+  void* dx;                           /* [B][H][W][Cin] dtype or NULL */
+  float* dw;                          /* [kh*kw*Cin][Cout] fp32 */
+  float* df_in; float* df_out; float* dbias;  /* [B][Cin], [B][Cout], [B][Cout] (df_in / dbias may be NULL) */
+} ed2_conv_factor_bwd_args;
+int ed2_conv_factor_bwd(const ed2_conv_factor_bwd_args* a, void* stream);
 /* out[b][t*C + c] = src[b / rows_per_entry][c], t < reps: a per-member ([E][C], rows_per_entry = B / E) or per-example
  * ([B][C], rows_per_entry = 1) channel table laid out for the patch matrix (reps = kh*kw) or the output (reps = 1) */
 int ed2_expand_table(const float* src, float* out, int batch, int channels, int rows_per_entry, int reps, void* stream);

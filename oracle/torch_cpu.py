@@ -144,6 +144,37 @@ def time_rank1_mlp(dims, batch, steps, warmup=1, ensemble_size=4, threads=None):
     return _time(lambda: model.step(x, labels), batch, steps, warmup, threads)
 
 
+def time_rank1_conv(batch, height, width, channels, n_layers, steps, warmup=1, ensemble_size=4, threads=None):
+    """Stacked Conv2DRank1 3x3 'same' layers as the reference computes them (convolutional.py:1968-2020): per-example
+    alpha / gamma samples [B, C] broadcast over the spatial axes, x * alpha -> conv2d -> * gamma + bias."""
+    g = torch.Generator().manual_seed(1234)
+    E, n = ensemble_size, batch // ensemble_size
+    x = torch.randn(batch, channels, height, width, generator=g)
+    labels = torch.randint(0, channels, (batch,), generator=g)
+    rho0 = float(torch.log(torch.expm1(torch.tensor((1e-3 / (1 - 1e-3)) ** 0.5))))
+    params = []
+    for _ in range(n_layers):
+        w = (torch.randn(channels, channels, 3, 3, generator=g) * (1.0 / (9 * channels) ** 0.5)).requires_grad_(True)
+        sign = lambda shape: (torch.randint(0, 2, shape, generator=g).float() * 2 - 1)  # noqa: E731
+        params.append((w, sign((E, channels)).requires_grad_(True), torch.full((E, channels), rho0, requires_grad=True),
+                       sign((E, channels)).requires_grad_(True), torch.full((E, channels), rho0, requires_grad=True),
+                       torch.zeros(E, channels, requires_grad=True)))
+
+    def step():
+        h, kl = x, 0.0
+        for li, (w, mr, rr, ms, rs, b) in enumerate(params):
+            rep = lambda t: t.repeat_interleave(n, 0)  # noqa: E731
+            alpha = torch.clamp(rep(mr) + rep(_softplus(rr)) * torch.randn(batch, channels), -10, 10)[:, :, None, None]
+            gamma = torch.clamp(rep(ms) + rep(_softplus(rs)) * torch.randn(batch, channels), -10, 10)[:, :, None, None]
+            z = torch.nn.functional.conv2d(h * alpha, w, padding=1) * gamma + rep(b)[:, :, None, None]
+            h = torch.relu(z) if li < n_layers - 1 else z
+            kl = kl + Rank1MLP._kl(mr, rr, 1.0 / 50000) + Rank1MLP._kl(ms, rs, 1.0 / 50000)
+        loss = torch.nn.functional.cross_entropy(h.mean(dim=(2, 3)), labels) + kl
+        return loss.detach(), torch.autograd.grad(loss, [p for t in params for p in t])
+
+    return _time(step, batch, steps, warmup, threads)
+
+
 class BatchEnsembleMLP:
     """cfg1: DenseBatchEnsemble MLP (dense.py:551-584, rank-1 branch): reshape to [E, n, I], x * alpha, matmul,
     * gamma, + bias, activation, reshape back — each a separate eager op."""
