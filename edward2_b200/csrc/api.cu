@@ -718,6 +718,24 @@ int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream) {
   return ED2_OK;
 }
 
+// ------------------------------------------------------------------------------------------ heteroscedastic heads
+int ed2_mc_softmax_fa_fwd(const float* loc, const float* fac, const float* diag_raw, const float* sngp_var, float w_het,
+                          float w_sngp, ed2_noise noise, int batch, int num_samples, int num_classes, int num_factors,
+                          int share_samples, float temperature, float eps, float* probs_mean, float* logits,
+                          float* variance, void* stream) {
+  if (temperature <= 0.f) return set_error(ED2_ERR_BAD_ARG, "mc_softmax: temperature must be positive");
+  return k_mc_softmax_fwd(loc, fac, diag_raw, sngp_var, w_het, w_sngp, N(noise), batch, num_samples, num_classes,
+                          num_factors, share_samples, temperature, eps, probs_mean, logits, variance, S(stream));
+}
+int ed2_mc_softmax_fa_bwd(const float* g, const float* probs_mean, const float* loc, const float* fac,
+                          const float* diag_raw, ed2_noise noise, int batch, int num_samples, int num_classes,
+                          int num_factors, int share_samples, float temperature, float eps, float* dloc, float* dfac,
+                          float* ddiag_raw, void* stream) {
+  if (temperature <= 0.f) return set_error(ED2_ERR_BAD_ARG, "mc_softmax: temperature must be positive");
+  return k_mc_softmax_bwd(g, probs_mean, loc, fac, diag_raw, N(noise), batch, num_samples, num_classes, num_factors,
+                          share_samples, temperature, eps, dloc, dfac, ddiag_raw, S(stream));
+}
+
 // ------------------------------------------------------------------------------------------ Conv2D support
 namespace {
 ConvArgs conv_args(const ed2_conv_geometry* g) {

@@ -190,4 +190,12 @@ int k_expand_table_bwd(const float* dout, float* dsrc, int B, int C, int rows_pe
 int k_rank1_factor_bwd(const float* df, const float* mu, const float* rho, Noise eps, int E, int n, int C, float lo, float hi,
                        float* dmu, float* drho, cudaStream_t s);
 
+// ---- Monte-Carlo softmax of the heteroscedastic heads (mcsoftmax.cu; heteroscedastic.py:178-250,749-785, hetsngp.py:143-170)
+int k_mc_softmax_fwd(const float* loc, const float* fac, const float* diag_raw, const float* sngp_var, float w_het,
+                     float w_sngp, Noise noise, int B, int S, int K, int F, int shared, float temperature, float eps,
+                     float* probs_mean, float* logits, float* variance, cudaStream_t s);
+int k_mc_softmax_bwd(const float* g, const float* probs_mean, const float* loc, const float* fac, const float* diag_raw,
+                     Noise noise, int B, int S, int K, int F, int shared, float temperature, float eps, float* dloc,
+                     float* dfac, float* ddiag_raw, cudaStream_t s);
+
 }  // namespace ed2

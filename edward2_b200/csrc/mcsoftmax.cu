@@ -1,0 +1,319 @@
+// Monte-Carlo softmax of the heteroscedastic output layers (edward2/tensorflow/layers/heteroscedastic.py:178-250
+// _compute_mc_samples / _compute_predictive_mean / _compute_predictive_variance, :749-785 factor-analysis noise;
+// edward2/tensorflow/layers/hetsngp.py:143-170 variance mixing of HeteroscedasticSNGPLayer):
+//
+//   latent[b,s,k] = loc[b,k] + sum_f V[b,k,f] z[b,s,f] + diag[b,k] e[b,s,k],   z, e ~ N(0, 1)
+//   probs_mean[b,k] = mean_s softmax_k(latent / T),   logits = log(clip(probs_mean, eps, 1))
+//   diag = softplus(diag_raw) + 1e-3;  eval with an SNGP variance: diag <- sqrt(w_het diag² + w_sngp var[b])
+//
+// The reference materialises [S, B, F] and [S, B, K] noise tensors and an [B, S, K] latent tensor (S = 1000 samples).
+// Here one WARP owns one example and one LANE one sample at a time: the lane draws its sample's F + K normals from
+// Philox (sample (b, s) owns the element range [(b S + s) P, +P), P = round8(F) + round8(K): z first, then e, each
+// 8-aligned so a Philox block never straddles the two), evaluates latent -> softmax in registers and accumulates the
+// class probabilities; nothing of size B x S ever exists.  The backward regenerates the same noise:
+//   u = g / probs_mean / S;  dlatent_s = p_s ∘ (u - <p_s, u>) / T;  dloc = sum_s dlatent_s,
+//   ddiag = sum_s dlatent_s ∘ e_s,  dV[k,f] = sum_s dlatent_s[k] z_s[f]  (per-warp shared-memory outer products).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "kernels.h"
+#include "philox.cuh"
+#include "status.h"
+
+namespace ed2 {
+namespace {
+
+constexpr int kWarps = 2;   // examples per block
+constexpr int kFMax = 16;   // num_factors <= 16
+constexpr float kMinScale = 1e-3f;  // MIN_SCALE_MONTE_CARLO, heteroscedastic.py:24
+
+__device__ __forceinline__ float softplus_d(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct McArgs {
+  const float* loc;       // [B][K]
+  const float* fac;       // [B][K*F] factor loadings (row-major [K][F] per example)
+  const float* diag_raw;  // [B][K] pre-softplus
+  const float* sngp_var;  // [B] or nullptr (eval: variance mixing)
+  float w_het, w_sngp;
+  Noise noise;            // normal stream; injected: [NB][S][P] fp32
+  int B, S, K, F;
+  int shared;             // share_samples_across_batch
+  float inv_t, eps;
+  float* probs_mean;      // [B][K]
+  float* logits;          // [B][K]
+  float* variance;        // [B][K] or nullptr
+  // backward
+  const float* g;         // [B][K] dL/dlogits
+  float* dloc; float* dfac; float* ddiag_raw;
+};
+
+// the P = FP + KP normals of sample (nb, s): z[f] and e[k] (8-aligned halves)
+template <int KMAX>
+__device__ __forceinline__ void draw_sample(const McArgs& a, uint64_t key, long long sample, int FP, int KP, float (&z)[kFMax],
+                                            float (&e)[KMAX]) {
+  const long long base = sample * (FP + KP);
+  if (a.noise.injected != nullptr) {
+#pragma unroll
+    for (int f = 0; f < kFMax; ++f) z[f] = f < a.F ? __ldg(a.noise.injected + base + f) : 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) e[k] = k < a.K ? __ldg(a.noise.injected + base + FP + k) : 0.f;
+    return;
+  }
+#pragma unroll
+  for (int fb = 0; fb < kFMax / 8; ++fb) {
+    float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (fb * 8 < a.F) philox_normal8<false>(key, a.noise.stream, static_cast<uint64_t>((base >> 3) + fb), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[fb * 8 + j] = t[j];
+  }
+#pragma unroll
+  for (int kb = 0; kb < KMAX / 8; ++kb) {
+    float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (kb * 8 < a.K) philox_normal8<false>(key, a.noise.stream, static_cast<uint64_t>(((base + FP) >> 3) + kb), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[kb * 8 + j] = t[j];
+  }
+}
+
+// softmax probabilities of one sample (registers): p[k], k < K
+template <int KMAX>
+__device__ __forceinline__ void sample_probs(const McArgs& a, const float* sloc, const float* sfac, const float* sdiag,
+                                             const float (&z)[kFMax], const float (&e)[KMAX], float (&p)[KMAX]) {
+  float m = -3.0e38f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    float lat = -3.0e38f;
+    if (k < a.K) {
+      lat = fmaf(sdiag[k], e[k], sloc[k]);
+#pragma unroll
+      for (int f = 0; f < kFMax; ++f)
+        if (f < a.F) lat = fmaf(sfac[k * a.F + f], z[f], lat);
+      lat *= a.inv_t;
+      m = fmaxf(m, lat);
+    }
+    p[k] = lat;
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    p[k] = k < a.K ? expf(p[k] - m) : 0.f;
+    sum += p[k];
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) p[k] *= inv;
+}
+
+// per-warp staging of the example's parameters: sloc[K], sdiag[K] (effective scale), sfac[K*F]
+__device__ __forceinline__ void stage_params(const McArgs& a, int b, int lane, float* sloc, float* sdiag, float* sfac) {
+  for (int k = lane; k < a.K; k += 32) {
+    sloc[k] = __ldg(a.loc + static_cast<long long>(b) * a.K + k);
+    float d = softplus_d(__ldg(a.diag_raw + static_cast<long long>(b) * a.K + k)) + kMinScale;
+    if (a.sngp_var != nullptr) d = sqrtf(a.w_het * d * d + a.w_sngp * __ldg(a.sngp_var + b));
+    sdiag[k] = d;
+  }
+  for (int i = lane; i < a.K * a.F; i += 32) sfac[i] = __ldg(a.fac + static_cast<long long>(b) * a.K * a.F + i);
+  __syncwarp();
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(kWarps * 32) mc_softmax_fwd_kernel(McArgs a) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kWarps + warp;
+  if (b >= a.B) return;
+  const int per_warp = a.K * a.F + 2 * a.K;
+  float* sfac = smem + warp * per_warp;
+  float* sloc = sfac + a.K * a.F;
+  float* sdiag = sloc + a.K;
+  stage_params(a, b, lane, sloc, sdiag, sfac);
+  const int FP = (a.F + 7) & ~7, KP = (a.K + 7) & ~7;
+  const uint64_t key = noise_key(a.noise);
+  const long long nb = a.shared ? 0 : (a.noise.injected != nullptr ? b : noise_row(a.noise, b));
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  for (int s = lane; s < a.S; s += 32) {
+    float z[kFMax], e[KMAX], p[KMAX];
+    draw_sample<KMAX>(a, key, nb * a.S + s, FP, KP, z, e);
+    sample_probs<KMAX>(a, sloc, sfac, sdiag, z, e, p);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) acc[k] += p[k];
+  }
+  const float inv_s = 1.f / static_cast<float>(a.S);
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < a.K) {
+      acc[k] = warp_sum(acc[k]) * inv_s;
+      if (lane == 0) {
+        a.probs_mean[static_cast<long long>(b) * a.K + k] = acc[k];
+        a.logits[static_cast<long long>(b) * a.K + k] = logf(fminf(fmaxf(acc[k], a.eps), 1.f));
+      }
+    }
+  }
+  if (a.variance == nullptr) return;
+  // second pass over the same samples: total variance mean_s (p_s - mean)^2 (heteroscedastic.py:246-250)
+  float var[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) var[k] = 0.f;
+  for (int s = lane; s < a.S; s += 32) {
+    float z[kFMax], e[KMAX], p[KMAX];
+    draw_sample<KMAX>(a, key, nb * a.S + s, FP, KP, z, e);
+    sample_probs<KMAX>(a, sloc, sfac, sdiag, z, e, p);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) var[k] += (p[k] - acc[k]) * (p[k] - acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < a.K) {
+      const float v = warp_sum(var[k]) * inv_s;
+      if (lane == 0) a.variance[static_cast<long long>(b) * a.K + k] = v;
+    }
+  }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kWarps + warp;
+  if (b >= a.B) return;
+  const int KF = a.K * a.F, row = a.K + a.F;
+  const int per_warp = KF + 3 * a.K + 32 * row;
+  float* sfac = smem + warp * per_warp;
+  float* sloc = sfac + KF;
+  float* sdiag = sloc + a.K;
+  float* su = sdiag + a.K;
+  float* scratch = su + a.K;  // [32][K + F]: dlatent then z of each lane's current sample
+  stage_params(a, b, lane, sloc, sdiag, sfac);
+  const float inv_s = 1.f / static_cast<float>(a.S);
+  for (int k = lane; k < a.K; k += 32) {
+    const float pm = __ldg(a.probs_mean + static_cast<long long>(b) * a.K + k);
+    su[k] = (pm > a.eps && pm <= 1.f) ? __ldg(a.g + static_cast<long long>(b) * a.K + k) / pm * inv_s : 0.f;  // clip: zero gradient outside
+  }
+  __syncwarp();
+  const int FP = (a.F + 7) & ~7, KP = (a.K + 7) & ~7;
+  const uint64_t key = noise_key(a.noise);
+  const long long nb = a.shared ? 0 : (a.noise.injected != nullptr ? b : noise_row(a.noise, b));
+  float dl[KMAX], dd[KMAX];
+  constexpr int kSlots = (KMAX * kFMax + 31) / 32;  // outer-product entries owned by one lane
+  float dv[kSlots];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) { dl[k] = 0.f; dd[k] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < kSlots; ++i) dv[i] = 0.f;
+  const int rounds = (a.S + 31) / 32;
+  for (int r = 0; r < rounds; ++r) {
+    const int s = r * 32 + lane;
+    const bool live = s < a.S;
+    float z[kFMax], e[KMAX], p[KMAX];
+    if (live) {
+      draw_sample<KMAX>(a, key, nb * a.S + s, FP, KP, z, e);
+      sample_probs<KMAX>(a, sloc, sfac, sdiag, z, e, p);
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < a.K && live) dot = fmaf(p[k], su[k], dot);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < a.K) {
+        const float d = live ? a.inv_t * p[k] * (su[k] - dot) : 0.f;
+        dl[k] += d;
+        dd[k] = fmaf(d, live ? e[k] : 0.f, dd[k]);
+        scratch[lane * row + k] = d;
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < kFMax; ++f)
+      if (f < a.F) scratch[lane * row + a.K + f] = live ? z[f] : 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kSlots; ++i) {
+      const int idx = i * 32 + lane;
+      if (idx < KF) {
+        const int k = idx / a.F, f = idx - k * a.F;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) acc = fmaf(scratch[l * row + k], scratch[l * row + a.K + f], acc);
+        dv[i] += acc;
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < a.K) {
+      const float tl = warp_sum(dl[k]), td = warp_sum(dd[k]);
+      if (lane == 0) {
+        a.dloc[static_cast<long long>(b) * a.K + k] = tl;
+        // diag = softplus(raw) + 1e-3: chain through the softplus
+        const float raw = __ldg(a.diag_raw + static_cast<long long>(b) * a.K + k);
+        a.ddiag_raw[static_cast<long long>(b) * a.K + k] = td / (1.f + expf(-raw));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kSlots; ++i) {
+    const int idx = i * 32 + lane;
+    if (idx < KF) a.dfac[static_cast<long long>(b) * KF + idx] = dv[i];
+  }
+}
+
+int check(const McArgs& a) {
+  if (a.B <= 0 || a.S <= 0 || a.K < 2 || a.F < 1) return set_error(ED2_ERR_BAD_SHAPE, "mc_softmax: B=%d S=%d K=%d F=%d", a.B, a.S, a.K, a.F);
+  if (a.K > 64) return set_error(ED2_ERR_BAD_SHAPE, "mc_softmax: num_classes %d > 64 is not built", a.K);
+  if (a.F > kFMax) return set_error(ED2_ERR_BAD_SHAPE, "mc_softmax: num_factors %d > %d is not built", a.F, kFMax);
+  return ED2_OK;
+}
+
+}  // namespace
+
+int k_mc_softmax_fwd(const float* loc, const float* fac, const float* diag_raw, const float* sngp_var, float w_het,
+                     float w_sngp, Noise noise, int B, int S, int K, int F, int shared, float temperature, float eps,
+                     float* probs_mean, float* logits, float* variance, cudaStream_t s) {
+  McArgs a{};
+  a.loc = loc; a.fac = fac; a.diag_raw = diag_raw; a.sngp_var = sngp_var; a.w_het = w_het; a.w_sngp = w_sngp;
+  a.noise = noise; a.B = B; a.S = S; a.K = K; a.F = F; a.shared = shared; a.inv_t = 1.f / temperature; a.eps = eps;
+  a.probs_mean = probs_mean; a.logits = logits; a.variance = variance;
+  const int st = check(a);
+  if (st != ED2_OK) return st;
+  const size_t smem = sizeof(float) * kWarps * (static_cast<size_t>(K) * F + 2 * K);
+  const int grid = (B + kWarps - 1) / kWarps;
+  if (K <= 16) mc_softmax_fwd_kernel<16><<<grid, kWarps * 32, smem, s>>>(a);
+  else if (K <= 32) mc_softmax_fwd_kernel<32><<<grid, kWarps * 32, smem, s>>>(a);
+  else mc_softmax_fwd_kernel<64><<<grid, kWarps * 32, smem, s>>>(a);
+  count_launch();
+  return check_launch("mc_softmax_fwd");
+}
+
+int k_mc_softmax_bwd(const float* g, const float* probs_mean, const float* loc, const float* fac, const float* diag_raw,
+                     Noise noise, int B, int S, int K, int F, int shared, float temperature, float eps, float* dloc,
+                     float* dfac, float* ddiag_raw, cudaStream_t s) {
+  McArgs a{};
+  a.loc = loc; a.fac = fac; a.diag_raw = diag_raw; a.noise = noise;
+  a.B = B; a.S = S; a.K = K; a.F = F; a.shared = shared; a.inv_t = 1.f / temperature; a.eps = eps;
+  a.probs_mean = const_cast<float*>(probs_mean); a.g = g; a.dloc = dloc; a.dfac = dfac; a.ddiag_raw = ddiag_raw;
+  const int st = check(a);
+  if (st != ED2_OK) return st;
+  const size_t smem = sizeof(float) * kWarps * (static_cast<size_t>(K) * F + 3 * K + 32 * (K + F));
+  const int grid = (B + kWarps - 1) / kWarps;
+  if (K <= 16) mc_softmax_bwd_kernel<16><<<grid, kWarps * 32, smem, s>>>(a);
+  else if (K <= 32) mc_softmax_bwd_kernel<32><<<grid, kWarps * 32, smem, s>>>(a);
+  else mc_softmax_bwd_kernel<64><<<grid, kWarps * 32, smem, s>>>(a);
+  count_launch();
+  return check_launch("mc_softmax_bwd");
+}
+
+}  // namespace ed2

@@ -1004,6 +1004,51 @@ class FlipoutPatches(torch.autograd.Function):
         return dx, dmu, drho, dbias, None, None, None, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------- heteroscedastic heads
+class MCSoftmaxFA(torch.autograd.Function):
+    """Monte-Carlo softmax with factor-analysis logit noise (include/ed2b200.h: ed2_mc_softmax_fa_fwd / _bwd).
+    Returns (logits, probs_mean, variance-or-empty); gradients flow from `logits` only (the reference trains on them)."""
+
+    @staticmethod
+    def forward(ctx, loc, fac, diag_raw, sngp_var, w_het, w_sngp, noise, num_samples, num_factors, share, temperature,
+                eps, want_variance):
+        lib = _lib.load()
+        B, K = loc.shape
+        dev = loc.device
+        loc32, fac32, d32 = (t.to(torch.float32).contiguous() for t in (loc, fac, diag_raw))
+        v32 = None if sngp_var is None else sngp_var.to(torch.float32).contiguous()
+        pm = torch.empty(B, K, dtype=torch.float32, device=dev)
+        logits = torch.empty(B, K, dtype=torch.float32, device=dev)
+        var = torch.empty(B, K, dtype=torch.float32, device=dev) if want_variance else None
+        _lib.check(lib.ed2_mc_softmax_fa_fwd(loc32.data_ptr(), fac32.data_ptr(), d32.data_ptr(), _p(v32), w_het, w_sngp,
+                                             noise.c(), B, num_samples, K, num_factors, int(share), temperature, eps,
+                                             pm.data_ptr(), logits.data_ptr(), _p(var), _lib.stream_ptr()),
+                   "ed2_mc_softmax_fa_fwd")
+        ctx.save_for_backward(loc32, fac32, d32, pm)
+        ctx.meta = (noise, num_samples, num_factors, share, temperature, eps, sngp_var is not None,
+                    (loc.dtype, fac.dtype, diag_raw.dtype))
+        ctx.mark_non_differentiable(pm)
+        if var is not None:
+            ctx.mark_non_differentiable(var)
+        return logits, pm, (var if var is not None else torch.empty(0, device=dev))
+
+    @staticmethod
+    def backward(ctx, g, _gpm, _gvar):
+        lib = _lib.load()
+        loc, fac, d, pm = ctx.saved_tensors
+        noise, S, Fn, share, temp, eps, mixed, dts = ctx.meta
+        if mixed:
+            raise RuntimeError("MCSoftmaxFA: the evaluation form (SNGP variance mixing) has no backward")
+        B, K = loc.shape
+        g32 = g.to(torch.float32).contiguous()
+        dloc, dfac, dd = torch.empty_like(loc), torch.empty_like(fac), torch.empty_like(d)
+        _lib.check(lib.ed2_mc_softmax_fa_bwd(g32.data_ptr(), pm.data_ptr(), loc.data_ptr(), fac.data_ptr(), d.data_ptr(),
+                                             noise.c(), B, S, K, Fn, int(share), temp, eps, dloc.data_ptr(),
+                                             dfac.data_ptr(), dd.data_ptr(), _lib.stream_ptr()), "ed2_mc_softmax_fa_bwd")
+        return (dloc.to(dts[0]), dfac.to(dts[1]), dd.to(dts[2]), None, None, None, None, None, None, None, None, None,
+                None)
+
+
 # ------------------------------------------------------------------------------------------------- KL regulariser
 class NormalKL(torch.autograd.Function):
     """scale * sum KL(N(mu, softplus(rho)+1e-7) || N(m, s)) as a 0-dim fp32 tensor (regularizers.py:175-186)."""

@@ -505,6 +505,26 @@ int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream);
 int ed2_flipout_fusable(int batch, int in_dim, int out_dim);
 
 /* ------------------------------------------------------------------------------------------------
+ * Heteroscedastic heads: MCSoftmaxDenseFA (edward2/tensorflow/layers/heteroscedastic.py:508, Monte-Carlo machinery
+ * :178-250, factor-analysis noise :749-785) and HeteroscedasticSNGPLayer (edward2/tensorflow/layers/hetsngp.py:25,
+ * variance mixing :143-170).  fp32.
+ *   latent[b,s,k] = loc[b,k] + sum_f fac[b,k,f] z[b,s,f] + diag[b,k] e[b,s,k],  z, e ~ N(0,1),  s < num_samples
+ *   diag = softplus(diag_raw) + 1e-3;  with sngp_var (evaluation): diag <- sqrt(w_het diag² + w_sngp sngp_var[b])
+ *   probs_mean = mean_s softmax(latent / temperature);  logits = log(clip(probs_mean, eps, 1));
+ *   variance (optional) = mean_s (softmax_s - probs_mean)²
+ * Noise: a normal stream; sample (b, s) owns elements [(row(b) S + s) P, +P), P = round8(F) + round8(K) (z, then e);
+ * injected: [batch][S][P] fp32.  share_samples: every example reads row 0.  num_classes <= 64, num_factors <= 16.
+ * The backward regenerates the samples: dloc, dfac, ddiag_raw from g = dL/dlogits (training form: no sngp_var). */
+int ed2_mc_softmax_fa_fwd(const float* loc, const float* fac, const float* diag_raw, const float* sngp_var, float w_het,
+                          float w_sngp, ed2_noise noise, int batch, int num_samples, int num_classes, int num_factors,
+                          int share_samples, float temperature, float eps, float* probs_mean, float* logits,
+                          float* variance, void* stream);
+int ed2_mc_softmax_fa_bwd(const float* g, const float* probs_mean, const float* loc, const float* fac,
+                          const float* diag_raw, ed2_noise noise, int batch, int num_samples, int num_classes,
+                          int num_factors, int share_samples, float temperature, float eps, float* dloc, float* dfac,
+                          float* ddiag_raw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Conv2D stochastic-weight layers (edward2/tensorflow/layers/convolutional.py:32 Conv2DReparameterization, :167
  * Conv2DFlipout, :560 Conv2DBatchEnsemble, :2056 Conv2DRank1).  Their per-example factors are channel vectors broadcast
  * over the spatial axes (:235-249, :681-699, :1976-1989), so on the patch matrix

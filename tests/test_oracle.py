@@ -565,3 +565,44 @@ def test_per_example_noise_is_a_function_of_the_global_row():
     # ungrouped (Flipout signs): a rank's rows are a contiguous block of the global batch
     s_full = op.per_example("sign", 3, 2, 24, 5)
     np.testing.assert_array_equal(op.per_example("sign", 3, 2, 8, 5, 16, 0, 0), s_full[16:24])
+
+
+def test_heteroscedastic_oracle_gradients_and_identities():
+    """oracle/heteroscedastic.py: closed-form gradients == float64 autograd of the reference recipe
+    (heteroscedastic.py:178-226, 749-785); zero scale -> softmax(loc); probabilities sum to one; the HetSNGP variance
+    mixing (hetsngp.py:160-168) reduces to the heteroscedastic scale when sngp_var_weight = 0."""
+    from oracle import heteroscedastic as oh
+
+    rng = np.random.default_rng(11)
+    B, S, K, Fn, T = 5, 40, 6, 3, 0.7
+    loc, fac, draw = rng.standard_normal((B, K)), rng.standard_normal((B, K * Fn)) * 0.5, rng.standard_normal((B, K))
+    z, e = rng.standard_normal((B, S, Fn)), rng.standard_normal((B, S, K))
+    logits, pm, var = oh.mc_softmax_fa(loc, fac, draw, z, e, T)
+    np.testing.assert_allclose(pm.sum(-1), 1.0, rtol=1e-12)
+    assert (var >= 0).all()
+    lt, ft, dt_ = (torch.tensor(t, requires_grad=True) for t in (loc, fac, draw))
+    diag = torch.nn.functional.softplus(dt_) + 1e-3
+    lat = lt[:, None, :] + torch.einsum("ijk,iak->iaj", ft.reshape(B, K, Fn), torch.tensor(z)) + torch.tensor(e) * diag[:, None, :]
+    pt = torch.softmax(lat / T, -1).mean(1)
+    lg = torch.log(torch.clamp(pt, 1e-7, 1.0))
+    g = rng.standard_normal((B, K))
+    (lg * torch.tensor(g)).sum().backward()
+    np.testing.assert_allclose(logits, lg.detach().numpy(), rtol=1e-12)
+    got = oh.mc_softmax_fa_bwd(loc, fac, draw, z, e, g, T)
+    for a, b_ in ((got["dloc"], lt.grad), (got["dfac"], ft.grad), (got["ddiag_raw"], dt_.grad)):
+        np.testing.assert_allclose(a, b_.numpy(), rtol=1e-9, atol=1e-12)
+    # shared samples: batch dimension 1 broadcasts
+    l2, _, _ = oh.mc_softmax_fa(loc, fac, draw, z[:1], e[:1], T)
+    l3, _, _ = oh.mc_softmax_fa(loc, fac, draw, np.repeat(z[:1], B, 0), np.repeat(e[:1], B, 0), T)
+    np.testing.assert_allclose(l2, l3, rtol=1e-12)
+    # no noise -> plain softmax; variance mixing with zero SNGP weight == heteroscedastic scale
+    l0, p0, _ = oh.mc_softmax_fa(loc, np.zeros_like(fac), np.full_like(draw, -800.0), z * 0, e * 0, 1.0)
+    ref = np.exp(loc - loc.max(-1, keepdims=True))
+    np.testing.assert_allclose(p0, ref / ref.sum(-1, keepdims=True), rtol=1e-12)
+    np.testing.assert_allclose(oh.effective_diag(draw, rng.random(B), 1.0, 0.0), oh.effective_diag(draw), rtol=1e-12)
+    # native noise layout: z and e are disjoint 8-aligned slices of one stream
+    zz, ee = oh.native_noise(5, 7, 3, 4, Fn, K)
+    assert zz.shape == (3, 4, Fn) and ee.shape == (3, 4, K)
+    flat = __import__("oracle.philox", fromlist=["normal"]).normal(5, 7, 3 * 4 * 16).reshape(3, 4, 16)
+    np.testing.assert_array_equal(zz, flat[:, :, :Fn])
+    np.testing.assert_array_equal(ee, flat[:, :, 8:8 + K])
