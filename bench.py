@@ -392,8 +392,46 @@ def wl_conv_rank1(ed, device, step_counter, rank, world):
                          "bf16; im2col + dense rank-1 path; fwd + dW of both layers + dX of the second")
 
 
+def wl_hetsngp(ed, device, step_counter, rank, world):
+    """SURVEY.md §8f-2 (next row): HeteroscedasticSNGPLayer head (hetsngp.py:25) on 512-dim features, batch 8192, 10
+    classes, 10 factors, D = 1024 random features, 1000 Monte-Carlo samples per example (the reference's default)."""
+    import torch
+
+    from edward2_b200 import functional as F
+
+    B, d, K, Fn, S, D = 8192, 512, 10, 10, 1000, 1024
+    head = ed.layers.HeteroscedasticSNGPLayer(K, num_factors=Fn, train_mc_samples=S, test_mc_samples=S, num_inducing=D,
+                                              gp_cov_momentum=0.999, gp_cov_ridge_penalty=1e-3, normalize_input=True,
+                                              dtype="bfloat16", seed=4040)
+    head.train()
+    with torch.no_grad():
+        head(torch.randn(256, d, device=device).to(torch.bfloat16), training=True)
+    head.step_counter = step_counter
+    gb = B * world
+
+    def step(x, y):
+        logits = head(x, training=True)
+        loss = F.SoftmaxCrossEntropy.apply(logits, y, gb)
+        F.backward(loss)
+        return loss.detach()
+
+    def cpu(steps):
+        from oracle import torch_cpu
+
+        rows = 1024
+        sps, dt, th = torch_cpu.time_hetsngp(d, D, K, Fn, S, rows, steps, warmup=1)
+        return sps, dt, th, f"{steps} train steps on {rows}-row batches (torch-CPU fp32 restatement, linear in rows)"
+
+    # tensor work: RFF fwd + dX, GP output layer, loc / scale / diag Dense layers (fwd + dW + dX), PhiT Phi
+    flops = 2.0 * B * d * D * 2 + 2.0 * B * D * K * 3 + 2.0 * B * d * (K * Fn + 2 * K) * 3 + 2.0 * B * D * D
+    return dict(step=step, params=list(head.parameters()), batch=B, in_dim=d, x_dtype=torch.bfloat16, classes=K, flops=flops,
+                cpu=cpu, dtype="bf16/f32", modules=head,
+                workload="hetsngp (SURVEY §8f-2): HeteroscedasticSNGPLayer train step, 512-dim features, batch 8192, 10 "
+                         "classes, 10 factors, D=1024, 1000 MC samples per example (393 M normals per direction)")
+
+
 WORKLOADS = {
-    "cfg4": wl_cfg4, "conv_rank1": wl_conv_rank1, "cfg2_reparam": wl_cfg2(False), "cfg2_flipout": wl_cfg2(True), "cfg1": wl_cfg1,
+    "cfg4": wl_cfg4, "conv_rank1": wl_conv_rank1, "hetsngp_train": wl_hetsngp, "cfg2_reparam": wl_cfg2(False), "cfg2_flipout": wl_cfg2(True), "cfg1": wl_cfg1,
     "cfg3_train": wl_sngp("cfg3", True), "cfg3_eval": wl_sngp("cfg3", False),
     "cfg5_train": wl_sngp("cfg5", True), "cfg5_eval": wl_sngp("cfg5", False),
 }

@@ -175,6 +175,39 @@ def time_rank1_conv(batch, height, width, channels, n_layers, steps, warmup=1, e
     return _time(step, batch, steps, warmup, threads)
 
 
+def time_hetsngp(in_dim, num_inducing, classes, factors, mc_samples, batch, steps, warmup=1, threads=None):
+    """HeteroscedasticSNGPLayer train step as the reference computes it (hetsngp.py:186-240, heteroscedastic.py:178-226,
+    749-785): materialised [S, B, F] / [S, B, K] noise, einsum to [B, S, K] latents, softmax, mean over samples."""
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, in_dim, generator=g)
+    labels = torch.randint(0, classes, (batch,), generator=g)
+    w_rf = torch.randn(in_dim, num_inducing, generator=g)
+    b_rf = torch.rand(num_inducing, generator=g) * 6.283185307179586
+    mk = lambda o: ((torch.randn(in_dim, o, generator=g) / in_dim ** 0.5).requires_grad_(True), torch.zeros(o, requires_grad=True))  # noqa: E731
+    beta = (torch.randn(num_inducing, classes, generator=g) * 0.05).requires_grad_(True)
+    (ws, bs), (wd, bd) = mk(classes * factors), mk(classes)
+    ln_g, ln_b = torch.ones(in_dim, requires_grad=True), torch.zeros(in_dim, requires_grad=True)
+    prec = torch.zeros(num_inducing, num_inducing)
+    params = [beta, ws, bs, wd, bd, ln_g, ln_b]
+
+    def step():
+        h = torch.nn.functional.layer_norm(x, (in_dim,), ln_g, ln_b, 1e-3)
+        phi = torch.cos(h @ w_rf + b_rf) * (2.0 / num_inducing) ** 0.5
+        loc = phi @ beta
+        with torch.no_grad():
+            prec.mul_(0.999).add_(phi.T @ phi, alpha=0.001 / batch)
+        fac = (x @ ws + bs).reshape(batch, classes, factors)
+        diag = torch.nn.functional.softplus(x @ wd + bd) + 1e-3
+        z = torch.randn(mc_samples, batch, factors).transpose(0, 1)
+        e = torch.randn(mc_samples, batch, classes).transpose(0, 1)
+        lat = loc[:, None, :] + torch.einsum("ijk,iak->iaj", fac, z) + e * diag[:, None, :]
+        pm = torch.softmax(lat, -1).mean(1)
+        loss = torch.nn.functional.nll_loss(torch.log(torch.clamp(pm, 1e-7, 1.0)), labels)
+        return loss.detach(), torch.autograd.grad(loss, params)
+
+    return _time(step, batch, steps, warmup, threads)
+
+
 class BatchEnsembleMLP:
     """cfg1: DenseBatchEnsemble MLP (dense.py:551-584, rank-1 branch): reshape to [E, n, I], x * alpha, matmul,
     * gamma, + bias, activation, reshape back — each a separate eager op."""

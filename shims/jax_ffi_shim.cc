@@ -201,6 +201,103 @@ ffi::Error FlipoutDenseBwd(cudaStream_t s, Any gy, Any y, Any x, Any xs, Any mu_
   return done(ed2_flipout_dense_bwd(&a, s));
 }
 
+// Fused DenseFlipout: one dual-accumulator launch per product pair (mu_lp / delta_lp drawn by Ed2SampleNormalWeights-style
+// calls beforehand; here they are inputs).  next_xs: the NEXT layer's x∘S (pass next_seed < 0 to skip).
+ffi::Error FlipoutFusedFwd(cudaStream_t s, Any x, Any xs_in, Any mu_lp, Any delta_lp, F32B bias, int32_t act, int64_t seed,
+                           int64_t next_seed, int64_t row0, int32_t xs_ready, Out<Any> y, Out<Any> xs, Out<Any> next_xs) {
+  ed2_flipout_fused_fwd_args a{};
+  a.batch = dim(x, 0); a.in_dim = dim(x, 1); a.out_dim = dim(mu_lp, 1); a.act = act;
+  a.x = x.untyped_data(); a.x_ld = a.in_dim;
+  a.xs = xs_ready ? const_cast<void*>(xs_in.untyped_data()) : xs->untyped_data(); a.xs_ld = a.in_dim; a.xs_ready = xs_ready;
+  a.sign_in = philox(seed, 2, row0); a.sign_out = philox(seed, 3, row0);
+  a.mu_lp = mu_lp.untyped_data(); a.mu_ld = a.out_dim;
+  a.delta_lp = delta_lp.untyped_data(); a.delta_ld = a.out_dim;
+  a.bias = bias.typed_data();
+  a.y = y->untyped_data(); a.y_ld = a.out_dim;
+  if (next_seed >= 0) {
+    a.next_xs = next_xs->untyped_data(); a.next_xs_ld = a.out_dim; a.next_sign_in = philox(next_seed, 2, row0);
+  }
+  return done(ed2_flipout_fused_fwd(&a, s));
+}
+ffi::Error FlipoutFusedBwd(cudaStream_t s, Any gy, Any y, Any x, Any xs, Any mu_lp, Any delta_lp, F32B mu, F32B rho,
+                           F64B kl_upstream, int32_t act, int64_t seed, int64_t row0, float kl_grad_scale, float prior_mean,
+                           float prior_std, Out<Any> dx, Out<F32B> dmu, Out<F32B> drho, Out<F32B> dbias, Out<Any> gp_ws,
+                           Out<Any> gt_ws) {
+  ed2_flipout_fused_bwd_args a{};
+  a.batch = dim(x, 0); a.in_dim = dim(x, 1); a.out_dim = dim(mu, 1); a.act = act; a.premade = 0;
+  a.gy = gy.untyped_data(); a.gy_ld = a.out_dim;
+  a.y = y.untyped_data(); a.y_ld = a.out_dim;
+  a.gp = gp_ws->untyped_data(); a.gp_ld = a.out_dim;
+  a.gt = gt_ws->untyped_data(); a.gt_ld = a.out_dim;
+  a.x = x.untyped_data(); a.x_ld = a.in_dim;
+  a.xs = xs.untyped_data(); a.xs_ld = a.in_dim;
+  a.mu_lp = mu_lp.untyped_data(); a.mu_ld = a.out_dim;
+  a.delta_lp = delta_lp.untyped_data(); a.delta_ld = a.out_dim;
+  a.mu = mu.typed_data(); a.rho = rho.typed_data(); a.eps = philox(seed, 0);
+  a.sign_in = philox(seed, 2, row0); a.sign_out = philox(seed, 3, row0);
+  a.dmu = dmu->typed_data(); a.drho = drho->typed_data(); a.dbias = dbias->typed_data();
+  a.kl_grad_scale = kl_grad_scale; a.prior_mean = prior_mean; a.prior_std = prior_std;
+  a.kl_upstream = kl_upstream.typed_data();
+  a.dx = dx->untyped_data(); a.dx_ld = a.in_dim;
+  return done(ed2_flipout_fused_bwd(&a, s));
+}
+
+// ---------------------------------------------------------------------------------------------- heteroscedastic heads
+// Monte-Carlo softmax with factor-analysis noise — edward2/jax/nn/heteroscedastic_lib.py / tensorflow heteroscedastic.py:178-253
+ffi::Error McSoftmaxFaFwd(cudaStream_t s, F32B loc, F32B fac, F32B diag_raw, int32_t num_samples, int32_t num_factors,
+                          int32_t share_samples, float temperature, float eps, int64_t seed, int64_t row0, Out<F32B> probs_mean,
+                          Out<F32B> logits, Out<F32B> variance) {
+  return done(ed2_mc_softmax_fa_fwd(loc.typed_data(), fac.typed_data(), diag_raw.typed_data(), nullptr, 1.f, 1.f,
+                                    philox(seed, 7, row0), dim(loc, 0), num_samples, dim(loc, 1), num_factors, share_samples,
+                                    temperature, eps, probs_mean->typed_data(), logits->typed_data(), variance->typed_data(),
+                                    s));
+}
+ffi::Error McSoftmaxFaBwd(cudaStream_t s, F32B g, F32B probs_mean, F32B loc, F32B fac, F32B diag_raw, int32_t num_samples,
+                          int32_t num_factors, int32_t share_samples, float temperature, float eps, int64_t seed, int64_t row0,
+                          Out<F32B> dloc, Out<F32B> dfac, Out<F32B> ddiag_raw) {
+  return done(ed2_mc_softmax_fa_bwd(g.typed_data(), probs_mean.typed_data(), loc.typed_data(), fac.typed_data(),
+                                    diag_raw.typed_data(), philox(seed, 7, row0), dim(loc, 0), num_samples, dim(loc, 1),
+                                    num_factors, share_samples, temperature, eps, dloc->typed_data(), dfac->typed_data(),
+                                    ddiag_raw->typed_data(), s));
+}
+
+// ---------------------------------------------------------------------------------------------- factorised Conv2D
+// y[b] = act(conv(x[b] ∘ f_in[b], W) ∘ f_out[b] + bias[b]) — Conv2DBatchEnsemble / Conv2DRank1 with per-example tables
+inline ed2_conv_geometry geometry(const Any& x, int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t same) {
+  ed2_conv_geometry g{};
+  g.batch = dim(x, 0); g.height = dim(x, 1); g.width = dim(x, 2); g.channels = dim(x, 3);
+  g.kh = kh; g.kw = kw; g.sh = sh; g.sw = sw; g.same = same;
+  return g;
+}
+ffi::Error ConvFactorFwd(cudaStream_t s, Any x, Any w, F32B f_in, F32B f_out, F32B bias, int32_t kh, int32_t kw, int32_t sh,
+                         int32_t sw, int32_t same, int32_t act, Out<Any> y, Out<Any> xa, Out<Any> z) {
+  ed2_conv_factor_fwd_args a{};
+  a.geom = geometry(x, kh, kw, sh, sw, same);
+  a.dtype = dt_of(x); a.out_channels = dim(w, 1); a.act = act;
+  a.x = x.untyped_data(); a.w_lp = w.untyped_data(); a.w_ld = a.out_channels;
+  a.f_in = f_in.typed_data(); a.f_out = f_out.typed_data(); a.bias = bias.typed_data();
+  a.xa = xa->untyped_data(); a.xa_ld = kh * kw * a.geom.channels;
+  a.y = y->untyped_data(); a.y_ld = a.out_channels; a.z = z->untyped_data(); a.z_ld = a.out_channels;
+  return done(ed2_conv_factor_fwd(&a, s));
+}
+ffi::Error ConvFactorBwd(cudaStream_t s, Any gy, Any y, Any z, Any x, Any xa, Any w, F32B f_in, F32B f_out, int32_t kh,
+                         int32_t kw, int32_t sh, int32_t sw, int32_t same, int32_t act, Out<Any> dx, Out<F32B> dw,
+                         Out<F32B> df_in, Out<F32B> df_out, Out<F32B> dbias, Out<Any> dz_ws, Out<Any> dxa_ws, Out<Any> gimg_ws) {
+  ed2_conv_factor_bwd_args a{};
+  a.geom = geometry(x, kh, kw, sh, sw, same);
+  a.dtype = dt_of(x); a.out_channels = dim(w, 1); a.act = act;
+  a.gy = gy.untyped_data(); a.gy_ld = a.out_channels; a.y = y.untyped_data(); a.y_ld = a.out_channels;
+  a.z = z.untyped_data(); a.z_ld = a.out_channels;
+  a.x = x.untyped_data(); a.xa = xa.untyped_data(); a.xa_ld = kh * kw * a.geom.channels;
+  a.w_lp = w.untyped_data(); a.w_ld = a.out_channels;
+  a.f_in = f_in.typed_data(); a.f_out = f_out.typed_data();
+  a.dz = dz_ws->untyped_data(); a.dz_ld = a.out_channels;
+  a.dxa = dxa_ws->untyped_data(); a.dxa_ld = a.xa_ld; a.gimg = gimg_ws->untyped_data();
+  a.dx = dx->untyped_data(); a.dw = dw->typed_data();
+  a.df_in = df_in->typed_data(); a.df_out = df_out->typed_data(); a.dbias = dbias->typed_data();
+  return done(ed2_conv_factor_bwd(&a, s));
+}
+
 // ---------------------------------------------------------------------------------------------- NormalKLDivergence
 ffi::Error NormalKlFwd(cudaStream_t s, F32B mu, F32B rho, float prior_mean, float prior_std, float scale, Out<F64B> kl) {
   return done(ed2_normal_kl_fwd(mu.typed_data(), rho.typed_data(), static_cast<long long>(mu.element_count()), prior_mean,
@@ -294,6 +391,29 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2FlipoutDenseBwd, FlipoutDenseBwd,
         .Attr<int32_t>("act").Attr<int64_t>("seed").Attr<int64_t>("row0").Attr<float>("kl_grad_scale")
         .Attr<float>("prior_mean").Attr<float>("prior_std")
         .Ret<Any>().Ret<F32B>().Ret<F32B>().Ret<F32B>().Ret<Any>().Ret<Any>().Ret<F32B>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2FlipoutFusedFwd, FlipoutFusedFwd,
+    ED2_STREAM.Arg<Any>().Arg<Any>().Arg<Any>().Arg<Any>().Arg<F32B>().Attr<int32_t>("act").Attr<int64_t>("seed")
+        .Attr<int64_t>("next_seed").Attr<int64_t>("row0").Attr<int32_t>("xs_ready").Ret<Any>().Ret<Any>().Ret<Any>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2FlipoutFusedBwd, FlipoutFusedBwd,
+    ED2_STREAM.Arg<Any>().Arg<Any>().Arg<Any>().Arg<Any>().Arg<Any>().Arg<Any>().Arg<F32B>().Arg<F32B>().Arg<F64B>()
+        .Attr<int32_t>("act").Attr<int64_t>("seed").Attr<int64_t>("row0").Attr<float>("kl_grad_scale")
+        .Attr<float>("prior_mean").Attr<float>("prior_std")
+        .Ret<Any>().Ret<F32B>().Ret<F32B>().Ret<F32B>().Ret<Any>().Ret<Any>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2McSoftmaxFaFwd, McSoftmaxFaFwd,
+    ED2_STREAM.Arg<F32B>().Arg<F32B>().Arg<F32B>().Attr<int32_t>("num_samples").Attr<int32_t>("num_factors")
+        .Attr<int32_t>("share_samples").Attr<float>("temperature").Attr<float>("eps").Attr<int64_t>("seed")
+        .Attr<int64_t>("row0").Ret<F32B>().Ret<F32B>().Ret<F32B>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2McSoftmaxFaBwd, McSoftmaxFaBwd,
+    ED2_STREAM.Arg<F32B>().Arg<F32B>().Arg<F32B>().Arg<F32B>().Arg<F32B>().Attr<int32_t>("num_samples")
+        .Attr<int32_t>("num_factors").Attr<int32_t>("share_samples").Attr<float>("temperature").Attr<float>("eps")
+        .Attr<int64_t>("seed").Attr<int64_t>("row0").Ret<F32B>().Ret<F32B>().Ret<F32B>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2ConvFactorFwd, ConvFactorFwd,
+    ED2_STREAM.Arg<Any>().Arg<Any>().Arg<F32B>().Arg<F32B>().Arg<F32B>().Attr<int32_t>("kh").Attr<int32_t>("kw")
+        .Attr<int32_t>("sh").Attr<int32_t>("sw").Attr<int32_t>("same").Attr<int32_t>("act").Ret<Any>().Ret<Any>().Ret<Any>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2ConvFactorBwd, ConvFactorBwd,
+    ED2_STREAM.Arg<Any>().Arg<Any>().Arg<Any>().Arg<Any>().Arg<Any>().Arg<Any>().Arg<F32B>().Arg<F32B>().Attr<int32_t>("kh")
+        .Attr<int32_t>("kw").Attr<int32_t>("sh").Attr<int32_t>("sw").Attr<int32_t>("same").Attr<int32_t>("act")
+        .Ret<Any>().Ret<F32B>().Ret<F32B>().Ret<F32B>().Ret<F32B>().Ret<Any>().Ret<Any>().Ret<Any>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2NormalKlFwd, NormalKlFwd,
     ED2_STREAM.Arg<F32B>().Arg<F32B>().Attr<float>("prior_mean").Attr<float>("prior_std").Attr<float>("scale").Ret<F64B>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2NormalKlBwd, NormalKlBwd,

@@ -313,6 +313,117 @@ class Ed2FlipoutDenseBwdOp : public OpKernel {
 };
 ED2_REGISTER("Ed2FlipoutDenseBwd", Ed2FlipoutDenseBwdOp);
 
+// Fused DenseFlipout (bf16): the dual-accumulator launches; mu_lp / delta_lp come from Ed2FlipoutDenseFwd-style sampling
+// (ed2_sample_normal_weights mode 1), xs = x∘S is produced here (first layer of a stack) or by the previous layer.
+REGISTER_OP("Ed2FlipoutFusedFwd")
+    .Input("x: T").Input("mu_lp: T").Input("delta_lp: T").Input("bias: float")
+    .Output("y: T").Output("xs: T") ED2_KL_ATTRS;
+template <typename T>
+class Ed2FlipoutFusedFwdOp : public OpKernel {
+ public:
+  explicit Ed2FlipoutFusedFwdOp(OpKernelConstruction* c) : OpKernel(c) { at_.Read(c); }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &x = c->input(0), &mu_lp = c->input(1), &delta_lp = c->input(2), &bias = c->input(3);
+    const int B = D(x, 0), I = D(x, 1), O = D(mu_lp, 1);
+    ED2_OUT(0, TensorShape({B, O}), y); ED2_OUT(1, TensorShape({B, I}), xs);
+    ed2_flipout_fused_fwd_args a{};
+    a.batch = B; a.in_dim = I; a.out_dim = O; a.act = at_.act;
+    a.x = x.data(); a.x_ld = I; a.xs = xs->data(); a.xs_ld = I; a.xs_ready = 0;
+    a.sign_in = Philox(at_.seed, 2, at_.row0); a.sign_out = Philox(at_.seed, 3, at_.row0);
+    a.mu_lp = mu_lp.data(); a.mu_ld = O; a.delta_lp = delta_lp.data(); a.delta_ld = O; a.bias = F(bias);
+    a.y = y->data(); a.y_ld = O;
+    ED2_CALL(ed2_flipout_fused_fwd(&a, c->eigen_gpu_device().stream()));
+  }
+ private:
+  KlAttrs at_;
+};
+ED2_REGISTER("Ed2FlipoutFusedFwd", Ed2FlipoutFusedFwdOp);
+
+REGISTER_OP("Ed2FlipoutFusedBwd")
+    .Input("gy: T").Input("y: T").Input("x: T").Input("xs: T").Input("mu_lp: T").Input("delta_lp: T").Input("mu: float")
+    .Input("rho: float").Input("kl_upstream: double")
+    .Output("dx: T").Output("dmu: float").Output("drho: float").Output("dbias: float") ED2_KL_ATTRS;
+template <typename T>
+class Ed2FlipoutFusedBwdOp : public OpKernel {
+ public:
+  explicit Ed2FlipoutFusedBwdOp(OpKernelConstruction* c) : OpKernel(c) { at_.Read(c); }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &gy = c->input(0), &y = c->input(1), &x = c->input(2), &xs = c->input(3), &mu_lp = c->input(4),
+                 &delta_lp = c->input(5), &mu = c->input(6), &rho = c->input(7), &up = c->input(8);
+    const int B = D(x, 0), I = D(x, 1), O = D(mu, 1);
+    ED2_OUT(0, TensorShape({B, I}), dx); ED2_OUT(1, TensorShape({I, O}), dmu); ED2_OUT(2, TensorShape({I, O}), drho);
+    ED2_OUT(3, TensorShape({O}), dbias);
+    ED2_TMP(TensorShape({B, O}), gp); ED2_TMP(TensorShape({B, O}), gt);
+    ed2_flipout_fused_bwd_args a{};
+    a.batch = B; a.in_dim = I; a.out_dim = O; a.act = at_.act; a.premade = 0;
+    a.gy = gy.data(); a.gy_ld = O; a.y = y.data(); a.y_ld = O;
+    a.gp = gp.data(); a.gp_ld = O; a.gt = gt.data(); a.gt_ld = O;
+    a.x = x.data(); a.x_ld = I; a.xs = xs.data(); a.xs_ld = I;
+    a.mu_lp = mu_lp.data(); a.mu_ld = O; a.delta_lp = delta_lp.data(); a.delta_ld = O;
+    a.mu = F(mu); a.rho = F(rho); a.eps = Philox(at_.seed, 0);
+    a.sign_in = Philox(at_.seed, 2, at_.row0); a.sign_out = Philox(at_.seed, 3, at_.row0);
+    a.dmu = F(dmu); a.drho = F(drho); a.dbias = F(dbias);
+    a.kl_grad_scale = at_.kl_scale; a.prior_mean = at_.pm; a.prior_std = at_.ps; a.kl_upstream = up.flat<double>().data();
+    a.dx = dx->data(); a.dx_ld = I;
+    ED2_CALL(ed2_flipout_fused_bwd(&a, c->eigen_gpu_device().stream()));
+  }
+ private:
+  KlAttrs at_;
+};
+ED2_REGISTER("Ed2FlipoutFusedBwd", Ed2FlipoutFusedBwdOp);
+
+// ================================================================================================ heteroscedastic heads
+// edward2/tensorflow/layers/heteroscedastic.py:178-253, 749-785 (MCSoftmaxDenseFA), hetsngp.py:143-240
+struct McAttrs {
+  int num_samples, num_factors, share_samples; float temperature, eps; int64_t seed, row0;
+  void Read(OpKernelConstruction* c) {
+    OP_REQUIRES_OK(c, c->GetAttr("num_samples", &num_samples)); OP_REQUIRES_OK(c, c->GetAttr("num_factors", &num_factors));
+    OP_REQUIRES_OK(c, c->GetAttr("share_samples", &share_samples)); OP_REQUIRES_OK(c, c->GetAttr("temperature", &temperature));
+    OP_REQUIRES_OK(c, c->GetAttr("eps", &eps)); OP_REQUIRES_OK(c, c->GetAttr("seed", &seed));
+    OP_REQUIRES_OK(c, c->GetAttr("row0", &row0));
+  }
+};
+#define ED2_MC_ATTRS                                                                                                   \
+  .Attr("num_samples: int = 1000").Attr("num_factors: int = 10").Attr("share_samples: int = 0")                        \
+  .Attr("temperature: float = 1.0").Attr("eps: float = 1e-7").Attr("seed: int = 0").Attr("row0: int = 0")
+REGISTER_OP("Ed2McSoftmaxFaFwd")
+    .Input("loc: float").Input("fac: float").Input("diag_raw: float")
+    .Output("logits: float").Output("probs_mean: float").Output("variance: float") ED2_MC_ATTRS;
+class Ed2McSoftmaxFaFwdOp : public OpKernel {
+ public:
+  explicit Ed2McSoftmaxFaFwdOp(OpKernelConstruction* c) : OpKernel(c) { at_.Read(c); }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &loc = c->input(0), &fac = c->input(1), &diag = c->input(2);
+    const int B = D(loc, 0), K = D(loc, 1);
+    ED2_OUT(0, TensorShape({B, K}), logits); ED2_OUT(1, TensorShape({B, K}), pm); ED2_OUT(2, TensorShape({B, K}), var);
+    ED2_CALL(ed2_mc_softmax_fa_fwd(F(loc), F(fac), F(diag), nullptr, 1.f, 1.f, Philox(at_.seed, 7, at_.row0), B,
+                                   at_.num_samples, K, at_.num_factors, at_.share_samples, at_.temperature, at_.eps, F(pm),
+                                   F(logits), F(var), c->eigen_gpu_device().stream()));
+  }
+ private:
+  McAttrs at_;
+};
+REGISTER_KERNEL_BUILDER(Name("Ed2McSoftmaxFaFwd").Device(DEVICE_GPU), Ed2McSoftmaxFaFwdOp);
+
+REGISTER_OP("Ed2McSoftmaxFaBwd")
+    .Input("g: float").Input("probs_mean: float").Input("loc: float").Input("fac: float").Input("diag_raw: float")
+    .Output("dloc: float").Output("dfac: float").Output("ddiag_raw: float") ED2_MC_ATTRS;
+class Ed2McSoftmaxFaBwdOp : public OpKernel {
+ public:
+  explicit Ed2McSoftmaxFaBwdOp(OpKernelConstruction* c) : OpKernel(c) { at_.Read(c); }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &g = c->input(0), &pm = c->input(1), &loc = c->input(2), &fac = c->input(3), &diag = c->input(4);
+    const int B = D(loc, 0), K = D(loc, 1);
+    ED2_OUT(0, TensorShape({B, K}), dloc); ED2_OUT(1, TensorShape({B, D(fac, 1)}), dfac); ED2_OUT(2, TensorShape({B, K}), dd);
+    ED2_CALL(ed2_mc_softmax_fa_bwd(F(g), F(pm), F(loc), F(fac), F(diag), Philox(at_.seed, 7, at_.row0), B, at_.num_samples, K,
+                                   at_.num_factors, at_.share_samples, at_.temperature, at_.eps, F(dloc), F(dfac), F(dd),
+                                   c->eigen_gpu_device().stream()));
+  }
+ private:
+  McAttrs at_;
+};
+REGISTER_KERNEL_BUILDER(Name("Ed2McSoftmaxFaBwd").Device(DEVICE_GPU), Ed2McSoftmaxFaBwdOp);
+
 // ================================================================================================ SNGP head
 // phi = cos(x W + b) * scale — edward2/tensorflow/layers/random_feature.py:258-266
 REGISTER_OP("Ed2RffFwd").Input("x: T").Input("wt: T").Input("bias: float").Output("phi: T").Output("pre: float")
