@@ -198,4 +198,11 @@ int k_mc_softmax_bwd(const float* g, const float* probs_mean, const float* loc, 
                      Noise noise, int B, int S, int K, int F, int shared, float temperature, float eps, float* dloc,
                      float* dfac, float* ddiag_raw, cudaStream_t s);
 
+// ---- pointwise part of the Bayesian LSTM cells (recurrent.cu; recurrent.py:163-184, gate order i | f | c | o)
+int k_lstm_pointwise_fwd(const void* z, int dt, long long z_ld, const float* c_prev, int B, int H, float* c, void* h,
+                         long long h_ld, cudaStream_t s);
+int k_lstm_pointwise_bwd(const void* z, int dt, long long z_ld, const float* c_prev, const float* c, const void* dh,
+                         long long dh_ld, const float* dc, int B, int H, void* dz, long long dz_ld, float* dc_prev,
+                         float* dbias, cudaStream_t s);
+
 }  // namespace ed2

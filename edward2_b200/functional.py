@@ -1049,6 +1049,132 @@ class MCSoftmaxFA(torch.autograd.Function):
                 None)
 
 
+# ------------------------------------------------------------------------------------------------- LSTM cells
+class SequenceKernel:
+    """One sample of a Normal kernel posterior that a whole sequence of cell steps shares (recurrent.py:138-161:
+    LSTM weight noise is drawn once per sequence and reused by every time step).  `w_lp` is the compute-dtype operand;
+    the steps add their raw weight gradients into `dw` (fp32) and hold `token`, a 0-dim tensor of the autograd graph whose
+    backward — it runs after the last step's — turns `dw` into (dmu, drho) with the noise regenerated and the KL gradient
+    added."""
+
+    def __init__(self, mu, rho, eps, dtype, kl_scale, prior_mean, prior_std):
+        self.w_lp, self.kl, self.token = _SampleSequenceKernel.apply(mu, rho, self, eps, dtype, kl_scale, prior_mean, prior_std)
+        self.dw = None
+
+    def add_grad(self, rows, cols, a, b, m):
+        """dw += aᵀ·b ([rows, cols], contraction over m) on the tensor cores."""
+        if self.dw is None:
+            self.dw = torch.zeros(rows, cols, dtype=torch.float32, device=a.device)
+        if a.dtype == torch.bfloat16:
+            ops.gemm(a, b, rows, cols, m, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=self.dw, accumulate=True)
+        else:
+            ops.gemm(a, b, rows, cols, m, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=self.dw, addend=self.dw)
+
+
+class _SampleSequenceKernel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, rho, holder, eps, dtype, kl_scale, prior_mean, prior_std):
+        lib = _lib.load()
+        I, O = mu.shape
+        dev = mu.device
+        w_lp = _new(I, O, dtype, dev)
+        kl64 = torch.zeros((), dtype=torch.float64, device=dev)
+        _lib.check(lib.ed2_sample_normal_weights(
+            mu.data_ptr(), rho.data_ptr(), eps.c(), I, O, 0, w_lp.data_ptr(), _compute_dt(dtype), _lib.ld(w_lp), None, 0,
+            kl64.data_ptr() if kl_scale != 0 else None, kl_scale, prior_mean, prior_std, _lib.stream_ptr()),
+            "ed2_sample_normal_weights")
+        ctx.save_for_backward(mu, rho)
+        ctx.meta = (holder, eps, dtype, kl_scale, prior_mean, prior_std)
+        ctx.mark_non_differentiable(w_lp)
+        return w_lp, kl64, torch.zeros((), dtype=torch.float32, device=dev)
+
+    @staticmethod
+    def backward(ctx, _gw, gkl, _gtoken):
+        lib = _lib.load()
+        mu, rho = ctx.saved_tensors
+        holder, eps, dtype, kl_scale, pm, ps = ctx.meta
+        I, O = mu.shape
+        dw = holder.dw if holder.dw is not None else torch.zeros(I, O, dtype=torch.float32, device=mu.device)
+        holder.dw = None
+        dmu, drho = torch.empty_like(mu), torch.empty_like(rho)
+        up = (gkl if gkl.dtype == torch.float64 else gkl.to(torch.float64)).reshape(1) if gkl is not None else None
+        klg = (kl_scale if gkl is not None else 0.0) / GradSync.replicas
+        _lib.check(lib.ed2_normal_grad_finish(dw.data_ptr(), F32, mu.data_ptr(), rho.data_ptr(), eps.c(), I * O, klg,
+                                              _p(up), pm, ps, dmu.data_ptr(), drho.data_ptr(),
+                                              int(dtype == torch.bfloat16), _lib.stream_ptr()), "ed2_normal_grad_finish")
+        return dmu, drho, None, None, None, None, None, None
+
+
+class LSTMStep(torch.autograd.Function):
+    """One LSTM cell step on sampled (or deterministic) kernels: z = x·W + h_prev·U + b, pointwise gates
+    (include/ed2b200.h: ed2_lstm_pointwise_fwd / _bwd).  W / U are compute-dtype operands; their raw gradients go to
+    `kw.add_grad` / `ku.add_grad` (SequenceKernel) when given, else they are returned for `w` / `u`."""
+
+    @staticmethod
+    def forward(ctx, x, h_prev, c_prev, w, u, bias, tok_w, tok_u, kw, ku, dtype):
+        lib = _lib.load()
+        B, I = x.shape
+        H = h_prev.shape[1]
+        dev = x.device
+        xc, hc = as_compute(x, dtype), as_compute(h_prev, dtype)
+        w_lp = w if w.dtype == dtype else as_compute(w, dtype)
+        u_lp = u if u.dtype == dtype else as_compute(u, dtype)
+        c32 = c_prev.to(torch.float32).contiguous()
+        z = _new(B, 4 * H, dtype, dev)
+        ops.gemm(xc, w_lp, B, 4 * H, I, major_a=ops.MAJOR_K, major_b=ops.MAJOR_MN, out=z,
+                 col_bias=bias.reshape(1, -1).to(torch.float32) if bias is not None else None)
+        ops.gemm(hc, u_lp, B, 4 * H, H, major_a=ops.MAJOR_K, major_b=ops.MAJOR_MN, out=z, addend=z)
+        c = torch.empty(B, H, dtype=torch.float32, device=dev)
+        h = _new(B, H, dtype, dev)
+        _lib.check(lib.ed2_lstm_pointwise_fwd(z.data_ptr(), _compute_dt(dtype), _lib.ld(z), c32.data_ptr(), B, H,
+                                              c.data_ptr(), h.data_ptr(), _lib.ld(h), _lib.stream_ptr()),
+                   "ed2_lstm_pointwise_fwd")
+        ctx.save_for_backward(xc, hc, c32, c, z, w_lp, u_lp)
+        ctx.meta = (dtype, bias is not None, x.dtype, h_prev.dtype, c_prev.dtype, kw, ku)
+        ctx.set_materialize_grads(False)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        lib = _lib.load()
+        xc, hc, c_prev, c, z, w_lp, u_lp = ctx.saved_tensors
+        dtype, has_bias, x_dt, h_dt, c_dt, kw, ku = ctx.meta
+        B, I = xc.shape
+        H = hc.shape[1]
+        dev = xc.device
+        dhc = as_compute(dh, dtype) if dh is not None else None
+        dc32 = dc.to(torch.float32).contiguous() if dc is not None else None
+        dz = _new(B, 4 * H, dtype, dev)
+        dc_prev = torch.empty(B, H, dtype=torch.float32, device=dev)
+        dbias = torch.empty(4 * H, dtype=torch.float32, device=dev) if has_bias else None
+        _lib.check(lib.ed2_lstm_pointwise_bwd(z.data_ptr(), _compute_dt(dtype), _lib.ld(z), c_prev.data_ptr(), c.data_ptr(),
+                                              _p(dhc), _ldn(dhc), _p(dc32), B, H, dz.data_ptr(), _lib.ld(dz),
+                                              dc_prev.data_ptr(), _p(dbias), _lib.stream_ptr()), "ed2_lstm_pointwise_bwd")
+        dw = du = None
+        if kw is not None:
+            kw.add_grad(I, 4 * H, xc, dz, B)
+        else:
+            dw = torch.empty(I, 4 * H, dtype=torch.float32, device=dev)
+            ops.gemm(xc, dz, I, 4 * H, B, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=dw)
+        if ku is not None:
+            ku.add_grad(H, 4 * H, hc, dz, B)
+        else:
+            du = torch.empty(H, 4 * H, dtype=torch.float32, device=dev)
+            ops.gemm(hc, dz, H, 4 * H, B, major_a=ops.MAJOR_MN, major_b=ops.MAJOR_MN, out=du)
+        dx = dhp = None
+        if ctx.needs_input_grad[0]:
+            dx = _new(B, I, dtype, dev)
+            ops.gemm(dz, w_lp, B, I, 4 * H, major_a=ops.MAJOR_K, major_b=ops.MAJOR_K, out=dx)
+            dx = dx if dx.dtype == x_dt else dx.to(x_dt)
+        if ctx.needs_input_grad[1]:
+            dhp = _new(B, H, dtype, dev)
+            ops.gemm(dz, u_lp, B, H, 4 * H, major_a=ops.MAJOR_K, major_b=ops.MAJOR_K, out=dhp)
+            dhp = dhp if dhp.dtype == h_dt else dhp.to(h_dt)
+        zero = lambda t: torch.zeros((), dtype=torch.float32, device=dev) if t is not None else None  # noqa: E731
+        return (dx, dhp, dc_prev if c_dt == torch.float32 else dc_prev.to(c_dt), dw, du, dbias,
+                zero(kw), zero(ku), None, None, None)
+
+
 # ------------------------------------------------------------------------------------------------- KL regulariser
 class NormalKL(torch.autograd.Function):
     """scale * sum KL(N(mu, softplus(rho)+1e-7) || N(m, s)) as a 0-dim fp32 tensor (regularizers.py:175-186)."""

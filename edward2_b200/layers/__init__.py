@@ -5,9 +5,10 @@ from .convolutional import Conv2DBatchEnsemble, Conv2DFlipout, Conv2DRank1, Conv
 from .heteroscedastic import HeteroscedasticSNGPLayer, MCSoftmaxDenseFA
 from .dense import Dense, DenseBatchEnsemble, DenseFlipout, DenseRank1, DenseReparameterization
 from .normalization import SpectralNormalization
+from .recurrent import LSTMCellReparameterization
 from .random_feature import LaplaceRandomFeatureCovariance, RandomFeatureGaussianProcess
 
 __all__ = [
-    "Layer", "Conv2DBatchEnsemble", "Conv2DFlipout", "Conv2DRank1", "Conv2DReparameterization", "Dense", "DenseBatchEnsemble", "DenseFlipout", "DenseRank1", "DenseReparameterization", "HeteroscedasticSNGPLayer", "MCSoftmaxDenseFA",
+    "Layer", "Conv2DBatchEnsemble", "Conv2DFlipout", "Conv2DRank1", "Conv2DReparameterization", "Dense", "DenseBatchEnsemble", "DenseFlipout", "DenseRank1", "DenseReparameterization", "HeteroscedasticSNGPLayer", "LSTMCellReparameterization", "MCSoftmaxDenseFA",
     "SpectralNormalization", "LaplaceRandomFeatureCovariance", "RandomFeatureGaussianProcess", "utils",
 ]

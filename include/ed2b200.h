@@ -525,6 +525,20 @@ int ed2_mc_softmax_fa_bwd(const float* g, const float* probs_mean, const float* 
                           float* ddiag_raw, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Bayesian LSTM cells (edward2/tensorflow/layers/recurrent.py:30 LSTMCellReparameterization): the weights are sampled once
+ * per sequence (call_weights / get_initial_state, :138-161) and reused by every time step, so a step is
+ *   z = x·W_lp + h_prev·U_lp + b   (two ed2_gemm calls, the second with addend = z)   [B][4H], gates i | f | c | o
+ *   i, f, o = sigmoid(z_.), g = tanh(z_c);  c = f c_prev + i g;  h = o tanh(c)          (:163-184)
+ * and its backward dz = [di | df | dg | do] (pre-activation), dc_prev, dbias (column sums, fp32 atomics, zeroed here),
+ * followed by the four GEMMs dx = dz·Wᵀ, dh_prev = dz·Uᵀ, dW += xᵀ·dz, dU += h_prevᵀ·dz.  Cell state fp32, z / h / dz in
+ * `dtype`. */
+int ed2_lstm_pointwise_fwd(const void* z, int dtype, long long z_ld, const float* c_prev, int batch, int units, float* c,
+                           void* h, long long h_ld, void* stream);
+int ed2_lstm_pointwise_bwd(const void* z, int dtype, long long z_ld, const float* c_prev, const float* c, const void* dh,
+                           long long dh_ld, const float* dc, int batch, int units, void* dz, long long dz_ld,
+                           float* dc_prev, float* dbias, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Conv2D stochastic-weight layers (edward2/tensorflow/layers/convolutional.py:32 Conv2DReparameterization, :167
  * Conv2DFlipout, :560 Conv2DBatchEnsemble, :2056 Conv2DRank1).  Their per-example factors are channel vectors broadcast
  * over the spatial axes (:235-249, :681-699, :1976-1989), so on the patch matrix

@@ -606,3 +606,30 @@ def test_heteroscedastic_oracle_gradients_and_identities():
     flat = __import__("oracle.philox", fromlist=["normal"]).normal(5, 7, 3 * 4 * 16).reshape(3, 4, 16)
     np.testing.assert_array_equal(zz, flat[:, :, :Fn])
     np.testing.assert_array_equal(ee, flat[:, :, 8:8 + K])
+
+
+def test_recurrent_oracle_bptt_matches_autograd():
+    """oracle/recurrent.py: the closed-form backpropagation through time of the LSTM cell
+    (recurrent.py:163-183, gate order i | f | c | o) == float64 autograd."""
+    from oracle import recurrent as orc
+
+    rng = np.random.default_rng(21)
+    T, B, I, H = 4, 3, 5, 6
+    xs, h0, c0 = rng.standard_normal((T, B, I)), rng.standard_normal((B, H)), rng.standard_normal((B, H))
+    W, U, b = rng.standard_normal((I, 4 * H)) * 0.4, rng.standard_normal((H, 4 * H)) * 0.4, rng.standard_normal(4 * H) * 0.1
+    hs, cT, caches = orc.lstm_sequence(xs, h0, c0, W, U, b)
+    dhs, dcl = rng.standard_normal((T, B, H)), rng.standard_normal((B, H))
+    g = orc.lstm_sequence_bwd(caches, W, U, dhs, dcl)
+    t = {k: torch.tensor(v, requires_grad=True) for k, v in dict(xs=xs, h0=h0, c0=c0, W=W, U=U, b=b).items()}
+    h, c, loss = t["h0"], t["c0"], 0.0
+    for s in range(T):
+        z = t["xs"][s] @ t["W"] + h @ t["U"] + t["b"]
+        i, f, gg, o = torch.sigmoid(z[:, :H]), torch.sigmoid(z[:, H:2 * H]), torch.tanh(z[:, 2 * H:3 * H]), torch.sigmoid(z[:, 3 * H:])
+        c = f * c + i * gg
+        h = o * torch.tanh(c)
+        loss = loss + (h * torch.tensor(dhs[s])).sum()
+    (loss + (c * torch.tensor(dcl)).sum()).backward()
+    np.testing.assert_allclose(hs[-1], h.detach().numpy(), rtol=1e-12)
+    for key, ref in (("dxs", t["xs"].grad), ("dh0", t["h0"].grad), ("dc0", t["c0"].grad), ("dW", t["W"].grad),
+                     ("dU", t["U"].grad), ("db", t["b"].grad)):
+        np.testing.assert_allclose(g[key], ref.numpy(), rtol=1e-9, atol=1e-12)
