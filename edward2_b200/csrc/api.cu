@@ -8,6 +8,7 @@
 #include "kernels.h"
 #include "status.h"
 #include <algorithm>
+#include <cstdlib>
 
 using namespace ed2;
 
@@ -38,6 +39,15 @@ FastSide fast_side(const float* mu, const float* sg, const float* sgm, const ed2
   return f;
 }
 inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// ED2_FUSED_DW=1 finishes the Reparameterization weight gradient in the epilogue of its own GEMM (gemm_flipout.cuh mode 2).
+// OFF by default — measured on B200 (cfg2, profiles/r02_reparam_fused_dw_ab.txt): the fused launch runs at 708 TFLOP/s
+// against 1280 for the plain dW GEMM (a thread of the epilogue owns a ROW, so its mu / rho loads and dmu / drho stores are
+// 32 lines per warp instruction: ~16 K LSU wavefronts per tile, as long as the tile's MMAs) and the step goes from
+// 0.625 to 0.699 ms, although the dX GEMM gains 30 us from not sharing the SMs with the finishing pass.
+inline bool fused_dw_enabled() {
+  static const bool v = [] { const char* e = std::getenv("ED2_FUSED_DW"); return e != nullptr && std::atoi(e) != 0; }();
+  return v;
+}
 
 EpiParams epi_default() {
   EpiParams e{};
@@ -504,6 +514,11 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
     e.out = a->dmu_lp; e.out_ld = a->out_dim; e.out_dt = kBF16;
     return gemm_xtg(a->dtype, a->x, a->x_ld, gp, gp_ld, a->batch, a->in_dim, a->out_dim, e, s);
   }
+  // Opt-in (ED2_FUSED_DW=1, see fused_dw_enabled): the weight gradient FINISHED in the epilogue of its own GEMM
+  // (gemm_flipout.cuh mode 2: dmu = acc + KL', drho = (acc eps + KL') sigmoid(rho), eps regenerated).
+  const bool fused_dw = a->phase == 0 && a->dtype == kBF16 && a->eps.injected == nullptr && a->dmu_lp == nullptr &&
+                        a->batch > 128 && gemm_flipout_fusable(a->in_dim, a->out_dim, a->batch) && al16p(a->mu) &&
+                        al16p(a->rho) && al16p(a->dmu) && al16p(a->drho) && fused_dw_enabled();
   if (a->phase != 2) {
     if (!a->gy_premasked) {
       BwdOutArgs o{};
@@ -513,15 +528,29 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
       o.dbias = a->dbias;
       ED2_TRY(k_bwd_out(o, s));
     }
-    // dW = xᵀ gp lands in dmu; the finishing pass turns it into (dmu, drho) in place (+ bf16 bucket copies).
-    EpiParams e = epi_default();
-    e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
-    ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, gp, gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
+    if (fused_dw) {
+      FlipoutGemm w{};
+      w.mode = 2; w.major_a = kMajorMN; w.major_b = kMajorMN;
+      w.A0 = a->x; w.lda0 = a->x_ld; w.A1 = a->x; w.lda1 = a->x_ld;
+      w.B0 = gp; w.ldb0 = gp_ld; w.B1 = gp; w.ldb1 = gp_ld;
+      w.M = a->in_dim; w.N = a->out_dim; w.K = a->batch;
+      w.epi.sa.seed = a->eps.seed; w.epi.sa.stream = a->eps.stream;
+      w.epi.sa.step = reinterpret_cast<const unsigned long long*>(a->eps.step); w.epi.sa.on = 1;
+      w.epi.mu = a->mu; w.epi.rho = a->rho; w.epi.dmu = a->dmu; w.epi.drho = a->drho;
+      w.epi.klg = a->kl_grad_scale; w.epi.kl_upstream = a->kl_upstream;
+      w.epi.prior_mean = a->prior_mean; w.epi.prior_std = a->prior_std;
+      ED2_TRY(gemm_flipout(w, s));
+    } else {
+      // dW = xᵀ gp lands in dmu; the finishing pass turns it into (dmu, drho) in place (+ bf16 bucket copies).
+      EpiParams e = epi_default();
+      e.out = a->dmu; e.out_ld = a->out_dim; e.out_dt = kF32;
+      ED2_TRY(gemm_xtg(a->dtype, a->x, a->x_ld, gp, gp_ld, a->batch, a->in_dim, a->out_dim, e, s));
+    }
   }
   // Whole-backward call: the finishing pass (CUDA cores) is forked onto the side stream and the dX GEMM (tensor
   // cores) is enqueued first.  Split call (phase 1): the finishing pass stays on the caller's stream because the
   // caller launches the gradient all-reduce right after it.
-  ForkJoin fj(s, a->phase == 0 && a->dx != nullptr);
+  ForkJoin fj(s, a->phase == 0 && a->dx != nullptr && !fused_dw);
   int st = ED2_OK;
   if (a->phase != 1 && a->dx != nullptr) {
     EpiParams e2 = epi_default();
@@ -532,7 +561,7 @@ int ed2_reparam_dense_bwd(const ed2_reparam_bwd_args* a, void* stream) {
     }
     st = gemm_gwt(a->dtype, gp, gp_ld, a->w_lp, a->w_ld, a->batch, a->in_dim, a->out_dim, e2, s);
   }
-  if (a->phase != 2 && st == ED2_OK)
+  if (a->phase != 2 && st == ED2_OK && !fused_dw)
     st = k_normal_grad_finish(a->dmu, a->dmu, a->mu, a->rho, N(a->eps), (long long)a->in_dim * a->out_dim,
                               a->kl_grad_scale, a->kl_upstream, Prior{a->prior_mean, a->prior_std}, a->dmu, a->drho,
                               a->dtype == kBF16, fj.side(), a->dmu_lp, a->drho_lp);

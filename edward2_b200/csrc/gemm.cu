@@ -268,7 +268,7 @@ int gemm_flipout(const FlipoutGemm& g, cudaStream_t stream) {
     return set_error(ED2_ERR_BAD_SHAPE, "flipout gemm: needs N, K multiples of 8 (M=%d N=%d K=%d)", g.M, g.N, g.K);
   if (!tma_ok(g.A0, g.lda0, 2) || !tma_ok(g.A1, g.lda1, 2) || !tma_ok(g.B0, g.ldb0, 2) || !tma_ok(g.B1, g.ldb1, 2))
     return set_error(ED2_ERR_BAD_ARG, "flipout gemm: operands must be 16-byte aligned with a pitch that is a multiple of 8 bf16");
-  if (g.mode == 1) {
+  if (g.mode == 1 || g.mode == 2) {
     if (g.major_a != kMajorMN || g.major_b != kMajorMN) return set_error(ED2_ERR_BAD_ARG, "flipout gemm: weight-gradient mode takes MN-major operands");
     if (g.epi.mu == nullptr || g.epi.rho == nullptr || g.epi.dmu == nullptr || g.epi.drho == nullptr)
       return set_error(ED2_ERR_BAD_ARG, "flipout gemm: weight-gradient mode needs mu / rho / dmu / drho");
@@ -282,6 +282,7 @@ int gemm_flipout(const FlipoutGemm& g, cudaStream_t stream) {
                     make_map(&tb0, g.B0, kBF16, g.K, g.N, g.ldb0, tc::kBlockK, 64) &&
                     make_map(&tb1, g.B1, kBF16, g.K, g.N, g.ldb1, tc::kBlockK, 64);
     if (!ok) return set_error(ED2_ERR_CUDA, "cuTensorMapEncodeTiled failed for a flipout GEMM operand");
+    if (g.mode == 2) return launch_flipout<kMajorMN, kMajorMN, 2>(g, ta0, ta1, tb0, tb1, to, 0, stream);
     return launch_flipout<kMajorMN, kMajorMN, 1>(g, ta0, ta1, tb0, tb1, to, 0, stream);
   }
   if (g.major_a != kMajorK) return set_error(ED2_ERR_BAD_ARG, "flipout gemm: the summed mode takes K-major A operands");

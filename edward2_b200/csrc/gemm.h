@@ -46,6 +46,7 @@ struct FlipoutGemm {
   FlipoutEpi epi;
   int major_a = kMajorK;
   int mode = 0;           // 1: weight-gradient pair finished in the epilogue (epi.mu / rho / dmu / drho; A and B MN-major)
+                          // 2: the same epilogue on the single product A0·B0 (A1 / B1 = A0 / B0, not staged)
 };
 bool gemm_flipout_fusable(int M, int N, int K);
 int gemm_flipout(const FlipoutGemm& g, cudaStream_t stream);

@@ -119,6 +119,8 @@ __device__ __forceinline__ float fo_sigma_from_rho_fast(float rho, float& e) {
 //   drho[i,o] = (acc1 · eps[i,o] + klg (sigma / s² - 1 / sigma)) · sigmoid(rho)     eps regenerated from Philox
 //   — the arithmetic of grad_finish_lean_kernel, so the fp32 raw gradients are never written and re-read (24 B per
 //   weight) and the two products share one tile grid (512 tiles = 6.9 waves of 74 pairs instead of 2 x 3.46).
+// kMode 2: the same finishing epilogue on ONE product (DenseReparameterization: the single weight gradient xᵀ·gp feeds
+//   both dmu and drho); only A0 / B0 are staged, so the ring is 8 stages of 24 KB.
 template <int kMajorA, int kMajorB, int kMode>
 __global__ void __maxnreg__(168)
 gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
@@ -128,17 +130,19 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
   constexpr int kTileM = kBlockM * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr bool kDual = kMode != 2;
+  constexpr int kSt = kDual ? kFoStages : 2 * kFoStages;  // same bytes: 4 x 48 KB or 8 x 24 KB
   uint8_t* smem_a0 = smem;
-  uint8_t* smem_a1 = smem_a0 + kFoStages * kFoABytes;
-  uint8_t* smem_b0 = smem_a1 + kFoStages * kFoABytes;
-  uint8_t* smem_b1 = smem_b0 + kFoStages * kFoBBytes;
-  uint8_t* smem_store = smem_b1 + kFoStages * kFoBBytes;
+  uint8_t* smem_a1 = smem_a0 + kSt * kFoABytes;                       // dual only
+  uint8_t* smem_b0 = smem_a1 + (kDual ? kSt * kFoABytes : 0);
+  uint8_t* smem_b1 = smem_b0 + kSt * kFoBBytes;                       // dual only
+  uint8_t* smem_store = smem + kFoStages * kFoStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + 2 * kStoreBufBytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kFoStages;
-  uint64_t* tmem_full_bar = bars + 2 * kFoStages;
-  uint64_t* tmem_empty_bar = bars + 2 * kFoStages + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kFoStages + 4);
+  uint64_t* empty_bar = bars + kSt;
+  uint64_t* tmem_full_bar = bars + 2 * kSt;
+  uint64_t* tmem_empty_bar = bars + 2 * kSt + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kSt + 4);
 
   const int warp_idx = __shfl_sync(0xffffffff, threadIdx.x / 32, 0);
   const uint32_t lane = ptx::lane_id();
@@ -154,7 +158,7 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
     if (out_tma) ptx::prefetch_tensormap(&tm_out);
   }
   if (warp_idx == 1 && ptx::elect_one()) {
-    for (int i = 0; i < kFoStages; ++i) {
+    for (int i = 0; i < kSt; ++i) {
       ptx::mbar_init(&full_bar[i], 2);
       ptx::mbar_init(&empty_bar[i], 1);
     }
@@ -192,24 +196,25 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
           uint64_t* fb = &full_bar[stage];
           if constexpr (kMajorA == kMajorK) {
             ptx::tma_load_2d_pair(smem_a0 + stage * kFoABytes, &tm_a0, fb, k0, m0);
-            ptx::tma_load_2d_pair(smem_a1 + stage * kFoABytes, &tm_a1, fb, k0, m0);
+            if constexpr (kDual) ptx::tma_load_2d_pair(smem_a1 + stage * kFoABytes, &tm_a1, fb, k0, m0);
           } else {
 #pragma unroll
             for (int i = 0; i < kBlockM / 64; ++i) {
               ptx::tma_load_2d_pair(smem_a0 + stage * kFoABytes + i * (kBlockK * 128), &tm_a0, fb, m0 + i * 64, k0);
-              ptx::tma_load_2d_pair(smem_a1 + stage * kFoABytes + i * (kBlockK * 128), &tm_a1, fb, m0 + i * 64, k0);
+              if constexpr (kDual)
+                ptx::tma_load_2d_pair(smem_a1 + stage * kFoABytes + i * (kBlockK * 128), &tm_a1, fb, m0 + i * 64, k0);
             }
           }
           if constexpr (kMajorB == kMajorK) {
             ptx::tma_load_2d_pair(smem_b0 + stage * kFoBBytes, &tm_b0, fb, k0, n0);
-            ptx::tma_load_2d_pair(smem_b1 + stage * kFoBBytes, &tm_b1, fb, k0, n0);
+            if constexpr (kDual) ptx::tma_load_2d_pair(smem_b1 + stage * kFoBBytes, &tm_b1, fb, k0, n0);
           } else {
             ptx::tma_load_2d_pair(smem_b0 + stage * kFoBBytes, &tm_b0, fb, n0, k0);
-            ptx::tma_load_2d_pair(smem_b1 + stage * kFoBBytes, &tm_b1, fb, n0, k0);
+            if constexpr (kDual) ptx::tma_load_2d_pair(smem_b1 + stage * kFoBBytes, &tm_b1, fb, n0, k0);
           }
-          if (is_leader) ptx::mbar_arrive_expect_tx(fb, kFoStageBytes * 2);
+          if (is_leader) ptx::mbar_arrive_expect_tx(fb, (kDual ? kFoStageBytes : kFoStageBytes / 2) * 2);
           else ptx::mbar_arrive_cluster(fb, 0);
-          if (++stage == kFoStages) { stage = 0; phase ^= 1; }
+          if (++stage == kSt) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -237,16 +242,17 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
             ptx::umma<2, false>(tmem_d0, da0 + k * desc_k_step<kMajorA>(), db0 + k * desc_k_step<kMajorB>(), idesc, accum);
-            ptx::umma<2, false>(tmem_d1, da1 + k * desc_k_step<kMajorA>(), db1 + k * desc_k_step<kMajorB>(), idesc, accum);
+            if constexpr (kDual)
+              ptx::umma<2, false>(tmem_d1, da1 + k * desc_k_step<kMajorA>(), db1 + k * desc_k_step<kMajorB>(), idesc, accum);
           }
           ptx::umma_commit<2>(&empty_bar[stage]);
           if (kb == num_kb - 1) ptx::umma_commit<2>(&tmem_full_bar[acc]);
-          if (++stage == kFoStages) { stage = 0; phase ^= 1; }
+          if (++stage == kSt) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp_idx >= 4) {
-   if constexpr (kMode == 1) {
+   if constexpr (kMode >= 1) {
     // ------------------------------------------------------------------ weight-gradient epilogue (8 warps)
     const int grp_id = (warp_idx - 4) >> 2;
     const int ew = warp_idx & 3;
@@ -281,8 +287,12 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
         uint32_t a0[16], a1[16];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * (2 * kFoBlockN) + tcol;
         tmem_ld_32x16(taddr, a0);
-        tmem_ld_32x16(taddr + kFoBlockN, a1);
+        if constexpr (kMode == 1) tmem_ld_32x16(taddr + kFoBlockN, a1);
         ptx::tmem_ld_wait();
+        if constexpr (kMode == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a1[j] = a0[j];  // one product feeds both gradients
+        }
         if (cc == 3) {
           ptx::tc_fence_before();
           if (is_leader) ptx::mbar_arrive(&tmem_empty_bar[acc]);
