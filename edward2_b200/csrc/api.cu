@@ -40,10 +40,10 @@ FastSide fast_side(const float* mu, const float* sg, const float* sgm, const ed2
 }
 inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 // ED2_FUSED_DW=1 finishes the Reparameterization weight gradient in the epilogue of its own GEMM (gemm_flipout.cuh mode 2).
-// OFF by default — measured on B200 (cfg2, profiles/r02_reparam_fused_dw_ab.txt): the fused launch runs at 708 TFLOP/s
-// against 1280 for the plain dW GEMM (a thread of the epilogue owns a ROW, so its mu / rho loads and dmu / drho stores are
-// 32 lines per warp instruction: ~16 K LSU wavefronts per tile, as long as the tile's MMAs) and the step goes from
-// 0.625 to 0.699 ms, although the dX GEMM gains 30 us from not sharing the SMs with the finishing pass.
+// OFF by default — measured on B200 (cfg2, profiles/r02_reparam_fused_dw_ab.txt): the step is 0.636 ms with it against
+// 0.625 ms without.  The fused launch (256x128 tiles, 222 us per step) is slower than the plain 256x256 dW GEMM (160 us)
+// by more than the dX GEMM gains from not sharing the SMs with the finishing pass (186 -> 157 us).  First version, with the
+// row-per-thread global accesses of the epilogue (32 lines per warp instruction): 290 us, step 0.699 ms.
 inline bool fused_dw_enabled() {
   static const bool v = [] { const char* e = std::getenv("ED2_FUSED_DW"); return e != nullptr && std::atoi(e) != 0; }();
   return v;

@@ -582,7 +582,10 @@ constexpr int kLeanRows = 64;  // upper bound; the host shrinks it until the gri
 inline int lean_rows_for(long long rows, int cols) {
   const long long col_blocks = (cols / 8 + kBlock - 1) / kBlock;
   int r = kLeanRows;
-  while (r > 4 && (rows / r) * col_blocks < 148 * 6) r >>= 1;
+  // one column block (<= 2048 columns, e.g. the 1000-unit head): every row chunk ends in one atomic per column per
+  // accumulator on the SAME few thousand addresses, so fewer, longer chunks win (one block per SM is enough)
+  const long long want = col_blocks == 1 ? 148 : 148 * 6;
+  while (r > 4 && (rows / r) * col_blocks < want) r >>= 1;
   return r;
 }
 

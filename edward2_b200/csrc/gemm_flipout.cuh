@@ -257,6 +257,9 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
     const int grp_id = (warp_idx - 4) >> 2;
     const int ew = warp_idx & 3;
     const int row = ew * 32 + lane;
+    const int gtid = ew * 32 + static_cast<int>(lane);  // thread index within the group (== row)
+    const uint32_t bar_id = 1 + grp_id;
+    const uint32_t sbuf = ptx::smem_u32(smem_store + grp_id * kStoreBufBytes);  // 16 KB: two [128][16] fp32 slabs
     const uint64_t key_e = sign_key(fe.sa);  // sa carries the eps stream in this mode
     const float klg = fe.klg * (fe.kl_upstream != nullptr ? static_cast<float>(*fe.kl_upstream) : 1.f);
     const float inv_s2 = 1.f / (fe.prior_std * fe.prior_std);
@@ -276,13 +279,22 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
       for (int cc = 0; cc < 4; ++cc) {
         const int tcol = grp_id * 64 + cc * 16;
         const int nc = n0 + tcol;
-        // parameters of this chunk: in flight during the TMEM load and the Philox rounds
+        // A thread of this epilogue owns a ROW of the tile (tcgen05.ld 32x32b), so touching mu / rho / dmu / drho straight
+        // from its registers is 32 lines per warp instruction (measured: ~16 K LSU wavefronts per tile, as long as the
+        // tile's MMAs).  Global traffic therefore uses a column-major thread mapping — 4 threads cover the chunk's 64
+        // bytes of a row, a warp instruction 8 rows — and is transposed through the group's staging buffer (XOR-swizzled
+        // 16-byte pieces: conflict-free for both mappings).
         float4 mq[4], rq[4];
+        {
+          const int gr = gtid >> 2, gc = gtid & 3;  // row within a 32-row pass, 16-byte piece within the 64-byte row
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool ok = m_ok && nc + 4 * j < N;  // N % 4 == 0
-          mq[j] = ok ? __ldg(reinterpret_cast<const float4*>(fe.mu + row_off + nc) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          rq[j] = ok ? __ldg(reinterpret_cast<const float4*>(fe.rho + row_off + nc) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int p = 0; p < 4; ++p) {
+            const int r = p * 32 + gr;
+            const bool ok = m0 + r < M && nc + 4 * gc < N;  // N % 4 == 0
+            const long long off = static_cast<long long>(m0 + r) * N + nc;
+            mq[p] = ok ? __ldg(reinterpret_cast<const float4*>(fe.mu + off) + gc) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rq[p] = ok ? __ldg(reinterpret_cast<const float4*>(fe.rho + off) + gc) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         uint32_t a0[16], a1[16];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * (2 * kFoBlockN) + tcol;
@@ -300,9 +312,24 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
         }
         float e[16], unused[16];
         noise16<false>(key_e, fe.sa.stream, row_off + nc, e, 0, 0, 0, unused);
+        // stage the parameters (column-major mapping) and read them back row-per-thread
+        {
+          const int gr = gtid >> 2, gc = gtid & 3;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int r = p * 32 + gr;
+            const uint32_t a = r * 64 + ((gc ^ ((r >> 1) & 3)) << 4);
+            ptx::st_shared_v4(sbuf + a, __float_as_uint(mq[p].x), __float_as_uint(mq[p].y), __float_as_uint(mq[p].z), __float_as_uint(mq[p].w));
+            ptx::st_shared_v4(sbuf + 8192 + a, __float_as_uint(rq[p].x), __float_as_uint(rq[p].y), __float_as_uint(rq[p].z), __float_as_uint(rq[p].w));
+          }
+        }
+        ptx::named_bar_sync(bar_id, 128);
+        float4 om4[4], or4[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float mm[4] = {mq[j].x, mq[j].y, mq[j].z, mq[j].w}, rr[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
+          const uint32_t a = row * 64 + ((j ^ ((row >> 1) & 3)) << 4);
+          const float4 m4 = ld_shared_v4f(sbuf + a), r4 = ld_shared_v4f(sbuf + 8192 + a);
+          const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
           float om[4], orr[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -312,11 +339,31 @@ gemm_flipout_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_cons
             om[i] = __uint_as_float(a0[4 * j + i]) + klg * (mm[i] - fe.prior_mean) * inv_s2;
             orr[i] = (__uint_as_float(a1[4 * j + i]) * e[4 * j + i] + klg * (sigma * inv_s2 - __fdividef(1.f, sigma))) * sgm;
           }
-          if (m_ok && nc + 4 * j < N) {
-            reinterpret_cast<float4*>(fe.dmu + row_off + nc)[j] = make_float4(om[0], om[1], om[2], om[3]);
-            reinterpret_cast<float4*>(fe.drho + row_off + nc)[j] = make_float4(orr[0], orr[1], orr[2], orr[3]);
+          om4[j] = make_float4(om[0], om[1], om[2], om[3]);
+          or4[j] = make_float4(orr[0], orr[1], orr[2], orr[3]);
+        }
+        ptx::named_bar_sync(bar_id, 128);  // every thread has read its parameters: the buffer takes the results
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a = row * 64 + ((j ^ ((row >> 1) & 3)) << 4);
+          ptx::st_shared_v4(sbuf + a, __float_as_uint(om4[j].x), __float_as_uint(om4[j].y), __float_as_uint(om4[j].z), __float_as_uint(om4[j].w));
+          ptx::st_shared_v4(sbuf + 8192 + a, __float_as_uint(or4[j].x), __float_as_uint(or4[j].y), __float_as_uint(or4[j].z), __float_as_uint(or4[j].w));
+        }
+        ptx::named_bar_sync(bar_id, 128);
+        {
+          const int gr = gtid >> 2, gc = gtid & 3;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int r = p * 32 + gr;
+            if (m0 + r < M && nc + 4 * gc < N) {
+              const uint32_t a = r * 64 + ((gc ^ ((r >> 1) & 3)) << 4);
+              const long long off = static_cast<long long>(m0 + r) * N + nc;
+              reinterpret_cast<float4*>(fe.dmu + off)[gc] = ld_shared_v4f(sbuf + a);
+              reinterpret_cast<float4*>(fe.drho + off)[gc] = ld_shared_v4f(sbuf + 8192 + a);
+            }
           }
         }
+        ptx::named_bar_sync(bar_id, 128);  // results read out: the next chunk may overwrite the buffer
       }
     }
    } else {
