@@ -80,6 +80,7 @@ class Rank1Fwd(C.Structure):
         ("rho_b", _vp), ("eps_b", Noise), ("bias_buf", _vp), ("bias_ld", _i),
         ("fast_ws", _vp), ("xr_ready", _i),
         ("next_mu_r", _vp), ("next_rho_r", _vp), ("next_eps_r", Noise), ("next_xr", _vp), ("next_xr_ld", _i),
+        ("gemm_ready_event", _vp),
     ]
 
 

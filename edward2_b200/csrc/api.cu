@@ -331,6 +331,10 @@ int ed2_rank1_dense_fwd(const ed2_rank1_fwd_args* a, void* stream) {
     g.B = a->w_lp; g.ldb = a->w_ld; g.major_b = kMajorMN;
     g.M = a->batch; g.N = a->out_dim; g.K = a->in_dim;
     g.ep = e; g.epi_mode = kEpiRank1Fwd; g.r1 = &r;
+    if (a->gemm_ready_event != nullptr) {
+      cudaError_t ce = cudaEventRecord(reinterpret_cast<cudaEvent_t>(a->gemm_ready_event), s);
+      if (ce != cudaSuccess) return set_error(ED2_ERR_CUDA, "cudaEventRecord(gemm_ready_event): %s", cudaGetErrorString(ce));
+    }
     return gemm_bf16(g, s);
   }
   if (a->next_mu_r != nullptr)

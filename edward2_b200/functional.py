@@ -162,7 +162,7 @@ class Rank1Dense(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernel, mu_r, rho_r, mu_s, rho_s, bias, act, ensemble_size, dtype, eps_r, eps_s,
                 additive=False, clip=(-10.0, 10.0), rho_b=None, eps_b=None, in_link=None, out_link=None,
-                next_fast=None, precast=None):
+                next_fast=None, precast=None, ready_event=None):
         """additive: (x + r) W + s (dense.py:1126-1127); clip: (min, max)_perturbation_value (dense.py:1108-1110);
         rho_b / eps_b: per-example sampled ensemble bias, `bias` being its mean (dense.py:1131-1139).
         in_link / out_link / next_fast: cross-layer fusion (Rank1Link); next_fast = (mu_r, rho_r, eps_r) of the layer
@@ -221,6 +221,8 @@ class Rank1Dense(torch.autograd.Function):
         a.bias = _p(bias)
         a.y, a.y_ld, a.xr, a.xr_ld = y.data_ptr(), _lib.ld(y), xr.data_ptr(), _lib.ld(xr)
         a.s_buf, a.s_ld, a.z, a.z_ld = _p(s_buf), _ldn(s_buf), _p(z), _ldn(z)
+        if ready_event is not None and fused:
+            a.gemm_ready_event = ready_event.cuda_event
         _lib.check(lib.ed2_rank1_dense_fwd(C.byref(a), _lib.stream_ptr()), "ed2_rank1_dense_fwd")
         if out_link is not None:
             out_link.y_ptr, out_link.z, out_link.mu_s, out_link.rho_s, out_link.eps_s = y.data_ptr(), z, mu_s, rho_s, eps_s
@@ -328,7 +330,7 @@ class Rank1Dense(torch.autograd.Function):
         if dx is not None and dx.dtype != x_dtype:
             dx = dx.to(x_dtype)
         return (dx, dw, dmu_r, drho_r, dmu_s, drho_s, dbias, None, None, None, None, None, None, None, drho_b, None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 class GradSync:

@@ -463,6 +463,20 @@ class DenseRank1(Layer):
         with torch.cuda.stream(self._cast_stream):
             self._precast = (ops.cast(self.kernel.detach(), self.compute_dtype), self.kernel._version)
 
+    def gemm_ready(self):
+        """A CUDA event that the next `call` records right before its GEMM is enqueued (fused bf16 path).  Side-stream work
+        waiting on it — typically `next_layer.precast(ready=layer.gemm_ready())` — becomes runnable together with the GEMM,
+        whose CTAs (higher-priority stream) are placed first; the side work then runs on the SMs the GEMM grid leaves free
+        instead of occupying every SM before the GEMM can start."""
+        ev = torch.cuda.Event()
+        ev.record()  # materialises the handle; re-recorded by the library
+        self._ready_ev = ev
+        return ev
+
+    def _gemm_ready_event(self):
+        ev, self._ready_ev = getattr(self, "_ready_ev", None), None
+        return ev
+
     def _next_fast(self, per):
         ref = getattr(self, "_consumer", None)
         nxt = ref() if ref is not None else None
@@ -498,7 +512,7 @@ class DenseRank1(Layer):
                                self.use_additive_perturbation,
                                (self.min_perturbation_value, self.max_perturbation_value), rho_b,
                                self._noise("eps_bias", S_B, per_example=per) if rho_b is not None else None,
-                               in_link, out_link, self._next_fast(per), w_pre)
+                               in_link, out_link, self._next_fast(per), w_pre, self._gemm_ready_event())
         y._ed2_rank1_link = out_link
         return y
 

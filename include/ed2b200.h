@@ -238,6 +238,10 @@ typedef struct {
   int xr_ready;
   const float* next_mu_r; const float* next_rho_r; ed2_noise next_eps_r;
   void* next_xr; int next_xr_ld;
+  void* gemm_ready_event;  /* optional cudaEvent_t recorded on `stream` right BEFORE the layer's GEMM is enqueued: side-stream
+                              work that should share the SMs with that GEMM (e.g. the next layer's weight cast) waits on it
+                              and becomes runnable at the same moment, so the block scheduler places the higher-priority
+                              GEMM CTAs first and the side work takes the SMs the GEMM grid leaves free */
 } ed2_rank1_fwd_args;
 int ed2_rank1_dense_fwd(const ed2_rank1_fwd_args* a, void* stream);
 
