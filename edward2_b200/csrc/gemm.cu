@@ -163,6 +163,10 @@ int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
       return set_error(ED2_ERR_BAD_ARG, "gemm: fused rank-1 epilogue not available for M=%d N=%d group_rows=%d", g.M,
                        g.N, g.ep.group_rows);
     bn = 256; cg = 2;
+    // few output tiles (the 1000-unit head at 2048 rows: 8 x 4 = 32 tiles of 256 x 256 for 74 SM pairs): 128-column tiles
+    // double the number of work units (forward epilogue only)
+    const long long tiles256 = static_cast<long long>((g.M + 255) / 256) * ((g.N + 255) / 256);
+    if (g.epi_mode == kEpiRank1Fwd && tiles256 * 2 <= num_sms() / 2) bn = 128;
   }
   if (g.ep.lower_only) {
     if (g.M != g.N || g.epi_mode != kEpiGeneric) return set_error(ED2_ERR_BAD_ARG, "gemm: lower_only needs a square generic product");
@@ -209,6 +213,7 @@ int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
 
   if (g.epi_mode == kEpiRank1Fwd) {
     if (g.major_a != kMajorK || g.major_b != kMajorMN) return set_error(ED2_ERR_BAD_ARG, "rank-1 fwd epilogue: layout");
+    if (bn == 128) return launch_one<kMajorK, kMajorMN, 128, 2, kEpiRank1Fwd>(g, ta, tb, to, stream);
     return launch_one<kMajorK, kMajorMN, 256, 2, kEpiRank1Fwd>(g, ta, tb, to, stream);
   }
   if (g.epi_mode == kEpiRank1Bwd) {

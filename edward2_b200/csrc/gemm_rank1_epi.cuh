@@ -157,7 +157,9 @@ __device__ __forceinline__ void rank1_epilogue(const CUtensorMap& tm_out, const 
                                                uint64_t* tmem_empty_bar, uint8_t* smem_store, uint8_t* smem_table,
                                                int warp_idx, uint32_t lane, uint32_t cta_rank, int cluster_id,
                                                int num_clusters, int num_m, int num_n) {
-  static_assert(BLOCK_N == 256, "fused rank-1 epilogue: one configuration (256-column tiles)");
+  static_assert(BLOCK_N == 256 || BLOCK_N == 128, "fused rank-1 epilogue: 256- or 128-column tiles");
+  constexpr int kHalf = BLOCK_N / 2;                 // columns owned by one epilogue group
+  constexpr int kChunks = kHalf / kR1Chunk;          // 16-column chunks per group per tile
   constexpr int kTileM = kBlockM * kCtaGroup;
   const bool is_leader = cta_rank == 0;
   const int grp_id = (warp_idx - 4) >> 2;
@@ -186,7 +188,7 @@ __device__ __forceinline__ void rank1_epilogue(const CUtensorMap& tm_out, const 
     {
       const int n = n0 + et;
       const long long o = static_cast<long long>(e) * N + n;
-      const bool ok = n < N;
+      const bool ok = n < N && et < BLOCK_N;
       st_shared_f32(tab + (0 * 256 + et) * 4, (ok && has_s) ? __ldg(r1.s.mu + o) : 1.f);
       st_shared_f32(tab + (1 * 256 + et) * 4, (ok && samp_s) ? __ldg(r1.s.sg + o) : 0.f);
       st_shared_f32(tab + (3 * 256 + et) * 4, (ok && has_r) ? __ldg(r1.r.mu + o) : 1.f);
@@ -211,7 +213,7 @@ __device__ __forceinline__ void rank1_epilogue(const CUtensorMap& tm_out, const 
     [[maybe_unused]] uint4 xq[2], zq[2];
     [[maybe_unused]] const __nv_bfloat16* x_row = nullptr;
     [[maybe_unused]] const __nv_bfloat16* z_row = nullptr;
-    const int ncol0 = n0 + grp_id * 128;
+    const int ncol0 = n0 + grp_id * kHalf;
     if constexpr (kEpi == kEpiRank1Bwd) {
       x_row = reinterpret_cast<const __nv_bfloat16*>(r1.x) + static_cast<long long>(m_ok ? m : 0) * r1.x_ld;
       if (has_s) z_row = reinterpret_cast<const __nv_bfloat16*>(r1.z_prev) + static_cast<long long>(m_ok ? m : 0) * r1.z_prev_ld;
@@ -227,13 +229,13 @@ __device__ __forceinline__ void rank1_epilogue(const CUtensorMap& tm_out, const 
     }
 
 #pragma unroll 1
-    for (int cc = 0; cc < 128 / kR1Chunk; ++cc) {
-      const int tcol = grp_id * 128 + cc * kR1Chunk;  // column inside the tile
+    for (int cc = 0; cc < kChunks; ++cc) {
+      const int tcol = grp_id * kHalf + cc * kR1Chunk;  // column inside the tile
       const int nc = n0 + tcol;
       uint32_t vr[16];
       tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N + tcol, vr);
       ptx::tmem_ld_wait();
-      if (cc == 128 / kR1Chunk - 1) {
+      if (cc == kChunks - 1) {
         ptx::tc_fence_before();
         if (is_leader) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         else ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
@@ -310,7 +312,7 @@ __device__ __forceinline__ void rank1_epilogue(const CUtensorMap& tm_out, const 
           }
         }
         // next chunk's operands: in flight during this chunk's arithmetic
-        if (m_ok && cc + 1 < 128 / kR1Chunk) {
+        if (m_ok && cc + 1 < kChunks) {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (nc + kR1Chunk + 8 * j < N) {
