@@ -167,6 +167,9 @@ int gemm_bf16(const GemmDesc& g_in, cudaStream_t stream) {
     // double the number of work units (forward epilogue only)
     const long long tiles256 = static_cast<long long>((g.M + 255) / 256) * ((g.N + 255) / 256);
     if (g.epi_mode == kEpiRank1Fwd && tiles256 * 2 <= num_sms() / 2) bn = 128;
+    // (measured, not kept: 128-column tiles for the short-K, epilogue-bound launches — 512 units on 74 pairs instead of
+    // 256 on 64 — leave the dX launch of the 1000-unit head at 148 us: the bound is the epilogue's total instruction
+    // work, not tile granularity)
   }
   if (g.ep.lower_only) {
     if (g.M != g.N || g.epi_mode != kEpiGeneric) return set_error(ED2_ERR_BAD_ARG, "gemm: lower_only needs a square generic product");
