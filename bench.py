@@ -500,6 +500,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and args.gemm_ctas > 0:
         os.environ.setdefault("ED2_GEMM_MAX_CTAS", str(args.gemm_ctas))
+    if world > 1:
+        # full GEMM grids under data parallelism: the exchange's SM kernels then run at full width between two GEMMs
+        # instead of starting on the 20 SMs a minimal-wave grid leaves free (libed2b200: ED2_GEMM_MINWAVE)
+        os.environ.setdefault("ED2_GEMM_MINWAVE", "0")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     lib = _lib.load()

@@ -91,7 +91,11 @@ int launch_one(const GemmDesc& g, const CUtensorMap& ta, const CUtensorMap& tb, 
   // the smallest grid that needs the same number of waves: 256 tiles on 74 SM pairs are 4 waves, and so they are on 64
   // pairs — the 20 SMs left over run the side-stream kernels (weight casts, KL, the gradient exchange) that cannot
   // co-reside with a persistent GEMM CTA
-  {
+  // ED2_GEMM_MINWAVE=0 keeps the full grid: in data-parallel runs the exchange's SM kernels (persistent grids) would
+  // otherwise start on the few free SMs while a GEMM runs and crawl there instead of running at full width between two
+  // GEMMs (measured at N = 8: 1.92 ms per step with the reduced grids)
+  static const bool min_wave = [] { const char* e = std::getenv("ED2_GEMM_MINWAVE"); return e == nullptr || std::atoi(e) != 0; }();
+  if (min_wave) {
     const int waves = (num_tiles + clusters - 1) / clusters;
     clusters = (num_tiles + waves - 1) / waves;
   }

@@ -4,8 +4,13 @@ _compute_predictive_mean :204-226, _compute_predictive_variance :228-253, factor
 variance mixing of HeteroscedasticSNGPLayer (edward2/tensorflow/layers/hetsngp.py:143-170, call :186-240).
 
 Every random tensor is an explicit argument: z [B or 1, S, F] standard-normal factor samples, e [B or 1, S, K] diagonal
-noise samples (batch dimension 1 = share_samples_across_batch).  Parity is unpinned against the reference itself (TF /
-TFP are not installable here); the closed-form gradient is pinned against float64 autograd in tests/test_oracle.py."""
+noise samples (batch dimension 1 = share_samples_across_batch).  PINNED to the reference: the unmodified
+edward2/jax/nn/heteroscedastic_lib.py (MCSoftmaxDenseFA, :43-336) is executed under the NumPy-backed jax / flax stand-ins
+with its jax.random.normal draws recorded (tests/golden/make_reference_golden.py); tests/test_oracle.py::
+test_reference_mc_softmax_dense_fa checks this restatement against those outputs at 1e-12 and
+tests/test_gpu_reference_golden.py checks the CUDA kernel against them.  (The TF classes cannot run here — TF / TFP are
+not installable; they differ from the JAX class only in drawing the diagonal noise per class instead of per sample, which
+is an input here.)  The closed-form gradient is pinned against float64 autograd in tests/test_oracle.py."""
 from __future__ import annotations
 
 import numpy as np

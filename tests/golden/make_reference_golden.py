@@ -1,6 +1,6 @@
 """Generates tests/golden/reference_vectors.npz by EXECUTING THE UNMODIFIED REFERENCE SOURCE FILES
 
-    /root/reference/edward2/jax/nn/{dense,random_feature,normalization,utils}.py
+    /root/reference/edward2/jax/nn/{dense,random_feature,normalization,utils,heteroscedastic_lib}.py
 
 under the NumPy-backed stand-ins of jax / flax in tests/golden/refstub/ (neither library is installed here; see
 refstub/README.md).  Every arithmetic statement that runs is the reference's; the stand-ins evaluate it in float64.
@@ -30,7 +30,7 @@ def load_reference():
     for name in ("edward2", "edward2.jax", "edward2.jax.nn"):
         sys.modules.setdefault(name, types.ModuleType(name))
     mods = {}
-    for name in ("utils", "dense", "normalization", "random_feature"):
+    for name in ("utils", "dense", "normalization", "random_feature", "heteroscedastic_lib"):
         full = f"edward2.jax.nn.{name}"
         spec = importlib.util.spec_from_file_location(full, os.path.join(REF, f"{name}.py"))
         m = importlib.util.module_from_spec(spec)
@@ -138,6 +138,42 @@ def main():
         out[f"mf_{lik}"] = utils.mean_field_logits(lg, var, mean_field_factor=0.7, likelihood=lik)
     out["mf_nocov"] = utils.mean_field_logits(lg, None, mean_field_factor=3.0)
     out["mf_negative"] = utils.mean_field_logits(lg, var, mean_field_factor=-1.0)
+
+    # ---- §8f-2 MCSoftmaxDenseFA.__call__ (heteroscedastic_lib.py:43-336): Monte-Carlo softmax with factor-analysis noise.
+    # The stand-in jax.random.normal is wrapped so that the draws the reference makes are stored next to its outputs.
+    het = mods["heteroscedastic_lib"]
+    import jax.random as jr
+
+    real_normal = jr.normal
+    for tag, share, temp in (("het", False, 1.0), ("het_shared", True, 0.6)):
+        drawn = []
+
+        def recording_normal(key, shape=(), dtype=None, _d=drawn):
+            v = real_normal(key, shape, dtype)
+            _d.append(np.array(v))
+            return v
+
+        jr.normal = jax.random.normal = recording_normal
+        try:
+            B, Din, K, Fn, S = 9, 7, 5, 3, 64
+            layer = het.MCSoftmaxDenseFA(num_classes=K, num_factors=Fn, temperature=temp, train_mc_samples=S,
+                                         test_mc_samples=S, share_samples_across_batch=share)
+            x = rng.standard_normal((B, Din))
+            rngs = {"params": jax.random.PRNGKey(6), "diag_noise_samples": jax.random.PRNGKey(7),
+                    "standard_norm_noise_samples": jax.random.PRNGKey(8)}
+            v = layer.init(rngs, x)
+            for name in ("loc_layer", "scale_layer", "diag_layer"):  # non-trivial biases (init: zeros)
+                v["params"][name]["bias"] = rng.standard_normal(v["params"][name]["bias"].shape) * 0.2
+            del drawn[:]
+            logits, log_probs, probs = layer.apply(v, x, training=True, rngs=rngs)
+        finally:
+            jr.normal = jax.random.normal = real_normal
+        diag_n, fac_n = [d for d in drawn if d.ndim == 3 and d.shape[-1] == 1][-1], [d for d in drawn if d.ndim == 3 and d.shape[-1] == Fn][-1]
+        out.update({f"{tag}_x": x, f"{tag}_logits": logits, f"{tag}_log_probs": log_probs, f"{tag}_probs": probs,
+                    f"{tag}_diag_noise": diag_n, f"{tag}_factor_noise": fac_n, f"{tag}_temperature": np.float64(temp)})
+        for name in ("loc_layer", "scale_layer", "diag_layer"):
+            out[f"{tag}_{name}_kernel"] = v["params"][name]["kernel"]
+            out[f"{tag}_{name}_bias"] = v["params"][name]["bias"]
 
     np.savez_compressed(OUT, **{k: np.asarray(a) for k, a in out.items()})
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")

@@ -4,6 +4,7 @@ runs inside a reference module is the reference's own code."""
 import dataclasses
 import functools
 import types
+import zlib
 from typing import Any, Optional
 
 import numpy as np
@@ -61,6 +62,10 @@ initializers = types.SimpleNamespace(
     he_normal=lambda: _variance_scaling(2.0, "fan_in", "truncated_normal"),
     zeros_init=lambda: _zeros, ones_init=lambda: _ones,
 )
+
+
+# flax.linen.linear.default_kernel_init (heteroscedastic_lib.py:90)
+linear = types.SimpleNamespace(default_kernel_init=initializers.lecun_normal())
 
 
 def relu(x):
@@ -279,7 +284,8 @@ class Module:
     def make_rng(self, name):
         base = self._scope.rngs[name]
         self._scope.rng_count += 1
-        mix = hash((self._path, self._scope.rng_count)) & 0xFFFFFFFF
+        # deterministic across processes (Python's str hash is salted): the fixture can be regenerated bit for bit
+        mix = zlib.crc32(repr((self._path, self._scope.rng_count)).encode()) & 0xFFFFFFFF
         return np.array([int(np.asarray(base).reshape(-1)[-1]), mix], dtype=np.uint32)
 
     def has_variable(self, col, name):

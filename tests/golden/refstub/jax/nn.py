@@ -12,3 +12,10 @@ def softplus(x):
 
 def relu(x):
     return _np.maximum(x, 0.0)
+
+
+def softmax(x, axis=-1):
+    x = _np.asarray(x, dtype=_np.float64)
+    x = x - x.max(axis=axis, keepdims=True)
+    e = _np.exp(x)
+    return e / e.sum(axis=axis, keepdims=True)

@@ -134,3 +134,29 @@ def test_mean_field_logits_vs_reference(cuda, ref):
         assert rel_err(to_np(out), ref[f"mf_{lik}"]) < FP32
     assert rel_err(to_np(ed.nn.mean_field_logits(lg, None, mean_field_factor=3.0)), ref["mf_nocov"]) < FP32
     assert rel_err(to_np(ed.nn.mean_field_logits(lg, var, mean_field_factor=-1.0)), ref["mf_negative"]) < 1e-7
+
+
+@pytest.mark.parametrize("tag", ["het", "het_shared"])
+def test_mc_softmax_dense_fa_vs_reference(cuda, ref, tag):
+    """The Monte-Carlo softmax kernel against the outputs of the reference's own MCSoftmaxDenseFA
+    (edward2/jax/nn/heteroscedastic_lib.py:43-336) with its recorded noise injected; the three Dense parameter layers run on
+    the CUDA path with the reference's variables."""
+    from edward2_b200 import functional as F
+
+    x = ref[f"{tag}_x"]
+    B = x.shape[0]
+    xt = _t(x, cuda)
+    lin = lambda n: F.Dense.apply(xt, _t(ref[f"{tag}_{n}_kernel"], cuda), _t(ref[f"{tag}_{n}_bias"], cuda), 0,  # noqa: E731
+                                  torch.float32, None)
+    loc, fac, draw = lin("loc_layer"), lin("scale_layer"), lin("diag_layer")
+    K, Fn = loc.shape[1], ref[f"{tag}_factor_noise"].shape[-1]
+    z, n = ref[f"{tag}_factor_noise"], ref[f"{tag}_diag_noise"]
+    rows, S = z.shape[0], z.shape[1]
+    FP, KP = (Fn + 7) // 8 * 8, (K + 7) // 8 * 8
+    buf = np.zeros((rows, S, FP + KP), dtype=np.float32)
+    buf[:, :, :Fn] = z
+    buf[:, :, FP:FP + K] = np.broadcast_to(n, (rows, S, K))
+    logits, probs, _ = F.MCSoftmaxFA.apply(loc, fac, draw, None, 1.0, 1.0, F.Randomness(torch.tensor(buf, device=cuda)), S, Fn,
+                                           rows == 1 and B > 1, float(ref[f"{tag}_temperature"]), 1e-7, False)
+    assert rel_err(to_np(probs), ref[f"{tag}_probs"]) < FP32
+    assert rel_err(to_np(logits), ref[f"{tag}_logits"]) < FP32

@@ -633,3 +633,24 @@ def test_recurrent_oracle_bptt_matches_autograd():
     for key, ref in (("dxs", t["xs"].grad), ("dh0", t["h0"].grad), ("dc0", t["c0"].grad), ("dW", t["W"].grad),
                      ("dU", t["U"].grad), ("db", t["b"].grad)):
         np.testing.assert_allclose(g[key], ref.numpy(), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["het", "het_shared"])
+def test_reference_mc_softmax_dense_fa(ref, tag):
+    """jax/nn/heteroscedastic_lib.py:43-336 (MCSoftmaxDenseFA) run as shipped, with the draws of its jax.random.normal calls
+    recorded: loc / scale / diag Dense layers, latent = loc + V z + diag * n, softmax / T, mean over samples, clip, log.
+    (The JAX class draws ONE diagonal-noise scalar per (example, sample), shape [B, S, 1] (:186-188); the TF class draws one
+    per class (heteroscedastic.py:676-707) — the oracle takes the noise as an explicit [B, S, K] argument, so both are the
+    same formula.)"""
+    from oracle import heteroscedastic as oh
+
+    x = ref[f"{tag}_x"]
+    lin = lambda n: x @ ref[f"{tag}_{n}_kernel"] + ref[f"{tag}_{n}_bias"]  # noqa: E731
+    loc, fac, draw = lin("loc_layer"), lin("scale_layer"), lin("diag_layer")
+    K = loc.shape[1]
+    z = ref[f"{tag}_factor_noise"]
+    e = np.broadcast_to(ref[f"{tag}_diag_noise"], ref[f"{tag}_diag_noise"].shape[:2] + (K,))
+    logits, probs, _ = oh.mc_softmax_fa(loc, fac, draw, z, e, float(ref[f"{tag}_temperature"]), 1e-7)
+    _close(probs, ref[f"{tag}_probs"])
+    _close(logits, ref[f"{tag}_logits"])
+    _close(logits, ref[f"{tag}_log_probs"])
