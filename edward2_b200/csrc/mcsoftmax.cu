@@ -49,7 +49,7 @@ struct McArgs {
   float w_het, w_sngp;
   Noise noise;            // normal stream; injected: [NB][S][P] fp32
   int B, S, K, F;
-  int shared;             // share_samples_across_batch
+  int shared;             // bit 0: share_samples_across_batch; bit 1: one diagonal draw per sample for all classes
   float inv_t, eps;
   float* probs_mean;      // [B][K]
   float* logits;          // [B][K]
@@ -64,11 +64,12 @@ template <int KMAX>
 __device__ __forceinline__ void draw_sample(const McArgs& a, uint64_t key, long long sample, int FP, int KP, float (&z)[kFMax],
                                             float (&e)[KMAX]) {
   const long long base = sample * (FP + KP);
+  const bool diag_one = (a.shared & 2) != 0;  // ONE diagonal draw per (example, sample), shared by the classes
   if (a.noise.injected != nullptr) {
 #pragma unroll
     for (int f = 0; f < kFMax; ++f) z[f] = f < a.F ? __ldg(a.noise.injected + base + f) : 0.f;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) e[k] = k < a.K ? __ldg(a.noise.injected + base + FP + k) : 0.f;
+    for (int k = 0; k < KMAX; ++k) e[k] = k < a.K ? __ldg(a.noise.injected + base + FP + (diag_one ? 0 : k)) : 0.f;
     return;
   }
 #pragma unroll
@@ -81,9 +82,14 @@ __device__ __forceinline__ void draw_sample(const McArgs& a, uint64_t key, long 
 #pragma unroll
   for (int kb = 0; kb < KMAX / 8; ++kb) {
     float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (kb * 8 < a.K) philox_normal8<true>(key, a.noise.stream, static_cast<uint64_t>(((base + FP) >> 3) + kb), t);
+    if (kb * 8 < a.K && !(diag_one && kb > 0))
+      philox_normal8<true>(key, a.noise.stream, static_cast<uint64_t>(((base + FP) >> 3) + kb), t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) e[kb * 8 + j] = t[j];
+  }
+  if (diag_one) {
+#pragma unroll
+    for (int k = 1; k < KMAX; ++k) e[k] = e[0];
   }
 }
 
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_fwd_kernel(McArgs a) {
   stage_params(a, b, lane, sloc, sdiag, sfac);
   const int FP = (a.F + 7) & ~7, KP = (a.K + 7) & ~7;
   const uint64_t key = noise_key(a.noise);
-  const long long nb = a.shared ? 0 : (a.noise.injected != nullptr ? b : noise_row(a.noise, b));
+  const long long nb = (a.shared & 1) ? 0 : (a.noise.injected != nullptr ? b : noise_row(a.noise, b));
   float acc[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
   __syncwarp();
   const int FP = (a.F + 7) & ~7, KP = (a.K + 7) & ~7;
   const uint64_t key = noise_key(a.noise);
-  const long long nb = a.shared ? 0 : (a.noise.injected != nullptr ? b : noise_row(a.noise, b));
+  const long long nb = (a.shared & 1) ? 0 : (a.noise.injected != nullptr ? b : noise_row(a.noise, b));
   float dl[KMAX], dd[KMAX];
   constexpr int kSlots = (KMAX * kFMax + 31) / 32;  // outer-product entries owned by one lane
   float dv[kSlots];

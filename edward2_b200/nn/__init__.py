@@ -2,14 +2,16 @@
 
 The JAX backend of the reference exports DenseBatchEnsemble, RandomFeatureGaussianProcess, RandomFourierFeatures,
 LaplaceRandomFeatureCovariance, SpectralNormalization and utils (edward2/jax/nn/__init__.py:18-53); it has no
-DenseRank1 / DenseFlipout / DenseReparameterization.
+DenseRank1 / DenseFlipout / DenseReparameterization.  MCSoftmaxDenseFA mirrors
+edward2/jax/nn/heteroscedastic_lib.py.
 """
 from . import utils
 from .dense import DenseBatchEnsemble
+from .heteroscedastic import MCSoftmaxDenseFA
 from .module import Module
 from .normalization import Dense, SpectralNormalization
 from .random_feature import LaplaceRandomFeatureCovariance, RandomFeatureGaussianProcess, RandomFourierFeatures
 from .utils import make_sign_initializer, mean_field_logits
 
 __all__ = ["Module", "Dense", "DenseBatchEnsemble", "SpectralNormalization", "LaplaceRandomFeatureCovariance",
-           "RandomFeatureGaussianProcess", "RandomFourierFeatures", "make_sign_initializer", "mean_field_logits", "utils"]
+           "RandomFeatureGaussianProcess", "RandomFourierFeatures", "MCSoftmaxDenseFA", "make_sign_initializer", "mean_field_logits", "utils"]

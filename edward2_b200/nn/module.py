@@ -31,8 +31,9 @@ class PRNG:
 
 
 class _Scope:
-    def __init__(self, variables, mutable, initializing, rng, path=()):
+    def __init__(self, variables, mutable, initializing, rng, path=(), rngs=None):
         self.variables, self.mutable, self.initializing, self.rng, self.path = variables, mutable, initializing, rng, path
+        self.rngs = rngs or {}  # named streams passed to init / apply (flax: rngs={'dropout': key, ...})
 
     def collection(self, col, create=False):
         d = self.variables.setdefault(col, {}) if create else self.variables.get(col, {})
@@ -44,7 +45,7 @@ class _Scope:
         return d
 
     def child(self, name):
-        return _Scope(self.variables, self.mutable, self.initializing, self.rng.fold(name), self.path + (name,))
+        return _Scope(self.variables, self.mutable, self.initializing, self.rng.fold(name), self.path + (name,), self.rngs)
 
 
 class Module:
@@ -84,7 +85,8 @@ class Module:
     def init(self, rngs, *args, device="cuda", **kwargs):
         rng = rngs.get("params", 0) if isinstance(rngs, dict) else rngs
         variables = {}
-        with self._bind(_Scope(variables, mutable=True, initializing=True, rng=PRNG(rng)), device):
+        named = {k: v for k, v in rngs.items() if k != "params"} if isinstance(rngs, dict) else {}
+        with self._bind(_Scope(variables, mutable=True, initializing=True, rng=PRNG(rng), rngs=named), device):
             self(*args, **kwargs)
         variables.pop("intermediates", None)
         return variables
@@ -98,7 +100,7 @@ class Module:
             mut = set([mutable] if isinstance(mutable, str) else mutable)
         work = {k: _copy_tree(v) for k, v in variables.items()}
         dev = _first_device(variables)
-        with self._bind(_Scope(work, mutable=mut, initializing=False, rng=PRNG(0)), dev):
+        with self._bind(_Scope(work, mutable=mut, initializing=False, rng=PRNG(0), rngs=dict(rngs or {})), dev):
             out = self(*args, **kwargs)
         if mutable is False or mutable is None:
             return out
@@ -128,6 +130,13 @@ class Module:
         return self._scope.initializing
 
     def make_rng(self, name="params") -> PRNG:
+        """A named stream passed as rngs={name: seed} to init / apply (folded with the module path), else derived from
+        the module's own stream."""
+        if name in self._scope.rngs:
+            base = PRNG(self._scope.rngs[name])
+            for p in self._scope.path:
+                base = base.fold(p)
+            return base.fold(name)
         return self._scope.rng.fold(name)
 
     def param(self, name, init_fn, *init_args):

@@ -517,7 +517,10 @@ int ed2_flipout_fusable(int batch, int in_dim, int out_dim);
  *   probs_mean = mean_s softmax(latent / temperature);  logits = log(clip(probs_mean, eps, 1));
  *   variance (optional) = mean_s (softmax_s - probs_mean)²
  * Noise: a normal stream; sample (b, s) owns elements [(row(b) S + s) P, +P), P = round8(F) + round8(K) (z, then e);
- * injected: [batch][S][P] fp32.  share_samples: every example reads row 0.  num_classes <= 64, num_factors <= 16.
+ * injected: [batch][S][P] fp32.  share_samples bit 0: every example reads row 0 (share_samples_across_batch); bit 1: ONE
+ * diagonal draw per (example, sample), element 0 of the e block, shared by all classes — the JAX class
+ * (edward2/jax/nn/heteroscedastic_lib.py:186-188: noise of shape [B, S, 1]); the TF class draws one per class.
+ * num_classes <= 64, num_factors <= 16.
  * The backward regenerates the samples: dloc, dfac, ddiag_raw from g = dL/dlogits (training form: no sngp_var). */
 int ed2_mc_softmax_fa_fwd(const float* loc, const float* fac, const float* diag_raw, const float* sngp_var, float w_het,
                           float w_sngp, ed2_noise noise, int batch, int num_samples, int num_classes, int num_factors,

@@ -138,25 +138,32 @@ def test_mean_field_logits_vs_reference(cuda, ref):
 
 @pytest.mark.parametrize("tag", ["het", "het_shared"])
 def test_mc_softmax_dense_fa_vs_reference(cuda, ref, tag):
-    """The Monte-Carlo softmax kernel against the outputs of the reference's own MCSoftmaxDenseFA
-    (edward2/jax/nn/heteroscedastic_lib.py:43-336) with its recorded noise injected; the three Dense parameter layers run on
-    the CUDA path with the reference's variables."""
-    from edward2_b200 import functional as F
-
+    """`edward2_b200.nn.MCSoftmaxDenseFA` with the reference's variables loaded and its recorded noise injected, against
+    the outputs of the reference's own MCSoftmaxDenseFA (edward2/jax/nn/heteroscedastic_lib.py:43-336): Dense parameter
+    layers + Monte-Carlo softmax kernel in its JAX form (one diagonal draw per sample)."""
+    ed = _ed()
     x = ref[f"{tag}_x"]
-    B = x.shape[0]
-    xt = _t(x, cuda)
-    lin = lambda n: F.Dense.apply(xt, _t(ref[f"{tag}_{n}_kernel"], cuda), _t(ref[f"{tag}_{n}_bias"], cuda), 0,  # noqa: E731
-                                  torch.float32, None)
-    loc, fac, draw = lin("loc_layer"), lin("scale_layer"), lin("diag_layer")
-    K, Fn = loc.shape[1], ref[f"{tag}_factor_noise"].shape[-1]
     z, n = ref[f"{tag}_factor_noise"], ref[f"{tag}_diag_noise"]
-    rows, S = z.shape[0], z.shape[1]
+    rows, S, Fn = z.shape
+    K = ref[f"{tag}_loc_layer_bias"].shape[0]
     FP, KP = (Fn + 7) // 8 * 8, (K + 7) // 8 * 8
     buf = np.zeros((rows, S, FP + KP), dtype=np.float32)
     buf[:, :, :Fn] = z
-    buf[:, :, FP:FP + K] = np.broadcast_to(n, (rows, S, K))
-    logits, probs, _ = F.MCSoftmaxFA.apply(loc, fac, draw, None, 1.0, 1.0, F.Randomness(torch.tensor(buf, device=cuda)), S, Fn,
-                                           rows == 1 and B > 1, float(ref[f"{tag}_temperature"]), 1e-7, False)
+    buf[:, :, FP] = n[:, :, 0]
+    layer = ed.nn.MCSoftmaxDenseFA(num_classes=K, num_factors=Fn, temperature=float(ref[f"{tag}_temperature"]),
+                                   train_mc_samples=S, test_mc_samples=S, share_samples_across_batch=(tag == "het_shared"))
+    variables = {"params": {name: {"kernel": _t(ref[f"{tag}_{name}_kernel"], cuda, True), "bias": _t(ref[f"{tag}_{name}_bias"], cuda, True)}
+                            for name in ("loc_layer", "scale_layer", "diag_layer")}}
+    logits, log_probs, probs = layer.apply(variables, _t(x, cuda), training=True, mc_noise=torch.tensor(buf, device=cuda))
     assert rel_err(to_np(probs), ref[f"{tag}_probs"]) < FP32
     assert rel_err(to_np(logits), ref[f"{tag}_logits"]) < FP32
+    assert rel_err(to_np(log_probs), ref[f"{tag}_log_probs"]) < FP32
+    # init / apply with named rng streams: fresh noise per seed, reproducible per seed; gradients reach every parameter
+    v = layer.init({"params": 0, "diag_noise_samples": 1, "standard_norm_noise_samples": 2}, _t(x, cuda))
+    assert set(v["params"]) == {"loc_layer", "scale_layer", "diag_layer"}
+    a = layer.apply(v, _t(x, cuda), rngs={"diag_noise_samples": 5, "standard_norm_noise_samples": 6})[0]
+    b = layer.apply(v, _t(x, cuda), rngs={"diag_noise_samples": 5, "standard_norm_noise_samples": 6})[0]
+    c = layer.apply(v, _t(x, cuda), rngs={"diag_noise_samples": 7, "standard_norm_noise_samples": 6})[0]
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    a.sum().backward()
+    assert all(v["params"][nm]["kernel"].grad is not None for nm in v["params"])
