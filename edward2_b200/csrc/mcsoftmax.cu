@@ -49,7 +49,8 @@ struct McArgs {
   float w_het, w_sngp;
   Noise noise;            // normal stream; injected: [NB][S][P] fp32
   int B, S, K, F;
-  int shared;             // bit 0: share_samples_across_batch; bit 1: one diagonal draw per sample for all classes
+  int shared;             // flags — bit 0: share_samples_across_batch; bit 1: one diagonal draw per sample for all
+                          // classes; bit 2: sigmoid link instead of softmax
   float inv_t, eps;
   float* probs_mean;      // [B][K]
   float* logits;          // [B][K]
@@ -111,6 +112,11 @@ __device__ __forceinline__ void sample_probs(const McArgs& a, const float* sloc,
     }
     p[k] = lat;
   }
+  if (a.shared & 4) {  // sigmoid link (MCSigmoidDenseFA): independent outputs
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) p[k] = k < a.K ? 1.f / (1.f + expf(-p[k])) : 0.f;
+    return;
+  }
   float sum = 0.f;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
@@ -165,7 +171,10 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_fwd_kernel(McArgs a) {
       acc[k] = warp_sum(acc[k]) * inv_s;
       if (lane == 0) {
         a.probs_mean[static_cast<long long>(b) * a.K + k] = acc[k];
-        a.logits[static_cast<long long>(b) * a.K + k] = logf(fminf(fmaxf(acc[k], a.eps), 1.f));
+        // softmax: log(clip(pm, eps, 1));  sigmoid: inverse sigmoid log(clip(pm, eps)) - log(1 - clip(pm, eps, 1 - eps))
+        a.logits[static_cast<long long>(b) * a.K + k] =
+            (a.shared & 4) ? logf(fmaxf(acc[k], a.eps)) - logf(1.f - fminf(fmaxf(acc[k], a.eps), 1.f - a.eps))
+                           : logf(fminf(fmaxf(acc[k], a.eps), 1.f));
       }
     }
   }
@@ -207,7 +216,13 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
   const float inv_s = 1.f / static_cast<float>(a.S);
   for (int k = lane; k < a.K; k += 32) {
     const float pm = __ldg(a.probs_mean + static_cast<long long>(b) * a.K + k);
-    su[k] = (pm > a.eps && pm <= 1.f) ? __ldg(a.g + static_cast<long long>(b) * a.K + k) / pm * inv_s : 0.f;  // clip: zero gradient outside
+    const float gk = __ldg(a.g + static_cast<long long>(b) * a.K + k);
+    if (a.shared & 4) {  // d logit / d pm of the inverse sigmoid; the clips pass no gradient outside their ranges
+      const float d = (pm > a.eps ? 1.f / pm : 0.f) + ((pm > a.eps && pm < 1.f - a.eps) ? 1.f / (1.f - pm) : 0.f);
+      su[k] = gk * d * inv_s;
+    } else {
+      su[k] = (pm > a.eps && pm <= 1.f) ? gk / pm * inv_s : 0.f;  // clip: zero gradient outside
+    }
   }
   __syncwarp();
   const int FP = (a.F + 7) & ~7, KP = (a.K + 7) & ~7;
@@ -236,7 +251,7 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < a.K) {
-        const float d = live ? a.inv_t * p[k] * (su[k] - dot) : 0.f;
+        const float d = !live ? 0.f : (a.shared & 4) ? a.inv_t * su[k] * p[k] * (1.f - p[k]) : a.inv_t * p[k] * (su[k] - dot);
         dl[k] += d;
         dd[k] = fmaf(d, live ? e[k] : 0.f, dd[k]);
         scratch[lane * row + k] = d;
@@ -279,7 +294,7 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
 }
 
 int check(const McArgs& a) {
-  if (a.B <= 0 || a.S <= 0 || a.K < 2 || a.F < 1) return set_error(ED2_ERR_BAD_SHAPE, "mc_softmax: B=%d S=%d K=%d F=%d", a.B, a.S, a.K, a.F);
+  if (a.B <= 0 || a.S <= 0 || a.K < 1 || a.F < 1) return set_error(ED2_ERR_BAD_SHAPE, "mc_softmax: B=%d S=%d K=%d F=%d", a.B, a.S, a.K, a.F);
   if (a.K > 64) return set_error(ED2_ERR_BAD_SHAPE, "mc_softmax: num_classes %d > 64 is not built", a.K);
   if (a.F > kFMax) return set_error(ED2_ERR_BAD_SHAPE, "mc_softmax: num_factors %d > %d is not built", a.F, kFMax);
   return ED2_OK;

@@ -2,13 +2,13 @@
 from . import utils
 from .base import Layer
 from .convolutional import Conv2DBatchEnsemble, Conv2DFlipout, Conv2DRank1, Conv2DReparameterization
-from .heteroscedastic import HeteroscedasticSNGPLayer, MCSoftmaxDenseFA
+from .heteroscedastic import HeteroscedasticSNGPLayer, MCSigmoidDenseFA, MCSoftmaxDenseFA
 from .dense import Dense, DenseBatchEnsemble, DenseFlipout, DenseRank1, DenseReparameterization
 from .normalization import SpectralNormalization
 from .recurrent import LSTMCellReparameterization
 from .random_feature import LaplaceRandomFeatureCovariance, RandomFeatureGaussianProcess
 
 __all__ = [
-    "Layer", "Conv2DBatchEnsemble", "Conv2DFlipout", "Conv2DRank1", "Conv2DReparameterization", "Dense", "DenseBatchEnsemble", "DenseFlipout", "DenseRank1", "DenseReparameterization", "HeteroscedasticSNGPLayer", "LSTMCellReparameterization", "MCSoftmaxDenseFA",
+    "Layer", "Conv2DBatchEnsemble", "Conv2DFlipout", "Conv2DRank1", "Conv2DReparameterization", "Dense", "DenseBatchEnsemble", "DenseFlipout", "DenseRank1", "DenseReparameterization", "HeteroscedasticSNGPLayer", "LSTMCellReparameterization", "MCSigmoidDenseFA", "MCSoftmaxDenseFA",
     "SpectralNormalization", "LaplaceRandomFeatureCovariance", "RandomFeatureGaussianProcess", "utils",
 ]

@@ -98,6 +98,54 @@ class MCSoftmaxDenseFA(Layer):
         return cfg
 
 
+class MCSigmoidDenseFA(MCSoftmaxDenseFA):
+    """Sigmoid and factor-analysis approximation to heteroscedastic (multi-label) predictions
+    (edward2/tensorflow/layers/heteroscedastic.py:1362-1680): independent sigmoid outputs, logits = inverse sigmoid of the
+    Monte-Carlo mean probabilities.  __call__ -> logits, or (logits, log_probs, probs, predictive_variance)."""
+
+    def __init__(self, num_outputs, num_factors=0, temperature=1.0, parameter_efficient=False, train_mc_samples=1000,
+                 test_mc_samples=1000, compute_pred_variance=False, share_samples_across_batch=False, logits_only=False,
+                 eps=1e-7, dtype=None, kernel_regularizer=None, bias_regularizer=None, return_unaveraged_logits=False,
+                 tune_temperature=False, temperature_lower_bound=None, temperature_upper_bound=None,
+                 name="MCSigmoidDenseFA", **kwargs):
+        if num_factors <= 0:
+            raise NotImplementedError("num_factors = 0 (the diagonal method) is not built: num_factors >= 1")
+        if return_unaveraged_logits or tune_temperature:
+            raise NotImplementedError("return_unaveraged_logits / tune_temperature are not built")
+        # the softmax head's constructor rejects num_classes <= 2; the sigmoid head has no such restriction
+        super().__init__(num_classes=max(int(num_outputs), 3), num_factors=num_factors, temperature=temperature,
+                         parameter_efficient=parameter_efficient, train_mc_samples=train_mc_samples,
+                         test_mc_samples=test_mc_samples, compute_pred_variance=compute_pred_variance,
+                         share_samples_across_batch=share_samples_across_batch, logits_only=logits_only, eps=eps,
+                         dtype=dtype, kernel_regularizer=kernel_regularizer, bias_regularizer=bias_regularizer, name=name,
+                         **kwargs)
+        if int(num_outputs) != self._num_classes:  # rebuild the parameter layers at the true width
+            from .dense import Dense
+
+            self._num_classes = int(num_outputs)
+            mk = lambda units, nm: Dense(units, kernel_regularizer=kernel_regularizer, bias_regularizer=bias_regularizer,  # noqa: E731
+                                         dtype=dtype, name=f"{name}_{nm}")
+            self._scale_layer = mk(self._num_classes * self._num_factors, "scale_layer")
+            self._loc_layer = mk(self._num_classes, "loc_layer")
+            self._diag_layer = mk(self._num_classes, "diag_layer")
+
+    def call(self, inputs, training=True, seed=None):
+        if inputs.dim() != 2:
+            raise ValueError("the Monte-Carlo heads take [batch, features] inputs")
+        locs, _ = self._compute_loc_param(inputs, training)
+        fac, diag_raw = self._scale_params(inputs)
+        samples = self._train_mc_samples if training else self._test_mc_samples
+        flags = (1 if self._share_samples_across_batch else 0) | 4  # sigmoid link; one diagonal draw per class (TF)
+        logits, probs, var = F.MCSoftmaxFA.apply(locs.float(), fac.float(), diag_raw.float(), None, 1.0, 1.0,
+                                                 self._mc_noise(inputs.shape[0], seed), samples, self._num_factors, flags,
+                                                 self._temperature, self._eps, self._compute_pred_variance)
+        if self._logits_only:
+            return logits
+        probs_lo = torch.clamp(probs, min=self._eps)
+        return (logits, torch.log(probs_lo), torch.clamp(probs_lo, self._eps, 1.0 - self._eps),
+                (var if self._compute_pred_variance else None))
+
+
 class HeteroscedasticSNGPLayer(MCSoftmaxDenseFA):
     """MC estimation of the softmax approximation to heteroscedastic SNGP predictions (hetsngp.py:25-245): the location
     parameter is the random-feature GP's output, and at evaluation the diagonal scale mixes in the SNGP marginal variance

@@ -7,11 +7,11 @@ edward2/jax/nn/heteroscedastic_lib.py.
 """
 from . import utils
 from .dense import DenseBatchEnsemble
-from .heteroscedastic import MCSoftmaxDenseFA
+from .heteroscedastic import MCSigmoidDenseFA, MCSoftmaxDenseFA
 from .module import Module
 from .normalization import Dense, SpectralNormalization
 from .random_feature import LaplaceRandomFeatureCovariance, RandomFeatureGaussianProcess, RandomFourierFeatures
 from .utils import make_sign_initializer, mean_field_logits
 
 __all__ = ["Module", "Dense", "DenseBatchEnsemble", "SpectralNormalization", "LaplaceRandomFeatureCovariance",
-           "RandomFeatureGaussianProcess", "RandomFourierFeatures", "MCSoftmaxDenseFA", "make_sign_initializer", "mean_field_logits", "utils"]
+           "RandomFeatureGaussianProcess", "RandomFourierFeatures", "MCSigmoidDenseFA", "MCSoftmaxDenseFA", "make_sign_initializer", "mean_field_logits", "utils"]

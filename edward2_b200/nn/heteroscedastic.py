@@ -77,3 +77,44 @@ class MCSoftmaxDenseFA(m.Module):
             return logits
         # jnp.clip(probs_mean, min=eps) (:317): no upper clip
         return logits, log_probs, torch.clamp(probs, min=self.eps)
+
+
+class MCSigmoidDenseFA(m.Module):
+    """`edward2.jax.nn.MCSigmoidDenseFA` (heteroscedastic_lib.py:338-594): the multi-label form — independent sigmoid
+    outputs, logits = inverse sigmoid of the Monte-Carlo mean probabilities."""
+    num_outputs: int
+    num_factors: int
+    temperature: float = 1.0
+    parameter_efficient: bool = False
+    train_mc_samples: int = 1000
+    test_mc_samples: int = 1000
+    share_samples_across_batch: bool = False
+    logits_only: bool = False
+    return_locs: bool = False
+    eps: float = 1e-7
+    tune_temperature: bool = False
+    temperature_lower_bound: Optional[float] = None
+    temperature_upper_bound: Optional[float] = None
+    latent_dim: Optional[int] = None
+
+    _noise = MCSoftmaxDenseFA._noise
+
+    def __call__(self, inputs, training=True, mc_noise=None):
+        if self.parameter_efficient or self.tune_temperature or self.latent_dim is not None or self.num_factors <= 0:
+            raise NotImplementedError("parameter_efficient / tune_temperature / latent_dim / num_factors == 0 are not built")
+        K, Fn = self.num_outputs, self.num_factors
+        loc = self.sub(Dense(K), "loc_layer")(inputs)
+        fac = self.sub(Dense(K * Fn), "scale_layer")(inputs)
+        diag_raw = self.sub(Dense(K), "diag_layer")(inputs)
+        samples = self.train_mc_samples if training else self.test_mc_samples
+        flags = (1 if self.share_samples_across_batch else 0) | 2 | 4  # JAX diagonal noise, sigmoid link
+        logits, probs, _ = F.MCSoftmaxFA.apply(loc.float(), fac.float(), diag_raw.float(), None, 1.0, 1.0,
+                                               self._noise(inputs, mc_noise), samples, Fn, flags, float(self.temperature),
+                                               float(self.eps), False)
+        probs_lo = torch.clamp(probs, min=self.eps)                      # :575
+        log_probs = torch.log(probs_lo)
+        if self.return_locs:
+            logits = loc
+        if self.logits_only:
+            return logits
+        return logits, log_probs, torch.clamp(probs_lo, self.eps, 1.0 - self.eps)  # :578: the returned probs carry both clips

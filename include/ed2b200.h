@@ -520,6 +520,8 @@ int ed2_flipout_fusable(int batch, int in_dim, int out_dim);
  * injected: [batch][S][P] fp32.  share_samples bit 0: every example reads row 0 (share_samples_across_batch); bit 1: ONE
  * diagonal draw per (example, sample), element 0 of the e block, shared by all classes — the JAX class
  * (edward2/jax/nn/heteroscedastic_lib.py:186-188: noise of shape [B, S, 1]); the TF class draws one per class.
+ * bit 2: SIGMOID link (MCSigmoidDenseFA, heteroscedastic_lib.py:338-594): probs = mean_s sigmoid(latent / T), logits =
+ * log(clip(probs, eps)) - log(1 - clip(probs, eps, 1 - eps)).
  * num_classes <= 64, num_factors <= 16.
  * The backward regenerates the samples: dloc, dfac, ddiag_raw from g = dL/dlogits (training form: no sngp_var). */
 int ed2_mc_softmax_fa_fwd(const float* loc, const float* fac, const float* diag_raw, const float* sngp_var, float w_het,

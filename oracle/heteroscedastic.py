@@ -82,3 +82,36 @@ def native_noise(seed, stream, batch, num_samples, num_factors, num_classes, sha
     first = 0 if share else row0
     flat = op.normal(seed, stream, (first + rows) * num_samples * P).reshape(-1, num_samples, P)[first:first + rows]
     return flat[:, :, :num_factors], flat[:, :, FP:FP + num_classes]
+
+
+# ---- sigmoid link: MCSigmoidDenseFA (edward2/jax/nn/heteroscedastic_lib.py:338-594; TF heteroscedastic.py, same recipe)
+def sample_sigmoids(loc, fac, diag, z, e, temperature=1.0):
+    loc = np.asarray(loc, dtype=np.float64)
+    B, K = loc.shape
+    V = np.asarray(fac, dtype=np.float64).reshape(B, K, -1)
+    z = np.broadcast_to(np.asarray(z, dtype=np.float64), (B,) + tuple(np.shape(z)[1:]))
+    e = np.broadcast_to(np.asarray(e, dtype=np.float64), (B,) + tuple(np.shape(e)[1:]))
+    lat = (loc[:, None, :] + np.einsum("ijk,iak->iaj", V, z) + e * diag[:, None, :]) / temperature
+    return 1.0 / (1.0 + np.exp(-lat)), z, e
+
+
+def mc_sigmoid_fa(loc, fac, diag_raw, z, e, temperature=1.0, eps=1e-7):
+    """Returns (logits, log_probs, probs_mean): probs = mean_s sigmoid(latent / T) clipped from below at eps (:575-576);
+    logits = inverse sigmoid with the second clip to [eps, 1 - eps] (:578-580)."""
+    p, _, _ = sample_sigmoids(loc, fac, effective_diag(diag_raw), z, e, temperature)
+    pm = np.clip(p.mean(1), eps, None)
+    log_probs = np.log(pm)
+    return log_probs - np.log(1.0 - np.clip(pm, eps, 1.0 - eps)), log_probs, pm
+
+
+def mc_sigmoid_fa_bwd(loc, fac, diag_raw, z, e, g, temperature=1.0, eps=1e-7):
+    """Closed-form gradients of the inverse-sigmoid logits w.r.t. loc, fac, diag_raw (g = dL/dlogits)."""
+    diag = effective_diag(diag_raw)
+    p, zb, eb = sample_sigmoids(loc, fac, diag, z, e, temperature)
+    S = p.shape[1]
+    pm = p.mean(1)
+    d = np.where(pm > eps, 1.0 / pm, 0.0) + np.where((pm > eps) & (pm < 1.0 - eps), 1.0 / (1.0 - pm), 0.0)
+    u = np.asarray(g, dtype=np.float64) * d / S
+    dlat = u[:, None, :] * p * (1.0 - p) / temperature
+    dV = np.einsum("iaj,iak->ijk", dlat, zb)
+    return dict(dloc=dlat.sum(1), dfac=dV.reshape(dV.shape[0], -1), ddiag_raw=(dlat * eb).sum(1) * od.sigmoid(diag_raw))

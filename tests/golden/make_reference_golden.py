@@ -175,6 +175,35 @@ def main():
             out[f"{tag}_{name}_kernel"] = v["params"][name]["kernel"]
             out[f"{tag}_{name}_bias"] = v["params"][name]["bias"]
 
+    # ---- §8f-2 MCSigmoidDenseFA.__call__ (heteroscedastic_lib.py:338-594)
+    drawn = []
+
+    def recording_normal2(key, shape=(), dtype=None, _d=drawn):
+        v = real_normal(key, shape, dtype)
+        _d.append(np.array(v))
+        return v
+
+    jr.normal = jax.random.normal = recording_normal2
+    try:
+        B, Din, K, Fn, S = 8, 6, 4, 2, 48
+        layer = het.MCSigmoidDenseFA(num_outputs=K, num_factors=Fn, temperature=0.8, train_mc_samples=S, test_mc_samples=S)
+        x = rng.standard_normal((B, Din))
+        rngs = {"params": jax.random.PRNGKey(9), "diag_noise_samples": jax.random.PRNGKey(10),
+                "standard_norm_noise_samples": jax.random.PRNGKey(11)}
+        v = layer.init(rngs, x)
+        for name in ("loc_layer", "scale_layer", "diag_layer"):
+            v["params"][name]["bias"] = rng.standard_normal(v["params"][name]["bias"].shape) * 0.2
+        del drawn[:]
+        logits, log_probs, probs = layer.apply(v, x, training=True, rngs=rngs)
+    finally:
+        jr.normal = jax.random.normal = real_normal
+    out.update(hsig_x=x, hsig_logits=logits, hsig_log_probs=log_probs, hsig_probs=probs, hsig_temperature=np.float64(0.8),
+               hsig_diag_noise=[d for d in drawn if d.ndim == 3 and d.shape[-1] == 1][-1],
+               hsig_factor_noise=[d for d in drawn if d.ndim == 3 and d.shape[-1] == Fn][-1])
+    for name in ("loc_layer", "scale_layer", "diag_layer"):
+        out[f"hsig_{name}_kernel"] = v["params"][name]["kernel"]
+        out[f"hsig_{name}_bias"] = v["params"][name]["bias"]
+
     np.savez_compressed(OUT, **{k: np.asarray(a) for k, a in out.items()})
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")
 

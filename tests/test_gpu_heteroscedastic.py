@@ -138,3 +138,45 @@ def test_heteroscedastic_sngp_layer(cuda):
     assert (sv > 0).all()
     layer.reset_covariance_matrix()
     assert float(layer.sngp_layer._gp_cov_layer.precision_matrix.abs().sum()) >= 0
+
+
+@pytest.mark.parametrize("inject", [True, False])
+def test_mc_sigmoid_fa_op_and_layer(cuda, inject):
+    """Sigmoid link (MCSigmoidDenseFA): forward and the gradients of the inverse-sigmoid logits against the oracle; the TF
+    layer class end to end (one diagonal draw per class)."""
+    import edward2_b200 as ed
+    from edward2_b200 import functional as F
+    from edward2_b200.layers import heteroscedastic as lh
+
+    B, S, K, Fn, T = 21, 96, 6, 3, 1.3
+    rng = np.random.default_rng(17)
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)  # noqa: E731
+    loc, fac, draw = f32(rng.standard_normal((B, K))), f32(rng.standard_normal((B, K * Fn)) * 0.5), f32(rng.standard_normal((B, K)))
+    FP, KP = 8, 8
+    if inject:
+        buf = rng.standard_normal((B, S, FP + KP)).astype(np.float32)
+        z, e = buf[:, :, :Fn].astype(np.float64), buf[:, :, FP:FP + K].astype(np.float64)
+        noise = F.Randomness(torch.tensor(buf, device=cuda))
+    else:
+        z, e = oh.native_noise(4, 7, B, S, Fn, K)
+        noise = F.Randomness(seed=4, stream=7)
+    lt, ft, dt_ = _f32(loc, cuda, True), _f32(fac, cuda, True), _f32(draw, cuda, True)
+    logits, pm, _ = F.MCSoftmaxFA.apply(lt, ft, dt_, None, 1.0, 1.0, noise, S, Fn, 4, T, 1e-7, False)
+    l_ref, _, pm_ref = oh.mc_sigmoid_fa(loc, fac, draw, z, e, T)
+    assert rel_err(to_np(pm), pm_ref) < TOL and rel_err(to_np(logits), l_ref) < TOL
+    g = rng.standard_normal((B, K))
+    logits.backward(_f32(g, cuda))
+    gr = oh.mc_sigmoid_fa_bwd(loc, fac, draw, z, e, g, T)
+    assert rel_err(to_np(lt.grad), gr["dloc"]) < 2e-5
+    assert rel_err(to_np(ft.grad), gr["dfac"]) < 2e-5
+    assert rel_err(to_np(dt_.grad), gr["ddiag_raw"]) < 2e-5
+    if not inject:
+        layer = ed.layers.MCSigmoidDenseFA(2, 3, train_mc_samples=64, seed=5)  # two outputs: allowed for the sigmoid head
+        x = torch.randn(10, 12, device=cuda)
+        lg, lp, pr, var = layer(x, training=True)
+        assert tuple(lg.shape) == (10, 2) and var is None and float(pr.min()) > 0 and float(pr.max()) < 1
+        x64 = to_np(x)
+        lin = lambda l: x64 @ to_np(l.kernel) + to_np(l.bias)  # noqa: E731
+        zz, ee = oh.native_noise(layer.seed, lh.S_MC, 10, 64, 3, 2)
+        l2, lp2, p2 = oh.mc_sigmoid_fa(lin(layer._loc_layer), lin(layer._scale_layer), lin(layer._diag_layer), zz, ee, 1.0)
+        assert rel_err(to_np(lg), l2) < 1e-4 and rel_err(to_np(lp), lp2) < 1e-4 and rel_err(to_np(pr), p2) < 1e-4

@@ -167,3 +167,24 @@ def test_mc_softmax_dense_fa_vs_reference(cuda, ref, tag):
     assert torch.equal(a, b) and not torch.equal(a, c)
     a.sum().backward()
     assert all(v["params"][nm]["kernel"].grad is not None for nm in v["params"])
+
+
+def test_mc_sigmoid_dense_fa_vs_reference(cuda, ref):
+    """`edward2_b200.nn.MCSigmoidDenseFA` against the reference's own MCSigmoidDenseFA outputs
+    (edward2/jax/nn/heteroscedastic_lib.py:338-594) with its recorded noise injected."""
+    ed = _ed()
+    x, z, n = ref["hsig_x"], ref["hsig_factor_noise"], ref["hsig_diag_noise"]
+    rows, S, Fn = z.shape
+    K = ref["hsig_loc_layer_bias"].shape[0]
+    FP, KP = (Fn + 7) // 8 * 8, (K + 7) // 8 * 8
+    buf = np.zeros((rows, S, FP + KP), dtype=np.float32)
+    buf[:, :, :Fn] = z
+    buf[:, :, FP] = n[:, :, 0]
+    layer = ed.nn.MCSigmoidDenseFA(num_outputs=K, num_factors=Fn, temperature=float(ref["hsig_temperature"]),
+                                   train_mc_samples=S, test_mc_samples=S)
+    variables = {"params": {name: {"kernel": _t(ref[f"hsig_{name}_kernel"], cuda, True), "bias": _t(ref[f"hsig_{name}_bias"], cuda, True)}
+                            for name in ("loc_layer", "scale_layer", "diag_layer")}}
+    logits, log_probs, probs = layer.apply(variables, _t(x, cuda), training=True, mc_noise=torch.tensor(buf, device=cuda))
+    assert rel_err(to_np(probs), ref["hsig_probs"]) < FP32
+    assert rel_err(to_np(log_probs), ref["hsig_log_probs"]) < FP32
+    assert rel_err(to_np(logits), ref["hsig_logits"]) < FP32

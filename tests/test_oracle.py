@@ -654,3 +654,32 @@ def test_reference_mc_softmax_dense_fa(ref, tag):
     _close(probs, ref[f"{tag}_probs"])
     _close(logits, ref[f"{tag}_logits"])
     _close(logits, ref[f"{tag}_log_probs"])
+
+
+def test_reference_mc_sigmoid_dense_fa(ref):
+    """jax/nn/heteroscedastic_lib.py:338-594 (MCSigmoidDenseFA) run as shipped with its draws recorded: sigmoid link, clip
+    from below, inverse-sigmoid logits with the second clip; plus the closed-form gradient against float64 autograd."""
+    from oracle import heteroscedastic as oh
+
+    x = ref["hsig_x"]
+    lin = lambda n: x @ ref[f"hsig_{n}_kernel"] + ref[f"hsig_{n}_bias"]  # noqa: E731
+    loc, fac, draw = lin("loc_layer"), lin("scale_layer"), lin("diag_layer")
+    K = loc.shape[1]
+    z = ref["hsig_factor_noise"]
+    e = np.broadcast_to(ref["hsig_diag_noise"], ref["hsig_diag_noise"].shape[:2] + (K,))
+    T = float(ref["hsig_temperature"])
+    logits, log_probs, probs = oh.mc_sigmoid_fa(loc, fac, draw, z, e, T, 1e-7)
+    _close(probs, ref["hsig_probs"])
+    _close(log_probs, ref["hsig_log_probs"])
+    _close(logits, ref["hsig_logits"])
+    lt, ft, dt_ = (torch.tensor(t, requires_grad=True) for t in (loc, fac, draw))
+    B, Fn = loc.shape[0], z.shape[-1]
+    diag = torch.nn.functional.softplus(dt_) + 1e-3
+    lat = lt[:, None, :] + torch.einsum("ijk,iak->iaj", ft.reshape(B, K, Fn), torch.tensor(z)) + torch.tensor(e.copy()) * diag[:, None, :]
+    pm = torch.sigmoid(lat / T).mean(1)
+    lg = torch.log(torch.clamp(pm, min=1e-7)) - torch.log(1 - torch.clamp(pm, 1e-7, 1 - 1e-7))
+    g = np.random.default_rng(0).standard_normal(loc.shape)
+    (lg * torch.tensor(g)).sum().backward()
+    got = oh.mc_sigmoid_fa_bwd(loc, fac, draw, z, e, g, T)
+    for a, b_ in ((got["dloc"], lt.grad), (got["dfac"], ft.grad), (got["ddiag_raw"], dt_.grad)):
+        np.testing.assert_allclose(a, b_.numpy(), rtol=1e-9, atol=1e-12)
