@@ -782,6 +782,19 @@ int ed2_lstm_pointwise_bwd(const void* z, int dtype, long long z_ld, const float
   return k_lstm_pointwise_bwd(z, dtype, z_ld, c_prev, c, dh, dh_ld, dc, batch, units, dz, dz_ld, dc_prev, dbias, S(stream));
 }
 
+int ed2_lstm_gates_fwd(const void* z, const void* z2, int dtype, long long z_ld, long long z2_ld, const float* c_prev,
+                       int batch, int units, float* c, void* h, long long h_ld, void* stream) {
+  ED2_TRY(check_dt(dtype));
+  return k_lstm_pointwise_fwd(z, dtype, z_ld, c_prev, batch, units, c, h, h_ld, S(stream), z2, z2_ld);
+}
+int ed2_lstm_gates_bwd(const void* z, const void* z2, int dtype, long long z_ld, long long z2_ld, const float* c_prev,
+                       const float* c, const void* dh, long long dh_ld, const float* dc, int batch, int units, void* dz,
+                       long long dz_ld, float* dc_prev, void* stream) {
+  ED2_TRY(check_dt(dtype));
+  return k_lstm_pointwise_bwd(z, dtype, z_ld, c_prev, c, dh, dh_ld, dc, batch, units, dz, dz_ld, dc_prev, nullptr, S(stream), z2,
+                              z2_ld);
+}
+
 // ------------------------------------------------------------------------------------------ Conv2D support
 namespace {
 ConvArgs conv_args(const ed2_conv_geometry* g) {

@@ -200,9 +200,9 @@ int k_mc_softmax_bwd(const float* g, const float* probs_mean, const float* loc, 
 
 // ---- pointwise part of the Bayesian LSTM cells (recurrent.cu; recurrent.py:163-184, gate order i | f | c | o)
 int k_lstm_pointwise_fwd(const void* z, int dt, long long z_ld, const float* c_prev, int B, int H, float* c, void* h,
-                         long long h_ld, cudaStream_t s);
+                         long long h_ld, cudaStream_t s, const void* z2 = nullptr, long long z2_ld = 0);
 int k_lstm_pointwise_bwd(const void* z, int dt, long long z_ld, const float* c_prev, const float* c, const void* dh,
                          long long dh_ld, const float* dc, int B, int H, void* dz, long long dz_ld, float* dc_prev,
-                         float* dbias, cudaStream_t s);
+                         float* dbias, cudaStream_t s, const void* z2 = nullptr, long long z2_ld = 0);
 
 }  // namespace ed2

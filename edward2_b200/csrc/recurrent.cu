@@ -27,14 +27,19 @@ __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); 
 
 __global__ void __launch_bounds__(kBlock) lstm_pointwise_fwd_kernel(const void* __restrict__ z, int dt, long long z_ld,
                                                                    const float* __restrict__ c_prev, int B, int H,
-                                                                   float* __restrict__ c, void* __restrict__ h, long long h_ld) {
+                                                                   float* __restrict__ c, void* __restrict__ h, long long h_ld,
+                                                                   const void* __restrict__ z2, long long z2_ld) {
   const long long total = static_cast<long long>(B) * H;
   for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < total; idx += (long long)gridDim.x * kBlock) {
     const long long b = idx / H;
     const int j = static_cast<int>(idx - b * H);
-    const long long zr = b * z_ld;
-    const float i = sigm(ldz(z, dt, zr + j)), f = sigm(ldz(z, dt, zr + H + j));
-    const float g = tanhf(ldz(z, dt, zr + 2 * H + j)), o = sigm(ldz(z, dt, zr + 3 * H + j));
+    const long long zr = b * z_ld, zr2 = b * z2_ld;
+    auto pre = [&](int gate) {  // pre-activation of one gate: z (+ z2: the recurrent branch of the Flipout / rank-1 cells)
+      const float v = ldz(z, dt, zr + gate * H + j);
+      return z2 != nullptr ? v + ldz(z2, dt, zr2 + gate * H + j) : v;
+    };
+    const float i = sigm(pre(0)), f = sigm(pre(1));
+    const float g = tanhf(pre(2)), o = sigm(pre(3));
     const float cn = fmaf(f, c_prev[idx], i * g);
     c[idx] = cn;
     stz(h, dt, b * h_ld + j, o * tanhf(cn));
@@ -48,14 +53,19 @@ __global__ void __launch_bounds__(kBlock) lstm_pointwise_bwd_kernel(const void* 
                                                                    const void* __restrict__ dh, long long dh_ld,
                                                                    const float* __restrict__ dc, int B, int H,
                                                                    void* __restrict__ dz, long long dz_ld,
-                                                                   float* __restrict__ dc_prev, float* __restrict__ dbias) {
+                                                                   float* __restrict__ dc_prev, float* __restrict__ dbias,
+                                                                   const void* __restrict__ z2, long long z2_ld) {
   const long long total = static_cast<long long>(B) * H;
   for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < total; idx += (long long)gridDim.x * kBlock) {
     const long long b = idx / H;
     const int j = static_cast<int>(idx - b * H);
-    const long long zr = b * z_ld;
-    const float i = sigm(ldz(z, dt, zr + j)), f = sigm(ldz(z, dt, zr + H + j));
-    const float g = tanhf(ldz(z, dt, zr + 2 * H + j)), o = sigm(ldz(z, dt, zr + 3 * H + j));
+    const long long zr = b * z_ld, zr2 = b * z2_ld;
+    auto pre = [&](int gate) {
+      const float v = ldz(z, dt, zr + gate * H + j);
+      return z2 != nullptr ? v + ldz(z2, dt, zr2 + gate * H + j) : v;
+    };
+    const float i = sigm(pre(0)), f = sigm(pre(1));
+    const float g = tanhf(pre(2)), o = sigm(pre(3));
     const float tc = tanhf(c[idx]);
     const float gh = dh != nullptr ? ldz(dh, dt, b * dh_ld + j) : 0.f;
     const float dct = (dc != nullptr ? dc[idx] : 0.f) + gh * o * (1.f - tc * tc);
@@ -81,20 +91,20 @@ int grid_for(long long work) {
 }  // namespace
 
 int k_lstm_pointwise_fwd(const void* z, int dt, long long z_ld, const float* c_prev, int B, int H, float* c, void* h,
-                         long long h_ld, cudaStream_t s) {
+                         long long h_ld, cudaStream_t s, const void* z2, long long z2_ld) {
   if (B <= 0 || H <= 0) return set_error(ED2_ERR_BAD_SHAPE, "lstm_pointwise: empty");
-  lstm_pointwise_fwd_kernel<<<grid_for(static_cast<long long>(B) * H), kBlock, 0, s>>>(z, dt, z_ld, c_prev, B, H, c, h, h_ld);
+  lstm_pointwise_fwd_kernel<<<grid_for(static_cast<long long>(B) * H), kBlock, 0, s>>>(z, dt, z_ld, c_prev, B, H, c, h, h_ld, z2, z2_ld);
   count_launch();
   return check_launch("lstm_pointwise_fwd");
 }
 
 int k_lstm_pointwise_bwd(const void* z, int dt, long long z_ld, const float* c_prev, const float* c, const void* dh,
                          long long dh_ld, const float* dc, int B, int H, void* dz, long long dz_ld, float* dc_prev,
-                         float* dbias, cudaStream_t s) {
+                         float* dbias, cudaStream_t s, const void* z2, long long z2_ld) {
   if (B <= 0 || H <= 0) return set_error(ED2_ERR_BAD_SHAPE, "lstm_pointwise: empty");
   if (dbias != nullptr) cudaMemsetAsync(dbias, 0, sizeof(float) * 4 * static_cast<size_t>(H), s);
   lstm_pointwise_bwd_kernel<<<grid_for(static_cast<long long>(B) * H), kBlock, 0, s>>>(z, dt, z_ld, c_prev, c, dh, dh_ld, dc, B,
-                                                                                        H, dz, dz_ld, dc_prev, dbias);
+                                                                                        H, dz, dz_ld, dc_prev, dbias, z2, z2_ld);
   count_launch();
   return check_launch("lstm_pointwise_bwd");
 }

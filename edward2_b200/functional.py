@@ -1177,6 +1177,49 @@ class LSTMStep(torch.autograd.Function):
                 zero(kw), zero(ku), None, None, None)
 
 
+class LSTMGates(torch.autograd.Function):
+    """(h, c) from the gate pre-activations z (+ z2) [B, 4H] and c_prev (include/ed2b200.h: ed2_lstm_gates_fwd / _bwd).
+    The input and the recurrent branch of LSTMCellFlipout / LSTMCellRank1 are separate stochastic-weight products, so
+    their pre-activations arrive as two tensors; the backward returns the same dz for both."""
+
+    @staticmethod
+    def forward(ctx, z, z2, c_prev, dtype):
+        lib = _lib.load()
+        B, H4 = z.shape
+        H = H4 // 4
+        dev = z.device
+        zc = as_compute(z, dtype)
+        z2c = as_compute(z2, dtype) if z2 is not None else None
+        c32 = c_prev.to(torch.float32).contiguous()
+        c = torch.empty(B, H, dtype=torch.float32, device=dev)
+        h = _new(B, H, dtype, dev)
+        _lib.check(lib.ed2_lstm_gates_fwd(zc.data_ptr(), _p(z2c), _compute_dt(dtype), _lib.ld(zc), _ldn(z2c), c32.data_ptr(), B, H,
+                                          c.data_ptr(), h.data_ptr(), _lib.ld(h), _lib.stream_ptr()), "ed2_lstm_gates_fwd")
+        ctx.save_for_backward(zc, c32, c, *([z2c] if z2c is not None else []))
+        ctx.meta = (dtype, z.dtype, None if z2 is None else z2.dtype, c_prev.dtype)
+        ctx.set_materialize_grads(False)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        lib = _lib.load()
+        zc, c_prev, c = ctx.saved_tensors[:3]
+        z2c = ctx.saved_tensors[3] if len(ctx.saved_tensors) > 3 else None
+        dtype, z_dt, z2_dt, c_dt = ctx.meta
+        B, H = c.shape
+        dev = zc.device
+        dhc = as_compute(dh, dtype) if dh is not None else None
+        dc32 = dc.to(torch.float32).contiguous() if dc is not None else None
+        dz = _new(B, 4 * H, dtype, dev)
+        dc_prev = torch.empty(B, H, dtype=torch.float32, device=dev)
+        _lib.check(lib.ed2_lstm_gates_bwd(zc.data_ptr(), _p(z2c), _compute_dt(dtype), _lib.ld(zc), _ldn(z2c), c_prev.data_ptr(),
+                                          c.data_ptr(), _p(dhc), _ldn(dhc), _p(dc32), B, H, dz.data_ptr(), _lib.ld(dz),
+                                          dc_prev.data_ptr(), _lib.stream_ptr()), "ed2_lstm_gates_bwd")
+        g1 = dz if dz.dtype == z_dt else dz.to(z_dt)
+        g2 = None if z2c is None else (dz if dz.dtype == z2_dt else dz.to(z2_dt))
+        return g1, g2, (dc_prev if c_dt == torch.float32 else dc_prev.to(c_dt)), None
+
+
 # ------------------------------------------------------------------------------------------------- KL regulariser
 class NormalKL(torch.autograd.Function):
     """scale * sum KL(N(mu, softplus(rho)+1e-7) || N(m, s)) as a 0-dim fp32 tensor (regularizers.py:175-186)."""

@@ -543,6 +543,14 @@ int ed2_mc_softmax_fa_bwd(const float* g, const float* probs_mean, const float* 
  * `dtype`. */
 int ed2_lstm_pointwise_fwd(const void* z, int dtype, long long z_ld, const float* c_prev, int batch, int units, float* c,
                            void* h, long long h_ld, void* stream);
+/* The same gates on z + z2: the input and the recurrent branch kept as two pre-activation tensors — LSTMCellFlipout
+ * (recurrent.py:185-358: each branch is a Flipout product with its own sign tensors) and LSTMCellRank1 (:360-830: each
+ * branch a rank-1 product with its own alpha / gamma).  dz is the gradient of both. */
+int ed2_lstm_gates_fwd(const void* z, const void* z2, int dtype, long long z_ld, long long z2_ld, const float* c_prev,
+                       int batch, int units, float* c, void* h, long long h_ld, void* stream);
+int ed2_lstm_gates_bwd(const void* z, const void* z2, int dtype, long long z_ld, long long z2_ld, const float* c_prev,
+                       const float* c, const void* dh, long long dh_ld, const float* dc, int batch, int units, void* dz,
+                       long long dz_ld, float* dc_prev, void* stream);
 int ed2_lstm_pointwise_bwd(const void* z, int dtype, long long z_ld, const float* c_prev, const float* c, const void* dh,
                            long long dh_ld, const float* dc, int batch, int units, void* dz, long long dz_ld,
                            float* dc_prev, float* dbias, void* stream);

@@ -57,3 +57,46 @@ def lstm_sequence_bwd(caches, W, U, dhs, dc_last=None):
 
 def reparam_kernel(mu, rho, eps):
     return np.asarray(mu, dtype=np.float64) + od.stddev(rho) * np.asarray(eps, dtype=np.float64)
+
+
+# ---- two-branch cells: LSTMCellFlipout (recurrent.py:185-358) and LSTMCellRank1 (:360-830) -----------------------------
+def gates(z, c_prev):
+    """(h, c, cache) from the summed pre-activations z [B, 4H] (gate order i | f | c | o)."""
+    H = c_prev.shape[1]
+    i, f, g, o = sigmoid(z[:, :H]), sigmoid(z[:, H:2 * H]), np.tanh(z[:, 2 * H:3 * H]), sigmoid(z[:, 3 * H:])
+    c = f * c_prev + i * g
+    return o * np.tanh(c), c, (i, f, g, o)
+
+
+def gates_bwd(c_prev, c, cache, dh, dc):
+    """(dz, dc_prev) of `gates`."""
+    i, f, g, o = cache
+    tc = np.tanh(c)
+    dct = dc + dh * o * (1 - tc * tc)
+    dz = np.concatenate([dct * g * i * (1 - i), dct * c_prev * f * (1 - f), dct * i * (1 - g * g), dh * tc * o * (1 - o)], 1)
+    return dz, dct * f
+
+
+def two_branch_sequence(xs, h0, c0, branch_x, branch_h, bwd_x, bwd_h, dhs):
+    """Unrolled cell whose pre-activation is branch_x(x) + branch_h(h): forward over xs [T, B, I] and backpropagation
+    through time of sum_t <dhs[t], h_t>.  branch_* (inp) -> z;  bwd_* (inp, dz) -> dict with 'dx' and parameter gradients
+    (summed over the steps here).  Returns (hs, dxs, grads_x, grads_h)."""
+    h, c, hs, tape = h0, c0, [], []
+    for x in xs:
+        z = branch_x(x) + branch_h(h)
+        h_new, c_new, cache = gates(z, c)
+        tape.append((x, h, c, c_new, cache))
+        h, c = h_new, c_new
+        hs.append(h)
+    dh_next, dc_next = np.zeros_like(h0), np.zeros_like(c0)
+    dxs, gx, gh = [None] * len(xs), {}, {}
+    for t in reversed(range(len(xs))):
+        x, h_prev, c_prev, c_new, cache = tape[t]
+        dz, dc_next = gates_bwd(c_prev, c_new, cache, dhs[t] + dh_next, dc_next)
+        bx, bh = bwd_x(x, dz), bwd_h(h_prev, dz)
+        dxs[t], dh_next = bx.pop("dx"), bh.pop("dx")
+        for acc, b in ((gx, bx), (gh, bh)):
+            for k, v in b.items():
+                if v is not None:
+                    acc[k] = acc.get(k, 0.0) + v
+    return np.stack(hs), np.stack(dxs), gx, gh

@@ -633,6 +633,15 @@ def test_recurrent_oracle_bptt_matches_autograd():
     for key, ref in (("dxs", t["xs"].grad), ("dh0", t["h0"].grad), ("dc0", t["c0"].grad), ("dW", t["W"].grad),
                      ("dU", t["U"].grad), ("db", t["b"].grad)):
         np.testing.assert_allclose(g[key], ref.numpy(), rtol=1e-9, atol=1e-12)
+    # the two-branch driver (LSTMCellFlipout / LSTMCellRank1 oracles) with plain linear branches reproduces the same BPTT
+    bx, bh = (lambda x: x @ W + b), (lambda h: h @ U)
+    gx_ = lambda x, dz: dict(dx=dz @ W.T, dW=x.T @ dz, db=dz.sum(0))  # noqa: E731
+    gh_ = lambda h, dz: dict(dx=dz @ U.T, dU=h.T @ dz)  # noqa: E731
+    hs2, dxs2, gx2, gh2 = orc.two_branch_sequence(xs, h0, c0, bx, bh, gx_, gh_, dhs)
+    g0 = orc.lstm_sequence_bwd(caches, W, U, dhs)
+    np.testing.assert_allclose(hs2, hs, rtol=1e-12)
+    for a, b_ in ((dxs2, g0["dxs"]), (gx2["dW"], g0["dW"]), (gh2["dU"], g0["dU"]), (gx2["db"], g0["db"])):
+        np.testing.assert_allclose(a, b_, rtol=1e-10, atol=1e-12)
 
 
 @pytest.mark.parametrize("tag", ["het", "het_shared"])
