@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libed2b200.so")
 
-SOURCES = ["status.cu", "gemm.cu", "gemm_f32.cu", "elementwise.cu", "sngp.cu", "peer.cu", "conv.cu", "mcsoftmax.cu", "recurrent.cu", "api.cu"]
+SOURCES = ["status.cu", "gemm.cu", "gemm_f32.cu", "elementwise.cu", "sngp.cu", "peer.cu", "conv.cu", "mcsoftmax.cu", "recurrent.cu", "inverse.cu", "api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

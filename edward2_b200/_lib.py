@@ -265,6 +265,8 @@ SIGNATURES = {
     "ed2_lstm_pointwise_bwd": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _ll, _vp, _vp, _vp]),
     "ed2_lstm_gates_fwd": (_i, [_vp, _vp, _i, _ll, _ll, _vp, _i, _i, _vp, _vp, _ll, _vp]),
     "ed2_lstm_gates_bwd": (_i, [_vp, _vp, _i, _ll, _ll, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _ll, _vp, _vp]),
+    "ed2_spd_inverse_workspace_floats": (_ll, [_i]),
+    "ed2_spd_inverse": (_i, [_vp, _i, _vp, _vp]),
     "ed2_conv_out_size": (_i, [C.POINTER(ConvGeometry), C.POINTER(_i), C.POINTER(_i)]),
     "ed2_im2col": (_i, [C.POINTER(ConvGeometry), _vp, _i, _vp, _ll, _vp]),
     "ed2_col2im": (_i, [C.POINTER(ConvGeometry), _vp, _i, _ll, _vp, _i, _vp]),

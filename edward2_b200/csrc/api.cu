@@ -751,6 +751,12 @@ int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream) {
   return ED2_OK;
 }
 
+long long ed2_spd_inverse_workspace_floats(int n) { return k_spd_inverse_workspace_floats(n); }
+int ed2_spd_inverse(float* a, int n, float* workspace, void* stream) {
+  if (a == nullptr || workspace == nullptr) return set_error(ED2_ERR_BAD_ARG, "spd_inverse: null pointer");
+  return k_spd_inverse(a, n, workspace, S(stream));
+}
+
 // ------------------------------------------------------------------------------------------ heteroscedastic heads
 int ed2_mc_softmax_fa_fwd(const float* loc, const float* fac, const float* diag_raw, const float* sngp_var, float w_het,
                           float w_sngp, ed2_noise noise, int batch, int num_samples, int num_classes, int num_factors,

@@ -205,4 +205,8 @@ int k_lstm_pointwise_bwd(const void* z, int dt, long long z_ld, const float* c_p
                          long long dh_ld, const float* dc, int B, int H, void* dz, long long dz_ld, float* dc_prev,
                          float* dbias, cudaStream_t s, const void* z2 = nullptr, long long z2_ld = 0);
 
+// ---- SPD inverse without a library call (inverse.cu): in-place block Gauss-Jordan, fp32; ws >= workspace_floats(n)
+long long k_spd_inverse_workspace_floats(int n);
+int k_spd_inverse(float* a, int n, float* ws, cudaStream_t s);
+
 }  // namespace ed2

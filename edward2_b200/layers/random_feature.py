@@ -119,14 +119,16 @@ class LaplaceRandomFeatureCovariance(Layer):
         self.precision_matrix.zero_()
 
     def update_feature_covariance_matrix(self):
-        """random_feature.py:435-459.  The D^3 inverse is a library call (torch.linalg.inv), outside the measured
-        path."""
+        """random_feature.py:435-459: Sigma = (ridge I + P)^-1, computed on the GPU by the library's own block Gauss-Jordan
+        kernel chain (include/ed2b200.h: ed2_spd_inverse; no cuSOLVER / torch.linalg call).  One-off per evaluation phase,
+        outside the per-step figure."""
         self._sync_flag()
         if self._needs_inverse:
             self.synchronize_precision()
             a = self.precision_matrix.clone()
             a.diagonal().add_(self.ridge_penalty)
-            self.covariance_matrix.copy_(torch.linalg.inv(a))
+            sigma, _status = ops.spd_inverse(a)
+            self.covariance_matrix.copy_(sigma)
         return self.covariance_matrix
 
     def _covariance_lp(self):

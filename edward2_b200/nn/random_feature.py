@@ -126,11 +126,10 @@ class LaplaceRandomFeatureCovariance(m.Module):
 
     def compute_predictive_covariance(self, gp_features, precision_matrix, diagonal_only, dtype=torch.float32):
         """ridge * Φ P^-1 Φᵀ (:393-404).  The reference factorises P by Cholesky on every call; here P^-1 comes from
-        a library Cholesky inverse (outside the measured path) and the contraction with Φ is the
-        fused GEMM (row-sum epilogue for the diagonal)."""
+        the library's own on-GPU block Gauss-Jordan inverse (ed2_spd_inverse) and the contraction with
+        Φ is the fused GEMM (row-sum epilogue for the diagonal)."""
         p = precision_matrix.value if hasattr(precision_matrix, "value") else precision_matrix
-        chol = torch.linalg.cholesky(p.double())
-        sigma = torch.cholesky_inverse(chol).to(torch.float32).contiguous()
+        sigma, _status = ops.spd_inverse(p.detach().to(torch.float32))
         phi = F.as_compute(gp_features, dtype)
         sig = sigma if dtype == torch.float32 else ops.cast(sigma, dtype)
         if diagonal_only:

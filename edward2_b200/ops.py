@@ -266,3 +266,17 @@ def rff_fwd_split(x: torch.Tensor, wt_split: torch.Tensor, bias: torch.Tensor, s
                                scale, B, Kp, D, phi.data_ptr(), _lib.ld(phi), _lib.dt_of(phi), _lib.ptr(pre),
                                0 if pre is None else _lib.ld(pre), 1, _lib.stream_ptr()), "ed2_rff_fwd[split]")
     return phi, pre
+
+
+def spd_inverse(a: torch.Tensor):
+    """Inverse of a symmetric positive definite fp32 matrix on the GPU without a library call (ed2_spd_inverse: block
+    Gauss-Jordan).  Returns (inverse, status): a new [n, n] tensor and a one-element int32 device tensor that is
+    non-zero when a pivot was not positive (the input was not positive definite).  Reading the status synchronises, so
+    it is left to the caller."""
+    lib = _lib.load()
+    n = a.shape[0]
+    assert a.dim() == 2 and a.shape[1] == n and a.dtype == torch.float32 and a.is_cuda
+    out = a.contiguous().clone()
+    ws = torch.empty(int(lib.ed2_spd_inverse_workspace_floats(n)), dtype=torch.float32, device=a.device)
+    _lib.check(lib.ed2_spd_inverse(out.data_ptr(), n, ws.data_ptr(), _lib.stream_ptr()), "ed2_spd_inverse")
+    return out, ws[-4:].view(torch.int32)[0:1]

@@ -508,6 +508,14 @@ int ed2_flipout_fused_bwd(const ed2_flipout_fused_bwd_args* a, void* stream);
 /* 1 when the fused calls accept this shape (batch > 128, batch, in_dim and out_dim multiples of 8) */
 int ed2_flipout_fusable(int batch, int in_dim, int out_dim);
 
+/* Covariance of the Laplace approximation: a <- a^-1 for the symmetric positive definite a = ridge I + precision
+ * (edward2/tensorflow/layers/random_feature.py:447-459 tf.linalg.inv; edward2/jax/nn/random_feature.py:393-404 Cholesky +
+ * triangular solves), in place, fp32, no library call: block Gauss-Jordan with 64-wide pivot blocks (each pivot block a
+ * Schur complement of an SPD matrix: no pivoting), three fp32 GEMMs per block step, 2 n^3 FLOP.  workspace: at least
+ * ed2_spd_inverse_workspace_floats(n) floats; its last word is a status flag (non-zero: a pivot was not positive). */
+long long ed2_spd_inverse_workspace_floats(int n);
+int ed2_spd_inverse(float* a, int n, float* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Heteroscedastic heads: MCSoftmaxDenseFA (edward2/tensorflow/layers/heteroscedastic.py:508, Monte-Carlo machinery
  * :178-250, factor-analysis noise :749-785) and HeteroscedasticSNGPLayer (edward2/tensorflow/layers/hetsngp.py:25,
