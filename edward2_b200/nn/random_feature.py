@@ -181,3 +181,85 @@ class RandomFeatureGaussianProcess(m.Module):
         if return_random_features:
             return gp_logits, gp_covmat, gp_features
         return gp_logits, gp_covmat
+
+
+class MCSigmoidDenseFASNGP(m.Module):
+    """`edward2.jax.nn.MCSigmoidDenseFASNGP` (edward2/jax/nn/random_feature.py:407-695): heteroscedastic SNGP head with
+    sigmoid outputs.  The location is the RandomFeatureGaussianProcess head (`loc_layer`), the factor loadings and
+    the diagonal scale are Dense layers (`scale_layer`, `diag_layer`); at evaluation the diagonal scale becomes
+    sqrt(het_var_weight·diag² + sngp_var_weight·var_GP(x)) (:531-536) inside the Monte-Carlo kernel
+    (include/ed2b200.h: ed2_mc_softmax_fa_fwd, sigmoid link, JAX noise form).  Returns (logits, covmat_sngp) if
+    logits_only else (logits, covmat_sngp, log_probs, probs).  Not built (raise): parameter_efficient, num_factors == 0."""
+    num_outputs: int
+    num_factors: int
+    temperature: float = 1.0
+    parameter_efficient: bool = False
+    train_mc_samples: int = 1000
+    test_mc_samples: int = 1000
+    share_samples_across_batch: bool = False
+    logits_only: bool = False
+    return_locs: bool = False
+    eps: float = 1e-7
+    het_var_weight: float = 1.0
+    sngp_var_weight: float = 0.0
+    hidden_features: int = 1024
+    normalize_input: bool = True
+    norm_kwargs: Mapping[str, Any] = None
+    hidden_kwargs: Mapping[str, Any] = None
+    output_kwargs: Mapping[str, Any] = None
+    covmat_kwargs: Mapping[str, Any] = None
+
+    def _dense(self, features):
+        return Dense(features)
+
+    def setup(self):
+        K = self.num_outputs
+        self._loc_layer = RandomFeatureGaussianProcess(features=K, hidden_features=self.hidden_features,
+                                                       normalize_input=self.normalize_input, norm_kwargs=self.norm_kwargs,
+                                                       hidden_kwargs=self.hidden_kwargs, output_kwargs=self.output_kwargs,
+                                                       covmat_kwargs=self.covmat_kwargs)
+        self._scale_layer = self._dense(K * max(self.num_factors, 1))
+        self._diag_layer = self._dense(K)
+
+    def _noise(self, injected=None):
+        if injected is not None:
+            return F.Randomness(injected)
+        a, b = self.make_rng("diag_noise_samples"), self.make_rng("standard_norm_noise_samples")
+        return F.Randomness(seed=(a.seed * 0x9E3779B97F4A7C15 + b.seed) & 0xFFFFFFFFFFFFFFFF, stream=7)
+
+    def __call__(self, inputs, training=True, mc_noise=None):
+        """`mc_noise` (tests): injected noise [batch or 1, samples, round8(num_factors) + round8(num_outputs)] fp32 —
+        factor draws first, the diagonal draw at element round8(num_factors)."""
+        if self.parameter_efficient or self.num_factors <= 0:
+            raise NotImplementedError("parameter_efficient / num_factors == 0 are not built")
+        K, Fn = self.num_outputs, self.num_factors
+        locs, covmat_sngp = self.sub(self._loc_layer, "loc_layer")(inputs)
+        fac = self.sub(self._scale_layer, "scale_layer")(inputs)
+        diag_raw = self.sub(self._diag_layer, "diag_layer")(inputs)
+        initializing = self.is_mutable_collection("params")
+        mix = not (training or initializing)                                  # :528-536
+        if mix and covmat_sngp is None:
+            raise ValueError("evaluation needs the GP variance: apply without `laplace_covariance` in `mutable`")
+        samples = self.train_mc_samples if training else self.test_mc_samples
+        flags = (1 if self.share_samples_across_batch else 0) | 2 | 4         # JAX diagonal noise, sigmoid link
+        logits, probs, _ = F.MCSoftmaxFA.apply(locs.float(), fac.float(), diag_raw.float(),
+                                               covmat_sngp.reshape(-1) if mix else None, float(self.het_var_weight),
+                                               float(self.sngp_var_weight), self._noise(mc_noise), samples, Fn, flags,
+                                               float(self.temperature), float(self.eps), False)
+        probs_lo = torch.clamp(probs, min=self.eps)                           # :680
+        log_probs = torch.log(probs_lo)
+        if self.return_locs:
+            logits = locs
+        if self.logits_only:
+            return logits, covmat_sngp
+        return logits, covmat_sngp, log_probs, torch.clamp(probs_lo, self.eps, 1.0 - self.eps)
+
+
+class MCSigmoidDenseFASNGPBE(MCSigmoidDenseFASNGP):
+    """`edward2.jax.nn.MCSigmoidDenseFASNGPBE` (:698-735): the same head with BatchEnsemble scale / diagonal layers
+    (`DenseBatchEnsemble(ens_size)`, batch rows member-major)."""
+    ens_size: int = 1
+
+    def _dense(self, features):
+        from .dense import DenseBatchEnsemble
+        return DenseBatchEnsemble(features, ens_size=self.ens_size)

@@ -95,10 +95,11 @@ def sample_sigmoids(loc, fac, diag, z, e, temperature=1.0):
     return 1.0 / (1.0 + np.exp(-lat)), z, e
 
 
-def mc_sigmoid_fa(loc, fac, diag_raw, z, e, temperature=1.0, eps=1e-7):
+def mc_sigmoid_fa(loc, fac, diag_raw, z, e, temperature=1.0, eps=1e-7, sngp_var=None, w_het=1.0, w_sngp=1.0):
     """Returns (logits, log_probs, probs_mean): probs = mean_s sigmoid(latent / T) clipped from below at eps (:575-576);
-    logits = inverse sigmoid with the second clip to [eps, 1 - eps] (:578-580)."""
-    p, _, _ = sample_sigmoids(loc, fac, effective_diag(diag_raw), z, e, temperature)
+    logits = inverse sigmoid with the second clip to [eps, 1 - eps] (:578-580).  sngp_var [B]: the evaluation form of
+    MCSigmoidDenseFASNGP (edward2/jax/nn/random_feature.py:531-536): diag <- sqrt(w_het diag² + w_sngp var)."""
+    p, _, _ = sample_sigmoids(loc, fac, effective_diag(diag_raw, sngp_var, w_het, w_sngp), z, e, temperature)
     pm = np.clip(p.mean(1), eps, None)
     log_probs = np.log(pm)
     return log_probs - np.log(1.0 - np.clip(pm, eps, 1.0 - eps)), log_probs, pm

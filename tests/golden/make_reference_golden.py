@@ -204,6 +204,57 @@ def main():
         out[f"hsig_{name}_kernel"] = v["params"][name]["kernel"]
         out[f"hsig_{name}_bias"] = v["params"][name]["bias"]
 
+    # ---- §8f-2 MCSigmoidDenseFASNGP / MCSigmoidDenseFASNGPBE (random_feature.py:407-735): one training call (the
+    # precision matrix is updated), then an evaluation call that mixes the GP variance into the diagonal scale
+    for tag, cls, extra in (("hsngp", rf.MCSigmoidDenseFASNGP, {}), ("hsngpbe", rf.MCSigmoidDenseFASNGPBE, dict(ens_size=2))):
+        drawn = []
+
+        def recording_normal3(key, shape=(), dtype=None, _d=drawn):
+            v = real_normal(key, shape, dtype)
+            _d.append(np.array(v))
+            return v
+
+        jr.normal = jax.random.normal = recording_normal3
+        try:
+            B, Din, K, Fn, S, D = 8, 6, 4, 2, 48, 32
+            layer = cls(num_outputs=K, num_factors=Fn, temperature=0.8, train_mc_samples=S, test_mc_samples=S,
+                        hidden_features=D, het_var_weight=0.7, sngp_var_weight=1.3,
+                        covmat_kwargs=dict(ridge_penalty=1.0), **extra)
+            x, xt = rng.standard_normal((B, Din)), rng.standard_normal((B, Din))
+            rngs = {"params": jax.random.PRNGKey(12), "diag_noise_samples": jax.random.PRNGKey(13),
+                    "standard_norm_noise_samples": jax.random.PRNGKey(14)}
+            v = layer.init(rngs, x)
+            for name in ("scale_layer", "diag_layer"):
+                v["params"][name]["bias"] = rng.standard_normal(v["params"][name]["bias"].shape) * 0.2
+                if extra:  # BatchEnsemble fast weights away from their all-ones init
+                    for fw in ("fast_weight_alpha", "fast_weight_gamma"):
+                        v["params"][name][fw] = 1.0 + 0.3 * rng.standard_normal(v["params"][name][fw].shape)
+            v["params"]["loc_layer"]["output_layer"]["bias"] = rng.standard_normal(K) * 0.2
+            del drawn[:]
+            (lg, cov, lp, pr), st = layer.apply(v, x, training=True, rngs=rngs, mutable=["laplace_covariance"])
+            assert cov is None
+            train_noise = list(drawn)
+            v2 = {**{k: v[k] for k in v if k != "laplace_covariance"}, **st}
+            del drawn[:]
+            lg_e, cov_e, lp_e, pr_e = layer.apply(v2, xt, training=False, rngs=rngs)
+            eval_noise = list(drawn)
+        finally:
+            jr.normal = jax.random.normal = real_normal
+        pick = lambda ds, last: [d for d in ds if d.ndim == 3 and d.shape[-1] == last][-1]  # noqa: E731
+        out.update({f"{tag}_x": x, f"{tag}_xt": xt, f"{tag}_logits": lg, f"{tag}_log_probs": lp, f"{tag}_probs": pr,
+                    f"{tag}_diag_noise": pick(train_noise, 1), f"{tag}_factor_noise": pick(train_noise, Fn),
+                    f"{tag}_eval_logits": lg_e, f"{tag}_eval_var": cov_e, f"{tag}_eval_log_probs": lp_e,
+                    f"{tag}_eval_probs": pr_e, f"{tag}_eval_diag_noise": pick(eval_noise, 1),
+                    f"{tag}_eval_factor_noise": pick(eval_noise, Fn),
+                    f"{tag}_precision": st["laplace_covariance"]["loc_layer"]["covmat_layer"]["precision_matrix"],
+                    f"{tag}_rff_kernel": v["random_features"]["loc_layer"]["hidden_layer"]["kernel"],
+                    f"{tag}_rff_bias": v["random_features"]["loc_layer"]["hidden_layer"]["bias"],
+                    f"{tag}_out_kernel": v["params"]["loc_layer"]["output_layer"]["kernel"],
+                    f"{tag}_out_bias": v["params"]["loc_layer"]["output_layer"]["bias"]})
+        for name in ("scale_layer", "diag_layer"):
+            for leaf, val in v["params"][name].items():
+                out[f"{tag}_{name}_{leaf}"] = val
+
     np.savez_compressed(OUT, **{k: np.asarray(a) for k, a in out.items()})
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")
 

@@ -188,3 +188,53 @@ def test_mc_sigmoid_dense_fa_vs_reference(cuda, ref):
     assert rel_err(to_np(probs), ref["hsig_probs"]) < FP32
     assert rel_err(to_np(log_probs), ref["hsig_log_probs"]) < FP32
     assert rel_err(to_np(logits), ref["hsig_logits"]) < FP32
+
+
+@pytest.mark.parametrize("tag", ["hsngp", "hsngpbe"])
+def test_mc_sigmoid_dense_fa_sngp_vs_reference(cuda, ref, tag):
+    """`edward2_b200.nn.MCSigmoidDenseFASNGP` / `...BE` against the reference's own outputs
+    (edward2/jax/nn/random_feature.py:407-735) with its recorded noise injected: a training call (precision update), then
+    an evaluation call whose diagonal scale mixes in the GP variance."""
+    ed = _ed()
+    K, D = ref[f"{tag}_out_bias"].shape[0], ref[f"{tag}_rff_kernel"].shape[1]
+    Fn, S = ref[f"{tag}_factor_noise"].shape[2], ref[f"{tag}_factor_noise"].shape[1]
+    FP, KP = (Fn + 7) // 8 * 8, (K + 7) // 8 * 8
+
+    def noise(prefix):
+        z, n = ref[f"{tag}_{prefix}factor_noise"], ref[f"{tag}_{prefix}diag_noise"]
+        buf = np.zeros((z.shape[0], S, FP + KP), dtype=np.float32)
+        buf[:, :, :Fn] = z
+        buf[:, :, FP] = n[:, :, 0]
+        return torch.tensor(buf, device=cuda)
+
+    kw = dict(num_outputs=K, num_factors=Fn, temperature=0.8, train_mc_samples=S, test_mc_samples=S, hidden_features=D,
+              het_var_weight=0.7, sngp_var_weight=1.3, covmat_kwargs=dict(ridge_penalty=1.0))
+    layer = ed.nn.MCSigmoidDenseFASNGPBE(ens_size=2, **kw) if tag == "hsngpbe" else ed.nn.MCSigmoidDenseFASNGP(**kw)
+    leaves = ("kernel", "bias") + (("fast_weight_alpha", "fast_weight_gamma") if tag == "hsngpbe" else ())
+    params = {name: {leaf: _t(ref[f"{tag}_{name}_{leaf}"], cuda, True) for leaf in leaves}
+              for name in ("scale_layer", "diag_layer")}
+    params["loc_layer"] = {"output_layer": {"kernel": _t(ref[f"{tag}_out_kernel"], cuda, True),
+                                            "bias": _t(ref[f"{tag}_out_bias"], cuda, True)}}
+    variables = {
+        "params": params,
+        "random_features": {"loc_layer": {"hidden_layer": {"kernel": _t(ref[f"{tag}_rff_kernel"], cuda),
+                                                           "bias": _t(ref[f"{tag}_rff_bias"], cuda)}}},
+        "laplace_covariance": {"loc_layer": {"covmat_layer": {"precision_matrix": _t(np.eye(D), cuda)}}},
+    }
+    (logits, cov, log_probs, probs), st = layer.apply(variables, _t(ref[f"{tag}_x"], cuda), training=True,
+                                                      mc_noise=noise(""), mutable=["laplace_covariance"])
+    assert cov is None
+    assert rel_err(to_np(probs), ref[f"{tag}_probs"]) < FP32
+    assert rel_err(to_np(log_probs), ref[f"{tag}_log_probs"]) < FP32
+    assert rel_err(to_np(logits), ref[f"{tag}_logits"]) < FP32
+    assert rel_err(to_np(st["laplace_covariance"]["loc_layer"]["covmat_layer"]["precision_matrix"]),
+                   ref[f"{tag}_precision"]) < FP32
+    logits.sum().backward()   # the training form differentiates through the Monte-Carlo head into all three layers
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in
+               (params["scale_layer"]["kernel"], params["diag_layer"]["kernel"], params["loc_layer"]["output_layer"]["kernel"]))
+    logits, var, log_probs, probs = layer.apply(dict(variables, **st), _t(ref[f"{tag}_xt"], cuda), training=False,
+                                                mc_noise=noise("eval_"))
+    assert rel_err(to_np(var), ref[f"{tag}_eval_var"]) < 1e-4
+    assert rel_err(to_np(probs), ref[f"{tag}_eval_probs"]) < 1e-4
+    assert rel_err(to_np(log_probs), ref[f"{tag}_eval_log_probs"]) < 1e-4
+    assert rel_err(to_np(logits), ref[f"{tag}_eval_logits"]) < 1e-4

@@ -692,3 +692,48 @@ def test_reference_mc_sigmoid_dense_fa(ref):
     got = oh.mc_sigmoid_fa_bwd(loc, fac, draw, z, e, g, T)
     for a, b_ in ((got["dloc"], lt.grad), (got["dfac"], ft.grad), (got["ddiag_raw"], dt_.grad)):
         np.testing.assert_allclose(a, b_.numpy(), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["hsngp", "hsngpbe"])
+def test_reference_mc_sigmoid_dense_fa_sngp(ref, tag):
+    """jax/nn/random_feature.py:407-735 (MCSigmoidDenseFASNGP / ...BE) run as shipped with its draws recorded: a training
+    call (GP location, precision update, Monte-Carlo sigmoid head) and an evaluation call whose diagonal scale mixes in
+    the GP variance — restated from the oracle's pieces."""
+    from oracle import dense as od, heteroscedastic as oh, sngp as osn
+
+    D = ref[f"{tag}_rff_kernel"].shape[1]
+
+    def lin(name, x):
+        k, b = ref[f"{tag}_{name}_kernel"], ref[f"{tag}_{name}_bias"]
+        if tag == "hsngpbe":
+            return od.batch_ensemble_fwd(x, k, ref[f"{tag}_{name}_fast_weight_alpha"],
+                                         ref[f"{tag}_{name}_fast_weight_gamma"], b, None)[0]
+        return x @ k + b
+
+    def head(x):
+        phi, _ = osn.rff(osn.layer_norm(x, eps=1e-6), ref[f"{tag}_rff_kernel"], ref[f"{tag}_rff_bias"], 1.0)
+        return phi, osn.gp_output(phi, ref[f"{tag}_out_kernel"], ref[f"{tag}_out_bias"])
+
+    def noise(prefix, K):
+        e = ref[f"{tag}_{prefix}diag_noise"]
+        return ref[f"{tag}_{prefix}factor_noise"], np.broadcast_to(e, e.shape[:2] + (K,))
+
+    x, xt = ref[f"{tag}_x"], ref[f"{tag}_xt"]
+    phi, loc = head(x)
+    K = loc.shape[1]
+    z, e = noise("", K)
+    logits, log_probs, probs = oh.mc_sigmoid_fa(loc, lin("scale_layer", x), lin("diag_layer", x), z, e, 0.8, 1e-7)
+    _close(probs, ref[f"{tag}_probs"])
+    _close(log_probs, ref[f"{tag}_log_probs"])
+    _close(logits, ref[f"{tag}_logits"])
+    precision = osn.precision_update_jax(np.eye(D), phi, None)
+    _close(precision, ref[f"{tag}_precision"])
+    phit, loct = head(xt)
+    var = osn.predictive_covariance_jax(phit, precision, 1.0, diagonal_only=True)
+    _close(var, ref[f"{tag}_eval_var"])
+    z, e = noise("eval_", K)
+    logits, log_probs, probs = oh.mc_sigmoid_fa(loct, lin("scale_layer", xt), lin("diag_layer", xt), z, e, 0.8, 1e-7,
+                                                sngp_var=var, w_het=0.7, w_sngp=1.3)
+    _close(probs, ref[f"{tag}_eval_probs"])
+    _close(log_probs, ref[f"{tag}_eval_log_probs"])
+    _close(logits, ref[f"{tag}_eval_logits"])
