@@ -338,6 +338,15 @@ ffi::Error PredictiveVariance(cudaStream_t s, Any phi, Any sigma_lp, F32B logits
                                       dim(phi, 0), dim(phi, 1), ridge, var->typed_data(), logits.typed_data(), dim(logits, 1),
                                       mean_field_factor, likelihood, logits_out->typed_data(), s));
 }
+// Sigma = (ridge I + P)^-1 on the GPU (jax/nn/random_feature.py:393-395 factorises and solves on every evaluation call);
+// `a` is inverted in place (input_output_aliases={0: 0}); workspace of ed2_spd_inverse_workspace_floats(n) floats
+ffi::Error SpdInverse(cudaStream_t s, F32B a_in, Out<F32B> a, Out<F32B> workspace) {
+  (void)a_in;
+  const int n = dim(*a, 0);
+  if (static_cast<long long>(workspace->element_count()) < ed2_spd_inverse_workspace_floats(n))
+    return ffi::Error::InvalidArgument("Ed2SpdInverse: workspace too small");
+  return done(ed2_spd_inverse(a->typed_data(), n, workspace->typed_data(), s));
+}
 ffi::Error MeanFieldLogits(cudaStream_t s, F32B logits, F32B var, float mean_field_factor, int32_t likelihood,
                            Out<F32B> out) {
   return done(ed2_mean_field_logits(logits.typed_data(), var.typed_data(), dim(logits, 0), dim(logits, 1), mean_field_factor,
@@ -428,6 +437,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2LaplacePrecisionUpdate, LaplacePrecisionUpdate,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2PredictiveVariance, PredictiveVariance,
     ED2_STREAM.Arg<Any>().Arg<Any>().Arg<F32B>().Attr<float>("ridge").Attr<float>("mean_field_factor")
         .Attr<int32_t>("likelihood").Ret<F32B>().Ret<F32B>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2SpdInverse, SpdInverse, ED2_STREAM.Arg<F32B>().Ret<F32B>().Ret<F32B>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2MeanFieldLogits, MeanFieldLogits,
     ED2_STREAM.Arg<F32B>().Arg<F32B>().Attr<float>("mean_field_factor").Attr<int32_t>("likelihood").Ret<F32B>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2SpectralNormUpdate, SpectralNormUpdate,

@@ -494,6 +494,27 @@ class Ed2PredictiveVarianceOp : public OpKernel {
 };
 ED2_REGISTER("Ed2PredictiveVariance", Ed2PredictiveVarianceOp);
 
+// covariance = inv(ridge I + precision) — random_feature.py:447-459 (tf.linalg.inv), as the library's block Gauss-Jordan
+REGISTER_OP("Ed2SpdInverse").Input("a: float").Output("inverse: float").Output("status: int32");
+class Ed2SpdInverseOp : public OpKernel {
+ public:
+  explicit Ed2SpdInverseOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    const Tensor& a = c->input(0);
+    const int n = D(a, 0);
+    ED2_OUT(0, TensorShape({n, n}), inv); ED2_OUT(1, TensorShape({}), status);
+    const long long wsn = ed2_spd_inverse_workspace_floats(n);
+    Tensor ws;
+    OP_REQUIRES_OK(c, c->allocate_temp(DataTypeToEnum<float>::value, TensorShape({wsn}), &ws));
+    auto stream = c->eigen_gpu_device().stream();
+    cudaMemcpyAsync(F(inv), F(a), sizeof(float) * n * n, cudaMemcpyDeviceToDevice, stream);
+    ED2_CALL(ed2_spd_inverse(F(inv), n, F(&ws), stream));
+    // the last workspace word is the status flag (non-zero: a pivot was not positive)
+    cudaMemcpyAsync(status->data(), F(&ws) + wsn - 1, sizeof(int), cudaMemcpyDeviceToDevice, stream);
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("Ed2SpdInverse").Device(DEVICE_GPU), Ed2SpdInverseOp);
+
 // SpectralNormalization.update_weights — edward2/tensorflow/layers/normalization.py:369-391 (mode 0, in-place kernel)
 REGISTER_OP("Ed2SpectralNormUpdate").Input("w: float").Input("u: float").Input("v: float")
     .Output("w_out: float").Output("sigma: float").Attr("iterations: int = 1").Attr("norm_multiplier: float = 0.95")

@@ -164,7 +164,8 @@ def test_shims_type_check(shim):
     for entry in ("ed2_be_dense_fwd", "ed2_be_dense_bwd", "ed2_rank1_dense_fwd", "ed2_rank1_dense_bwd",
                   "ed2_reparam_dense_fwd", "ed2_reparam_dense_bwd", "ed2_flipout_dense_fwd", "ed2_flipout_dense_bwd",
                   "ed2_rff_fwd", "ed2_laplace_precision_update", "ed2_predictive_variance", "ed2_spectral_norm_update",
-                  "ed2_flipout_fused_fwd", "ed2_flipout_fused_bwd", "ed2_mc_softmax_fa_fwd", "ed2_mc_softmax_fa_bwd"):
+                  "ed2_flipout_fused_fwd", "ed2_flipout_fused_bwd", "ed2_mc_softmax_fa_fwd", "ed2_mc_softmax_fa_bwd",
+                  "ed2_spd_inverse"):
         assert entry + "(" in src, f"{shim} does not bind {entry}"
     if shim == "jax_ffi_shim.cc":
         for entry in ("ed2_conv_factor_fwd", "ed2_conv_factor_bwd"):
