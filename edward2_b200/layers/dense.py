@@ -339,11 +339,13 @@ class DenseBatchEnsemble(Layer):
                  kernel_regularizer=None, bias_regularizer=None, activity_regularizer=None, kernel_constraint=None,
                  bias_constraint=None, **kwargs):
         super().__init__(**kwargs)
-        if rank != 1:
-            raise NotImplementedError("rank > 1 fast weights (dense.py:560-570) are not built; rank=1 is the hot path")
-        self.units, self.rank, self.ensemble_size = int(units), rank, int(ensemble_size)
+        if int(rank) < 1:
+            raise ValueError("rank must be at least 1")
+        self.units, self.rank, self.ensemble_size = int(units), int(rank), int(ensemble_size)
         self.ensemble_activation = activation
         self._act = ops.act_id(activation)
+        if self.rank > 1 and self._act not in (ops.ACT_NONE, ops.ACT_RELU):
+            raise NotImplementedError("rank > 1 fast weights take activation None or 'relu'")
         self.use_ensemble_bias = use_bias
         self.alpha_initializer = initializers.get(alpha_initializer)
         self.gamma_initializer = initializers.get(gamma_initializer)
@@ -356,8 +358,9 @@ class DenseBatchEnsemble(Layer):
         dev = self._device
         in_dim, E = input_shape[-1], self.ensemble_size
         self.kernel = nn.Parameter(self.kernel_initializer((in_dim, self.units)).to(dev))
-        self.alpha = nn.Parameter(self.alpha_initializer((E, in_dim)).to(dev))
-        self.gamma = nn.Parameter(self.gamma_initializer((E, self.units)).to(dev))
+        lead = (self.rank,) if self.rank > 1 else ()   # dense.py:518-523: [rank, ensemble_size, dim] when rank > 1
+        self.alpha = nn.Parameter(self.alpha_initializer(lead + (E, in_dim)).to(dev))
+        self.gamma = nn.Parameter(self.gamma_initializer(lead + (E, self.units)).to(dev))
         self.ensemble_bias = (nn.Parameter(self.ensemble_bias_initializer((E, self.units)).to(dev))
                               if self.use_ensemble_bias else None)
         self.built = True
@@ -367,8 +370,27 @@ class DenseBatchEnsemble(Layer):
             raise ValueError("DenseBatchEnsemble (TF signature) takes [ensemble_size * examples_per_model, features]")
         if inputs.shape[0] % self.ensemble_size != 0:
             raise ValueError(f"batch size {inputs.shape[0]} is not divisible by ensemble_size {self.ensemble_size}")
+        if self.rank > 1:
+            return self._call_rank_r(inputs)
         return F.BatchEnsembleDense.apply(inputs, self.kernel, self.alpha, self.gamma, self.ensemble_bias, self._act,
                                           self.ensemble_size, self.compute_dtype)
+
+    def _call_rank_r(self, inputs):
+        """dense.py:560-570: y = act(sum_r ((x∘alpha[r, e]) W)∘gamma[r, e] + bias[e]).  The rank axis is stacked onto the
+        batch — ONE BatchEnsemble launch over rank·ensemble_size members ([rank·B, I] rows, member (r, e) owns rows
+        r·B + e·n .. + n, exactly the reference's tile / reshape) — and the sum over rank, the bias and the activation
+        follow as elementwise tensor ops (this branch is off the measured path)."""
+        R, E = self.rank, self.ensemble_size
+        B, I = inputs.shape
+        stacked = inputs.unsqueeze(0).expand(R, B, I).reshape(R * B, I)
+        y = F.BatchEnsembleDense.apply(stacked, self.kernel, self.alpha.reshape(R * E, I),
+                                       self.gamma.reshape(R * E, self.units), None, ops.ACT_NONE, R * E, self.compute_dtype)
+        y = y.view(R, B, self.units).float().sum(0)
+        if self.ensemble_bias is not None:
+            y = (y.view(E, B // E, self.units) + self.ensemble_bias[:, None, :]).view(B, self.units)
+        if self._act == ops.ACT_RELU:
+            y = torch.relu(y)
+        return y.to(self.compute_dtype)
 
     @property
     def losses(self):
@@ -381,8 +403,8 @@ class DenseBatchEnsemble(Layer):
 
     def get_config(self):
         cfg = super().get_config()
-        cfg.update(units=self.units, ensemble_size=self.ensemble_size, ensemble_activation=self.ensemble_activation,
-                   use_ensemble_bias=self.use_ensemble_bias,
+        cfg.update(units=self.units, rank=self.rank, ensemble_size=self.ensemble_size,
+                   ensemble_activation=self.ensemble_activation, use_ensemble_bias=self.use_ensemble_bias,
                    alpha_initializer=initializers.serialize(self.alpha_initializer),
                    gamma_initializer=initializers.serialize(self.gamma_initializer),
                    ensemble_bias_initializer=initializers.serialize(self.ensemble_bias_initializer),

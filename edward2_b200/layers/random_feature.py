@@ -306,8 +306,7 @@ class RandomFeatureGaussianProcess(Layer):
         self.use_custom_random_features = use_custom_random_features
         if not use_custom_random_features:
             raise NotImplementedError("tf.keras RandomFourierFeatures (use_custom_random_features=False) is not built")
-        if gp_kernel_type.lower() == "linear":
-            raise NotImplementedError("gp_kernel_type='linear' (identity features) is outside the hot path")
+        self._linear = gp_kernel_type.lower() == "linear"   # identity features (random_feature.py:221-223)
         if custom_random_features_activation is not None and getattr(custom_random_features_activation, "__name__", "") != "cos":
             raise NotImplementedError("only the cosine random-feature activation is fused")
         self.custom_random_features_initializer = (
@@ -325,14 +324,13 @@ class RandomFeatureGaussianProcess(Layer):
     def build(self, input_shape):
         dt = self.compute_dtype
         # the normalised input stays fp32 when the phase is evaluated at fp32 grade (it is split on the fly)
-        norm_dt = torch.float32 if self.phase_precision != "native" else dt
+        norm_dt = torch.float32 if (self.phase_precision != "native" and not self._linear) else dt
         if self.normalize_input:
             self._input_norm_layer = _LayerNormalization(dtype=norm_dt, name="gp_input_normalization")
         scale = self.gp_feature_scale if self.scale_random_features else 1.0
-        self._random_feature = _RandomFeature(self.num_inducing, self.custom_random_features_initializer,
-                                              self.random_features_bias_initializer, scale,
-                                              phase_precision=self.phase_precision, dtype=dt,
-                                              name="gp_random_feature")
+        self._random_feature = None if self._linear else _RandomFeature(
+            self.num_inducing, self.custom_random_features_initializer, self.random_features_bias_initializer, scale,
+            phase_precision=self.phase_precision, dtype=dt, name="gp_random_feature")
         if self.return_gp_cov:
             self._gp_cov_layer = LaplaceRandomFeatureCovariance(
                 momentum=self.gp_cov_momentum, ridge_penalty=self.gp_cov_ridge_penalty,
@@ -354,6 +352,16 @@ class RandomFeatureGaussianProcess(Layer):
         """Random features of a 2-D batch: input normalisation / scaling + cos(xW + b) * scale (random_feature.py:250-266)."""
         gp_inputs = x
         rf = self._random_feature
+        if self._linear:
+            # gp_kernel_type='linear': the features are the (normalised / rescaled) inputs themselves, times
+            # sqrt(2 / num_inducing) when scale_random_features (:250-266 with the Lambda layer of :221-223)
+            if self.normalize_input:
+                gp_inputs = self._input_norm_layer(gp_inputs)
+            elif self.gp_input_scale is not None:
+                gp_inputs = gp_inputs * self.gp_input_scale
+            if self.scale_random_features:
+                gp_inputs = gp_inputs * self.gp_feature_scale
+            return gp_inputs.to(self.compute_dtype)
         if (self.normalize_input and self._input_norm_layer.built and rf.built and rf._nsplit == 2
                 and x.shape[-1] % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16)):
             # fused unit: LayerNorm writes the split operand, the GEMM epilogue writes phi and -scale*sin(phase)

@@ -80,6 +80,23 @@ def batch_ensemble_fwd(x, w, alpha, gamma, bias=None, act=None):
     return y.reshape(E * n, -1), z.reshape(E * n, -1)
 
 
+def batch_ensemble_rank_fwd(x, w, alpha, gamma, bias=None, act=None):
+    """edward2/tensorflow/layers/dense.py:560-570 (rank > 1 branch), statement by statement: alpha [R, E, I] and gamma
+    [R, E, O] are tiled along their last axis and reshaped to [R, B, dim], the perturbed inputs go through the shared
+    kernel, the products are weighted by gamma and summed over the rank axis."""
+    x = np.asarray(x, dtype=np.float64)
+    R, E, I = alpha.shape
+    B = x.shape[0]
+    n = B // E
+    a = np.tile(alpha, (1, 1, n)).reshape(R, B, I)
+    g = np.tile(gamma, (1, 1, n)).reshape(R, B, -1)
+    out = (((x[None] * a) @ np.asarray(w, dtype=np.float64)) * g).sum(0)
+    out = out.reshape(E, n, -1)
+    if bias is not None:
+        out = out + np.asarray(bias, dtype=np.float64)[:, None, :]
+    return activation(out, act).reshape(B, -1)
+
+
 def batch_ensemble_bwd(x, w, alpha, gamma, bias, act, gy, y_mask=None):
     """Closed-form gradients of batch_ensemble_fwd.  y_mask: optional forward output whose sign
     pattern defines relu' (bf16 parity is conditioned on the kernel's own activation pattern)."""

@@ -114,6 +114,41 @@ def test_batch_ensemble_vectorised_equals_loop(cuda, dtype, tol):
         layer(x[:-1])
 
 
+@pytest.mark.parametrize("dtype,tol", [("float32", 1e-5), ("bfloat16", 2e-2)])
+def test_batch_ensemble_rank_r(cuda, dtype, tol):
+    """DenseBatchEnsemble(rank=3) (dense.py:518-523, 560-570): forward against the oracle's statement-by-statement
+    restatement, gradients against float64 autograd of the same formula."""
+    from oracle import dense as od
+
+    ed = _ed()
+    R, E, n, I, O = 3, 2, 8, 24, 16
+    rng = np.random.default_rng(11)
+    layer = ed.layers.DenseBatchEnsemble(O, rank=R, ensemble_size=E, alpha_initializer="he_normal",
+                                         gamma_initializer="he_normal", bias_initializer="he_normal", activation="relu",
+                                         dtype=dtype)
+    x = torch.tensor(rng.standard_normal((E * n, I)), dtype=torch.float32, device=cuda).to(layer.compute_dtype).requires_grad_(True)
+    y = layer(x)
+    assert tuple(layer.alpha.shape) == (R, E, I) and tuple(layer.gamma.shape) == (R, E, O)
+    gy = torch.tensor(rng.standard_normal((E * n, O)), dtype=torch.float32, device=cuda)
+    (y.float() * gy).sum().backward()
+    torch.cuda.synchronize()
+    xin, w = to_np(x.detach()), to_np(layer.kernel.detach().to(layer.compute_dtype))
+    alpha, gamma, bias = to_np(layer.alpha.detach()), to_np(layer.gamma.detach()), to_np(layer.ensemble_bias.detach())
+    assert rel_err(to_np(y), od.batch_ensemble_rank_fwd(xin, w, alpha, gamma, bias, "relu")) < tol
+    t = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in
+         dict(x=xin, w=w, a=alpha, g=gamma, b=bias).items()}
+    a_rows = t["a"].repeat_interleave(n, dim=1)          # [R, B, I]: member e owns rows e*n .. e*n + n
+    g_rows = t["g"].repeat_interleave(n, dim=1)
+    pre = (((t["x"][None] * a_rows) @ t["w"]) * g_rows).sum(0) + t["b"].repeat_interleave(n, dim=0)
+    mask = torch.tensor(to_np(y) > 0)                    # bf16: relu' conditioned on the kernel's own pattern
+    ((pre * mask) * torch.tensor(to_np(gy), dtype=torch.float64)).sum().backward()
+    assert rel_err(to_np(x.grad), t["x"].grad.numpy()) < tol
+    assert rel_err(to_np(layer.kernel.grad), t["w"].grad.numpy()) < tol
+    assert rel_err(to_np(layer.alpha.grad), t["a"].grad.numpy()) < tol
+    assert rel_err(to_np(layer.gamma.grad), t["g"].grad.numpy()) < tol
+    assert rel_err(to_np(layer.ensemble_bias.grad), t["b"].grad.numpy()) < tol
+
+
 def test_rank1_deterministic_equals_batch_ensemble(cuda):
     """dense_test.py:430-460 (testDenseRank1BatchEnsemble): with deterministic fast weights DenseRank1 == BatchEnsemble."""
     ed = _ed()
@@ -228,6 +263,36 @@ def test_rfgp_end_to_end(cuda):
     assert rel_err(to_np(cov2), og.predictive_covariance_tf(phi_ref, sigma, 1.0)) < 1e-4
     adj = ed.layers.utils.mean_field_logits(logits2, cov2, mean_field_factor=1.0)
     assert rel_err(to_np(adj), og.mean_field_logits(to_np(logits2), to_np(cov2), 1.0)) < 1e-5
+
+
+def test_rfgp_linear_kernel(cuda):
+    """gp_kernel_type='linear' (random_feature.py:221-223): the features are the normalised inputs times
+    sqrt(2 / num_inducing); output layer, precision update and predictive covariance act on the input width."""
+    ed = _ed()
+    rng = np.random.default_rng(17)
+    B, d, K = 48, 24, 5
+    x = torch.tensor(rng.standard_normal((B, d)), dtype=torch.float32, device=cuda, requires_grad=True)
+    gp = ed.layers.RandomFeatureGaussianProcess(K, num_inducing=64, gp_kernel_type="linear", gp_cov_momentum=-1,
+                                                gp_cov_ridge_penalty=1.0, return_random_features=True)
+    logits, cov, feats = gp(x, training=True)
+    assert feats.shape == (B, d) and gp._random_feature is None
+    ln = gp._input_norm_layer
+    phi_ref = og.layer_norm(to_np(x), to_np(ln.gamma), to_np(ln.beta), 1e-3) * np.sqrt(2.0 / 64)
+    assert rel_err(to_np(feats), phi_ref) < 1e-5
+    logits_ref = og.gp_output(phi_ref, to_np(gp._gp_output_layer.kernel), to_np(gp._gp_output_bias))
+    assert rel_err(to_np(logits), logits_ref) < 1e-5
+    logits.sum().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all()
+    assert rel_err(to_np(gp._gp_cov_layer.precision_matrix), phi_ref.T @ phi_ref) < 1e-5
+    _, cov2, _ = gp(x.detach(), training=False)
+    sigma = og.covariance_tf(phi_ref.T @ phi_ref, 1.0)
+    assert rel_err(to_np(cov2), og.predictive_covariance_tf(phi_ref, sigma, 1.0)) < 1e-4
+    # without input normalisation the inputs are rescaled by 1 / sqrt(gp_kernel_scale) (:253-257)
+    gp2 = ed.layers.RandomFeatureGaussianProcess(K, num_inducing=64, gp_kernel_type="linear", normalize_input=False,
+                                                 gp_kernel_scale=4.0, scale_random_features=False,
+                                                 return_gp_cov=False, return_random_features=True)
+    _, feats2 = gp2(x.detach())
+    assert rel_err(to_np(feats2), to_np(x) * 0.5) < 1e-6
 
 
 def test_spectral_normalization_layer(cuda):

@@ -68,6 +68,19 @@ def test_batch_ensemble_equals_member_loop():
     np.testing.assert_allclose(y, loop, rtol=1e-12, atol=1e-12)
 
 
+def test_batch_ensemble_rank_r_equals_sum_of_rank_one_members():
+    """dense.py:560-570: the rank > 1 branch is the sum over r of rank-1 BatchEnsemble products, one bias per member."""
+    rng = np.random.default_rng(7)
+    R, E, n, I, O = 3, 2, 4, 5, 6
+    x, w = rng.standard_normal((E * n, I)), rng.standard_normal((I, O))
+    a, g, b = rng.standard_normal((R, E, I)), rng.standard_normal((R, E, O)), rng.standard_normal((E, O))
+    y = od.batch_ensemble_rank_fwd(x, w, a, g, b, "relu")
+    loop = np.concatenate([sum(((x[e * n:(e + 1) * n] * a[r, e]) @ w) * g[r, e] for r in range(R)) + b[e] for e in range(E)])
+    np.testing.assert_allclose(y, np.maximum(loop, 0), rtol=1e-12, atol=1e-12)
+    y1 = od.batch_ensemble_rank_fwd(x, w, a[:1], g[:1], b, None)
+    np.testing.assert_allclose(y1, od.batch_ensemble_fwd(x, w, a[0], g[0], b)[0], rtol=1e-12, atol=1e-12)
+
+
 def test_kl_properties():
     """regularizers_test.py:65-80: KL >= 0, linear in scale_factor, 0 for q == p; TFP's expm1 form agrees."""
     rng = np.random.default_rng(1)
