@@ -61,11 +61,12 @@ struct McArgs {
 };
 
 // the P = FP + KP normals of sample (nb, s): z[f] and e[k] (8-aligned halves)
-template <int KMAX>
+// kDiagOne (flag bit 1, compile time): ONE diagonal draw per (example, sample), shared by the classes
+template <int KMAX, bool kDiagOne>
 __device__ __forceinline__ void draw_sample(const McArgs& a, uint64_t key, long long sample, int FP, int KP, float (&z)[kFMax],
                                             float (&e)[KMAX]) {
   const long long base = sample * (FP + KP);
-  const bool diag_one = (a.shared & 2) != 0;  // ONE diagonal draw per (example, sample), shared by the classes
+  constexpr bool diag_one = kDiagOne;
   if (a.noise.injected != nullptr) {
 #pragma unroll
     for (int f = 0; f < kFMax; ++f) z[f] = f < a.F ? __ldg(a.noise.injected + base + f) : 0.f;
@@ -95,7 +96,7 @@ __device__ __forceinline__ void draw_sample(const McArgs& a, uint64_t key, long 
 }
 
 // softmax probabilities of one sample (registers): p[k], k < K
-template <int KMAX>
+template <int KMAX, bool kSigmoid>
 __device__ __forceinline__ void sample_probs(const McArgs& a, const float* sloc, const float* sfac, const float* sdiag,
                                              const float (&z)[kFMax], const float (&e)[KMAX], float (&p)[KMAX]) {
   float m = -3.0e38f;
@@ -112,7 +113,7 @@ __device__ __forceinline__ void sample_probs(const McArgs& a, const float* sloc,
     }
     p[k] = lat;
   }
-  if (a.shared & 4) {  // sigmoid link (MCSigmoidDenseFA): independent outputs
+  if constexpr (kSigmoid) {  // sigmoid link (MCSigmoidDenseFA): independent outputs
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) p[k] = k < a.K ? 1.f / (1.f + expf(-p[k])) : 0.f;
     return;
@@ -140,7 +141,7 @@ __device__ __forceinline__ void stage_params(const McArgs& a, int b, int lane, f
   __syncwarp();
 }
 
-template <int KMAX>
+template <int KMAX, bool kSigmoid, bool kDiagOne>
 __global__ void __launch_bounds__(kWarps * 32) mc_softmax_fwd_kernel(McArgs a) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,8 +160,8 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_fwd_kernel(McArgs a) {
   for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
   for (int s = lane; s < a.S; s += 32) {
     float z[kFMax], e[KMAX], p[KMAX];
-    draw_sample<KMAX>(a, key, nb * a.S + s, FP, KP, z, e);
-    sample_probs<KMAX>(a, sloc, sfac, sdiag, z, e, p);
+    draw_sample<KMAX, kDiagOne>(a, key, nb * a.S + s, FP, KP, z, e);
+    sample_probs<KMAX, kSigmoid>(a, sloc, sfac, sdiag, z, e, p);
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) acc[k] += p[k];
   }
@@ -173,8 +174,8 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_fwd_kernel(McArgs a) {
         a.probs_mean[static_cast<long long>(b) * a.K + k] = acc[k];
         // softmax: log(clip(pm, eps, 1));  sigmoid: inverse sigmoid log(clip(pm, eps)) - log(1 - clip(pm, eps, 1 - eps))
         a.logits[static_cast<long long>(b) * a.K + k] =
-            (a.shared & 4) ? logf(fmaxf(acc[k], a.eps)) - logf(1.f - fminf(fmaxf(acc[k], a.eps), 1.f - a.eps))
-                           : logf(fminf(fmaxf(acc[k], a.eps), 1.f));
+            kSigmoid ? logf(fmaxf(acc[k], a.eps)) - logf(1.f - fminf(fmaxf(acc[k], a.eps), 1.f - a.eps))
+                     : logf(fminf(fmaxf(acc[k], a.eps), 1.f));
       }
     }
   }
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_fwd_kernel(McArgs a) {
   for (int k = 0; k < KMAX; ++k) var[k] = 0.f;
   for (int s = lane; s < a.S; s += 32) {
     float z[kFMax], e[KMAX], p[KMAX];
-    draw_sample<KMAX>(a, key, nb * a.S + s, FP, KP, z, e);
-    sample_probs<KMAX>(a, sloc, sfac, sdiag, z, e, p);
+    draw_sample<KMAX, kDiagOne>(a, key, nb * a.S + s, FP, KP, z, e);
+    sample_probs<KMAX, kSigmoid>(a, sloc, sfac, sdiag, z, e, p);
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) var[k] += (p[k] - acc[k]) * (p[k] - acc[k]);
   }
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_fwd_kernel(McArgs a) {
   }
 }
 
-template <int KMAX>
+template <int KMAX, bool kSigmoid, bool kDiagOne>
 __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
   for (int k = lane; k < a.K; k += 32) {
     const float pm = __ldg(a.probs_mean + static_cast<long long>(b) * a.K + k);
     const float gk = __ldg(a.g + static_cast<long long>(b) * a.K + k);
-    if (a.shared & 4) {  // d logit / d pm of the inverse sigmoid; the clips pass no gradient outside their ranges
+    if constexpr (kSigmoid) {  // d logit / d pm of the inverse sigmoid; the clips pass no gradient outside their ranges
       const float d = (pm > a.eps ? 1.f / pm : 0.f) + ((pm > a.eps && pm < 1.f - a.eps) ? 1.f / (1.f - pm) : 0.f);
       su[k] = gk * d * inv_s;
     } else {
@@ -241,8 +242,8 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
     const bool live = s < a.S;
     float z[kFMax], e[KMAX], p[KMAX];
     if (live) {
-      draw_sample<KMAX>(a, key, nb * a.S + s, FP, KP, z, e);
-      sample_probs<KMAX>(a, sloc, sfac, sdiag, z, e, p);
+      draw_sample<KMAX, kDiagOne>(a, key, nb * a.S + s, FP, KP, z, e);
+      sample_probs<KMAX, kSigmoid>(a, sloc, sfac, sdiag, z, e, p);
     }
     float dot = 0.f;
 #pragma unroll
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < a.K) {
-        const float d = !live ? 0.f : (a.shared & 4) ? a.inv_t * su[k] * p[k] * (1.f - p[k]) : a.inv_t * p[k] * (su[k] - dot);
+        const float d = !live ? 0.f : kSigmoid ? a.inv_t * su[k] * p[k] * (1.f - p[k]) : a.inv_t * p[k] * (su[k] - dot);
         dl[k] += d;
         dd[k] = fmaf(d, live ? e[k] : 0.f, dd[k]);
         scratch[lane * row + k] = d;
@@ -300,6 +301,28 @@ int check(const McArgs& a) {
   return ED2_OK;
 }
 
+// the link (bit 2 of `shared`) and the diagonal-noise form (bit 1) are compile-time variants: as run-time branches they
+// cost the softmax / per-class form 39 registers in the forward kernel and ~20 % of its time
+template <bool kFwd, int KMAX, bool kSigmoid, bool kDiagOne>
+void launch_kmax(const McArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if constexpr (kFwd) mc_softmax_fwd_kernel<KMAX, kSigmoid, kDiagOne><<<grid, kWarps * 32, smem, s>>>(a);
+  else mc_softmax_bwd_kernel<KMAX, kSigmoid, kDiagOne><<<grid, kWarps * 32, smem, s>>>(a);
+}
+template <bool kFwd, bool kSigmoid, bool kDiagOne>
+void launch_link(const McArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (a.K <= 16) launch_kmax<kFwd, 16, kSigmoid, kDiagOne>(a, grid, smem, s);
+  else if (a.K <= 32) launch_kmax<kFwd, 32, kSigmoid, kDiagOne>(a, grid, smem, s);
+  else launch_kmax<kFwd, 64, kSigmoid, kDiagOne>(a, grid, smem, s);
+}
+template <bool kFwd>
+void launch_variant(const McArgs& a, int grid, size_t smem, cudaStream_t s) {
+  const bool sig = (a.shared & 4) != 0, one = (a.shared & 2) != 0;
+  if (sig && one) launch_link<kFwd, true, true>(a, grid, smem, s);
+  else if (sig) launch_link<kFwd, true, false>(a, grid, smem, s);
+  else if (one) launch_link<kFwd, false, true>(a, grid, smem, s);
+  else launch_link<kFwd, false, false>(a, grid, smem, s);
+}
+
 }  // namespace
 
 int k_mc_softmax_fwd(const float* loc, const float* fac, const float* diag_raw, const float* sngp_var, float w_het,
@@ -313,9 +336,7 @@ int k_mc_softmax_fwd(const float* loc, const float* fac, const float* diag_raw, 
   if (st != ED2_OK) return st;
   const size_t smem = sizeof(float) * kWarps * (static_cast<size_t>(K) * F + 2 * K);
   const int grid = (B + kWarps - 1) / kWarps;
-  if (K <= 16) mc_softmax_fwd_kernel<16><<<grid, kWarps * 32, smem, s>>>(a);
-  else if (K <= 32) mc_softmax_fwd_kernel<32><<<grid, kWarps * 32, smem, s>>>(a);
-  else mc_softmax_fwd_kernel<64><<<grid, kWarps * 32, smem, s>>>(a);
+  launch_variant<true>(a, grid, smem, s);
   count_launch();
   return check_launch("mc_softmax_fwd");
 }
@@ -331,9 +352,7 @@ int k_mc_softmax_bwd(const float* g, const float* probs_mean, const float* loc, 
   if (st != ED2_OK) return st;
   const size_t smem = sizeof(float) * kWarps * (static_cast<size_t>(K) * F + 3 * K + 32 * (K + F));
   const int grid = (B + kWarps - 1) / kWarps;
-  if (K <= 16) mc_softmax_bwd_kernel<16><<<grid, kWarps * 32, smem, s>>>(a);
-  else if (K <= 32) mc_softmax_bwd_kernel<32><<<grid, kWarps * 32, smem, s>>>(a);
-  else mc_softmax_bwd_kernel<64><<<grid, kWarps * 32, smem, s>>>(a);
+  launch_variant<false>(a, grid, smem, s);
   count_launch();
   return check_launch("mc_softmax_bwd");
 }
