@@ -13,7 +13,8 @@
 // averages to ~1e-7 on the class probabilities), evaluates latent -> softmax in registers and accumulates the
 // class probabilities; nothing of size B x S ever exists.  The backward regenerates the same noise:
 //   u = g / probs_mean / S;  dlatent_s = p_s ∘ (u - <p_s, u>) / T;  dloc = sum_s dlatent_s,
-//   ddiag = sum_s dlatent_s ∘ e_s,  dV[k,f] = sum_s dlatent_s[k] z_s[f]  (per-warp shared-memory outer products).
+//   ddiag = sum_s dlatent_s ∘ e_s,  dV[k,f] = sum_s dlatent_s[k] z_s[f]  (per-warp shared-memory outer products: the 32
+// samples of a round are staged as rows [z | dlatent]; a lane owns one class and four factors).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -77,7 +78,7 @@ __device__ __forceinline__ void draw_sample(const McArgs& a, uint64_t key, long 
 #pragma unroll
   for (int fb = 0; fb < kFMax / 8; ++fb) {
     float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (fb * 8 < a.F) philox_normal8<true>(key, a.noise.stream, static_cast<uint64_t>((base >> 3) + fb), t);
+    if (fb * 8 < a.F) philox_normal8_n<true>(key, a.noise.stream, static_cast<uint64_t>((base >> 3) + fb), a.F - fb * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[fb * 8 + j] = t[j];
   }
@@ -85,7 +86,8 @@ __device__ __forceinline__ void draw_sample(const McArgs& a, uint64_t key, long 
   for (int kb = 0; kb < KMAX / 8; ++kb) {
     float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (kb * 8 < a.K && !(diag_one && kb > 0))
-      philox_normal8<true>(key, a.noise.stream, static_cast<uint64_t>(((base + FP) >> 3) + kb), t);
+      philox_normal8_n<true>(key, a.noise.stream, static_cast<uint64_t>(((base + FP) >> 3) + kb),
+                             diag_one ? 1 : a.K - kb * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) e[kb * 8 + j] = t[j];
   }
@@ -200,19 +202,24 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_fwd_kernel(McArgs a) {
   }
 }
 
+// scratch row of one lane's current sample: z[kFMax] then dlatent[KMAX]; the stride is 4 x odd floats, so the eight lanes
+// of a 16-byte store phase land in eight different bank groups
+template <int KMAX> constexpr int mc_row() { return kFMax + KMAX + 4; }
+template <int KMAX> constexpr int mc_bwd_warp_floats(int K, int F) { return 32 * mc_row<KMAX>() + ((K * F + 3 * K + 3) & ~3); }
+
 template <int KMAX, bool kSigmoid, bool kDiagOne>
 __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
-  extern __shared__ float smem[];
+  extern __shared__ float4 smem4[];
+  constexpr int kRow = mc_row<KMAX>();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kWarps + warp;
   if (b >= a.B) return;
-  const int KF = a.K * a.F, row = a.K + a.F;
-  const int per_warp = KF + 3 * a.K + 32 * row;
-  float* sfac = smem + warp * per_warp;
+  const int KF = a.K * a.F;
+  float* scratch = reinterpret_cast<float*>(smem4) + warp * mc_bwd_warp_floats<KMAX>(a.K, a.F);  // [32][kRow], 16-byte aligned
+  float* sfac = scratch + 32 * kRow;
   float* sloc = sfac + KF;
   float* sdiag = sloc + a.K;
   float* su = sdiag + a.K;
-  float* scratch = su + a.K;  // [32][K + F]: dlatent then z of each lane's current sample
   stage_params(a, b, lane, sloc, sdiag, sfac);
   const float inv_s = 1.f / static_cast<float>(a.S);
   for (int k = lane; k < a.K; k += 32) {
@@ -230,12 +237,23 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
   const uint64_t key = noise_key(a.noise);
   const long long nb = (a.shared & 1) ? 0 : (a.noise.injected != nullptr ? b : noise_row(a.noise, b));
   float dl[KMAX], dd[KMAX];
-  constexpr int kSlots = (KMAX * kFMax + 31) / 32;  // outer-product entries owned by one lane
-  float dv[kSlots];
+  // outer product dV[k][f] = sum_s dlatent_s[k] z_s[f]: a task is one class k and four consecutive factors; task
+  // t = slot * 32 + lane = k * nfg + fg.  Per staged sample a task reads one scalar and one float4 and issues 4 FMAs.
+  constexpr int kSlots = KMAX / 8;  // KMAX * (kFMax / 4) tasks over 32 lanes
+  const int nfg = (a.F + 3) >> 2, ntasks = a.K * nfg;
+  float dv[kSlots][4];
+  int tk[kSlots], tf[kSlots];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) { dl[k] = 0.f; dd[k] = 0.f; }
 #pragma unroll
-  for (int i = 0; i < kSlots; ++i) dv[i] = 0.f;
+  for (int i = 0; i < kSlots; ++i) {
+    const int t = i * 32 + lane;
+    tk[i] = t < ntasks ? t / nfg : -1;
+    tf[i] = t < ntasks ? t - tk[i] * nfg : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dv[i][j] = 0.f;
+  }
+  float4* my_row = reinterpret_cast<float4*>(scratch + lane * kRow);
   const int rounds = (a.S + 31) / 32;
   for (int r = 0; r < rounds; ++r) {
     const int s = r * 32 + lane;
@@ -250,27 +268,40 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
     for (int k = 0; k < KMAX; ++k)
       if (k < a.K && live) dot = fmaf(p[k], su[k], dot);
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < a.K) {
-        const float d = !live ? 0.f : kSigmoid ? a.inv_t * su[k] * p[k] * (1.f - p[k]) : a.inv_t * p[k] * (su[k] - dot);
-        dl[k] += d;
-        dd[k] = fmaf(d, live ? e[k] : 0.f, dd[k]);
-        scratch[lane * row + k] = d;
+    for (int kq = 0; kq < KMAX / 4; ++kq) {
+      if (kq * 4 < a.K) {
+        float d4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kq * 4 + j;
+          float d = 0.f;
+          if (k < a.K && live) d = kSigmoid ? a.inv_t * su[k] * p[k] * (1.f - p[k]) : a.inv_t * p[k] * (su[k] - dot);
+          dl[k] += d;
+          dd[k] = fmaf(d, live ? e[k] : 0.f, dd[k]);
+          d4[j] = d;
+        }
+        my_row[kFMax / 4 + kq] = make_float4(d4[0], d4[1], d4[2], d4[3]);
       }
     }
 #pragma unroll
-    for (int f = 0; f < kFMax; ++f)
-      if (f < a.F) scratch[lane * row + a.K + f] = live ? z[f] : 0.f;
+    for (int fq = 0; fq < kFMax / 4; ++fq)
+      if (fq * 4 < a.F)
+        my_row[fq] = live ? make_float4(z[fq * 4], z[fq * 4 + 1], z[fq * 4 + 2], z[fq * 4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < kSlots; ++i) {
-      const int idx = i * 32 + lane;
-      if (idx < KF) {
-        const int k = idx / a.F, f = idx - k * a.F;
-        float acc = 0.f;
+      if (tk[i] >= 0) {
+        const float* pd = scratch + kFMax + tk[i];
+        const float4* pz = reinterpret_cast<const float4*>(scratch) + tf[i];
 #pragma unroll 8
-        for (int l = 0; l < 32; ++l) acc = fmaf(scratch[l * row + k], scratch[l * row + a.K + f], acc);
-        dv[i] += acc;
+        for (int l = 0; l < 32; ++l) {
+          const float d = pd[l * kRow];
+          const float4 zz = pz[l * (kRow / 4)];
+          dv[i][0] = fmaf(d, zz.x, dv[i][0]);
+          dv[i][1] = fmaf(d, zz.y, dv[i][1]);
+          dv[i][2] = fmaf(d, zz.z, dv[i][2]);
+          dv[i][3] = fmaf(d, zz.w, dv[i][3]);
+        }
       }
     }
     __syncwarp();
@@ -289,8 +320,13 @@ __global__ void __launch_bounds__(kWarps * 32) mc_softmax_bwd_kernel(McArgs a) {
   }
 #pragma unroll
   for (int i = 0; i < kSlots; ++i) {
-    const int idx = i * 32 + lane;
-    if (idx < KF) a.dfac[static_cast<long long>(b) * KF + idx] = dv[i];
+    if (tk[i] >= 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = tf[i] * 4 + j;
+        if (f < a.F) a.dfac[static_cast<long long>(b) * KF + tk[i] * a.F + f] = dv[i][j];
+      }
+    }
   }
 }
 
@@ -350,7 +386,8 @@ int k_mc_softmax_bwd(const float* g, const float* probs_mean, const float* loc, 
   a.probs_mean = const_cast<float*>(probs_mean); a.g = g; a.dloc = dloc; a.dfac = dfac; a.ddiag_raw = ddiag_raw;
   const int st = check(a);
   if (st != ED2_OK) return st;
-  const size_t smem = sizeof(float) * kWarps * (static_cast<size_t>(K) * F + 3 * K + 32 * (K + F));
+  const size_t smem = sizeof(float) * kWarps *
+                      (K <= 16 ? mc_bwd_warp_floats<16>(K, F) : K <= 32 ? mc_bwd_warp_floats<32>(K, F) : mc_bwd_warp_floats<64>(K, F));
   const int grid = (B + kWarps - 1) / kWarps;
   launch_variant<false>(a, grid, smem, s);
   count_launch();

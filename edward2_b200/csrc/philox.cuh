@@ -104,6 +104,24 @@ __device__ __forceinline__ void philox_normal8(uint64_t seed, uint64_t stream, u
   }
 }
 
+// the first n (<= 8) normals of Philox block `block8`, the rest zero: the Box-Muller transform is skipped for the words
+// whose pair lies entirely beyond n (same values as philox_normal8 where defined)
+template <bool kFast = false>
+__device__ __forceinline__ void philox_normal8_n(uint64_t seed, uint64_t stream, uint64_t block8, int n, float (&z)[8]) {
+  uint32_t x[4];
+  philox_block(seed, stream, block8, x);
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    if (2 * w < n) {
+      if constexpr (kFast) box_muller_fast(x[w], z[2 * w], z[2 * w + 1]);
+      else box_muller(x[w], z[2 * w], z[2 * w + 1]);
+    } else {
+      z[2 * w] = 0.f;
+      z[2 * w + 1] = 0.f;
+    }
+  }
+}
+
 // the 4 normals 4*block4 .. 4*block4+3: one half of Philox block block4 / 2 (callers that consume 8 consecutive
 // elements use philox_normal8 and pay for the block once)
 template <bool kFast = false>
