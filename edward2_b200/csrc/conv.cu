@@ -75,6 +75,65 @@ __global__ void __launch_bounds__(kBlock) im2col_vec_kernel(const V* __restrict_
   }
 }
 
+// The same copy with ONE WARP PER PATCH ROW (the kh*kw*C elements of a row are contiguous in `cols`): the row's (b, ho, wo)
+// is decoded once per warp, the tap offsets come from a per-block table and a lane tracks its (tap, channel vector)
+// incrementally — no division per element (the flat kernel above spends ~5 integer divisions per 16-byte store and is
+// instruction-bound at 1.8 TB/s).  Needs kh*kw <= kMaxTaps and fewer than 2^31 rows.
+constexpr int kMaxTaps = 64;
+template <int kVec, typename V>
+__global__ void __launch_bounds__(kBlock) im2col_rows_kernel(const V* __restrict__ x, V* __restrict__ cols, long long cols_ldv,
+                                                            ConvGeom g, const float* __restrict__ fac, unsigned rows) {
+  __shared__ int s_dh[kMaxTaps], s_dw[kMaxTaps];
+  const int taps = g.kh * g.kw;
+  if (threadIdx.x < taps) {
+    const int i = threadIdx.x / g.kw;
+    s_dh[threadIdx.x] = i - g.pt;
+    s_dw[threadIdx.x] = threadIdx.x - i * g.kw - g.pl;
+  }
+  __syncthreads();
+  const int cv = g.C / kVec, per_row = taps * cv;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t0 = lane / cv, c0 = lane - t0 * cv;    // (tap, channel vector) of element `lane` of a row
+  const int dt_ = 32 / cv, dc_ = 32 - dt_ * cv;     // ... and of a step of 32 elements
+  const unsigned wpb = kBlock / 32;
+  for (unsigned m = blockIdx.x * wpb + warp; m < rows; m += gridDim.x * wpb) {
+    const unsigned wo = m % static_cast<unsigned>(g.Wo), bh = m / static_cast<unsigned>(g.Wo);
+    const unsigned ho = bh % static_cast<unsigned>(g.Ho), b = bh / static_cast<unsigned>(g.Ho);
+    const int h0 = static_cast<int>(ho) * g.sh, w0 = static_cast<int>(wo) * g.sw;
+    const V* __restrict__ img = x + static_cast<long long>(b) * g.H * g.W * cv;
+    const float* __restrict__ fb = fac != nullptr ? fac + static_cast<long long>(b) * g.C : nullptr;
+    V* __restrict__ dst = cols + static_cast<long long>(m) * cols_ldv;
+    int t = t0, c = c0;
+    // four elements per lane and pass: the four loads are issued before the first store (a row is only kh*kw*C/kVec
+    // vectors long, so without this a warp has one 512-byte request in flight at a time)
+    for (int rem = lane; rem < per_row; rem += 128) {
+      V v[4];
+      int cu[4];
+      bool in[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = V{};
+        cu[u] = c;
+        in[u] = false;
+        if (rem + 32 * u < per_row) {
+          const int h = h0 + s_dh[t], w = w0 + s_dw[t];
+          in[u] = h >= 0 && h < g.H && w >= 0 && w < g.W;
+          if (in[u]) v[u] = __ldg(img + (h * g.W + w) * cv + c);
+        }
+        t += dt_; c += dc_;
+        if (c >= cv) { c -= cv; ++t; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rem + 32 * u < per_row) {
+          if (fb != nullptr && in[u]) v[u] = scale_vec(v[u], fb + cu[u] * kVec);
+          dst[rem + 32 * u] = v[u];
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) im2col_kernel(const void* __restrict__ x, int dt, void* __restrict__ cols,
                                                        long long cols_ld, ConvGeom g, const float* __restrict__ fac = nullptr) {
   const long long per_row = static_cast<long long>(g.kh) * g.kw * g.C;
@@ -128,26 +187,28 @@ __global__ void __launch_bounds__(kBlock) col2im_kernel(const void* __restrict__
 }
 
 // bf16 patch gradients, C % 8 == 0: one thread owns 8 consecutive channels of one pixel (16-byte loads per tap)
+// kUnit: strides 1 x 1 (no division per tap); the element index is decoded in 32 bits (the launcher checks the range)
+template <bool kUnit>
 __global__ void __launch_bounds__(kBlock) col2im_bf16x8_kernel(const uint4* __restrict__ dcols, long long cols_ldv,
                                                               void* __restrict__ dx, int dx_dt, ConvGeom g) {
-  const int cv = g.C / 8;
-  const long long total = static_cast<long long>(g.B) * g.H * g.W * cv;
-  for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < total; idx += (long long)gridDim.x * kBlock) {
+  const unsigned cv = g.C / 8;
+  const unsigned total = static_cast<unsigned>(g.B) * g.H * g.W * cv;
+  for (unsigned idx = blockIdx.x * kBlock + threadIdx.x; idx < total; idx += gridDim.x * kBlock) {
     const int c = static_cast<int>(idx % cv);
-    long long r = idx / cv;
-    const int w = static_cast<int>(r % g.W);
-    r /= g.W;
-    const int h = static_cast<int>(r % g.H), b = static_cast<int>(r / g.H);
+    unsigned r = idx / cv;
+    const int w = static_cast<int>(r % static_cast<unsigned>(g.W));
+    r /= static_cast<unsigned>(g.W);
+    const int h = static_cast<int>(r % static_cast<unsigned>(g.H)), b = static_cast<int>(r / static_cast<unsigned>(g.H));
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < g.kh; ++i) {
       const int hh = h + g.pt - i;
-      if (hh < 0 || hh % g.sh != 0) continue;
-      const int ho = hh / g.sh;
+      if (hh < 0 || (!kUnit && hh % g.sh != 0)) continue;
+      const int ho = kUnit ? hh : hh / g.sh;
       if (ho >= g.Ho) continue;
       for (int j = 0; j < g.kw; ++j) {
         const int ww = w + g.pl - j;
-        if (ww < 0 || ww % g.sw != 0) continue;
-        const int wo = ww / g.sw;
+        if (ww < 0 || (!kUnit && ww % g.sw != 0)) continue;
+        const int wo = kUnit ? ww : ww / g.sw;
         if (wo >= g.Wo) continue;
         const long long m = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
         const uint4 q = __ldg(dcols + m * cols_ldv + (static_cast<long long>(i) * g.kw + j) * cv + c);
@@ -285,7 +346,14 @@ int k_im2col(const ConvArgs& a, const void* x, int dt, void* cols, long long col
   const int vec = dt == kBF16 ? 8 : 4;
   const bool aligned = g.C % vec == 0 && cols_ld % vec == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(cols) & 15) == 0;
-  if (aligned) {
+  if (aligned && g.kh * g.kw <= kMaxTaps && rows < (1LL << 31) && static_cast<long long>(g.H) * g.W * (g.C / vec) < (1LL << 31)) {
+    const int grid = static_cast<int>(std::min<long long>((rows + 7) / 8, 148 * 8));
+    const unsigned r = static_cast<unsigned>(rows);
+    if (dt == kBF16)
+      im2col_rows_kernel<8, uint4><<<grid, kBlock, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(cols), cols_ld / 8, g, fac, r);
+    else
+      im2col_rows_kernel<4, float4><<<grid, kBlock, 0, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(cols), cols_ld / 4, g, fac, r);
+  } else if (aligned) {
     const long long work = rows * g.kh * g.kw * (g.C / vec);
     if (dt == kBF16)
       im2col_vec_kernel<8, uint4><<<grid_for(work), kBlock, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(cols), cols_ld / 8, g, fac);
@@ -304,8 +372,11 @@ int k_col2im(const ConvArgs& a, const void* dcols, int dt, long long cols_ld, vo
   if (st != ED2_OK) return st;
   const long long total = static_cast<long long>(g.B) * g.H * g.W * g.C;
   if (dt == kBF16 && g.C % 8 == 0 && cols_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dcols) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
-    col2im_bf16x8_kernel<<<grid_for(total / 8), kBlock, 0, s>>>(reinterpret_cast<const uint4*>(dcols), cols_ld / 8, dx, dx_dt, g);
+      (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && total / 8 < (1LL << 31)) {
+    if (g.sh == 1 && g.sw == 1)
+      col2im_bf16x8_kernel<true><<<grid_for(total / 8), kBlock, 0, s>>>(reinterpret_cast<const uint4*>(dcols), cols_ld / 8, dx, dx_dt, g);
+    else
+      col2im_bf16x8_kernel<false><<<grid_for(total / 8), kBlock, 0, s>>>(reinterpret_cast<const uint4*>(dcols), cols_ld / 8, dx, dx_dt, g);
     count_launch();
     return check_launch("col2im");
   }

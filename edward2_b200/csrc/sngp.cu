@@ -240,6 +240,79 @@ __global__ void __launch_bounds__(kBlock) layernorm_bwd_kernel(const void* x, in
   }
 }
 
+// The same backward for cols == NJ * 32 <= 1024 with the row held in registers: x and dy are read ONCE (the kernel above
+// re-reads x four times and issues two shared-memory atomics per element), the dgamma / dbeta column sums of the rows
+// a warp owns accumulate in its registers and reach shared memory once per warp, global memory once per block.
+template <int NJ>
+__global__ void __launch_bounds__(kBlock) layernorm_bwd_rows_kernel(const void* x, int xdt, long long x_ld, const void* dy,
+                                                                    int dydt, long long dy_ld, long long rows,
+                                                                    const float* gamma, float eps, void* dx, int dxdt,
+                                                                    long long dx_ld, float* dgamma, float* dbeta) {
+  constexpr int cols = NJ * 32;
+  __shared__ float sg[cols], sb[cols];
+  const bool want_param = dgamma != nullptr || dbeta != nullptr;
+  if (want_param) {
+    for (int c = threadIdx.x; c < cols; c += kBlock) { sg[c] = 0.f; sb[c] = 0.f; }
+    __syncthreads();
+  }
+  const long long warp = (blockIdx.x * (long long)kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * kBlock) >> 5;
+  float ag[NJ], ab[NJ], gam[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    ag[j] = 0.f; ab[j] = 0.f;
+    gam[j] = gamma != nullptr ? gamma[j * 32 + lane] : 1.f;
+  }
+  for (long long r = warp; r < rows; r += nwarps) {
+    float xv[NJ], dv[NJ];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      xv[j] = ld1(x, xdt, r * x_ld + j * 32 + lane);
+      dv[j] = ld1(dy, dydt, r * dy_ld + j * 32 + lane);
+      s += xv[j];
+    }
+    const float mean = warp_sum(s) / cols;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float d = xv[j] - mean;
+      q += d * d;
+    }
+    const float inv = rsqrtf(warp_sum(q) / cols + eps);
+    float sum_g = 0.f, sum_gx = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float xh = (xv[j] - mean) * inv;
+      const float g = dv[j] * gam[j];
+      sum_g += g;
+      sum_gx += g * xh;
+      ag[j] = fmaf(dv[j], xh, ag[j]);
+      ab[j] += dv[j];
+      xv[j] = xh;
+      dv[j] = g;
+    }
+    const float mg = warp_sum(sum_g) / cols, mgx = warp_sum(sum_gx) / cols;
+    if (dx != nullptr) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) st1(dx, dxdt, r * dx_ld + j * 32 + lane, inv * (dv[j] - mg - xv[j] * mgx));
+    }
+  }
+  if (want_param) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      atomicAdd(&sg[j * 32 + lane], ag[j]);
+      atomicAdd(&sb[j * 32 + lane], ab[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += kBlock) {
+      if (dgamma != nullptr) atomicAdd(dgamma + c, sg[c]);
+      if (dbeta != nullptr) atomicAdd(dbeta + c, sb[c]);
+    }
+  }
+}
+
 __global__ void precision_blend_kernel(float* p, const float* __restrict__ summed, long long n, float momentum,
                                        float inv_batch) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -612,6 +685,18 @@ int k_layernorm_bwd(const void* x, int xdt, long long x_ld, const void* dy, int 
   if (cols > 8192) return set_error(ED2_ERR_BAD_SHAPE, "layernorm_bwd: feature dimension %d > 8192", cols);
   if (dgamma) cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, s);
   if (dbeta) cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, s);
+  if (cols == 128 || cols == 256 || cols == 512 || cols == 1024) {
+    // register-resident rows; a few rows per warp so that the per-block flush of the column sums stays small
+    const int g = static_cast<int>(std::min<long long>(148LL * 2, (rows + 7) / 8));
+#define ED2_LN_ROWS(NJ) layernorm_bwd_rows_kernel<NJ><<<g, kBlock, 0, s>>>(x, xdt, x_ld, dy, dydt, dy_ld, rows, gamma, eps, dx, dxdt, dx_ld, dgamma, dbeta)
+    if (cols == 128) ED2_LN_ROWS(4);
+    else if (cols == 256) ED2_LN_ROWS(8);
+    else if (cols == 512) ED2_LN_ROWS(16);
+    else ED2_LN_ROWS(32);
+#undef ED2_LN_ROWS
+    count_launch();
+    return check_launch("layernorm_bwd");
+  }
   const size_t smem = 2 * sizeof(float) * (size_t)cols;
   // one warp per row and latency-bound: as many blocks per SM as the per-block column accumulators leave room for
   const int per_sm = static_cast<int>(std::max<size_t>(2, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1024))));

@@ -54,11 +54,12 @@ def test_spectral_norm_converges(cuda):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("affine", [True, False])
-def test_layernorm_fwd_bwd(cuda, dtype, affine):
+@pytest.mark.parametrize("d", [264, 128, 512, 1024])   # 128 / 256 / 512 / 1024: register-resident backward kernel
+def test_layernorm_fwd_bwd(cuda, dtype, affine, d):
     from edward2_b200 import functional as F
 
     rng = np.random.default_rng(2)
-    B, d = 200, 264
+    B = 200 if d == 264 else 3000   # several rows per warp on the register-resident path
     x = round_to(rng.standard_normal((B, d)) * 2 + 0.5, dtype)
     g = np.float32(rng.standard_normal(d) * 0.2 + 1).astype(np.float64) if affine else None
     b = np.float32(rng.standard_normal(d) * 0.2).astype(np.float64) if affine else None
