@@ -462,12 +462,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]) * ep.alpha;
 
-        if (split_k > 1) {  // K-slice partial: out += alpha * partial (fp32 atomics), nothing else
+        if (split_k > 1) {  // K-slice partial: out += alpha * partial (fp32 reductions in L2), nothing else
           if (active) {
             float* o = reinterpret_cast<float*>(ep.out) + static_cast<long long>(m) * ep.out_ld + nc;
+            // 16-byte vector reductions where the row is aligned: a quarter of the L2 atomic operations (the scalar form
+            // made the short split-K launches of the SNGP head atomic-bound: 64 K-slices x 65536 elements per tile)
+            if (n_valid == 32 && ((reinterpret_cast<uintptr_t>(ep.out) | (static_cast<uintptr_t>(ep.out_ld) << 2)) & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < n_valid) atomicAdd(o + j, v[j]);
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(v[j]), "f"(v[j + 1]),
+                             "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < n_valid) atomicAdd(o + j, v[j]);
+            }
           }
           continue;
         }
