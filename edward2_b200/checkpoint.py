@@ -23,6 +23,11 @@ _RENAMED = {
 }
 
 
+# constructor argument `<x>_initializer` -> the weight it initialises, where the two names differ
+# (recurrent.py:100-112: `recurrent_initializer` creates the variable `recurrent_kernel`)
+_WEIGHT_OF_INITIALIZER = {"recurrent": "recurrent_kernel"}
+
+
 def _walk(module: nn.Module, path: str):
     for store in (module._parameters, module._buffers):
         for name, t in store.items():
@@ -32,7 +37,8 @@ def _walk(module: nn.Module, path: str):
         if child is None:
             continue
         if cname.endswith("_initializer"):  # TrainableNormal & co.: <layer>/kernel/mean:0
-            sub = f"{path}/{cname[:-len('_initializer')]}"
+            weight = cname[:-len("_initializer")]
+            sub = f"{path}/{_WEIGHT_OF_INITIALIZER.get(weight, weight)}"
         elif isinstance(child, Layer):
             sub = f"{path}/{child.layer_name}"
         else:

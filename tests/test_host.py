@@ -130,6 +130,23 @@ def test_reference_variable_names_roundtrip():
     assert sorted(checkpoint.reference_variables(cov)) == [
         "gp_covariance/gp_covariance_matrix:0", "gp_covariance/gp_precision_matrix:0", "gp_covariance/update_gp_covariance:0"]
 
+    # rank > 1 fast weights carry a leading rank axis (dense.py:518-523)
+    be3 = built(ed.layers.DenseBatchEnsemble(8, rank=3, ensemble_size=2, name="be3"))
+    shapes = {k: tuple(v.shape) for k, v in checkpoint.reference_variables(be3).items()}
+    assert shapes["be3/alpha:0"] == (3, 2, 16) and shapes["be3/gamma:0"] == (3, 2, 8) and shapes["be3/ensemble_bias:0"] == (2, 8)
+    assert be3.get_config()["rank"] == 3
+    # Conv2DRank1 (convolutional.py:1907-1960) and the LSTM cells (recurrent.py:100-130, 543-610)
+    conv = built(ed.layers.Conv2DRank1(8, 3, ensemble_size=2, name="c"), (4, 8, 8, 16))
+    assert {k: tuple(v.shape) for k, v in checkpoint.reference_variables(conv).items()} == {
+        "c/kernel:0": (3, 3, 16, 8), "c/ensemble_bias:0": (2, 8), "c/alpha/mean:0": (2, 16), "c/alpha/stddev:0": (2, 16),
+        "c/gamma/mean:0": (2, 8), "c/gamma/stddev:0": (2, 8)}
+    lstm = built(ed.layers.LSTMCellReparameterization(8, name="l"))
+    assert sorted(checkpoint.reference_variables(lstm)) == [
+        "l/bias:0", "l/kernel/mean:0", "l/kernel/stddev:0", "l/recurrent_kernel/mean:0", "l/recurrent_kernel/stddev:0"]
+    l1 = built(ed.layers.LSTMCellRank1(8, ensemble_size=2, name="l1"))
+    assert {"l1/kernel:0", "l1/recurrent_kernel:0", "l1/alpha/mean:0", "l1/gamma/stddev:0", "l1/recurrent_alpha/mean:0",
+            "l1/recurrent_gamma/stddev:0"} <= set(checkpoint.reference_variables(l1))
+
     src = checkpoint.reference_variables(dense)
     other = built(ed.layers.DenseReparameterization(8, name="dense", seed=7))
     numpy_vars = {k: (v + 1.0).numpy() for k, v in src.items()}  # arrays, as a reference checkpoint reader yields them
