@@ -3,16 +3,24 @@
 TEST INFRASTRUCTURE ONLY.  Nothing under `edward2_b200/` may import this package; only `tests/`,
 `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of `bench.py` do.
 
-PARITY STATUS: **parity unpinned for sampled values**.  The reference (google/edward2 0.0.3) is pure Python over
-TensorFlow / TFP / JAX / Flax, none of which is installed here or on the GPU box, so it cannot be executed to
-produce golden vectors, and its own tests hold no golden vectors or RNG-stream pins for this path
-(SURVEY.md §8c).  What *is* pinned:
+PARITY STATUS: **pinned to the reference for the deterministic arithmetic; unpinned for sampled VALUES** (the reference
+holds no RNG-stream pins for this path).  The reference (google/edward2 0.0.3) is pure Python over TensorFlow / TFP /
+JAX / Flax, none of which is installed here or on the GPU box.  Its JAX files are pure `jnp` / `lax.linalg` code, so
+`tests/golden/make_reference_golden.py` EXECUTES THEM UNMODIFIED under NumPy-backed stand-ins of jax / flax
+(`tests/golden/refstub/`) and commits their outputs as `tests/golden/reference_vectors.npz`:
+  * `edward2/jax/nn/dense.py` DenseBatchEnsemble, `random_feature.py` RandomFourierFeatures /
+    LaplaceRandomFeatureCovariance / RandomFeatureGaussianProcess / MCSigmoidDenseFASNGP(BE), `normalization.py`
+    SpectralNormalization, `utils.py` mean_field_logits, `heteroscedastic_lib.py` MCSoftmaxDenseFA / MCSigmoidDenseFA
+    (with the draws of their `jax.random.normal` calls recorded) — `tests/test_oracle.py::test_reference_*` checks this
+    oracle against those vectors at 1e-12, `tests/test_gpu_reference_golden.py` checks the CUDA path against them.
+The TF-only classes (DenseRank1, DenseFlipout, DenseReparameterization, the Conv2D variants, the LSTM cells) cannot be
+run here; for them, and for all sampled layers, what is pinned is:
   * the Philox4x32-10 generator against the three Random123 known-answer vectors (tests/golden/philox_kat.json);
   * `mean_field_logits` against the reference's known-answer tests (edward2/tensorflow/layers/utils_test.py:201-241,
     edward2/jax/nn/utils_test.py:28-68);
   * every algebraic identity the reference's tests assert (vectorised == per-member loop, exact / momentum
     precision updates, (1+ridge)·I on orthogonal data, diag == diag(full), spectral norm -> c, KL >= 0 and linear
-    in scale_factor, softplus(-3) initial scale) — restated in tests/test_oracle_*.py;
+    in scale_factor, softplus(-3) initial scale, DenseRank1 with deterministic fast weights == DenseBatchEnsemble);
   * closed-form gradients against torch.autograd in float64.
 Every function cites the reference file:line it follows; all randomness is an explicit argument.
 """
