@@ -13,8 +13,14 @@ JAX / Flax, none of which is installed here or on the GPU box.  Its JAX files ar
     SpectralNormalization, `utils.py` mean_field_logits, `heteroscedastic_lib.py` MCSoftmaxDenseFA / MCSigmoidDenseFA
     (with the draws of their `jax.random.normal` calls recorded) — `tests/test_oracle.py::test_reference_*` checks this
     oracle against those vectors at 1e-12, `tests/test_gpu_reference_golden.py` checks the CUDA path against them.
-The TF-only classes (DenseRank1, DenseFlipout, DenseReparameterization, the Conv2D variants, the LSTM cells) cannot be
-run here; for them, and for all sampled layers, what is pinned is:
+  * `edward2/tensorflow/layers/dense.py` (with `layers/utils.py`, `initializers.py`, `regularizers.py`, `constraints.py`)
+    is executed the same way under NumPy-backed tensorflow / tfp stand-ins (`tests/golden/refstub_tf/`,
+    `tests/golden/make_reference_golden_tf.py` -> `reference_vectors_tf.npz`): DenseReparameterization, DenseFlipout
+    (with its Uniform[-1, 3) sign_output), DenseBatchEnsemble rank 1 / rank 3 and DenseRank1 (clip bounds, additive
+    perturbations, sampled bias) with every draw recorded, plus TrainableNormal / Softplus / NormalKLDivergence —
+    `tests/test_oracle.py::test_reference_tf_*` checks `oracle/dense.py` against them at 1e-12.
+The Conv2D variants and the LSTM cells (TF-only, Keras conv / RNN machinery) are not executed; for them, and for the
+VALUES of all native samplers, what is pinned is:
   * the Philox4x32-10 generator against the three Random123 known-answer vectors (tests/golden/philox_kat.json);
   * `mean_field_logits` against the reference's known-answer tests (edward2/tensorflow/layers/utils_test.py:201-241,
     edward2/jax/nn/utils_test.py:28-68);

@@ -1,0 +1,177 @@
+"""Generates tests/golden/reference_vectors_tf.npz by EXECUTING THE UNMODIFIED REFERENCE SOURCE FILES
+
+    /root/reference/edward2/tensorflow/layers/dense.py        (DenseReparameterization, DenseFlipout,
+                                                                DenseBatchEnsemble, DenseRank1)
+    /root/reference/edward2/tensorflow/layers/utils.py        (the add_weight decorator)
+    /root/reference/edward2/tensorflow/{initializers,regularizers,constraints}.py
+                                                               (TrainableNormal, NormalKLDivergence, Softplus)
+
+under the NumPy-backed stand-ins of tensorflow / tensorflow_probability / ed.RandomVariable in tests/golden/refstub_tf/
+(TensorFlow and TFP are not installable here; see refstub_tf/README.md for what the stand-ins restate).  Every statement
+of the layers' build / call / regulariser code that runs is the reference's; the stand-ins evaluate it in float64 and
+record every random draw (standard normals of Normal.sample, tf.random.uniform) next to the outputs.  The fixture pins
+`oracle/dense.py` to the reference's TF classes (tests/test_oracle.py::test_reference_tf_*); the CUDA path is checked
+against that oracle on injected noise (tests/test_gpu_dense_ops.py, tests/test_gpu_layers.py).
+
+Run here (the GPU box has no /root/reference):  python tests/golden/make_reference_golden_tf.py
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/edward2/tensorflow"
+OUT = os.path.join(HERE, "reference_vectors_tf.npz")
+
+
+def load_reference():
+    sys.path.insert(0, os.path.join(HERE, "refstub_tf"))
+    import ed_random_variable as rv  # stand-in
+    import tensorflow as tf  # noqa: F401  (stand-in)
+    import tensorflow_probability as tfp  # noqa: F401  (stand-in)
+
+    for name in ("edward2", "edward2.tensorflow", "edward2.tensorflow.layers"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    pkg = sys.modules["edward2.tensorflow"]
+    for name in ("random_variable", "generated_random_variables"):
+        sys.modules[f"edward2.tensorflow.{name}"] = rv
+        setattr(pkg, name, rv)
+    mods = {}
+    for full, rel in (("edward2.tensorflow.constraints", "constraints.py"),
+                      ("edward2.tensorflow.regularizers", "regularizers.py"),
+                      ("edward2.tensorflow.initializers", "initializers.py"),
+                      ("edward2.tensorflow.layers.utils", "layers/utils.py"),
+                      ("edward2.tensorflow.layers.dense", "layers/dense.py")):
+        spec = importlib.util.spec_from_file_location(full, os.path.join(REF, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[full] = m
+        spec.loader.exec_module(m)
+        parent, leaf = full.rsplit(".", 1)
+        setattr(sys.modules[parent], leaf, m)
+        mods[leaf] = m
+    return mods
+
+
+def main():
+    mods = load_reference()
+    import tensorflow as tf
+    import tensorflow_probability as tfp
+
+    dense = mods["dense"]
+    rng = np.random.default_rng(20261021)
+    tf.random._rng = np.random.default_rng(7)
+    out = {}
+
+    uniforms = []
+    real_uniform = tf.random.uniform
+
+    def recording_uniform(*args, **kwargs):
+        v = real_uniform(*args, **kwargs)
+        uniforms.append(np.array(v, dtype=np.float64))
+        return v
+
+    tf.random.uniform = recording_uniform
+
+    def set_normal(init, mean, rho):
+        """Overwrite the variables of a built TrainableNormal initializer (mean, pre-softplus stddev)."""
+        init.mean, init.stddev = tf._t(mean), tf._t(rho)
+
+    # ---- a2 DenseReparameterization (dense.py:33-83) + a5-a7: add_weight, TrainableNormal, Softplus, NormalKLDivergence
+    B, I, O = 6, 10, 7
+    layer = dense.DenseReparameterization(O, activation="relu", bias_initializer="zeros")
+    x = rng.standard_normal((B, I))
+    layer(x)  # builds: kernel is an ed.RandomVariable made by the trainable initializer
+    mu, rho = rng.standard_normal((I, O)) * 0.3, rng.standard_normal((I, O)) * 0.5 - 2.0
+    set_normal(layer.kernel_initializer, mu, rho)
+    layer.bias = tf._t(rng.standard_normal(O) * 0.2)
+    del tfp.recorded[:]
+    y = layer(x)
+    eps = tfp.recorded[-1]  # the draw behind the kernel that call() used (call_weights re-samples, dense.py:75-78)
+    kl = layer.losses
+    assert len(kl) == 1
+    out.update(rp_x=x, rp_mu=mu, rho_rp=rho, rp_eps=eps, rp_bias=np.asarray(layer.bias), rp_y=y, rp_kl=kl[0],
+               rp_kernel=np.asarray(layer.kernel.value), rp_stddev=np.asarray(layer.kernel.distribution.stddev()))
+    # the regulariser with a non-default prior and scale_factor (regularizers.py:166-186)
+    reg = mods["regularizers"].NormalKLDivergence(mean=0.3, stddev=0.7, scale_factor=1.0 / 50000.0)
+    out.update(rp_kl_prior=reg(layer.kernel), rp_kl_prior_args=np.array([0.3, 0.7, 1.0 / 50000.0]))
+    # 3-D inputs go through Keras Dense's tensordot branch
+    x3 = rng.standard_normal((2, 3, I))
+    del tfp.recorded[:]
+    y3 = layer(x3)
+    out.update(rp_x3=x3, rp_eps3=tfp.recorded[-1], rp_y3=y3)
+
+    # ---- a3 DenseFlipout (dense.py:227-285): int32 sign_input, FLOAT sign_output (Uniform[-1, 3) for float inputs)
+    layer = dense.DenseFlipout(O, activation="relu")
+    x = tf._t(rng.standard_normal((B, I)))
+    layer(x)
+    mu, rho = rng.standard_normal((I, O)) * 0.3, rng.standard_normal((I, O)) * 0.5 - 2.0
+    set_normal(layer.kernel_initializer, mu, rho)
+    layer.bias = tf._t(rng.standard_normal(O) * 0.2)
+    del tfp.recorded[:], uniforms[:]
+    y = layer(x)
+    assert len(uniforms) == 2
+    out.update(fo_x=np.asarray(x), fo_mu=mu, fo_rho=rho, fo_eps=tfp.recorded[-1], fo_bias=np.asarray(layer.bias),
+               fo_sign_in=2 * uniforms[0] - 1, fo_sign_out=2 * uniforms[1] - 1, fo_y=y)
+    x3 = tf._t(rng.standard_normal((2, 3, I)))
+    del tfp.recorded[:], uniforms[:]
+    y3 = layer(x3)
+    out.update(fo_x3=np.asarray(x3), fo_eps3=tfp.recorded[-1], fo_sign_in3=2 * uniforms[0] - 1,
+               fo_sign_out3=2 * uniforms[1] - 1, fo_y3=y3)
+
+    # ---- a1 DenseBatchEnsemble, TF class (dense.py:470-607): rank 1 and rank 3
+    E, n = 3, 4
+    for tag, rank in (("be", 1), ("be_r3", 3)):
+        layer = dense.DenseBatchEnsemble(O, rank=rank, ensemble_size=E, activation="relu")
+        x = rng.standard_normal((E * n, I))
+        layer(x)
+        lead = (rank,) if rank > 1 else ()
+        layer.alpha = tf._t(1.0 + 0.4 * rng.standard_normal(lead + (E, I)))
+        layer.gamma = tf._t(1.0 + 0.4 * rng.standard_normal(lead + (E, O)))
+        layer.ensemble_bias = tf._t(0.2 * rng.standard_normal((E, O)))
+        y = layer(x)
+        out.update({f"{tag}_x": x, f"{tag}_kernel": np.asarray(layer.kernel), f"{tag}_alpha": np.asarray(layer.alpha),
+                    f"{tag}_gamma": np.asarray(layer.gamma), f"{tag}_bias": np.asarray(layer.ensemble_bias), f"{tag}_y": y})
+
+    # ---- a4 DenseRank1 (dense.py:991-1175): per-example sampled fast weights [n, E, dim] -> transposed to [E, n, dim],
+    # clip bounds, multiplicative / additive perturbations, deterministic / sampled ensemble bias, KL of the fast weights
+    for tag, additive, sampled_bias, lo, hi in (("r1", False, False, 0.6, 1.5), ("r1_add", True, False, -10, 10),
+                                                ("r1_bias", False, True, -10, 10)):
+        layer = dense.DenseRank1(O, activation="relu", ensemble_size=E, use_additive_perturbation=additive,
+                                 min_perturbation_value=lo, max_perturbation_value=hi,
+                                 bias_initializer="trainable_normal" if sampled_bias else "zeros")
+        x = rng.standard_normal((E * n, I))
+        layer(x)
+        mu_r, rho_r = 1.0 + 0.3 * rng.standard_normal((E, I)), rng.standard_normal((E, I)) * 0.3 - 1.5
+        mu_s, rho_s = 1.0 + 0.3 * rng.standard_normal((E, O)), rng.standard_normal((E, O)) * 0.3 - 1.5
+        set_normal(layer.alpha_initializer, mu_r, rho_r)
+        set_normal(layer.gamma_initializer, mu_s, rho_s)
+        if sampled_bias:
+            mu_b, rho_b = 0.2 * rng.standard_normal((E, O)), rng.standard_normal((E, O)) * 0.3 - 2.0
+            set_normal(layer.ensemble_bias_initializer, mu_b, rho_b)
+            out.update({f"{tag}_rho_b": rho_b})
+        else:
+            mu_b = 0.2 * rng.standard_normal((E, O))
+            layer.ensemble_bias = tf._t(mu_b)
+        del tfp.recorded[:]
+        y = layer(x)
+        # Normal.sample(examples_per_model) draws are the [n, E, dim] ones; each initializer call also makes one [E, dim] draw
+        per_example = [r for r in tfp.recorded if r.ndim == 3]
+        assert len(per_example) == (3 if sampled_bias else 2)
+        # reference layout eps[i, e, :] -> member-major rows b = e * n + i
+        to_rows = lambda a: np.transpose(a, (1, 0, 2)).reshape(E * n, -1)  # noqa: E731
+        out.update({f"{tag}_x": x, f"{tag}_kernel": np.asarray(layer.kernel), f"{tag}_mu_r": mu_r, f"{tag}_rho_r": rho_r,
+                    f"{tag}_mu_s": mu_s, f"{tag}_rho_s": rho_s, f"{tag}_bias": mu_b, f"{tag}_eps_r": to_rows(per_example[0]),
+                    f"{tag}_eps_s": to_rows(per_example[1]), f"{tag}_y": y, f"{tag}_clip": np.array([lo, hi], dtype=np.float64),
+                    f"{tag}_kl": np.array([float(np.asarray(v)) for v in layer.losses])})
+        if sampled_bias:
+            out[f"{tag}_eps_b"] = to_rows(per_example[2])
+
+    np.savez_compressed(OUT, **{k: np.asarray(a, dtype=np.float64) for k, a in out.items()})
+    print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")
+
+
+if __name__ == "__main__":
+    main()

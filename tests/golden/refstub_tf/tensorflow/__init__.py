@@ -1,0 +1,374 @@
+"""`tensorflow`: a NumPy-backed stand-in (float64) with just the surface that the reference files
+
+    edward2/tensorflow/layers/dense.py, layers/utils.py, initializers.py, regularizers.py, constraints.py
+
+touch when DenseReparameterization / DenseFlipout / DenseBatchEnsemble / DenseRank1 are built and called.  TensorFlow is
+not installable here; the stand-in exists so that tests/golden/make_reference_golden_tf.py can EXECUTE THOSE FILES
+UNMODIFIED and record their outputs (see ../README.md).  Third-party behaviour restated here, and only here:
+tf.keras.layers.Dense (`matmul(inputs, kernel)`, tensordot for rank > 2, bias_add, activation), the Keras initializers
+that the reference falls back to by name, and the op semantics of reshape / tile / transpose / clip_by_value / ...
+(their NumPy equivalents).  Randomness comes from `random._rng` (a seeded numpy Generator); tf.random.uniform keeps
+TensorFlow's dtype-dependent behaviour — integer dtypes draw integers in [minval, maxval), float dtypes draw reals in
+[minval, maxval) — which is what gives DenseFlipout.sign_output its Uniform[-1, 3) values (dense.py:266-270)."""
+import contextlib
+import sys
+import types
+
+import numpy as np
+
+float32, float64, int32, int64 = "float32", "float64", "int32", "int64"
+newaxis = None
+
+
+class TensorShape(tuple):
+    def __new__(cls, dims=()):
+        if isinstance(dims, TensorShape):
+            return dims
+        return super().__new__(cls, tuple(int(d) for d in dims))
+
+    @property
+    def ndims(self):
+        return len(self)
+
+    rank = ndims
+
+    def as_list(self):
+        return list(self)
+
+    def __getitem__(self, i):
+        out = tuple.__getitem__(self, i)
+        return TensorShape(out) if isinstance(i, slice) else out
+
+
+class Tensor(np.ndarray):
+    """ndarray whose `.shape` is a TensorShape (the reference reads `inputs.shape.ndims`)."""
+
+    @property
+    def shape(self):
+        return TensorShape(np.ndarray.shape.__get__(self))
+
+
+def _t(x, dtype=None):
+    if hasattr(x, "value") and hasattr(x, "distribution"):  # an ed.RandomVariable stand-in
+        x = x.value
+    kind = np.int64 if (dtype is not None and "int" in str(dtype)) else np.float64
+    a = np.asarray(x)
+    if dtype is None and a.dtype.kind in "iub":
+        kind = a.dtype
+    return np.array(a, dtype=kind).view(Tensor)
+
+
+convert_to_tensor = constant = _t
+
+
+def is_tensor(x):
+    return isinstance(x, np.ndarray)
+
+
+def get_static_value(x):
+    return np.asarray(x)
+
+
+def shape(x):
+    return np.array(np.shape(np.asarray(_t(x))), dtype=np.int64)
+
+
+def cast(x, dtype):
+    return _t(x, dtype)
+
+
+def reshape(x, shp):
+    return _t(np.reshape(_t(x), [int(s) for s in np.asarray(shp).tolist()]))
+
+
+def tile(x, multiples):
+    return _t(np.tile(_t(x), [int(m) for m in np.asarray(multiples).tolist()]))
+
+
+def expand_dims(x, axis):
+    return _t(np.expand_dims(_t(x), axis))
+
+
+def transpose(x, perm=None):
+    return _t(np.transpose(_t(x), perm))
+
+
+def clip_by_value(x, lo, hi):
+    return _t(np.clip(_t(x), lo, hi))
+
+
+def matmul(a, b):
+    return _t(np.matmul(_t(a), _t(b)))
+
+
+def tensordot(a, b, axes):
+    return _t(np.tensordot(_t(a), _t(b), axes))
+
+
+def concat(values, axis):
+    return np.concatenate([np.atleast_1d(np.asarray(v)) for v in values], axis)
+
+
+def stack(values, axis=0):
+    return _t(np.stack([_t(v) for v in values], axis))
+
+
+def zeros(shp, dtype=None):
+    return _t(np.zeros([int(s) for s in np.asarray(shp).tolist()]))
+
+
+def zeros_like(x):
+    return _t(np.zeros_like(_t(x)))
+
+
+def broadcast_to(x, shp):
+    return _t(np.broadcast_to(np.asarray(x, dtype=np.float64), tuple(int(s) for s in shp)))
+
+
+def reduce_sum(x, axis=None, keepdims=False):
+    return _t(np.sum(_t(x), axis=axis, keepdims=keepdims))
+
+
+def reduce_mean(x, axis=None, keepdims=False):
+    return _t(np.mean(_t(x), axis=axis, keepdims=keepdims))
+
+
+def square(x):
+    return _t(np.square(_t(x)))
+
+
+def sqrt(x):
+    return _t(np.sqrt(_t(x)))
+
+
+def exp(x):
+    return _t(np.exp(_t(x)))
+
+
+def abs(x):  # noqa: A001
+    return _t(np.abs(_t(x)))
+
+
+def maximum(a, b):
+    return _t(np.maximum(_t(a), b))
+
+
+def multiply(a, b):
+    return _t(_t(a) * _t(b))
+
+
+@contextlib.contextmanager
+def name_scope(name):
+    yield
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+# ---- tf.math / tf.nn / tf.linalg / tf.random
+def _softplus(x):
+    x = _t(x)
+    return _t(np.where(x > 30, x, np.log1p(np.exp(np.minimum(x, 30)))))
+
+
+math = _module("tensorflow.math", log=lambda x: _t(np.log(_t(x))), reduce_mean=reduce_mean, softplus=_softplus)
+nn = _module("tensorflow.nn", relu=lambda x: _t(np.maximum(_t(x), 0.0)), softplus=_softplus,
+             bias_add=lambda v, b: _t(_t(v) + _t(b)),
+             softmax=lambda x, axis=-1: _t(np.exp(_t(x) - np.max(_t(x), axis, keepdims=True))
+                                           / np.sum(np.exp(_t(x) - np.max(_t(x), axis, keepdims=True)), axis, keepdims=True)))
+linalg = _module("tensorflow.linalg", matmul=matmul)
+
+
+def _uniform(shape, minval=0, maxval=None, dtype=float32, seed=None):
+    shp = tuple(int(s) for s in np.asarray(shape).tolist())
+    if "int" in str(dtype):
+        return random._rng.integers(minval, maxval, size=shp).view(Tensor)
+    return _t(random._rng.uniform(minval, 1.0 if maxval is None else maxval, size=shp))
+
+
+def _normal(shape, mean=0.0, stddev=1.0, dtype=float32, seed=None):
+    shp = tuple(int(s) for s in np.asarray(shape).tolist())
+    return _t(mean + stddev * random._rng.standard_normal(shp))
+
+
+random = _module("tensorflow.random", uniform=_uniform, normal=_normal, _rng=np.random.default_rng(0))
+
+
+# ---- tf.keras
+class _Initializer:
+    def get_config(self):
+        return {}
+
+
+class _Zeros(_Initializer):
+    def __call__(self, shape, dtype=None, **kw):
+        return zeros(shape)
+
+
+class _Ones(_Initializer):
+    def __call__(self, shape, dtype=None, **kw):
+        return _t(np.ones([int(s) for s in shape]))
+
+
+class _TruncatedNormal(_Initializer):
+    def __init__(self, mean=0.0, stddev=0.05, seed=None):
+        self.mean, self.stddev, self.seed = mean, stddev, seed
+
+    def __call__(self, shape, dtype=None, **kw):
+        shp = tuple(int(s) for s in shape)
+        z = random._rng.standard_normal(shp)
+        while np.any(np.abs(z) > 2.0):  # Keras: redraw beyond two standard deviations
+            bad = np.abs(z) > 2.0
+            z[bad] = random._rng.standard_normal(int(bad.sum()))
+        return _t(self.mean + self.stddev * z)
+
+
+class _VarianceScaling(_Initializer):
+    def __init__(self, scale=1.0, mode="fan_in", distribution="truncated_normal", seed=None):
+        self.scale, self.mode, self.distribution, self.seed = scale, mode, distribution, seed
+
+    def __call__(self, shape, dtype=None, **kw):
+        shp = tuple(int(s) for s in shape)
+        fan_in, fan_out = (shp[-2], shp[-1]) if len(shp) >= 2 else (shp[0], shp[0])
+        n = {"fan_in": fan_in, "fan_out": fan_out, "fan_avg": (fan_in + fan_out) / 2.0}[self.mode]
+        if self.distribution == "uniform":
+            lim = np.sqrt(3.0 * self.scale / n)
+            return _t(random._rng.uniform(-lim, lim, shp))
+        return _t(np.sqrt(self.scale / n) * random._rng.standard_normal(shp))
+
+
+class _Orthogonal(_Initializer):
+    def __init__(self, gain=1.0, seed=None):
+        self.gain, self.seed = gain, seed
+
+
+def _get_initializer(identifier):
+    if identifier is None or callable(identifier):
+        return identifier
+    table = {"zeros": _Zeros, "zero": _Zeros, "ones": _Ones,
+             "glorot_uniform": lambda: _VarianceScaling(1.0, "fan_avg", "uniform"),
+             "he_normal": lambda: _VarianceScaling(2.0, "fan_in", "truncated_normal"),
+             "glorot_normal": lambda: _VarianceScaling(1.0, "fan_avg", "truncated_normal")}
+    return table[str(identifier)]()
+
+
+class _Regularizer:
+    pass
+
+
+class _Constraint:
+    pass
+
+
+def _get_plain(identifier):
+    if identifier is None or callable(identifier):
+        return identifier
+    raise ValueError(f"stand-in keras has no object named {identifier!r}")
+
+
+def _activation(identifier):
+    if identifier is None or identifier == "linear":
+        return None if identifier is None else (lambda x: x)
+    if callable(identifier):
+        return identifier
+    return {"relu": nn.relu}[identifier]
+
+
+def _serialize(obj):
+    return None if obj is None else {"class_name": type(obj).__name__, "config": obj.get_config() if hasattr(obj, "get_config") else {}}
+
+
+def _deserialize(config, module_objects=None, custom_objects=None, printable_module_name="object"):
+    name = config["class_name"]
+    cls = (module_objects or {}).get(name)
+    if cls is None or not callable(cls):
+        raise ValueError(f"Unknown {printable_module_name}: {name}")
+    return cls(**config.get("config", {}))
+
+
+class Layer:
+    def __init__(self, trainable=True, name=None, dtype=None, **kwargs):
+        self.trainable, self.name, self.dtype, self.built = trainable, name, dtype or float32, False
+        self.compute_dtype = self.dtype
+        self._loss_fns = []
+
+    def add_weight(self, name=None, shape=None, dtype=None, initializer=None, regularizer=None, trainable=True,
+                   constraint=None, **kwargs):
+        w = _t(_get_initializer(initializer)(shape, dtype))
+        if regularizer is not None:
+            self._loss_fns.append(lambda: regularizer(w))
+        return w
+
+    def add_loss(self, fn):
+        self._loss_fns.append(fn)
+
+    @property
+    def losses(self):
+        return [f() if callable(f) else f for f in self._loss_fns]
+
+    def build(self, input_shape):
+        self.built = True
+
+    def __call__(self, inputs, *args, **kwargs):
+        if not self.built:
+            self.build(_t(inputs).shape)
+        return self.call(inputs, *args, **kwargs)
+
+    def get_config(self):
+        return {"name": self.name, "dtype": self.dtype}
+
+
+class Dense(Layer):
+    """tf.keras.layers.Dense, restated: kernel [in, units], bias [units]; call = matmul / tensordot, bias_add, activation."""
+
+    def __init__(self, units, activation=None, use_bias=True, kernel_initializer="glorot_uniform", bias_initializer="zeros",
+                 kernel_regularizer=None, bias_regularizer=None, activity_regularizer=None, kernel_constraint=None,
+                 bias_constraint=None, **kwargs):
+        super().__init__(**kwargs)
+        self.units, self.activation, self.use_bias = int(units), _activation(activation), use_bias
+        self.kernel_initializer, self.bias_initializer = _get_initializer(kernel_initializer), _get_initializer(bias_initializer)
+        self.kernel_regularizer, self.bias_regularizer = kernel_regularizer, bias_regularizer
+        self.activity_regularizer = activity_regularizer
+        self.kernel_constraint, self.bias_constraint = kernel_constraint, bias_constraint
+
+    def build(self, input_shape):
+        last = int(TensorShape(input_shape)[-1])
+        self.kernel = self.add_weight("kernel", shape=[last, self.units], initializer=self.kernel_initializer,
+                                      regularizer=self.kernel_regularizer, constraint=self.kernel_constraint,
+                                      dtype=self.dtype, trainable=True)
+        self.bias = self.add_weight("bias", shape=[self.units], initializer=self.bias_initializer,
+                                    regularizer=self.bias_regularizer, constraint=self.bias_constraint, dtype=self.dtype,
+                                    trainable=True) if self.use_bias else None
+        self.built = True
+
+    def call(self, inputs):
+        x = _t(inputs)
+        out = matmul(x, self.kernel) if x.ndim == 2 else tensordot(x, self.kernel, [[x.ndim - 1], [0]])
+        if self.use_bias:
+            out = nn.bias_add(out, self.bias)
+        return self.activation(out) if self.activation is not None else out
+
+
+_layers = _module("tensorflow.keras.layers", Layer=Layer, Dense=Dense)
+_initializers = _module("tensorflow.keras.initializers", Initializer=_Initializer, Zeros=_Zeros, Ones=_Ones,
+                        TruncatedNormal=_TruncatedNormal, VarianceScaling=_VarianceScaling, Orthogonal=_Orthogonal,
+                        get=_get_initializer, he_normal=lambda seed=None: _VarianceScaling(2.0, "fan_in", "truncated_normal"),
+                        glorot_normal=lambda seed=None: _VarianceScaling(1.0, "fan_avg", "truncated_normal"),
+                        GlorotNormal=lambda seed=None: _VarianceScaling(1.0, "fan_avg", "truncated_normal"),
+                        glorot_uniform=lambda seed=None: _VarianceScaling(1.0, "fan_avg", "uniform"),
+                        zeros=_Zeros, ones=_Ones, Constant=lambda value=0.0: (lambda shape, dtype=None, **kw: _t(np.full([int(s) for s in shape], value))))
+_regularizers = _module("tensorflow.keras.regularizers", Regularizer=_Regularizer, get=_get_plain)
+_constraints = _module("tensorflow.keras.constraints", Constraint=_Constraint, get=_get_plain)
+_activations = _module("tensorflow.keras.activations", get=_activation, serialize=lambda a: getattr(a, "__name__", None),
+                       relu=nn.relu, linear=lambda x: x)
+_backend = _module("tensorflow.keras.backend", epsilon=lambda: 1e-7)
+_legacy = _module("tensorflow.keras.utils.legacy", serialize_keras_object=_serialize, deserialize_keras_object=_deserialize)
+_utils = _module("tensorflow.keras.utils", legacy=_legacy)
+keras = _module("tensorflow.keras", layers=_layers, initializers=_initializers, regularizers=_regularizers,
+                constraints=_constraints, activations=_activations, backend=_backend, utils=_utils)
+_v1 = _module("tensorflow.compat.v1")
+compat = _module("tensorflow.compat", v1=_v1)

@@ -750,3 +750,75 @@ def test_reference_mc_sigmoid_dense_fa_sngp(ref, tag):
     _close(probs, ref[f"{tag}_eval_probs"])
     _close(log_probs, ref[f"{tag}_eval_log_probs"])
     _close(logits, ref[f"{tag}_eval_logits"])
+
+
+# -------------------------------------------------------------------------------------- the reference's TF classes, executed
+# edward2/tensorflow/layers/dense.py (+ layers/utils.py add_weight, initializers.py TrainableNormal, regularizers.py
+# NormalKLDivergence, constraints.py Softplus) run UNMODIFIED under NumPy-backed tensorflow / tfp stand-ins with every random
+# draw recorded (tests/golden/make_reference_golden_tf.py).  These tests pin oracle/dense.py to those classes.
+@pytest.fixture(scope="module")
+def ref_tf():
+    return np.load(os.path.join(GOLD, "reference_vectors_tf.npz"))
+
+
+def test_reference_tf_dense_reparameterization(ref_tf):
+    """dense.py:33-83: kernel = mean + (softplus(raw stddev) + 1e-7) * eps re-sampled by call_weights, Keras Dense call (2-D
+    matmul and the tensordot branch for 3-D inputs); the layer's loss is NormalKLDivergence of the kernel variable."""
+    r = ref_tf
+    _close(od.stddev(r["rho_rp"]), r["rp_stddev"])
+    y, w = od.reparam_fwd(r["rp_x"], r["rp_mu"], r["rho_rp"], r["rp_eps"], r["rp_bias"], "relu")
+    _close(w, r["rp_kernel"])
+    _close(y, r["rp_y"])
+    _close(od.normal_kl(r["rp_mu"], r["rho_rp"]), r["rp_kl"])
+    m, s, f = r["rp_kl_prior_args"]
+    _close(od.normal_kl(r["rp_mu"], r["rho_rp"], prior_mean=m, prior_std=s, scale_factor=f), r["rp_kl_prior"])
+    x3 = r["rp_x3"]
+    y3, _ = od.reparam_fwd(x3.reshape(-1, x3.shape[-1]), r["rp_mu"], r["rho_rp"], r["rp_eps3"], r["rp_bias"], "relu")
+    _close(y3.reshape(r["rp_y3"].shape), r["rp_y3"])
+
+
+def test_reference_tf_dense_flipout(ref_tf):
+    """dense.py:255-285 as executed: int32 sign_input in {-1, +1}, FLOAT sign_output = 2 U[0, 2) - 1 in [-1, 3) (the
+    reference's dtype quirk), perturbation = kernel - mean, 2-D matmul and 3-D tensordot branches."""
+    r = ref_tf
+    assert set(np.unique(r["fo_sign_in"])) <= {-1.0, 1.0}
+    so = r["fo_sign_out"]
+    assert so.min() >= -1.0 and so.max() < 3.0 and len(np.unique(so)) > 2  # real-valued, not a sign tensor
+    y, _ = od.flipout_fwd(r["fo_x"], r["fo_mu"], r["fo_rho"], r["fo_eps"], r["fo_sign_in"], so, r["fo_bias"], "relu")
+    _close(y, r["fo_y"])
+    x3 = r["fo_x3"]
+    flat = lambda a: a.reshape(-1, a.shape[-1])  # noqa: E731
+    y3, _ = od.flipout_fwd(flat(x3), r["fo_mu"], r["fo_rho"], r["fo_eps3"], flat(r["fo_sign_in3"]), flat(r["fo_sign_out3"]),
+                           r["fo_bias"], "relu")
+    _close(y3.reshape(r["fo_y3"].shape), r["fo_y3"])
+
+
+def test_reference_tf_dense_batch_ensemble(ref_tf):
+    """dense.py:551-584, TF class: rank 1 (reshape to [E, n, I]) and rank 3 (tile / reshape of [rank, E, dim] fast weights)."""
+    r = ref_tf
+    y, _ = od.batch_ensemble_fwd(r["be_x"], r["be_kernel"], r["be_alpha"], r["be_gamma"], r["be_bias"], "relu")
+    _close(y, r["be_y"])
+    y3 = od.batch_ensemble_rank_fwd(r["be_r3_x"], r["be_r3_kernel"], r["be_r3_alpha"], r["be_r3_gamma"], r["be_r3_bias"], "relu")
+    _close(y3, r["be_r3_y"])
+
+
+@pytest.mark.parametrize("tag", ["r1", "r1_add", "r1_bias"])
+def test_reference_tf_dense_rank1(ref_tf, tag):
+    """dense.py:1096-1144 as executed: distribution.sample(examples_per_model) -> [n, E, dim], clip, transpose to
+    [E, n, dim] (recorded draws re-laid to member-major rows), multiplicative / additive perturbations, deterministic /
+    per-example sampled ensemble bias; the layer's losses are the KLs of alpha and gamma (and the sampled bias)."""
+    r = ref_tf
+    lo, hi = r[f"{tag}_clip"]
+    sampled_bias = f"{tag}_rho_b" in r.files
+    y, _, fr, fs = od.rank1_fwd(r[f"{tag}_x"], r[f"{tag}_kernel"], r[f"{tag}_mu_r"], r[f"{tag}_rho_r"], r[f"{tag}_eps_r"],
+                                r[f"{tag}_mu_s"], r[f"{tag}_rho_s"], r[f"{tag}_eps_s"], r[f"{tag}_bias"], "relu",
+                                additive=(tag == "r1_add"), clip=(lo, hi),
+                                rho_b=r[f"{tag}_rho_b"] if sampled_bias else None,
+                                eps_b=r[f"{tag}_eps_b"] if sampled_bias else None)
+    _close(y, r[f"{tag}_y"])
+    if tag == "r1":  # the narrow clip bounds of this case are active
+        assert (fr == lo).any() or (fr == hi).any() or (fs == lo).any() or (fs == hi).any()
+    kls = [od.normal_kl(r[f"{tag}_mu_r"], r[f"{tag}_rho_r"]), od.normal_kl(r[f"{tag}_mu_s"], r[f"{tag}_rho_s"])]
+    got = sorted(float(v) for v in r[f"{tag}_kl"])
+    for k in kls:
+        assert min(abs(k - g) for g in got) <= 1e-12 * max(1.0, abs(k))
