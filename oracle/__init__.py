@@ -17,8 +17,11 @@ JAX / Flax, none of which is installed here or on the GPU box.  Its JAX files ar
     is executed the same way under NumPy-backed tensorflow / tfp stand-ins (`tests/golden/refstub_tf/`,
     `tests/golden/make_reference_golden_tf.py` -> `reference_vectors_tf.npz`): DenseReparameterization, DenseFlipout
     (with its Uniform[-1, 3) sign_output), DenseBatchEnsemble rank 1 / rank 3 and DenseRank1 (clip bounds, additive
-    perturbations, sampled bias) with every draw recorded, plus TrainableNormal / Softplus / NormalKLDivergence —
-    `tests/test_oracle.py::test_reference_tf_*` checks `oracle/dense.py` against them at 1e-12.
+    perturbations, sampled bias) with every draw recorded, plus TrainableNormal / Softplus / NormalKLDivergence; and
+    `layers/normalization.py` SpectralNormalization (in-place TF form), `layers/random_feature.py`
+    RandomFeatureGaussianProcess / LaplaceRandomFeatureCovariance (momentum and exact updates, three likelihoods, the
+    covariance inverse), `layers/utils.py` mean_field_logits — `tests/test_oracle.py::test_reference_tf_*` checks
+    `oracle/dense.py` and `oracle/sngp.py` against them at 1e-12 (1e-10 through the matrix inverse).
 The Conv2D variants and the LSTM cells (TF-only, Keras conv / RNN machinery) are not executed; for them, and for the
 VALUES of all native samplers, what is pinned is:
   * the Philox4x32-10 generator against the three Random123 known-answer vectors (tests/golden/philox_kat.json);

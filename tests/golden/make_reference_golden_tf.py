@@ -4,7 +4,11 @@
                                                                 DenseBatchEnsemble, DenseRank1)
     /root/reference/edward2/tensorflow/layers/utils.py        (the add_weight decorator)
     /root/reference/edward2/tensorflow/{initializers,regularizers,constraints}.py
-                                                               (TrainableNormal, NormalKLDivergence, Softplus)
+                                                               (TrainableNormal, NormalKLDivergence, Softplus,
+                                                                OrthogonalRandomFeatures)
+    /root/reference/edward2/tensorflow/layers/normalization.py (SpectralNormalization)
+    /root/reference/edward2/tensorflow/layers/random_feature.py (RandomFeatureGaussianProcess,
+                                                                LaplaceRandomFeatureCovariance)
 
 under the NumPy-backed stand-ins of tensorflow / tensorflow_probability / ed.RandomVariable in tests/golden/refstub_tf/
 (TensorFlow and TFP are not installable here; see refstub_tf/README.md for what the stand-ins restate).  Every statement
@@ -39,12 +43,16 @@ def load_reference():
     for name in ("random_variable", "generated_random_variables"):
         sys.modules[f"edward2.tensorflow.{name}"] = rv
         setattr(pkg, name, rv)
+    sys.modules["edward2.tensorflow.transformed_random_variable"] = types.ModuleType("transformed_random_variable")
+    pkg.transformed_random_variable = sys.modules["edward2.tensorflow.transformed_random_variable"]
     mods = {}
     for full, rel in (("edward2.tensorflow.constraints", "constraints.py"),
                       ("edward2.tensorflow.regularizers", "regularizers.py"),
                       ("edward2.tensorflow.initializers", "initializers.py"),
                       ("edward2.tensorflow.layers.utils", "layers/utils.py"),
-                      ("edward2.tensorflow.layers.dense", "layers/dense.py")):
+                      ("edward2.tensorflow.layers.dense", "layers/dense.py"),
+                      ("edward2.tensorflow.layers.normalization", "layers/normalization.py"),
+                      ("edward2.tensorflow.layers.random_feature", "layers/random_feature.py")):
         spec = importlib.util.spec_from_file_location(full, os.path.join(REF, rel))
         m = importlib.util.module_from_spec(spec)
         sys.modules[full] = m
@@ -168,6 +176,74 @@ def main():
                     f"{tag}_kl": np.array([float(np.asarray(v)) for v in layer.losses])})
         if sampled_bias:
             out[f"{tag}_eps_b"] = to_rows(per_example[2])
+
+    # ---- a9 SpectralNormalization, TF class (normalization.py:284-395): power iteration, sigma, IN-PLACE kernel update
+    # (self.w aliases self.layer.kernel, so restore_weights is a no-op and the kernel stays normalised)
+    norm = mods["normalization"]
+    for tag, iters, c, wscale in (("sn1", 1, 0.95, 1.0), ("sn3", 3, 0.6, 1.0), ("sn_small", 2, 0.95, 0.02)):
+        inner = tf.keras.layers.Dense(14)
+        sn = norm.SpectralNormalization(inner, iteration=iters, norm_multiplier=c)
+        x = rng.standard_normal((9, 10))
+        sn(x)  # builds (and already runs update_weights once, normalization.py:352)
+        w0 = rng.standard_normal((10, 14)) * wscale
+        u0, v0 = rng.standard_normal((1, 14)), rng.standard_normal((1, 10))
+        inner.kernel.assign(w0); sn.u.assign(u0); sn.v.assign(v0)  # noqa: E702
+        inner.bias.assign(rng.standard_normal(14) * 0.1)
+        y = sn(x, training=True)
+        out.update({f"{tag}_x": x, f"{tag}_w0": w0, f"{tag}_u0": u0, f"{tag}_v0": v0, f"{tag}_b": np.array(inner.bias),
+                    f"{tag}_iters": iters, f"{tag}_c": c, f"{tag}_y": y, f"{tag}_u1": np.array(sn.u), f"{tag}_v1": np.array(sn.v),
+                    f"{tag}_w1": np.array(inner.kernel)})
+        y_eval = sn(x, training=False)  # no power iteration: sigma from the stored u, v and the already normalised kernel
+        out.update({f"{tag}_y_eval": y_eval, f"{tag}_w2": np.array(inner.kernel)})
+
+    # ---- a11 LaplaceRandomFeatureCovariance, TF class (random_feature.py:284-549): momentum / exact updates, likelihoods,
+    # the covariance inverse on the first evaluation call, the update flag
+    rfm = mods["random_feature"]
+    D = 24
+    phi1, phi2, phit = rng.standard_normal((16, D)) * 0.3, rng.standard_normal((16, D)) * 0.3, rng.standard_normal((9, D)) * 0.3
+    lg1, lg2 = rng.standard_normal((16, 1)), rng.standard_normal((16, 1))
+    out.update(cov_phi1=phi1, cov_phi2=phi2, cov_phit=phit, cov_logits1=lg1, cov_logits2=lg2)
+    for tag, momentum, likelihood, ridge in (("cov_exact", -1.0, "gaussian", 1.0), ("cov_mom", 0.9, "gaussian", 0.5),
+                                             ("cov_logistic", -1.0, "binary_logistic", 1.0),
+                                             ("cov_poisson", 0.99, "poisson", 2.0)):
+        layer = rfm.LaplaceRandomFeatureCovariance(momentum=momentum, ridge_penalty=ridge, likelihood=likelihood)
+        r1 = layer(tf._t(phi1), tf._t(lg1), training=True)
+        assert np.array_equal(np.asarray(r1), np.eye(16))  # random_feature.py:531: identity while training
+        p1 = np.array(layer.precision_matrix)
+        layer(tf._t(phi2), tf._t(lg2), training=True)
+        p2 = np.array(layer.precision_matrix)
+        assert bool(np.asarray(layer.if_update_covariance))
+        cov = layer(tf._t(phit), None, training=False)
+        assert not bool(np.asarray(layer.if_update_covariance))
+        out.update({f"{tag}_p1": p1, f"{tag}_p2": p2, f"{tag}_sigma": np.array(layer.covariance_matrix), f"{tag}_cov": cov,
+                    f"{tag}_args": np.array([momentum, ridge])})
+
+    # ---- a10 RandomFeatureGaussianProcess, TF class (random_feature.py:33-281) end to end: LayerNormalization ->
+    # Dense(cos) with OrthogonalRandomFeatures / Uniform(0, 2 pi) bias -> * sqrt(2 / D) -> output weights + bias -> covariance
+    gp = rfm.RandomFeatureGaussianProcess(units=3, num_inducing=32, gp_cov_momentum=-1, gp_cov_ridge_penalty=1.0,
+                                          return_random_features=True)
+    xa, xt = rng.standard_normal((20, 12)), rng.standard_normal((7, 12))
+    la, cova, fa = gp(tf._t(xa), training=True)
+    gp._gp_output_bias.assign(rng.standard_normal(3) * 0.1)
+    la, cova, fa = gp(tf._t(xa), training=True)   # precision now holds two exact-sum updates of the same batch
+    lt, covt, ft = gp(tf._t(xt), training=False)
+    rf_w = np.array(gp._random_feature.kernel)
+    out.update(gp_xa=xa, gp_xt=xt, gp_rff_kernel=rf_w, gp_rff_bias=np.array(gp._random_feature.bias),
+               gp_out_kernel=np.array(gp._gp_output_layer.kernel), gp_out_bias=np.array(gp._gp_output_bias),
+               gp_ln_gamma=np.array(gp._input_norm_layer.gamma), gp_ln_beta=np.array(gp._input_norm_layer.beta),
+               gp_logits_a=la, gp_features_a=fa, gp_precision=np.array(gp._gp_cov_layer.precision_matrix),
+               gp_logits=lt, gp_cov=covt, gp_features=ft)
+    # OrthogonalRandomFeatures (initializers.py:759-832): orthogonal directions, rows < cols -> concatenated square blocks
+    out["orf_gram"] = rf_w[:, :12].T @ rf_w[:, :12]
+
+    # ---- a12 mean_field_logits, TF function (layers/utils.py:379-424)
+    utils = mods["utils"]
+    lg, covm = rng.standard_normal((11, 5)) * 3, np.diag(rng.uniform(0.0, 4.0, 11)) + 0.01
+    out.update(mf_logits=lg, mf_cov=covm)
+    for lik in ("logistic", "binary_logistic", "poisson"):
+        out[f"mf_{lik}"] = utils.mean_field_logits(tf._t(lg), tf._t(covm), mean_field_factor=0.7, likelihood=lik)
+    out["mf_nocov"] = utils.mean_field_logits(tf._t(lg), None, mean_field_factor=3.0)
+    out["mf_negative"] = utils.mean_field_logits(tf._t(lg), tf._t(covm), mean_field_factor=-1.0)
 
     np.savez_compressed(OUT, **{k: np.asarray(a, dtype=np.float64) for k, a in out.items()})
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")

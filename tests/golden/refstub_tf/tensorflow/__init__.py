@@ -41,24 +41,71 @@ class TensorShape(tuple):
 
 
 class Tensor(np.ndarray):
-    """ndarray whose `.shape` is a TensorShape (the reference reads `inputs.shape.ndims`)."""
+    """ndarray whose `.shape` is a TensorShape (the reference reads `inputs.shape.ndims`); `assign` makes it double as a
+    tf.Variable (in place, so aliases such as SpectralNormalization's `self.w = self.layer.kernel` keep aliasing)."""
 
     @property
     def shape(self):
         return TensorShape(np.ndarray.shape.__get__(self))
 
+    def assign(self, value):
+        self[...] = np.asarray(_t(value))
+        return self
+
 
 def _t(x, dtype=None):
     if hasattr(x, "value") and hasattr(x, "distribution"):  # an ed.RandomVariable stand-in
         x = x.value
-    kind = np.int64 if (dtype is not None and "int" in str(dtype)) else np.float64
     a = np.asarray(x)
-    if dtype is None and a.dtype.kind in "iub":
+    if dtype is not None and "bool" in str(dtype):
+        kind = np.bool_
+    elif dtype is not None and "int" in str(dtype):
+        kind = np.int64
+    elif dtype is None and a.dtype.kind in "iub":
         kind = a.dtype
+    else:
+        kind = np.float64
     return np.array(a, dtype=kind).view(Tensor)
 
 
-convert_to_tensor = constant = _t
+convert_to_tensor = _t
+bool = "bool"  # noqa: A001
+
+
+class DType:
+    pass
+
+
+def constant(value, dtype=None, **kwargs):
+    return _t(value, dtype)
+
+
+def Variable(initial_value=None, dtype=None, trainable=True, name=None, **kwargs):  # noqa: N802
+    return _t(initial_value, dtype)
+
+
+class VariableSynchronization:
+    AUTO, ON_READ, ON_WRITE, NONE = "auto", "on_read", "on_write", "none"
+
+
+class VariableAggregation:
+    NONE, SUM, MEAN, ONLY_FIRST_REPLICA = "none", "sum", "mean", "only_first_replica"
+
+
+def cond(pred, true_fn, false_fn):
+    return true_fn() if np.asarray(pred).item() else false_fn()
+
+
+def eye(n, dtype=None, **kwargs):
+    return _t(np.eye(int(n)))
+
+
+def ones(shape, dtype=None):
+    return _t(np.ones([int(d) for d in shape]))
+
+
+def sigmoid(x):
+    return _t(1.0 / (1.0 + np.exp(-_t(x))))
 
 
 def is_tensor(x):
@@ -97,8 +144,9 @@ def clip_by_value(x, lo, hi):
     return _t(np.clip(_t(x), lo, hi))
 
 
-def matmul(a, b):
-    return _t(np.matmul(_t(a), _t(b)))
+def matmul(a, b, transpose_a=False, transpose_b=False):
+    a, b = _t(a), _t(b)
+    return _t(np.matmul(a.T if transpose_a else a, b.T if transpose_b else b))
 
 
 def tensordot(a, b, axes):
@@ -175,12 +223,15 @@ def _softplus(x):
     return _t(np.where(x > 30, x, np.log1p(np.exp(np.minimum(x, 30)))))
 
 
-math = _module("tensorflow.math", log=lambda x: _t(np.log(_t(x))), reduce_mean=reduce_mean, softplus=_softplus)
+math = _module("tensorflow.math", log=lambda x: _t(np.log(_t(x))), reduce_mean=reduce_mean, softplus=_softplus,
+               cos=lambda x: _t(np.cos(_t(x))))
 nn = _module("tensorflow.nn", relu=lambda x: _t(np.maximum(_t(x), 0.0)), softplus=_softplus,
              bias_add=lambda v, b: _t(_t(v) + _t(b)),
              softmax=lambda x, axis=-1: _t(np.exp(_t(x) - np.max(_t(x), axis, keepdims=True))
                                            / np.sum(np.exp(_t(x) - np.max(_t(x), axis, keepdims=True)), axis, keepdims=True)))
-linalg = _module("tensorflow.linalg", matmul=matmul)
+nn.l2_normalize = lambda x, axis=None, epsilon=1e-12: _t(_t(x) / np.sqrt(np.maximum(np.sum(np.square(_t(x)), axis=axis, keepdims=True), epsilon)))  # noqa: E731,E501
+linalg = _module("tensorflow.linalg", matmul=matmul, inv=lambda a: _t(np.linalg.inv(_t(a))),
+                 diag_part=lambda a: _t(np.diagonal(_t(a)).copy()))
 
 
 def _uniform(shape, minval=0, maxval=None, dtype=float32, seed=None):
@@ -242,8 +293,43 @@ class _VarianceScaling(_Initializer):
 
 
 class _Orthogonal(_Initializer):
+    """tf.keras.initializers.Orthogonal: QR of a normal matrix, sign-fixed by diag(R), transposed when rows < cols."""
+
     def __init__(self, gain=1.0, seed=None):
         self.gain, self.seed = gain, seed
+
+    def __call__(self, shape, dtype=None, **kw):
+        shp = tuple(int(d) for d in shape)
+        rows, cols = int(np.prod(shp[:-1])), shp[-1]
+        a = random._rng.standard_normal((max(rows, cols), min(rows, cols)))
+        q, r = np.linalg.qr(a)
+        q = q * np.sign(np.diagonal(r))
+        if rows < cols:
+            q = q.T
+        return _t(self.gain * q.reshape(shp))
+
+    def get_config(self):
+        return {"gain": self.gain, "seed": self.seed}
+
+
+class _RandomUniform(_Initializer):
+    def __init__(self, minval=-0.05, maxval=0.05, seed=None):
+        self.minval, self.maxval, self.seed = minval, maxval, seed
+
+    def __call__(self, shape, dtype=None, **kw):
+        return _t(random._rng.uniform(self.minval, self.maxval, tuple(int(d) for d in shape)))
+
+
+class _RandomNormal(_Initializer):
+    def __init__(self, mean=0.0, stddev=0.05, seed=None):
+        self.mean, self.stddev, self.seed = mean, stddev, seed
+
+    def __call__(self, shape, dtype=None, **kw):
+        return _t(self.mean + self.stddev * random._rng.standard_normal(tuple(int(d) for d in shape)))
+
+
+random_uniform_initializer = _RandomUniform
+initializers = _module("tensorflow.initializers", random_normal=_RandomNormal)
 
 
 def _get_initializer(identifier):
@@ -298,13 +384,22 @@ class Layer:
 
     def add_weight(self, name=None, shape=None, dtype=None, initializer=None, regularizer=None, trainable=True,
                    constraint=None, **kwargs):
-        w = _t(_get_initializer(initializer)(shape, dtype))
+        if initializer is None:  # Keras default: glorot_uniform for floating dtypes, zeros otherwise
+            initializer = "zeros" if (dtype is not None and ("bool" in str(dtype) or "int" in str(dtype))) or len(shape) < 1 \
+                else "glorot_uniform"
+        w = _t(_get_initializer(initializer)(shape, dtype), dtype if dtype is not None and "bool" in str(dtype) else None)
         if regularizer is not None:
             self._loss_fns.append(lambda: regularizer(w))
         return w
 
     def add_loss(self, fn):
         self._loss_fns.append(fn)
+
+    def add_update(self, op):
+        pass
+
+    def compute_output_shape(self, input_shape):
+        return TensorShape(input_shape)
 
     @property
     def losses(self):
@@ -353,7 +448,63 @@ class Dense(Layer):
         return self.activation(out) if self.activation is not None else out
 
 
-_layers = _module("tensorflow.keras.layers", Layer=Layer, Dense=Dense)
+class LayerNormalization(Layer):
+    """tf.keras.layers.LayerNormalization defaults: axis -1, epsilon 1e-3, trainable gamma (ones) / beta (zeros)."""
+
+    def __init__(self, axis=-1, epsilon=1e-3, **kwargs):
+        super().__init__(**kwargs)
+        self.epsilon = epsilon
+
+    def build(self, input_shape):
+        d = int(TensorShape(input_shape)[-1])
+        self.gamma, self.beta = _t(np.ones(d)), _t(np.zeros(d))
+        self.built = True
+
+    def call(self, inputs):
+        x = _t(inputs)
+        mean = x.mean(-1, keepdims=True)
+        var = np.square(x - mean).mean(-1, keepdims=True)
+        return _t((x - mean) / np.sqrt(var + self.epsilon) * self.gamma + self.beta)
+
+
+class Lambda(Layer):
+    def __init__(self, function, **kwargs):
+        super().__init__(**kwargs)
+        self.function = function
+
+    def call(self, inputs):
+        return self.function(inputs)
+
+
+class Wrapper(Layer):
+    def __init__(self, layer, **kwargs):
+        super().__init__(**kwargs)
+        self.layer = layer
+
+    def build(self, input_shape=None):
+        if not self.layer.built:
+            self.layer.build(input_shape)
+            self.layer.built = True
+        self.built = True
+
+
+def _dense_output_shape(self, input_shape):
+    return TensorShape(tuple(TensorShape(input_shape)[:-1]) + (self.units,))
+
+
+Dense.compute_output_shape = _dense_output_shape
+
+
+class _L2(_Regularizer):
+    def __init__(self, l2=0.01):
+        self.l2 = l2
+
+    def __call__(self, w):
+        return self.l2 * np.sum(np.square(_t(w)))
+
+
+_layers = _module("tensorflow.keras.layers", Layer=Layer, Dense=Dense, LayerNormalization=LayerNormalization,
+                  Lambda=Lambda, Wrapper=Wrapper, experimental=types.SimpleNamespace())
 _initializers = _module("tensorflow.keras.initializers", Initializer=_Initializer, Zeros=_Zeros, Ones=_Ones,
                         TruncatedNormal=_TruncatedNormal, VarianceScaling=_VarianceScaling, Orthogonal=_Orthogonal,
                         get=_get_initializer, he_normal=lambda seed=None: _VarianceScaling(2.0, "fan_in", "truncated_normal"),
@@ -361,14 +512,19 @@ _initializers = _module("tensorflow.keras.initializers", Initializer=_Initialize
                         GlorotNormal=lambda seed=None: _VarianceScaling(1.0, "fan_avg", "truncated_normal"),
                         glorot_uniform=lambda seed=None: _VarianceScaling(1.0, "fan_avg", "uniform"),
                         zeros=_Zeros, ones=_Ones, Constant=lambda value=0.0: (lambda shape, dtype=None, **kw: _t(np.full([int(s) for s in shape], value))))
-_regularizers = _module("tensorflow.keras.regularizers", Regularizer=_Regularizer, get=_get_plain)
+_regularizers = _module("tensorflow.keras.regularizers", Regularizer=_Regularizer, get=_get_plain, l2=_L2, L2=_L2)
 _constraints = _module("tensorflow.keras.constraints", Constraint=_Constraint, get=_get_plain)
 _activations = _module("tensorflow.keras.activations", get=_activation, serialize=lambda a: getattr(a, "__name__", None),
                        relu=nn.relu, linear=lambda x: x)
-_backend = _module("tensorflow.keras.backend", epsilon=lambda: 1e-7)
+_backend = _module("tensorflow.keras.backend", epsilon=lambda: 1e-7, learning_phase=lambda: 0)
 _legacy = _module("tensorflow.keras.utils.legacy", serialize_keras_object=_serialize, deserialize_keras_object=_deserialize)
 _utils = _module("tensorflow.keras.utils", legacy=_legacy)
 keras = _module("tensorflow.keras", layers=_layers, initializers=_initializers, regularizers=_regularizers,
                 constraints=_constraints, activations=_activations, backend=_backend, utils=_utils)
-_v1 = _module("tensorflow.compat.v1")
-compat = _module("tensorflow.compat", v1=_v1)
+class _Dimension:
+    pass
+
+
+_v1 = _module("tensorflow.compat.v1", Dimension=_Dimension)
+sys.modules["tensorflow.compat.v2"] = sys.modules[__name__]   # `import tensorflow.compat.v2 as tf`
+compat = _module("tensorflow.compat", v1=_v1, v2=sys.modules[__name__])

@@ -822,3 +822,74 @@ def test_reference_tf_dense_rank1(ref_tf, tag):
     got = sorted(float(v) for v in r[f"{tag}_kl"])
     for k in kls:
         assert min(abs(k - g) for g in got) <= 1e-12 * max(1.0, abs(k))
+
+
+@pytest.mark.parametrize("tag", ["sn1", "sn3", "sn_small"])
+def test_reference_tf_spectral_normalization(ref_tf, tag):
+    """normalization.py:284-395, TF class as executed: power iteration from the stored (u, v), sigma, the kernel normalised
+    IN PLACE (self.w aliases layer.kernel), the wrapped Dense output; then an evaluation call (no power iteration) on the
+    already normalised kernel."""
+    r = ref_tf
+    it, c = int(r[f"{tag}_iters"]), float(r[f"{tag}_c"])
+    w1, u1, v1, _ = og.spectral_norm_tf(r[f"{tag}_w0"], r[f"{tag}_u0"], r[f"{tag}_v0"], it, c, True)
+    _close(u1, r[f"{tag}_u1"])
+    _close(v1, r[f"{tag}_v1"])
+    _close(w1, r[f"{tag}_w1"])
+    _close(r[f"{tag}_x"] @ w1 + r[f"{tag}_b"], r[f"{tag}_y"])
+    w2, _, _, _ = og.spectral_norm_tf(w1, u1, v1, it, c, False)
+    _close(w2, r[f"{tag}_w2"])
+    _close(r[f"{tag}_x"] @ w2 + r[f"{tag}_b"], r[f"{tag}_y_eval"])
+    if tag == "sn_small":  # a kernel already below the bound is left unchanged (normalization.py:384-386)
+        np.testing.assert_array_equal(r[f"{tag}_w1"], r[f"{tag}_w0"])
+
+
+@pytest.mark.parametrize("tag", ["cov_exact", "cov_mom", "cov_logistic", "cov_poisson"])
+def test_reference_tf_laplace_covariance(ref_tf, tag):
+    """random_feature.py:284-549, TF class as executed: two training calls (exact-sum / momentum updates, Gaussian /
+    logistic / Poisson likelihoods), then the evaluation call that inverts ridge I + P and returns ridge Phi Sigma Phi^T."""
+    r = ref_tf
+    momentum, ridge = r[f"{tag}_args"]
+    lik = {"cov_exact": "gaussian", "cov_mom": "gaussian", "cov_logistic": "binary_logistic", "cov_poisson": "poisson"}[tag]
+    D = r["cov_phi1"].shape[1]
+    p1 = og.precision_update_tf(np.zeros((D, D)), r["cov_phi1"], momentum, r["cov_logits1"], lik)
+    _close(p1, r[f"{tag}_p1"])
+    p2 = og.precision_update_tf(p1, r["cov_phi2"], momentum, r["cov_logits2"], lik)
+    _close(p2, r[f"{tag}_p2"])
+    sigma = og.covariance_tf(p2, ridge)
+    _close(sigma, r[f"{tag}_sigma"], 1e-10)
+    _close(og.predictive_covariance_tf(r["cov_phit"], sigma, ridge), r[f"{tag}_cov"], 1e-10)
+
+
+def test_reference_tf_rfgp_end_to_end(ref_tf):
+    """random_feature.py:33-281, TF class as executed: Keras LayerNormalization (eps 1e-3), frozen random-feature Dense with
+    cos activation, sqrt(2 / D) feature scale, output weights + bias variable, exact-sum precision, evaluation covariance;
+    the reference's OrthogonalRandomFeatures draws mutually orthogonal directions within a square block."""
+    r = ref_tf
+    D = r["gp_rff_kernel"].shape[1]
+
+    def head(x):
+        xn = og.layer_norm(x, r["gp_ln_gamma"], r["gp_ln_beta"], 1e-3)
+        phi, _ = og.rff(xn, r["gp_rff_kernel"], r["gp_rff_bias"], np.sqrt(2.0 / D))
+        return phi, og.gp_output(phi, r["gp_out_kernel"], r["gp_out_bias"])
+
+    phi_a, logits_a = head(r["gp_xa"])
+    _close(phi_a, r["gp_features_a"])
+    _close(logits_a, r["gp_logits_a"])
+    precision = og.precision_update_tf(og.precision_update_tf(np.zeros((D, D)), phi_a, -1.0), phi_a, -1.0)
+    _close(precision, r["gp_precision"])
+    phi_t, logits_t = head(r["gp_xt"])
+    _close(phi_t, r["gp_features"])
+    _close(logits_t, r["gp_logits"])
+    _close(og.predictive_covariance_tf(phi_t, og.covariance_tf(precision, 1.0), 1.0), r["gp_cov"], 1e-10)
+    gram = r["orf_gram"]
+    assert np.abs(gram - np.diag(np.diag(gram))).max() < 1e-10 * np.abs(gram).max()
+    assert r["gp_rff_bias"].min() >= 0.0 and r["gp_rff_bias"].max() <= 2.0 * np.pi
+
+
+def test_reference_tf_mean_field_logits(ref_tf):
+    """layers/utils.py:379-424 as executed: the [B, B] covariance enters through its diagonal."""
+    r = ref_tf
+    for lik in ("logistic", "binary_logistic", "poisson"):
+        _close(og.mean_field_logits(r["mf_logits"], r["mf_cov"], 0.7, lik), r[f"mf_{lik}"])
+    _close(og.mean_field_logits(r["mf_logits"], None, 3.0), r["mf_nocov"])
+    _close(og.mean_field_logits(r["mf_logits"], r["mf_cov"], -1.0), r["mf_negative"])
