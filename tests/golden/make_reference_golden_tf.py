@@ -52,7 +52,8 @@ def load_reference():
                       ("edward2.tensorflow.layers.utils", "layers/utils.py"),
                       ("edward2.tensorflow.layers.dense", "layers/dense.py"),
                       ("edward2.tensorflow.layers.normalization", "layers/normalization.py"),
-                      ("edward2.tensorflow.layers.random_feature", "layers/random_feature.py")):
+                      ("edward2.tensorflow.layers.random_feature", "layers/random_feature.py"),
+                      ("edward2.tensorflow.layers.convolutional", "layers/convolutional.py")):
         spec = importlib.util.spec_from_file_location(full, os.path.join(REF, rel))
         m = importlib.util.module_from_spec(spec)
         sys.modules[full] = m
@@ -244,6 +245,58 @@ def main():
         out[f"mf_{lik}"] = utils.mean_field_logits(tf._t(lg), tf._t(covm), mean_field_factor=0.7, likelihood=lik)
     out["mf_nocov"] = utils.mean_field_logits(tf._t(lg), None, mean_field_factor=3.0)
     out["mf_negative"] = utils.mean_field_logits(tf._t(lg), tf._t(covm), mean_field_factor=-1.0)
+
+    # ---- §8f-1 Conv2D variants (layers/convolutional.py:32,167,560,2056), NHWC
+    conv = mods["convolutional"]
+    Bc, Hc, Wc, Ci, Co = 4, 6, 7, 3, 5
+    # Conv2DReparameterization (:88-98): 'same' padding, stride 1
+    layer = conv.Conv2DReparameterization(Co, 3, padding="same", activation="relu")
+    x = rng.standard_normal((Bc, Hc, Wc, Ci))
+    layer(tf._t(x))
+    mu, rho = rng.standard_normal((3, 3, Ci, Co)) * 0.3, rng.standard_normal((3, 3, Ci, Co)) * 0.5 - 2.0
+    set_normal(layer.kernel_initializer, mu, rho)
+    layer.bias = tf._t(rng.standard_normal(Co) * 0.2)
+    del tfp.recorded[:]
+    y = layer(tf._t(x))
+    out.update(crp_x=x, crp_mu=mu, crp_rho=rho, crp_eps=tfp.recorded[-1], crp_bias=np.asarray(layer.bias), crp_y=y,
+               crp_kl=layer.losses[0])
+    # Conv2DFlipout (:225-249): 'valid' padding, stride 2; both sign tensors int32 of shape [B, 1, 1, C]
+    layer = conv.Conv2DFlipout(Co, 3, strides=2, padding="valid", activation="relu")
+    layer(tf._t(x))
+    mu, rho = rng.standard_normal((3, 3, Ci, Co)) * 0.3, rng.standard_normal((3, 3, Ci, Co)) * 0.5 - 2.0
+    set_normal(layer.kernel_initializer, mu, rho)
+    layer.bias = tf._t(rng.standard_normal(Co) * 0.2)
+    del tfp.recorded[:], uniforms[:]
+    y = layer(tf._t(x))
+    assert len(uniforms) == 2 and uniforms[0].shape == (Bc, 1, 1, Ci) and uniforms[1].shape == (Bc, 1, 1, Co)
+    out.update(cfo_x=x, cfo_mu=mu, cfo_rho=rho, cfo_eps=tfp.recorded[-1], cfo_bias=np.asarray(layer.bias),
+               cfo_sign_in=(2 * uniforms[0] - 1).reshape(Bc, Ci), cfo_sign_out=(2 * uniforms[1] - 1).reshape(Bc, Co), cfo_y=y)
+    # Conv2DBatchEnsemble (:681-699), rank 1, two members
+    Ec, nc = 2, 2
+    layer = conv.Conv2DBatchEnsemble(Co, 3, ensemble_size=Ec, padding="same", activation="relu")
+    layer(tf._t(x))
+    layer.alpha = tf._t(1.0 + 0.4 * rng.standard_normal((Ec, Ci)))
+    layer.gamma = tf._t(1.0 + 0.4 * rng.standard_normal((Ec, Co)))
+    layer.ensemble_bias = tf._t(0.2 * rng.standard_normal((Ec, Co)))
+    y = layer(tf._t(x))
+    out.update(cbe_x=x, cbe_kernel=np.asarray(layer.kernel), cbe_alpha=np.asarray(layer.alpha),
+               cbe_gamma=np.asarray(layer.gamma), cbe_bias=np.asarray(layer.ensemble_bias), cbe_y=y)
+    # Conv2DRank1 (:1968-2020): per-example fast weights [n, E, C] -> [E, n, C] -> rows, broadcast over the spatial axes
+    layer = conv.Conv2DRank1(Co, 3, ensemble_size=Ec, padding="same", strides=(2, 1), activation="relu")
+    layer(tf._t(x))
+    mu_r, rho_r = 1.0 + 0.3 * rng.standard_normal((Ec, Ci)), rng.standard_normal((Ec, Ci)) * 0.3 - 1.5
+    mu_s, rho_s = 1.0 + 0.3 * rng.standard_normal((Ec, Co)), rng.standard_normal((Ec, Co)) * 0.3 - 1.5
+    set_normal(layer.alpha_initializer, mu_r, rho_r)
+    set_normal(layer.gamma_initializer, mu_s, rho_s)
+    mu_b = 0.2 * rng.standard_normal((Ec, Co))
+    layer.ensemble_bias = tf._t(mu_b)
+    del tfp.recorded[:]
+    y = layer(tf._t(x))
+    per_example = [r_ for r_ in tfp.recorded if r_.ndim == 3]
+    assert len(per_example) == 2
+    rows = lambda a: np.transpose(a, (1, 0, 2)).reshape(Ec * nc, -1)  # noqa: E731
+    out.update(cr1_x=x, cr1_kernel=np.asarray(layer.kernel), cr1_mu_r=mu_r, cr1_rho_r=rho_r, cr1_mu_s=mu_s, cr1_rho_s=rho_s,
+               cr1_bias=mu_b, cr1_eps_r=rows(per_example[0]), cr1_eps_s=rows(per_example[1]), cr1_y=y)
 
     np.savez_compressed(OUT, **{k: np.asarray(a, dtype=np.float64) for k, a in out.items()})
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")

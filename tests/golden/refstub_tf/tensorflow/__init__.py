@@ -226,7 +226,7 @@ def _softplus(x):
 math = _module("tensorflow.math", log=lambda x: _t(np.log(_t(x))), reduce_mean=reduce_mean, softplus=_softplus,
                cos=lambda x: _t(np.cos(_t(x))))
 nn = _module("tensorflow.nn", relu=lambda x: _t(np.maximum(_t(x), 0.0)), softplus=_softplus,
-             bias_add=lambda v, b: _t(_t(v) + _t(b)),
+             bias_add=lambda v, b, data_format=None: _t(_t(v) + _t(b)),
              softmax=lambda x, axis=-1: _t(np.exp(_t(x) - np.max(_t(x), axis, keepdims=True))
                                            / np.sum(np.exp(_t(x) - np.max(_t(x), axis, keepdims=True)), axis, keepdims=True)))
 nn.l2_normalize = lambda x, axis=None, epsilon=1e-12: _t(_t(x) / np.sqrt(np.maximum(np.sum(np.square(_t(x)), axis=axis, keepdims=True), epsilon)))  # noqa: E731,E501
@@ -495,6 +495,86 @@ def _dense_output_shape(self, input_shape):
 Dense.compute_output_shape = _dense_output_shape
 
 
+def _conv2d_nhwc(x, k, strides, padding):
+    """Direct NHWC cross-correlation (what tf.nn.convolution computes): 'VALID' or TensorFlow's 'SAME' padding (extra
+    padding at the bottom / right)."""
+    x, k = np.asarray(_t(x)), np.asarray(_t(k))
+    kh, kw, cin, cout = k.shape
+    sh, sw = strides
+    B, H, W, _ = x.shape
+    if str(padding).upper() == "SAME":
+        ho, wo = -(-H // sh), -(-W // sw)
+        ph, pw = max((ho - 1) * sh + kh - H, 0), max((wo - 1) * sw + kw - W, 0)
+        x = np.pad(x, ((0, 0), (ph // 2, ph - ph // 2), (pw // 2, pw - pw // 2), (0, 0)))
+    else:
+        ho, wo = (H - kh) // sh + 1, (W - kw) // sw + 1
+    out = np.zeros((B, ho, wo, cout))
+    for i in range(kh):
+        for j in range(kw):
+            patch = x[:, i:i + (ho - 1) * sh + 1:sh, j:j + (wo - 1) * sw + 1:sw, :]
+            out += patch @ k[i, j]
+    return _t(out)
+
+
+def _pair(v):
+    return (int(v), int(v)) if np.isscalar(v) else tuple(int(a) for a in v)
+
+
+nn.convolution = lambda input, filters, strides=None, padding="VALID", data_format=None, dilations=None: _conv2d_nhwc(  # noqa: E731,A002
+    input, filters, _pair(1 if strides is None else strides), padding)
+
+
+class Conv2D(Layer):
+    """tf.keras.layers.Conv2D, restated for channels_last / dilation 1: kernel [kh, kw, Cin, filters], bias [filters];
+    call = convolution_op(inputs, kernel), bias_add, activation."""
+
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding="valid", data_format=None, dilation_rate=(1, 1),
+                 groups=1, activation=None, use_bias=True, kernel_initializer="glorot_uniform", bias_initializer="zeros",
+                 kernel_regularizer=None, bias_regularizer=None, activity_regularizer=None, kernel_constraint=None,
+                 bias_constraint=None, **kwargs):
+        super().__init__(**kwargs)
+        self.rank, self.filters, self.kernel_size, self.strides = 2, int(filters), _pair(kernel_size), _pair(strides)
+        self.padding, self.data_format = padding, data_format or "channels_last"
+        self.dilation_rate, self.groups = _pair(dilation_rate), groups
+        self.activation, self.use_bias = _activation(activation), use_bias
+        self.kernel_initializer, self.bias_initializer = _get_initializer(kernel_initializer), _get_initializer(bias_initializer)
+        self.kernel_regularizer, self.bias_regularizer = kernel_regularizer, bias_regularizer
+        self.activity_regularizer = activity_regularizer
+        self.kernel_constraint, self.bias_constraint = kernel_constraint, bias_constraint
+
+    def build(self, input_shape):
+        cin = int(TensorShape(input_shape)[-1])
+        self.kernel = self.add_weight(name="kernel", shape=self.kernel_size + (cin, self.filters),
+                                      initializer=self.kernel_initializer, regularizer=self.kernel_regularizer,
+                                      constraint=self.kernel_constraint, trainable=True, dtype=self.dtype)
+        self.bias = self.add_weight(name="bias", shape=(self.filters,), initializer=self.bias_initializer,
+                                    regularizer=self.bias_regularizer, constraint=self.bias_constraint, trainable=True,
+                                    dtype=self.dtype) if self.use_bias else None
+        self.built = True
+
+    def convolution_op(self, inputs, kernel):
+        return _conv2d_nhwc(inputs, kernel, self.strides, self.padding)
+
+    def call(self, inputs):
+        out = self.convolution_op(inputs, self.kernel)
+        if self.use_bias:
+            out = nn.bias_add(out, self.bias)
+        return self.activation(out) if self.activation is not None else out
+
+
+class Conv1D(Layer):
+    pass
+
+
+class DepthwiseConv2D(Layer):
+    pass
+
+
+class InputSpec:
+    def __init__(self, **kwargs):
+        self.__dict__.update(kwargs)
+
+
 class _L2(_Regularizer):
     def __init__(self, l2=0.01):
         self.l2 = l2
@@ -504,7 +584,8 @@ class _L2(_Regularizer):
 
 
 _layers = _module("tensorflow.keras.layers", Layer=Layer, Dense=Dense, LayerNormalization=LayerNormalization,
-                  Lambda=Lambda, Wrapper=Wrapper, experimental=types.SimpleNamespace())
+                  Lambda=Lambda, Wrapper=Wrapper, experimental=types.SimpleNamespace(), Conv2D=Conv2D, Conv1D=Conv1D,
+                  DepthwiseConv2D=DepthwiseConv2D, InputSpec=InputSpec)
 _initializers = _module("tensorflow.keras.initializers", Initializer=_Initializer, Zeros=_Zeros, Ones=_Ones,
                         TruncatedNormal=_TruncatedNormal, VarianceScaling=_VarianceScaling, Orthogonal=_Orthogonal,
                         get=_get_initializer, he_normal=lambda seed=None: _VarianceScaling(2.0, "fan_in", "truncated_normal"),

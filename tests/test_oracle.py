@@ -893,3 +893,25 @@ def test_reference_tf_mean_field_logits(ref_tf):
         _close(og.mean_field_logits(r["mf_logits"], r["mf_cov"], 0.7, lik), r[f"mf_{lik}"])
     _close(og.mean_field_logits(r["mf_logits"], None, 3.0), r["mf_nocov"])
     _close(og.mean_field_logits(r["mf_logits"], r["mf_cov"], -1.0), r["mf_negative"])
+
+
+def test_reference_tf_conv2d_variants(ref_tf):
+    """layers/convolutional.py as executed (NHWC): Conv2DReparameterization ('same', stride 1; :88-98), Conv2DFlipout
+    ('valid', stride 2, int32 signs of shape [B, 1, 1, C]; :225-249), Conv2DBatchEnsemble (tile / reshape of the fast
+    weights; :681-699) and Conv2DRank1 (per-example fast weights, strides (2, 1); :1968-2020) against oracle/conv.py."""
+    from oracle import conv as oc
+
+    r = ref_tf
+    y, _ = oc.reparam_conv2d(r["crp_x"], r["crp_mu"], r["crp_rho"], r["crp_eps"], r["crp_bias"], "relu", (1, 1), "same")
+    _close(y, r["crp_y"])
+    _close(od.normal_kl(r["crp_mu"], r["crp_rho"]), r["crp_kl"])
+    assert set(np.unique(r["cfo_sign_in"])) <= {-1.0, 1.0} and set(np.unique(r["cfo_sign_out"])) <= {-1.0, 1.0}
+    y, _ = oc.flipout_conv2d(r["cfo_x"], r["cfo_mu"], r["cfo_rho"], r["cfo_eps"], r["cfo_sign_in"], r["cfo_sign_out"],
+                             r["cfo_bias"], "relu", (2, 2), "valid")
+    _close(y, r["cfo_y"])
+    y = oc.batch_ensemble_conv2d(r["cbe_x"], r["cbe_kernel"], r["cbe_alpha"], r["cbe_gamma"], r["cbe_bias"], "relu",
+                                 (1, 1), "same")
+    _close(y, r["cbe_y"])
+    y, _, _ = oc.rank1_conv2d(r["cr1_x"], r["cr1_kernel"], r["cr1_mu_r"], r["cr1_rho_r"], r["cr1_eps_r"], r["cr1_mu_s"],
+                              r["cr1_rho_s"], r["cr1_eps_s"], r["cr1_bias"], "relu", (2, 1), "same")
+    _close(y, r["cr1_y"])
