@@ -22,8 +22,10 @@ JAX / Flax, none of which is installed here or on the GPU box.  Its JAX files ar
     RandomFeatureGaussianProcess / LaplaceRandomFeatureCovariance (momentum and exact updates, three likelihoods, the
     covariance inverse), `layers/utils.py` mean_field_logits — `tests/test_oracle.py::test_reference_tf_*` checks
     `oracle/dense.py` and `oracle/sngp.py` against them at 1e-12 (1e-10 through the matrix inverse).
-The Conv2D variants and the LSTM cells (TF-only, Keras conv / RNN machinery) are not executed; for them, and for the
-VALUES of all native samplers, what is pinned is:
+    `layers/convolutional.py` (Conv2DReparameterization / Flipout / BatchEnsemble / Rank1) and `layers/recurrent.py`
+    (LSTMCellReparameterization / Flipout, Keras implementations 1 and 2, and LSTMCellRank1, multiplicative and additive)
+    run the same way and pin `oracle/conv.py` and `oracle/recurrent.py`.
+For the VALUES of the native samplers (the reference has no RNG-stream contract) what is pinned is:
   * the Philox4x32-10 generator against the three Random123 known-answer vectors (tests/golden/philox_kat.json);
   * `mean_field_logits` against the reference's known-answer tests (edward2/tensorflow/layers/utils_test.py:201-241,
     edward2/jax/nn/utils_test.py:28-68);

@@ -53,7 +53,8 @@ def load_reference():
                       ("edward2.tensorflow.layers.dense", "layers/dense.py"),
                       ("edward2.tensorflow.layers.normalization", "layers/normalization.py"),
                       ("edward2.tensorflow.layers.random_feature", "layers/random_feature.py"),
-                      ("edward2.tensorflow.layers.convolutional", "layers/convolutional.py")):
+                      ("edward2.tensorflow.layers.convolutional", "layers/convolutional.py"),
+                      ("edward2.tensorflow.layers.recurrent", "layers/recurrent.py")):
         spec = importlib.util.spec_from_file_location(full, os.path.join(REF, rel))
         m = importlib.util.module_from_spec(spec)
         sys.modules[full] = m
@@ -297,6 +298,67 @@ def main():
     rows = lambda a: np.transpose(a, (1, 0, 2)).reshape(Ec * nc, -1)  # noqa: E731
     out.update(cr1_x=x, cr1_kernel=np.asarray(layer.kernel), cr1_mu_r=mu_r, cr1_rho_r=rho_r, cr1_mu_s=mu_s, cr1_rho_s=rho_s,
                cr1_bias=mu_b, cr1_eps_r=rows(per_example[0]), cr1_eps_s=rows(per_example[1]), cr1_y=y)
+
+    # ---- §8f-3 LSTM cells (layers/recurrent.py:30,185,360): weights / signs / fast weights drawn once per sequence by
+    # get_initial_state, reused by every step
+    rec = mods["recurrent"]
+    Hh, Ii, T = 5, 4, 3
+
+    def unroll(cell, xs, states):
+        hs = []
+        for t in range(xs.shape[0]):
+            h, states = cell(tf._t(xs[t]), states)
+            hs.append(np.array(h))
+        return np.stack(hs), np.array(states[1])
+
+    for tag, cls, impl in (("lrp", rec.LSTMCellReparameterization, 2), ("lrp1", rec.LSTMCellReparameterization, 1),
+                           ("lfo", rec.LSTMCellFlipout, 2), ("lfo1", rec.LSTMCellFlipout, 1)):
+        Bl = 3
+        cell = cls(Hh, implementation=impl)
+        xs = rng.standard_normal((T, Bl, Ii))
+        cell(tf._t(xs[0]), cell.get_initial_state(batch_size=Bl, dtype=tf.float32))  # builds
+        mu_k, rho_k = rng.standard_normal((Ii, 4 * Hh)) * 0.4, rng.standard_normal((Ii, 4 * Hh)) * 0.5 - 2.0
+        mu_u, rho_u = rng.standard_normal((Hh, 4 * Hh)) * 0.4, rng.standard_normal((Hh, 4 * Hh)) * 0.5 - 2.0
+        set_normal(cell.kernel_initializer, mu_k, rho_k)
+        set_normal(cell.recurrent_initializer, mu_u, rho_u)
+        cell.bias = tf._t(rng.standard_normal(4 * Hh) * 0.3)
+        del tfp.recorded[:], uniforms[:]
+        states = cell.get_initial_state(batch_size=Bl, dtype=tf.float32)  # samples the weights (and the Flipout signs)
+        draws = [d for d in tfp.recorded]
+        assert [d.shape for d in draws] == [(Ii, 4 * Hh)] * 2 + [(Hh, 4 * Hh)] * 2
+        hs, c_last = unroll(cell, xs, states)
+        assert len(tfp.recorded) == 4  # nothing is re-drawn by the steps
+        out.update({f"{tag}_xs": xs, f"{tag}_mu_k": mu_k, f"{tag}_rho_k": rho_k, f"{tag}_mu_u": mu_u, f"{tag}_rho_u": rho_u,
+                    f"{tag}_bias": np.array(cell.bias), f"{tag}_eps_k": draws[1], f"{tag}_eps_u": draws[3], f"{tag}_hs": hs,
+                    f"{tag}_c": c_last, f"{tag}_kl": np.array([float(np.asarray(v)) for v in cell.losses])})
+        if cls is rec.LSTMCellFlipout:
+            assert [u.shape for u in uniforms] == [(Bl, Ii), (Bl, 4 * Hh), (Bl, Hh), (Bl, 4 * Hh)]
+            out.update({f"{tag}_sign_in": 2 * uniforms[0] - 1, f"{tag}_sign_out": 2 * uniforms[1] - 1,
+                        f"{tag}_rsign_in": 2 * uniforms[2] - 1, f"{tag}_rsign_out": 2 * uniforms[3] - 1})
+
+    El, nl = 2, 3
+    for tag, additive in (("lr1", False), ("lr1_add", True)):
+        cell = rec.LSTMCellRank1(Hh, ensemble_size=El, use_additive_perturbation=additive)
+        xs = rng.standard_normal((T, El * nl, Ii))
+        cell(tf._t(xs[0]), cell.get_initial_state(batch_size=El * nl, dtype=tf.float32))  # builds
+        params = {}
+        for name, dim in (("alpha", Ii), ("gamma", 4 * Hh), ("recurrent_alpha", Hh), ("recurrent_gamma", 4 * Hh)):
+            mu, rho = 1.0 + 0.3 * rng.standard_normal((El, dim)), rng.standard_normal((El, dim)) * 0.3 - 1.5
+            set_normal(getattr(cell, name + "_initializer"), mu, rho)
+            params[name] = (mu, rho)
+        cell.kernel = tf._t(rng.standard_normal((Ii, 4 * Hh)) * 0.4)
+        cell.recurrent_kernel = tf._t(rng.standard_normal((Hh, 4 * Hh)) * 0.4)
+        cell.bias = tf._t(rng.standard_normal((El, 4 * Hh)) * 0.3)
+        del tfp.recorded[:]
+        states = cell.get_initial_state(batch_size=El * nl, dtype=tf.float32)
+        per_example = [d for d in tfp.recorded if d.ndim == 3]
+        assert len(per_example) == 4
+        hs, c_last = unroll(cell, xs, states)
+        rows = lambda a: np.transpose(a, (1, 0, 2)).reshape(El * nl, -1)  # noqa: E731
+        out.update({f"{tag}_xs": xs, f"{tag}_kernel": np.array(cell.kernel), f"{tag}_rkernel": np.array(cell.recurrent_kernel),
+                    f"{tag}_bias": np.array(cell.bias), f"{tag}_hs": hs, f"{tag}_c": c_last})
+        for (name, (mu, rho)), eps in zip(params.items(), per_example):
+            out.update({f"{tag}_{name}_mu": mu, f"{tag}_{name}_rho": rho, f"{tag}_{name}_eps": rows(eps)})
 
     np.savez_compressed(OUT, **{k: np.asarray(a, dtype=np.float64) for k, a in out.items()})
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")

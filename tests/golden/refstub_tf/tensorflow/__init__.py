@@ -338,7 +338,8 @@ def _get_initializer(identifier):
     table = {"zeros": _Zeros, "zero": _Zeros, "ones": _Ones,
              "glorot_uniform": lambda: _VarianceScaling(1.0, "fan_avg", "uniform"),
              "he_normal": lambda: _VarianceScaling(2.0, "fan_in", "truncated_normal"),
-             "glorot_normal": lambda: _VarianceScaling(1.0, "fan_avg", "truncated_normal")}
+             "glorot_normal": lambda: _VarianceScaling(1.0, "fan_avg", "truncated_normal"),
+             "orthogonal": lambda: _Orthogonal()}
     return table[str(identifier)]()
 
 
@@ -411,6 +412,7 @@ class Layer:
     def __call__(self, inputs, *args, **kwargs):
         if not self.built:
             self.build(_t(inputs).shape)
+            self.built = True
         return self.call(inputs, *args, **kwargs)
 
     def get_config(self):
@@ -562,6 +564,85 @@ class Conv2D(Layer):
         return self.activation(out) if self.activation is not None else out
 
 
+class LSTMCell(Layer):
+    """tf.keras.layers.LSTMCell, restated (dropout 0): kernel [in, 4 units], recurrent_kernel [units, 4 units], gate order
+    i | f | c | o; implementation 1 works on the four gate slices through `_compute_carry_and_output`, implementation 2 on
+    the fused pre-activation through `_compute_carry_and_output_fused`; h = o * activation(c)."""
+
+    def __init__(self, units, activation="tanh", recurrent_activation="sigmoid", use_bias=True,
+                 kernel_initializer="glorot_uniform", recurrent_initializer="orthogonal", bias_initializer="zeros",
+                 unit_forget_bias=True, kernel_regularizer=None, recurrent_regularizer=None, bias_regularizer=None,
+                 kernel_constraint=None, recurrent_constraint=None, bias_constraint=None, dropout=0.0,
+                 recurrent_dropout=0.0, implementation=2, **kwargs):
+        super().__init__(**kwargs)
+        acts = {"tanh": lambda x: _t(np.tanh(_t(x))), "sigmoid": sigmoid}
+        self.units = int(units)
+        self.activation = acts.get(activation, activation)
+        self.recurrent_activation = acts.get(recurrent_activation, recurrent_activation)
+        self.use_bias, self.unit_forget_bias = use_bias, unit_forget_bias
+        self.kernel_initializer, self.recurrent_initializer = kernel_initializer, recurrent_initializer
+        self.bias_initializer = _get_initializer(bias_initializer)
+        self.kernel_regularizer, self.recurrent_regularizer, self.bias_regularizer = (kernel_regularizer,
+                                                                                      recurrent_regularizer, bias_regularizer)
+        self.kernel_constraint, self.recurrent_constraint, self.bias_constraint = (kernel_constraint, recurrent_constraint,
+                                                                                   bias_constraint)
+        self.dropout, self.recurrent_dropout, self.implementation = dropout, recurrent_dropout, implementation
+        self.state_size = [self.units, self.units]
+
+    def get_dropout_mask_for_cell(self, inputs, training, count=1):
+        return None
+
+    def get_recurrent_dropout_mask_for_cell(self, inputs, training, count=1):
+        return None
+
+    def get_initial_state(self, inputs=None, batch_size=None, dtype=None):
+        if inputs is not None:
+            batch_size = np.shape(inputs)[0]
+        return [zeros([batch_size, self.units]), zeros([batch_size, self.units])]
+
+    def _compute_carry_and_output(self, x, h_tm1, c_tm1):
+        x_i, x_f, x_c, x_o = x
+        h_i, h_f, h_c, h_o = h_tm1
+        u, rk = self.units, _t(self.recurrent_kernel)
+        i = self.recurrent_activation(x_i + matmul(h_i, rk[:, :u]))
+        f = self.recurrent_activation(x_f + matmul(h_f, rk[:, u:2 * u]))
+        c = f * c_tm1 + i * self.activation(x_c + matmul(h_c, rk[:, 2 * u:3 * u]))
+        o = self.recurrent_activation(x_o + matmul(h_o, rk[:, 3 * u:]))
+        return c, o
+
+    def _compute_carry_and_output_fused(self, z, c_tm1):
+        z0, z1, z2, z3 = z
+        i, f = self.recurrent_activation(z0), self.recurrent_activation(z1)
+        c = f * c_tm1 + i * self.activation(z2)
+        return c, self.recurrent_activation(z3)
+
+    def call(self, inputs, states, training=None):
+        h_tm1, c_tm1 = states[0], states[1]
+        if self.implementation == 1:
+            k = split(_t(self.kernel), 4, axis=1)
+            x = [matmul(inputs, ki) for ki in k]
+            if self.use_bias:
+                x = [nn.bias_add(xi, bi) for xi, bi in zip(x, split(_t(self.bias), 4, axis=0))]
+            c, o = self._compute_carry_and_output(tuple(x), (h_tm1,) * 4, c_tm1)
+        else:
+            z = matmul(inputs, self.kernel) + matmul(h_tm1, self.recurrent_kernel)
+            if self.use_bias:
+                z = nn.bias_add(z, self.bias)
+            c, o = self._compute_carry_and_output_fused(split(z, 4, axis=1), c_tm1)
+        h = o * self.activation(c)
+        return h, [h, c]
+
+    def __call__(self, inputs, states, training=None):
+        if not self.built:
+            self.build(_t(inputs).shape)
+            self.built = True
+        return self.call(inputs, states, training)
+
+
+def split(value, num_or_size_splits, axis=0):
+    return [_t(a) for a in np.split(np.asarray(_t(value)), num_or_size_splits, axis=axis)]
+
+
 class Conv1D(Layer):
     pass
 
@@ -585,7 +666,7 @@ class _L2(_Regularizer):
 
 _layers = _module("tensorflow.keras.layers", Layer=Layer, Dense=Dense, LayerNormalization=LayerNormalization,
                   Lambda=Lambda, Wrapper=Wrapper, experimental=types.SimpleNamespace(), Conv2D=Conv2D, Conv1D=Conv1D,
-                  DepthwiseConv2D=DepthwiseConv2D, InputSpec=InputSpec)
+                  DepthwiseConv2D=DepthwiseConv2D, InputSpec=InputSpec, LSTMCell=LSTMCell)
 _initializers = _module("tensorflow.keras.initializers", Initializer=_Initializer, Zeros=_Zeros, Ones=_Ones,
                         TruncatedNormal=_TruncatedNormal, VarianceScaling=_VarianceScaling, Orthogonal=_Orthogonal,
                         get=_get_initializer, he_normal=lambda seed=None: _VarianceScaling(2.0, "fan_in", "truncated_normal"),
@@ -597,7 +678,9 @@ _regularizers = _module("tensorflow.keras.regularizers", Regularizer=_Regularize
 _constraints = _module("tensorflow.keras.constraints", Constraint=_Constraint, get=_get_plain)
 _activations = _module("tensorflow.keras.activations", get=_activation, serialize=lambda a: getattr(a, "__name__", None),
                        relu=nn.relu, linear=lambda x: x)
-_backend = _module("tensorflow.keras.backend", epsilon=lambda: 1e-7, learning_phase=lambda: 0)
+_backend = _module("tensorflow.keras.backend", epsilon=lambda: 1e-7, learning_phase=lambda: 0, dot=matmul,
+                  bias_add=lambda v, b: _t(_t(v) + _t(b)),
+                  concatenate=lambda ts, axis=-1: _t(np.concatenate([np.asarray(_t(a)) for a in ts], axis)))
 _legacy = _module("tensorflow.keras.utils.legacy", serialize_keras_object=_serialize, deserialize_keras_object=_deserialize)
 _utils = _module("tensorflow.keras.utils", legacy=_legacy)
 keras = _module("tensorflow.keras", layers=_layers, initializers=_initializers, regularizers=_regularizers,

@@ -915,3 +915,65 @@ def test_reference_tf_conv2d_variants(ref_tf):
     y, _, _ = oc.rank1_conv2d(r["cr1_x"], r["cr1_kernel"], r["cr1_mu_r"], r["cr1_rho_r"], r["cr1_eps_r"], r["cr1_mu_s"],
                               r["cr1_rho_s"], r["cr1_eps_s"], r["cr1_bias"], "relu", (2, 1), "same")
     _close(y, r["cr1_y"])
+
+
+@pytest.mark.parametrize("tag", ["lrp", "lrp1", "lfo", "lfo1"])
+def test_reference_tf_lstm_cell_reparameterization_and_flipout(ref_tf, tag):
+    """layers/recurrent.py:30-183 (LSTMCellReparameterization) and :185-358 (LSTMCellFlipout) as executed over three steps,
+    both Keras implementations (1: per-gate slices through _compute_carry_and_output; 2: fused): ONE weight sample / sign
+    draw per sequence (get_initial_state), reused by every step."""
+    from oracle import recurrent as orc
+
+    r = ref_tf
+    xs = r[f"{tag}_xs"]
+    T, B, _ = xs.shape
+    H = r[f"{tag}_mu_u"].shape[0]
+    h, c = np.zeros((B, H)), np.zeros((B, H))
+    if tag.startswith("lrp"):
+        W = orc.reparam_kernel(r[f"{tag}_mu_k"], r[f"{tag}_rho_k"], r[f"{tag}_eps_k"])
+        U = orc.reparam_kernel(r[f"{tag}_mu_u"], r[f"{tag}_rho_u"], r[f"{tag}_eps_u"])
+        hs, c_last, _ = orc.lstm_sequence(xs, h, c, W, U, r[f"{tag}_bias"])
+    else:
+        hs = []
+        for t in range(T):
+            z = od.flipout_fwd(xs[t], r[f"{tag}_mu_k"], r[f"{tag}_rho_k"], r[f"{tag}_eps_k"], r[f"{tag}_sign_in"],
+                               r[f"{tag}_sign_out"])[0]
+            z = z + od.flipout_fwd(h, r[f"{tag}_mu_u"], r[f"{tag}_rho_u"], r[f"{tag}_eps_u"], r[f"{tag}_rsign_in"],
+                                   r[f"{tag}_rsign_out"])[0] + r[f"{tag}_bias"]
+            h, c, _ = orc.gates(z, c)
+            hs.append(h)
+        hs, c_last = np.stack(hs), c
+    _close(hs, r[f"{tag}_hs"])
+    _close(c_last, r[f"{tag}_c"])
+    kls = sorted([od.normal_kl(r[f"{tag}_mu_k"], r[f"{tag}_rho_k"]), od.normal_kl(r[f"{tag}_mu_u"], r[f"{tag}_rho_u"])])
+    np.testing.assert_allclose(sorted(r[f"{tag}_kl"]), kls, rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["lr1", "lr1_add"])
+def test_reference_tf_lstm_cell_rank1(ref_tf, tag):
+    """layers/recurrent.py:360-830 (LSTMCellRank1) as executed: per-example fast weights of the input and the recurrent
+    branch drawn once per sequence ([n, E, dim] -> member-major rows, no clipping), multiplicative and additive
+    perturbations, one bias row per member."""
+    from oracle import recurrent as orc
+
+    r = ref_tf
+    xs = r[f"{tag}_xs"]
+    T, B, _ = xs.shape
+    E = r[f"{tag}_bias"].shape[0]
+    n = B // E
+    H = r[f"{tag}_rkernel"].shape[0]
+    f = {name: od.rank1_factors(r[f"{tag}_{name}_mu"], r[f"{tag}_{name}_rho"], r[f"{tag}_{name}_eps"], E, None)[0]
+         for name in ("alpha", "gamma", "recurrent_alpha", "recurrent_gamma")}
+    bias = np.repeat(r[f"{tag}_bias"], n, axis=0)
+    h, c, hs = np.zeros((B, H)), np.zeros((B, H)), []
+    for t in range(T):
+        if tag == "lr1_add":
+            z = (xs[t] + f["alpha"]) @ r[f"{tag}_kernel"] + f["gamma"]
+            z = z + (h + f["recurrent_alpha"]) @ r[f"{tag}_rkernel"] + f["recurrent_gamma"]
+        else:
+            z = ((xs[t] * f["alpha"]) @ r[f"{tag}_kernel"]) * f["gamma"]
+            z = z + ((h * f["recurrent_alpha"]) @ r[f"{tag}_rkernel"]) * f["recurrent_gamma"]
+        h, c, _ = orc.gates(z + bias, c)
+        hs.append(h)
+    _close(np.stack(hs), r[f"{tag}_hs"])
+    _close(c, r[f"{tag}_c"])
