@@ -24,7 +24,9 @@ JAX / Flax, none of which is installed here or on the GPU box.  Its JAX files ar
     `oracle/dense.py` and `oracle/sngp.py` against them at 1e-12 (1e-10 through the matrix inverse).
     `layers/convolutional.py` (Conv2DReparameterization / Flipout / BatchEnsemble / Rank1) and `layers/recurrent.py`
     (LSTMCellReparameterization / Flipout, Keras implementations 1 and 2, and LSTMCellRank1, multiplicative and additive)
-    run the same way and pin `oracle/conv.py` and `oracle/recurrent.py`.
+    run the same way and pin `oracle/conv.py` and `oracle/recurrent.py`; `layers/heteroscedastic.py` (MCSoftmaxDenseFA,
+    MCSigmoidDenseFA: one diagonal draw per class) and `layers/hetsngp.py` (HeteroscedasticSNGPLayer, training and
+    evaluation calls) pin the TF form of `oracle/heteroscedastic.py`.
 For the VALUES of the native samplers (the reference has no RNG-stream contract) what is pinned is:
   * the Philox4x32-10 generator against the three Random123 known-answer vectors (tests/golden/philox_kat.json);
   * `mean_field_logits` against the reference's known-answer tests (edward2/tensorflow/layers/utils_test.py:201-241,

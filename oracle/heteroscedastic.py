@@ -8,9 +8,10 @@ noise samples (batch dimension 1 = share_samples_across_batch).  PINNED to the r
 edward2/jax/nn/heteroscedastic_lib.py (MCSoftmaxDenseFA, :43-336) is executed under the NumPy-backed jax / flax stand-ins
 with its jax.random.normal draws recorded (tests/golden/make_reference_golden.py); tests/test_oracle.py::
 test_reference_mc_softmax_dense_fa checks this restatement against those outputs at 1e-12 and
-tests/test_gpu_reference_golden.py checks the CUDA kernel against them.  (The TF classes cannot run here — TF / TFP are
-not installable; they differ from the JAX class only in drawing the diagonal noise per class instead of per sample, which
-is an input here.)  The closed-form gradient is pinned against float64 autograd in tests/test_oracle.py."""
+tests/test_gpu_reference_golden.py checks the CUDA kernel against them.  The TF classes (one diagonal draw per class) are pinned the same way: layers/heteroscedastic.py
+MCSoftmaxDenseFA / MCSigmoidDenseFA and layers/hetsngp.py HeteroscedasticSNGPLayer run unmodified under the tensorflow / tfp
+stand-ins (tests/golden/make_reference_golden_tf.py; tests/test_oracle.py::test_reference_tf_mc_heads,
+test_reference_tf_heteroscedastic_sngp_layer).  The closed-form gradient is pinned against float64 autograd in tests/test_oracle.py."""
 from __future__ import annotations
 
 import numpy as np

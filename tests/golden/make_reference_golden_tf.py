@@ -54,7 +54,9 @@ def load_reference():
                       ("edward2.tensorflow.layers.normalization", "layers/normalization.py"),
                       ("edward2.tensorflow.layers.random_feature", "layers/random_feature.py"),
                       ("edward2.tensorflow.layers.convolutional", "layers/convolutional.py"),
-                      ("edward2.tensorflow.layers.recurrent", "layers/recurrent.py")):
+                      ("edward2.tensorflow.layers.recurrent", "layers/recurrent.py"),
+                      ("edward2.tensorflow.layers.heteroscedastic", "layers/heteroscedastic.py"),
+                      ("edward2.tensorflow.layers.hetsngp", "layers/hetsngp.py")):
         spec = importlib.util.spec_from_file_location(full, os.path.join(REF, rel))
         m = importlib.util.module_from_spec(spec)
         sys.modules[full] = m
@@ -359,6 +361,76 @@ def main():
                     f"{tag}_bias": np.array(cell.bias), f"{tag}_hs": hs, f"{tag}_c": c_last})
         for (name, (mu, rho)), eps in zip(params.items(), per_example):
             out.update({f"{tag}_{name}_mu": mu, f"{tag}_{name}_rho": rho, f"{tag}_{name}_eps": rows(eps)})
+
+    # ---- §8f-2 heteroscedastic heads, TF classes (layers/heteroscedastic.py:508 MCSoftmaxDenseFA, :1382 MCSigmoidDenseFA;
+    # layers/hetsngp.py:25 HeteroscedasticSNGPLayer): ONE diagonal draw per CLASS (the JAX classes draw one per sample)
+    het, hsn = mods["heteroscedastic"], mods["hetsngp"]
+    Bh, Dh, Kh, Fh, Sh = 6, 7, 5, 3, 24
+
+    def fill_dense(layer_, scale=0.5):
+        layer_.kernel.assign(rng.standard_normal(layer_.kernel.shape) * scale)
+        layer_.bias.assign(rng.standard_normal(layer_.bias.shape) * 0.2)
+
+    def head_params(layer_, tag):
+        for name in ("_loc_layer", "_scale_layer", "_diag_layer"):
+            sub = getattr(layer_, name)
+            out[f"{tag}{name}_kernel"], out[f"{tag}{name}_bias"] = np.array(sub.kernel), np.array(sub.bias)
+
+    def mc_draws():
+        """(diag [B or 1, S, K], factors [B or 1, S, F]) of the last predictive-mean pass, as [rows, S, dim]."""
+        d = [a for a in tfp.recorded if a.ndim == 3]
+        return np.transpose(d[0], (1, 0, 2)), np.transpose(d[1], (1, 0, 2))
+
+    for tag, cls, share in (("hsm", het.MCSoftmaxDenseFA, False), ("hsm_shared", het.MCSoftmaxDenseFA, True),
+                            ("hsg", het.MCSigmoidDenseFA, False)):
+        kw = dict(num_factors=Fh, temperature=0.7, train_mc_samples=Sh, test_mc_samples=Sh, compute_pred_variance=True,
+                  share_samples_across_batch=share)
+        layer = cls(Kh, **kw)
+        x = rng.standard_normal((Bh, Dh))
+        layer(tf._t(x), training=True, seed=1)
+        for name in ("_loc_layer", "_scale_layer", "_diag_layer"):
+            fill_dense(getattr(layer, name))
+        del tfp.recorded[:]
+        logits, log_probs, probs, var = layer(tf._t(x), training=True, seed=11)
+        e, z = mc_draws()
+        # the variance pass re-draws with the same seed: identical samples (TF semantics, see the tfp stand-in)
+        d3 = [a for a in tfp.recorded if a.ndim == 3]
+        assert len(d3) == 4 and np.array_equal(d3[0], d3[2]) and np.array_equal(d3[1], d3[3])
+        head_params(layer, tag)
+        out.update({f"{tag}_x": x, f"{tag}_logits": logits, f"{tag}_log_probs": log_probs, f"{tag}_probs": probs,
+                    f"{tag}_var": var, f"{tag}_diag_noise": e, f"{tag}_factor_noise": z})
+
+    layer = hsn.HeteroscedasticSNGPLayer(Kh, num_factors=Fh, temperature=0.8, train_mc_samples=Sh, test_mc_samples=Sh,
+                                         logits_only=False, num_inducing=16, gp_cov_momentum=-1.0, gp_cov_ridge_penalty=1.0,
+                                         normalize_input=True, sngp_var_weight=1.3, het_var_weight=0.7)
+    x, xt = rng.standard_normal((Bh, Dh)), rng.standard_normal((Bh, Dh))
+    # hetsngp.py:160 calls the SNGP layer without `training`: it follows tf.keras.backend.learning_phase()
+    tf.keras.backend.learning_phase = lambda: 1
+    layer(tf._t(x), training=True, seed=2)  # builds; first exact-sum precision update
+    for name in ("_scale_layer", "_diag_layer"):
+        fill_dense(getattr(layer, name))
+    sn = layer.sngp_layer
+    sn._gp_output_layer.kernel.assign(rng.standard_normal(sn._gp_output_layer.kernel.shape) * 0.5)
+    sn._gp_output_bias.assign(rng.standard_normal(Kh) * 0.2)
+    sn._gp_cov_layer.precision_matrix.assign(np.zeros((16, 16)))
+    del tfp.recorded[:]
+    logits, log_probs, probs, _ = layer(tf._t(x), training=True, seed=12)
+    e, z = mc_draws()
+    out.update(hsn_x=x, hsn_xt=xt, hsn_logits=logits, hsn_log_probs=log_probs, hsn_probs=probs, hsn_diag_noise=e,
+               hsn_factor_noise=z, hsn_precision=np.array(sn._gp_cov_layer.precision_matrix),
+               hsn_rff_kernel=np.array(sn._random_feature.kernel), hsn_rff_bias=np.array(sn._random_feature.bias),
+               hsn_out_kernel=np.array(sn._gp_output_layer.kernel), hsn_out_bias=np.array(sn._gp_output_bias),
+               hsn_ln_gamma=np.array(sn._input_norm_layer.gamma), hsn_ln_beta=np.array(sn._input_norm_layer.beta),
+               hsn_weights=np.array([0.7, 1.3, 0.8]))
+    for name in ("_scale_layer", "_diag_layer"):
+        sub = getattr(layer, name)
+        out[f"hsn{name}_kernel"], out[f"hsn{name}_bias"] = np.array(sub.kernel), np.array(sub.bias)
+    tf.keras.backend.learning_phase = lambda: 0
+    del tfp.recorded[:]
+    logits, log_probs, probs, _ = layer(tf._t(xt), training=False, seed=13)
+    e, z = mc_draws()
+    out.update(hsn_eval_logits=logits, hsn_eval_log_probs=log_probs, hsn_eval_probs=probs, hsn_eval_diag_noise=e,
+               hsn_eval_factor_noise=z, hsn_eval_sigma=np.array(sn._gp_cov_layer.covariance_matrix))
 
     np.savez_compressed(OUT, **{k: np.asarray(a, dtype=np.float64) for k, a in out.items()})
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")

@@ -210,6 +210,22 @@ def name_scope(name):
     yield
 
 
+def einsum(equation, *operands):
+    return _t(np.einsum(equation, *[np.asarray(_t(o)) for o in operands]))
+
+
+def executing_eagerly():
+    return True
+
+
+def zeros_initializer():
+    return _Zeros()
+
+
+def squeeze(x, axis=None):
+    return _t(np.squeeze(_t(x), axis=axis))
+
+
 def _module(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
@@ -224,7 +240,7 @@ def _softplus(x):
 
 
 math = _module("tensorflow.math", log=lambda x: _t(np.log(_t(x))), reduce_mean=reduce_mean, softplus=_softplus,
-               cos=lambda x: _t(np.cos(_t(x))))
+               cos=lambda x: _t(np.cos(_t(x))), sigmoid=lambda x: sigmoid(x), exp=lambda x: exp(x))
 nn = _module("tensorflow.nn", relu=lambda x: _t(np.maximum(_t(x), 0.0)), softplus=_softplus,
              bias_add=lambda v, b, data_format=None: _t(_t(v) + _t(b)),
              softmax=lambda x, axis=-1: _t(np.exp(_t(x) - np.max(_t(x), axis, keepdims=True))
@@ -246,7 +262,9 @@ def _normal(shape, mean=0.0, stddev=1.0, dtype=float32, seed=None):
     return _t(mean + stddev * random._rng.standard_normal(shp))
 
 
-random = _module("tensorflow.random", uniform=_uniform, normal=_normal, _rng=np.random.default_rng(0))
+random = _module("tensorflow.random", uniform=_uniform, normal=_normal, _rng=np.random.default_rng(0),
+                 set_seed=lambda seed: None)
+dtypes = _module("tensorflow.dtypes", DType=DType)
 
 
 # ---- tf.keras
@@ -664,7 +682,11 @@ class _L2(_Regularizer):
         return self.l2 * np.sum(np.square(_t(w)))
 
 
-_layers = _module("tensorflow.keras.layers", Layer=Layer, Dense=Dense, LayerNormalization=LayerNormalization,
+def _layer_serialize(layer):
+    return {"class_name": type(layer).__name__}
+
+
+_layers = _module("tensorflow.keras.layers", serialize=_layer_serialize, Layer=Layer, Dense=Dense, LayerNormalization=LayerNormalization,
                   Lambda=Lambda, Wrapper=Wrapper, experimental=types.SimpleNamespace(), Conv2D=Conv2D, Conv1D=Conv1D,
                   DepthwiseConv2D=DepthwiseConv2D, InputSpec=InputSpec, LSTMCell=LSTMCell)
 _initializers = _module("tensorflow.keras.initializers", Initializer=_Initializer, Zeros=_Zeros, Ones=_Ones,

@@ -31,7 +31,11 @@ class Normal(Distribution):
 
     def sample(self, sample_shape=(), seed=None):
         lead = tuple(np.atleast_1d(np.asarray(sample_shape, dtype=np.int64)).tolist())
-        eps = tf.random._rng.standard_normal(lead + tuple(self.batch_shape))
+        shape = lead + tuple(self.batch_shape)
+        # TensorFlow: the same (global seed, op seed) pair reproduces the same values — the reference relies on it to
+        # evaluate the predictive variance on the samples of the predictive mean (heteroscedastic.py:159-160, 228-253)
+        rng = tf.random._rng if seed is None else np.random.default_rng([int(seed)] + [int(d) for d in shape])
+        eps = rng.standard_normal(shape)
         recorded.append(eps)
         return tf._t(self.loc + self.scale * eps)
 
@@ -73,5 +77,14 @@ class Independent(Distribution):
 
 recorded = []  # standard-normal draws of every Normal.sample call, in call order (read by the fixture generator)
 distributions = types.ModuleType("tensorflow_probability.distributions")
-distributions.__dict__.update(Distribution=Distribution, Normal=Normal, Independent=Independent)
+class Logistic(Distribution):   # named as default arguments by heteroscedastic.py; not sampled by the fixtures
+    pass
+
+
+class Gumbel(Distribution):
+    pass
+
+
+distributions.__dict__.update(Distribution=Distribution, Normal=Normal, Independent=Independent, Logistic=Logistic,
+                              Gumbel=Gumbel)
 sys.modules["tensorflow_probability.distributions"] = distributions

@@ -977,3 +977,66 @@ def test_reference_tf_lstm_cell_rank1(ref_tf, tag):
         hs.append(h)
     _close(np.stack(hs), r[f"{tag}_hs"])
     _close(c, r[f"{tag}_c"])
+
+
+@pytest.mark.parametrize("tag", ["hsm", "hsm_shared", "hsg"])
+def test_reference_tf_mc_heads(ref_tf, tag):
+    """layers/heteroscedastic.py as executed: MCSoftmaxDenseFA (:508; per-example and shared noise) and MCSigmoidDenseFA
+    (:1382) — Dense parameter layers, softplus + 1e-3 diagonal, ONE diagonal draw per class, einsum factor noise,
+    temperature, clips; the predictive variance is evaluated on the samples of the predictive mean."""
+    from oracle import heteroscedastic as oh
+
+    r = ref_tf
+    x = r[f"{tag}_x"]
+    lin = lambda n: x @ r[f"{tag}_{n}_kernel"] + r[f"{tag}_{n}_bias"]  # noqa: E731
+    loc, fac, draw = lin("loc_layer"), lin("scale_layer"), lin("diag_layer")
+    z, e = r[f"{tag}_factor_noise"], r[f"{tag}_diag_noise"]
+    assert e.shape[0] == (1 if tag == "hsm_shared" else x.shape[0]) and e.shape[2] == loc.shape[1]
+    if tag == "hsg":
+        logits, log_probs, probs = oh.mc_sigmoid_fa(loc, fac, draw, z, e, 0.7, 1e-7)
+        _close(np.clip(probs, 1e-7, 1 - 1e-7), r[f"{tag}_probs"])
+    else:
+        logits, probs, var = oh.mc_softmax_fa(loc, fac, draw, z, e, 0.7, 1e-7)
+        log_probs = logits
+        _close(probs, r[f"{tag}_probs"])
+        _close(var, r[f"{tag}_var"])
+    _close(log_probs, r[f"{tag}_log_probs"])
+    _close(logits, r[f"{tag}_logits"])
+
+
+def test_reference_tf_heteroscedastic_sngp_layer(ref_tf):
+    """layers/hetsngp.py:25-245 as executed: location = RandomFeatureGaussianProcess logits, a training call (exact-sum
+    precision update, plain diagonal scale) and an evaluation call whose diagonal scale is
+    sqrt(het_var_weight diag^2 + sngp_var_weight diag(cov))."""
+    from oracle import heteroscedastic as oh
+
+    r = ref_tf
+    w_het, w_sngp, T = r["hsn_weights"]
+    D = r["hsn_rff_kernel"].shape[1]
+
+    def gp(x):
+        xn = og.layer_norm(x, r["hsn_ln_gamma"], r["hsn_ln_beta"], 1e-3)
+        phi, _ = og.rff(xn, r["hsn_rff_kernel"], r["hsn_rff_bias"], np.sqrt(2.0 / D))
+        return phi, og.gp_output(phi, r["hsn_out_kernel"], r["hsn_out_bias"])
+
+    def scale(x):
+        return (x @ r["hsn_scale_layer_kernel"] + r["hsn_scale_layer_bias"],
+                x @ r["hsn_diag_layer_kernel"] + r["hsn_diag_layer_bias"])
+
+    x, xt = r["hsn_x"], r["hsn_xt"]
+    phi, loc = gp(x)
+    fac, draw = scale(x)
+    logits, probs, _ = oh.mc_softmax_fa(loc, fac, draw, r["hsn_factor_noise"], r["hsn_diag_noise"], T, 1e-7)
+    _close(probs, r["hsn_probs"])
+    _close(logits, r["hsn_logits"])
+    precision = og.precision_update_tf(np.zeros((D, D)), phi, -1.0)
+    _close(precision, r["hsn_precision"])
+    sigma = og.covariance_tf(precision, 1.0)
+    _close(sigma, r["hsn_eval_sigma"], 1e-10)
+    phit, loct = gp(xt)
+    var = np.diag(og.predictive_covariance_tf(phit, sigma, 1.0))
+    fac, draw = scale(xt)
+    logits, probs, _ = oh.mc_softmax_fa(loct, fac, draw, r["hsn_eval_factor_noise"], r["hsn_eval_diag_noise"], T, 1e-7,
+                                        sngp_var=var, w_het=w_het, w_sngp=w_sngp)
+    _close(probs, r["hsn_eval_probs"], 1e-10)
+    _close(logits, r["hsn_eval_logits"], 1e-10)
