@@ -1,5 +1,6 @@
-// TensorFlow custom-op shim for libed2b200: forward AND backward ops of the four dense layers plus the SNGP-head
-// operators, each a thin OpKernel that fills the argument struct of include/ed2b200.h from its inputs / outputs and
+// TensorFlow custom-op shim for libed2b200: forward AND backward ops of the four dense layers, the KL regulariser, the
+// factorised Conv2D variants, the LSTM gate kernels, the Monte-Carlo heads and the SNGP-head operators (incl. the
+// covariance inverse), each a thin OpKernel that fills the argument struct of include/ed2b200.h from its inputs / outputs and
 // calls the C entry point on TensorFlow's GPU stream.  The Python side (tf.load_op_library + tf.custom_gradient) is in
 // INTEGRATION.md §3.
 //
@@ -493,6 +494,235 @@ class Ed2PredictiveVarianceOp : public OpKernel {
   float ridge_, mff_; int lik_;
 };
 ED2_REGISTER("Ed2PredictiveVariance", Ed2PredictiveVarianceOp);
+
+// ================================================================================================ NormalKLDivergence
+// scale_factor * KL(N(mu, softplus(rho) + 1e-7) || N(prior_mean, prior_std)) — edward2/tensorflow/regularizers.py:166-186
+REGISTER_OP("Ed2NormalKlFwd").Input("mu: float").Input("rho: float").Output("kl: double")
+    .Attr("prior_mean: float = 0.0").Attr("prior_std: float = 1.0").Attr("scale: float = 1.0");
+class Ed2NormalKlFwdOp : public OpKernel {
+ public:
+  explicit Ed2NormalKlFwdOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("prior_mean", &m_)); OP_REQUIRES_OK(c, c->GetAttr("prior_std", &s_));
+    OP_REQUIRES_OK(c, c->GetAttr("scale", &scale_));
+  }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &mu = c->input(0), &rho = c->input(1);
+    ED2_OUT(0, TensorShape({}), kl);
+    auto stream = c->eigen_gpu_device().stream();
+    cudaMemsetAsync(kl->data(), 0, sizeof(double), stream);
+    ED2_CALL(ed2_normal_kl_fwd(F(mu), F(rho), mu.NumElements(), m_, s_, scale_, static_cast<double*>(kl->data()), stream));
+  }
+ private:
+  float m_, s_, scale_;
+};
+REGISTER_KERNEL_BUILDER(Name("Ed2NormalKlFwd").Device(DEVICE_GPU), Ed2NormalKlFwdOp);
+
+REGISTER_OP("Ed2NormalKlBwd").Input("mu: float").Input("rho: float").Input("upstream: float")
+    .Output("dmu: float").Output("drho: float")
+    .Attr("prior_mean: float = 0.0").Attr("prior_std: float = 1.0").Attr("scale: float = 1.0");
+class Ed2NormalKlBwdOp : public OpKernel {
+ public:
+  explicit Ed2NormalKlBwdOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("prior_mean", &m_)); OP_REQUIRES_OK(c, c->GetAttr("prior_std", &s_));
+    OP_REQUIRES_OK(c, c->GetAttr("scale", &scale_));
+  }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &mu = c->input(0), &rho = c->input(1), &up = c->input(2);
+    ED2_OUT(0, mu.shape(), dmu); ED2_OUT(1, mu.shape(), drho);
+    auto stream = c->eigen_gpu_device().stream();
+    const size_t bytes = sizeof(float) * static_cast<size_t>(mu.NumElements());
+    cudaMemsetAsync(F(dmu), 0, bytes, stream); cudaMemsetAsync(F(drho), 0, bytes, stream);  // the kernel accumulates
+    ED2_CALL(ed2_normal_kl_bwd(F(mu), F(rho), mu.NumElements(), m_, s_, scale_, F(up), F(dmu), F(drho), stream));
+  }
+ private:
+  float m_, s_, scale_;
+};
+REGISTER_KERNEL_BUILDER(Name("Ed2NormalKlBwd").Device(DEVICE_GPU), Ed2NormalKlBwdOp);
+
+// ================================================================================================ Conv2D (factorised)
+// Conv2DBatchEnsemble / Conv2DRank1 — edward2/tensorflow/layers/convolutional.py:681-699, 1968-2020: the per-example
+// channel factors f_in / f_out / bias are [B][C] tables (ed2_expand_table / ed2_rank1_factors build them)
+#define ED2_CONV_ATTRS \
+  .Attr("kh: int = 3").Attr("kw: int = 3").Attr("sh: int = 1").Attr("sw: int = 1").Attr("same: int = 1").Attr("act: int = 0")
+struct ConvAttrs {
+  int kh, kw, sh, sw, same, act;
+  void Read(OpKernelConstruction* c) {
+    OP_REQUIRES_OK(c, c->GetAttr("kh", &kh)); OP_REQUIRES_OK(c, c->GetAttr("kw", &kw));
+    OP_REQUIRES_OK(c, c->GetAttr("sh", &sh)); OP_REQUIRES_OK(c, c->GetAttr("sw", &sw));
+    OP_REQUIRES_OK(c, c->GetAttr("same", &same)); OP_REQUIRES_OK(c, c->GetAttr("act", &act));
+  }
+  ed2_conv_geometry Geometry(const Tensor& x) const {  // x is NHWC
+    ed2_conv_geometry g{};
+    g.batch = D(x, 0); g.height = D(x, 1); g.width = D(x, 2); g.channels = D(x, 3);
+    g.kh = kh; g.kw = kw; g.sh = sh; g.sw = sw; g.same = same;
+    return g;
+  }
+};
+REGISTER_OP("Ed2ConvFactorFwd")
+    .Input("x: T").Input("w: T").Input("f_in: float").Input("f_out: float").Input("bias: float")
+    .Output("y: T").Output("xa: T").Output("z: T").Attr("T: {float, bfloat16}") ED2_CONV_ATTRS;
+template <typename T>
+class Ed2ConvFactorFwdOp : public OpKernel {
+ public:
+  explicit Ed2ConvFactorFwdOp(OpKernelConstruction* c) : OpKernel(c) { at_.Read(c); }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &x = c->input(0), &w = c->input(1), &f_in = c->input(2), &f_out = c->input(3), &bias = c->input(4);
+    ed2_conv_factor_fwd_args a{};
+    a.geom = at_.Geometry(x);
+    int ho = 0, wo = 0;
+    ED2_CALL(ed2_conv_out_size(&a.geom, &ho, &wo));
+    const int rows = a.geom.batch * ho * wo, K = at_.kh * at_.kw * a.geom.channels, O = D(w, 1);
+    ED2_OUT(0, TensorShape({a.geom.batch, ho, wo, O}), y); ED2_OUT(1, TensorShape({rows, K}), xa);
+    ED2_OUT(2, TensorShape({rows, O}), z);
+    a.dtype = Dt<T>(); a.out_channels = O; a.act = at_.act;
+    a.x = x.data(); a.w_lp = w.data(); a.w_ld = O;
+    a.f_in = F(f_in); a.f_out = F(f_out); a.bias = F(bias);
+    a.xa = xa->data(); a.xa_ld = K; a.y = y->data(); a.y_ld = O; a.z = z->data(); a.z_ld = O;
+    ED2_CALL(ed2_conv_factor_fwd(&a, c->eigen_gpu_device().stream()));
+  }
+ private:
+  ConvAttrs at_;
+};
+ED2_REGISTER("Ed2ConvFactorFwd", Ed2ConvFactorFwdOp);
+
+REGISTER_OP("Ed2ConvFactorBwd")
+    .Input("gy: T").Input("y: T").Input("z: T").Input("x: T").Input("xa: T").Input("w: T").Input("f_in: float").Input("f_out: float")
+    .Output("dx: T").Output("dw: float").Output("df_in: float").Output("df_out: float").Output("dbias: float")
+    .Attr("T: {float, bfloat16}") ED2_CONV_ATTRS;
+template <typename T>
+class Ed2ConvFactorBwdOp : public OpKernel {
+ public:
+  explicit Ed2ConvFactorBwdOp(OpKernelConstruction* c) : OpKernel(c) { at_.Read(c); }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &gy = c->input(0), &y = c->input(1), &z = c->input(2), &x = c->input(3), &xa = c->input(4), &w = c->input(5),
+                 &f_in = c->input(6), &f_out = c->input(7);
+    ed2_conv_factor_bwd_args a{};
+    a.geom = at_.Geometry(x);
+    const int rows = D(xa, 0), K = D(xa, 1), O = D(w, 1), B = a.geom.batch, C = a.geom.channels;
+    ED2_OUT(0, x.shape(), dx); ED2_OUT(1, TensorShape({K, O}), dw); ED2_OUT(2, TensorShape({B, C}), df_in);
+    ED2_OUT(3, TensorShape({B, O}), df_out); ED2_OUT(4, TensorShape({B, O}), dbias);
+    ED2_TMP(TensorShape({rows, O}), dz); ED2_TMP(TensorShape({rows, K}), dxa); ED2_TMP(x.shape(), gimg);
+    a.dtype = Dt<T>(); a.out_channels = O; a.act = at_.act;
+    a.gy = gy.data(); a.gy_ld = O; a.y = y.data(); a.y_ld = O; a.z = z.data(); a.z_ld = O;
+    a.x = x.data(); a.xa = xa.data(); a.xa_ld = K; a.w_lp = w.data(); a.w_ld = O;
+    a.f_in = F(f_in); a.f_out = F(f_out);
+    a.dz = dz.data(); a.dz_ld = O; a.dxa = dxa.data(); a.dxa_ld = K; a.gimg = gimg.data();
+    a.dx = dx->data(); a.dw = F(dw); a.df_in = F(df_in); a.df_out = F(df_out); a.dbias = F(dbias);
+    ED2_CALL(ed2_conv_factor_bwd(&a, c->eigen_gpu_device().stream()));
+  }
+ private:
+  ConvAttrs at_;
+};
+ED2_REGISTER("Ed2ConvFactorBwd", Ed2ConvFactorBwdOp);
+
+// ================================================================================================ LSTM cells
+// Gate arithmetic of one step — edward2/tensorflow/layers/recurrent.py:163-183 (LSTMCellReparameterization: z = x W + h U + b
+// from two GEMMs), :243-269 / :330-356 (LSTMCellFlipout) and :616-640 / :747-760 (LSTMCellRank1): the input and the
+// recurrent branch arrive as two pre-activation tensors z + z2.  c fp32; gate order i | f | c | o.
+REGISTER_OP("Ed2LstmGatesFwd").Input("z: T").Input("z2: T").Input("c_prev: float").Output("h: T").Output("c: float")
+    .Attr("T: {float, bfloat16}");
+template <typename T>
+class Ed2LstmGatesFwdOp : public OpKernel {
+ public:
+  explicit Ed2LstmGatesFwdOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    const Tensor &z = c->input(0), &z2 = c->input(1), &c_prev = c->input(2);
+    const int B = D(c_prev, 0), H = D(c_prev, 1);
+    ED2_OUT(0, TensorShape({B, H}), h); ED2_OUT(1, TensorShape({B, H}), cn);
+    ED2_CALL(ed2_lstm_gates_fwd(z.data(), z2.data(), Dt<T>(), 4 * H, 4 * H, F(c_prev), B, H, F(cn), h->data(), H,
+                                c->eigen_gpu_device().stream()));
+  }
+};
+ED2_REGISTER("Ed2LstmGatesFwd", Ed2LstmGatesFwdOp);
+
+REGISTER_OP("Ed2LstmGatesBwd").Input("z: T").Input("z2: T").Input("c_prev: float").Input("c: float").Input("dh: T").Input("dc: float")
+    .Output("dz: T").Output("dc_prev: float").Attr("T: {float, bfloat16}");
+template <typename T>
+class Ed2LstmGatesBwdOp : public OpKernel {
+ public:
+  explicit Ed2LstmGatesBwdOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    const Tensor &z = c->input(0), &z2 = c->input(1), &c_prev = c->input(2), &cn = c->input(3), &dh = c->input(4), &dc = c->input(5);
+    const int B = D(c_prev, 0), H = D(c_prev, 1);
+    ED2_OUT(0, TensorShape({B, 4 * H}), dz); ED2_OUT(1, TensorShape({B, H}), dc_prev);
+    ED2_CALL(ed2_lstm_gates_bwd(z.data(), z2.data(), Dt<T>(), 4 * H, 4 * H, F(c_prev), F(cn), dh.data(), H, F(dc), B, H,
+                                dz->data(), 4 * H, F(dc_prev), c->eigen_gpu_device().stream()));
+  }
+};
+ED2_REGISTER("Ed2LstmGatesBwd", Ed2LstmGatesBwdOp);
+
+// the single-tensor form (LSTMCellReparameterization: z already holds x W + h U + b); the backward also reduces dbias
+REGISTER_OP("Ed2LstmPointwiseFwd").Input("z: T").Input("c_prev: float").Output("h: T").Output("c: float")
+    .Attr("T: {float, bfloat16}");
+template <typename T>
+class Ed2LstmPointwiseFwdOp : public OpKernel {
+ public:
+  explicit Ed2LstmPointwiseFwdOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    const Tensor &z = c->input(0), &c_prev = c->input(1);
+    const int B = D(c_prev, 0), H = D(c_prev, 1);
+    ED2_OUT(0, TensorShape({B, H}), h); ED2_OUT(1, TensorShape({B, H}), cn);
+    ED2_CALL(ed2_lstm_pointwise_fwd(z.data(), Dt<T>(), 4 * H, F(c_prev), B, H, F(cn), h->data(), H,
+                                    c->eigen_gpu_device().stream()));
+  }
+};
+ED2_REGISTER("Ed2LstmPointwiseFwd", Ed2LstmPointwiseFwdOp);
+
+REGISTER_OP("Ed2LstmPointwiseBwd").Input("z: T").Input("c_prev: float").Input("c: float").Input("dh: T").Input("dc: float")
+    .Output("dz: T").Output("dc_prev: float").Output("dbias: float").Attr("T: {float, bfloat16}");
+template <typename T>
+class Ed2LstmPointwiseBwdOp : public OpKernel {
+ public:
+  explicit Ed2LstmPointwiseBwdOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    const Tensor &z = c->input(0), &c_prev = c->input(1), &cn = c->input(2), &dh = c->input(3), &dc = c->input(4);
+    const int B = D(c_prev, 0), H = D(c_prev, 1);
+    ED2_OUT(0, TensorShape({B, 4 * H}), dz); ED2_OUT(1, TensorShape({B, H}), dc_prev); ED2_OUT(2, TensorShape({4 * H}), dbias);
+    ED2_CALL(ed2_lstm_pointwise_bwd(z.data(), Dt<T>(), 4 * H, F(c_prev), F(cn), dh.data(), H, F(dc), B, H, dz->data(), 4 * H,
+                                    F(dc_prev), F(dbias), c->eigen_gpu_device().stream()));
+  }
+};
+ED2_REGISTER("Ed2LstmPointwiseBwd", Ed2LstmPointwiseBwdOp);
+
+// ================================================================================================ SNGP head (continued)
+// d phi / d x of the random-feature layer — random_feature.py:258-266 (+ autodiff); w [d][D]
+REGISTER_OP("Ed2RffBwd").Input("dphi: T").Input("pre: float").Input("bias: float").Input("w: T").Output("dx: T")
+    .Attr("T: {float, bfloat16}").Attr("scale: float = 1.0");
+template <typename T>
+class Ed2RffBwdOp : public OpKernel {
+ public:
+  explicit Ed2RffBwdOp(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("scale", &scale_)); }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &dphi = c->input(0), &pre = c->input(1), &bias = c->input(2), &w = c->input(3);
+    const int B = D(dphi, 0), Dn = D(dphi, 1), d = D(w, 0);
+    ED2_OUT(0, TensorShape({B, d}), dx);
+    ED2_TMP(TensorShape({B, Dn}), gpre);
+    ED2_CALL(ed2_rff_bwd(Dt<T>(), dphi.data(), Dn, Dt<T>(), F(pre), Dn, /*pre_mode=*/0, F(bias), w.data(), Dn, scale_, B, d, Dn,
+                         gpre.data(), Dn, dx->data(), d, Dt<T>(), c->eigen_gpu_device().stream()));
+  }
+ private:
+  float scale_;
+};
+ED2_REGISTER("Ed2RffBwd", Ed2RffBwdOp);
+
+// mean-field adjusted logits from the [B] predictive variances — edward2/tensorflow/layers/utils.py:379-424
+REGISTER_OP("Ed2MeanFieldLogits").Input("logits: float").Input("var: float").Output("adjusted: float")
+    .Attr("mean_field_factor: float = 1.0").Attr("likelihood: int = 0");
+class Ed2MeanFieldLogitsOp : public OpKernel {
+ public:
+  explicit Ed2MeanFieldLogitsOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("mean_field_factor", &mff_)); OP_REQUIRES_OK(c, c->GetAttr("likelihood", &lik_));
+  }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &logits = c->input(0), &var = c->input(1);
+    const int B = D(logits, 0), K = D(logits, 1);
+    ED2_OUT(0, TensorShape({B, K}), adj);
+    ED2_CALL(ed2_mean_field_logits(F(logits), F(var), B, K, mff_, lik_, F(adj), c->eigen_gpu_device().stream()));
+  }
+ private:
+  float mff_; int lik_;
+};
+REGISTER_KERNEL_BUILDER(Name("Ed2MeanFieldLogits").Device(DEVICE_GPU), Ed2MeanFieldLogitsOp);
 
 // covariance = inv(ridge I + precision) — random_feature.py:447-459 (tf.linalg.inv), as the library's block Gauss-Jordan
 REGISTER_OP("Ed2SpdInverse").Input("a: float").Output("inverse: float").Output("status: int32");
