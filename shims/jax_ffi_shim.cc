@@ -323,6 +323,18 @@ ffi::Error RffBwd(cudaStream_t s, Any dphi, F32B pre, F32B bias, Any w /* [d][D]
                           bias.typed_data(), w.untyped_data(), D, scale, B, d, D, gpre_ws->untyped_data(), D,
                           dx->untyped_data(), d, dt_of(*dx), s));
 }
+// LayerNorm over the last axis (flax nn.LayerNorm(use_bias=False, use_scale=False), epsilon 1e-6:
+// edward2/jax/nn/random_feature.py:98-102) and its backward (the reference relies on autodiff)
+ffi::Error LayerNormFwd(cudaStream_t s, Any x, float epsilon, Out<Any> y) {
+  const int cols = dim(x, 1);
+  return done(ed2_input_normalize(x.untyped_data(), dt_of(x), cols, y->untyped_data(), dt_of(*y), cols, dim(x, 0), cols, nullptr,
+                                  nullptr, epsilon, /*scale_only=*/0, 1.f, s));
+}
+ffi::Error LayerNormBwd(cudaStream_t s, Any x, Any dy, float epsilon, Out<Any> dx) {
+  const int cols = dim(x, 1);
+  return done(ed2_layernorm_bwd(x.untyped_data(), dt_of(x), cols, dy.untyped_data(), dt_of(dy), cols, dim(x, 0), cols, nullptr,
+                                epsilon, dx->untyped_data(), dt_of(*dx), cols, nullptr, nullptr, s));
+}
 // precision <- momentum * precision + (1 - momentum) * phi^T phi / batch_total, or precision + phi^T phi
 // (jax/nn/random_feature.py:350-362); `precision` is updated IN PLACE (input_output_aliases={1: 0} on the Python side)
 ffi::Error LaplacePrecisionUpdate(cudaStream_t s, Any phi, F32B precision_in, float momentum, int64_t batch_total,
@@ -432,6 +444,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2RffFwd, RffFwd,
     ED2_STREAM.Arg<Any>().Arg<Any>().Arg<F32B>().Attr<float>("scale").Ret<Any>().Ret<F32B>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2RffBwd, RffBwd,
     ED2_STREAM.Arg<Any>().Arg<F32B>().Arg<F32B>().Arg<Any>().Attr<float>("scale").Ret<Any>().Ret<Any>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2LayerNormFwd, LayerNormFwd, ED2_STREAM.Arg<Any>().Attr<float>("epsilon").Ret<Any>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2LayerNormBwd, LayerNormBwd, ED2_STREAM.Arg<Any>().Arg<Any>().Attr<float>("epsilon").Ret<Any>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2LaplacePrecisionUpdate, LaplacePrecisionUpdate,
     ED2_STREAM.Arg<Any>().Arg<F32B>().Attr<float>("momentum").Attr<int64_t>("batch_total").Ret<F32B>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(Ed2PredictiveVariance, PredictiveVariance,

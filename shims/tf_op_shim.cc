@@ -705,6 +705,43 @@ class Ed2RffBwdOp : public OpKernel {
 };
 ED2_REGISTER("Ed2RffBwd", Ed2RffBwdOp);
 
+// tf.keras.layers.LayerNormalization in front of the random features (random_feature.py:167-171, 252) and its backward
+REGISTER_OP("Ed2LayerNormFwd").Input("x: T").Input("gamma: float").Input("beta: float").Output("y: T")
+    .Attr("T: {float, bfloat16}").Attr("epsilon: float = 1e-3");
+template <typename T>
+class Ed2LayerNormFwdOp : public OpKernel {
+ public:
+  explicit Ed2LayerNormFwdOp(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_)); }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &x = c->input(0), &gamma = c->input(1), &beta = c->input(2);
+    const int B = D(x, 0), d = D(x, 1);
+    ED2_OUT(0, TensorShape({B, d}), y);
+    ED2_CALL(ed2_input_normalize(x.data(), Dt<T>(), d, y->data(), Dt<T>(), d, B, d, F(gamma), F(beta), eps_, /*scale_only=*/0,
+                                 1.f, c->eigen_gpu_device().stream()));
+  }
+ private:
+  float eps_;
+};
+ED2_REGISTER("Ed2LayerNormFwd", Ed2LayerNormFwdOp);
+
+REGISTER_OP("Ed2LayerNormBwd").Input("x: T").Input("dy: T").Input("gamma: float")
+    .Output("dx: T").Output("dgamma: float").Output("dbeta: float").Attr("T: {float, bfloat16}").Attr("epsilon: float = 1e-3");
+template <typename T>
+class Ed2LayerNormBwdOp : public OpKernel {
+ public:
+  explicit Ed2LayerNormBwdOp(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_)); }
+  void Compute(OpKernelContext* c) override {
+    const Tensor &x = c->input(0), &dy = c->input(1), &gamma = c->input(2);
+    const int B = D(x, 0), d = D(x, 1);
+    ED2_OUT(0, TensorShape({B, d}), dx); ED2_OUT(1, TensorShape({d}), dgamma); ED2_OUT(2, TensorShape({d}), dbeta);
+    ED2_CALL(ed2_layernorm_bwd(x.data(), Dt<T>(), d, dy.data(), Dt<T>(), d, B, d, F(gamma), eps_, dx->data(), Dt<T>(), d,
+                               F(dgamma), F(dbeta), c->eigen_gpu_device().stream()));
+  }
+ private:
+  float eps_;
+};
+ED2_REGISTER("Ed2LayerNormBwd", Ed2LayerNormBwdOp);
+
 // mean-field adjusted logits from the [B] predictive variances — edward2/tensorflow/layers/utils.py:379-424
 REGISTER_OP("Ed2MeanFieldLogits").Input("logits: float").Input("var: float").Output("adjusted: float")
     .Attr("mean_field_factor: float = 1.0").Attr("likelihood: int = 0");

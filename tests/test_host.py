@@ -185,7 +185,7 @@ def test_shims_type_check(shim):
                   "ed2_spd_inverse"):
         assert entry + "(" in src, f"{shim} does not bind {entry}"
     for entry in ("ed2_conv_factor_fwd", "ed2_conv_factor_bwd", "ed2_normal_kl_fwd", "ed2_normal_kl_bwd", "ed2_rff_bwd",
-                  "ed2_mean_field_logits"):
+                  "ed2_mean_field_logits", "ed2_input_normalize", "ed2_layernorm_bwd"):
         assert entry + "(" in src, f"{shim} does not bind {entry}"
     if shim == "tf_op_shim.cc":  # the LSTM cells exist only in the reference's TensorFlow backend
         for entry in ("ed2_lstm_gates_fwd", "ed2_lstm_gates_bwd", "ed2_lstm_pointwise_fwd", "ed2_lstm_pointwise_bwd"):
